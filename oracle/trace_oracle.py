@@ -1,0 +1,191 @@
+"""CPU oracle for the sequential skew-ray trace and the spot/RMS reduction.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``torchoptics_b200/`` may import this
+module: only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` use it, and only as the checker (or as
+the CPU arm that is timed *beside* the CUDA path, never instead of it).
+
+It restates, in plain eager PyTorch on whatever dtype the inputs carry (fp32
+for parity, fp64 for the "distance to truth" reports), the algorithm of the
+reference tracer ``/root/reference/torchlens/ray_tracing_lite.py``:
+
+* ``trace``              <- ``trace_skew``                         rtl:594-675
+* ``_march_to_sphere``   <- ``find_marching_distance_spherical``   rtl:525-545
+* ``_advance``           <- ``update_ray_coordinates``             rtl:514-522
+* ``_refract``           <- ``apply_snell_spherical``              rtl:548-571
+* ``_park_failed``       <- ``reset_bad_rays``                     rtl:574-591
+* ``spot_rms``           <- ``compute_rms2d``                      rtl:678-702
+
+Every arithmetic statement keeps the reference's operand order and grouping,
+because the CUDA kernels' "exact" arithmetic policy reproduces exactly this
+sequence of individually rounded IEEE-754 operations and is tested for
+*bit-identical* outputs against this file.  Do not "simplify" expressions here.
+
+Pinning: the reference ships no tests or golden vectors, so
+the pins are outputs of the unmodified reference itself, generated in the build
+container by ``tests/golden/make_golden.py`` and committed under
+``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` holds this oracle to
+them bit-for-bit (masks, points, cosines) and to 1e-6 on gradients.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Tuple
+
+import torch
+
+# rtl:530 and rtl:552 -- the reference uses the same guard for "missed the
+# sphere", "total internal reflection" and "direction lost normalisation".
+GUARD = 1e-6
+
+
+def _march_to_sphere(curv, px, py, pz, dx, dy, dz):
+    """rtl:525-545.  Closed-form distance along (dx,dy,dz) from (px,py,pz) to the
+    vertex-centred sphere of curvature ``curv`` (works for curv == 0)."""
+    along = -(px * dx + py * dy + pz * dz)                       # rtl:531
+    closest_z = pz + along * dz                                  # rtl:532
+    perp2 = px ** 2 + py ** 2 + pz ** 2 - along ** 2             # rtl:533
+    aux = curv * perp2 - 2 * closest_z                           # rtl:534
+    cos2_inc = dz ** 2 - curv * aux                              # rtl:535
+    missed = cos2_inc - GUARD < 0                                # rtl:540
+    cos_inc = torch.sqrt(torch.where(~missed, cos2_inc, 1))      # rtl:541
+    dist = along + aux / (dz + cos_inc)                          # rtl:543
+    return missed, dist, cos_inc, cos2_inc
+
+
+def _advance(px, py, pz, dx, dy, dz, dist):
+    """rtl:514-522.  Move the point; also hand back the z travel."""
+    dz_travel = dist * dz
+    px = px + dist * dx
+    py = py + dist * dy
+    pz = pz + dz_travel
+    return px, py, pz, dz_travel
+
+
+def _refract(curv, ratio, px, py, dx, dy, cos_inc):
+    """rtl:548-571.  Scalar-g spherical Snell; ``ratio`` = n / n'."""
+    cos2_out = 1 - ratio ** 2 * (1 - cos_inc ** 2)               # rtl:553
+    lost = cos2_out - GUARD < 0                                  # rtl:558 (TIR)
+    cos_out = torch.sqrt(torch.where(~lost, cos2_out, 1))        # rtl:559
+    g = cos_out - ratio * cos_inc                                # rtl:560
+    dx = ratio * dx - g * curv * px                              # rtl:563
+    dy = ratio * dy - g * curv * py                              # rtl:564
+    dz2 = 1 - (dx ** 2 + dy ** 2)                                # rtl:566
+    lost = lost | (dz2 - GUARD < 0)                              # rtl:567
+    dz = torch.sqrt(torch.where(~lost, dz2, 1))                  # rtl:568
+    return lost, dx, dy, dz, cos2_out
+
+
+def _park_failed(alive, px, py, pz, dx, dy, dz):
+    """rtl:574-591 (normalize=False branch, the only one trace_skew uses).
+    Failed rays are parked on the axis: point (0,0,0), direction (0,0,1)."""
+    px = torch.where(alive, px, 0)
+    py = torch.where(alive, py, 0)
+    pz = torch.where(alive, pz, 0)
+    dx = torch.where(alive, dx, 0)
+    dy = torch.where(alive, dy, 0)
+    dz = torch.where(alive, dz, 1)
+    return px, py, pz, dx, dy, dz
+
+
+def trace(x, y, z, cx, cy, c, t, mu, mask, aggregate: bool = False,
+          allow_backward_rays: bool = True):
+    """rtl:594-675.  Same arguments, same returns as the reference ``trace_skew``.
+
+    x, y, z, cx, cy : broadcastable to [B, F, P, W]
+    c, t, mask      : [B, 1, 1, 1, S];  mu : [B, 1, 1, W, S]
+    """
+    penalties: Dict[str, List[torch.Tensor]] = {
+        'z_RELU': [], 'theta_norm': [], 'theta_prime_norm': []}
+    n_surf = t.shape[-1]
+    curv = c.unbind(-1)
+    gap = t.unbind(-1)
+    ratio = mu.unbind(-1)
+    live = mask.unbind(-1)
+
+    ray_ok = torch.ones_like(y, dtype=torch.bool)                # rtl:605
+    ray_backward = torch.zeros_like(y, dtype=torch.bool)         # rtl:606
+    cz = torch.sqrt(1 - cx ** 2 - cy ** 2)                       # rtl:609
+
+    for k in range(n_surf):                                      # rtl:611
+        missed, dist, cos_inc, cos2_inc = _march_to_sphere(curv[k], x, y, z, cx, cy, cz)
+        x, y, z, dz_travel = _advance(x, y, z, cx, cy, cz, dist)
+        ray_ok = ray_ok & ~missed                                # rtl:619
+        x, y, z, cx, cy, cz = _park_failed(ray_ok, x, y, z, cx, cy, cz)
+        lost, cx, cy, cz, cos2_out = _refract(curv[k], ratio[k], x, y, cx, cy, cos_inc)
+        if k > 0:                                                # rtl:626-632
+            counted = ray_ok & live[k - 1]
+            if allow_backward_rays:
+                ray_backward = ray_backward | ((dz_travel < 0) & counted)
+            else:
+                ray_ok = ray_ok & ~((dz_travel < 0) & counted)
+        ray_ok = ray_ok & ~lost                                  # rtl:635
+        x, y, z, cx, cy, cz = _park_failed(ray_ok, x, y, z, cx, cy, cz)
+        z = z - gap[k]                                           # rtl:639
+
+        if aggregate:                                            # rtl:641-657
+            z_pos = z.clone()
+            z_pos[z_pos <= 0] = 0.
+            tiny = 1e-7
+            ang_in = torch.acos(torch.clamp(torch.sqrt(cos2_inc), min=-1.0 + tiny, max=1.0 - tiny))
+            ang_out = torch.acos(torch.clamp(torch.sqrt(cos2_out), min=-1.0 + tiny, max=1.0 - tiny))
+            ang_in = ang_in / (1 / 2 * math.pi)
+            ang_out = ang_out / (1 / 2 * math.pi)
+            ang_in[~ray_ok] = 1.
+            ang_out[~ray_ok] = 1.
+            full = (*x.shape[:3], ratio[0].shape[-1])
+            penalties['z_RELU'].append(torch.broadcast_to(z_pos, full))
+            penalties['theta_norm'].append(torch.broadcast_to(ang_in, full))
+            penalties['theta_prime_norm'].append(torch.broadcast_to(ang_out, full))
+
+    # image plane, rtl:660-670
+    dz_travel = -z
+    dist = dz_travel / cz
+    x = x + dist * cx
+    y = y + dist * cy
+    counted = ray_ok & live[-1]
+    if allow_backward_rays:
+        ray_backward = ray_backward | ((dz_travel < 0) & counted)
+    else:
+        ray_ok = ray_ok & ~((dz_travel < 0) & counted)
+
+    if aggregate:
+        return x, y, cx, cy, ray_ok, ray_backward, penalties
+    return x, y, cx, cy, ray_ok, ray_backward
+
+
+def spot_rms(x, y, ray_ok):
+    """rtl:678-702.  Mean over fields of the y-only RMS spot radius of lens 0.
+
+    The centroid is the mean over *all* rays of the field (parked rays sit at
+    y = 0 and are included, rtl:695-697); the squared deviations are summed over
+    surviving rays only but divided by the full count P*W (rtl:699)."""
+    n_field, n_pupil, n_wave = y.shape[1], y.shape[2], y.shape[3]
+    total = 0.
+    for f in range(n_field):
+        centroid_sum = 0.
+        for w in range(n_wave):
+            centroid_sum = centroid_sum + torch.mean(y[0, f, :, w])
+        centroid = centroid_sum / n_wave
+        kept = y[0, f, :, :][ray_ok[0, f, :, :]]
+        total = total + torch.sqrt(torch.sum((kept - centroid) ** 2) / (n_pupil * n_wave))
+    return total / n_field
+
+
+def spot_rms_all_lenses(y, ray_ok):
+    """Vectorised restatement of :func:`spot_rms` for every lens of the batch
+    (the reference hard-codes lens 0, rtl:695/:699).  Returns [B].  Used to check
+    the batched CUDA reduction; lens 0 of the result equals ``spot_rms``
+    up to summation order."""
+    n_pupil, n_wave = y.shape[2], y.shape[3]
+    centroid = y.mean(dim=2).mean(dim=2)                         # [B, F]
+    dev2 = torch.where(ray_ok, (y - centroid[:, :, None, None]) ** 2, torch.zeros_like(y))
+    per_field = torch.sqrt(dev2.sum(dim=(2, 3)) / (n_pupil * n_wave))
+    return per_field.mean(dim=1)
+
+
+def trace_and_rms(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays: bool = True):
+    """The fwd+bwd hot path as one call (trace -> RMS spot loss), for timing the
+    CPU baseline: returns (rms, outputs)."""
+    out = trace(x, y, z, cx, cy, c, t, mu, mask, False, allow_backward_rays)
+    return spot_rms(out[0], out[1], out[4]), out
