@@ -1,0 +1,156 @@
+/*
+ * torchoptics_b200 -- C ABI of the B200-native sequential ray-trace hot path.
+ *
+ * This is the drop-in boundary for the hot path of the reference tracer
+ * (/root/reference/torchlens/ray_tracing_lite.py, "rtl" below).  Every entry
+ * point takes plain device pointers, element strides and sizes; nothing here
+ * knows about torch.  The caller owns all memory (inputs, outputs, workspace)
+ * and passes the CUDA stream to launch on (a cudaStream_t cast to void*; NULL =
+ * the legacy default stream).  All functions return 0 on success or a negative
+ * TL_ERR_* code and never throw; tl_last_error() gives the message of the last
+ * failure on the calling thread.  Nothing allocates, synchronises or copies to
+ * the host.
+ *
+ * Tensor convention (rtl:4-9): ray tensors are [B lenses, F fields, P pupil
+ * points, W wavelengths]; prescriptions carry a trailing surface axis S.
+ *
+ *   tl_trace_fwd           replaces  trace_skew forward                 rtl:594-675
+ *                          (find_marching_distance_spherical rtl:525-545,
+ *                           update_ray_coordinates rtl:514-522,
+ *                           apply_snell_spherical rtl:548-571,
+ *                           reset_bad_rays rtl:574-591)
+ *   tl_trace_bwd           replaces  autograd of trace_skew             rtl:594-675
+ *   tl_rms_fwd/tl_rms_bwd  replace   compute_rms2d and its autograd     rtl:678-702
+ *   tl_spot_accumulate +   replace   trace_skew -> compute_rms2d -> .backward()
+ *   tl_spot_finalize                 as one pass (the fwd+bwd hot path) rtl:594-702
+ */
+#ifndef TORCHOPTICS_B200_H
+#define TORCHOPTICS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TL_ABI_VERSION 1
+
+enum {
+  TL_OK = 0,
+  TL_ERR_INVALID = -1,      /* bad argument (null pointer, size, unsupported S) */
+  TL_ERR_WORKSPACE = -2,    /* workspace too small                             */
+  TL_ERR_CUDA = -3          /* a CUDA runtime call / launch failed             */
+};
+
+/* Arithmetic policy of the forward trace.
+ * TL_ARITH_GUARDED: FMA-contracted fast path for rays that stay clear of every
+ *   mask threshold by a guard band; every other ray is re-traced with
+ *   TL_ARITH_EXACT arithmetic, so masks are those of the exact path.
+ * TL_ARITH_EXACT: every operation individually rounded (IEEE-754 RN, no
+ *   contraction) in the operand order of rtl:525-571 -- outputs are bit-identical
+ *   to the reference's eager fp32 evaluation. */
+enum { TL_ARITH_GUARDED = 0, TL_ARITH_EXACT = 1 };
+
+#define TL_MAX_SURFACES_FWD   256  /* tl_trace_fwd                          */
+#define TL_MAX_SURFACES_BWD    32  /* tl_trace_bwd                          */
+#define TL_MAX_SURFACES_SPOT   16  /* tl_spot_accumulate with want_grad     */
+
+/* A ray-bundle input broadcastable to [B,F,P,W]: base pointer + element strides
+ * (0 = broadcast along that axis), exactly what torch.broadcast_to() yields. */
+typedef struct TlStrided {
+  const float *ptr;
+  int64_t stride[4];
+} TlStrided;
+
+/* Arguments of trace_skew (rtl:594). */
+typedef struct TlProblem {
+  TlStrided x, y, z, cx, cy;   /* entrance-pupil point and direction cosines      */
+  const float *c;              /* [B,S] surface curvatures                         */
+  const float *t;              /* [B,S] thickness after each surface               */
+  const float *mu;             /* [B,W,S] index ratio n/n' per wavelength          */
+  const uint8_t *live;         /* [B,S] structure mask (1 = real surface)          */
+  int32_t B, F, P, W, S;
+  int32_t allow_backward_rays; /* rtl:594 flag                                     */
+  int32_t arith;               /* TL_ARITH_*                                       */
+  int32_t p_begin, p_end;      /* pupil slice [p_begin,p_end) traced by this call
+                                  (tl_spot_accumulate only; shards rays over GPUs) */
+} TlProblem;
+
+/* Outputs of trace_skew, each a contiguous [B,F,P,W] array. */
+typedef struct TlTraceOut {
+  float *x, *y, *cx, *cy;
+  uint8_t *ok, *backward;      /* 0/1 bytes (torch.bool storage)                   */
+} TlTraceOut;
+
+/* Upstream gradients of the four differentiable outputs; contiguous [B,F,P,W]
+ * or NULL (= zero). */
+typedef struct TlSeeds {
+  const float *gx, *gy, *gcx, *gcy;
+} TlSeeds;
+
+/* Gradients produced by tl_trace_bwd.  Prescription gradients are summed over
+ * rays; per-ray gradients are contiguous [B,F,P,W] and optional (NULL = skip). */
+typedef struct TlGrads {
+  float *gc;                   /* [B,S]                                            */
+  float *gt;                   /* [B,S]                                            */
+  float *gmu;                  /* [B,W,S]                                          */
+  float *gz_sum;               /* [B]   d/dz summed over the lens' rays            */
+  float *gx, *gy, *gz, *gcx, *gcy;  /* per ray, optional                           */
+} TlGrads;
+
+/* Results of the fused spot pass for each lens. */
+typedef struct TlSpotOut {
+  float *rms;                  /* [B]   mean over fields of the y-RMS (rtl:678-702, every lens) */
+  float *rms_field;            /* [B,F] per-field RMS                               */
+  float *gc, *gt, *gmu, *gz;   /* d rms[b] / d{c[b,:], t[b,:], mu[b,:,:], z[b]}; NULL if no grad */
+} TlSpotOut;
+
+int tl_abi_version(void);
+const char *tl_last_error(void);
+
+/* Forward trace: fills all six outputs. */
+int tl_trace_fwd(const TlProblem *pb, const TlTraceOut *out, void *stream);
+
+/* Backward of the trace.  Re-traces every ray (nothing is saved by the forward),
+ * applies the adjoint surface by surface and reduces the prescription gradients
+ * over rays in fp64.  Workspace: tl_trace_bwd_workspace() bytes, 8-byte aligned. */
+size_t tl_trace_bwd_workspace(const TlProblem *pb);
+int tl_trace_bwd(const TlProblem *pb, const TlSeeds *seeds, const TlGrads *grads,
+                 void *workspace, size_t workspace_bytes, void *stream);
+
+/* compute_rms2d for every lens of the batch and its backward.
+ * y, ok: contiguous [B,F,P,W].  stats: [B,F,4] doubles written by the forward
+ * and consumed by the backward.  gy = grad_rms[b] * d rms[b] / d y. */
+size_t tl_rms_workspace(int32_t B, int32_t F, int32_t P, int32_t W);
+int tl_rms_fwd(const float *y, const uint8_t *ok, int32_t B, int32_t F, int32_t P, int32_t W,
+               float *rms, float *rms_field, double *stats,
+               void *workspace, size_t workspace_bytes, void *stream);
+int tl_rms_bwd(const float *y, const uint8_t *ok, const double *stats, const float *grad_rms,
+               int32_t B, int32_t F, int32_t P, int32_t W, float *gy, void *stream);
+
+/* Fused hot path.  tl_spot_accumulate traces the pupil slice [p_begin,p_end) of
+ * every (lens, field, wavelength), and in the same pass applies the adjoint with
+ * a unit seed on y so that the RMS gradient can be assembled later without a
+ * second trace.  It leaves, in `moments` ([B,F,W,tl_spot_moment_count()] doubles),
+ * sums that are ADDITIVE over pupil slices: ranks that traced different slices
+ * all-reduce (sum) this one buffer.  `ref_y` ([B,F] floats) receives the per-field
+ * reference height the sums are centred on (identical on every rank).
+ * tl_spot_finalize turns the (reduced) moments into the RMS and its gradients;
+ * P_total is the full pupil count of the job. */
+int32_t tl_spot_moment_count(int32_t S, int32_t want_grad);
+size_t tl_spot_workspace(const TlProblem *pb, int32_t want_grad);
+int tl_spot_accumulate(const TlProblem *pb, int32_t want_grad, double *moments, float *ref_y,
+                       void *workspace, size_t workspace_bytes, void *stream);
+int tl_spot_finalize(const double *moments, const float *ref_y, int32_t B, int32_t F, int32_t W,
+                     int32_t S, int64_t P_total, int32_t want_grad, const TlSpotOut *out,
+                     void *stream);
+
+/* Number of kernels this library has launched since it was loaded (bench.py's
+ * gpu_launches counter). */
+int64_t tl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TORCHOPTICS_B200_H */

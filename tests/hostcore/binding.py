@@ -1,0 +1,51 @@
+"""ctypes binding of the CPU test aid (tests/hostcore/hostcore.cpp)."""
+import ctypes
+
+import numpy as np
+
+from .build import build
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def trace_exact(x, y, z, cx, cy, c, t, mu, live, allow_backward=True):
+    n = x.size
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    x, y, z, cx, cy, c, t, mu = map(f, (x, y, z, cx, cy, c, t, mu))
+    live = np.ascontiguousarray(live, dtype=np.uint8)
+    out = [np.empty(n, np.float32) for _ in range(4)] + [np.empty(n, np.uint8) for _ in range(2)]
+    lib().hc_trace_exact(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(cx), _p(cy), ctypes.c_int(c.size),
+                         _p(c), _p(t), _p(mu), _p(live), ctypes.c_int(int(allow_backward)),
+                         *[_p(o) for o in out])
+    return out
+
+
+def fast(dtype, x, y, z, cx, cy, c, t, mu, live, seeds=None):
+    """Fast-policy forward (+ adjoint when seeds=(gx,gy,gcx,gcy) is given)."""
+    n = x.size
+    f = lambda a: np.ascontiguousarray(a, dtype=dtype)
+    x, y, z, cx, cy, c, t, mu = map(f, (x, y, z, cx, cy, c, t, mu))
+    live = np.ascontiguousarray(live, dtype=np.uint8)
+    S = c.size
+    outs = [np.zeros(n, dtype) for _ in range(6)]
+    grads = [np.zeros(n, dtype) for _ in range(5)]
+    pg = [np.zeros(S, np.float64) for _ in range(3)]
+    sd = [None] * 4 if seeds is None else [f(s) for s in seeds]
+    fn = lib().hc_fast_f32 if dtype == np.float32 else lib().hc_fast_f64
+    fn(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(cx), _p(cy), ctypes.c_int(S), _p(c), _p(t), _p(mu),
+       _p(live), *[_p(s) for s in sd], *[_p(o) for o in outs], *[_p(g) for g in grads],
+       *[_p(g) for g in pg])
+    return dict(x=outs[0], y=outs[1], cx=outs[2], cy=outs[3], min_cos2=outs[4], min_travel=outs[5],
+                gx=grads[0], gy=grads[1], gz=grads[2], gcx=grads[3], gcy=grads[4],
+                gc=pg[0], gt=pg[1], gmu=pg[2])

@@ -1,0 +1,21 @@
+"""Build the CPU test aid tests/hostcore/_hostcore.so (see hostcore.cpp)."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, '_hostcore.so')
+
+
+def build(force=False):
+    src = os.path.join(HERE, 'hostcore.cpp')
+    core = os.path.join(HERE, '..', '..', 'torchoptics_b200', 'csrc', 'trace_core.cuh')
+    if (not force and os.path.exists(SO)
+            and os.path.getmtime(SO) >= max(os.path.getmtime(src), os.path.getmtime(core))):
+        return SO
+    subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-fno-fast-math', '-std=c++17',
+                           '-shared', '-fPIC', '-x', 'c++', src, '-o', SO])
+    return SO
+
+
+if __name__ == '__main__':
+    print(build(force=True))

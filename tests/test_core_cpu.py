@@ -1,0 +1,96 @@
+"""The per-ray arithmetic that the CUDA kernels execute (csrc/trace_core.cuh),
+compiled for the CPU by tests/hostcore, against the oracle:
+
+* exact policy  -> bit-identical to the golden vectors of the reference,
+* fast policy   -> within 1e-5 of them on clearly-good rays,
+* adjoint       -> fp64, against autograd of the oracle (~1e-10).
+"""
+import numpy as np
+import torch
+
+from oracle import trace_oracle as oracle
+from tests.hostcore import binding as hc
+
+
+def _per_wavelength(rec):
+    """Yield the [B=1,F,P,W] problem of a golden record one wavelength at a time,
+    every input broadcast to full ray shape."""
+    shape = rec['out_ok'].shape
+    full = {k: np.broadcast_to(rec['in_' + k], shape) for k in ('x', 'y', 'z', 'cx', 'cy')}
+    for w in range(shape[3]):
+        rays = {k: np.ascontiguousarray(v[0, :, :, w]).ravel() for k, v in full.items()}
+        yield w, rays, rec['in_c'][0, 0, 0, 0], rec['in_t'][0, 0, 0, 0], rec['in_mu'][0, 0, 0, w], \
+            rec['in_mask'][0, 0, 0, 0]
+
+
+def test_exact_policy_is_bit_identical(golden):
+    """Exact policy == oracle with the correctly rounded sqrt, bit for bit; and its
+    masks == the reference's own (golden), values within the 1e-5 budget."""
+    allow = bool(golden['allow_backward_rays'])
+    i = {k[3:]: torch.from_numpy(golden[k]) for k in golden if k.startswith('in_')}
+    with oracle.ieee_sqrt():
+        ref = oracle.trace(i['x'], i['y'], i['z'], i['cx'], i['cy'], i['c'], i['t'], i['mu'],
+                           i['mask'], False, allow)
+    ref = [torch.broadcast_to(r, ref[4].shape).numpy() for r in ref]
+    scale = max(np.abs(golden['out_x']).max(), np.abs(golden['out_y']).max())
+    for w, rays, c, t, mu, live in _per_wavelength(golden):
+        got = hc.trace_exact(rays['x'], rays['y'], rays['z'], rays['cx'], rays['cy'],
+                             c, t, mu, live, allow)
+        for j, (key, tol) in enumerate((('out_x', 1e-5 * scale), ('out_y', 1e-5 * scale),
+                                        ('out_cx', 1e-5), ('out_cy', 1e-5))):
+            want = np.ascontiguousarray(ref[j][0, :, :, w]).ravel()
+            assert np.array_equal(got[j].view(np.uint32), want.view(np.uint32)), (key, w)
+            assert np.abs(got[j] - golden[key][0, :, :, w].ravel()).max() <= tol, (key, w)
+        for j, key in ((4, 'out_ok'), (5, 'out_backward')):
+            assert np.array_equal(got[j].astype(bool), ref[j][0, :, :, w].ravel())
+            # (the reference returns an un-broadcast all-False `ray_backward` when the flag is off)
+            want = np.broadcast_to(golden[key], golden['out_ok'].shape)[0, :, :, w].ravel()
+            assert np.array_equal(got[j].astype(bool), want)
+
+
+def test_fast_policy_close_on_clear_rays(golden):
+    scale = max(np.abs(golden['out_x']).max(), np.abs(golden['out_y']).max())
+    n_clear = 0
+    for w, rays, c, t, mu, live in _per_wavelength(golden):
+        r = hc.fast(np.float32, rays['x'], rays['y'], rays['z'], rays['cx'], rays['cy'], c, t, mu, live)
+        length = np.abs(t).sum() + np.abs(rays['z']).max()
+        clear = (r['min_cos2'] > 1e-6 + 1e-4) & (r['min_travel'] > 1e-5 * max(1.0, length))
+        ok = golden['out_ok'][0, :, :, w].ravel()
+        bw = np.broadcast_to(golden['out_backward'], golden['out_ok'].shape)[0, :, :, w].ravel()
+        # a clearly-good ray must be ok and not flagged in the reference
+        assert np.all(ok[clear]) and not np.any(bw[clear])
+        n_clear += clear.sum()
+        for key, ref_key, tol in (('x', 'out_x', 1e-5 * scale), ('y', 'out_y', 1e-5 * scale),
+                                  ('cx', 'out_cx', 1e-5), ('cy', 'out_cy', 1e-5)):
+            want = golden[ref_key][0, :, :, w].ravel()
+            assert np.abs(r[key][clear] - want[clear]).max(initial=0.0) <= tol, (key, w)
+    if golden['out_ok'].all() and not golden['out_backward'].any():
+        assert n_clear == golden['out_ok'].size
+
+
+def test_adjoint_matches_autograd_fp64(golden):
+    rng = np.random.default_rng(0)
+    for w, rays, c, t, mu, live in _per_wavelength(golden):
+        ok = golden['out_ok'][0, :, :, w].ravel()
+        keep = np.nonzero(ok)[0][:200]
+        if keep.size == 0:
+            continue
+        rays = {k: v[keep].astype(np.float64) for k, v in rays.items()}
+        seeds = [rng.standard_normal(keep.size) for _ in range(4)]
+        r = hc.fast(np.float64, rays['x'], rays['y'], rays['z'], rays['cx'], rays['cy'],
+                    c.astype(np.float64), t.astype(np.float64), mu.astype(np.float64), live, seeds)
+        ti = {k: torch.tensor(v.reshape(1, 1, -1, 1), requires_grad=True) for k, v in rays.items()}
+        tc = torch.tensor(c.astype(np.float64).reshape(1, 1, 1, 1, -1), requires_grad=True)
+        tt = torch.tensor(t.astype(np.float64).reshape(1, 1, 1, 1, -1), requires_grad=True)
+        tmu = torch.tensor(mu.astype(np.float64).reshape(1, 1, 1, 1, -1), requires_grad=True)
+        tmask = torch.tensor(live.reshape(1, 1, 1, 1, -1))
+        out = oracle.trace(ti['x'], ti['y'], ti['z'], ti['cx'], ti['cy'], tc, tt, tmu, tmask)
+        assert bool(out[4].all())
+        loss = sum((torch.tensor(s.reshape(1, 1, -1, 1)) * o).sum() for s, o in zip(seeds, out[:4]))
+        g = torch.autograd.grad(loss, [ti['x'], ti['y'], ti['z'], ti['cx'], ti['cy'], tc, tt, tmu])
+        for got, want in zip((r['gx'], r['gy'], r['gz'], r['gcx'], r['gcy'], r['gc'], r['gt'], r['gmu']), g):
+            want = want.numpy().ravel()
+            err = np.abs(got - want).max() / max(np.abs(want).max(), 1e-3)
+            assert err < 1e-9, err
+        # the forward itself, in fp64, equals the oracle in fp64
+        assert np.abs(r['y'] - out[1].detach().numpy().ravel()).max() < 1e-11

@@ -1,0 +1,348 @@
+// Per-ray arithmetic of the sequential skew-ray trace: forward (two arithmetic
+// policies) and the hand-derived adjoint of one surface.
+//
+// Everything here is a pure function of a ray's registers; the kernels in
+// trace_kernels.cu decide how rays map to threads, where per-surface state is
+// parked and how gradients are reduced.  The file also compiles as plain C++
+// (g++ -ffp-contract=off) so that tests/hostcore can run the very same code on
+// the CPU against the oracle -- a test aid only, never a product fallback.
+//
+// Reference behaviour followed (file: /root/reference/torchlens/ray_tracing_lite.py):
+//   march      find_marching_distance_spherical   rtl:525-545
+//   advance    update_ray_coordinates             rtl:514-522
+//   refract    apply_snell_spherical              rtl:548-571
+//   park       reset_bad_rays                     rtl:574-591
+//   loop/masks trace_skew                         rtl:594-675
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define TL_HD __host__ __device__ __forceinline__
+#else
+#define TL_HD inline
+#endif
+
+namespace tl {
+
+constexpr float kGuard = 1e-6f;   // rtl:530, rtl:552: eps of every mask predicate
+// Guard bands of the GUARDED policy: a ray takes the contracted fast path only if
+// every predicate quantity clears its threshold by this much (cos^2-like
+// quantities are O(1); z travel is compared against the system length).
+constexpr float kBandCos2 = 1e-4f;
+constexpr float kBandTravelRel = 1e-5f;
+
+// ---------------------------------------------------------------------------
+// exact scalar ops: one IEEE-754 round-to-nearest operation each, never fused
+// ---------------------------------------------------------------------------
+TL_HD float xmul(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  return a * b;
+#endif
+}
+TL_HD float xadd(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+TL_HD float xsub(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fsub_rn(a, b);
+#else
+  return a - b;
+#endif
+}
+TL_HD float xdiv(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fdiv_rn(a, b);
+#else
+  return a / b;
+#endif
+}
+TL_HD float xsqrt(float a) {
+#if defined(__CUDA_ARCH__)
+  return __fsqrt_rn(a);
+#else
+  return sqrtf(a);
+#endif
+}
+
+// ---------------------------------------------------------------------------
+// fast ops (contracted, approximate reciprocal / rsqrt on the MUFU unit)
+// ---------------------------------------------------------------------------
+TL_HD float ffma(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+  return __fmaf_rn(a, b, c);
+#else
+  return fmaf(a, b, c);
+#endif
+}
+TL_HD float frcp(float a) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+#else
+  return 1.0f / a;
+#endif
+}
+TL_HD float frsqrt(float a) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+#else
+  return 1.0f / sqrtf(a);
+#endif
+}
+TL_HD double ffma(double a, double b, double c) { return fma(a, b, c); }
+TL_HD double frcp(double a) { return 1.0 / a; }
+TL_HD double frsqrt(double a) { return 1.0 / sqrt(a); }
+TL_HD float fmin2(float a, float b) { return fminf(a, b); }
+TL_HD double fmin2(double a, double b) { return fmin(a, b); }
+
+template <class T>
+struct Ray {
+  T x, y, z, cx, cy, cz;
+};
+
+// One surface as a ray of a given wavelength sees it.
+struct Surface {
+  float c;    // curvature
+  float t;    // distance to the next vertex
+  float mu;   // n / n'
+};
+
+// ---------------------------------------------------------------------------
+// EXACT policy.  Statement by statement the reference's eager evaluation.
+// ---------------------------------------------------------------------------
+TL_HD float exact_cz0(float cx, float cy) {            // rtl:609
+  return xsqrt(xsub(xsub(1.0f, xmul(cx, cx)), xmul(cy, cy)));
+}
+
+TL_HD void exact_park(bool ok, Ray<float> &r) {         // rtl:574-591
+  if (!ok) {
+    r.x = 0.f; r.y = 0.f; r.z = 0.f; r.cx = 0.f; r.cy = 0.f; r.cz = 1.f;
+  }
+}
+
+// Trace one surface.  `count_travel`: this surface takes part in the backward-ray
+// test (k > 0 and mask[k-1], rtl:626-628).
+TL_HD void exact_surface(Ray<float> &r, const Surface s, bool count_travel, bool allow_backward,
+                         bool &ok, bool &backward) {
+  // rtl:531-535
+  const float e = -xadd(xadd(xmul(r.x, r.cx), xmul(r.y, r.cy)), xmul(r.z, r.cz));
+  const float mz = xadd(r.z, xmul(e, r.cz));
+  const float m2 = xsub(xadd(xadd(xmul(r.x, r.x), xmul(r.y, r.y)), xmul(r.z, r.z)), xmul(e, e));
+  const float temp = xsub(xmul(s.c, m2), xmul(2.0f, mz));
+  const float cos2_in = xsub(xmul(r.cz, r.cz), xmul(s.c, temp));
+  const bool missed = xsub(cos2_in, kGuard) < 0.0f;                       // rtl:540
+  const float cos_in = xsqrt(missed ? 1.0f : cos2_in);                    // rtl:541
+  const float dist = xadd(e, xdiv(temp, xadd(r.cz, cos_in)));             // rtl:543
+  // rtl:518-521
+  const float travel = xmul(dist, r.cz);
+  r.x = xadd(r.x, xmul(dist, r.cx));
+  r.y = xadd(r.y, xmul(dist, r.cy));
+  r.z = xadd(r.z, travel);
+  ok = ok && !missed;                                                     // rtl:619
+  exact_park(ok, r);
+  // rtl:553-568
+  const float cos2_out = xsub(1.0f, xmul(xmul(s.mu, s.mu), xsub(1.0f, xmul(cos_in, cos_in))));
+  bool lost = xsub(cos2_out, kGuard) < 0.0f;
+  const float cos_out = xsqrt(lost ? 1.0f : cos2_out);
+  const float g = xsub(cos_out, xmul(s.mu, cos_in));
+  const float gc = xmul(g, s.c);
+  r.cx = xsub(xmul(s.mu, r.cx), xmul(gc, r.x));
+  r.cy = xsub(xmul(s.mu, r.cy), xmul(gc, r.y));
+  const float cz2 = xsub(1.0f, xadd(xmul(r.cx, r.cx), xmul(r.cy, r.cy)));
+  lost = lost || (xsub(cz2, kGuard) < 0.0f);
+  r.cz = xsqrt(lost ? 1.0f : cz2);
+  if (count_travel) {                                                     // rtl:626-632
+    const bool flagged = (travel < 0.0f) && ok;
+    if (allow_backward) backward = backward || flagged;
+    else ok = ok && !flagged;
+  }
+  ok = ok && !lost;                                                       // rtl:635
+  exact_park(ok, r);
+  r.z = xsub(r.z, s.t);                                                   // rtl:639
+}
+
+// Image plane, rtl:660-670.  Returns through r.x, r.y; direction unchanged.
+TL_HD void exact_image(Ray<float> &r, bool last_live, bool allow_backward, bool &ok,
+                       bool &backward) {
+  const float travel = -r.z;
+  const float dist = xdiv(travel, r.cz);
+  r.x = xadd(r.x, xmul(dist, r.cx));
+  r.y = xadd(r.y, xmul(dist, r.cy));
+  const bool flagged = (travel < 0.0f) && ok && last_live;
+  if (allow_backward) backward = backward || flagged;
+  else ok = ok && !flagged;
+}
+
+// ---------------------------------------------------------------------------
+// FAST policy (generic over the lane type so the CPU check can run it in fp64).
+// No masks, no parking: the caller tracks `clear` = the smallest margin by which
+// any predicate quantity cleared its threshold and discards the result (falls
+// back to the exact policy) unless the ray was clearly good everywhere.
+// ---------------------------------------------------------------------------
+template <class T>
+TL_HD T fast_cz0(T cx, T cy) {
+  const T w = ffma(-cy, cy, ffma(-cx, cx, T(1)));
+  return w * frsqrt(w);
+}
+
+template <class T>
+TL_HD void fast_surface(Ray<T> &r, T c, T mu, T mu2, T t, T &min_cos2, T &travel) {
+  const T ne = ffma(r.z, r.cz, ffma(r.y, r.cy, r.x * r.cx));          // -e
+  const T mz = ffma(-ne, r.cz, r.z);
+  const T m2 = ffma(-ne, ne, ffma(r.z, r.z, ffma(r.y, r.y, r.x * r.x)));
+  const T tmp = ffma(c, m2, T(-2) * mz);
+  const T q = ffma(-c, tmp, r.cz * r.cz);                               // cos^2 in
+  const T ci = q * frsqrt(q);
+  const T dist = ffma(tmp, frcp(r.cz + ci), -ne);
+  travel = dist * r.cz;
+  r.x = ffma(dist, r.cx, r.x);
+  r.y = ffma(dist, r.cy, r.y);
+  r.z = r.z + travel;
+  const T qo = ffma(-mu2, T(1) - q, T(1));                              // cos^2 out
+  const T co = qo * frsqrt(qo);
+  const T gc = ffma(-mu, ci, co) * c;
+  r.cx = ffma(-gc, r.x, mu * r.cx);
+  r.cy = ffma(-gc, r.y, mu * r.cy);
+  const T w = T(1) - ffma(r.cy, r.cy, r.cx * r.cx);
+  r.cz = w * frsqrt(w);
+  min_cos2 = fmin2(min_cos2, fmin2(q, fmin2(qo, w)));
+  r.z = r.z - t;
+}
+
+// Image plane; returns the z travel (for the backward-ray margin).
+template <class T>
+TL_HD T fast_image(Ray<T> &r) {
+  const T dist = -r.z * frcp(r.cz);
+  r.x = ffma(dist, r.cx, r.x);
+  r.y = ffma(dist, r.cy, r.y);
+  return -r.z;
+}
+
+// ---------------------------------------------------------------------------
+// Adjoint.  `a` holds the adjoint of a ray state (d loss / d state).
+// ---------------------------------------------------------------------------
+template <class T>
+struct SurfaceGrad {
+  T c, t, mu;
+};
+
+// Adjoint of the image-plane transfer.  `r` is the state in front of the image
+// plane (after the last surface's z shift); seeds are d loss / d(x, y, cx, cy) of
+// the outputs.
+template <class T>
+TL_HD Ray<T> adjoint_image(const Ray<T> &r, T gx, T gy, T gcx, T gcy) {
+  const T rcz = frcp(r.cz);
+  const T dist = -r.z * rcz;
+  const T gdist = ffma(gy, r.cy, gx * r.cx);
+  Ray<T> a;
+  a.x = gx;
+  a.y = gy;
+  a.cx = ffma(dist, gx, gcx);
+  a.cy = ffma(dist, gy, gcy);
+  a.z = -gdist * rcz;
+  a.cz = a.z * dist;          // d dist / d cz = -dist / cz
+  return a;
+}
+
+// Adjoint of one surface.  `in` is the ray state in front of the surface, `out`
+// the state behind it (x, y, direction; = the next surface's `in`), `a` the
+// adjoint of `out` on entry and of `in` on return.
+template <class T>
+TL_HD SurfaceGrad<T> adjoint_surface(const Ray<T> &in, const Ray<T> &out, T c, T mu, T mu2,
+                                     Ray<T> &a) {
+  SurfaceGrad<T> g;
+  g.t = -a.z;                                           // z_out = z_hit - t
+  // -- recompute the forward intermediates from `in`
+  const T ne = ffma(in.z, in.cz, ffma(in.y, in.cy, in.x * in.cx));
+  const T mz = ffma(-ne, in.cz, in.z);
+  const T m2 = ffma(-ne, ne, ffma(in.z, in.z, ffma(in.y, in.y, in.x * in.x)));
+  const T tmp = ffma(c, m2, T(-2) * mz);
+  const T q = ffma(-c, tmp, in.cz * in.cz);
+  const T rsq_q = frsqrt(q);
+  const T ci = q * rsq_q;
+  const T ru = frcp(in.cz + ci);
+  const T tu = tmp * ru;
+  const T dist = tu - ne;
+  const T omq = T(1) - q;
+  const T qo = ffma(-mu2, omq, T(1));
+  const T rsq_qo = frsqrt(qo);
+  const T gsn = ffma(-mu, ci, qo * rsq_qo);             // g = cos_out - mu cos_in
+  const T gcv = gsn * c;
+  // -- cz_out = sqrt(1 - cx_out^2 - cy_out^2)
+  const T rr = a.cz * frcp(out.cz);
+  const T acx = ffma(-out.cx, rr, a.cx);
+  const T acy = ffma(-out.cy, rr, a.cy);
+  // -- cx_out = mu cx - (g c) x_hit
+  T gmu = ffma(acy, in.cy, acx * in.cx);
+  const T gG = -ffma(acy, out.y, acx * out.x);
+  const T ax1 = ffma(-gcv, acx, a.x);
+  const T ay1 = ffma(-gcv, acy, a.y);
+  const T az1 = a.z;
+  T ncx = mu * acx;
+  T ncy = mu * acy;
+  const T gg = gG * c;
+  T gc = gG * gsn;
+  // -- g = cos_out - mu cos_in ; cos_out = sqrt(qo) ; qo = 1 - mu^2 (1 - q)
+  gmu = ffma(-gg, ci, gmu);
+  T gci = -gg * mu;
+  const T gqo = gg * (T(0.5) * rsq_qo);
+  T gq = mu2 * gqo;
+  gmu = ffma(T(-2) * mu * omq, gqo, gmu);
+  // -- advance: hit = in + dist * dir
+  const T gdist = ffma(az1, in.cz, ffma(ay1, in.cy, ax1 * in.cx));
+  ncx = ffma(dist, ax1, ncx);
+  ncy = ffma(dist, ay1, ncy);
+  T ncz = dist * az1;
+  // -- dist = e + tmp / (cz + cos_in)
+  T ge = gdist;
+  T gtmp = gdist * ru;
+  const T gu = -gtmp * tu;
+  ncz = ncz + gu;
+  gci = gci + gu;
+  // -- cos_in = sqrt(q) ; q = cz^2 - c tmp
+  gq = ffma(gci, T(0.5) * rsq_q, gq);
+  ncz = ffma(T(2) * in.cz, gq, ncz);
+  gc = ffma(-tmp, gq, gc);
+  gtmp = ffma(-c, gq, gtmp);
+  // -- tmp = c m2 - 2 mz
+  gc = ffma(m2, gtmp, gc);
+  const T gm2 = c * gtmp;
+  const T gmz = T(-2) * gtmp;
+  // -- m2 = |r|^2 - e^2 ; mz = z + e cz ; e = -(r . d)     (ne = -e)
+  const T gm2x2 = gm2 + gm2;
+  T nx = ffma(gm2x2, in.x, ax1);
+  T ny = ffma(gm2x2, in.y, ay1);
+  T nz = ffma(gm2x2, in.z, az1 + gmz);
+  ge = ffma(gm2x2, ne, ge);                    // -2 e gm2 = +2 ne gm2
+  ge = ffma(in.cz, gmz, ge);
+  ncz = ffma(-ne, gmz, ncz);                   // e gmz
+  a.x = ffma(-in.cx, ge, nx);
+  a.y = ffma(-in.cy, ge, ny);
+  a.z = ffma(-in.cz, ge, nz);
+  a.cx = ffma(-in.x, ge, ncx);
+  a.cy = ffma(-in.y, ge, ncy);
+  a.cz = ffma(-in.z, ge, ncz);
+  g.c = gc;
+  g.mu = gmu;
+  return g;
+}
+
+// Fold the adjoint of cz0 = sqrt(1 - cx^2 - cy^2) (rtl:609) into (cx, cy).
+template <class T>
+TL_HD void adjoint_cz0(const Ray<T> &in0, Ray<T> &a) {
+  const T rr = a.cz * frcp(in0.cz);
+  a.cx = ffma(-in0.cx, rr, a.cx);
+  a.cy = ffma(-in0.cy, rr, a.cy);
+}
+
+}  // namespace tl
