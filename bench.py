@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the ray-trace hot path: ray-surface events/s, forward+backward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): Double-Gauss 50 mm f/3, 11 surfaces,
+16 fields x 3 wavelengths x 296^2 pupil points = 4 205 568 rays per GPU,
+i.e. 46.3 M ray-surface events per step.  One step = trace -> RMS spot loss ->
+gradients w.r.t. c, t, mu, z (the fused `spot_rms` pass + its backward).
+With N > 1 (torchrun) every rank traces its own 4.2 M-ray slice of an N x larger
+pupil grid (weak scaling) and the per-field sums are all-reduced over NCCL.
+
+Printed keys follow the driver contract: `value` is device-timed with inputs
+resident in HBM (CUDA events on the launching stream, L2 flushed between steps);
+`e2e` goes through the public RayTracer API from pinned host buffers and reads
+the loss and gradients back; `roofline` is the dominant kernel against the FP32
+FMA peak (this path has no dense contraction and ~0 HBM traffic);
+`cpu_baseline` is the oracle port timed on the host cores on a bounded sample.
+`--impl reference` runs only that CPU arm.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOPS_FWD, FLOPS_BWD = 61, 105          # per spherical ray-surface event
+N_FIELDS, N_SIDE = 16, 296
+WAVELENGTHS = ('C', 'd', 'F')
+CPU_SAMPLE_SIDE = 160                    # bounded CPU sample: 16 x 3 x 160^2 rays
+METRIC = 'ray-surface events/sec fwd+bwd'
+
+
+def workload_name(n_theta):
+    return (f'double_gauss_S11_F{N_FIELDS}_W{len(WAVELENGTHS)}_pupil{N_SIDE}x{n_theta}'
+            f'_fwd+bwd_rms')
+
+
+# ----------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    """Polls SM clock and throttle reasons through NVML while the timed region runs."""
+    REASONS = {0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap', 0x8: 'hw_slowdown',
+               0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown', 0x80: 'hw_power_brake',
+               0x100: 'display_clock_setting'}
+
+    def __init__(self, index):
+        self.samples, self.mask, self.max_mhz = [], 0, None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                self.mask |= nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['nvml_unavailable']}
+        reasons = [name for bit, name in self.REASONS.items() if self.mask & bit]
+        return {'sm_mhz': statistics.median(self.samples), 'sm_max_mhz': self.max_mhz,
+                'reasons': reasons, 'samples': len(self.samples)}
+
+
+# ----------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path on the host cores
+# ----------------------------------------------------------------------------
+def cpu_arm(steps, warmup, side=CPU_SAMPLE_SIDE):
+    from oracle import trace_oracle as oracle
+    from torchoptics_b200 import RayTracer, prescriptions
+    specs, lens = prescriptions.double_gauss('cpu')
+    for name in ('c', 't', 'nd'):
+        getattr(lens, name).requires_grad_(True)
+    tracer = RayTracer(mode='circular', n_rays=(side, side),
+                       rel_fields=tuple(np.linspace(0, 1, N_FIELDS).tolist()),
+                       wavelengths=WAVELENGTHS, default_device='cpu')
+    events = N_FIELDS * len(WAVELENGTHS) * side * side * lens.c.shape[1]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        args = tracer._ray_set(specs, lens)
+        out = oracle.trace(*args)
+        rms = oracle.spot_rms(out[0], out[1], out[4])
+        torch.autograd.grad(rms, [lens.c, lens.t, lens.nd])
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    best = min(times)
+    return {'value': events / best, 'unit': 'events/s', 'cores': torch.get_num_threads(),
+            'kind': 'port',
+            'sample': f'oracle (torch CPU eager port of trace_skew+compute_rms2d+autograd), '
+                      f'double-gauss S11, {N_FIELDS} fields x {len(WAVELENGTHS)} wavelengths x '
+                      f'{side}^2 pupil = {events // lens.c.shape[1]} rays, best of {steps} '
+                      f'after {warmup} warm-up',
+            'ms_per_step': statistics.mean(times) * 1e3, 'host_cpus': os.cpu_count()}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 10))
+    base = cpu_arm(steps, max(1, min(args.warmup, 2)))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'events/s',
+            'n_gpus': args.gpus, 'steps': steps, 'warmup': max(1, min(args.warmup, 2)),
+            'ms_per_step': base['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': workload_name(N_SIDE), 'cpu_sample': base['sample']},
+            'cpu_baseline': {k: base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+            'e2e': {'value': base['value'], 'unit': 'events/s', 'h2d_bytes_per_step': 0,
+                    'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of a CUDA graph')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+    from torchoptics_b200 import RayTracer, _native, ops, prescriptions
+    from torchoptics_b200 import ray_tracing_lite as rt
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = f'cuda:{local_rank}'
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+    _native.load()
+
+    n_theta = N_SIDE * world                     # weak scaling: 4.2 M rays per rank
+    fields = tuple(np.linspace(0, 1, N_FIELDS).tolist())
+    specs, lens = prescriptions.double_gauss(dev)
+    S = lens.c.shape[1]
+    tracer = RayTracer(mode='circular', n_rays=(N_SIDE, n_theta), rel_fields=fields,
+                       wavelengths=WAVELENGTHS, default_device=dev)
+    rays_total = N_FIELDS * len(WAVELENGTHS) * N_SIDE * n_theta
+    events_total = rays_total * S
+    shard = (rank, world)
+
+    # ---- device-resident step: inputs already in HBM ------------------------
+    ray_args = [a.detach() for a in tracer._ray_set(specs, lens)]
+    for i in (2, 5, 6, 7):                       # z, c, t, mu carry gradients
+        ray_args[i] = ray_args[i].clone().requires_grad_(True)
+    leaves = [ray_args[i] for i in (2, 5, 6, 7)]
+
+    def step():
+        rms, _ = ops.spot_rms(*ray_args, True, _native.ARITH_GUARDED, shard, None)
+        return rms, torch.autograd.grad(rms[0], leaves)
+
+    before = _native.launch_count()
+    step()
+    torch.cuda.synchronize()
+    launches_per_step = _native.launch_count() - before
+
+    graph = None
+    if not args.no_graph and world == 1:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                graph_out = step()
+        except Exception as exc:                 # fall back to eager launches
+            print(f'[bench] CUDA graph capture failed, timing eager launches: {exc}', file=sys.stderr)
+            graph = None
+    run_step = graph.replay if graph is not None else step
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 2x L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        run_step()
+    barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    with ClockSampler(local_rank) as clocks:
+        for i in range(args.steps):
+            flush.zero_()                        # evict L2 between timed iterations
+            starts[i].record()
+            run_step()
+            stops[i].record()
+        barrier()
+    step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    ms_per_step = total_ms / args.steps
+    value = events_total / (ms_per_step * 1e-3)
+
+    # ---- dominant kernel alone (tl_spot_accumulate), live CUDA events --------
+    k_starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k_stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    plain = [a.detach() for a in ray_args]
+    for _ in range(3):
+        ops.spot_moments(*plain, shard=shard)
+    torch.cuda.synchronize()
+    for i in range(args.steps):
+        flush.zero_()
+        k_starts[i].record()
+        ops.spot_moments(*plain, shard=shard)
+        k_stops[i].record()
+    torch.cuda.synchronize()
+    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in zip(k_starts, k_stops))
+    events_rank = events_total // world
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    sm_max_mhz = peaks.get('sm_max_mhz') or clocks.summary().get('sm_max_mhz') or 1965.0
+    peak_tflops = sms * 128 * 2 * sm_max_mhz * 1e6 / 1e12
+    achieved = events_rank * (FLOPS_FWD + FLOPS_BWD) / (kernel_ms * 1e-3) / 1e12
+    roofline = {'bound': 'fp32_fma', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
+                'frac': achieved / peak_tflops, 'traffic': None,
+                'kernel': 'k_trace_adj<12,SPOT_GRAD> (+k_reduce_chunks)', 'kernel_ms': kernel_ms,
+                'flops_per_event': FLOPS_FWD + FLOPS_BWD,
+                'peak_source': f'{sms} SMs x 128 lanes x 2 flop x {sm_max_mhz:.0f} MHz '
+                               f'(sm_max_mhz of MEASURED_PEAKS.json); algorithmic HBM bytes ~0, '
+                               f'hbm peak {peaks.get("hbm_gbs")} GB/s is not the bound'}
+
+    # ---- end to end through the public API, host buffers in, loss+grads out ---
+    host = {k: getattr(lens, k).detach().cpu().pin_memory() for k in ('c', 't', 'nd', 'v')}
+    host_epd = specs.epd.cpu().pin_memory()
+    host_hfov = specs.hfov.cpu().pin_memory()
+    h2d = sum(v.numel() * 4 for v in host.values()) + 8
+    d2h = 4 + (2 * S + lens.nd.shape[1]) * 4
+
+    def e2e_step():
+        from torchoptics_b200 import lens_modeling as lm
+        dl = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        for k in ('c', 't', 'nd'):
+            dl[k].requires_grad_(True)
+        lens_i = lm.Lens(lens.structure, dl['c'], dl['t'], dl['nd'], dl['v'])
+        specs_i = lm.Specs(lens.structure, host_epd.to(dev, non_blocking=True),
+                           host_hfov.to(dev, non_blocking=True))
+        rms, _ = tracer.spot_rms(specs_i, lens_i, shard=shard)
+        rms[0].backward()
+        return rms[0].item(), [dl[k].grad.cpu() for k in ('c', 't', 'nd')]
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = events_total * args.steps / float(e2e_s.item())
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': 'events/s', 'n_gpus': world,
+                'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_per_step,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic',
+                'config': {'workload': workload_name(n_theta), 'lens': 'double_gauss_50mm_f3',
+                           'surfaces': S, 'fields': N_FIELDS, 'wavelengths': len(WAVELENGTHS),
+                           'rays': rays_total, 'events_per_step': events_total,
+                           'rays_per_gpu': rays_total // world,
+                           'parallelism': f'pupil-sharded dp{world}',
+                           'l2': 'flushed between timed steps (256 MiB write)',
+                           'launch': 'cuda_graph' if graph is not None else 'eager',
+                           'arith': 'guarded'},
+                'clocks': clocks.summary(),
+                'e2e': {'value': e2e_value, 'unit': 'events/s', 'h2d_bytes_per_step': h2d,
+                        'd2h_bytes_per_step': d2h,
+                        'ms_per_step': float(e2e_s.item()) / args.steps * 1e3},
+                'gpu_launches': launches_per_step * args.steps,
+                'roofline': roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            base = cpu_arm(5, 1)
+            line['cpu_baseline'] = {k: base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

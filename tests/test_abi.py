@@ -1,0 +1,44 @@
+"""The C-ABI library loads on a CPU-only box and exports every function that
+include/torchoptics_b200.h declares (no compute calls here)."""
+import ctypes
+import os
+import re
+
+from torchoptics_b200 import _native
+from torchoptics_b200.build import build_library
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, 'include', 'torchoptics_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(tl_[a-z_0-9]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    build_library()
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 13
+    for name in names:
+        assert hasattr(lib, name), name
+    assert set(names) == set(_native.EXPORTS), set(names) ^ set(_native.EXPORTS)
+
+
+def test_abi_version_and_argument_checks():
+    lib = _native.load()
+    assert lib.tl_abi_version() == 1
+    assert lib.tl_spot_moment_count(11, 1) == 6 * 11 + 5
+    assert lib.tl_spot_moment_count(11, 0) == 3
+    assert lib.tl_rms_workspace(1, 3, 64, 3) > 0
+    # NULL problem -> error code and message, never a crash
+    assert lib.tl_trace_fwd(None, None, None) == -1
+    assert b'NULL' in lib.tl_last_error()
+
+
+def test_struct_layout_matches_header():
+    # TlStrided = pointer + 4 x int64; TlProblem packs 5 of them, 4 pointers, 9 int32
+    assert ctypes.sizeof(_native.TlStrided) == 40
+    assert ctypes.sizeof(_native.TlProblem) == 5 * 40 + 4 * 8 + 9 * 4 + 4
+    assert ctypes.sizeof(_native.TlGrads) == 9 * 8

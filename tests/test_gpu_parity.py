@@ -1,0 +1,267 @@
+"""Parity of the CUDA hot path (through the C ABI) with the oracle and with the
+golden records of the reference.  Needs a B200: ``pytest -m gpu``.
+
+Tolerances (BASELINE.json north_star / SURVEY.md section 8c): masks bit-exact;
+points max|d(x,y)| / max|(x,y)| <= 1e-5; direction cosines max|d| <= 1e-5;
+gradients ||dg|| / ||g|| <= 1e-4 per parameter group; RMS 1e-5 relative.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import trace_oracle as oracle
+from tests.conftest import load_golden
+from torchoptics_b200 import lens_modeling as lm
+from torchoptics_b200 import ops, prescriptions
+from torchoptics_b200 import ray_tracing_lite as rt
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+POINT_TOL = 1e-5
+COS_TOL = 1e-5
+GRAD_TOL = 1e-4
+RMS_TOL = 1e-5
+
+
+def _inputs(rec, device, grad=()):
+    t = {k[3:]: torch.from_numpy(rec[k]).to(device) for k in rec if k.startswith('in_')}
+    for k in grad:
+        t[k] = t[k].clone().requires_grad_(True)
+    return t
+
+
+def _args(i):
+    return [i[k] for k in ('x', 'y', 'z', 'cx', 'cy', 'c', 't', 'mu', 'mask')]
+
+
+def _rel(got, want):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    return np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-30)
+
+
+def _check_outputs(out, rec, exact_ref=None):
+    ok_shape = rec['out_ok'].shape
+    scale = max(np.abs(rec['out_x']).max(), np.abs(rec['out_y']).max())
+    x, y, cx, cy, ok, bw = [o.cpu().numpy() for o in out]
+    assert np.array_equal(ok, rec['out_ok'])
+    assert np.array_equal(bw, np.broadcast_to(rec['out_backward'], ok_shape))
+    assert np.abs(x - rec['out_x']).max() <= POINT_TOL * scale
+    assert np.abs(y - rec['out_y']).max() <= POINT_TOL * scale
+    assert np.abs(cx - rec['out_cx']).max() <= COS_TOL
+    assert np.abs(cy - rec['out_cy']).max() <= COS_TOL
+    # failed rays are parked: all four outputs exactly zero
+    dead = ~rec['out_ok']
+    assert not x[dead].any() and not y[dead].any() and not cx[dead].any() and not cy[dead].any()
+    if exact_ref is not None:
+        for got, want in zip((x, y, cx, cy), exact_ref[:4]):
+            want = np.broadcast_to(want.numpy(), ok_shape)
+            assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(want).view(np.uint32))
+
+
+def test_forward_exact_policy_bit_identical(golden):
+    i = _inputs(golden, DEV)
+    allow = bool(golden['allow_backward_rays'])
+    out = rt.trace_skew(*_args(i), allow_backward_rays=allow, arith='exact')
+    cpu = _inputs(golden, 'cpu')
+    with oracle.ieee_sqrt():
+        ref = oracle.trace(*_args(cpu), False, allow)
+    _check_outputs(out, golden, exact_ref=ref)
+
+
+def test_forward_guarded_policy(golden):
+    i = _inputs(golden, DEV)
+    out = rt.trace_skew(*_args(i), allow_backward_rays=bool(golden['allow_backward_rays']))
+    _check_outputs(out, golden)
+
+
+@pytest.mark.parametrize('arith', ['guarded', 'exact'])
+def test_backward_against_oracle_autograd(golden, arith):
+    allow = bool(golden['allow_backward_rays'])
+    gen = torch.Generator().manual_seed(1)
+    shape = golden['out_ok'].shape
+    seeds = [torch.randn(shape, generator=gen) for _ in range(4)]
+    wrt = ('x', 'y', 'z', 'cx', 'cy', 'c', 't', 'mu')
+    cpu = _inputs(golden, 'cpu', grad=wrt)
+    ref_out = oracle.trace(*_args(cpu), False, allow)
+    ref_loss = sum((s * o).sum() for s, o in zip(seeds, ref_out[:4]))
+    ref = torch.autograd.grad(ref_loss, [cpu[k] for k in wrt])
+    gpu = _inputs(golden, DEV, grad=wrt)
+    out = rt.trace_skew(*_args(gpu), allow_backward_rays=allow, arith=arith)
+    loss = sum((s.to(DEV) * o).sum() for s, o in zip(seeds, out[:4]))
+    got = torch.autograd.grad(loss, [gpu[k] for k in wrt])
+    for name, g, r in zip(wrt, got, ref):
+        assert g.shape == r.shape, name
+        assert _rel(g.cpu().numpy(), r.numpy()) <= GRAD_TOL, (name, _rel(g.cpu().numpy(), r.numpy()))
+
+
+def test_rms_from_rays(golden):
+    y = torch.from_numpy(golden['out_y']).to(DEV).requires_grad_(True)
+    ok = torch.from_numpy(golden['out_ok']).to(DEV)
+    rms = rt.compute_rms2d(None, y, ok)
+    assert abs(rms.item() - float(golden['rms'])) <= RMS_TOL * float(golden['rms'])
+    (gy,) = torch.autograd.grad(rms, [y])
+    y_cpu = torch.from_numpy(golden['out_y']).requires_grad_(True)
+    ref = oracle.spot_rms(None, y_cpu, torch.from_numpy(golden['out_ok']))
+    (ref_gy,) = torch.autograd.grad(ref, [y_cpu])
+    assert _rel(gy.cpu().numpy(), ref_gy.numpy()) <= GRAD_TOL
+
+
+@pytest.mark.parametrize('arith', ['guarded', 'exact'])
+def test_fused_spot_pass(golden, arith):
+    allow = bool(golden['allow_backward_rays'])
+    gpu = _inputs(golden, DEV, grad=('z', 'c', 't', 'mu'))
+    rms, rms_field = ops.spot_rms(*_args(gpu), allow, rt._arith_code(arith))
+    want = float(golden['rms'])
+    assert abs(rms[0].item() - want) <= RMS_TOL * want, (rms[0].item(), want)
+    got = torch.autograd.grad(rms[0], [gpu[k] for k in ('z', 'c', 't', 'mu')])
+    for name, g in zip(('z', 'c', 't', 'mu'), got):
+        ref = golden['grad_in_' + name]
+        assert g.shape == ref.shape
+        assert _rel(g.cpu().numpy(), ref) <= GRAD_TOL, (name, _rel(g.cpu().numpy(), ref))
+    # the forward-only (no grad) variant gives the same value
+    plain = _inputs(golden, DEV)
+    rms2, _ = ops.spot_rms(*_args(plain), allow, rt._arith_code(arith))
+    assert abs(rms2[0].item() - rms[0].item()) <= 1e-6 * want
+
+
+def test_raytracer_end_to_end(golden):
+    """RayTracer on the GPU (incl. ray aiming, which differentiates the trace
+    w.r.t. the pupil coordinates) against the reference's outputs and lens gradients."""
+    structure = lm.Structure(golden['stop_idx'], sequence=golden['sequence'], default_device=DEV)
+    lens = lm.Lens(structure, *[torch.from_numpy(golden[k]).to(DEV).requires_grad_(True)
+                                for k in ('lens_c', 'lens_t', 'lens_nd', 'lens_v')])
+    specs = lm.Specs(structure, torch.from_numpy(golden['epd']).to(DEV),
+                     torch.from_numpy(golden['hfov']).to(DEV))
+    aimed = 'aimed' in golden['name']
+    tracer = rt.RayTracer(mode='circular', n_rays=tuple(int(v) for v in golden['n_rays']),
+                          rel_fields=tuple(float(v) for v in golden['rel_fields']),
+                          wavelengths=tuple(float(v) for v in golden['wavelengths']),
+                          n_ray_aiming_iter=1 if aimed else 0,
+                          allow_backward_rays=bool(golden['allow_backward_rays']), default_device=DEV)
+    out = tracer.trace_rays(specs, lens)
+    if aimed:
+        # the aimed pupil goes through a division by a traced slope: compare values only
+        scale = np.abs(golden['out_y']).max()
+        assert np.array_equal(out[4].cpu().numpy(), golden['out_ok'])
+        assert np.abs(out[1].detach().cpu().numpy() - golden['out_y']).max() <= 5e-5 * scale
+    else:
+        _check_outputs([o.detach() for o in out], golden)
+    rms = rt.compute_rms2d(out[0], out[1], out[4])
+    assert abs(rms.item() - float(golden['rms'])) <= (5e-5 if aimed else RMS_TOL) * float(golden['rms'])
+    grads = torch.autograd.grad(rms, [lens.c, lens.t, lens.nd, lens.v])
+    tol = 5e-4 if aimed else GRAD_TOL
+    for name, g in zip(('c', 't', 'nd', 'v'), grads):
+        ref = golden['grad_' + name]
+        g = np.nan_to_num(g.cpu().numpy())
+        assert _rel(g, ref) <= tol, (name, _rel(g, ref))
+    # fused pass through the same front end
+    lens2 = lm.Lens(structure, *[torch.from_numpy(golden[k]).to(DEV).requires_grad_(True)
+                                 for k in ('lens_c', 'lens_t', 'lens_nd', 'lens_v')])
+    rms_f, _ = tracer.spot_rms(specs, lens2)
+    assert abs(rms_f[0].item() - rms.item()) <= 2e-6 * rms.item() + 1e-9
+    grads_f = torch.autograd.grad(rms_f[0], [lens2.c, lens2.t, lens2.nd])
+    for name, g, r in zip(('c', 't', 'nd'), grads_f, grads):
+        assert _rel(g.cpu().numpy(), r.cpu().numpy()) <= GRAD_TOL, name
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json sizes: size-independent properties
+# ---------------------------------------------------------------------------
+def _double_gauss_problem(n_side, fields=16, requires_grad=False):
+    specs, lens = prescriptions.double_gauss(DEV)
+    if requires_grad:
+        for name in ('c', 't', 'nd'):
+            getattr(lens, name).requires_grad_(True)
+    tracer = rt.RayTracer(mode='circular', n_rays=(n_side, n_side),
+                          rel_fields=tuple(np.linspace(0, 1, fields).tolist()),
+                          wavelengths=('C', 'd', 'F'), default_device=DEV)
+    return tracer, specs, lens
+
+
+def test_double_gauss_1m_rays_exact_equals_oracle_on_device():
+    """Config-2 lens at ~1M rays: the exact policy is bit-identical to the oracle
+    evaluated by torch on the same GPU (IEEE sqrt/div there), masks included, and
+    the guarded policy has identical masks and values within tolerance."""
+    tracer, specs, lens = _double_gauss_problem(148)
+    args = tracer._ray_set(specs, lens)
+    exact = rt.trace_skew(*args, arith='exact')
+    ref = oracle.trace(*args)
+    for got, want in zip(exact, ref):
+        assert torch.equal(got, torch.broadcast_to(want, got.shape))
+    fast = rt.trace_skew(*args)
+    assert torch.equal(fast[4], exact[4]) and torch.equal(fast[5], exact[5])
+    scale = float(exact[1].abs().max())
+    assert float((fast[0] - exact[0]).abs().max()) <= POINT_TOL * scale
+    assert float((fast[1] - exact[1]).abs().max()) <= POINT_TOL * scale
+    assert float((fast[2] - exact[2]).abs().max()) <= COS_TOL
+    assert float((fast[3] - exact[3]).abs().max()) <= COS_TOL
+    assert bool(exact[4].all())                    # 100 % of rays pass this lens
+
+
+def test_double_gauss_4m_rays_fused_equals_split_and_shards_add_up():
+    """Config 2 at full size (16 fields x 3 wavelengths x 296^2 = 4.2M rays):
+    fused pass == trace + compute_rms2d + autograd (linearity of the deferred-seed
+    adjoint), and the moments of two pupil shards sum to the unsharded ones."""
+    tracer, specs, lens = _double_gauss_problem(296, requires_grad=True)
+    rms_f, field_f = tracer.spot_rms(specs, lens)
+    g_f = torch.autograd.grad(rms_f[0], [lens.c, lens.t, lens.nd])
+    out = tracer.trace_rays(specs, lens)
+    assert out[0].numel() == 16 * 3 * 296 * 296
+    rms_s, field_s = rt.compute_rms2d_all(out[1], out[4])
+    g_s = torch.autograd.grad(rms_s[0], [lens.c, lens.t, lens.nd])
+    assert abs(rms_f[0].item() - rms_s[0].item()) <= RMS_TOL * rms_s[0].item()
+    assert torch.allclose(field_f, field_s, rtol=1e-5)
+    for a, b in zip(g_f, g_s):
+        assert _rel(a.cpu().numpy(), b.cpu().numpy()) <= GRAD_TOL
+    args = tracer._ray_set(specs, lens)
+    whole, ref_y = ops.spot_moments(*args)
+    m0, r0 = ops.spot_moments(*args, shard=(0, 2))
+    m1, r1 = ops.spot_moments(*args, shard=(1, 2))
+    assert torch.equal(ref_y, r0) and torch.equal(ref_y, r1)
+    denom = whole.abs().amax(dim=(0, 1, 2)).clamp_min(1e-30)
+    assert float(((m0 + m1 - whole).abs().amax(dim=(0, 1, 2)) / denom).max()) <= 1e-5
+    assert float(whole[..., -1].sum()) == 16 * 3 * 296 * 296      # every ray counted once, all ok
+
+
+def test_empty_and_unsupported_inputs_fail_loudly():
+    from torchoptics_b200 import _native
+    rec = load_golden('cooke_8x8')
+    i = _inputs(rec, DEV)
+    with pytest.raises(NotImplementedError):
+        rt.trace_skew(*_args(i), aggregate=True)
+    bad = dict(i)
+    bad['x'] = i['x'].double()
+    with pytest.raises(TypeError):
+        rt.trace_skew(*_args(bad))
+    empty = dict(i)
+    empty['x'] = i['x'][:, :, :0]
+    empty['y'] = i['y'][:, :, :0]
+    out = rt.trace_skew(*_args(empty))          # empty ray set -> empty results, no launch
+    assert all(o.shape == (1, 3, 0, 3) for o in out)
+    with pytest.raises((ValueError, _native.NativeLibraryError)):
+        ops.spot_rms(*_args(empty))
+
+
+def test_batch_of_lenses_matches_single_lens_runs():
+    """B > 1: every lens of a batch gets the result of tracing it alone
+    (the reference's compute_rms2d only ever looks at lens 0, rtl:695)."""
+    recs = [load_golden('cooke_8x8'), load_golden('cooke_16x16_epd2.0')]
+    base = _inputs(recs[0], DEV)
+    scale = torch.tensor([1.0, 0.97, 1.05], device=DEV).reshape(3, 1, 1, 1, 1)
+    batch = dict(base)
+    batch['c'] = (base['c'] * scale).requires_grad_(True)
+    batch['t'] = base['t'].expand(3, -1, -1, -1, -1).contiguous().requires_grad_(True)
+    batch['mu'] = base['mu'].expand(3, -1, -1, -1, -1).contiguous()
+    batch['mask'] = base['mask'].expand(3, -1, -1, -1, -1).contiguous()
+    batch['z'] = base['z'].expand(3, -1, -1, -1).contiguous()
+    batch['cy'] = base['cy'].expand(3, -1, -1, -1).contiguous()
+    rms, _ = ops.spot_rms(*_args(batch))
+    gc, = torch.autograd.grad(rms.sum(), [batch['c']])
+    for b in range(3):
+        one = {k: (v[b:b + 1] if v.shape[0] == 3 else v) for k, v in batch.items()}
+        one['c'] = one['c'].detach().requires_grad_(True)
+        r1, _ = ops.spot_rms(*_args(one))
+        g1, = torch.autograd.grad(r1[0], [one['c']])
+        assert abs(r1[0].item() - rms[b].item()) <= 1e-6 * r1[0].item()
+        assert _rel(gc[b].cpu().numpy(), g1[0].cpu().numpy()) <= 1e-5

@@ -1,0 +1,99 @@
+"""Host-side mirror of the reference API (ray-set construction, paraxial optics,
+data model) against the golden records of the reference -- CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from torchoptics_b200 import lens_modeling as lm
+from torchoptics_b200 import prescriptions
+from torchoptics_b200 import ray_tracing_lite as rt
+
+
+def _lens_from(rec):
+    structure = lm.Structure(rec['stop_idx'], sequence=rec['sequence'], default_device='cpu')
+    lens = lm.Lens(structure, torch.from_numpy(rec['lens_c']), torch.from_numpy(rec['lens_t']),
+                   torch.from_numpy(rec['lens_nd']), torch.from_numpy(rec['lens_v']))
+    specs = lm.Specs(structure, torch.from_numpy(rec['epd']), torch.from_numpy(rec['hfov']))
+    return specs, lens
+
+
+def test_first_order_matches_reference(golden):
+    _, lens = _lens_from(golden)
+    efl, bfl = rt.get_first_order(lens)
+    assert np.allclose(efl.numpy(), golden['efl'], rtol=2e-6)
+    assert np.allclose(bfl.numpy(), golden['bfl'], rtol=2e-6)
+    assert np.allclose(lens.efl.numpy(), golden['efl'], rtol=2e-6)
+
+
+def test_ray_set_matches_reference(golden):
+    if 'aimed' in golden['name']:
+        pytest.skip('ray aiming traces rays: covered by the gpu tests')
+    specs, lens = _lens_from(golden)
+    tracer = rt.RayTracer(mode='circular', n_rays=tuple(int(v) for v in golden['n_rays']),
+                          rel_fields=tuple(float(v) for v in golden['rel_fields']),
+                          wavelengths=tuple(float(v) for v in golden['wavelengths']),
+                          default_device='cpu')
+    x, y, z, cx, cy, c, t, mu, mask = tracer._ray_set(specs, lens)
+    for got, key in ((x, 'in_x'), (y, 'in_y'), (cx, 'in_cx'), (cy, 'in_cy'), (c, 'in_c'), (t, 'in_t')):
+        assert got.shape == golden[key].shape, key
+        assert np.array_equal(got.numpy(), golden[key]), key
+    assert np.array_equal(mask.numpy(), golden['in_mask'])
+    assert np.allclose(z.numpy(), golden['in_z'], rtol=1e-6, atol=1e-7)
+    assert np.allclose(mu.numpy(), golden['in_mu'], rtol=1e-6)
+
+
+def test_yaml_loader_and_shipped_lenses():
+    for fn, efl in (('singlet_lens.yml', 17.156055), ('baseline_doublet.yml', 17.156054),
+                    ('baseline_cooke.yml', 17.156055), ('baseline_tessar.yml', 17.154451)):
+        specs, lens = prescriptions.load_yaml(fn, 'cpu')
+        assert abs(float(lens.efl[0]) - efl) < 1e-4
+        assert specs.epd.shape == (1,)
+    specs, lens = prescriptions.double_gauss('cpu')
+    assert lens.c.shape == (1, 11)
+    assert abs(float(lens.efl[0]) - 49.75) < 0.05
+    assert abs(float(lens.bfl[0]) - 28.749) < 0.05
+
+
+def test_compute_last_curvature_normalises_efl():
+    specs, lens = prescriptions.load_yaml('baseline_cooke.yml', 'cpu')
+    s = lens.structure
+    c = rt.compute_last_curvature(s, lens.flat_c_but_last, lens.flat_t, lens.flat_nd)
+    assert abs(float(c[-1]) - (-1.6177329)) < 2e-5
+    solved = lm.Lens(s, c, lens.flat_t, lens.flat_nd, lens.flat_v)
+    assert abs(float(solved.efl[0]) - 1.0) < 1e-5
+
+
+def test_structure_slicing_and_up_to_stop():
+    s = lm.Structure(np.array([4, 2]), sequence=np.array(['GAGAAGA', 'GAGA']), default_device='cpu')
+    assert s.mask.shape == (2, 7) and s.mask[1].sum() == 4
+    front = s.up_to_stop()
+    assert front.mask.shape == (2, 4)
+    assert front.mask[0].all() and front.mask[1].tolist() == [True, True, False, False]
+    assert s[1].mask.shape == (1, 4)
+    assert s.last_g_idx.tolist() == [5, 2]
+
+
+def test_glass_round_trip():
+    n = torch.tensor([1.5168, 1.7552])
+    v = torch.tensor([64.17, 27.51])
+    n2, v2 = lm.n_v_from_g(lm.g_from_n_v(n, v))
+    assert torch.allclose(n, n2, atol=1e-5) and torch.allclose(v, v2, atol=1e-3)
+
+
+def test_pupil_samplers_shapes():
+    x, y = rt.circle(None, 4, 6, 'cpu')
+    assert x.shape == (1, 1, 24, 1) and float(x[0, 0, 0, 0]) == 0.0
+    x, y = rt.tee(None, 'cpu')
+    assert y.flatten().tolist() == [-1., 1., 0.]
+    x, y = rt.circle_pseudo_random(torch.zeros(2, 1, 1, 1), 3, 5, device='cpu')
+    assert x.shape == (2, 1, 15, 1) and float((x ** 2 + y ** 2).max()) <= 1.0 + 1e-6
+    x, y = rt.circle_outer_edge_uniform(None, 8, 'cpu')
+    assert torch.allclose(x ** 2 + y ** 2, torch.ones_like(x), atol=1e-6)
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    from torchoptics_b200 import _native
+    specs, lens = prescriptions.load_yaml('baseline_cooke.yml', 'cpu')
+    tracer = rt.RayTracer(mode='circular', n_rays=(4, 4), default_device='cpu')
+    with pytest.raises(_native.NativeLibraryError):
+        tracer.trace_rays(specs, lens)

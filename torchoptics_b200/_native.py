@@ -1,0 +1,132 @@
+"""ctypes binding of ``libtorchoptics_b200.so`` (C ABI: include/torchoptics_b200.h).
+
+There is no fallback: if the library has not been built, or a call fails, this
+module raises.  Torch is used here only to hand over device pointers and the
+current CUDA stream.
+"""
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, 'libtorchoptics_b200.so')
+
+ARITH_GUARDED = 0
+ARITH_EXACT = 1
+MAX_SURFACES_FWD = 256
+MAX_SURFACES_BWD = 32
+MAX_SURFACES_SPOT = 16
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+class TlStrided(ctypes.Structure):
+    _fields_ = [('ptr', ctypes.c_void_p), ('stride', ctypes.c_int64 * 4)]
+
+
+class TlProblem(ctypes.Structure):
+    _fields_ = [('x', TlStrided), ('y', TlStrided), ('z', TlStrided), ('cx', TlStrided),
+                ('cy', TlStrided),
+                ('c', ctypes.c_void_p), ('t', ctypes.c_void_p), ('mu', ctypes.c_void_p),
+                ('live', ctypes.c_void_p),
+                ('B', ctypes.c_int32), ('F', ctypes.c_int32), ('P', ctypes.c_int32),
+                ('W', ctypes.c_int32), ('S', ctypes.c_int32),
+                ('allow_backward_rays', ctypes.c_int32), ('arith', ctypes.c_int32),
+                ('p_begin', ctypes.c_int32), ('p_end', ctypes.c_int32)]
+
+
+class TlTraceOut(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ('x', 'y', 'cx', 'cy', 'ok', 'backward')]
+
+
+class TlSeeds(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ('gx', 'gy', 'gcx', 'gcy')]
+
+
+class TlGrads(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ('gc', 'gt', 'gmu', 'gz_sum', 'gx', 'gy', 'gz', 'gcx', 'gcy')]
+
+
+class TlSpotOut(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ('rms', 'rms_field', 'gc', 'gt', 'gmu', 'gz')]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    'tl_abi_version': (ctypes.c_int, []),
+    'tl_last_error': (ctypes.c_char_p, []),
+    'tl_launch_count': (ctypes.c_int64, []),
+    'tl_trace_fwd': (ctypes.c_int, [ctypes.POINTER(TlProblem), ctypes.POINTER(TlTraceOut), ctypes.c_void_p]),
+    'tl_trace_bwd_workspace': (ctypes.c_size_t, [ctypes.POINTER(TlProblem)]),
+    'tl_trace_bwd': (ctypes.c_int, [ctypes.POINTER(TlProblem), ctypes.POINTER(TlSeeds),
+                                    ctypes.POINTER(TlGrads), ctypes.c_void_p, ctypes.c_size_t,
+                                    ctypes.c_void_p]),
+    'tl_rms_workspace': (ctypes.c_size_t, [ctypes.c_int32] * 4),
+    'tl_rms_fwd': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int32] * 4 +
+                   [ctypes.c_void_p] * 4 + [ctypes.c_size_t, ctypes.c_void_p]),
+    'tl_rms_bwd': (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int32] * 4 +
+                   [ctypes.c_void_p, ctypes.c_void_p]),
+    'tl_spot_moment_count': (ctypes.c_int32, [ctypes.c_int32, ctypes.c_int32]),
+    'tl_spot_workspace': (ctypes.c_size_t, [ctypes.POINTER(TlProblem), ctypes.c_int32]),
+    'tl_spot_accumulate': (ctypes.c_int, [ctypes.POINTER(TlProblem), ctypes.c_int32, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                          ctypes.c_void_p]),
+    'tl_spot_finalize': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int32] * 4 +
+                         [ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(TlSpotOut), ctypes.c_void_p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and declare every export of the header."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f'{LIB_PATH} is missing: build it with `python -m torchoptics_b200.build` '
+            '(or __graft_entry__.build()).  torchoptics_b200 has no CPU or eager fallback.')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in EXPORTS.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.tl_abi_version() != 1:
+        raise NativeLibraryError('libtorchoptics_b200.so: ABI version mismatch, rebuild it')
+    _lib = lib
+    return lib
+
+
+def check(code, what):
+    if code != 0:
+        msg = load().tl_last_error().decode(errors='replace')
+        raise NativeLibraryError(f'{what} failed ({code}): {msg}')
+
+
+def launch_count():
+    return int(load().tl_launch_count())
+
+
+def stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise NativeLibraryError(
+            f'{name} is on {t.device}: the ray-trace kernels run on CUDA devices only '
+            '(there is no CPU path; use the oracle under oracle/ for CPU checks)')
+
+
+def strided(t, shape):
+    """Broadcast view of ``t`` over ``shape`` as (pointer, element strides)."""
+    v = torch.broadcast_to(t, shape)
+    s = TlStrided()
+    s.ptr = v.data_ptr()
+    for i, st in enumerate(v.stride()):
+        s.stride[i] = st
+    return s

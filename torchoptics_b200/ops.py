@@ -1,0 +1,320 @@
+"""torch.autograd front end of the CUDA hot path.
+
+Three differentiable operators, each a thin shim that lays out pointers for the
+C ABI (include/torchoptics_b200.h) and launches on the current CUDA stream:
+
+* :func:`trace`     -- ``trace_skew``            (reference rtl:594-675)
+* :func:`spot_rms_from_rays` -- ``compute_rms2d`` (rtl:678-702), every lens
+* :func:`spot_rms`  -- both fused, forward and backward in ONE pass over the rays
+
+rtl = /root/reference/torchlens/ray_tracing_lite.py.  No CPU path exists.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _native as nat
+
+_GRAD_PER_RAY = ('x', 'y', 'z', 'cx', 'cy')
+
+
+class _Layout:
+    """Shapes and flat device views of one trace_skew argument set."""
+
+    def __init__(self, x, y, z, cx, cy, c, t, mu, mask):
+        for name, v in (('x', x), ('y', y), ('z', z), ('cx', cx), ('cy', cy), ('c', c), ('t', t),
+                        ('mu', mu), ('mask', mask)):
+            nat.require_cuda(v, name)
+            if name != 'mask' and v.dtype != torch.float32:
+                raise TypeError(f'{name} must be float32 (got {v.dtype}); the kernels compute in fp32')
+        for name, v in (('x', x), ('y', y), ('z', z), ('cx', cx), ('cy', cy)):
+            if v.dim() != 4:
+                raise ValueError(f'{name} must be 4-D [B,F,P,W]-broadcastable, got {tuple(v.shape)}')
+        for name, v in (('c', c), ('t', t), ('mu', mu), ('mask', mask)):
+            if v.dim() != 5:
+                raise ValueError(f'{name} must be 5-D [B,1,1,W|1,S], got {tuple(v.shape)}')
+        S = t.shape[-1]
+        if not (c.shape[-1] == S and mu.shape[-1] == S and mask.shape[-1] == S):
+            raise ValueError('c, t, mu and mask must agree on the number of surfaces')
+        full = torch.broadcast_shapes(x.shape, y.shape, z.shape, cx.shape, cy.shape, c.shape[:-1],
+                                      t.shape[:-1], mu.shape[:-1], mask.shape[:-1])
+        B, F, P, W = full
+        for name, v in (('c', c), ('t', t), ('mask', mask)):
+            if v.shape[1] != 1 or v.shape[2] != 1 or v.shape[3] != 1:
+                raise ValueError(f'{name} must have shape [B|1,1,1,1,S], got {tuple(v.shape)}')
+        if mu.shape[1] != 1 or mu.shape[2] != 1:
+            raise ValueError(f'mu must have shape [B|1,1,1,W|1,S], got {tuple(mu.shape)}')
+        self.B, self.F, self.P, self.W, self.S = B, F, P, W, S
+        self.shape = (B, F, P, W)
+        self.device = y.device
+        # tiny per-lens tables, contiguous
+        self.c2 = torch.broadcast_to(c.detach(), (B, 1, 1, 1, S)).reshape(B, S).contiguous()
+        self.t2 = torch.broadcast_to(t.detach(), (B, 1, 1, 1, S)).reshape(B, S).contiguous()
+        self.mu3 = torch.broadcast_to(mu.detach(), (B, 1, 1, W, S)).reshape(B, W, S).contiguous()
+        self.live = torch.broadcast_to(mask, (B, 1, 1, 1, S)).reshape(B, S).to(torch.uint8).contiguous()
+        self.rays = [v.detach() for v in (x, y, z, cx, cy)]
+
+    def problem(self, allow_backward_rays, arith, p_begin=0, p_end=None):
+        pb = nat.TlProblem()
+        for name, v in zip(_GRAD_PER_RAY, self.rays):
+            setattr(pb, name, nat.strided(v, self.shape))
+        pb.c = self.c2.data_ptr()
+        pb.t = self.t2.data_ptr()
+        pb.mu = self.mu3.data_ptr()
+        pb.live = self.live.data_ptr()
+        pb.B, pb.F, pb.P, pb.W, pb.S = self.B, self.F, self.P, self.W, self.S
+        pb.allow_backward_rays = int(bool(allow_backward_rays))
+        pb.arith = int(arith)
+        pb.p_begin = int(p_begin)
+        pb.p_end = int(self.P if p_end is None else p_end)
+        return pb
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class _TraceSkew(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays, arith):
+        lay = _Layout(x, y, z, cx, cy, c, t, mu, mask)
+        if lay.S > nat.MAX_SURFACES_FWD:
+            raise ValueError(f'at most {nat.MAX_SURFACES_FWD} surfaces are supported')
+        lib = nat.load()
+        with torch.cuda.device(lay.device):
+            outs = [torch.empty(lay.shape, dtype=torch.float32, device=lay.device) for _ in range(4)]
+            ok = torch.empty(lay.shape, dtype=torch.bool, device=lay.device)
+            backward = torch.empty(lay.shape, dtype=torch.bool, device=lay.device)
+            pb = lay.problem(allow_backward_rays, arith)
+            out = nat.TlTraceOut(*[o.data_ptr() for o in outs], ok.data_ptr(), backward.data_ptr())
+            nat.check(lib.tl_trace_fwd(ctypes.byref(pb), ctypes.byref(out), nat.stream_ptr(lay.device)),
+                      'tl_trace_fwd')
+        ctx.save_for_backward(x, y, z, cx, cy, c, t, mu, mask)
+        ctx.flags = (allow_backward_rays, arith)
+        ctx.mark_non_differentiable(ok, backward)
+        return (*outs, ok, backward)
+
+    @staticmethod
+    def backward(ctx, gx, gy, gcx, gcy, _gok, _gbw):
+        x, y, z, cx, cy, c, t, mu, mask = ctx.saved_tensors
+        allow_backward_rays, arith = ctx.flags
+        lay = _Layout(x, y, z, cx, cy, c, t, mu, mask)
+        if lay.S > nat.MAX_SURFACES_BWD:
+            raise ValueError(f'backward supports at most {nat.MAX_SURFACES_BWD} surfaces')
+        lib = nat.load()
+        dev = lay.device
+        need = ctx.needs_input_grad
+        with torch.cuda.device(dev):
+            seeds = [None if g is None else g.to(torch.float32).expand(lay.shape).contiguous()
+                     for g in (gx, gy, gcx, gcy)]
+            gc = torch.empty((lay.B, lay.S), dtype=torch.float32, device=dev)
+            gt = torch.empty_like(gc)
+            gmu = torch.empty((lay.B, lay.W, lay.S), dtype=torch.float32, device=dev)
+            gz_sum = torch.empty((lay.B,), dtype=torch.float32, device=dev)
+            z_per_lens = z.numel() == z.shape[0]      # [B|1,1,1,1]
+            per_ray = {}
+            for i, name in enumerate(_GRAD_PER_RAY):
+                if need[i] and not (name == 'z' and z_per_lens):
+                    per_ray[name] = torch.empty(lay.shape, dtype=torch.float32, device=dev)
+            pb = lay.problem(allow_backward_rays, arith)
+            sd = nat.TlSeeds(*[_ptr(s) for s in seeds])
+            gr = nat.TlGrads(gc.data_ptr(), gt.data_ptr(), gmu.data_ptr(), gz_sum.data_ptr(),
+                             *[_ptr(per_ray.get(n)) for n in _GRAD_PER_RAY])
+            ws_bytes = lib.tl_trace_bwd_workspace(ctypes.byref(pb))
+            if ws_bytes == 0:
+                nat.check(-1, 'tl_trace_bwd_workspace')
+            ws = torch.empty((ws_bytes // 8,), dtype=torch.float64, device=dev)
+            nat.check(lib.tl_trace_bwd(ctypes.byref(pb), ctypes.byref(sd), ctypes.byref(gr),
+                                       ws.data_ptr(), ws_bytes, nat.stream_ptr(dev)), 'tl_trace_bwd')
+        grads = []
+        for i, (name, v) in enumerate(zip(_GRAD_PER_RAY, (x, y, z, cx, cy))):
+            if not need[i]:
+                grads.append(None)
+            elif name == 'z' and z_per_lens:
+                g = gz_sum.reshape(lay.B, 1, 1, 1)
+                grads.append(g.sum_to_size(z.shape))
+            else:
+                grads.append(per_ray[name].sum_to_size(v.shape))
+        grads.append(gc.reshape(lay.B, 1, 1, 1, lay.S).sum_to_size(c.shape) if need[5] else None)
+        grads.append(gt.reshape(lay.B, 1, 1, 1, lay.S).sum_to_size(t.shape) if need[6] else None)
+        grads.append(gmu.reshape(lay.B, 1, 1, lay.W, lay.S).sum_to_size(mu.shape) if need[7] else None)
+        return (*grads, None, None, None)
+
+
+def trace(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arith=nat.ARITH_GUARDED):
+    """CUDA ``trace_skew``: returns (x, y, cx, cy, ray_ok, ray_backward), all [B,F,P,W]."""
+    full = torch.broadcast_shapes(x.shape, y.shape, z.shape, cx.shape, cy.shape, c.shape[:-1],
+                                  t.shape[:-1], mu.shape[:-1], mask.shape[:-1])
+    if 0 in full:       # empty ray set: nothing to launch, same (empty) results as the reference
+        for name, v in (('x', x), ('y', y)):
+            nat.require_cuda(v, name)
+        zero = (x.sum() + y.sum() + z.sum() + cx.sum() + cy.sum() + c.sum() + t.sum() + mu.sum()) * 0
+        outs = [zero.expand(full).clone() for _ in range(4)]
+        flags = [torch.zeros(full, dtype=torch.bool, device=y.device) for _ in range(2)]
+        flags[0] = ~flags[0]
+        return (*outs, *flags)
+    return _TraceSkew.apply(x, y, z, cx, cy, c, t, mu, mask, bool(allow_backward_rays), int(arith))
+
+
+class _RmsFromRays(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, ray_ok):
+        nat.require_cuda(y, 'y')
+        nat.require_cuda(ray_ok, 'ray_ok')
+        if y.dim() != 4 or y.dtype != torch.float32:
+            raise ValueError('y must be a float32 [B,F,P,W] tensor')
+        B, F, P, W = y.shape
+        lib = nat.load()
+        dev = y.device
+        with torch.cuda.device(dev):
+            yc = y.detach().contiguous()
+            okc = torch.broadcast_to(ray_ok, y.shape).to(torch.uint8).contiguous()
+            rms = torch.empty((B,), dtype=torch.float32, device=dev)
+            rms_field = torch.empty((B, F), dtype=torch.float32, device=dev)
+            stats = torch.empty((B, F, 4), dtype=torch.float64, device=dev)
+            ws_bytes = lib.tl_rms_workspace(B, F, P, W)
+            ws = torch.empty((ws_bytes // 8,), dtype=torch.float64, device=dev)
+            nat.check(lib.tl_rms_fwd(yc.data_ptr(), okc.data_ptr(), B, F, P, W, rms.data_ptr(),
+                                     rms_field.data_ptr(), stats.data_ptr(), ws.data_ptr(), ws_bytes,
+                                     nat.stream_ptr(dev)), 'tl_rms_fwd')
+        ctx.save_for_backward(yc, okc, stats)
+        ctx.mark_non_differentiable(rms_field)
+        return rms, rms_field
+
+    @staticmethod
+    def backward(ctx, grad_rms, _grad_field):
+        yc, okc, stats = ctx.saved_tensors
+        B, F, P, W = yc.shape
+        lib = nat.load()
+        dev = yc.device
+        with torch.cuda.device(dev):
+            g = grad_rms.to(torch.float32).contiguous()
+            gy = torch.empty_like(yc)
+            nat.check(lib.tl_rms_bwd(yc.data_ptr(), okc.data_ptr(), stats.data_ptr(), g.data_ptr(),
+                                     B, F, P, W, gy.data_ptr(), nat.stream_ptr(dev)), 'tl_rms_bwd')
+        return gy, None
+
+
+def spot_rms_from_rays(y, ray_ok):
+    """Per-lens mean-over-fields y-RMS spot size of already traced rays:
+    returns (rms [B], rms_field [B,F])."""
+    return _RmsFromRays.apply(y, ray_ok)
+
+
+def pupil_slice(n_pupil, rank, world):
+    """Contiguous slice [begin, end) of the pupil axis traced by ``rank`` of ``world``."""
+    if not 0 <= rank < world:
+        raise ValueError(f'rank {rank} outside world of {world}')
+    return (n_pupil * rank) // world, (n_pupil * (rank + 1)) // world
+
+
+def reduce_moments(moments, group=None):
+    """The one data-path collective of the sharded spot pass: per-(lens, field,
+    wavelength) sums are additive over pupil slices -> SUM all-reduce (fp64,
+    a few KB; NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+    torch.distributed.all_reduce(moments, op=torch.distributed.ReduceOp.SUM, group=group)
+    return moments
+
+
+def _accumulate(lay, allow_backward_rays, arith, want_grad, p_begin, p_end):
+    lib = nat.load()
+    dev = lay.device
+    n_acc = lib.tl_spot_moment_count(lay.S, int(want_grad))
+    moments = torch.empty((lay.B, lay.F, lay.W, n_acc), dtype=torch.float64, device=dev)
+    ref_y = torch.empty((lay.B, lay.F), dtype=torch.float32, device=dev)
+    pb = lay.problem(allow_backward_rays, arith, p_begin, p_end)
+    ws_bytes = lib.tl_spot_workspace(ctypes.byref(pb), int(want_grad))
+    if ws_bytes == 0:
+        nat.check(-1, 'tl_spot_workspace')
+    ws = torch.empty((ws_bytes // 8,), dtype=torch.float64, device=dev)
+    nat.check(lib.tl_spot_accumulate(ctypes.byref(pb), int(want_grad), moments.data_ptr(),
+                                     ref_y.data_ptr(), ws.data_ptr(), ws_bytes, nat.stream_ptr(dev)),
+              'tl_spot_accumulate')
+    return moments, ref_y
+
+
+def spot_moments(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arith=nat.ARITH_GUARDED,
+                 want_grad=True, shard=(0, 1)):
+    """Raw additive sums of one pupil slice (no autograd): (moments [B,F,W,n], ref_y [B,F])."""
+    lay = _Layout(x, y, z, cx, cy, c, t, mu, mask)
+    p_begin, p_end = pupil_slice(lay.P, *shard)
+    with torch.cuda.device(lay.device):
+        return _accumulate(lay, allow_backward_rays, arith, want_grad, p_begin, p_end)
+
+
+class _SpotRms(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays, arith, shard, group):
+        if any(ctx.needs_input_grad[i] for i in (0, 1, 3, 4)):
+            raise ValueError('the fused spot pass differentiates w.r.t. z, c, t and mu only; '
+                             'use trace() + spot_rms_from_rays() for gradients of x, y, cx, cy')
+        lay = _Layout(x, y, z, cx, cy, c, t, mu, mask)
+        if z.numel() != z.shape[0]:
+            raise ValueError('the fused spot pass needs a per-lens pupil position z of shape [B,1,1,1]')
+        want_grad = any(ctx.needs_input_grad[i] for i in (2, 5, 6, 7))
+        limit = nat.MAX_SURFACES_SPOT if want_grad else nat.MAX_SURFACES_FWD
+        if lay.S > limit:
+            raise ValueError(f'the fused spot pass supports at most {limit} surfaces '
+                             f'({"with" if want_grad else "without"} gradients)')
+        lib = nat.load()
+        dev = lay.device
+        rank, world = shard
+        p_begin, p_end = pupil_slice(lay.P, rank, world)
+        if p_end <= p_begin:
+            raise ValueError(f'pupil axis ({lay.P}) is too short to shard over {world} ranks')
+        with torch.cuda.device(dev):
+            moments, ref_y = _accumulate(lay, allow_backward_rays, arith, want_grad, p_begin, p_end)
+            stream = nat.stream_ptr(dev)
+            if world > 1:
+                reduce_moments(moments, group)
+            rms = torch.empty((lay.B,), dtype=torch.float32, device=dev)
+            rms_field = torch.empty((lay.B, lay.F), dtype=torch.float32, device=dev)
+            if want_grad:
+                gc = torch.empty((lay.B, lay.S), dtype=torch.float32, device=dev)
+                gt = torch.empty_like(gc)
+                gmu = torch.empty((lay.B, lay.W, lay.S), dtype=torch.float32, device=dev)
+                gz = torch.empty((lay.B,), dtype=torch.float32, device=dev)
+                out = nat.TlSpotOut(rms.data_ptr(), rms_field.data_ptr(), gc.data_ptr(), gt.data_ptr(),
+                                    gmu.data_ptr(), gz.data_ptr())
+            else:
+                out = nat.TlSpotOut(rms.data_ptr(), rms_field.data_ptr(), None, None, None, None)
+            nat.check(lib.tl_spot_finalize(moments.data_ptr(), ref_y.data_ptr(), lay.B, lay.F, lay.W,
+                                           lay.S, lay.P, int(want_grad), ctypes.byref(out), stream),
+                      'tl_spot_finalize')
+        if want_grad:
+            ctx.save_for_backward(gc, gt, gmu, gz)
+        ctx.meta = (lay.B, lay.W, lay.S, z.shape, c.shape, t.shape, mu.shape)
+        ctx.mark_non_differentiable(rms_field)
+        return rms, rms_field
+
+    @staticmethod
+    def backward(ctx, grad_rms, _grad_field):
+        gc, gt, gmu, gz = ctx.saved_tensors
+        B, W, S, z_shape, c_shape, t_shape, mu_shape = ctx.meta
+        need = ctx.needs_input_grad
+        g = grad_rms.to(torch.float32).reshape(B)
+        out = [None] * 13
+        if need[2]:
+            out[2] = (gz * g).reshape(B, 1, 1, 1).sum_to_size(z_shape)
+        if need[5]:
+            out[5] = (gc * g[:, None]).reshape(B, 1, 1, 1, S).sum_to_size(c_shape)
+        if need[6]:
+            out[6] = (gt * g[:, None]).reshape(B, 1, 1, 1, S).sum_to_size(t_shape)
+        if need[7]:
+            out[7] = (gmu * g[:, None, None]).reshape(B, 1, 1, W, S).sum_to_size(mu_shape)
+        return tuple(out)
+
+
+def spot_rms(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arith=nat.ARITH_GUARDED,
+             shard=(0, 1), group=None):
+    """Fused ``trace_skew`` -> ``compute_rms2d`` (and, when any of z, c, t, mu
+    requires grad, its backward) in one pass over the rays.
+
+    ``shard=(rank, world)`` traces only this rank's slice of the pupil axis and
+    all-reduces the per-field sums over ``group``; every rank returns the same
+    (rms [B], rms_field [B,F]) and, after ``.backward()``, the same gradients.
+    """
+    return _SpotRms.apply(x, y, z, cx, cy, c, t, mu, mask, bool(allow_backward_rays), int(arith),
+                          (int(shard[0]), int(shard[1])), group)

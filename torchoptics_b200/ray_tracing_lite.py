@@ -1,0 +1,390 @@
+"""Sequential ray tracing of batched lenses -- host side of the CUDA hot path.
+
+Drop-in for the reference module ``torchlens/ray_tracing_lite.py`` ("rtl"): the
+same public names, arguments and tensor conventions
+
+    dim 0 lenses (B), dim 1 fields (F), dim 2 pupil points (P), dim 3 wavelengths (W),
+    dim 4 surfaces (S)                                                      rtl:4-9
+
+but :func:`trace_skew` (rtl:594-675) and :func:`compute_rms2d` (rtl:678-702) run as
+hand-written sm_100a kernels behind ``torchoptics_b200.ops``; this file only
+prepares their (tiny) inputs: refractive-index ratios, paraxial pupil position,
+pupil grids and field angles.  ``RayTracer.spot_rms`` is the fused
+trace -> RMS -> gradient pass that the reference spells as
+``trace_rays`` + ``compute_rms2d`` + ``.backward()``.
+
+Only CUDA tensors are accepted by the traced functions (no CPU path).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import ops
+from .lens_modeling import mask_replace  # noqa: F401  (re-exported like the reference, rtl:18)
+
+WAVELENGTH_ALIASES = {'C': 656.3, 'd': 587.6, 'F': 486.1}   # rtl:71-75
+
+
+# ---------------------------------------------------------------------------
+# Pupil samplers.  Each returns (x, y) in relative pupil units, shape [1|n,1,P,1].
+# ---------------------------------------------------------------------------
+def tee(tensor=None, device='cuda'):
+    """Lower / upper meridional and one sagittal ray (rtl:353-360)."""
+    y = torch.tensor([-1., 1., 0.], device=device).reshape(1, 1, 3, 1)
+    x = torch.tensor([0., 0., 1.], device=device).reshape(1, 1, 3, 1)
+    return x, y
+
+
+def chief(tensor=None, n_rays=None, device='cuda'):
+    """The pupil-centre ray (rt_tf:378-385)."""
+    zero = torch.zeros((1, 1, 1, 1), device=device)
+    return zero, zero.clone()
+
+
+def meridional_uniform(tensor, n_rays, device='cuda'):
+    """``n_rays`` equidistant points on the pupil's y axis (rt_tf:358-365)."""
+    y = torch.linspace(-1., 1., n_rays, device=device).reshape(1, 1, -1, 1)
+    return torch.zeros_like(y), y
+
+
+def sagittal_uniform(tensor, n_rays, device='cuda'):
+    """``n_rays`` equidistant points on the pupil's x axis (rt_tf:368-375)."""
+    x = torch.linspace(-1., 1., n_rays, device=device).reshape(1, 1, -1, 1)
+    return x, torch.zeros_like(x)
+
+
+def circle(tensor, n_r, n_theta, default_device='cuda'):
+    """Polar grid: radii i/n_r (the first ring is the centre), angles 2 pi j/n_theta,
+    ring-major (rtl:412-422).  Built in fp32 exactly like the reference so that the
+    pupil points are bit-identical."""
+    radius = torch.from_numpy(np.linspace(0, 1.0, n_r, endpoint=False, dtype=np.float32))
+    angle = torch.from_numpy(np.linspace(0, 2 * np.pi, n_theta, endpoint=False, dtype=np.float32))
+    radius = radius.to(default_device)[:, None]
+    angle = angle.to(default_device)[None, :]
+    x = radius * torch.cos(angle)
+    y = radius * torch.sin(angle)
+    return x.reshape(1, 1, n_r * n_theta, 1), y.reshape(1, 1, n_r * n_theta, 1)
+
+
+def circle_pseudo_random(tensor, n_r, n_theta, device='cuda'):
+    """Jittered equal-area polar cells, one independent draw per element of
+    ``tensor`` (rtl:393-410)."""
+    n_sets = int(np.prod(tensor.shape))
+    jitter_r2 = torch.rand((n_sets, n_r, n_theta)) / n_r
+    jitter_angle = torch.rand((n_sets, n_r, n_theta)) / n_theta
+    r2_start = torch.from_numpy(np.linspace(0, 1, n_r, endpoint=False, dtype=np.float32))[None, :, None]
+    angle_start = torch.from_numpy(np.linspace(0, 1, n_theta, endpoint=False, dtype=np.float32))[None, None, :]
+    radius = torch.sqrt(jitter_r2 + r2_start)
+    angle = (jitter_angle + angle_start) * 2 * np.pi
+    x = (radius * torch.cos(angle)).reshape(n_sets, 1, n_r * n_theta, 1)
+    y = (radius * torch.sin(angle)).reshape(n_sets, 1, n_r * n_theta, 1)
+    return x.to(device), y.to(device)
+
+
+def circle_outer_edge_uniform(tensor, n_rays, device='cuda'):
+    """``n_rays`` points on the pupil rim (rt_tf:468-476)."""
+    angle = torch.arange(n_rays, dtype=torch.float32, device=device) * (2 * math.pi / n_rays)
+    return torch.cos(angle).reshape(1, 1, -1, 1), torch.sin(angle).reshape(1, 1, -1, 1)
+
+
+def apply_vignetting(y, vig_up, vig_down):
+    """Squeeze relative pupil coordinates by the vignetting factors (rt_tf:479-490)."""
+    vig_up = vig_up[..., None, None]
+    vig_down = vig_down[..., None, None]
+    return y * (1 - (vig_up + vig_down) / 2) + (vig_down - vig_up) / 2
+
+
+def scale_to_epd(y, epd):
+    """Relative pupil coordinate -> length units: y * EPD / 2 (rtl:497-507)."""
+    return y * epd.reshape(-1, *([1] * (y.dim() - 1))) / 2
+
+
+# ---------------------------------------------------------------------------
+# Paraxial optics (per-lens scalars, plain torch)
+# ---------------------------------------------------------------------------
+def interface_propagation_abcd(c, t, n):
+    """ABCD matrix of 'refract at curvature c, then travel t' for every surface:
+    [[1 + t C, t D], [C, D]] with D = n/n', C = c (D - 1).  c, t: [B,S]; n: [B,S+1].
+    Returns [B,S,2,2] (rtl:314-327)."""
+    assert n.shape[-1] - 1 == c.shape[-1] == t.shape[-1]
+    ratio = n[:, :-1] / n[:, 1:]
+    power = c * (ratio - 1)
+    rows = torch.stack((1 + power * t, ratio * t, power, ratio), dim=-1)
+    return rows.reshape(n.shape[0], -1, 2, 2)
+
+
+def reduce_abcd(abcd):
+    """Ordered product M_{S-1} ... M_1 M_0 of [B,S,2,2] matrices -> [B,2,2], by
+    pairwise (log-depth) multiplication (rtl:301-311)."""
+    while abcd.shape[1] > 1:
+        n_pairs = abcd.shape[1] // 2
+        paired = abcd[:, 1:2 * n_pairs:2] @ abcd[:, 0:2 * n_pairs:2]
+        abcd = paired if abcd.shape[1] % 2 == 0 else torch.cat((paired, abcd[:, -1:]), dim=1)
+    return abcd[:, 0]
+
+
+def compute_pupil_position(lens):
+    """Paraxial entrance-pupil position relative to the first vertex: B/A of the
+    system in front of the stop (rtl:330-350).  Differentiable w.r.t. the lens."""
+    front = lens.up_to_stop()
+    if front.structure.mask.shape[1] == 0:
+        return torch.zeros(len(front), device=lens.c.device)
+    nd = torch.cat((torch.ones_like(front.nd[:, 0:1]), front.nd), dim=1)
+    system = reduce_abcd(interface_propagation_abcd(front.c, front.t, nd))
+    return system[:, 0, 1] / system[:, 0, 0]
+
+
+def get_first_order(lens):
+    """(EFL, BFL) of every lens (rtl:772-794)."""
+    nd = torch.cat((torch.ones_like(lens.nd[:, 0:1]), lens.nd), dim=1)
+    last = lens.structure.mask_torch.sum(dim=1) - 1
+    t = lens.t.clone()
+    t[torch.arange(len(lens), device=t.device), last] = 0.
+    system = reduce_abcd(interface_propagation_abcd(lens.c, t, nd))
+    return -1 / system[:, 1, 0], -system[:, 0, 0] / system[:, 1, 0]
+
+
+def extraction_from_indices(params, indices):
+    """``params[i, j]`` for the single (i, j) row of ``indices`` (rtl:705-722)."""
+    assert indices.dim() == 2 and indices.shape == (1, 2)
+    assert params.dim() == 2 and params.shape[0] == 1
+    indices = indices.long()
+    return params[indices[:, 0], indices[:, 1]]
+
+
+def compute_last_curvature(structures, c, t, nd):
+    """Compact curvatures with the last free curvature solved so that EFL = 1
+    (rtl:725-769).  ``c`` holds every curvature but the last surface's; a trailing
+    air-air surface (e.g. a cover-glass back) keeps curvature as given and the
+    solve moves one surface forward."""
+    device = structures.mask_torch.device
+    mask = structures.mask_torch
+    B = mask.shape[0]
+    rows = torch.arange(B, device=device)
+    n_surf = mask.sum(dim=1)
+    ends_air_air = ~structures.mask_G_torch[rows, n_surf - 2]
+    solve_at = n_surf - 1 - ends_air_air.long()
+    given = mask.clone()
+    given[rows, n_surf - 1] = False
+    c2d = mask_replace(given.cpu().numpy(), torch.zeros(mask.shape, dtype=torch.float32, device=device), c)
+    t2d = mask_replace(structures.mask, torch.zeros(mask.shape, dtype=torch.float32, device=device), t)
+    n2d = mask_replace(structures.mask_G, torch.ones(mask.shape, dtype=torch.float32, device=device), nd)
+    n2d = torch.cat((torch.ones_like(n2d[:, 0:1]), n2d), dim=1)
+    ahead = given.clone()
+    ahead[rows, solve_at] = False
+    abcd = interface_propagation_abcd(c2d, t2d, n2d)
+    eye = torch.eye(2, device=device).expand_as(abcd)
+    system = reduce_abcd(torch.where(ahead[..., None, None], abcd, eye))
+    n_after = n2d[rows, solve_at]
+    solved = -(1 + n_after * system[:, 1, 0]) / (system[:, 0, 0] * (n_after - 1))
+    c2d = c2d.clone()
+    c2d[rows, solve_at] = solved
+    return c2d[mask]
+
+
+def compute_magnification(lens):
+    """Paraxial pupil magnification of the system in front of the stop
+    (rt_tf:765-777): stop height per unit entrance-pupil height."""
+    if lens.structure.mask.shape[1] == 0:
+        return torch.ones(len(lens), device=lens.c.device)
+    nd = torch.cat((torch.ones_like(lens.nd[:, 0:1]), lens.nd), dim=1)
+    system = reduce_abcd(interface_propagation_abcd(lens.c, lens.t, nd))
+    return 1 / system[:, 1, 1]
+
+
+# ---------------------------------------------------------------------------
+# The hot path
+# ---------------------------------------------------------------------------
+def trace_skew(x, y, z, cx, cy, c, t, mu, mask, aggregate=False, allow_backward_rays=True,
+               arith=None):
+    """Trace rays from the entrance pupil to the image plane (rtl:594-675).
+
+    Inputs broadcast to [B,F,P,W] (c, t, mask: [B,1,1,1,S]; mu: [B,1,1,W,S]).
+    Returns ``(x, y, cx, cy, ray_ok, ray_backward)`` at the image plane, each
+    [B,F,P,W].  Differentiable w.r.t. x, y, z, cx, cy, c, t and mu.  ``arith``
+    selects the arithmetic policy (default: guarded fast path; ``'exact'`` =
+    bit-identical to the reference's fp32 evaluation order).
+    """
+    if aggregate:
+        raise NotImplementedError(
+            'aggregate=True (per-surface penalty stacks, rtl:641-657) is not part of the CUDA '
+            'hot path yet')
+    return ops.trace(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays, _arith_code(arith))
+
+
+def compute_rms2d(x, y, ray_ok):
+    """Mean over fields of the y-RMS spot radius of lens 0 (rtl:678-702): per field
+    the centroid is the mean over *all* rays, deviations are summed over
+    surviving rays and divided by P*W.  ``x`` is unused, as in the reference."""
+    rms, _ = ops.spot_rms_from_rays(y, ray_ok)
+    return rms[0]
+
+
+def compute_rms2d_all(y, ray_ok):
+    """:func:`compute_rms2d` for every lens of the batch: (rms [B], rms_field [B,F])."""
+    return ops.spot_rms_from_rays(y, ray_ok)
+
+
+def _arith_code(arith):
+    if arith is None or arith == 'guarded' or arith == nat.ARITH_GUARDED:
+        return nat.ARITH_GUARDED
+    if arith == 'exact' or arith == nat.ARITH_EXACT:
+        return nat.ARITH_EXACT
+    raise ValueError(f'unknown arithmetic policy {arith!r}')
+
+
+class RayTracer:
+    """Builds the ray set of a (specs, lens) batch and traces it (rtl:26-208).
+
+    Same constructor arguments as the reference.  ``mode`` selects the pupil
+    sampler; ``n_ray_aiming_iter`` > 0 enables real ray aiming to the stop.
+    """
+
+    def __init__(self, mode='skew_random', n_rays=(8, 8), rel_fields=(0., 0.707, 1.), vig_fn=None,
+                 double_precision=False, wavelengths=(656.3, 587.6, 486.1), n_ray_aiming_iter=0,
+                 ray_aiming_mode='real', allow_backward_rays=True, default_device='cuda', arith=None):
+        self.mode = mode
+        self.default_device = default_device
+        dev = default_device
+        samplers = {
+            'skew_random': lambda ref: circle_pseudo_random(ref, *n_rays, device=dev),
+            'circular': lambda ref: circle(ref, *n_rays, dev),
+            'tee': lambda ref: tee(ref, dev),
+            'chief': lambda ref: chief(ref, n_rays, dev),
+            'meridional_uniform': lambda ref: meridional_uniform(ref, n_rays, dev),
+            'sagittal_uniform': lambda ref: sagittal_uniform(ref, n_rays, dev),
+            'skew_outer_edge_uniform': lambda ref: circle_outer_edge_uniform(ref, n_rays, dev),
+        }
+        if mode not in samplers:
+            raise ValueError(f'Ray tracing mode must be one of {sorted(samplers)}, got {mode!r}')
+        if mode in ('skew_random', 'circular'):
+            assert len(n_rays) == 2
+        self.pupil_span = samplers[mode]
+        self.n_rays = n_rays
+        self.rel_fields = rel_fields
+        self.vig_fn = vig_fn
+        self.n_ray_aiming_iter = n_ray_aiming_iter
+        self.ray_aiming_mode = ray_aiming_mode
+        self.allow_backward_rays = allow_backward_rays
+        self.wavelengths = [WAVELENGTH_ALIASES.get(w, w) for w in wavelengths]
+        if double_precision:
+            raise NotImplementedError('the CUDA ray-trace kernels compute in fp32 only')
+        self.double_precision = False
+        self.arith = arith
+
+    # -- ray-set construction (rtl:80-124) ---------------------------------
+    def _ray_set(self, specs, lens, use_vig=True, xy=None, up_to_stop=False):
+        dev = self.default_device
+        n = lens.get_refractive_indices(self.wavelengths)                 # [B,S,W]
+        n = torch.cat((torch.ones_like(n[:, 0:1, :]), n), dim=1)          # air in front
+        n = n.transpose(1, 2).reshape(n.shape[0], 1, 1, n.shape[2], -1)   # [B,1,1,W,S+1]
+        z = compute_pupil_position(lens).reshape(-1, 1, 1, 1)
+        xp_rel, yp_rel = self.pupil_span(z) if xy is None else xy
+        fields = torch.tensor(self.rel_fields, dtype=torch.float32, device=dev)
+        if use_vig and self.vig_fn is not None and self.mode != 'chief':
+            xp_rel, yp_rel = self._vignette(specs, fields, xp_rel, yp_rel)
+        if self.n_ray_aiming_iter > 0 and not up_to_stop:
+            aim = self.ray_aiming(specs, lens.detach(), use_vig)
+            xp_rel, yp_rel = (torch.clamp(v, -2, 2).to(dev).detach() for v in aim(xp_rel, yp_rel))
+        xp = scale_to_epd(xp_rel, specs.epd)
+        yp = scale_to_epd(yp_rel, specs.epd)
+        cy = torch.sin(specs.hfov[:, None] * fields[None, :])[..., None, None]   # [B,F,1,1]
+        cx = torch.zeros((1, 1, 1, 1), device=dev)
+        c = lens.c.reshape(lens.c.shape[0], 1, 1, 1, -1)
+        t = lens.t.reshape(lens.t.shape[0], 1, 1, 1, -1)
+        mu = n[..., :-1] / n[..., 1:]
+        mask = lens.structure.mask_torch.reshape(lens.c.shape[0], 1, 1, 1, -1)
+        return xp, yp, z, cx, cy, c, t, mu, mask
+
+    def _vignette(self, specs, fields, xp_rel, yp_rel):
+        fields = fields[None, :]
+        vig_up = self.vig_fn(fields, specs.vig_up)
+        vig_down = self.vig_fn(fields, specs.vig_down)
+        vig_x = self.vig_fn(fields, specs.vig_x)
+        return apply_vignetting(xp_rel, vig_x, vig_x), apply_vignetting(yp_rel, vig_up, vig_down)
+
+    def trace_rays(self, specs, lens, use_vig=True, aggregate=False, xy=None, up_to_stop=False):
+        """Trace the configured ray set; returns what :func:`trace_skew` returns."""
+        args = self._ray_set(specs, lens, use_vig, xy, up_to_stop)
+        return trace_skew(*args, aggregate, self.allow_backward_rays, arith=self.arith)
+
+    def spot_rms(self, specs, lens, use_vig=True, shard=(0, 1), group=None):
+        """RMS spot size of every lens -- ``compute_rms2d(*trace_rays(...))`` fused
+        into one pass that also produces the gradients w.r.t. the lens
+        (no [B,F,P,W] tensor is ever materialised).  Returns (rms [B], rms_field [B,F]).
+        With ``shard=(rank, world)`` the pupil axis is split over ranks."""
+        args = self._ray_set(specs, lens, use_vig)
+        return ops.spot_rms(*args, self.allow_backward_rays, _arith_code(self.arith), shard, group)
+
+    # -- ray aiming (rtl:129-208) ---------------------------------------------
+    def ray_aiming(self, specs, lens, use_vig):
+        """One affine correction of the relative pupil coordinates per (lens, field,
+        wavelength) so that the 'tee' rays land where they should on the stop.
+        Returns a function (xp_rel, yp_rel) -> corrected (xp_rel, yp_rel)."""
+        if (lens.structure.stop_idx == 0).all():
+            return lambda xp_rel, yp_rel: (xp_rel, yp_rel)
+        specs2stop = specs.up_to_stop()
+        lens2stop = lens.up_to_stop()
+        dev = self.default_device
+        if self.ray_aiming_mode == 'paraxial':
+            stop_radius = compute_magnification(lens2stop) * specs2stop.epd / 2
+        elif self.ray_aiming_mode == 'real':
+            stop_radius = compute_pupil_radius(specs2stop, lens2stop, default_device=dev)
+        else:
+            raise ValueError(self.ray_aiming_mode)
+        stop_radius = stop_radius.reshape(-1, 1, 1, 1)
+
+        x_tee, y_tee = tee(None, dev)
+        shape = (len(lens), len(self.rel_fields), x_tee.shape[2], len(self.wavelengths))
+        x_tee = x_tee.expand(shape).contiguous()
+        y_tee = y_tee.expand(shape).contiguous()
+        if use_vig and self.vig_fn:
+            fields = torch.tensor(self.rel_fields, dtype=torch.float32, device=dev)
+            x_tee, y_tee = self._vignette(specs, fields, x_tee, y_tee)
+        x_target, y_target = x_tee.clone(), y_tee.clone()
+
+        correct = None
+        for _ in range(self.n_ray_aiming_iter):
+            if correct is not None:
+                x_tee, y_tee = correct(x_tee, y_tee)
+            x_tee = x_tee.detach().requires_grad_(True)
+            y_tee = y_tee.detach().requires_grad_(True)
+            with torch.enable_grad():
+                xs, ys, *_ = self.trace_rays(specs2stop, lens2stop, up_to_stop=True, use_vig=False,
+                                             xy=(x_tee, y_tee))
+                xs_rel = xs / stop_radius
+                ys_rel = ys / stop_radius
+            # d(stop)/d(pupil) summed over outputs, as the reference's two backward calls do
+            slope_x, slope_y = torch.autograd.grad(
+                [xs_rel, ys_rel], [x_tee, y_tee],
+                [torch.ones_like(xs_rel), torch.ones_like(ys_rel)])
+            step_x = -(xs_rel.detach() - x_target) / slope_x
+            step_y = -(ys_rel.detach() - y_target) / slope_y
+            step_x = torch.where(torch.isfinite(step_x), step_x, torch.zeros_like(step_x))
+            step_y = torch.where(torch.isfinite(step_y), step_y, torch.zeros_like(step_y))
+            x_tee, y_tee = x_tee.detach(), y_tee.detach()
+            # affine map through the sagittal ray (x) and the two meridional rays (y)
+            x_sag, dx_sag = x_tee[..., -1:, :], step_x[..., -1:, :]
+            y_lo, y_hi = y_tee[..., 0:1, :], y_tee[..., 1:2, :]
+            dy_lo, dy_hi = step_y[..., 0:1, :], step_y[..., 1:2, :]
+            x_gain = (x_sag + dx_sag) / x_sag
+            y_gain = (y_hi + dy_hi - (y_lo + dy_lo)) / (y_hi - y_lo)
+            y_shift = (y_lo * dy_hi - y_hi * dy_lo) / (y_lo - y_hi)
+
+            def correct(xp_rel, yp_rel, x_gain=x_gain, y_gain=y_gain, y_shift=y_shift):
+                return xp_rel * x_gain, yp_rel * y_gain + y_shift
+        return correct
+
+
+def compute_pupil_radius(specs, lens2stop, default_device='cuda'):
+    """Stop radius = height of the on-axis marginal ray at the stop (rtl:834-844)."""
+    x = torch.zeros((1, 1, 1, 1), device=default_device)
+    y = torch.ones((1, 1, 1, 1), device=default_device)
+    tracer = RayTracer(mode='tee', rel_fields=[0.], vig_fn=None, wavelengths=['d'],
+                       default_device=default_device)
+    _, yp, *_ = tracer.trace_rays(specs, lens2stop, xy=(x, y), use_vig=False)
+    return yp.reshape(yp.shape[0])
