@@ -334,11 +334,17 @@ class Lens:
         broadcasts for a batch of one lens; this one is the same for B = 1 and
         well defined for B > 1."""
         wl = torch.as_tensor(list(wavelengths), dtype=self.nd.dtype, device=self.nd.device)
-        slope = (self.nd - 1) / (self.v * (LINE_F ** -2 - LINE_C ** -2))
+        glass = self.structure.mask_G_torch
+        # air slots carry v = NaN padding: keep it out of the arithmetic so that the
+        # gradients of nd / v are 0 there instead of the reference's 0 * NaN
+        v = torch.where(glass, self.v, torch.ones_like(self.v))
+        dispersive = v != 0
+        v = torch.where(dispersive, v, torch.ones_like(v))
+        slope = (self.nd - 1) / (v * (LINE_F ** -2 - LINE_C ** -2))
         offset = self.nd - slope / LINE_D ** 2
         n = offset[..., None] + slope[..., None] / wl[None, None, :] ** 2
-        n = torch.where(self.structure.mask_G_torch[..., None], n, torch.ones_like(n))
-        return torch.where((self.v != 0)[..., None], n, self.nd[..., None].expand_as(n))
+        n = torch.where(glass[..., None], n, torch.ones_like(n))
+        return torch.where(dispersive[..., None], n, self.nd[..., None].expand_as(n))
 
     # ---- first-order properties (lm:376-386) ------------------------------
     @property
