@@ -10,7 +10,7 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, 'libtorchoptics_b200.so')
+LIB_PATH = os.environ.get('TL_LIB_OVERRIDE') or os.path.join(_PKG, 'libtorchoptics_b200.so')   # override: kernel experiments only
 
 ARITH_GUARDED = 0
 ARITH_EXACT = 1

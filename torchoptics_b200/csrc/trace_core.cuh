@@ -21,6 +21,7 @@
 #define TL_HD __host__ __device__ __forceinline__
 #else
 #define TL_HD inline
+struct float2 { float x, y; };   // host test build only
 #endif
 
 namespace tl {
@@ -99,6 +100,87 @@ TL_HD float frsqrt(float a) {
   return 1.0f / sqrtf(a);
 #endif
 }
+// Two rays per thread: a pair of fp32 lanes that maps onto Blackwell's packed
+// FFMA2 / FMUL2 / FADD2 (fma.rn.f32x2 ...).  The FMA pipe retires a packed
+// instruction at the same flop rate as two scalar ones, but it costs ONE issue
+// slot, which frees the scheduler for the MUFU / shared-memory / select traffic of
+// the trace (measured: tools/microbench.cu).  Each lane is rounded exactly like the
+// scalar op, so a pair gives bit-identical results to two scalar rays.
+struct alignas(8) f2 {
+  float2 v;
+  TL_HD f2() {}
+  TL_HD f2(float s) { v.x = s; v.y = s; }
+  TL_HD f2(float a, float b) { v.x = a; v.y = b; }
+};
+TL_HD f2 operator-(f2 a) { return f2(-a.v.x, -a.v.y); }
+TL_HD f2 operator+(f2 a, f2 b) {
+#if defined(__CUDA_ARCH__)
+  f2 r; r.v = __fadd2_rn(a.v, b.v); return r;
+#else
+  return f2(a.v.x + b.v.x, a.v.y + b.v.y);
+#endif
+}
+TL_HD f2 operator-(f2 a, f2 b) { return a + (-b); }
+TL_HD f2 operator*(f2 a, f2 b) {
+#if defined(__CUDA_ARCH__)
+  f2 r; r.v = __fmul2_rn(a.v, b.v); return r;
+#else
+  return f2(a.v.x * b.v.x, a.v.y * b.v.y);
+#endif
+}
+TL_HD f2 ffma(f2 a, f2 b, f2 c) {
+#if defined(__CUDA_ARCH__)
+  f2 r; r.v = __ffma2_rn(a.v, b.v, c.v); return r;
+#else
+  return f2(fmaf(a.v.x, b.v.x, c.v.x), fmaf(a.v.y, b.v.y, c.v.y));
+#endif
+}
+TL_HD f2 frcp(f2 a) { return f2(frcp(a.v.x), frcp(a.v.y)); }
+TL_HD f2 frsqrt(f2 a) { return f2(frsqrt(a.v.x), frsqrt(a.v.y)); }
+TL_HD f2 fmin2(f2 a, f2 b) { return f2(fminf(a.v.x, b.v.x), fminf(a.v.y, b.v.y)); }
+
+// Four rays per thread: two independent pairs.  Every operation is issued once per
+// pair, so a thread carries two independent dependency chains (ILP 2) -- the trace
+// is a long chain of dependent FMAs and MUFUs, and this is what hides their latency
+// at the low occupancy the per-thread state allows.
+struct alignas(16) f4 {
+  f2 a, b;
+  TL_HD f4() {}
+  TL_HD f4(float s) : a(s), b(s) {}
+  TL_HD f4(f2 a_, f2 b_) : a(a_), b(b_) {}
+};
+TL_HD f4 operator-(f4 v) { return f4(-v.a, -v.b); }
+TL_HD f4 operator+(f4 p, f4 q) { return f4(p.a + q.a, p.b + q.b); }
+TL_HD f4 operator-(f4 p, f4 q) { return f4(p.a - q.a, p.b - q.b); }
+TL_HD f4 operator*(f4 p, f4 q) { return f4(p.a * q.a, p.b * q.b); }
+TL_HD f4 ffma(f4 p, f4 q, f4 r) { return f4(ffma(p.a, q.a, r.a), ffma(p.b, q.b, r.b)); }
+TL_HD f4 frcp(f4 v) { return f4(frcp(v.a), frcp(v.b)); }
+TL_HD f4 frsqrt(f4 v) { return f4(frsqrt(v.a), frsqrt(v.b)); }
+TL_HD f4 fmin2(f4 p, f4 q) { return f4(fmin2(p.a, q.a), fmin2(p.b, q.b)); }
+
+// lane access (indices are compile-time constants after unrolling)
+template <class V> struct LaneCount;
+template <> struct LaneCount<float> { static constexpr int value = 1; };
+template <> struct LaneCount<f2> { static constexpr int value = 2; };
+template <> struct LaneCount<f4> { static constexpr int value = 4; };
+TL_HD float lane_get(const float &v, int) { return v; }
+TL_HD float lane_get(const f2 &v, int i) { return i ? v.v.y : v.v.x; }
+TL_HD float lane_get(const f4 &v, int i) { return i < 2 ? lane_get(v.a, i) : lane_get(v.b, i - 2); }
+TL_HD void lane_set(float &v, int, float s) { v = s; }
+TL_HD void lane_set(f2 &v, int i, float s) { if (i) v.v.y = s; else v.v.x = s; }
+TL_HD void lane_set(f4 &v, int i, float s) { if (i < 2) lane_set(v.a, i, s); else lane_set(v.b, i - 2, s); }
+TL_HD float lane_sum(const float &v) { return v; }
+TL_HD float lane_sum(const f2 &v) { return v.v.x + v.v.y; }
+TL_HD float lane_sum(const f4 &v) { return (v.a.v.x + v.a.v.y) + (v.b.v.x + v.b.v.y); }
+// sum over lanes of p * q, added to acc
+TL_HD float lane_dot(const float &p, const float &q, float acc) { return ffma(p, q, acc); }
+TL_HD float lane_dot(const f2 &p, const f2 &q, float acc) {
+  return ffma(p.v.x, q.v.x, ffma(p.v.y, q.v.y, acc));
+}
+TL_HD float lane_dot(const f4 &p, const f4 &q, float acc) {
+  return lane_dot(p.a, q.a, lane_dot(p.b, q.b, acc));
+}
+
 TL_HD double ffma(double a, double b, double c) { return fma(a, b, c); }
 TL_HD double frcp(double a) { return 1.0 / a; }
 TL_HD double frsqrt(double a) { return 1.0 / sqrt(a); }
@@ -229,6 +311,29 @@ TL_HD T fast_image(Ray<T> &r) {
 }
 
 // ---------------------------------------------------------------------------
+// Only (x, y, cx, cy) of the state in front of each surface is parked for the
+// adjoint sweep; the two dependent components are rebuilt from them:
+//   cz = sqrt(1 - cx^2 - cy^2)                       (how the forward made it, rtl:568)
+//   z  = sag of the previous surface at (x, y) minus its thickness: the point in
+//        front of surface k is the hit point on surface k-1 (x, y unchanged by the
+//        z shift of rtl:639), and a hit point lies on its sphere.
+// ---------------------------------------------------------------------------
+template <class T>
+TL_HD T rebuild_cz(T cx, T cy, T &rcz) {
+  const T w = ffma(-cy, cy, ffma(-cx, cx, T(1)));
+  rcz = frsqrt(w);            // 1 / cz, reused by the adjoint of the surface in front
+  return w * rcz;
+}
+
+template <class T>
+TL_HD T rebuild_z(T x, T y, T c_prev, T t_prev) {
+  const T rho = ffma(y, y, x * x);
+  const T w = ffma(-(c_prev * c_prev), rho, T(1));
+  const T root = w * frsqrt(w);
+  return ffma(c_prev * rho, frcp(T(1) + root), -t_prev);
+}
+
+// ---------------------------------------------------------------------------
 // Adjoint.  `a` holds the adjoint of a ray state (d loss / d state).
 // ---------------------------------------------------------------------------
 template <class T>
@@ -240,8 +345,8 @@ struct SurfaceGrad {
 // plane (after the last surface's z shift); seeds are d loss / d(x, y, cx, cy) of
 // the outputs.
 template <class T>
-TL_HD Ray<T> adjoint_image(const Ray<T> &r, T gx, T gy, T gcx, T gcy) {
-  const T rcz = frcp(r.cz);
+TL_HD Ray<T> adjoint_image(const Ray<T> &r, T gx, T gy, T gcx, T gcy, T &rcz) {
+  rcz = frcp(r.cz);
   const T dist = -r.z * rcz;
   const T gdist = ffma(gy, r.cy, gx * r.cx);
   Ray<T> a;
@@ -255,11 +360,11 @@ TL_HD Ray<T> adjoint_image(const Ray<T> &r, T gx, T gy, T gcx, T gcy) {
 }
 
 // Adjoint of one surface.  `in` is the ray state in front of the surface, `out`
-// the state behind it (x, y, direction; = the next surface's `in`), `a` the
-// adjoint of `out` on entry and of `in` on return.
+// the state behind it (x, y, direction; = the next surface's `in`) with
+// `out_rcz` = 1 / out.cz, `a` the adjoint of `out` on entry and of `in` on return.
 template <class T>
-TL_HD SurfaceGrad<T> adjoint_surface(const Ray<T> &in, const Ray<T> &out, T c, T mu, T mu2,
-                                     Ray<T> &a) {
+TL_HD SurfaceGrad<T> adjoint_surface(const Ray<T> &in, const Ray<T> &out, T out_rcz, T c, T mu,
+                                     T mu2, Ray<T> &a) {
   SurfaceGrad<T> g;
   g.t = -a.z;                                           // z_out = z_hit - t
   // -- recompute the forward intermediates from `in`
@@ -279,7 +384,7 @@ TL_HD SurfaceGrad<T> adjoint_surface(const Ray<T> &in, const Ray<T> &out, T c, T
   const T gsn = ffma(-mu, ci, qo * rsq_qo);             // g = cos_out - mu cos_in
   const T gcv = gsn * c;
   // -- cz_out = sqrt(1 - cx_out^2 - cy_out^2)
-  const T rr = a.cz * frcp(out.cz);
+  const T rr = a.cz * out_rcz;
   const T acx = ffma(-out.cx, rr, a.cx);
   const T acy = ffma(-out.cy, rr, a.cy);
   // -- cx_out = mu cx - (g c) x_hit
@@ -339,8 +444,8 @@ TL_HD SurfaceGrad<T> adjoint_surface(const Ray<T> &in, const Ray<T> &out, T c, T
 
 // Fold the adjoint of cz0 = sqrt(1 - cx^2 - cy^2) (rtl:609) into (cx, cy).
 template <class T>
-TL_HD void adjoint_cz0(const Ray<T> &in0, Ray<T> &a) {
-  const T rr = a.cz * frcp(in0.cz);
+TL_HD void adjoint_cz0(const Ray<T> &in0, T in0_rcz, Ray<T> &a) {
+  const T rr = a.cz * in0_rcz;
   a.cx = ffma(-in0.cx, rr, a.cx);
   a.cy = ffma(-in0.cy, rr, a.cy);
 }

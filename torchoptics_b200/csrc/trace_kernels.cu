@@ -11,6 +11,7 @@
 // accumulator of a thread belongs to one (b, f, w).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 
@@ -37,7 +38,12 @@ int fail(int code, const char *fmt, const char *detail = "") {
 
 constexpr int kTraceThreads = 128;   // adjoint kernels: 6*S floats of state per thread in smem
 constexpr int kFwdThreads = 256;
-constexpr int kMaxRaysPerThread = 128;  // bounds the fp32 run length of an accumulator
+#ifndef TL_DEFAULT_LANES_SPOT
+#define TL_DEFAULT_LANES_SPOT 4
+#endif
+#ifndef TL_DEFAULT_LANES_BWD
+#define TL_DEFAULT_LANES_BWD 4
+#endif
 
 struct DeviceInfo {
   int device = -1;
@@ -106,34 +112,23 @@ struct Traced {
   bool ok, backward;
 };
 
-// Per-thread slot of the parked in-states: element j of surface k lives at
-// state[(k * 6 + j) * stride] (stride = threads per CTA -> conflict-free).
-template <bool SAVE>
-__device__ __forceinline__ void park_state(float *state, int stride, int k, const Ray<float> &r) {
+// Parked in-states for the adjoint sweep: (x, y, cx, cy) in front of every surface
+// (z and cz are rebuilt, see trace_core.cuh).  One V-wide slot per (surface,
+// component, thread): slot (k, j) of thread t is state[(k * 4 + j) * stride + t], so a
+// warp's access is one contiguous, conflict-free 64/128-bit transaction per lane group.
+template <bool SAVE, class V>
+__device__ __forceinline__ void park(V *state, int stride, int k, const Ray<V> &r) {
   if (SAVE) {
-    float *s = state + (size_t)k * 6 * stride;
+    V *s = state + (size_t)k * 4 * stride;
     s[0] = r.x;
     s[stride] = r.y;
-    s[2 * stride] = r.z;
-    s[3 * stride] = r.cx;
-    s[4 * stride] = r.cy;
-    s[5 * stride] = r.cz;
+    s[2 * stride] = r.cx;
+    s[3 * stride] = r.cy;
   }
 }
 
-__device__ __forceinline__ Ray<float> load_state(const float *state, int stride, int k) {
-  const float *s = state + (size_t)k * 6 * stride;
-  Ray<float> r;
-  r.x = s[0];
-  r.y = s[stride];
-  r.z = s[2 * stride];
-  r.cx = s[3 * stride];
-  r.cy = s[4 * stride];
-  r.cz = s[5 * stride];
-  return r;
-}
-
-// Exact-policy trace of one ray (rtl:594-675 statement by statement).
+// Exact-policy trace of one ray (rtl:594-675 statement by statement).  When SAVE,
+// parks this ray's lane of the V-wide slots (scalar view: `stride` in floats).
 template <bool SAVE>
 __device__ __noinline__ Traced trace_exact(float x, float y, float z, float cx, float cy,
                                            const Table &tab, int S, bool allow_backward,
@@ -141,7 +136,7 @@ __device__ __noinline__ Traced trace_exact(float x, float y, float z, float cx, 
   Ray<float> r{x, y, z, cx, cy, exact_cz0(cx, cy)};
   bool ok = true, backward = false;
   for (int k = 0; k < S; ++k) {
-    park_state<SAVE>(state, stride, k, r);
+    park<SAVE, float>(state, stride, k, r);
     const Surface s{tab.c[k], tab.t[k], tab.mu[k]};
     exact_surface(r, s, k > 0 && tab.live[k - 1], allow_backward, ok, backward);
   }
@@ -155,37 +150,95 @@ __device__ __noinline__ Traced trace_exact(float x, float y, float z, float cx, 
   return out;
 }
 
-// Guarded policy: contracted fast path, exact re-trace unless clearly good.
-template <bool SAVE>
-__device__ __forceinline__ Traced trace_guarded(float x, float y, float z, float cx, float cy,
-                                                const Table &tab, int S, bool allow_backward,
-                                                int arith, float *state, int stride) {
+// N rays per thread (V = float, f2 or f4).
+template <class V>
+struct TracedN {
+  Ray<V> pre;
+  V x, y;
+  bool ok[LaneCount<V>::value], backward[LaneCount<V>::value];
+};
+
+// Guarded policy: contracted (and, for f2/f4, packed) fast path for all lanes; each
+// lane that was not clearly good everywhere is then re-traced alone with the exact
+// policy, overwriting its lane of the parked states.
+template <bool SAVE, class V>
+__device__ __forceinline__ TracedN<V> trace_guarded(V x, V y, V z, V cx, V cy, const Table &tab,
+                                                    int S, bool allow_backward, int arith,
+                                                    V *state, int stride) {
+  constexpr int N = LaneCount<V>::value;
+  TracedN<V> out;
+  bool clear[N];
+#pragma unroll
+  for (int l = 0; l < N; ++l) clear[l] = false;
   if (arith == TL_ARITH_GUARDED) {
-    Ray<float> r{x, y, z, cx, cy, fast_cz0(cx, cy)};
-    float min_cos2 = 1.0f, min_travel = 3.0e38f;
+    Ray<V> r{x, y, z, cx, cy, fast_cz0(cx, cy)};
+    V min_cos2(1.0f), min_travel(3.0e38f);
     for (int k = 0; k < S; ++k) {
-      park_state<SAVE>(state, stride, k, r);
-      float travel;
-      fast_surface(r, tab.c[k], tab.mu[k], tab.mu2[k], tab.t[k], min_cos2, travel);
-      if (k > 0 && tab.live[k - 1]) min_travel = fminf(min_travel, travel);
+      park<SAVE, V>(state, stride, k, r);
+      V travel;
+      fast_surface(r, V(tab.c[k]), V(tab.mu[k]), V(tab.mu2[k]), V(tab.t[k]), min_cos2, travel);
+      if (k > 0 && tab.live[k - 1]) min_travel = fmin2(min_travel, travel);
     }
-    Traced out;
     out.pre = r;
-    const float travel = fast_image(r);
-    if (tab.live[S - 1]) min_travel = fminf(min_travel, travel);
-    const float band = kBandTravelRel * fmaxf(1.0f, tab.length + fabsf(z));
-    const float probe = r.x + r.y + r.cx + r.cy;
-    const bool clear = (min_cos2 > kGuard + kBandCos2) && (min_travel > band) &&
-                       (fabsf(probe) < 3.0e38f);
-    if (clear) {
-      out.x = r.x;
-      out.y = r.y;
-      out.ok = true;
-      out.backward = false;
-      return out;
+    const V travel = fast_image(r);
+    if (tab.live[S - 1]) min_travel = fmin2(min_travel, travel);
+    out.x = r.x;
+    out.y = r.y;
+    const V probe = (r.x + r.y) + (r.cx + r.cy);
+#pragma unroll
+    for (int l = 0; l < N; ++l) {
+      const float band = kBandTravelRel * fmaxf(1.0f, tab.length + fabsf(lane_get(z, l)));
+      clear[l] = (lane_get(min_cos2, l) > kGuard + kBandCos2) && (lane_get(min_travel, l) > band) &&
+                 (fabsf(lane_get(probe, l)) < 3.0e38f);
     }
   }
-  return trace_exact<SAVE>(x, y, z, cx, cy, tab, S, allow_backward, state, stride);
+#pragma unroll
+  for (int l = 0; l < N; ++l) {
+    out.ok[l] = true;
+    out.backward[l] = false;
+    if (!clear[l]) {
+      const Traced one = trace_exact<SAVE>(lane_get(x, l), lane_get(y, l), lane_get(z, l),
+                                           lane_get(cx, l), lane_get(cy, l), tab, S, allow_backward,
+                                           reinterpret_cast<float *>(state) + l, N * stride);
+      lane_set(out.pre.x, l, one.pre.x);
+      lane_set(out.pre.y, l, one.pre.y);
+      lane_set(out.pre.z, l, one.pre.z);
+      lane_set(out.pre.cx, l, one.pre.cx);
+      lane_set(out.pre.cy, l, one.pre.cy);
+      lane_set(out.pre.cz, l, one.pre.cz);
+      lane_set(out.x, l, one.x);
+      lane_set(out.y, l, one.y);
+      out.ok[l] = one.ok;
+      out.backward[l] = one.backward;
+    }
+  }
+  return out;
+}
+
+// A failed ray's parked states (and `pre`) may hold anything.  Before the packed
+// adjoint runs over a lane group with some dead lanes, every dead lane is given a
+// live lane's states: its adjoint then stays finite and, seeded with 0, contributes
+// exact zeros.
+template <class V>
+__device__ __noinline__ void mirror_live_lane(V *state, int stride, int S, const bool *ok,
+                                              Ray<V> &pre, V &z_in) {
+  constexpr int N = LaneCount<V>::value;
+  int src = 0;
+  for (int l = 0; l < N; ++l)
+    if (ok[l]) src = l;
+  float *lanes = reinterpret_cast<float *>(state);
+  for (int i = 0; i < S * 4; ++i) {
+    float *slot = lanes + (size_t)i * stride * N;
+    const float v = slot[src];
+    for (int l = 0; l < N; ++l)
+      if (!ok[l]) slot[l] = v;
+  }
+  V *comp[7] = {&pre.x, &pre.y, &pre.z, &pre.cx, &pre.cy, &pre.cz, &z_in};
+  for (int j = 0; j < 7; ++j) {
+    const float v = lane_get(*comp[j], src);
+    for (int l = 0; l < N; ++l)
+      if (!ok[l]) lane_set(*comp[j], l, v);
+  }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -195,7 +248,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // --------------------------------------------------------------------------
-// K1: forward trace (trace_skew, rtl:594-675)
+// K1: forward trace (trace_skew, rtl:594-675), two rays per thread.
 // grid: (b, f, w, chunk) flattened; CTA strides over its pupil chunk.
 // --------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFwdThreads)
@@ -209,215 +262,303 @@ k_trace_fwd(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
   const Table tab = load_table(smem, pb, b, w);
   const int p_lo = chunk * chunk_len;
   const int p_hi = min(pb.P, p_lo + chunk_len);
-  for (int p = p_lo + threadIdx.x; p < p_hi; p += blockDim.x) {
-    const float x = pb.x.ptr[offset_of(pb.x, b, f, p, w)];
-    const float y = pb.y.ptr[offset_of(pb.y, b, f, p, w)];
-    const float z = pb.z.ptr[offset_of(pb.z, b, f, p, w)];
-    const float cx = pb.cx.ptr[offset_of(pb.cx, b, f, p, w)];
-    const float cy = pb.cy.ptr[offset_of(pb.cy, b, f, p, w)];
-    const Traced tr = trace_guarded<false>(x, y, z, cx, cy, tab, pb.S,
-                                           pb.allow_backward_rays != 0, pb.arith, nullptr, 0);
-    const int64_t o = (((int64_t)b * pb.F + f) * pb.P + p) * pb.W + w;
-    out.x[o] = tr.x;
-    out.y[o] = tr.y;
-    out.cx[o] = tr.pre.cx;
-    out.cy[o] = tr.pre.cy;
-    out.ok[o] = tr.ok;
-    out.backward[o] = tr.backward;
+  for (int p0 = p_lo + threadIdx.x; p0 < p_hi; p0 += 2 * kFwdThreads) {
+    const int p1 = p0 + kFwdThreads;
+    const bool has1 = p1 < p_hi;
+    const int q1 = has1 ? p1 : p0;
+    const f2 x(pb.x.ptr[offset_of(pb.x, b, f, p0, w)], pb.x.ptr[offset_of(pb.x, b, f, q1, w)]);
+    const f2 y(pb.y.ptr[offset_of(pb.y, b, f, p0, w)], pb.y.ptr[offset_of(pb.y, b, f, q1, w)]);
+    const f2 z(pb.z.ptr[offset_of(pb.z, b, f, p0, w)], pb.z.ptr[offset_of(pb.z, b, f, q1, w)]);
+    const f2 cx(pb.cx.ptr[offset_of(pb.cx, b, f, p0, w)], pb.cx.ptr[offset_of(pb.cx, b, f, q1, w)]);
+    const f2 cy(pb.cy.ptr[offset_of(pb.cy, b, f, p0, w)], pb.cy.ptr[offset_of(pb.cy, b, f, q1, w)]);
+    const TracedN<f2> tr = trace_guarded<false, f2>(x, y, z, cx, cy, tab, pb.S,
+                                                    pb.allow_backward_rays != 0, pb.arith, nullptr, 0);
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+      if (l == 1 && !has1) break;
+      const int64_t o = (((int64_t)b * pb.F + f) * pb.P + (l ? p1 : p0)) * pb.W + w;
+      out.x[o] = lane_get(tr.x, l);
+      out.y[o] = lane_get(tr.y, l);
+      out.cx[o] = lane_get(tr.pre.cx, l);
+      out.cy[o] = lane_get(tr.pre.cy, l);
+      out.ok[o] = tr.ok[l];
+      out.backward[o] = tr.backward[l];
+    }
   }
 }
 
+// Reference height of every (lens, field): the image height of the exact-policy
+// chief ray (pupil centre) at wavelength 0.  The spot sums are centred on it; it
+// depends only on the prescription, so every rank computes the same value.
+__global__ void k_chief_rays(TlProblem pb, float *ref_y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pb.B * pb.F) return;
+  const int b = i / pb.F, f = i % pb.F, S = pb.S;
+  const bool allow_backward = pb.allow_backward_rays != 0;
+  Ray<float> r{0.f, 0.f, pb.z.ptr[offset_of(pb.z, b, f, 0, 0)],
+               pb.cx.ptr[offset_of(pb.cx, b, f, 0, 0)], pb.cy.ptr[offset_of(pb.cy, b, f, 0, 0)], 0.f};
+  r.cz = exact_cz0(r.cx, r.cy);
+  bool ok = true, backward = false;
+  for (int k = 0; k < S; ++k) {
+    const Surface s{pb.c[(int64_t)b * S + k], pb.t[(int64_t)b * S + k],
+                    pb.mu[((int64_t)b * pb.W) * S + k]};
+    exact_surface(r, s, k > 0 && pb.live[(int64_t)b * S + k - 1], allow_backward, ok, backward);
+  }
+  exact_image(r, pb.live[(int64_t)b * S + S - 1] != 0, allow_backward, ok, backward);
+  ref_y[i] = (ok && fabsf(r.y) < 3.0e38f) ? r.y : 0.f;
+}
+
 // --------------------------------------------------------------------------
-// K2/K3: forward + adjoint in one pass.
+// K2/K3: forward + adjoint in one pass, N rays per thread (packed f32x2 math).
 //   MODE_BWD        seeds come from the caller (autograd of trace_skew)
 //   MODE_SPOT_GRAD  unit seed on y; accumulates both sum(J) and sum((y-y0) J) so
 //                   that the RMS gradient is assembled after the reduction
 //   MODE_SPOT_EVAL  forward moments only (no state, no adjoint)
+//
+// Persistent CTAs.  The work is the list of (row, group) items, row = (b, f, w),
+// group = kTraceThreads * N consecutive pupil points; CTA i owns the contiguous
+// slice [i G / n, (i + 1) G / n) of that list, so every CTA does the same amount of
+// work (no tail wave) and crosses a row boundary -- where it reduces and writes its
+// accumulators as one fp64 partial row ("segment") -- at most a couple of times.
 // --------------------------------------------------------------------------
 enum { MODE_BWD = 0, MODE_SPOT_GRAD = 1, MODE_SPOT_EVAL = 2 };
 
 struct AdjArgs {
   TlSeeds seeds;
   TlGrads grads;
-  double *partial;   // [n_blocks, n_acc]
-  float *ref_y;      // [B,F] (spot modes)
-  int nchunks, chunk_len, n_acc;
+  double *partial;      // [n_blocks, max_seg, n_acc]
+  const float *ref_y;   // [B,F] (spot modes)
+  int groups_per_row, max_seg, n_acc;
 };
 
-template <int NS_MAX, int MODE>
-__global__ void __launch_bounds__(kTraceThreads)
+#ifndef TL_ADJ_MIN_BLOCKS
+#define TL_ADJ_MIN_BLOCKS 1
+#endif
+
+template <int NS_MAX, int MODE, class V>
+__global__ void __launch_bounds__(kTraceThreads, TL_ADJ_MIN_BLOCKS)
 k_trace_adj(TlProblem pb, AdjArgs args) {
   extern __shared__ float smem[];
+  constexpr int N = LaneCount<V>::value;
   constexpr bool kSpot = MODE != MODE_BWD;
   constexpr bool kAdjoint = MODE != MODE_SPOT_EVAL;
   constexpr int NA = kAdjoint ? NS_MAX : 1;
+  constexpr int kWarps = kTraceThreads / 32;
   const int S = pb.S;
   const int tid = threadIdx.x;
-  int blk = blockIdx.x;
-  const int chunk = blk % args.nchunks; blk /= args.nchunks;
-  const int w = blk % pb.W; blk /= pb.W;
-  const int f = blk % pb.F;
-  const int b = blk / pb.F;
-  const Table tab = load_table(smem, pb, b, w);
-  float *state = smem + table_floats(S) + tid;
+  const int lane = tid & 31, warp = tid >> 5;
   const int stride = kTraceThreads;
   const bool allow_backward = pb.allow_backward_rays != 0;
+  const int n_acc = args.n_acc;
+  // parked states start on a 16-byte boundary behind the table
+  V *state = reinterpret_cast<V *>(smem + ((table_floats(S) + 3) & ~(size_t)3)) + tid;
+  float *red = smem + table_floats(S);
 
-  // reference height of this field: the exact-policy chief ray (pupil centre) of
-  // wavelength 0 -- every CTA and every rank computes the same value.
-  float y0 = 0.f;
-  if (kSpot) {
-    __shared__ float s_y0;
-    if (tid == 0) {
-      Ray<float> r{0.f, 0.f, pb.z.ptr[offset_of(pb.z, b, f, 0, 0)],
-                   pb.cx.ptr[offset_of(pb.cx, b, f, 0, 0)],
-                   pb.cy.ptr[offset_of(pb.cy, b, f, 0, 0)], 0.f};
-      r.cz = exact_cz0(r.cx, r.cy);
-      bool ok = true, backward = false;
-      for (int k = 0; k < S; ++k) {
-        const Surface s{tab.c[k], tab.t[k], pb.mu[((int64_t)b * pb.W) * S + k]};   // wavelength 0
-        exact_surface(r, s, k > 0 && tab.live[k - 1], allow_backward, ok, backward);
-      }
-      exact_image(r, tab.live[S - 1] != 0, allow_backward, ok, backward);
-      const float v = (ok && fabsf(r.y) < 3.0e38f) ? r.y : 0.f;
-      s_y0 = v;
-      if (chunk == 0 && w == 0) args.ref_y[b * pb.F + f] = v;
-    }
-    __syncthreads();
-    y0 = s_y0;
-  }
+  const int64_t total = (int64_t)pb.B * pb.F * pb.W * args.groups_per_row;
+  const int64_t g_begin = total * blockIdx.x / gridDim.x;
+  const int64_t g_end = total * (blockIdx.x + 1) / gridDim.x;
 
   // accumulators (registers: every index below is a compile-time constant)
   float acc_c[NA], acc_t[NA], acc_mu[NA];      // sum J        (BWD: sum of gradients)
   float wac_c[NA], wac_t[NA], wac_mu[NA];      // sum (y-y0) J (SPOT_GRAD only)
-#pragma unroll
-  for (int k = 0; k < NA; ++k) {
-    acc_c[k] = acc_t[k] = acc_mu[k] = 0.f;
-    wac_c[k] = wac_t[k] = wac_mu[k] = 0.f;
-  }
   float acc_z = 0.f, wac_z = 0.f;
   float m_s1 = 0.f, m_s2 = 0.f, m_n = 0.f;
+  Table tab;
+  float y0 = 0.f;
+  int row = -1, seg = 0, b = 0, f = 0, w = 0;
 
-  const int p_lo = pb.p_begin + chunk * args.chunk_len;
-  const int p_hi = min(pb.p_end, p_lo + args.chunk_len);
-  for (int p = p_lo + tid; p < p_hi; p += kTraceThreads) {
-    const float x = pb.x.ptr[offset_of(pb.x, b, f, p, w)];
-    const float y = pb.y.ptr[offset_of(pb.y, b, f, p, w)];
-    const float z = pb.z.ptr[offset_of(pb.z, b, f, p, w)];
-    const float cx = pb.cx.ptr[offset_of(pb.cx, b, f, p, w)];
-    const float cy = pb.cy.ptr[offset_of(pb.cy, b, f, p, w)];
-    const Traced tr = trace_guarded<kAdjoint>(x, y, z, cx, cy, tab, S, allow_backward, pb.arith,
-                                              state, stride);
-    const int64_t o = (((int64_t)b * pb.F + f) * pb.P + p) * pb.W + w;
-    float wgt = 0.f;
-    if (kSpot && tr.ok) {
-      wgt = tr.y - y0;
-      m_s1 += wgt;
-      m_s2 = ffma(wgt, wgt, m_s2);
-      m_n += 1.0f;
+  auto flush = [&]() {
+    // CTA reduction: warp shuffles -> smem [warp][slot] -> one fp64 partial row
+    __syncthreads();
+    auto put = [&](int slot, float v) {
+      v = warp_sum(v);
+      if (lane == 0) red[warp * n_acc + slot] = v;
+    };
+    if (MODE == MODE_BWD) {
+#pragma unroll
+      for (int k = 0; k < NA; ++k)
+        if (k < S) {
+          put(k, acc_c[k]);
+          put(S + k, acc_t[k]);
+          put(2 * S + k, acc_mu[k]);
+        }
+      put(3 * S, acc_z);
+    } else if (MODE == MODE_SPOT_GRAD) {
+#pragma unroll
+      for (int k = 0; k < NA; ++k)
+        if (k < S) {
+          put(k, wac_c[k]);
+          put(S + k, acc_c[k]);
+          put(2 * S + k, wac_t[k]);
+          put(3 * S + k, acc_t[k]);
+          put(4 * S + k, wac_mu[k]);
+          put(5 * S + k, acc_mu[k]);
+        }
+      put(6 * S, wac_z);
+      put(6 * S + 1, acc_z);
+      put(6 * S + 2, m_s1);
+      put(6 * S + 3, m_s2);
+      put(6 * S + 4, m_n);
+    } else {
+      put(0, m_s1);
+      put(1, m_s2);
+      put(2, m_n);
+    }
+    __syncthreads();
+    double *dst = args.partial + ((int64_t)blockIdx.x * args.max_seg + seg) * n_acc;
+    for (int i = tid; i < n_acc; i += kTraceThreads) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < kWarps; ++q) s += (double)red[q * n_acc + i];
+      dst[i] = s;
+    }
+    ++seg;
+    __syncthreads();
+  };
+
+  for (int64_t g = g_begin; g < g_end; ++g) {
+    const int r = (int)(g / args.groups_per_row);
+    const int j = (int)(g % args.groups_per_row);
+    if (r != row) {
+      if (row >= 0) flush();
+      row = r;
+      w = r % pb.W;
+      f = (r / pb.W) % pb.F;
+      b = r / (pb.W * pb.F);
+      tab = load_table(smem, pb, b, w);
+      if (kSpot) y0 = args.ref_y[b * pb.F + f];
+#pragma unroll
+      for (int k = 0; k < NA; ++k) {
+        acc_c[k] = acc_t[k] = acc_mu[k] = 0.f;
+        wac_c[k] = wac_t[k] = wac_mu[k] = 0.f;
+      }
+      acc_z = wac_z = 0.f;
+      m_s1 = m_s2 = m_n = 0.f;
+    }
+    // lane l of this thread = pupil point p_base + l * threads + tid
+    const int p_base = pb.p_begin + j * (kTraceThreads * N) + tid;
+    bool has[N];
+    int64_t o[N];
+    V x, y, z, cx, cy;
+#pragma unroll
+    for (int l = 0; l < N; ++l) {
+      const int p = p_base + l * kTraceThreads;
+      has[l] = p < pb.p_end;
+      const int q = has[l] ? p : p_base;          // past the end: a copy of lane 0 (p_base is valid)
+      o[l] = (((int64_t)b * pb.F + f) * pb.P + q) * pb.W + w;
+      lane_set(x, l, pb.x.ptr[offset_of(pb.x, b, f, q, w)]);
+      lane_set(y, l, pb.y.ptr[offset_of(pb.y, b, f, q, w)]);
+      lane_set(z, l, pb.z.ptr[offset_of(pb.z, b, f, q, w)]);
+      lane_set(cx, l, pb.cx.ptr[offset_of(pb.cx, b, f, q, w)]);
+      lane_set(cy, l, pb.cy.ptr[offset_of(pb.cy, b, f, q, w)]);
+    }
+    if (p_base >= pb.p_end) continue;   // whole thread past the end of the row
+    TracedN<V> tr = trace_guarded<kAdjoint, V>(x, y, z, cx, cy, tab, S, allow_backward, pb.arith,
+                                               state, stride);
+    bool live[N], any_live = false, all_ok = true;
+    V alive, wgt(0.f);
+#pragma unroll
+    for (int l = 0; l < N; ++l) {
+      live[l] = tr.ok[l] && has[l];
+      any_live = any_live || live[l];
+      all_ok = all_ok && tr.ok[l];
+      lane_set(alive, l, live[l] ? 1.0f : 0.0f);
+    }
+    if (kSpot) {
+      wgt = (tr.y - V(y0)) * alive;
+#pragma unroll
+      for (int l = 0; l < N; ++l)
+        if (!live[l]) lane_set(wgt, l, 0.f);      // a dead lane's y may be anything
+      m_s1 += lane_sum(wgt);
+      m_s2 = lane_dot(wgt, wgt, m_s2);
+      m_n += lane_sum(alive);
     }
     if (kAdjoint) {
-      Ray<float> a{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (tr.ok) {
-        float sx = 0.f, sy = 0.f, scx = 0.f, scy = 0.f;
+      Ray<V> a{V(0.f), V(0.f), V(0.f), V(0.f), V(0.f), V(0.f)};
+      if (any_live) {
+        if (!all_ok) mirror_live_lane<V>(state, stride, S, tr.ok, tr.pre, z);
+        V sx(0.f), sy(0.f), scx(0.f), scy(0.f);
         if (MODE == MODE_SPOT_GRAD) {
-          sy = 1.0f;
+          sy = alive;
         } else {
-          if (args.seeds.gx) sx = args.seeds.gx[o];
-          if (args.seeds.gy) sy = args.seeds.gy[o];
-          if (args.seeds.gcx) scx = args.seeds.gcx[o];
-          if (args.seeds.gcy) scy = args.seeds.gcy[o];
+#pragma unroll
+          for (int l = 0; l < N; ++l) {
+            if (!live[l]) continue;
+            if (args.seeds.gx) lane_set(sx, l, args.seeds.gx[o[l]]);
+            if (args.seeds.gy) lane_set(sy, l, args.seeds.gy[o[l]]);
+            if (args.seeds.gcx) lane_set(scx, l, args.seeds.gcx[o[l]]);
+            if (args.seeds.gcy) lane_set(scy, l, args.seeds.gcy[o[l]]);
+          }
         }
-        a = adjoint_image(tr.pre, sx, sy, scx, scy);
-        Ray<float> next = tr.pre;
+        V next_rcz;
+        a = adjoint_image(tr.pre, sx, sy, scx, scy, next_rcz);
+        Ray<V> next = tr.pre;
 #pragma unroll
         for (int k = NS_MAX - 1; k >= 0; --k) {
           if (k < S) {
-            const Ray<float> in = load_state(state, stride, k);
-            const SurfaceGrad<float> g =
-                adjoint_surface(in, next, tab.c[k], tab.mu[k], tab.mu2[k], a);
-            acc_c[k] += g.c;
-            acc_t[k] += g.t;
-            acc_mu[k] += g.mu;
+            const V *slot = state + (size_t)k * 4 * stride;
+            Ray<V> in;
+            in.x = slot[0];
+            in.y = slot[stride];
+            in.cx = slot[2 * stride];
+            in.cy = slot[3 * stride];
+            V in_rcz;
+            in.cz = rebuild_cz(in.cx, in.cy, in_rcz);
+            in.z = (k == 0) ? z : rebuild_z(in.x, in.y, V(tab.c[k > 0 ? k - 1 : 0]),
+                                            V(tab.t[k > 0 ? k - 1 : 0]));
+            const SurfaceGrad<V> g =
+                adjoint_surface(in, next, next_rcz, V(tab.c[k]), V(tab.mu[k]), V(tab.mu2[k]), a);
+            acc_c[k] += lane_sum(g.c);
+            acc_t[k] += lane_sum(g.t);
+            acc_mu[k] += lane_sum(g.mu);
             if (MODE == MODE_SPOT_GRAD) {
-              wac_c[k] = ffma(wgt, g.c, wac_c[k]);
-              wac_t[k] = ffma(wgt, g.t, wac_t[k]);
-              wac_mu[k] = ffma(wgt, g.mu, wac_mu[k]);
+              wac_c[k] = lane_dot(wgt, g.c, wac_c[k]);
+              wac_t[k] = lane_dot(wgt, g.t, wac_t[k]);
+              wac_mu[k] = lane_dot(wgt, g.mu, wac_mu[k]);
             }
             next = in;
+            next_rcz = in_rcz;
           }
         }
-        adjoint_cz0(next, a);
-        acc_z += a.z;
-        if (MODE == MODE_SPOT_GRAD) wac_z = ffma(wgt, a.z, wac_z);
+        adjoint_cz0(next, next_rcz, a);
+        acc_z += lane_sum(a.z);
+        if (MODE == MODE_SPOT_GRAD) wac_z = lane_dot(wgt, a.z, wac_z);
       }
       if (MODE == MODE_BWD) {
-        if (args.grads.gx) args.grads.gx[o] = a.x;
-        if (args.grads.gy) args.grads.gy[o] = a.y;
-        if (args.grads.gz) args.grads.gz[o] = a.z;
-        if (args.grads.gcx) args.grads.gcx[o] = a.cx;
-        if (args.grads.gcy) args.grads.gcy[o] = a.cy;
+#pragma unroll
+        for (int l = 0; l < N; ++l) {
+          if (!has[l]) continue;
+          if (args.grads.gx) args.grads.gx[o[l]] = lane_get(a.x, l);
+          if (args.grads.gy) args.grads.gy[o[l]] = lane_get(a.y, l);
+          if (args.grads.gz) args.grads.gz[o[l]] = lane_get(a.z, l);
+          if (args.grads.gcx) args.grads.gcx[o[l]] = lane_get(a.cx, l);
+          if (args.grads.gcy) args.grads.gcy[o[l]] = lane_get(a.cy, l);
+        }
       }
     }
   }
-
-  // ---- CTA reduction: warp shuffles -> smem [warp][slot] -> fp64 partial row
-  __syncthreads();
-  float *red = smem + table_floats(S);
-  const int lane = tid & 31, warp = tid >> 5;
-  constexpr int kWarps = kTraceThreads / 32;
-  const int n_acc = args.n_acc;
-  auto put = [&](int slot, float v) {
-    v = warp_sum(v);
-    if (lane == 0) red[warp * n_acc + slot] = v;
-  };
-  if (MODE == MODE_BWD) {
-#pragma unroll
-    for (int k = 0; k < NA; ++k)
-      if (k < S) {
-        put(k, acc_c[k]);
-        put(S + k, acc_t[k]);
-        put(2 * S + k, acc_mu[k]);
-      }
-    put(3 * S, acc_z);
-  } else if (MODE == MODE_SPOT_GRAD) {
-#pragma unroll
-    for (int k = 0; k < NA; ++k)
-      if (k < S) {
-        put(k, wac_c[k]);
-        put(S + k, acc_c[k]);
-        put(2 * S + k, wac_t[k]);
-        put(3 * S + k, acc_t[k]);
-        put(4 * S + k, wac_mu[k]);
-        put(5 * S + k, acc_mu[k]);
-      }
-    put(6 * S, wac_z);
-    put(6 * S + 1, acc_z);
-    put(6 * S + 2, m_s1);
-    put(6 * S + 3, m_s2);
-    put(6 * S + 4, m_n);
-  } else {
-    put(0, m_s1);
-    put(1, m_s2);
-    put(2, m_n);
-  }
-  __syncthreads();
-  for (int i = tid; i < n_acc; i += kTraceThreads) {
-    double s = 0.0;
-#pragma unroll
-    for (int q = 0; q < kWarps; ++q) s += (double)red[q * n_acc + i];
-    args.partial[(int64_t)blockIdx.x * n_acc + i] = s;
-  }
+  if (row >= 0) flush();
 }
 
-// partial[(bfw * nchunks + chunk), n_acc] -> dst[bfw, n_acc], fixed summation order
-__global__ void k_reduce_chunks(const double *partial, double *dst, int n_rows, int nchunks,
-                                int n_acc) {
+// CTA that owns work item g of `total` when they are dealt as contiguous slices
+__device__ __forceinline__ int64_t owner_of(int64_t g, int64_t total, int64_t n_blocks) {
+  return ((g + 1) * n_blocks - 1) / total;
+}
+
+// partial[block, segment, n_acc] -> dst[row, n_acc], fixed summation order
+__global__ void k_reduce_rows(const double *partial, double *dst, int n_rows, int groups_per_row,
+                              int n_blocks, int max_seg, int n_acc) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)n_rows * n_acc) return;
   const int row = (int)(i / n_acc), slot = (int)(i % n_acc);
+  const int64_t total = (int64_t)n_rows * groups_per_row;
+  const int64_t first = owner_of((int64_t)row * groups_per_row, total, n_blocks);
+  const int64_t last = owner_of((int64_t)(row + 1) * groups_per_row - 1, total, n_blocks);
   double s = 0.0;
-  for (int c = 0; c < nchunks; ++c) s += partial[((int64_t)row * nchunks + c) * n_acc + slot];
+  for (int64_t blk = first; blk <= last; ++blk) {
+    const int64_t first_row = (total * blk / n_blocks) / groups_per_row;
+    s += partial[((blk * max_seg) + (row - first_row)) * n_acc + slot];
+  }
   dst[i] = s;
 }
 
@@ -627,27 +768,16 @@ int validate(const TlProblem *pb, int max_s) {
   return TL_OK;
 }
 
-struct Plan {
+// K1 grid: chunks per (b,f,w) so that the machine is filled a few times over
+struct FwdPlan {
   int nchunks = 1, chunk_len = 1, n_blocks = 1;
-  size_t smem = 0;
 };
 
-size_t adj_smem_bytes(int S, int n_acc, bool with_state) {
-  const size_t state = with_state ? (size_t)6 * S * kTraceThreads : 0;
-  const size_t red = (size_t)(kTraceThreads / 32) * n_acc;
-  return (5 * (size_t)S + (state > red ? state : red)) * sizeof(float);
-}
-
-// Chunks per (b,f,w): enough CTAs to fill the machine a few times over and few
-// enough rays per thread that fp32 accumulators stay short.
-Plan make_plan(int sms, int bfw, int n_pupil, int threads, int ctas_per_sm) {
-  Plan pl;
-  const int64_t want_blocks = (int64_t)sms * ctas_per_sm * 2;
+FwdPlan make_fwd_plan(int sms, int bfw, int n_pupil, int rays_per_pass, int ctas_per_sm) {
+  FwdPlan pl;
+  const int64_t want_blocks = (int64_t)sms * ctas_per_sm * 4;
   int64_t nchunks = (want_blocks + bfw - 1) / bfw;
-  const int64_t min_chunks = ((int64_t)n_pupil + (int64_t)threads * kMaxRaysPerThread - 1) /
-                             ((int64_t)threads * kMaxRaysPerThread);
-  const int64_t max_chunks = ((int64_t)n_pupil + threads - 1) / threads;
-  if (nchunks < min_chunks) nchunks = min_chunks;
+  const int64_t max_chunks = ((int64_t)n_pupil + rays_per_pass - 1) / rays_per_pass;
   if (nchunks > max_chunks) nchunks = max_chunks;
   if (nchunks < 1) nchunks = 1;
   pl.nchunks = (int)nchunks;
@@ -660,52 +790,120 @@ int n_acc_of(int mode, int S) {
   return mode == MODE_BWD ? 3 * S + 1 : (mode == MODE_SPOT_GRAD ? 6 * S + 5 : 3);
 }
 
-template <int NS_MAX, int MODE>
-int launch_adj(const TlProblem &pb, const AdjArgs &args, const Plan &pl, cudaStream_t stream) {
-  auto kernel = k_trace_adj<NS_MAX, MODE>;
+// ---- K2/K3 variants -------------------------------------------------------
+typedef void (*AdjKernel)(TlProblem, AdjArgs);
+
+struct AdjVariant {
+  AdjKernel kernel = nullptr;
+  int lanes = 2;          // rays per thread
+};
+
+// Rays per thread.  Four (two interleaved pairs) hides the latency of the
+// dependent FMA/MUFU chain best when the accumulators still fit the register file
+// (S <= 12 for the fused pass); larger surface counts use two.  TL_LANES overrides
+// the choice for experiments.
+int pick_lanes(int mode, int S) {
+  int lanes = 2;
+  if (mode == MODE_SPOT_EVAL) lanes = 4;
+  else if (mode == MODE_SPOT_GRAD) lanes = (S <= 12) ? TL_DEFAULT_LANES_SPOT : 2;
+  else lanes = (S <= 12) ? TL_DEFAULT_LANES_BWD : 2;
+  if (const char *env = getenv("TL_LANES")) {
+    const int v = atoi(env);
+    if ((v == 2 || v == 4) && mode != MODE_SPOT_EVAL && !(mode == MODE_BWD && S > 16)) lanes = v;
+  }
+  return lanes;
+}
+
+template <int MODE, class V>
+AdjKernel adj_kernel_for(int S) {
+  if constexpr (MODE == MODE_SPOT_EVAL) {
+    return k_trace_adj<1, MODE_SPOT_EVAL, V>;
+  } else {
+    if (S <= 4) return k_trace_adj<4, MODE, V>;
+    if (S <= 8) return k_trace_adj<8, MODE, V>;
+    if (S <= 12) return k_trace_adj<12, MODE, V>;
+    return k_trace_adj<16, MODE, V>;
+  }
+}
+
+AdjVariant select_adj(int mode, int S) {
+  AdjVariant v;
+  v.lanes = pick_lanes(mode, S);
+  if (mode == MODE_SPOT_EVAL) {
+    v.kernel = adj_kernel_for<MODE_SPOT_EVAL, f4>(S);
+  } else if (mode == MODE_SPOT_GRAD) {
+    v.kernel = v.lanes == 4 ? adj_kernel_for<MODE_SPOT_GRAD, f4>(S) : adj_kernel_for<MODE_SPOT_GRAD, f2>(S);
+  } else if (S > 16) {
+    v.kernel = k_trace_adj<32, MODE_BWD, f2>;
+  } else {
+    v.kernel = v.lanes == 4 ? adj_kernel_for<MODE_BWD, f4>(S) : adj_kernel_for<MODE_BWD, f2>(S);
+  }
+  return v;
+}
+
+struct AdjPlan {
+  AdjVariant variant;
+  int n_blocks = 1, groups_per_row = 1, max_seg = 1, n_acc = 0;
+  size_t smem = 0;
+  size_t partial_bytes = 0;
+};
+
+size_t align8(size_t v) { return (v + 7) & ~(size_t)7; }
+
+int plan_adj(const TlProblem &pb, int mode, AdjPlan &pl) {
+  DeviceInfo info;
+  int rc = device_info(info);
+  if (rc) return rc;
+  pl.variant = select_adj(mode, pb.S);
+  pl.n_acc = n_acc_of(mode, pb.S);
+  const int lanes = pl.variant.lanes;
+  const size_t table = ((5 * (size_t)pb.S + 3) & ~(size_t)3) * sizeof(float);
+  const size_t state = mode != MODE_SPOT_EVAL ? (size_t)4 * pb.S * kTraceThreads * lanes * sizeof(float) : 0;
+  const size_t red = (size_t)(kTraceThreads / 32) * pl.n_acc * sizeof(float) + 16;
+  pl.smem = table + (state > red ? state : red);
+  if (pl.smem > 227 * 1024) return fail(TL_ERR_INVALID, "surface count needs too much shared memory%s");
   if (pl.smem > 48 * 1024)
-    TL_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)pl.smem));
-  kernel<<<pl.n_blocks, kTraceThreads, pl.smem, stream>>>(pb, args);
+    TL_CHECK_CUDA(cudaFuncSetAttribute((const void *)pl.variant.kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  int per_sm = 0;
+  TL_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)pl.variant.kernel,
+                                                              kTraceThreads, pl.smem));
+  if (per_sm < 1) return fail(TL_ERR_CUDA, "kernel does not fit on an SM%s");
+  const int n_pupil = pb.p_end - pb.p_begin;
+  const int group = kTraceThreads * lanes;
+  pl.groups_per_row = (n_pupil + group - 1) / group;
+  const int64_t total = (int64_t)pb.B * pb.F * pb.W * pl.groups_per_row;
+  int64_t n_blocks = (int64_t)info.sms * per_sm;
+  if (n_blocks > total) n_blocks = total;
+  pl.n_blocks = (int)n_blocks;
+  const int64_t len = (total + n_blocks - 1) / n_blocks;          // longest slice
+  pl.max_seg = (int)((len - 1 + pl.groups_per_row - 1) / pl.groups_per_row + 1);
+  pl.partial_bytes = align8((size_t)pl.n_blocks * pl.max_seg * pl.n_acc * sizeof(double));
+  return TL_OK;
+}
+
+int launch_adj(const TlProblem &pb, AdjArgs &args, const AdjPlan &pl, cudaStream_t stream) {
+  args.groups_per_row = pl.groups_per_row;
+  args.max_seg = pl.max_seg;
+  args.n_acc = pl.n_acc;
+  TlProblem pb_copy = pb;
+  void *params[] = {(void *)&pb_copy, (void *)&args};
+  TL_CHECK_CUDA(cudaLaunchKernel((const void *)pl.variant.kernel, dim3(pl.n_blocks), dim3(kTraceThreads),
+                                 params, pl.smem, stream));
+  g_launches++;
+  return TL_OK;
+}
+
+int reduce_rows(const AdjPlan &pl, const double *partial, double *rows_out, int rows,
+                cudaStream_t stream) {
+  const int64_t n = (int64_t)rows * pl.n_acc;
+  k_reduce_rows<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(partial, rows_out, rows,
+                                                                 pl.groups_per_row, pl.n_blocks,
+                                                                 pl.max_seg, pl.n_acc);
   g_launches++;
   TL_CHECK_CUDA(cudaGetLastError());
   return TL_OK;
 }
-
-int dispatch_adj(int mode, const TlProblem &pb, const AdjArgs &args, const Plan &pl,
-                 cudaStream_t stream) {
-  const int S = pb.S;
-  if (mode == MODE_SPOT_EVAL) return launch_adj<1, MODE_SPOT_EVAL>(pb, args, pl, stream);
-  if (mode == MODE_SPOT_GRAD) {
-    if (S <= 4) return launch_adj<4, MODE_SPOT_GRAD>(pb, args, pl, stream);
-    if (S <= 8) return launch_adj<8, MODE_SPOT_GRAD>(pb, args, pl, stream);
-    if (S <= 12) return launch_adj<12, MODE_SPOT_GRAD>(pb, args, pl, stream);
-    return launch_adj<16, MODE_SPOT_GRAD>(pb, args, pl, stream);
-  }
-  if (S <= 4) return launch_adj<4, MODE_BWD>(pb, args, pl, stream);
-  if (S <= 8) return launch_adj<8, MODE_BWD>(pb, args, pl, stream);
-  if (S <= 12) return launch_adj<12, MODE_BWD>(pb, args, pl, stream);
-  if (S <= 16) return launch_adj<16, MODE_BWD>(pb, args, pl, stream);
-  return launch_adj<32, MODE_BWD>(pb, args, pl, stream);
-}
-
-int plan_adj(const TlProblem &pb, int mode, Plan &pl) {
-  DeviceInfo info;
-  int rc = device_info(info);
-  if (rc) return rc;
-  const int n_acc = n_acc_of(mode, pb.S);
-  const size_t smem = adj_smem_bytes(pb.S, n_acc, mode != MODE_SPOT_EVAL);
-  if (smem > 227 * 1024) return fail(TL_ERR_INVALID, "surface count needs too much shared memory%s");
-  int per_sm = (int)((200 * 1024) / (smem > 1024 ? smem : 1024));
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
-  const int n_pupil = pb.p_end - pb.p_begin;
-  pl = make_plan(info.sms, pb.B * pb.F * pb.W, n_pupil, kTraceThreads, per_sm);
-  pl.smem = smem;
-  return TL_OK;
-}
-
-size_t align8(size_t v) { return (v + 7) & ~(size_t)7; }
 
 }  // namespace
 
@@ -726,7 +924,7 @@ int tl_trace_fwd(const TlProblem *pb, const TlTraceOut *out, void *stream_) {
   DeviceInfo info;
   rc = device_info(info);
   if (rc) return rc;
-  const Plan pl = make_plan(info.sms, pb->B * pb->F * pb->W, pb->P, kFwdThreads, 4);
+  const FwdPlan pl = make_fwd_plan(info.sms, pb->B * pb->F * pb->W, pb->P, 2 * kFwdThreads, 4);
   const size_t smem = 5 * (size_t)pb->S * sizeof(float);
   k_trace_fwd<<<pl.n_blocks, kFwdThreads, smem, (cudaStream_t)stream_>>>(*pb, *out, pl.nchunks,
                                                                          pl.chunk_len);
@@ -740,11 +938,9 @@ size_t tl_trace_bwd_workspace(const TlProblem *pb) {
   TlProblem full = *pb;
   full.p_begin = 0;
   full.p_end = pb->P;
-  Plan pl;
+  AdjPlan pl;
   if (plan_adj(full, MODE_BWD, pl)) return 0;
-  const size_t n_acc = n_acc_of(MODE_BWD, pb->S);
-  return align8((size_t)pl.n_blocks * n_acc * sizeof(double)) +
-         align8((size_t)pb->B * pb->F * pb->W * n_acc * sizeof(double));
+  return pl.partial_bytes + align8((size_t)pb->B * pb->F * pb->W * pl.n_acc * sizeof(double));
 }
 
 int tl_trace_bwd(const TlProblem *pb_, const TlSeeds *seeds, const TlGrads *grads, void *workspace,
@@ -756,31 +952,24 @@ int tl_trace_bwd(const TlProblem *pb_, const TlSeeds *seeds, const TlGrads *grad
   TlProblem pb = *pb_;
   pb.p_begin = 0;
   pb.p_end = pb.P;
-  Plan pl;
+  AdjPlan pl;
   rc = plan_adj(pb, MODE_BWD, pl);
   if (rc) return rc;
-  const int n_acc = n_acc_of(MODE_BWD, pb.S);
-  const size_t part_bytes = align8((size_t)pl.n_blocks * n_acc * sizeof(double));
   const int rows = pb.B * pb.F * pb.W;
-  const size_t rows_bytes = align8((size_t)rows * n_acc * sizeof(double));
-  if (!workspace || workspace_bytes < part_bytes + rows_bytes)
+  const size_t rows_bytes = align8((size_t)rows * pl.n_acc * sizeof(double));
+  if (!workspace || workspace_bytes < pl.partial_bytes + rows_bytes)
     return fail(TL_ERR_WORKSPACE, "workspace too small for tl_trace_bwd%s");
   cudaStream_t stream = (cudaStream_t)stream_;
   AdjArgs args;
+  memset(&args, 0, sizeof(args));
   args.seeds = *seeds;
   args.grads = *grads;
   args.partial = (double *)workspace;
-  args.ref_y = nullptr;
-  args.nchunks = pl.nchunks;
-  args.chunk_len = pl.chunk_len;
-  args.n_acc = n_acc;
-  rc = dispatch_adj(MODE_BWD, pb, args, pl, stream);
+  rc = launch_adj(pb, args, pl, stream);
   if (rc) return rc;
-  double *rowbuf = (double *)((char *)workspace + part_bytes);
-  const int64_t n = (int64_t)rows * n_acc;
-  k_reduce_chunks<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(args.partial, rowbuf, rows,
-                                                                   pl.nchunks, n_acc);
-  g_launches++;
+  double *rowbuf = (double *)((char *)workspace + pl.partial_bytes);
+  rc = reduce_rows(pl, args.partial, rowbuf, rows, stream);
+  if (rc) return rc;
   const int outs = pb.B * (2 * pb.S + pb.W * pb.S + 1);
   k_bwd_finalize<<<(outs + 127) / 128, 128, 0, stream>>>(rowbuf, *grads, pb.B, pb.F, pb.W, pb.S);
   g_launches++;
@@ -839,10 +1028,9 @@ int32_t tl_spot_moment_count(int32_t S, int32_t want_grad) {
 size_t tl_spot_workspace(const TlProblem *pb, int32_t want_grad) {
   if (validate(pb, want_grad ? TL_MAX_SURFACES_SPOT : TL_MAX_SURFACES_FWD)) return 0;
   if (pb->p_begin < 0 || pb->p_end > pb->P || pb->p_end <= pb->p_begin) return 0;
-  const int mode = want_grad ? MODE_SPOT_GRAD : MODE_SPOT_EVAL;
-  Plan pl;
-  if (plan_adj(*pb, mode, pl)) return 0;
-  return align8((size_t)pl.n_blocks * n_acc_of(mode, pb->S) * sizeof(double));
+  AdjPlan pl;
+  if (plan_adj(*pb, want_grad ? MODE_SPOT_GRAD : MODE_SPOT_EVAL, pl)) return 0;
+  return pl.partial_bytes;
 }
 
 int tl_spot_accumulate(const TlProblem *pb, int32_t want_grad, double *moments, float *ref_y,
@@ -853,29 +1041,22 @@ int tl_spot_accumulate(const TlProblem *pb, int32_t want_grad, double *moments, 
     return fail(TL_ERR_INVALID, "empty or out-of-range pupil slice%s");
   if (!moments || !ref_y) return fail(TL_ERR_INVALID, "NULL moments/ref_y%s");
   const int mode = want_grad ? MODE_SPOT_GRAD : MODE_SPOT_EVAL;
-  Plan pl;
+  AdjPlan pl;
   rc = plan_adj(*pb, mode, pl);
   if (rc) return rc;
-  const int n_acc = n_acc_of(mode, pb->S);
-  if (!workspace || workspace_bytes < align8((size_t)pl.n_blocks * n_acc * sizeof(double)))
+  if (!workspace || workspace_bytes < pl.partial_bytes)
     return fail(TL_ERR_WORKSPACE, "workspace too small for tl_spot_accumulate%s");
   cudaStream_t stream = (cudaStream_t)stream_;
+  const int n_bf = pb->B * pb->F;
+  k_chief_rays<<<(n_bf + 127) / 128, 128, 0, stream>>>(*pb, ref_y);
+  g_launches++;
   AdjArgs args;
   memset(&args, 0, sizeof(args));
   args.partial = (double *)workspace;
   args.ref_y = ref_y;
-  args.nchunks = pl.nchunks;
-  args.chunk_len = pl.chunk_len;
-  args.n_acc = n_acc;
-  rc = dispatch_adj(mode, *pb, args, pl, stream);
+  rc = launch_adj(*pb, args, pl, stream);
   if (rc) return rc;
-  const int rows = pb->B * pb->F * pb->W;
-  const int64_t n = (int64_t)rows * n_acc;
-  k_reduce_chunks<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(args.partial, moments, rows,
-                                                                   pl.nchunks, n_acc);
-  g_launches++;
-  TL_CHECK_CUDA(cudaGetLastError());
-  return TL_OK;
+  return reduce_rows(pl, args.partial, moments, pb->B * pb->F * pb->W, stream);
 }
 
 int tl_spot_finalize(const double *moments, const float *ref_y, int32_t B, int32_t F, int32_t W,
