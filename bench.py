@@ -202,7 +202,7 @@ def main():
     launches_per_step = _native.launch_count() - before
 
     graph = None
-    if not args.no_graph and world == 1:
+    if not args.no_graph:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -247,16 +247,30 @@ def main():
     value = events_total / (ms_per_step * 1e-3)
 
     # ---- dominant kernel alone (tl_spot_accumulate), live CUDA events --------
-    k_starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    k_stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    # (replayed from a CUDA graph so that Python's launch preparation is not in the timing)
     plain = [a.detach() for a in ray_args]
     for _ in range(3):
         ops.spot_moments(*plain, shard=shard)
     torch.cuda.synchronize()
+    k_run = lambda: ops.spot_moments(*plain, shard=shard)
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            k_run()
+        torch.cuda.current_stream().wait_stream(side)
+        k_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(k_graph):
+            k_run()
+        k_run = k_graph.replay
+    except Exception as exc:
+        print(f'[bench] kernel graph capture failed: {exc}', file=sys.stderr)
+    k_starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k_stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     for i in range(args.steps):
         flush.zero_()
         k_starts[i].record()
-        ops.spot_moments(*plain, shard=shard)
+        k_run()
         k_stops[i].record()
     torch.cuda.synchronize()
     kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in zip(k_starts, k_stops))
@@ -273,42 +287,64 @@ def main():
     achieved = events_rank * (FLOPS_FWD + FLOPS_BWD) / (kernel_ms * 1e-3) / 1e12
     roofline = {'bound': 'fp32_fma', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
                 'frac': achieved / peak_tflops, 'traffic': None,
-                'kernel': 'k_trace_adj<12,SPOT_GRAD> (+k_reduce_chunks)', 'kernel_ms': kernel_ms,
+                'kernel': 'k_trace_adj<12,SPOT_GRAD,f4> (+k_chief_rays, k_reduce_rows: ~2% of the time)', 'kernel_ms': kernel_ms,
                 'flops_per_event': FLOPS_FWD + FLOPS_BWD,
                 'peak_source': f'{sms} SMs x 128 lanes x 2 flop x {sm_max_mhz:.0f} MHz '
                                f'(sm_max_mhz of MEASURED_PEAKS.json); algorithmic HBM bytes ~0, '
                                f'hbm peak {peaks.get("hbm_gbs")} GB/s is not the bound'}
 
     # ---- end to end through the public API, host buffers in, loss+grads out ---
-    host = {k: getattr(lens, k).detach().cpu().pin_memory() for k in ('c', 't', 'nd', 'v')}
-    host_epd = specs.epd.cpu().pin_memory()
-    host_hfov = specs.hfov.cpu().pin_memory()
-    h2d = sum(v.numel() * 4 for v in host.values()) + 8
-    d2h = 4 + (2 * S + lens.nd.shape[1]) * 4
+    # GraphedSpotStep: pinned host prescription -> H2D -> index model / pupil position / ray set
+    # -> fused trace+adjoint -> finalize -> chain rule -> D2H, captured once as a CUDA graph.
+    from torchoptics_b200 import GraphedSpotStep, lens_modeling as lm
+    host_lens = {k: getattr(lens, k).detach().cpu() for k in ('c', 't', 'nd', 'v')}
+    graphed = None
+    try:
+        graphed = GraphedSpotStep(tracer, specs, lens, shard=shard)
+    except Exception as exc:
+        print(f'[bench] GraphedSpotStep capture failed, e2e uses the eager API: {exc}', file=sys.stderr)
 
-    def e2e_step():
-        from torchoptics_b200 import lens_modeling as lm
-        dl = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    def e2e_eager_step():
+        dl = {k: v.pin_memory().to(dev, non_blocking=True) for k, v in host_lens.items()}
         for k in ('c', 't', 'nd'):
             dl[k].requires_grad_(True)
         lens_i = lm.Lens(lens.structure, dl['c'], dl['t'], dl['nd'], dl['v'])
-        specs_i = lm.Specs(lens.structure, host_epd.to(dev, non_blocking=True),
-                           host_hfov.to(dev, non_blocking=True))
-        rms, _ = tracer.spot_rms(specs_i, lens_i, shard=shard)
+        rms, _ = tracer.spot_rms(specs, lens_i, shard=shard)
         rms[0].backward()
         return rms[0].item(), [dl[k].grad.cpu() for k in ('c', 't', 'nd')]
 
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = events_total * args.steps / float(e2e_s.item())
+    def e2e_step():
+        if graphed is None:
+            return e2e_eager_step()
+        rms, grads = graphed(**host_lens)
+        return float(rms[0]), grads
+
+    def time_e2e(fn, n):
+        for _ in range(3):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        barrier()
+        secs = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(secs, op=dist.ReduceOp.MAX)
+        return float(secs.item())
+
+    e2e_secs = time_e2e(e2e_step, args.steps)
+    e2e_value = events_total * args.steps / e2e_secs
+    eager_steps = max(3, min(args.steps, 20))
+    eager_secs = time_e2e(e2e_eager_step, eager_steps)
+    if graphed is not None:
+        h2d, d2h = graphed.h2d_bytes, graphed.d2h_bytes
+    else:
+        h2d = sum(v.numel() * 4 for v in host_lens.values())
+        d2h = 4 + (2 * S + lens.nd.shape[1]) * 4
+    # the graphed and the eager API must agree
+    check_rms, _ = e2e_eager_step()
+    got_rms, _ = e2e_step()
+    assert abs(check_rms - got_rms) <= 1e-6 * abs(check_rms), (check_rms, got_rms)
 
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': 'events/s', 'n_gpus': world,
@@ -325,8 +361,11 @@ def main():
                            'arith': 'guarded'},
                 'clocks': clocks.summary(),
                 'e2e': {'value': e2e_value, 'unit': 'events/s', 'h2d_bytes_per_step': h2d,
-                        'd2h_bytes_per_step': d2h,
-                        'ms_per_step': float(e2e_s.item()) / args.steps * 1e3},
+                        'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_secs / args.steps * 1e3,
+                        'api': 'GraphedSpotStep (CUDA graph of the public RayTracer.spot_rms path)'
+                               if graphed is not None else 'RayTracer.spot_rms (eager)',
+                        'eager_api_value': events_total * eager_steps / eager_secs,
+                        'eager_api_ms_per_step': eager_secs / eager_steps * 1e3},
                 'gpu_launches': launches_per_step * args.steps,
                 'roofline': roofline}
         if world == 1 and not args.no_cpu_baseline:

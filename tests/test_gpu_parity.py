@@ -275,3 +275,25 @@ def test_batch_of_lenses_matches_single_lens_runs():
         g1, = torch.autograd.grad(r1[0], [one['c']])
         assert abs(r1[0].item() - rms[b].item()) <= 1e-6 * r1[0].item()
         assert _rel(gc[b].cpu().numpy(), g1[0].cpu().numpy()) <= 1e-5
+
+
+def test_graphed_step_equals_eager_api():
+    """GraphedSpotStep (one CUDA-graph launch from pinned host memory) returns what the
+    eager RayTracer.spot_rms + autograd path returns, also after the inputs change."""
+    from torchoptics_b200 import GraphedSpotStep
+    specs, lens = prescriptions.load_yaml('baseline_tessar.yml', DEV)
+    tracer = rt.RayTracer(mode='circular', n_rays=(24, 24), rel_fields=(0., 0.5, 0.707, 1.),
+                          wavelengths=('C', 'd', 'F'), default_device=DEV)
+    step = GraphedSpotStep(tracer, specs, lens)
+    host = {k: getattr(lens, k).detach().cpu() for k in ('c', 't', 'nd', 'v')}
+    for scale in (1.0, 1.01):
+        host_c = host['c'] * scale
+        rms, grads = step(c=host_c, t=host['t'], nd=host['nd'], v=host['v'])
+        leaves = {k: (host_c if k == 'c' else host[k]).to(DEV).requires_grad_(True) for k in host}
+        ref_rms, _ = tracer.spot_rms(specs, lm.Lens(lens.structure, leaves['c'], leaves['t'],
+                                                    leaves['nd'], leaves['v']))
+        ref = torch.autograd.grad(ref_rms.sum(), [leaves['c'], leaves['t'], leaves['nd']])
+        assert abs(float(rms[0]) - ref_rms[0].item()) <= 1e-6 * ref_rms[0].item()
+        for k, r in zip(('c', 't', 'nd'), ref):
+            assert _rel(grads[k].numpy(), r.cpu().numpy()) <= 1e-5, k
+    assert step.h2d_bytes > 0 and step.d2h_bytes > 0

@@ -10,5 +10,6 @@ from . import lens_modeling, ray_tracing_lite          # noqa: F401
 from . import ray_tracing_lite as ray_tracing          # noqa: F401  same API as the TF original
 from .lens_modeling import Lens, Specs, Structure      # noqa: F401
 from .ray_tracing_lite import RayTracer, compute_rms2d, trace_skew   # noqa: F401
+from .graph import GraphedSpotStep                      # noqa: F401
 
 __version__ = '0.1.0'

@@ -1,0 +1,83 @@
+"""CUDA-graph capture of one lens evaluation: host prescription in, RMS spot size
+and its gradients out, as ONE graph launch.
+
+The reference evaluates a lens with ``trace_rays`` + ``compute_rms2d`` +
+``.backward()`` -- about 2 200 eager kernel launches for a 7-surface lens
+(SURVEY.md section 6).  Here the whole evaluation
+
+    pinned host (c, t, nd, v)  --H2D-->  index model, paraxial pupil position, ray set
+    (torch, ~60 tiny kernels)  -->  fused trace + adjoint kernel  -->  finalize  -->
+    chain rule back to (c, t, nd, v)  --D2H-->  pinned host (rms, gradients)
+
+is captured once and replayed, so a step costs one launch plus the kernels' own
+time: CUDA streams and graphs instead of a tracing compiler.  Shapes are static
+(the lens structure, ray counts, fields and wavelengths are fixed at capture).
+"""
+from __future__ import annotations
+
+import torch
+
+from .lens_modeling import Lens, Specs
+
+
+class GraphedSpotStep:
+    """``step(c, t, nd, v) -> (rms [B], {'c','t','nd','v': gradient of sum(rms)})``.
+
+    ``tracer`` / ``specs`` / ``lens`` fix the structure and sizes; the prescription
+    values themselves are inputs of every call (CPU tensors of the lens' 2-D padded
+    shapes, or None to keep the previous value).  With ``shard=(rank, world)`` every
+    rank traces its slice of the pupil and the graph contains the NCCL all-reduce.
+    """
+
+    PARAMS = ('c', 't', 'nd', 'v')
+
+    def __init__(self, tracer, specs, lens, shard=(0, 1), group=None, warmup=3):
+        dev = torch.device(tracer.default_device)
+        if dev.type != 'cuda':
+            raise ValueError('GraphedSpotStep needs a CUDA tracer')
+        self.device = dev
+        self.tracer, self.shard, self.group = tracer, shard, group
+        self.structure = lens.structure
+        self.host_in = {k: getattr(lens, k).detach().to('cpu', torch.float32).contiguous().pin_memory()
+                        for k in self.PARAMS}
+        self.dev_in = {k: v.to(dev) for k, v in self.host_in.items()}
+        self.specs = Specs(specs.structure, specs.epd.detach().to(dev), specs.hfov.detach().to(dev),
+                           specs.vig_up.detach().to(dev), specs.vig_down.detach().to(dev),
+                           specs.vig_x.detach().to(dev))
+        n_lens = len(lens)
+        self.host_out = {k: torch.empty_like(v).pin_memory() for k, v in self.host_in.items()}
+        self.host_rms = torch.empty((n_lens,), dtype=torch.float32).pin_memory()
+        self.h2d_bytes = sum(v.numel() * 4 for v in self.host_in.values())
+        self.d2h_bytes = sum(v.numel() * 4 for v in self.host_out.values()) + n_lens * 4
+        with torch.cuda.device(dev):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):      # warm-up outside capture (allocator, lazy init)
+                    self._body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._body()
+
+    def _body(self):
+        for k in self.PARAMS:
+            self.dev_in[k].copy_(self.host_in[k], non_blocking=True)
+        leaves = {k: self.dev_in[k].detach().requires_grad_(True) for k in self.PARAMS}
+        lens = Lens(self.structure, leaves['c'], leaves['t'], leaves['nd'], leaves['v'])
+        rms, _ = self.tracer.spot_rms(self.specs, lens, shard=self.shard, group=self.group)
+        grads = torch.autograd.grad(rms.sum(), [leaves[k] for k in self.PARAMS], allow_unused=True)
+        self.host_rms.copy_(rms.detach(), non_blocking=True)
+        for k, g in zip(self.PARAMS, grads):
+            if g is None:
+                g = torch.zeros_like(leaves[k])
+            self.host_out[k].copy_(g, non_blocking=True)
+
+    def __call__(self, c=None, t=None, nd=None, v=None):
+        for k, val in (('c', c), ('t', t), ('nd', nd), ('v', v)):
+            if val is not None:
+                self.host_in[k].copy_(val)
+        self.graph.replay()
+        torch.cuda.current_stream(self.device).synchronize()
+        return self.host_rms, self.host_out

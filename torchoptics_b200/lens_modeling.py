@@ -122,11 +122,15 @@ class Structure:
 
     def up_to_stop(self):
         """Sub-structure in front of the aperture stop (lm:185-192)."""
-        n_keep = int(self.stop_idx.max())
-        before_stop = np.arange(n_keep)[None, :] < self.stop_idx[:, None]
-        return Structure(self.stop_idx, self.mask[:, :n_keep] & before_stop,
-                         self.mask_G[:, :n_keep] & before_stop,
-                         default_device=self.default_device)
+        cached = getattr(self, '_front', None)
+        if cached is None:       # built once: masks are immutable, and a fresh host->device
+            n_keep = int(self.stop_idx.max())          # copy per call could not be graph-captured
+            before_stop = np.arange(n_keep)[None, :] < self.stop_idx[:, None]
+            cached = Structure(self.stop_idx, self.mask[:, :n_keep] & before_stop,
+                               self.mask_G[:, :n_keep] & before_stop,
+                               default_device=self.default_device)
+            self._front = cached
+        return cached
 
     def clone(self):
         return Structure(self.stop_idx.copy(), self.mask.copy(), self.mask_G.copy(),
@@ -190,6 +194,18 @@ class Specs:
             index = slice(index, index + 1)
         return Specs(self.structure[index], self.epd[index], self.hfov[index],
                      self.vig_up[index], self.vig_down[index], self.vig_x[index])
+
+
+_WL_CACHE = {}
+
+
+def _wavelength_tensor(wavelengths, dtype, device):
+    """Device tensor of the wavelength list, built once (a host->device copy per call
+    would also make the index model impossible to capture in a CUDA graph)."""
+    key = (wavelengths, dtype, str(device))
+    if key not in _WL_CACHE:
+        _WL_CACHE[key] = torch.tensor(wavelengths, dtype=dtype, device=device)
+    return _WL_CACHE[key]
 
 
 # --------------------------------------------------------------------------
@@ -333,7 +349,7 @@ class Lens:
         (n = nd).  The reference's version of that last fix-up (lm:372-373) only
         broadcasts for a batch of one lens; this one is the same for B = 1 and
         well defined for B > 1."""
-        wl = torch.as_tensor(list(wavelengths), dtype=self.nd.dtype, device=self.nd.device)
+        wl = _wavelength_tensor(tuple(float(w) for w in wavelengths), self.nd.dtype, self.nd.device)
         glass = self.structure.mask_G_torch
         # air slots carry v = NaN padding: keep it out of the arithmetic so that the
         # gradients of nd / v are 0 there instead of the reference's 0 * NaN

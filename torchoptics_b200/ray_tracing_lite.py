@@ -129,12 +129,22 @@ def reduce_abcd(abcd):
 
 def compute_pupil_position(lens):
     """Paraxial entrance-pupil position relative to the first vertex: B/A of the
-    system in front of the stop (rtl:330-350).  Differentiable w.r.t. the lens."""
-    front = lens.up_to_stop()
-    if front.structure.mask.shape[1] == 0:
-        return torch.zeros(len(front), device=lens.c.device)
-    nd = torch.cat((torch.ones_like(front.nd[:, 0:1]), front.nd), dim=1)
-    system = reduce_abcd(interface_propagation_abcd(front.c, front.t, nd))
+    system in front of the stop (rtl:330-350).  Differentiable w.r.t. the lens.
+
+    Works on the padded [B, Lmax] tensors directly (slots at or behind the stop
+    become identity matrices), so it launches no data-dependent-shape op and can be
+    captured in a CUDA graph."""
+    structure = lens.structure
+    n_front = int(structure.stop_idx.max())
+    if n_front == 0:
+        return torch.zeros(len(lens), device=lens.c.device)
+    front = structure.up_to_stop()
+    keep, keep_g = front.mask_torch, front.mask_G_torch
+    c = torch.where(keep, lens.c[:, :n_front], torch.zeros_like(lens.c[:, :n_front]))
+    t = torch.where(keep, lens.t[:, :n_front], torch.zeros_like(lens.t[:, :n_front]))
+    nd = torch.where(keep_g, lens.nd[:, :n_front], torch.ones_like(lens.nd[:, :n_front]))
+    nd = torch.cat((torch.ones_like(nd[:, 0:1]), nd), dim=1)
+    system = reduce_abcd(interface_propagation_abcd(c, t, nd))
     return system[:, 0, 1] / system[:, 0, 0]
 
 
@@ -275,6 +285,23 @@ class RayTracer:
             raise NotImplementedError('the CUDA ray-trace kernels compute in fp32 only')
         self.double_precision = False
         self.arith = arith
+        self._cache = {}
+
+    def _fields(self):
+        if 'fields' not in self._cache:
+            self._cache['fields'] = torch.tensor(self.rel_fields, dtype=torch.float32,
+                                                 device=self.default_device)
+        return self._cache['fields']
+
+    def _pupil(self, z):
+        """Relative pupil coordinates of the configured sampler.  Deterministic grids
+        are built once per tracer (they depend on nothing but the constructor
+        arguments); the random sampler draws afresh on every call like the reference."""
+        if self.mode == 'skew_random':
+            return self.pupil_span(z)
+        if 'pupil' not in self._cache:
+            self._cache['pupil'] = self.pupil_span(z)
+        return self._cache['pupil']
 
     # -- ray-set construction (rtl:80-124) ---------------------------------
     def _ray_set(self, specs, lens, use_vig=True, xy=None, up_to_stop=False):
@@ -283,8 +310,8 @@ class RayTracer:
         n = torch.cat((torch.ones_like(n[:, 0:1, :]), n), dim=1)          # air in front
         n = n.transpose(1, 2).reshape(n.shape[0], 1, 1, n.shape[2], -1)   # [B,1,1,W,S+1]
         z = compute_pupil_position(lens).reshape(-1, 1, 1, 1)
-        xp_rel, yp_rel = self.pupil_span(z) if xy is None else xy
-        fields = torch.tensor(self.rel_fields, dtype=torch.float32, device=dev)
+        xp_rel, yp_rel = self._pupil(z) if xy is None else xy
+        fields = self._fields()
         if use_vig and self.vig_fn is not None and self.mode != 'chief':
             xp_rel, yp_rel = self._vignette(specs, fields, xp_rel, yp_rel)
         if self.n_ray_aiming_iter > 0 and not up_to_stop:
@@ -293,7 +320,9 @@ class RayTracer:
         xp = scale_to_epd(xp_rel, specs.epd)
         yp = scale_to_epd(yp_rel, specs.epd)
         cy = torch.sin(specs.hfov[:, None] * fields[None, :])[..., None, None]   # [B,F,1,1]
-        cx = torch.zeros((1, 1, 1, 1), device=dev)
+        if 'cx' not in self._cache:
+            self._cache['cx'] = torch.zeros((1, 1, 1, 1), device=dev)
+        cx = self._cache['cx']
         c = lens.c.reshape(lens.c.shape[0], 1, 1, 1, -1)
         t = lens.t.reshape(lens.t.shape[0], 1, 1, 1, -1)
         mu = n[..., :-1] / n[..., 1:]
@@ -343,8 +372,7 @@ class RayTracer:
         x_tee = x_tee.expand(shape).contiguous()
         y_tee = y_tee.expand(shape).contiguous()
         if use_vig and self.vig_fn:
-            fields = torch.tensor(self.rel_fields, dtype=torch.float32, device=dev)
-            x_tee, y_tee = self._vignette(specs, fields, x_tee, y_tee)
+            x_tee, y_tee = self._vignette(specs, self._fields(), x_tee, y_tee)
         x_target, y_target = x_tee.clone(), y_tee.clone()
 
         correct = None
