@@ -165,6 +165,14 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
+    import faulthandler
+    # never hang a box: dump every thread's stack and exit if the whole run exceeds the limit
+    faulthandler.dump_traceback_later(float(os.environ.get('TL_BENCH_WATCHDOG_S', 600)), exit=True)
+
+    def note(msg):
+        if os.environ.get('TL_BENCH_VERBOSE'):
+            print(f'[bench rank {rank}] {msg}', file=sys.stderr, flush=True)
+
     import torch.distributed as dist
     from torchoptics_b200 import RayTracer, _native, ops, prescriptions
     from torchoptics_b200 import ray_tracing_lite as rt
@@ -196,12 +204,14 @@ def main():
         rms, _ = ops.spot_rms(*ray_args, True, _native.ARITH_GUARDED, shard, None)
         return rms, torch.autograd.grad(rms[0], leaves)
 
+    note('first eager step')
     before = _native.launch_count()
     step()
     torch.cuda.synchronize()
     launches_per_step = _native.launch_count() - before
 
     graph = None
+    note('capturing the step graph')
     if not args.no_graph:
         try:
             side = torch.cuda.Stream()
@@ -225,10 +235,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    note('warm-up')
     for _ in range(args.warmup):
         flush.zero_()
         run_step()
     barrier()
+    note('timed region')
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     with ClockSampler(local_rank) as clocks:
@@ -246,6 +258,7 @@ def main():
     ms_per_step = total_ms / args.steps
     value = events_total / (ms_per_step * 1e-3)
 
+    note('kernel-only timing')
     # ---- dominant kernel alone (tl_spot_accumulate), live CUDA events --------
     # (replayed from a CUDA graph so that Python's launch preparation is not in the timing)
     plain = [a.detach() for a in ray_args]
@@ -296,6 +309,7 @@ def main():
     # ---- end to end through the public API, host buffers in, loss+grads out ---
     # GraphedSpotStep: pinned host prescription -> H2D -> index model / pupil position / ray set
     # -> fused trace+adjoint -> finalize -> chain rule -> D2H, captured once as a CUDA graph.
+    note('end-to-end timing')
     from torchoptics_b200 import GraphedSpotStep, lens_modeling as lm
     host_lens = {k: getattr(lens, k).detach().cpu() for k in ('c', 't', 'nd', 'v')}
     graphed = None
@@ -372,6 +386,7 @@ def main():
             base = cpu_arm(5, 1)
             line['cpu_baseline'] = {k: base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
         print(json.dumps(line), flush=True)
+    faulthandler.cancel_dump_traceback_later()
     if world > 1:
         dist.destroy_process_group()
 

@@ -334,6 +334,9 @@ struct AdjArgs {
 #ifndef TL_ADJ_MIN_BLOCKS
 #define TL_ADJ_MIN_BLOCKS 1
 #endif
+#ifndef TL_ADJ_LOOPED
+#define TL_ADJ_LOOPED 0
+#endif
 
 template <int NS_MAX, int MODE, class V>
 __global__ void __launch_bounds__(kTraceThreads, TL_ADJ_MIN_BLOCKS)
@@ -493,9 +496,17 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
         V next_rcz;
         a = adjoint_image(tr.pre, sx, sy, scx, scy, next_rcz);
         Ray<V> next = tr.pre;
+#if TL_ADJ_LOOPED
+        // Rolled sweep: the ~260-instruction adjoint step stays resident in the instruction
+        // cache; the per-surface accumulators (registers) are reached through a uniform switch.
+#pragma unroll 1
+        for (int k = S - 1; k >= 0; --k) {
+#else
 #pragma unroll
         for (int k = NS_MAX - 1; k >= 0; --k) {
-          if (k < S) {
+          if (k >= S) continue;
+#endif
+          {
             const V *slot = state + (size_t)k * 4 * stride;
             Ray<V> in;
             in.x = slot[0];
@@ -508,14 +519,48 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
                                             V(tab.t[k > 0 ? k - 1 : 0]));
             const SurfaceGrad<V> g =
                 adjoint_surface(in, next, next_rcz, V(tab.c[k]), V(tab.mu[k]), V(tab.mu2[k]), a);
-            acc_c[k] += lane_sum(g.c);
-            acc_t[k] += lane_sum(g.t);
-            acc_mu[k] += lane_sum(g.mu);
+            const float s_c = lane_sum(g.c), s_t = lane_sum(g.t), s_mu = lane_sum(g.mu);
+            float w_c = 0.f, w_t = 0.f, w_mu = 0.f;
             if (MODE == MODE_SPOT_GRAD) {
-              wac_c[k] = lane_dot(wgt, g.c, wac_c[k]);
-              wac_t[k] = lane_dot(wgt, g.t, wac_t[k]);
-              wac_mu[k] = lane_dot(wgt, g.mu, wac_mu[k]);
+              w_c = lane_dot(wgt, g.c, 0.f);
+              w_t = lane_dot(wgt, g.t, 0.f);
+              w_mu = lane_dot(wgt, g.mu, 0.f);
             }
+#if TL_ADJ_LOOPED
+#define TL_ACC_CASE(K)                                          \
+  case K:                                                       \
+    if (K < NA) {                                               \
+      acc_c[K < NA ? K : 0] += s_c;                             \
+      acc_t[K < NA ? K : 0] += s_t;                             \
+      acc_mu[K < NA ? K : 0] += s_mu;                           \
+      if (MODE == MODE_SPOT_GRAD) {                             \
+        wac_c[K < NA ? K : 0] += w_c;                           \
+        wac_t[K < NA ? K : 0] += w_t;                           \
+        wac_mu[K < NA ? K : 0] += w_mu;                         \
+      }                                                         \
+    }                                                           \
+    break;
+            switch (k) {
+              TL_ACC_CASE(0) TL_ACC_CASE(1) TL_ACC_CASE(2) TL_ACC_CASE(3) TL_ACC_CASE(4)
+              TL_ACC_CASE(5) TL_ACC_CASE(6) TL_ACC_CASE(7) TL_ACC_CASE(8) TL_ACC_CASE(9)
+              TL_ACC_CASE(10) TL_ACC_CASE(11) TL_ACC_CASE(12) TL_ACC_CASE(13) TL_ACC_CASE(14)
+              TL_ACC_CASE(15) TL_ACC_CASE(16) TL_ACC_CASE(17) TL_ACC_CASE(18) TL_ACC_CASE(19)
+              TL_ACC_CASE(20) TL_ACC_CASE(21) TL_ACC_CASE(22) TL_ACC_CASE(23) TL_ACC_CASE(24)
+              TL_ACC_CASE(25) TL_ACC_CASE(26) TL_ACC_CASE(27) TL_ACC_CASE(28) TL_ACC_CASE(29)
+              TL_ACC_CASE(30) TL_ACC_CASE(31)
+              default: break;
+            }
+#undef TL_ACC_CASE
+#else
+            acc_c[k] += s_c;
+            acc_t[k] += s_t;
+            acc_mu[k] += s_mu;
+            if (MODE == MODE_SPOT_GRAD) {
+              wac_c[k] += w_c;
+              wac_t[k] += w_t;
+              wac_mu[k] += w_mu;
+            }
+#endif
             next = in;
             next_rcz = in_rcz;
           }
