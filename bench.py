@@ -388,7 +388,13 @@ def main():
         print(json.dumps(line), flush=True)
     faulthandler.cancel_dump_traceback_later()
     if world > 1:
-        dist.destroy_process_group()
+        # tearing the NCCL communicator down while captured graphs still reference it can block
+        # forever: drop the graphs, meet at a barrier and leave without the destructor chain
+        graph = graphed = k_graph = None
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':
