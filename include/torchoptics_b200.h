@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TL_ABI_VERSION 1
+#define TL_ABI_VERSION 2
 
 enum {
   TL_OK = 0,
@@ -75,6 +75,8 @@ typedef struct TlProblem {
   int32_t arith;               /* TL_ARITH_*                                       */
   int32_t p_begin, p_end;      /* pupil slice [p_begin,p_end) traced by this call
                                   (tl_spot_accumulate only; shards rays over GPUs) */
+  const float *xy_scale;       /* [B] or NULL: x and y are multiplied by xy_scale[b] on load
+                                  (relative pupil coordinates * EPD/2, scale_to_epd rtl:497-507) */
 } TlProblem;
 
 /* Outputs of trace_skew, each a contiguous [B,F,P,W] array. */
@@ -145,6 +147,30 @@ int tl_spot_accumulate(const TlProblem *pb, int32_t want_grad, double *moments, 
 int tl_spot_finalize(const double *moments, const float *ref_y, int32_t B, int32_t F, int32_t W,
                      int32_t S, int64_t P_total, int32_t want_grad, const TlSpotOut *out,
                      void *stream);
+
+/* Ray-set staging of RayTracer.trace_rays (rtl:80-124) and its chain rule, as two small
+ * kernels instead of ~60 eager tensor ops: the two-term dispersion model n(lambda) of
+ * Lens.get_refractive_indices (lens_modeling.py:355-374), the index ratios mu = n/n'
+ * (rtl:123), the paraxial entrance-pupil position z = B/A of the ABCD product in front of
+ * the stop (compute_pupil_position rtl:330-350) and cy = sin(hfov * rel_field) (rtl:116).
+ * Prescriptions are the padded [B,L] tensors of lens_modeling.Lens. */
+typedef struct TlLens {
+  const float *c, *t, *nd, *v;        /* [B,L]                                       */
+  const uint8_t *mask, *mask_g;       /* [B,L] surface present / followed by glass   */
+  const int32_t *stop_idx;            /* [B]                                         */
+  const float *hfov;                  /* [B] half field of view [rad]                */
+  const float *epd;                   /* [B] entrance pupil diameter                 */
+  const float *rel_fields;            /* [F]                                         */
+  const float *wavelengths;           /* [W] nm                                      */
+  int32_t B, L, F, W;
+} TlLens;
+
+/* mu [B,W,L], z [B], cy [B,F], half_epd [B] (= the xy_scale of TlProblem) */
+int tl_stage_fwd(const TlLens *lens, float *mu, float *z, float *cy, float *half_epd, void *stream);
+/* Chain rule: given d loss / d mu [B,W,L] and d loss / d z [B], ADDS the induced gradients to
+ * gc, gt, gnd, gv [B,L] (which the caller pre-fills, e.g. with the direct c / t gradients). */
+int tl_stage_bwd(const TlLens *lens, const float *gmu, const float *gz, float *gc, float *gt,
+                 float *gnd, float *gv, void *stream);
 
 /* Number of kernels this library has launched since it was loaded (bench.py's
  * gpu_launches counter). */

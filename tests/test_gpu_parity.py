@@ -297,3 +297,26 @@ def test_graphed_step_equals_eager_api():
         for k, r in zip(('c', 't', 'nd'), ref):
             assert _rel(grads[k].numpy(), r.cpu().numpy()) <= 1e-5, k
     assert step.h2d_bytes > 0 and step.d2h_bytes > 0
+
+
+@pytest.mark.parametrize('lens_file', ['baseline_cooke.yml', 'baseline_tessar.yml', 'baseline_doublet.yml',
+                                       'singlet_lens.yml'])
+def test_staging_kernels_equal_torch_front_end(lens_file):
+    """tl_stage_fwd / tl_stage_bwd (index model, pupil position, field cosines and their chain
+    rule) against the same quantities computed by the host torch code and autograd."""
+    specs, lens = prescriptions.load_yaml(lens_file, DEV)
+    tracer = rt.RayTracer(mode='circular', n_rays=(16, 12), rel_fields=(0., 0.4, 0.707, 1.),
+                          wavelengths=('C', 'd', 'F', 546.1), default_device=DEV)
+
+    def run(staged):
+        leaves = [getattr(lens, k).detach().clone().requires_grad_(True) for k in ('c', 't', 'nd', 'v')]
+        rms, field = tracer.spot_rms(specs, lm.Lens(lens.structure, *leaves), staged=staged)
+        return rms, field, torch.autograd.grad(rms.sum(), leaves)
+
+    rms_a, field_a, g_a = run(True)
+    rms_b, field_b, g_b = run(False)
+    assert abs(rms_a[0].item() - rms_b[0].item()) <= 1e-5 * rms_b[0].item()   # RMS_TOL: z differs by the ABCD product order
+    assert torch.allclose(field_a, field_b, rtol=1e-5)
+    for name, a, b in zip(('c', 't', 'nd', 'v'), g_a, g_b):
+        a, b = np.nan_to_num(a.cpu().numpy()), np.nan_to_num(b.cpu().numpy())
+        assert _rel(a, b) <= 2e-5, (name, _rel(a, b))

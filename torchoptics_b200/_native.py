@@ -35,7 +35,8 @@ class TlProblem(ctypes.Structure):
                 ('B', ctypes.c_int32), ('F', ctypes.c_int32), ('P', ctypes.c_int32),
                 ('W', ctypes.c_int32), ('S', ctypes.c_int32),
                 ('allow_backward_rays', ctypes.c_int32), ('arith', ctypes.c_int32),
-                ('p_begin', ctypes.c_int32), ('p_end', ctypes.c_int32)]
+                ('p_begin', ctypes.c_int32), ('p_end', ctypes.c_int32),
+                ('xy_scale', ctypes.c_void_p)]
 
 
 class TlTraceOut(ctypes.Structure):
@@ -48,6 +49,12 @@ class TlSeeds(ctypes.Structure):
 
 class TlGrads(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ('gc', 'gt', 'gmu', 'gz_sum', 'gx', 'gy', 'gz', 'gcx', 'gcy')]
+
+
+class TlLens(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ('c', 't', 'nd', 'v', 'mask', 'mask_g', 'stop_idx', 'hfov',
+                                               'epd', 'rel_fields', 'wavelengths')] + \
+               [(n, ctypes.c_int32) for n in ('B', 'L', 'F', 'W')]
 
 
 class TlSpotOut(ctypes.Structure):
@@ -74,6 +81,8 @@ EXPORTS = {
     'tl_spot_accumulate': (ctypes.c_int, [ctypes.POINTER(TlProblem), ctypes.c_int32, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                           ctypes.c_void_p]),
+    'tl_stage_fwd': (ctypes.c_int, [ctypes.POINTER(TlLens)] + [ctypes.c_void_p] * 5),
+    'tl_stage_bwd': (ctypes.c_int, [ctypes.POINTER(TlLens)] + [ctypes.c_void_p] * 7),
     'tl_spot_finalize': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int32] * 4 +
                          [ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(TlSpotOut), ctypes.c_void_p]),
 }
@@ -95,7 +104,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.tl_abi_version() != 1:
+    if lib.tl_abi_version() != 2:
         raise NativeLibraryError('libtorchoptics_b200.so: ABI version mismatch, rebuild it')
     _lib = lib
     return lib

@@ -266,8 +266,13 @@ k_trace_fwd(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
     const int p1 = p0 + kFwdThreads;
     const bool has1 = p1 < p_hi;
     const int q1 = has1 ? p1 : p0;
-    const f2 x(pb.x.ptr[offset_of(pb.x, b, f, p0, w)], pb.x.ptr[offset_of(pb.x, b, f, q1, w)]);
-    const f2 y(pb.y.ptr[offset_of(pb.y, b, f, p0, w)], pb.y.ptr[offset_of(pb.y, b, f, q1, w)]);
+    const float xy_scale = pb.xy_scale ? pb.xy_scale[b] : 1.0f;
+    f2 x(pb.x.ptr[offset_of(pb.x, b, f, p0, w)], pb.x.ptr[offset_of(pb.x, b, f, q1, w)]);
+    f2 y(pb.y.ptr[offset_of(pb.y, b, f, p0, w)], pb.y.ptr[offset_of(pb.y, b, f, q1, w)]);
+    if (pb.xy_scale) {          // one rounding per coordinate, like y * epd / 2 (rtl:505)
+      x = x * f2(xy_scale);
+      y = y * f2(xy_scale);
+    }
     const f2 z(pb.z.ptr[offset_of(pb.z, b, f, p0, w)], pb.z.ptr[offset_of(pb.z, b, f, q1, w)]);
     const f2 cx(pb.cx.ptr[offset_of(pb.cx, b, f, p0, w)], pb.cx.ptr[offset_of(pb.cx, b, f, q1, w)]);
     const f2 cy(pb.cy.ptr[offset_of(pb.cy, b, f, p0, w)], pb.cy.ptr[offset_of(pb.cy, b, f, q1, w)]);
@@ -287,25 +292,24 @@ k_trace_fwd(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
   }
 }
 
-// Reference height of every (lens, field): the image height of the exact-policy
-// chief ray (pupil centre) at wavelength 0.  The spot sums are centred on it; it
-// depends only on the prescription, so every rank computes the same value.
+// Reference height of every (lens, field): the image height of the chief ray (pupil
+// centre) at wavelength 0, traced with the fast policy.  The spot sums are centred on
+// it; any value near the centroid does (it cancels exactly in k_spot_finalize), it only
+// has to be the same number on every CTA and every rank -- it depends on nothing but the
+// prescription and is computed by the same instruction sequence everywhere.
 __global__ void k_chief_rays(TlProblem pb, float *ref_y) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pb.B * pb.F) return;
   const int b = i / pb.F, f = i % pb.F, S = pb.S;
-  const bool allow_backward = pb.allow_backward_rays != 0;
-  Ray<float> r{0.f, 0.f, pb.z.ptr[offset_of(pb.z, b, f, 0, 0)],
-               pb.cx.ptr[offset_of(pb.cx, b, f, 0, 0)], pb.cy.ptr[offset_of(pb.cy, b, f, 0, 0)], 0.f};
-  r.cz = exact_cz0(r.cx, r.cy);
-  bool ok = true, backward = false;
+  const float cx = pb.cx.ptr[offset_of(pb.cx, b, f, 0, 0)], cy = pb.cy.ptr[offset_of(pb.cy, b, f, 0, 0)];
+  Ray<float> r{0.f, 0.f, pb.z.ptr[offset_of(pb.z, b, f, 0, 0)], cx, cy, fast_cz0(cx, cy)};
+  float min_cos2 = 1.0f, travel;
   for (int k = 0; k < S; ++k) {
-    const Surface s{pb.c[(int64_t)b * S + k], pb.t[(int64_t)b * S + k],
-                    pb.mu[((int64_t)b * pb.W) * S + k]};
-    exact_surface(r, s, k > 0 && pb.live[(int64_t)b * S + k - 1], allow_backward, ok, backward);
+    const float mu = pb.mu[((int64_t)b * pb.W) * S + k];
+    fast_surface(r, pb.c[(int64_t)b * S + k], mu, mu * mu, pb.t[(int64_t)b * S + k], min_cos2, travel);
   }
-  exact_image(r, pb.live[(int64_t)b * S + S - 1] != 0, allow_backward, ok, backward);
-  ref_y[i] = (ok && fabsf(r.y) < 3.0e38f) ? r.y : 0.f;
+  fast_image(r);
+  ref_y[i] = (min_cos2 > kGuard && fabsf(r.y) < 3.0e38f) ? r.y : 0.f;
 }
 
 // --------------------------------------------------------------------------
@@ -333,9 +337,6 @@ struct AdjArgs {
 
 #ifndef TL_ADJ_MIN_BLOCKS
 #define TL_ADJ_MIN_BLOCKS 1
-#endif
-#ifndef TL_ADJ_LOOPED
-#define TL_ADJ_LOOPED 0
 #endif
 
 template <int NS_MAX, int MODE, class V>
@@ -367,7 +368,7 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
   float acc_z = 0.f, wac_z = 0.f;
   float m_s1 = 0.f, m_s2 = 0.f, m_n = 0.f;
   Table tab;
-  float y0 = 0.f;
+  float y0 = 0.f, xy_scale = 1.0f;
   int row = -1, seg = 0, b = 0, f = 0, w = 0;
 
   auto flush = [&]() {
@@ -429,6 +430,7 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
       f = (r / pb.W) % pb.F;
       b = r / (pb.W * pb.F);
       tab = load_table(smem, pb, b, w);
+      xy_scale = pb.xy_scale ? pb.xy_scale[b] : 1.0f;
       if (kSpot) y0 = args.ref_y[b * pb.F + f];
 #pragma unroll
       for (int k = 0; k < NA; ++k) {
@@ -449,8 +451,8 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
       has[l] = p < pb.p_end;
       const int q = has[l] ? p : p_base;          // past the end: a copy of lane 0 (p_base is valid)
       o[l] = (((int64_t)b * pb.F + f) * pb.P + q) * pb.W + w;
-      lane_set(x, l, pb.x.ptr[offset_of(pb.x, b, f, q, w)]);
-      lane_set(y, l, pb.y.ptr[offset_of(pb.y, b, f, q, w)]);
+      lane_set(x, l, __fmul_rn(pb.x.ptr[offset_of(pb.x, b, f, q, w)], xy_scale));
+      lane_set(y, l, __fmul_rn(pb.y.ptr[offset_of(pb.y, b, f, q, w)], xy_scale));
       lane_set(z, l, pb.z.ptr[offset_of(pb.z, b, f, q, w)]);
       lane_set(cx, l, pb.cx.ptr[offset_of(pb.cx, b, f, q, w)]);
       lane_set(cy, l, pb.cy.ptr[offset_of(pb.cy, b, f, q, w)]);
@@ -496,16 +498,9 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
         V next_rcz;
         a = adjoint_image(tr.pre, sx, sy, scx, scy, next_rcz);
         Ray<V> next = tr.pre;
-#if TL_ADJ_LOOPED
-        // Rolled sweep: the ~260-instruction adjoint step stays resident in the instruction
-        // cache; the per-surface accumulators (registers) are reached through a uniform switch.
-#pragma unroll 1
-        for (int k = S - 1; k >= 0; --k) {
-#else
 #pragma unroll
         for (int k = NS_MAX - 1; k >= 0; --k) {
           if (k >= S) continue;
-#endif
           {
             const V *slot = state + (size_t)k * 4 * stride;
             Ray<V> in;
@@ -526,32 +521,6 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
               w_t = lane_dot(wgt, g.t, 0.f);
               w_mu = lane_dot(wgt, g.mu, 0.f);
             }
-#if TL_ADJ_LOOPED
-#define TL_ACC_CASE(K)                                          \
-  case K:                                                       \
-    if (K < NA) {                                               \
-      acc_c[K < NA ? K : 0] += s_c;                             \
-      acc_t[K < NA ? K : 0] += s_t;                             \
-      acc_mu[K < NA ? K : 0] += s_mu;                           \
-      if (MODE == MODE_SPOT_GRAD) {                             \
-        wac_c[K < NA ? K : 0] += w_c;                           \
-        wac_t[K < NA ? K : 0] += w_t;                           \
-        wac_mu[K < NA ? K : 0] += w_mu;                         \
-      }                                                         \
-    }                                                           \
-    break;
-            switch (k) {
-              TL_ACC_CASE(0) TL_ACC_CASE(1) TL_ACC_CASE(2) TL_ACC_CASE(3) TL_ACC_CASE(4)
-              TL_ACC_CASE(5) TL_ACC_CASE(6) TL_ACC_CASE(7) TL_ACC_CASE(8) TL_ACC_CASE(9)
-              TL_ACC_CASE(10) TL_ACC_CASE(11) TL_ACC_CASE(12) TL_ACC_CASE(13) TL_ACC_CASE(14)
-              TL_ACC_CASE(15) TL_ACC_CASE(16) TL_ACC_CASE(17) TL_ACC_CASE(18) TL_ACC_CASE(19)
-              TL_ACC_CASE(20) TL_ACC_CASE(21) TL_ACC_CASE(22) TL_ACC_CASE(23) TL_ACC_CASE(24)
-              TL_ACC_CASE(25) TL_ACC_CASE(26) TL_ACC_CASE(27) TL_ACC_CASE(28) TL_ACC_CASE(29)
-              TL_ACC_CASE(30) TL_ACC_CASE(31)
-              default: break;
-            }
-#undef TL_ACC_CASE
-#else
             acc_c[k] += s_c;
             acc_t[k] += s_t;
             acc_mu[k] += s_mu;
@@ -560,7 +529,6 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
               wac_t[k] += w_t;
               wac_mu[k] += w_mu;
             }
-#endif
             next = in;
             next_rcz = in_rcz;
           }
@@ -634,17 +602,27 @@ __global__ void k_bwd_finalize(const double *rows, TlGrads g, int B, int F, int 
 }
 
 // moments[b,f,w][n_acc] -> rms, rms_field and (want_grad) gradients.  One CTA per lens.
-__global__ void k_spot_finalize(const double *mom, const float *ref_y, int B, int F, int W, int S,
-                                double n_rays, int want_grad, TlSpotOut out) {
-  extern __shared__ double sh[];   // alpha[F], shift[F], rms[F]
+// The lens' rows are first staged in shared memory with coalesced loads (STAGED), so the
+// dependent fp64 sums below do not each wait for a global-memory round trip.
+template <bool STAGED>
+__global__ void k_spot_finalize(const double *mom_global, const float *ref_y, int B, int F, int W,
+                                int S, double n_rays, int want_grad, TlSpotOut out) {
+  extern __shared__ double sh[];   // alpha[F], shift[F], rms[F], then (STAGED) the rows
   double *alpha = sh, *shift = sh + F, *rmsf = sh + 2 * F;
   const int b = blockIdx.x;
   const int n_acc = want_grad ? 6 * S + 5 : 3;
   const int m0 = want_grad ? 6 * S + 2 : 0;
+  const double *mom = mom_global + (int64_t)b * F * W * n_acc;    // this lens' rows
+  if (STAGED) {
+    double *rows = sh + 3 * F;
+    for (int i = threadIdx.x; i < F * W * n_acc; i += blockDim.x) rows[i] = mom[i];
+    __syncthreads();
+    mom = rows;
+  }
   for (int f = threadIdx.x; f < F; f += blockDim.x) {
     double s1 = 0.0, s2 = 0.0, n_ok = 0.0;
     for (int w = 0; w < W; ++w) {
-      const double *row = mom + (((int64_t)b * F + f) * W + w) * n_acc + m0;
+      const double *row = mom + ((int64_t)f * W + w) * n_acc + m0;
       s1 += row[0];
       s2 += row[1];
       n_ok += row[2];
@@ -676,7 +654,7 @@ __global__ void k_spot_finalize(const double *mom, const float *ref_y, int B, in
       for (int f = 0; f < F; ++f) {
         double a = 0.0, bsum = 0.0;
         for (int w = 0; w < W; ++w) {
-          const double *row = mom + (((int64_t)b * F + f) * W + w) * n_acc;
+          const double *row = mom + ((int64_t)f * W + w) * n_acc;
           a += row[base];
           bsum += row[base + S];
         }
@@ -687,7 +665,7 @@ __global__ void k_spot_finalize(const double *mom, const float *ref_y, int B, in
     } else if (j < 2 * S + W * S) {
       const int jj = j - 2 * S, w = jj / S, k = jj % S;
       for (int f = 0; f < F; ++f) {
-        const double *row = mom + (((int64_t)b * F + f) * W + w) * n_acc;
+        const double *row = mom + ((int64_t)f * W + w) * n_acc;
         s += alpha[f] * (row[4 * S + k] - shift[f] * row[5 * S + k]);
       }
       out.gmu[((int64_t)b * W + w) * S + k] = (float)s;
@@ -695,7 +673,7 @@ __global__ void k_spot_finalize(const double *mom, const float *ref_y, int B, in
       for (int f = 0; f < F; ++f) {
         double a = 0.0, bsum = 0.0;
         for (int w = 0; w < W; ++w) {
-          const double *row = mom + (((int64_t)b * F + f) * W + w) * n_acc;
+          const double *row = mom + ((int64_t)f * W + w) * n_acc;
           a += row[6 * S];
           bsum += row[6 * S + 1];
         }
@@ -793,6 +771,142 @@ __global__ void k_rms_bwd(const float *y, const uint8_t *ok, const double *stats
   const double *st = stats + bf * 4;
   const double dev = ok[i] ? ((double)y[i] - st[0]) : 0.0;
   gy[i] = (float)((double)grad_rms[bf / F] * st[2] * (dev - st[1]));
+}
+
+// --------------------------------------------------------------------------
+// Ray-set staging (RayTracer.trace_rays rtl:80-124) and its chain rule.
+// One CTA per lens; everything is O(L * W) scalars.
+// --------------------------------------------------------------------------
+constexpr int kStageMaxSurfaces = 64;
+constexpr double kLineC = 656.3, kLineD = 587.6, kLineF = 486.1;   // lens_modeling.py:362-364
+
+// n(lambda) of slot s (1 for air / padding), lens_modeling.py:355-374
+__device__ __forceinline__ float index_at(const TlLens &ln, int b, int s, float wl, float *dn_dnd,
+                                          float *dn_dv) {
+  const int64_t i = (int64_t)b * ln.L + s;
+  if (dn_dnd) *dn_dnd = 0.f;
+  if (dn_dv) *dn_dv = 0.f;
+  if (!ln.mask_g[i]) return 1.0f;
+  const float nd = ln.nd[i], v = ln.v[i];
+  if (v == 0.f) {                       // dispersion-free glass
+    if (dn_dnd) *dn_dnd = 1.f;
+    return nd;
+  }
+  // constants evaluated in double and rounded once, like the Python scalars of the host code
+  const float kk = (float)(1.0 / ((double)kLineF * kLineF) - 1.0 / ((double)kLineC * kLineC));
+  const float ld2 = (float)((double)kLineD * kLineD);
+  const float slope = (nd - 1.0f) / (v * kk);
+  const float offset = nd - slope / ld2;
+  const float span = 1.0f / (wl * wl) - 1.0f / ld2;
+  if (dn_dnd) *dn_dnd = 1.0f + span / (v * kk);
+  if (dn_dv) *dn_dv = -slope * span / v;
+  return offset + slope / (wl * wl);
+}
+
+__device__ __forceinline__ float nd_at(const TlLens &ln, int b, int s) {
+  const int64_t i = (int64_t)b * ln.L + s;
+  return ln.mask_g[i] ? ln.nd[i] : 1.0f;
+}
+
+// ABCD matrix of slot s in front of the stop (identity for padding), rtl:314-327
+struct Abcd {
+  float a, b, c, d;
+};
+__device__ __forceinline__ Abcd slot_matrix(const TlLens &ln, int b, int s, float *ratio_out,
+                                            float *power_out) {
+  const int64_t i = (int64_t)b * ln.L + s;
+  const bool on = ln.mask[i] && s < ln.stop_idx[b];
+  const float n_in = (s == 0) ? 1.0f : (on ? nd_at(ln, b, s - 1) : 1.0f);
+  const float n_out = on ? nd_at(ln, b, s) : 1.0f;
+  const float cc = on ? ln.c[i] : 0.f, tt = on ? ln.t[i] : 0.f;
+  const float ratio = n_in / n_out, power = cc * (ratio - 1.0f);
+  if (ratio_out) *ratio_out = ratio;
+  if (power_out) *power_out = power;
+  return Abcd{1.0f + power * tt, ratio * tt, power, ratio};
+}
+
+__global__ void k_stage_fwd(TlLens ln, float *mu, float *z, float *cy, float *half_epd) {
+  const int b = blockIdx.x;
+  if (threadIdx.x == 1 % blockDim.x) half_epd[b] = ln.epd[b] * 0.5f;
+  for (int i = threadIdx.x; i < ln.W * ln.L; i += blockDim.x) {
+    const int w = i / ln.L, s = i % ln.L;
+    const float wl = ln.wavelengths[w];
+    const float n_in = (s == 0) ? 1.0f : index_at(ln, b, s - 1, wl, nullptr, nullptr);
+    mu[((int64_t)b * ln.W + w) * ln.L + s] = n_in / index_at(ln, b, s, wl, nullptr, nullptr);
+  }
+  for (int f = threadIdx.x; f < ln.F; f += blockDim.x)
+    cy[(int64_t)b * ln.F + f] = sinf(ln.hfov[b] * ln.rel_fields[f]);
+  if (threadIdx.x == 0) {
+    Abcd m{1.f, 0.f, 0.f, 1.f};
+    const int n_front = min(ln.stop_idx[b], ln.L);
+    for (int s = 0; s < n_front; ++s) {                // M <- M_s M
+      const Abcd q = slot_matrix(ln, b, s, nullptr, nullptr);
+      m = Abcd{q.a * m.a + q.b * m.c, q.a * m.b + q.b * m.d, q.c * m.a + q.d * m.c,
+               q.c * m.b + q.d * m.d};
+    }
+    z[b] = n_front > 0 ? m.b / m.a : 0.f;
+  }
+}
+
+__global__ void k_stage_bwd(TlLens ln, const float *gmu, const float *gz, float *gc, float *gt,
+                            float *gnd, float *gv) {
+  const int b = blockIdx.x;
+  // ---- through mu[w,s] = n[w,s-1] / n[w,s]: one thread per slot gathers over wavelengths
+  for (int s = threadIdx.x; s < ln.L; s += blockDim.x) {
+    const int64_t i = (int64_t)b * ln.L + s;
+    if (!ln.mask_g[i]) continue;
+    float g_nd = 0.f, g_v = 0.f;
+    for (int w = 0; w < ln.W; ++w) {
+      const float wl = ln.wavelengths[w];
+      float dn_dnd, dn_dv;
+      const float n_s = index_at(ln, b, s, wl, &dn_dnd, &dn_dv);
+      const float n_in = (s == 0) ? 1.0f : index_at(ln, b, s - 1, wl, nullptr, nullptr);
+      const int64_t j = ((int64_t)b * ln.W + w) * ln.L + s;
+      float g_n = -gmu[j] * n_in / (n_s * n_s);                     // as denominator of mu[s]
+      if (s + 1 < ln.L)                                             // as numerator of mu[s+1]
+        g_n += gmu[j + 1] / index_at(ln, b, s + 1, wl, nullptr, nullptr);
+      g_nd += g_n * dn_dnd;
+      g_v += g_n * dn_dv;
+    }
+    gnd[i] += g_nd;
+    gv[i] += g_v;
+  }
+  __syncthreads();
+  // ---- through z = M01 / M00, M = M_{n-1} ... M_0 (thread 0, reverse sweep over the chain)
+  if (threadIdx.x != 0) return;
+  const int n_front = min(min(ln.stop_idx[b], ln.L), kStageMaxSurfaces);
+  if (n_front <= 0) return;
+  Abcd prefix[kStageMaxSurfaces];                      // P_s = M_{s-1} ... M_0
+  Abcd m{1.f, 0.f, 0.f, 1.f};
+  for (int s = 0; s < n_front; ++s) {
+    prefix[s] = m;
+    const Abcd q = slot_matrix(ln, b, s, nullptr, nullptr);
+    m = Abcd{q.a * m.a + q.b * m.c, q.a * m.b + q.b * m.d, q.c * m.a + q.d * m.c,
+             q.c * m.b + q.d * m.d};
+  }
+  const float gzz = gz[b];
+  Abcd g{-gzz * m.b / (m.a * m.a), gzz / m.a, 0.f, 0.f};        // adjoint of the full product
+  for (int s = n_front - 1; s >= 0; --s) {
+    // total = Q_s M_s P_s ; g holds Q_s^T G ; d M_s = g P_s^T
+    const Abcd p = prefix[s];
+    const Abcd dm{g.a * p.a + g.b * p.b, g.a * p.c + g.b * p.d, g.c * p.a + g.d * p.b,
+                  g.c * p.c + g.d * p.d};
+    float ratio, power;
+    const Abcd q = slot_matrix(ln, b, s, &ratio, &power);
+    const int64_t i = (int64_t)b * ln.L + s;
+    if (ln.mask[i]) {
+      const float tt = ln.t[i], cc = ln.c[i];
+      gt[i] += dm.a * power + dm.b * ratio;
+      const float g_power = dm.a * tt + dm.c;
+      float g_ratio = dm.b * tt + dm.d + g_power * cc;
+      gc[i] += g_power * (ratio - 1.0f);
+      const float n_out = nd_at(ln, b, s);
+      if (ln.mask_g[i]) gnd[i] += -g_ratio * ratio / n_out;
+      if (s > 0 && ln.mask_g[i - 1]) gnd[i - 1] += g_ratio / n_out;
+    }
+    g = Abcd{q.a * g.a + q.c * g.c, q.a * g.b + q.c * g.d, q.b * g.a + q.d * g.c,
+             q.b * g.b + q.d * g.d};                             // M_s^T g
+  }
 }
 
 // --------------------------------------------------------------------------
@@ -1112,10 +1226,52 @@ int tl_spot_finalize(const double *moments, const float *ref_y, int32_t B, int32
     return fail(TL_ERR_INVALID, "bad argument to tl_spot_finalize%s");
   if (want_grad && (!out->gc || !out->gt || !out->gmu || !out->gz))
     return fail(TL_ERR_INVALID, "NULL gradient output%s");
-  if ((size_t)F * 3 * sizeof(double) > 48 * 1024)
+  if ((size_t)F * 3 * sizeof(double) > 40 * 1024)
     return fail(TL_ERR_INVALID, "too many fields%s");
-  k_spot_finalize<<<B, 128, (size_t)F * 3 * sizeof(double), (cudaStream_t)stream_>>>(
-      moments, ref_y, B, F, W, S, (double)P_total * (double)W, want_grad, *out);
+  const int n_acc = n_acc_of(want_grad ? MODE_SPOT_GRAD : MODE_SPOT_EVAL, S);
+  const size_t base = (size_t)F * 3 * sizeof(double);
+  const size_t staged = base + (size_t)F * W * n_acc * sizeof(double);
+  const double n_rays = (double)P_total * (double)W;
+  if (staged <= 160 * 1024) {
+    if (staged > 48 * 1024)
+      TL_CHECK_CUDA(cudaFuncSetAttribute((const void *)k_spot_finalize<true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged));
+    k_spot_finalize<true><<<B, 256, staged, (cudaStream_t)stream_>>>(moments, ref_y, B, F, W, S, n_rays,
+                                                                     want_grad, *out);
+  } else {
+    k_spot_finalize<false><<<B, 256, base, (cudaStream_t)stream_>>>(moments, ref_y, B, F, W, S, n_rays,
+                                                                    want_grad, *out);
+  }
+  g_launches++;
+  TL_CHECK_CUDA(cudaGetLastError());
+  return TL_OK;
+}
+
+static int validate_lens(const TlLens *ln) {
+  if (!ln || !ln->c || !ln->t || !ln->nd || !ln->v || !ln->mask || !ln->mask_g || !ln->stop_idx ||
+      !ln->hfov || !ln->epd || !ln->rel_fields || !ln->wavelengths)
+    return fail(TL_ERR_INVALID, "NULL lens field%s");
+  if (ln->B < 1 || ln->L < 1 || ln->F < 1 || ln->W < 1 || ln->L > kStageMaxSurfaces)
+    return fail(TL_ERR_INVALID, "bad lens sizes (B, L, F, W >= 1, L <= 64)%s");
+  return TL_OK;
+}
+
+int tl_stage_fwd(const TlLens *lens, float *mu, float *z, float *cy, float *half_epd, void *stream_) {
+  int rc = validate_lens(lens);
+  if (rc) return rc;
+  if (!mu || !z || !cy || !half_epd) return fail(TL_ERR_INVALID, "NULL output of tl_stage_fwd%s");
+  k_stage_fwd<<<lens->B, 128, 0, (cudaStream_t)stream_>>>(*lens, mu, z, cy, half_epd);
+  g_launches++;
+  TL_CHECK_CUDA(cudaGetLastError());
+  return TL_OK;
+}
+
+int tl_stage_bwd(const TlLens *lens, const float *gmu, const float *gz, float *gc, float *gt,
+                 float *gnd, float *gv, void *stream_) {
+  int rc = validate_lens(lens);
+  if (rc) return rc;
+  if (!gmu || !gz || !gc || !gt || !gnd || !gv) return fail(TL_ERR_INVALID, "NULL argument of tl_stage_bwd%s");
+  k_stage_bwd<<<lens->B, 64, 0, (cudaStream_t)stream_>>>(*lens, gmu, gz, gc, gt, gnd, gv);
   g_launches++;
   TL_CHECK_CUDA(cudaGetLastError());
   return TL_OK;

@@ -318,3 +318,133 @@ def spot_rms(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arith=na
     """
     return _SpotRms.apply(x, y, z, cx, cy, c, t, mu, mask, bool(allow_backward_rays), int(arith),
                           (int(shard[0]), int(shard[1])), group)
+
+
+# ---------------------------------------------------------------------------
+# Lens-level fused pass: ray-set staging kernels + spot pass + chain rule
+# ---------------------------------------------------------------------------
+class LensTables:
+    """Device-side constants of a (structure, specs, tracer) triple that the staging
+    kernels read: masks, stop indices, fields, wavelengths.  Built once."""
+
+    def __init__(self, structure, rel_fields, wavelengths, device):
+        dev = torch.device(device)
+        self.mask = structure.mask_torch.to(dev).to(torch.uint8).contiguous()
+        self.mask_g = structure.mask_G_torch.to(dev).to(torch.uint8).contiguous()
+        self.stop_idx = torch.as_tensor(structure.stop_idx, dtype=torch.int32).to(dev).contiguous()
+        self.rel_fields = torch.tensor([float(f) for f in rel_fields], dtype=torch.float32, device=dev)
+        self.wavelengths = torch.tensor([float(w) for w in wavelengths], dtype=torch.float32, device=dev)
+        self.zero = torch.zeros((1, 1, 1, 1), dtype=torch.float32, device=dev)
+        self.B, self.L = self.mask.shape
+        self.F, self.W = self.rel_fields.numel(), self.wavelengths.numel()
+
+    def lens_struct(self, c, t, nd, v, hfov, epd):
+        ln = nat.TlLens()
+        ln.c, ln.t, ln.nd, ln.v = c.data_ptr(), t.data_ptr(), nd.data_ptr(), v.data_ptr()
+        ln.mask, ln.mask_g, ln.stop_idx = self.mask.data_ptr(), self.mask_g.data_ptr(), self.stop_idx.data_ptr()
+        ln.hfov, ln.epd = hfov.data_ptr(), epd.data_ptr()
+        ln.rel_fields, ln.wavelengths = self.rel_fields.data_ptr(), self.wavelengths.data_ptr()
+        ln.B, ln.L, ln.F, ln.W = self.B, self.L, self.F, self.W
+        return ln
+
+
+class _LensSpotRms(torch.autograd.Function):
+    """RayTracer.spot_rms as ONE autograd node over the lens tensors: staging kernel ->
+    chief rays -> fused trace+adjoint -> row reduction -> (all-reduce) -> finalize ->
+    staging chain rule.  Seven kernel launches, no per-ray tensor."""
+
+    @staticmethod
+    def forward(ctx, c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, shard,
+                group):
+        for name, val in (('c', c), ('t', t), ('nd', nd), ('v', v), ('hfov', hfov), ('epd', epd),
+                          ('x', x_rel), ('y', y_rel)):
+            nat.require_cuda(val, name)
+            if val.dtype != torch.float32:
+                raise TypeError(f'{name} must be float32')
+        if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
+            raise ValueError('the fused lens pass does not differentiate w.r.t. hfov / epd')
+        lib = nat.load()
+        dev = c.device
+        B, L, F, W = tables.B, tables.L, tables.F, tables.W
+        if tuple(c.shape) != (B, L):
+            raise ValueError(f'lens tensors must be [B={B}, L={L}], got {tuple(c.shape)}')
+        want_grad = any(ctx.needs_input_grad[:4])
+        if L > (nat.MAX_SURFACES_SPOT if want_grad else 64):
+            raise ValueError('too many surfaces for the fused lens pass')
+        P = x_rel.shape[2]
+        rank, world = shard
+        p_begin, p_end = pupil_slice(P, rank, world)
+        with torch.cuda.device(dev):
+            cc, tt, ndd, vv = (a.detach().contiguous() for a in (c, t, nd, v))
+            hf, ep = hfov.detach().contiguous(), epd.detach().contiguous()
+            mu = torch.empty((B, W, L), dtype=torch.float32, device=dev)
+            z = torch.empty((B,), dtype=torch.float32, device=dev)
+            cy = torch.empty((B, F), dtype=torch.float32, device=dev)
+            half_epd = torch.empty((B,), dtype=torch.float32, device=dev)
+            ln = tables.lens_struct(cc, tt, ndd, vv, hf, ep)
+            stream = nat.stream_ptr(dev)
+            nat.check(lib.tl_stage_fwd(ctypes.byref(ln), mu.data_ptr(), z.data_ptr(), cy.data_ptr(),
+                                       half_epd.data_ptr(), stream), 'tl_stage_fwd')
+            shape = (B, F, P, W)
+            pb = nat.TlProblem()
+            pb.x = nat.strided(x_rel.detach(), shape)
+            pb.y = nat.strided(y_rel.detach(), shape)
+            pb.z = nat.strided(z.reshape(B, 1, 1, 1), shape)
+            pb.cx = nat.strided(tables.zero, shape)
+            pb.cy = nat.strided(cy.reshape(B, F, 1, 1), shape)
+            pb.c, pb.t, pb.mu, pb.live = cc.data_ptr(), tt.data_ptr(), mu.data_ptr(), tables.mask.data_ptr()
+            pb.B, pb.F, pb.P, pb.W, pb.S = B, F, P, W, L
+            pb.allow_backward_rays, pb.arith = int(bool(allow_backward_rays)), int(arith)
+            pb.p_begin, pb.p_end = p_begin, p_end
+            pb.xy_scale = half_epd.data_ptr()
+            n_acc = lib.tl_spot_moment_count(L, int(want_grad))
+            moments = torch.empty((B, F, W, n_acc), dtype=torch.float64, device=dev)
+            ref_y = torch.empty((B, F), dtype=torch.float32, device=dev)
+            ws_bytes = lib.tl_spot_workspace(ctypes.byref(pb), int(want_grad))
+            if ws_bytes == 0:
+                nat.check(-1, 'tl_spot_workspace')
+            ws = torch.empty((ws_bytes // 8,), dtype=torch.float64, device=dev)
+            nat.check(lib.tl_spot_accumulate(ctypes.byref(pb), int(want_grad), moments.data_ptr(),
+                                             ref_y.data_ptr(), ws.data_ptr(), ws_bytes, stream),
+                      'tl_spot_accumulate')
+            if world > 1:
+                reduce_moments(moments, group)
+            rms = torch.empty((B,), dtype=torch.float32, device=dev)
+            rms_field = torch.empty((B, F), dtype=torch.float32, device=dev)
+            if want_grad:
+                gc = torch.empty((B, L), dtype=torch.float32, device=dev)
+                gt = torch.empty_like(gc)
+                gmu = torch.empty((B, W, L), dtype=torch.float32, device=dev)
+                gz = torch.empty((B,), dtype=torch.float32, device=dev)
+                out = nat.TlSpotOut(rms.data_ptr(), rms_field.data_ptr(), gc.data_ptr(), gt.data_ptr(),
+                                    gmu.data_ptr(), gz.data_ptr())
+            else:
+                out = nat.TlSpotOut(rms.data_ptr(), rms_field.data_ptr(), None, None, None, None)
+            nat.check(lib.tl_spot_finalize(moments.data_ptr(), ref_y.data_ptr(), B, F, W, L, P,
+                                           int(want_grad), ctypes.byref(out), stream), 'tl_spot_finalize')
+            if want_grad:
+                gnd = torch.zeros((B, L), dtype=torch.float32, device=dev)
+                gv = torch.zeros((B, L), dtype=torch.float32, device=dev)
+                nat.check(lib.tl_stage_bwd(ctypes.byref(ln), gmu.data_ptr(), gz.data_ptr(), gc.data_ptr(),
+                                           gt.data_ptr(), gnd.data_ptr(), gv.data_ptr(), stream),
+                          'tl_stage_bwd')
+                ctx.save_for_backward(gc, gt, gnd, gv)
+        ctx.mark_non_differentiable(rms_field)
+        return rms, rms_field
+
+    @staticmethod
+    def backward(ctx, grad_rms, _grad_field):
+        gc, gt, gnd, gv = ctx.saved_tensors
+        g = grad_rms.to(torch.float32).reshape(-1, 1)
+        need = ctx.needs_input_grad
+        grads = [(gc * g) if need[0] else None, (gt * g) if need[1] else None,
+                 (gnd * g) if need[2] else None, (gv * g) if need[3] else None]
+        return (*grads, None, None, None, None, None, None, None, None, None)
+
+
+def lens_spot_rms(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays=True,
+                  arith=nat.ARITH_GUARDED, shard=(0, 1), group=None):
+    """(rms [B], rms_field [B,F]) of a lens batch given as padded [B,L] tensors, differentiable
+    w.r.t. c, t, nd, v.  x_rel, y_rel: relative pupil coordinates [1,1,P,1]."""
+    return _LensSpotRms.apply(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, bool(allow_backward_rays),
+                              int(arith), (int(shard[0]), int(shard[1])), group)

@@ -341,11 +341,26 @@ class RayTracer:
         args = self._ray_set(specs, lens, use_vig, xy, up_to_stop)
         return trace_skew(*args, aggregate, self.allow_backward_rays, arith=self.arith)
 
-    def spot_rms(self, specs, lens, use_vig=True, shard=(0, 1), group=None):
+    def spot_rms(self, specs, lens, use_vig=True, shard=(0, 1), group=None, staged=True):
         """RMS spot size of every lens -- ``compute_rms2d(*trace_rays(...))`` fused
         into one pass that also produces the gradients w.r.t. the lens
         (no [B,F,P,W] tensor is ever materialised).  Returns (rms [B], rms_field [B,F]).
-        With ``shard=(rank, world)`` the pupil axis is split over ranks."""
+        With ``shard=(rank, world)`` the pupil axis is split over ranks.
+
+        ``staged`` (default): the ray set (index model, pupil position, field cosines) and its
+        chain rule also run as two small CUDA kernels; it applies when there is no pupil
+        vignetting function, no ray aiming and a deterministic pupil sampler, otherwise the
+        torch front end of :meth:`trace_rays` feeds the fused pass."""
+        plain = (self.vig_fn is None or not use_vig) and self.n_ray_aiming_iter == 0
+        if staged and plain and self.mode != 'skew_random' and lens.c.shape[1] <= 64:
+            key = ('tables', id(lens.structure))
+            if key not in self._cache:
+                self._cache[key] = ops.LensTables(lens.structure, self.rel_fields, self.wavelengths,
+                                                  self.default_device)
+            x_rel, y_rel = self._pupil(None)
+            return ops.lens_spot_rms(lens.c, lens.t, lens.nd, lens.v, specs.hfov, specs.epd, x_rel,
+                                     y_rel, self._cache[key], self.allow_backward_rays,
+                                     _arith_code(self.arith), shard, group)
         args = self._ray_set(specs, lens, use_vig)
         return ops.spot_rms(*args, self.allow_backward_rays, _arith_code(self.arith), shard, group)
 
