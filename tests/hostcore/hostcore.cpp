@@ -55,22 +55,15 @@ static void fast_and_adjoint(int64_t n, const T *x, const T *y, const T *z, cons
     ox[i] = r.x; oy[i] = r.y; ocx[i] = r.cx; ocy[i] = r.cy;
     min_cos2[i] = mq; min_travel[i] = mtr;
     if (!sx) continue;
-    T next_rcz;
-    Ray<T> a = adjoint_image(pre, sx[i], sy[i], scx[i], scy[i], next_rcz);
-    // like the kernels: only (x, y, cx, cy) of each in-state is kept, z and cz are rebuilt
-    Ray<T> next = pre;
+    // like the kernels: geometric sweep over the parked (hit x, hit y, in-dir x, in-dir y)
+    Sweep<T> sw = sweep_begin(pre, r.x, r.y, sx[i], sy[i], scx[i], scy[i]);
     for (int k = S - 1; k >= 0; --k) {
-      Ray<T> in;
-      in.x = st[k].x; in.y = st[k].y; in.cx = st[k].cx; in.cy = st[k].cy;
-      T in_rcz;
-      in.cz = rebuild_cz(in.cx, in.cy, in_rcz);
-      in.z = (k == 0) ? z[i] : rebuild_z(in.x, in.y, c[k - 1], t[k - 1]);
-      SurfaceGrad<T> g = adjoint_surface(in, next, next_rcz, c[k], mu[k], mu[k] * mu[k], a);
+      SurfaceGrad<T> g = sweep_sphere(sw, st[k + 1].x, st[k + 1].y, st[k].cx, st[k].cy, c[k], t[k], mu[k],
+                                      mu[k] * mu[k]);
       gc[k] += (double)g.c; gt[k] += (double)g.t; gmu[k] += (double)g.mu;
-      next = in;
-      next_rcz = in_rcz;
     }
-    adjoint_cz0(next, next_rcz, a);
+    Ray<T> a;
+    sweep_end(sw, z[i], a.x, a.y, a.z, a.cx, a.cy);
     gx[i] = a.x; gy[i] = a.y; gz[i] = a.z; gcx[i] = a.cx; gcy[i] = a.cy;
   }
 }

@@ -310,144 +310,113 @@ TL_HD T fast_image(Ray<T> &r) {
   return -r.z;
 }
 
-// ---------------------------------------------------------------------------
-// Only (x, y, cx, cy) of the state in front of each surface is parked for the
-// adjoint sweep; the two dependent components are rebuilt from them:
-//   cz = sqrt(1 - cx^2 - cy^2)                       (how the forward made it, rtl:568)
-//   z  = sag of the previous surface at (x, y) minus its thickness: the point in
-//        front of surface k is the hit point on surface k-1 (x, y unchanged by the
-//        z shift of rtl:639), and a hit point lies on its sphere.
-// ---------------------------------------------------------------------------
-template <class T>
-TL_HD T rebuild_cz(T cx, T cy, T &rcz) {
-  const T w = ffma(-cy, cy, ffma(-cx, cx, T(1)));
-  rcz = frsqrt(w);            // 1 / cz, reused by the adjoint of the surface in front
-  return w * rcz;
-}
-
-template <class T>
-TL_HD T rebuild_z(T x, T y, T c_prev, T t_prev) {
-  const T rho = ffma(y, y, x * x);
-  const T w = ffma(-(c_prev * c_prev), rho, T(1));
-  const T root = w * frsqrt(w);
-  return ffma(c_prev * rho, frcp(T(1) + root), -t_prev);
-}
-
-// ---------------------------------------------------------------------------
-// Adjoint.  `a` holds the adjoint of a ray state (d loss / d state).
-// ---------------------------------------------------------------------------
 template <class T>
 struct SurfaceGrad {
   T c, t, mu;
 };
 
-// Adjoint of the image-plane transfer.  `r` is the state in front of the image
-// plane (after the last surface's z shift); seeds are d loss / d(x, y, cx, cy) of
-// the outputs.
+// ---------------------------------------------------------------------------
+// Geometric adjoint (the one the kernels run).
+//
+// The reference differentiates its scalar formulas; on the manifold of unit
+// directions those formulas ARE "intersect the sphere, refract with the unit
+// normal" -- so the total derivatives w.r.t. every input equal those of the
+// geometric map, which is much cheaper to reverse (no quadratic-solve
+// intermediates): with hit point h on F(h) = c|h|^2/2 - h_z = 0, unit normal
+// n = z^ - c h, a = n.d, a' = n.d', d' = mu d + g n, g = a' - mu a:
+//   transfer  h = r + D d, F(h) = 0   ->  s = -(gh.d)/a, gr = gh + s n, gd += D gr,
+//                                          gc -= s |h|^2 / 2        (implicit function theorem)
+//   refract                            ->  gg = gd'.n, u = gg/a', ga = -mu g u,
+//                                          gmu = gd'.d - u (mu (1 - a^2) + a a'),
+//                                          gn = g gd' + ga d, gd = mu gd' + ga n
+//   normal    n = z^ - c h             ->  gh -= c gn, gc -= gn.h
+//   shift     r' = h - t z^            ->  gt = -gr'_z
+// Parked per surface: the hit point (hx, hy) and the incoming direction (dx, dy);
+// h_z = c rho / (1 + sqrt(1 - c^2 rho)) (the hit lies on the sphere; 1 - c h_z = sqrt(...) is
+// also n_z) and d_z = sqrt(1 - dx^2 - dy^2) are rebuilt.  Verified against autograd of the
+// oracle in fp64 (tests/test_core_cpu.py, ~1e-12).
+// ---------------------------------------------------------------------------
 template <class T>
-TL_HD Ray<T> adjoint_image(const Ray<T> &r, T gx, T gy, T gcx, T gcy, T &rcz) {
-  rcz = frcp(r.cz);
-  const T dist = -r.z * rcz;
-  const T gdist = ffma(gy, r.cy, gx * r.cx);
-  Ray<T> a;
-  a.x = gx;
-  a.y = gy;
-  a.cx = ffma(dist, gx, gcx);
-  a.cy = ffma(dist, gy, gcy);
-  a.z = -gdist * rcz;
-  a.cz = a.z * dist;          // d dist / d cz = -dist / cz
-  return a;
+struct Vec3 {
+  T x, y, z;
+};
+
+template <class T>
+TL_HD T dot3(const Vec3<T> &p, const Vec3<T> &q) {
+  return ffma(p.z, q.z, ffma(p.y, q.y, p.x * q.x));
 }
 
-// Adjoint of one surface.  `in` is the ray state in front of the surface, `out`
-// the state behind it (x, y, direction; = the next surface's `in`) with
-// `out_rcz` = 1 / out.cz, `a` the adjoint of `out` on entry and of `in` on return.
+// State carried from surface k+1 to surface k of the sweep.
 template <class T>
-TL_HD SurfaceGrad<T> adjoint_surface(const Ray<T> &in, const Ray<T> &out, T out_rcz, T c, T mu,
-                                     T mu2, Ray<T> &a) {
+struct Sweep {
+  Vec3<T> hit;   // hit point on surface k+1 (its vertex coordinates; image plane: z = 0)
+  Vec3<T> dir;   // direction of the ray between surfaces k and k+1
+  Vec3<T> gr;    // adjoint of a point of that ray
+  Vec3<T> gd;    // adjoint of its direction, still missing the (distance to `hit`) * gr term
+};
+
+// Image plane: seeds on the image point (gx, gy) and on the final direction (gcx, gcy).
+// `pre` = state in front of the image plane, (x_img, y_img) = the traced image point.
+template <class T>
+TL_HD Sweep<T> sweep_begin(const Ray<T> &pre, T x_img, T y_img, T gx, T gy, T gcx, T gcy) {
+  Sweep<T> s;
+  s.hit = Vec3<T>{x_img, y_img, T(0)};
+  s.dir = Vec3<T>{pre.cx, pre.cy, pre.cz};
+  s.gr = Vec3<T>{gx, gy, -ffma(gy, pre.cy, gx * pre.cx) * frcp(pre.cz)};   // plane: n = z^
+  s.gd = Vec3<T>{gcx, gcy, T(0)};
+  return s;
+}
+
+template <class T>
+TL_HD SurfaceGrad<T> sweep_sphere(Sweep<T> &s, T hx, T hy, T dx, T dy, T c, T t, T mu, T mu2) {
   SurfaceGrad<T> g;
-  g.t = -a.z;                                           // z_out = z_hit - t
-  // -- recompute the forward intermediates from `in`
-  const T ne = ffma(in.z, in.cz, ffma(in.y, in.cy, in.x * in.cx));
-  const T mz = ffma(-ne, in.cz, in.z);
-  const T m2 = ffma(-ne, ne, ffma(in.z, in.z, ffma(in.y, in.y, in.x * in.x)));
-  const T tmp = ffma(c, m2, T(-2) * mz);
-  const T q = ffma(-c, tmp, in.cz * in.cz);
-  const T rsq_q = frsqrt(q);
-  const T ci = q * rsq_q;
-  const T ru = frcp(in.cz + ci);
-  const T tu = tmp * ru;
-  const T dist = tu - ne;
-  const T omq = T(1) - q;
-  const T qo = ffma(-mu2, omq, T(1));
-  const T rsq_qo = frsqrt(qo);
-  const T gsn = ffma(-mu, ci, qo * rsq_qo);             // g = cos_out - mu cos_in
-  const T gcv = gsn * c;
-  // -- cz_out = sqrt(1 - cx_out^2 - cy_out^2)
-  const T rr = a.cz * out_rcz;
-  const T acx = ffma(-out.cx, rr, a.cx);
-  const T acy = ffma(-out.cy, rr, a.cy);
-  // -- cx_out = mu cx - (g c) x_hit
-  T gmu = ffma(acy, in.cy, acx * in.cx);
-  const T gG = -ffma(acy, out.y, acx * out.x);
-  const T ax1 = ffma(-gcv, acx, a.x);
-  const T ay1 = ffma(-gcv, acy, a.y);
-  const T az1 = a.z;
-  T ncx = mu * acx;
-  T ncy = mu * acy;
-  const T gg = gG * c;
-  T gc = gG * gsn;
-  // -- g = cos_out - mu cos_in ; cos_out = sqrt(qo) ; qo = 1 - mu^2 (1 - q)
-  gmu = ffma(-gg, ci, gmu);
-  T gci = -gg * mu;
-  const T gqo = gg * (T(0.5) * rsq_qo);
-  T gq = mu2 * gqo;
-  gmu = ffma(T(-2) * mu * omq, gqo, gmu);
-  // -- advance: hit = in + dist * dir
-  const T gdist = ffma(az1, in.cz, ffma(ay1, in.cy, ax1 * in.cx));
-  ncx = ffma(dist, ax1, ncx);
-  ncy = ffma(dist, ay1, ncy);
-  T ncz = dist * az1;
-  // -- dist = e + tmp / (cz + cos_in)
-  T ge = gdist;
-  T gtmp = gdist * ru;
-  const T gu = -gtmp * tu;
-  ncz = ncz + gu;
-  gci = gci + gu;
-  // -- cos_in = sqrt(q) ; q = cz^2 - c tmp
-  gq = ffma(gci, T(0.5) * rsq_q, gq);
-  ncz = ffma(T(2) * in.cz, gq, ncz);
-  gc = ffma(-tmp, gq, gc);
-  gtmp = ffma(-c, gq, gtmp);
-  // -- tmp = c m2 - 2 mz
-  gc = ffma(m2, gtmp, gc);
-  const T gm2 = c * gtmp;
-  const T gmz = T(-2) * gtmp;
-  // -- m2 = |r|^2 - e^2 ; mz = z + e cz ; e = -(r . d)     (ne = -e)
-  const T gm2x2 = gm2 + gm2;
-  T nx = ffma(gm2x2, in.x, ax1);
-  T ny = ffma(gm2x2, in.y, ay1);
-  T nz = ffma(gm2x2, in.z, az1 + gmz);
-  ge = ffma(gm2x2, ne, ge);                    // -2 e gm2 = +2 ne gm2
-  ge = ffma(in.cz, gmz, ge);
-  ncz = ffma(-ne, gmz, ncz);                   // e gmz
-  a.x = ffma(-in.cx, ge, nx);
-  a.y = ffma(-in.cy, ge, ny);
-  a.z = ffma(-in.cz, ge, nz);
-  a.cx = ffma(-in.x, ge, ncx);
-  a.cy = ffma(-in.y, ge, ncy);
-  a.cz = ffma(-in.z, ge, ncz);
-  g.c = gc;
-  g.mu = gmu;
+  // rebuild the dependent components
+  const T rho = ffma(hy, hy, hx * hx);
+  const T w = ffma(-(c * c), rho, T(1));
+  const T root = w * frsqrt(w);                       // = 1 - c h_z = n_z
+  const T hz = (c * rho) * frcp(T(1) + root);
+  const T wd = ffma(-dy, dy, ffma(-dx, dx, T(1)));
+  const T dz = wd * frsqrt(wd);
+  // finish the transfer behind this surface: distance from this hit to the next one
+  const T dist = ffma((s.hit.z - hz) + t, s.dir.z, ffma(s.hit.y - hy, s.dir.y, (s.hit.x - hx) * s.dir.x));
+  const Vec3<T> gdo{ffma(dist, s.gr.x, s.gd.x), ffma(dist, s.gr.y, s.gd.y), ffma(dist, s.gr.z, s.gd.z)};
+  g.t = -s.gr.z;
+  // refraction d' = mu d + g n
+  const Vec3<T> n{-c * hx, -c * hy, root};
+  const Vec3<T> d{dx, dy, dz};
+  const T a = dot3(n, d);
+  const T ap = dot3(n, s.dir);
+  const T gsn = ffma(-mu, a, ap);
+  const T gdd = dot3(gdo, d);
+  const T u = dot3(gdo, n) * frcp(ap);
+  const T ga = -(mu * gsn) * u;
+  g.mu = ffma(-u, ffma(a, ap, mu * ffma(-a, a, T(1))), gdd);
+  const Vec3<T> gn{ffma(ga, d.x, gsn * gdo.x), ffma(ga, d.y, gsn * gdo.y), ffma(ga, d.z, gsn * gdo.z)};
+  const Vec3<T> gdi{ffma(ga, n.x, mu * gdo.x), ffma(ga, n.y, mu * gdo.y), ffma(ga, n.z, mu * gdo.z)};
+  // normal n = z^ - c h
+  const Vec3<T> gh{ffma(-c, gn.x, s.gr.x), ffma(-c, gn.y, s.gr.y), ffma(-c, gn.z, s.gr.z)};
+  const T gc_n = ffma(gn.z, hz, ffma(gn.y, hy, gn.x * hx));
+  // transfer onto the sphere
+  const T sd = -dot3(gh, d) * frcp(a);
+  s.gr = Vec3<T>{ffma(sd, n.x, gh.x), ffma(sd, n.y, gh.y), ffma(sd, n.z, gh.z)};
+  g.c = -ffma(sd * T(0.5), ffma(hz, hz, rho), gc_n);
+  s.gd = gdi;
+  s.hit = Vec3<T>{hx, hy, hz};
+  s.dir = d;
   return g;
 }
 
-// Fold the adjoint of cz0 = sqrt(1 - cx^2 - cy^2) (rtl:609) into (cx, cy).
+// Entrance: the ray starts at (x, y, z_in) with direction (cx, cy, sqrt(1 - cx^2 - cy^2)).
 template <class T>
-TL_HD void adjoint_cz0(const Ray<T> &in0, T in0_rcz, Ray<T> &a) {
-  const T rr = a.cz * in0_rcz;
-  a.cx = ffma(-in0.cx, rr, a.cx);
-  a.cy = ffma(-in0.cy, rr, a.cy);
+TL_HD void sweep_end(const Sweep<T> &s, T z_in, T &gx, T &gy, T &gz, T &gcx, T &gcy) {
+  const T rdz = frcp(s.dir.z);
+  const T dist = (s.hit.z - z_in) * rdz;
+  const T gdz = ffma(dist, s.gr.z, s.gd.z) * rdz;
+  gx = s.gr.x;
+  gy = s.gr.y;
+  gz = s.gr.z;
+  gcx = ffma(-gdz, s.dir.x, ffma(dist, s.gr.x, s.gd.x));     // cz is a function of (cx, cy)
+  gcy = ffma(-gdz, s.dir.y, ffma(dist, s.gr.y, s.gd.y));
 }
 
 }  // namespace tl

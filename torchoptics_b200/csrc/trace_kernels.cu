@@ -112,18 +112,18 @@ struct Traced {
   bool ok, backward;
 };
 
-// Parked in-states for the adjoint sweep: (x, y, cx, cy) in front of every surface
-// (z and cz are rebuilt, see trace_core.cuh).  One V-wide slot per (surface,
+// Parked per surface for the adjoint sweep: the hit point (x, y) and the incoming
+// direction (cx, cy) (h_z and d_z are rebuilt, see trace_core.cuh).  One V-wide slot per (surface,
 // component, thread): slot (k, j) of thread t is state[(k * 4 + j) * stride + t], so a
 // warp's access is one contiguous, conflict-free 64/128-bit transaction per lane group.
 template <bool SAVE, class V>
-__device__ __forceinline__ void park(V *state, int stride, int k, const Ray<V> &r) {
+__device__ __forceinline__ void park(V *state, int stride, int k, V hit_x, V hit_y, V dir_x, V dir_y) {
   if (SAVE) {
     V *s = state + (size_t)k * 4 * stride;
-    s[0] = r.x;
-    s[stride] = r.y;
-    s[2 * stride] = r.cx;
-    s[3 * stride] = r.cy;
+    s[0] = hit_x;
+    s[stride] = hit_y;
+    s[2 * stride] = dir_x;
+    s[3 * stride] = dir_y;
   }
 }
 
@@ -136,9 +136,10 @@ __device__ __noinline__ Traced trace_exact(float x, float y, float z, float cx, 
   Ray<float> r{x, y, z, cx, cy, exact_cz0(cx, cy)};
   bool ok = true, backward = false;
   for (int k = 0; k < S; ++k) {
-    park<SAVE, float>(state, stride, k, r);
+    const float in_cx = r.cx, in_cy = r.cy;
     const Surface s{tab.c[k], tab.t[k], tab.mu[k]};
     exact_surface(r, s, k > 0 && tab.live[k - 1], allow_backward, ok, backward);
+    park<SAVE, float>(state, stride, k, r.x, r.y, in_cx, in_cy);
   }
   Traced out;
   out.pre = r;
@@ -174,9 +175,10 @@ __device__ __forceinline__ TracedN<V> trace_guarded(V x, V y, V z, V cx, V cy, c
     Ray<V> r{x, y, z, cx, cy, fast_cz0(cx, cy)};
     V min_cos2(1.0f), min_travel(3.0e38f);
     for (int k = 0; k < S; ++k) {
-      park<SAVE, V>(state, stride, k, r);
+      const V in_cx = r.cx, in_cy = r.cy;
       V travel;
       fast_surface(r, V(tab.c[k]), V(tab.mu[k]), V(tab.mu2[k]), V(tab.t[k]), min_cos2, travel);
+      park<SAVE, V>(state, stride, k, r.x, r.y, in_cx, in_cy);
       if (k > 0 && tab.live[k - 1]) min_travel = fmin2(min_travel, travel);
     }
     out.pre = r;
@@ -221,7 +223,7 @@ __device__ __forceinline__ TracedN<V> trace_guarded(V x, V y, V z, V cx, V cy, c
 // exact zeros.
 template <class V>
 __device__ __noinline__ void mirror_live_lane(V *state, int stride, int S, const bool *ok,
-                                              Ray<V> &pre, V &z_in) {
+                                              Ray<V> &pre, V &z_in, V &x_img, V &y_img) {
   constexpr int N = LaneCount<V>::value;
   int src = 0;
   for (int l = 0; l < N; ++l)
@@ -233,8 +235,8 @@ __device__ __noinline__ void mirror_live_lane(V *state, int stride, int S, const
     for (int l = 0; l < N; ++l)
       if (!ok[l]) slot[l] = v;
   }
-  V *comp[7] = {&pre.x, &pre.y, &pre.z, &pre.cx, &pre.cy, &pre.cz, &z_in};
-  for (int j = 0; j < 7; ++j) {
+  V *comp[9] = {&pre.x, &pre.y, &pre.z, &pre.cx, &pre.cy, &pre.cz, &z_in, &x_img, &y_img};
+  for (int j = 0; j < 9; ++j) {
     const float v = lane_get(*comp[j], src);
     for (int l = 0; l < N; ++l)
       if (!ok[l]) lane_set(*comp[j], l, v);
@@ -481,7 +483,7 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
     if (kAdjoint) {
       Ray<V> a{V(0.f), V(0.f), V(0.f), V(0.f), V(0.f), V(0.f)};
       if (any_live) {
-        if (!all_ok) mirror_live_lane<V>(state, stride, S, tr.ok, tr.pre, z);
+        if (!all_ok) mirror_live_lane<V>(state, stride, S, tr.ok, tr.pre, z, tr.x, tr.y);
         V sx(0.f), sy(0.f), scx(0.f), scy(0.f);
         if (MODE == MODE_SPOT_GRAD) {
           sy = alive;
@@ -495,45 +497,24 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
             if (args.seeds.gcy) lane_set(scy, l, args.seeds.gcy[o[l]]);
           }
         }
-        V next_rcz;
-        a = adjoint_image(tr.pre, sx, sy, scx, scy, next_rcz);
-        Ray<V> next = tr.pre;
+        Sweep<V> sw = sweep_begin(tr.pre, tr.x, tr.y, sx, sy, scx, scy);
 #pragma unroll
         for (int k = NS_MAX - 1; k >= 0; --k) {
           if (k >= S) continue;
-          {
-            const V *slot = state + (size_t)k * 4 * stride;
-            Ray<V> in;
-            in.x = slot[0];
-            in.y = slot[stride];
-            in.cx = slot[2 * stride];
-            in.cy = slot[3 * stride];
-            V in_rcz;
-            in.cz = rebuild_cz(in.cx, in.cy, in_rcz);
-            in.z = (k == 0) ? z : rebuild_z(in.x, in.y, V(tab.c[k > 0 ? k - 1 : 0]),
-                                            V(tab.t[k > 0 ? k - 1 : 0]));
-            const SurfaceGrad<V> g =
-                adjoint_surface(in, next, next_rcz, V(tab.c[k]), V(tab.mu[k]), V(tab.mu2[k]), a);
-            const float s_c = lane_sum(g.c), s_t = lane_sum(g.t), s_mu = lane_sum(g.mu);
-            float w_c = 0.f, w_t = 0.f, w_mu = 0.f;
-            if (MODE == MODE_SPOT_GRAD) {
-              w_c = lane_dot(wgt, g.c, 0.f);
-              w_t = lane_dot(wgt, g.t, 0.f);
-              w_mu = lane_dot(wgt, g.mu, 0.f);
-            }
-            acc_c[k] += s_c;
-            acc_t[k] += s_t;
-            acc_mu[k] += s_mu;
-            if (MODE == MODE_SPOT_GRAD) {
-              wac_c[k] += w_c;
-              wac_t[k] += w_t;
-              wac_mu[k] += w_mu;
-            }
-            next = in;
-            next_rcz = in_rcz;
+          const V *slot = state + (size_t)k * 4 * stride;
+          const SurfaceGrad<V> g = sweep_sphere(sw, slot[0], slot[stride], slot[2 * stride],
+                                                slot[3 * stride], V(tab.c[k]), V(tab.t[k]),
+                                                V(tab.mu[k]), V(tab.mu2[k]));
+          acc_c[k] += lane_sum(g.c);
+          acc_t[k] += lane_sum(g.t);
+          acc_mu[k] += lane_sum(g.mu);
+          if (MODE == MODE_SPOT_GRAD) {
+            wac_c[k] = lane_dot(wgt, g.c, wac_c[k]);
+            wac_t[k] = lane_dot(wgt, g.t, wac_t[k]);
+            wac_mu[k] = lane_dot(wgt, g.mu, wac_mu[k]);
           }
         }
-        adjoint_cz0(next, next_rcz, a);
+        sweep_end(sw, z, a.x, a.y, a.z, a.cx, a.cy);
         acc_z += lane_sum(a.z);
         if (MODE == MODE_SPOT_GRAD) wac_z = lane_dot(wgt, a.z, wac_z);
       }
