@@ -49,3 +49,42 @@ def fast(dtype, x, y, z, cx, cy, c, t, mu, live, seeds=None):
     return dict(x=outs[0], y=outs[1], cx=outs[2], cy=outs[3], min_cos2=outs[4], min_travel=outs[5],
                 gx=grads[0], gy=grads[1], gz=grads[2], gcx=grads[3], gcy=grads[4],
                 gc=pg[0], gt=pg[1], gmu=pg[2])
+
+
+def _asph_tables(dtype, c, k, a, t, mu, sd):
+    f = lambda v: np.ascontiguousarray(v, dtype=dtype)
+    sd2 = np.square(np.asarray(sd, dtype=np.float64)).astype(dtype)
+    return f(c), f(k), f(a).reshape(-1), f(t), f(mu), np.ascontiguousarray(sd2)
+
+
+def asph_exact(x, y, z, cx, cy, c, k, a, t, mu, sd, live, allow_backward=True):
+    n = x.size
+    f = lambda v: np.ascontiguousarray(v, dtype=np.float32)
+    x, y, z, cx, cy = map(f, (x, y, z, cx, cy))
+    c, k, a, t, mu, sd2 = _asph_tables(np.float32, c, k, a, t, mu, sd)
+    live = np.ascontiguousarray(live, dtype=np.uint8)
+    out = [np.empty(n, np.float32) for _ in range(4)] + [np.empty(n, np.uint8) for _ in range(2)] + \
+          [np.empty(n, np.float32)]
+    lib().hc_asph_exact(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(cx), _p(cy), ctypes.c_int(c.size),
+                        _p(c), _p(k), _p(a), _p(t), _p(mu), _p(sd2), _p(live),
+                        ctypes.c_int(int(allow_backward)), *[_p(o) for o in out])
+    return out
+
+
+def asph_fast(dtype, x, y, z, cx, cy, c, k, a, t, mu, sd, seeds=None):
+    n = x.size
+    f = lambda v: np.ascontiguousarray(v, dtype=dtype)
+    x, y, z, cx, cy = map(f, (x, y, z, cx, cy))
+    c, k, a, t, mu, sd2 = _asph_tables(dtype, c, k, a, t, mu, sd)
+    S = c.size
+    outs = [np.zeros(n, dtype) for _ in range(7)]
+    grads = [np.zeros(n, dtype) for _ in range(5)]
+    gp, gt, gmu = np.zeros(S * 9, np.float64), np.zeros(S, np.float64), np.zeros(S, np.float64)
+    sd_ = [None] * 4 if seeds is None else [f(s) for s in seeds]
+    fn = lib().hc_asph_fast_f32 if dtype == np.float32 else lib().hc_asph_fast_f64
+    fn(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(cx), _p(cy), ctypes.c_int(S), _p(c), _p(k), _p(a),
+       _p(t), _p(mu), _p(sd2), *[_p(s) for s in sd_], *[_p(o) for o in outs], *[_p(g) for g in grads],
+       _p(gp), _p(gt), _p(gmu))
+    return dict(x=outs[0], y=outs[1], cx=outs[2], cy=outs[3], opl=outs[4], min_cos2=outs[5],
+                min_clip=outs[6], gx=grads[0], gy=grads[1], gz=grads[2], gcx=grads[3], gcy=grads[4],
+                gp=gp.reshape(S, 9), gt=gt, gmu=gmu)

@@ -8,9 +8,10 @@ SO = os.path.join(HERE, '_hostcore.so')
 
 def build(force=False):
     src = os.path.join(HERE, 'hostcore.cpp')
-    core = os.path.join(HERE, '..', '..', 'torchoptics_b200', 'csrc', 'trace_core.cuh')
+    csrc = os.path.join(HERE, '..', '..', 'torchoptics_b200', 'csrc')
+    deps = [src, os.path.join(csrc, 'trace_core.cuh'), os.path.join(csrc, 'trace_core_asph.cuh')]
     if (not force and os.path.exists(SO)
-            and os.path.getmtime(SO) >= max(os.path.getmtime(src), os.path.getmtime(core))):
+            and os.path.getmtime(SO) >= max(os.path.getmtime(d) for d in deps)):
         return SO
     subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-fno-fast-math', '-std=c++17',
                            '-shared', '-fPIC', '-x', 'c++', src, '-o', SO])
