@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TL_ABI_VERSION 2
+#define TL_ABI_VERSION 3
 
 enum {
   TL_OK = 0,
@@ -55,6 +55,7 @@ enum { TL_ARITH_GUARDED = 0, TL_ARITH_EXACT = 1 };
 #define TL_MAX_SURFACES_FWD   256  /* tl_trace_fwd                          */
 #define TL_MAX_SURFACES_BWD    32  /* tl_trace_bwd                          */
 #define TL_MAX_SURFACES_SPOT   16  /* tl_spot_accumulate with want_grad     */
+#define TL_MAX_SURFACES_GEN    48  /* any entry point, general surfaces     */
 
 /* A ray-bundle input broadcastable to [B,F,P,W]: base pointer + element strides
  * (0 = broadcast along that axis), exactly what torch.broadcast_to() yields. */
@@ -77,12 +78,20 @@ typedef struct TlProblem {
                                   (tl_spot_accumulate only; shards rays over GPUs) */
   const float *xy_scale;       /* [B] or NULL: x and y are multiplied by xy_scale[b] on load
                                   (relative pupil coordinates * EPD/2, scale_to_epd rtl:497-507) */
+  /* EXTENSION surfaces (no reference behaviour; defined by oracle/asphere_oracle.py).  All three
+   * NULL = the reference's spherical lens.  Any non-NULL selects the general-surface kernels:
+   *   z = c rho / (1 + sqrt(1 - (1+k) c^2 rho)) + sum_i a_i rho^i,  rho = x^2 + y^2, i = 2..8 */
+  const float *k;              /* [B,S]   conic constants (NULL = 0)                */
+  const float *a;              /* [B,S,7] a4, a6, ..., a16 (NULL = 0)               */
+  const float *sd;             /* [B,S]   clear semi-diameters (NULL = +inf)        */
 } TlProblem;
 
 /* Outputs of trace_skew, each a contiguous [B,F,P,W] array. */
 typedef struct TlTraceOut {
   float *x, *y, *cx, *cy;
   uint8_t *ok, *backward;      /* 0/1 bytes (torch.bool storage)                   */
+  float *opl;                  /* optional: optical path length entrance -> image
+                                  (general-surface lenses only; NULL = not wanted)  */
 } TlTraceOut;
 
 /* Upstream gradients of the four differentiable outputs; contiguous [B,F,P,W]
@@ -106,6 +115,8 @@ typedef struct TlSpotOut {
   float *rms;                  /* [B]   mean over fields of the y-RMS (rtl:678-702, every lens) */
   float *rms_field;            /* [B,F] per-field RMS                               */
   float *gc, *gt, *gmu, *gz;   /* d rms[b] / d{c[b,:], t[b,:], mu[b,:,:], z[b]}; NULL if no grad */
+  float *gk, *ga;              /* general-surface lenses: d rms[b] / d{k[b,:], a[b,:,:]}; both
+                                  non-NULL selects the general moment layout          */
 } TlSpotOut;
 
 int tl_abi_version(void);
@@ -141,6 +152,7 @@ int tl_rms_bwd(const float *y, const uint8_t *ok, const double *stats, const flo
  * tl_spot_finalize turns the (reduced) moments into the RMS and its gradients;
  * P_total is the full pupil count of the job. */
 int32_t tl_spot_moment_count(int32_t S, int32_t want_grad);
+int32_t tl_spot_moment_count_general(int32_t S, int32_t want_grad);   /* general-surface lenses */
 size_t tl_spot_workspace(const TlProblem *pb, int32_t want_grad);
 int tl_spot_accumulate(const TlProblem *pb, int32_t want_grad, double *moments, float *ref_y,
                        void *workspace, size_t workspace_bytes, void *stream);

@@ -1,0 +1,120 @@
+"""Extension surfaces (conic / even asphere / clip / OPL) on the GPU against the extension
+oracle.  PARITY UNPINNED: the reference has no such surfaces; the oracle that defines them is
+itself checked by tests/test_asphere_oracle.py.  Needs a B200: ``pytest -m gpu``."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import asphere_oracle as gen
+from oracle import trace_oracle as sph
+from tests.conftest import load_golden
+from tests.test_asphere_oracle import _asphere_problem
+from torchoptics_b200 import ops
+from torchoptics_b200 import ray_tracing_lite as rt
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _rel(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-30)
+
+
+def _to(p, dev, grad=()):
+    q = {k: v.to(dev) for k, v in p.items()}
+    for k in grad:
+        q[k] = q[k].clone().requires_grad_(True)
+    return q
+
+
+def _problem(n=400, clip=True):
+    p = _asphere_problem(torch.float32, n=n)
+    sd = torch.full_like(p['c'], float('inf'))
+    if clip:
+        sd[..., 2] = 1.7
+    p['sd'] = sd
+    return p
+
+
+def _call(fn, q, **kw):
+    return fn(q['x'], q['y'], q['z'], q['cx'], q['cy'], q['c'], q['t'], q['mu'], q['mask'], **kw)
+
+
+def test_forward_exact_policy_bit_identical_incl_opl_and_clip():
+    p = _problem()
+    with sph.ieee_sqrt():
+        ref = _call(gen.trace, p, k=p['k'], a=p['a'], sd=p['sd'])
+    assert 0 < int(ref[4].sum()) < ref[4].numel()
+    q = _to(p, DEV)
+    out = _call(rt.trace_skew, q, arith='exact', k=q['k'], a=q['a'], sd=q['sd'])
+    assert len(out) == 7
+    for j in (0, 1, 2, 3, 6):
+        assert np.array_equal(out[j].cpu().numpy().view(np.uint32), ref[j].numpy().view(np.uint32)), j
+    assert torch.equal(out[4].cpu(), ref[4]) and torch.equal(out[5].cpu(), ref[5])
+
+
+def test_forward_guarded_policy():
+    p = _problem()
+    ref = _call(gen.trace, p, k=p['k'], a=p['a'], sd=p['sd'])
+    q = _to(p, DEV)
+    out = _call(rt.trace_skew, q, k=q['k'], a=q['a'], sd=q['sd'])
+    assert torch.equal(out[4].cpu(), ref[4]) and torch.equal(out[5].cpu(), ref[5])
+    scale = float(ref[1].abs().max())
+    for j, tol in ((0, 1e-5 * scale), (1, 1e-5 * scale), (2, 1e-5), (3, 1e-5), (6, 1e-5 * float(ref[6].max()))):
+        assert float((out[j].cpu() - ref[j]).abs().max()) <= tol, j
+    dead = ~ref[4]
+    for j in range(4):
+        assert not out[j].cpu()[dead].any()
+
+
+@pytest.mark.parametrize('arith', ['guarded', 'exact'])
+@pytest.mark.parametrize('clip', [False, True])
+def test_fused_spot_pass_general_surfaces(arith, clip):
+    p = _problem(n=600, clip=clip)
+    wrt = ('z', 'c', 't', 'mu', 'k', 'a')
+    # truth: the oracle in fp64; the fp32 oracle tells how much fp32 noise to expect
+    def oracle_run(dtype):
+        o = {k: (v if k == 'mask' else v.to(dtype)) for k, v in p.items()}
+        for k in wrt:
+            o[k] = o[k].clone().requires_grad_(True)
+        out = _call(gen.trace, o, k=o['k'], a=o['a'], sd=o['sd'])
+        rms = sph.spot_rms(out[0], out[1], out[4])
+        return rms, torch.autograd.grad(rms, [o[k] for k in wrt])
+    ref_rms, ref = oracle_run(torch.float64)
+    q = _to(p, DEV, grad=wrt)
+    rms, field = _call(ops.spot_rms, q, arith=rt._arith_code(arith), k=q['k'], a=q['a'], sd=q['sd'])
+    assert abs(rms[0].item() - ref_rms.item()) <= 2e-5 * ref_rms.item(), (rms[0].item(), ref_rms.item())
+    got = torch.autograd.grad(rms[0], [q[k] for k in wrt])
+    for name, g, r in zip(wrt, got, ref):
+        assert g.shape == r.shape, name
+        g, r = g.cpu().numpy(), r.numpy()
+        if name == 'z':
+            scale = max(abs(float(r.ravel()[0])), float(np.abs(ref[2].numpy()).max()))
+            assert abs(float(g.ravel()[0]) - float(r.ravel()[0])) <= 2e-4 * scale
+        elif name == 'a':
+            for i in range(7):      # coefficients of rho^2 .. rho^8 live on very different scales
+                assert _rel(g[..., i], r[..., i]) <= 2e-4, (name, i, _rel(g[..., i], r[..., i]))
+        else:
+            assert _rel(g, r) <= 2e-4, (name, _rel(g, r))
+
+
+def test_general_kernels_reduce_to_the_spherical_ones():
+    """k = 0, a = 0, sd = inf through the general kernels == the spherical kernels."""
+    rec = load_golden('cooke_32x32')
+    i = {k[3:]: torch.from_numpy(rec[k]).to(DEV) for k in rec if k.startswith('in_')}
+    for k in ('z', 'c', 't', 'mu'):
+        i[k] = i[k].clone().requires_grad_(True)
+    args = [i[k] for k in ('x', 'y', 'z', 'cx', 'cy', 'c', 't', 'mu', 'mask')]
+    rms_s, _ = ops.spot_rms(*args)
+    g_s = torch.autograd.grad(rms_s[0], [i[k] for k in ('c', 't', 'mu')])
+    zeros = torch.zeros_like(i['c'].detach())
+    rms_g, _ = ops.spot_rms(*args, k=zeros)
+    g_g = torch.autograd.grad(rms_g[0], [i[k] for k in ('c', 't', 'mu')])
+    assert abs(rms_g[0].item() - rms_s[0].item()) <= 1e-5 * rms_s[0].item()
+    for a_, b_ in zip(g_g, g_s):
+        assert _rel(a_.cpu().numpy(), b_.cpu().numpy()) <= 1e-4
+    out_s = rt.trace_skew(*[a_.detach() for a_ in args])
+    out_g = rt.trace_skew(*[a_.detach() for a_ in args], k=zeros)
+    assert torch.equal(out_s[4], out_g[4]) and torch.equal(out_s[5], out_g[5])
+    assert float((out_s[1] - out_g[1]).abs().max()) <= 1e-5 * float(out_s[1].abs().max())

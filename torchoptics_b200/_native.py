@@ -17,6 +17,8 @@ ARITH_EXACT = 1
 MAX_SURFACES_FWD = 256
 MAX_SURFACES_BWD = 32
 MAX_SURFACES_SPOT = 16
+MAX_SURFACES_GEN = 48
+N_ASPHERE_TERMS = 7
 
 
 class NativeLibraryError(RuntimeError):
@@ -36,11 +38,12 @@ class TlProblem(ctypes.Structure):
                 ('W', ctypes.c_int32), ('S', ctypes.c_int32),
                 ('allow_backward_rays', ctypes.c_int32), ('arith', ctypes.c_int32),
                 ('p_begin', ctypes.c_int32), ('p_end', ctypes.c_int32),
-                ('xy_scale', ctypes.c_void_p)]
+                ('xy_scale', ctypes.c_void_p),
+                ('k', ctypes.c_void_p), ('a', ctypes.c_void_p), ('sd', ctypes.c_void_p)]
 
 
 class TlTraceOut(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_void_p) for n in ('x', 'y', 'cx', 'cy', 'ok', 'backward')]
+    _fields_ = [(n, ctypes.c_void_p) for n in ('x', 'y', 'cx', 'cy', 'ok', 'backward', 'opl')]
 
 
 class TlSeeds(ctypes.Structure):
@@ -58,7 +61,7 @@ class TlLens(ctypes.Structure):
 
 
 class TlSpotOut(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_void_p) for n in ('rms', 'rms_field', 'gc', 'gt', 'gmu', 'gz')]
+    _fields_ = [(n, ctypes.c_void_p) for n in ('rms', 'rms_field', 'gc', 'gt', 'gmu', 'gz', 'gk', 'ga')]
 
 
 EXPORTS = {
@@ -77,6 +80,7 @@ EXPORTS = {
     'tl_rms_bwd': (ctypes.c_int, [ctypes.c_void_p] * 4 + [ctypes.c_int32] * 4 +
                    [ctypes.c_void_p, ctypes.c_void_p]),
     'tl_spot_moment_count': (ctypes.c_int32, [ctypes.c_int32, ctypes.c_int32]),
+    'tl_spot_moment_count_general': (ctypes.c_int32, [ctypes.c_int32, ctypes.c_int32]),
     'tl_spot_workspace': (ctypes.c_size_t, [ctypes.POINTER(TlProblem), ctypes.c_int32]),
     'tl_spot_accumulate': (ctypes.c_int, [ctypes.POINTER(TlProblem), ctypes.c_int32, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
@@ -104,7 +108,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.tl_abi_version() != 2:
+    if lib.tl_abi_version() != 3:
         raise NativeLibraryError('libtorchoptics_b200.so: ABI version mismatch, rebuild it')
     _lib = lib
     return lib

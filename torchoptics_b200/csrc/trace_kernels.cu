@@ -17,6 +17,7 @@
 
 #include "../../include/torchoptics_b200.h"
 #include "trace_core.cuh"
+#include "trace_core_asph.cuh"
 
 using namespace tl;
 
@@ -556,6 +557,8 @@ __global__ void k_reduce_rows(const double *partial, double *dst, int n_rows, in
   dst[i] = s;
 }
 
+#include "trace_kernels_gen.cuh"
+
 // rows[b,f,w][3S+1] -> gc[b,S], gt[b,S], gmu[b,w,S], gz[b]
 __global__ void k_bwd_finalize(const double *rows, TlGrads g, int B, int F, int W, int S) {
   const int n_acc = 3 * S + 1;
@@ -893,11 +896,16 @@ __global__ void k_stage_bwd(TlLens ln, const float *gmu, const float *gz, float 
 // --------------------------------------------------------------------------
 // host-side planning
 // --------------------------------------------------------------------------
+typedef void (*AdjKernelPtr)(TlProblem, AdjArgs);
+
+bool is_general(const TlProblem &pb) { return pb.k || pb.a || pb.sd; }
+
 int validate(const TlProblem *pb, int max_s) {
   if (!pb) return fail(TL_ERR_INVALID, "problem is NULL%s");
   if (pb->B < 1 || pb->F < 1 || pb->P < 1 || pb->W < 1 || pb->S < 1)
     return fail(TL_ERR_INVALID, "B, F, P, W, S must all be >= 1%s");
-  if (pb->S > max_s) return fail(TL_ERR_INVALID, "too many surfaces for this entry point%s");
+  if (pb->S > (is_general(*pb) ? TL_MAX_SURFACES_GEN : max_s))
+    return fail(TL_ERR_INVALID, "too many surfaces for this entry point%s");
   if (!pb->x.ptr || !pb->y.ptr || !pb->z.ptr || !pb->cx.ptr || !pb->cy.ptr || !pb->c || !pb->t ||
       !pb->mu || !pb->live)
     return fail(TL_ERR_INVALID, "NULL input pointer%s");
@@ -909,6 +917,15 @@ int validate(const TlProblem *pb, int max_s) {
 }
 
 // K1 grid: chunks per (b,f,w) so that the machine is filled a few times over
+int n_acc_gen(int S, int want_grad) { return want_grad ? kGenSlots * S + 5 : 3; }
+
+// plan of the general-surface spot kernel
+struct GenPlan {
+  AdjKernelPtr kernel = nullptr;
+  int lanes = 2, n_blocks = 1, groups_per_row = 1, max_seg = 1, n_acc = 0;
+  size_t smem = 0, partial_bytes = 0;
+};
+
 struct FwdPlan {
   int nchunks = 1, chunk_len = 1, n_blocks = 1;
 };
@@ -931,7 +948,7 @@ int n_acc_of(int mode, int S) {
 }
 
 // ---- K2/K3 variants -------------------------------------------------------
-typedef void (*AdjKernel)(TlProblem, AdjArgs);
+typedef AdjKernelPtr AdjKernel;
 
 struct AdjVariant {
   AdjKernel kernel = nullptr;
@@ -1045,6 +1062,38 @@ int reduce_rows(const AdjPlan &pl, const double *partial, double *rows_out, int 
   return TL_OK;
 }
 
+int plan_gen(const TlProblem &pb, int want_grad, GenPlan &pl) {
+  DeviceInfo info;
+  int rc = device_info(info);
+  if (rc) return rc;
+  pl.lanes = want_grad ? 2 : 4;
+  pl.kernel = want_grad ? (AdjKernelPtr)k_trace_gen<MODE_SPOT_GRAD, f2>
+                        : (AdjKernelPtr)k_trace_gen<MODE_SPOT_EVAL, f4>;
+  pl.n_acc = n_acc_gen(pb.S, want_grad);
+  const size_t table = ((14 * (size_t)pb.S + 2 + 3) & ~(size_t)3) * sizeof(float);
+  const size_t rows = want_grad ? (size_t)(kTraceThreads / 32) * pb.S * kGenRow * sizeof(float) : 0;
+  const size_t state = want_grad ? (size_t)4 * pb.S * kTraceThreads * pl.lanes * sizeof(float) : 0;
+  pl.smem = table + rows + state + 16;
+  if (pl.smem > 227 * 1024) return fail(TL_ERR_INVALID, "surface count needs too much shared memory%s");
+  if (pl.smem > 48 * 1024)
+    TL_CHECK_CUDA(cudaFuncSetAttribute((const void *)pl.kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  int per_sm = 0;
+  TL_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)pl.kernel,
+                                                              kTraceThreads, pl.smem));
+  if (per_sm < 1) return fail(TL_ERR_CUDA, "kernel does not fit on an SM%s");
+  const int group = kTraceThreads * pl.lanes;
+  pl.groups_per_row = (pb.p_end - pb.p_begin + group - 1) / group;
+  const int64_t total = (int64_t)pb.B * pb.F * pb.W * pl.groups_per_row;
+  int64_t n_blocks = (int64_t)info.sms * per_sm;
+  if (n_blocks > total) n_blocks = total;
+  pl.n_blocks = (int)n_blocks;
+  const int64_t len = (total + n_blocks - 1) / n_blocks;
+  pl.max_seg = (int)((len - 1 + pl.groups_per_row - 1) / pl.groups_per_row + 1);
+  pl.partial_bytes = align8((size_t)pl.n_blocks * pl.max_seg * pl.n_acc * sizeof(double));
+  return TL_OK;
+}
+
 }  // namespace
 
 // --------------------------------------------------------------------------
@@ -1065,6 +1114,14 @@ int tl_trace_fwd(const TlProblem *pb, const TlTraceOut *out, void *stream_) {
   rc = device_info(info);
   if (rc) return rc;
   const FwdPlan pl = make_fwd_plan(info.sms, pb->B * pb->F * pb->W, pb->P, 2 * kFwdThreads, 4);
+  if (is_general(*pb)) {
+    const size_t smem = (14 * (size_t)pb->S + 2) * sizeof(float);
+    k_trace_fwd_gen<<<pl.n_blocks, kFwdThreads, smem, (cudaStream_t)stream_>>>(*pb, *out, pl.nchunks,
+                                                                               pl.chunk_len);
+    g_launches++;
+    TL_CHECK_CUDA(cudaGetLastError());
+    return TL_OK;
+  }
   const size_t smem = 5 * (size_t)pb->S * sizeof(float);
   k_trace_fwd<<<pl.n_blocks, kFwdThreads, smem, (cudaStream_t)stream_>>>(*pb, *out, pl.nchunks,
                                                                          pl.chunk_len);
@@ -1074,7 +1131,7 @@ int tl_trace_fwd(const TlProblem *pb, const TlTraceOut *out, void *stream_) {
 }
 
 size_t tl_trace_bwd_workspace(const TlProblem *pb) {
-  if (validate(pb, TL_MAX_SURFACES_BWD)) return 0;
+  if (validate(pb, TL_MAX_SURFACES_BWD) || is_general(*pb)) return 0;
   TlProblem full = *pb;
   full.p_begin = 0;
   full.p_end = pb->P;
@@ -1089,6 +1146,9 @@ int tl_trace_bwd(const TlProblem *pb_, const TlSeeds *seeds, const TlGrads *grad
   if (rc) return rc;
   if (!seeds || !grads || !grads->gc || !grads->gt || !grads->gmu || !grads->gz_sum)
     return fail(TL_ERR_INVALID, "NULL seeds/grads%s");
+  if (is_general(*pb_))
+    return fail(TL_ERR_INVALID, "tl_trace_bwd: general-surface lenses are differentiated by the fused "
+                                "spot pass only (tl_spot_accumulate)%s");
   TlProblem pb = *pb_;
   pb.p_begin = 0;
   pb.p_end = pb.P;
@@ -1165,9 +1225,16 @@ int32_t tl_spot_moment_count(int32_t S, int32_t want_grad) {
   return n_acc_of(want_grad ? MODE_SPOT_GRAD : MODE_SPOT_EVAL, S);
 }
 
+int32_t tl_spot_moment_count_general(int32_t S, int32_t want_grad) { return n_acc_gen(S, want_grad); }
+
 size_t tl_spot_workspace(const TlProblem *pb, int32_t want_grad) {
   if (validate(pb, want_grad ? TL_MAX_SURFACES_SPOT : TL_MAX_SURFACES_FWD)) return 0;
   if (pb->p_begin < 0 || pb->p_end > pb->P || pb->p_end <= pb->p_begin) return 0;
+  if (is_general(*pb)) {
+    GenPlan gp;
+    if (plan_gen(*pb, want_grad, gp)) return 0;
+    return gp.partial_bytes;
+  }
   AdjPlan pl;
   if (plan_adj(*pb, want_grad ? MODE_SPOT_GRAD : MODE_SPOT_EVAL, pl)) return 0;
   return pl.partial_bytes;
@@ -1180,6 +1247,37 @@ int tl_spot_accumulate(const TlProblem *pb, int32_t want_grad, double *moments, 
   if (pb->p_begin < 0 || pb->p_end > pb->P || pb->p_end <= pb->p_begin)
     return fail(TL_ERR_INVALID, "empty or out-of-range pupil slice%s");
   if (!moments || !ref_y) return fail(TL_ERR_INVALID, "NULL moments/ref_y%s");
+  if (is_general(*pb)) {
+    GenPlan gp;
+    rc = plan_gen(*pb, want_grad, gp);
+    if (rc) return rc;
+    if (!workspace || workspace_bytes < gp.partial_bytes)
+      return fail(TL_ERR_WORKSPACE, "workspace too small for tl_spot_accumulate%s");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int n_bf = pb->B * pb->F;
+    k_chief_rays_gen<<<(n_bf + 127) / 128, 128, 0, stream>>>(*pb, ref_y);
+    g_launches++;
+    AdjArgs args;
+    memset(&args, 0, sizeof(args));
+    args.partial = (double *)workspace;
+    args.ref_y = ref_y;
+    args.groups_per_row = gp.groups_per_row;
+    args.max_seg = gp.max_seg;
+    args.n_acc = gp.n_acc;
+    TlProblem pb_copy = *pb;
+    void *params[] = {(void *)&pb_copy, (void *)&args};
+    TL_CHECK_CUDA(cudaLaunchKernel((const void *)gp.kernel, dim3(gp.n_blocks), dim3(kTraceThreads),
+                                   params, gp.smem, stream));
+    g_launches++;
+    const int rows = pb->B * pb->F * pb->W;
+    const int64_t n = (int64_t)rows * gp.n_acc;
+    k_reduce_rows<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(args.partial, moments, rows,
+                                                                   gp.groups_per_row, gp.n_blocks,
+                                                                   gp.max_seg, gp.n_acc);
+    g_launches++;
+    TL_CHECK_CUDA(cudaGetLastError());
+    return TL_OK;
+  }
   const int mode = want_grad ? MODE_SPOT_GRAD : MODE_SPOT_EVAL;
   AdjPlan pl;
   rc = plan_adj(*pb, mode, pl);
@@ -1209,6 +1307,14 @@ int tl_spot_finalize(const double *moments, const float *ref_y, int32_t B, int32
     return fail(TL_ERR_INVALID, "NULL gradient output%s");
   if ((size_t)F * 3 * sizeof(double) > 40 * 1024)
     return fail(TL_ERR_INVALID, "too many fields%s");
+  if (out->gk || out->ga) {                      // general-surface moment layout
+    if (want_grad && (!out->gk || !out->ga)) return fail(TL_ERR_INVALID, "gk and ga go together%s");
+    k_spot_finalize_gen<<<B, 256, (size_t)F * 3 * sizeof(double), (cudaStream_t)stream_>>>(
+        moments, ref_y, B, F, W, S, (double)P_total * (double)W, want_grad, *out);
+    g_launches++;
+    TL_CHECK_CUDA(cudaGetLastError());
+    return TL_OK;
+  }
   const int n_acc = n_acc_of(want_grad ? MODE_SPOT_GRAD : MODE_SPOT_EVAL, S);
   const size_t base = (size_t)F * 3 * sizeof(double);
   const size_t staged = base + (size_t)F * W * n_acc * sizeof(double);

@@ -1,0 +1,499 @@
+// Kernels for lenses with EXTENSION surfaces (conic / even asphere / clear semi-diameter,
+// optical path length): included by trace_kernels.cu inside its anonymous namespace.
+//
+// Same structure as the spherical kernels (persistent CTAs over contiguous (row, group)
+// slices, packed two-ray lanes, guarded fast path + exact re-trace, parked hit point +
+// incoming direction, geometric adjoint sweep), with two differences forced by the 11
+// gradients per surface (c, k, a4..a16, t, mu), twice (plain and (y - y0)-weighted):
+//   * the accumulators do not fit the register file, so every adjoint step reduces its 22
+//     values across the warp with a halving butterfly (31 shuffles; lane i ends up with the
+//     warp total of value i) and adds them to a per-warp accumulator row in shared memory;
+//   * the surface loops are therefore rolled (no static accumulator indices needed).
+#pragma once
+
+constexpr int kGenPar = kAsphParams + 2;        // c, k, a4..a16, t, mu  = 11 per surface
+constexpr int kGenSlots = 2 * kGenPar;           // weighted + plain      = 22 per surface
+constexpr int kGenRow = 32;                      // padded row of the per-warp accumulators
+
+// Surface table of one (lens, wavelength) in shared memory, general surfaces.
+struct GenTable {
+  float *c, *t, *mu, *k, *sd2, *index, *a;   // index[k] = refractive index in front of surface k
+  int *live;
+  float length;
+};
+
+__device__ __forceinline__ size_t gen_table_floats(int S) { return 14 * (size_t)S + 2; }
+
+__device__ __forceinline__ GenTable load_gen_table(float *base, const TlProblem &pb, int b, int w) {
+  GenTable tab;
+  const int S = pb.S;
+  tab.c = base;
+  tab.t = base + S;
+  tab.mu = base + 2 * S;
+  tab.k = base + 3 * S;
+  tab.sd2 = base + 4 * S;
+  tab.index = base + 5 * S;                    // S + 1 entries
+  tab.live = reinterpret_cast<int *>(base + 6 * S + 1);
+  tab.a = base + 7 * S + 1;                    // 7 S entries
+  for (int k = threadIdx.x; k < S; k += blockDim.x) {
+    const int64_t i = (int64_t)b * S + k;
+    tab.c[k] = pb.c[i];
+    tab.t[k] = pb.t[i];
+    tab.mu[k] = pb.mu[((int64_t)b * pb.W + w) * S + k];
+    tab.k[k] = pb.k ? pb.k[i] : 0.f;
+    const float sd = pb.sd ? pb.sd[i] : INFINITY;
+    tab.sd2[k] = __fmul_rn(sd, sd);
+    tab.live[k] = pb.live[i] != 0;
+    for (int j = 0; j < kAsphCoefs; ++j) tab.a[k * kAsphCoefs + j] = pb.a ? pb.a[i * kAsphCoefs + j] : 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float n = 1.0f;
+    for (int k = 0; k < S; ++k) {
+      tab.index[k] = n;
+      n = __fdiv_rn(n, tab.mu[k]);             // like the oracle: index = index / mu
+    }
+    tab.index[S] = n;
+  }
+  __syncthreads();
+  float len = 0.f;
+  for (int k = 0; k < S; ++k) len += fabsf(tab.t[k]);
+  tab.length = len;
+  return tab;
+}
+
+__device__ __forceinline__ AsphSurface gen_surface(const GenTable &tab, int k) {
+  AsphSurface s;
+  s.c = tab.c[k];
+  s.k = tab.k[k];
+  s.t = tab.t[k];
+  s.mu = tab.mu[k];
+  s.sd2 = tab.sd2[k];
+#pragma unroll
+  for (int j = 0; j < kAsphCoefs; ++j) s.a[j] = tab.a[k * kAsphCoefs + j];
+  return s;
+}
+
+struct TracedGen {
+  Ray<float> pre;
+  float x, y, opl;
+  bool ok, backward;
+};
+
+template <bool SAVE>
+__device__ __noinline__ TracedGen trace_exact_gen(float x, float y, float z, float cx, float cy,
+                                                  const GenTable &tab, int S, bool allow_backward,
+                                                  float *state, int stride) {
+  Ray<float> r{x, y, z, cx, cy, exact_cz0(cx, cy)};
+  bool ok = true, backward = false;
+  float index = 1.0f, opl = 0.0f;
+  for (int k = 0; k < S; ++k) {
+    const float in_cx = r.cx, in_cy = r.cy;
+    exact_asph_surface(r, gen_surface(tab, k), k > 0 && tab.live[k - 1], allow_backward, ok, backward,
+                       index, opl);
+    park<SAVE, float>(state, stride, k, r.x, r.y, in_cx, in_cy);
+  }
+  TracedGen out;
+  out.pre = r;
+  exact_asph_image(r, tab.live[S - 1] != 0, allow_backward, ok, backward, index, opl);
+  out.x = r.x;
+  out.y = r.y;
+  out.opl = opl;
+  out.ok = ok;
+  out.backward = backward;
+  return out;
+}
+
+template <class V>
+struct TracedGenN {
+  Ray<V> pre;
+  V x, y, opl;
+  bool ok[LaneCount<V>::value], backward[LaneCount<V>::value];
+};
+
+template <bool SAVE, class V>
+__device__ __forceinline__ TracedGenN<V> trace_guarded_gen(V x, V y, V z, V cx, V cy,
+                                                           const GenTable &tab, int S,
+                                                           bool allow_backward, int arith, V *state,
+                                                           int stride) {
+  constexpr int N = LaneCount<V>::value;
+  TracedGenN<V> out;
+  bool clear[N];
+#pragma unroll
+  for (int l = 0; l < N; ++l) clear[l] = false;
+  if (arith == TL_ARITH_GUARDED) {
+    Ray<V> r{x, y, z, cx, cy, fast_cz0(cx, cy)};
+    V min_cos2(1.0f), min_travel(3.0e38f), min_clip(3.0e38f), opl(0.0f);
+#pragma unroll 1
+    for (int k = 0; k < S; ++k) {
+      const V in_cx = r.cx, in_cy = r.cy;
+      V travel;
+      // clip margin relative to the size of rho: computed against sd2 inside
+      fast_asph_surface(r, gen_surface(tab, k), min_cos2, travel, min_clip, V(tab.index[k]), opl);
+      park<SAVE, V>(state, stride, k, r.x, r.y, in_cx, in_cy);
+      if (k > 0 && tab.live[k - 1]) min_travel = fmin2(min_travel, travel);
+    }
+    out.pre = r;
+    const V rcz = frcp(r.cz);
+    const V dist = -r.z * rcz;
+    opl = ffma(V(tab.index[S]), dist, opl);
+    const V travel = fast_image(r);
+    if (tab.live[S - 1]) min_travel = fmin2(min_travel, travel);
+    out.x = r.x;
+    out.y = r.y;
+    out.opl = opl;
+    const V probe = ((r.x + r.y) + (r.cx + r.cy)) + opl;
+#pragma unroll
+    for (int l = 0; l < N; ++l) {
+      const float band = kBandTravelRel * fmaxf(1.0f, tab.length + fabsf(lane_get(z, l)));
+      clear[l] = (lane_get(min_cos2, l) > kGuard + kBandCos2) && (lane_get(min_travel, l) > band) &&
+                 (lane_get(min_clip, l) > kBandTravelRel * fmaxf(1.0f, tab.length * tab.length)) &&
+                 (fabsf(lane_get(probe, l)) < 3.0e38f);
+    }
+  }
+#pragma unroll
+  for (int l = 0; l < N; ++l) {
+    out.ok[l] = true;
+    out.backward[l] = false;
+    if (!clear[l]) {
+      const TracedGen one = trace_exact_gen<SAVE>(lane_get(x, l), lane_get(y, l), lane_get(z, l),
+                                                  lane_get(cx, l), lane_get(cy, l), tab, S,
+                                                  allow_backward, reinterpret_cast<float *>(state) + l,
+                                                  N * stride);
+      lane_set(out.pre.x, l, one.pre.x);
+      lane_set(out.pre.y, l, one.pre.y);
+      lane_set(out.pre.z, l, one.pre.z);
+      lane_set(out.pre.cx, l, one.pre.cx);
+      lane_set(out.pre.cy, l, one.pre.cy);
+      lane_set(out.pre.cz, l, one.pre.cz);
+      lane_set(out.x, l, one.x);
+      lane_set(out.y, l, one.y);
+      lane_set(out.opl, l, one.opl);
+      out.ok[l] = one.ok;
+      out.backward[l] = one.backward;
+    }
+  }
+  return out;
+}
+
+// Halving butterfly: v[0..31] per lane in, lane i holds sum over the warp of v[i] out (in v[0]).
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = upper ? v[i] : v[i + n / 2];
+      const float keep = upper ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// --------------------------------------------------------------------------
+// forward trace, general surfaces (+ optical path length)
+// --------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFwdThreads)
+k_trace_fwd_gen(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
+  extern __shared__ float smem[];
+  int blk = blockIdx.x;
+  const int chunk = blk % nchunks; blk /= nchunks;
+  const int w = blk % pb.W; blk /= pb.W;
+  const int f = blk % pb.F;
+  const int b = blk / pb.F;
+  const GenTable tab = load_gen_table(smem, pb, b, w);
+  const int p_lo = chunk * chunk_len;
+  const int p_hi = min(pb.P, p_lo + chunk_len);
+  const float xy_scale = pb.xy_scale ? pb.xy_scale[b] : 1.0f;
+  for (int p0 = p_lo + threadIdx.x; p0 < p_hi; p0 += 2 * kFwdThreads) {
+    const int p1 = p0 + kFwdThreads;
+    const bool has1 = p1 < p_hi;
+    const int q1 = has1 ? p1 : p0;
+    f2 x(__fmul_rn(pb.x.ptr[offset_of(pb.x, b, f, p0, w)], xy_scale),
+         __fmul_rn(pb.x.ptr[offset_of(pb.x, b, f, q1, w)], xy_scale));
+    f2 y(__fmul_rn(pb.y.ptr[offset_of(pb.y, b, f, p0, w)], xy_scale),
+         __fmul_rn(pb.y.ptr[offset_of(pb.y, b, f, q1, w)], xy_scale));
+    const f2 z(pb.z.ptr[offset_of(pb.z, b, f, p0, w)], pb.z.ptr[offset_of(pb.z, b, f, q1, w)]);
+    const f2 cx(pb.cx.ptr[offset_of(pb.cx, b, f, p0, w)], pb.cx.ptr[offset_of(pb.cx, b, f, q1, w)]);
+    const f2 cy(pb.cy.ptr[offset_of(pb.cy, b, f, p0, w)], pb.cy.ptr[offset_of(pb.cy, b, f, q1, w)]);
+    const TracedGenN<f2> tr = trace_guarded_gen<false, f2>(x, y, z, cx, cy, tab, pb.S,
+                                                           pb.allow_backward_rays != 0, pb.arith,
+                                                           nullptr, 0);
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+      if (l == 1 && !has1) break;
+      const int64_t o = (((int64_t)b * pb.F + f) * pb.P + (l ? p1 : p0)) * pb.W + w;
+      out.x[o] = lane_get(tr.x, l);
+      out.y[o] = lane_get(tr.y, l);
+      out.cx[o] = lane_get(tr.pre.cx, l);
+      out.cy[o] = lane_get(tr.pre.cy, l);
+      out.ok[o] = tr.ok[l];
+      out.backward[o] = tr.backward[l];
+      if (out.opl) out.opl[o] = lane_get(tr.opl, l);
+    }
+  }
+}
+
+// Chief-ray reference heights for general lenses (fast policy, see k_chief_rays).
+__global__ void k_chief_rays_gen(TlProblem pb, float *ref_y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= pb.B * pb.F) return;
+  const int b = i / pb.F, f = i % pb.F, S = pb.S;
+  const float cx = pb.cx.ptr[offset_of(pb.cx, b, f, 0, 0)], cy = pb.cy.ptr[offset_of(pb.cy, b, f, 0, 0)];
+  Ray<float> r{0.f, 0.f, pb.z.ptr[offset_of(pb.z, b, f, 0, 0)], cx, cy, fast_cz0(cx, cy)};
+  float min_cos2 = 1.0f, travel, min_clip = 3.0e38f, opl = 0.f;
+  for (int k = 0; k < S; ++k) {
+    const int64_t j = (int64_t)b * S + k;
+    AsphSurface s;
+    s.c = pb.c[j];
+    s.t = pb.t[j];
+    s.mu = pb.mu[((int64_t)b * pb.W) * S + k];
+    s.k = pb.k ? pb.k[j] : 0.f;
+    s.sd2 = INFINITY;
+    for (int q = 0; q < kAsphCoefs; ++q) s.a[q] = pb.a ? pb.a[j * kAsphCoefs + q] : 0.f;
+    fast_asph_surface(r, s, min_cos2, travel, min_clip, 1.0f, opl);
+  }
+  fast_image(r);
+  ref_y[i] = (min_cos2 > kGuard && fabsf(r.y) < 3.0e38f) ? r.y : 0.f;
+}
+
+// --------------------------------------------------------------------------
+// fused spot pass, general surfaces.  MODE_SPOT_GRAD / MODE_SPOT_EVAL.
+// moments row layout: per surface 22 = [11 weighted | 11 plain] (c, k, a4..a16, t, mu),
+// then {weighted z, plain z, S1, S2, n_ok}: n_acc = 22 S + 5  (EVAL: 3).
+// --------------------------------------------------------------------------
+template <int MODE, class V>
+__global__ void __launch_bounds__(kTraceThreads)
+k_trace_gen(TlProblem pb, AdjArgs args) {
+  extern __shared__ float smem[];
+  constexpr int N = LaneCount<V>::value;
+  constexpr bool kAdjoint = MODE == MODE_SPOT_GRAD;
+  constexpr int kWarps = kTraceThreads / 32;
+  const int S = pb.S;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int stride = kTraceThreads;
+  const bool allow_backward = pb.allow_backward_rays != 0;
+  const int n_acc = args.n_acc;
+  float *after_table = smem + ((gen_table_floats(S) + 3) & ~(size_t)3);
+  // [warp][surface][32] accumulator rows, then the parked states
+  float *acc_rows = after_table;
+  const size_t acc_floats = kAdjoint ? (size_t)kWarps * S * kGenRow : 0;
+  V *state = reinterpret_cast<V *>(after_table + acc_floats) + tid;
+  float *my_rows = acc_rows + (size_t)warp * S * kGenRow;
+
+  const int64_t total = (int64_t)pb.B * pb.F * pb.W * args.groups_per_row;
+  const int64_t g_begin = total * blockIdx.x / gridDim.x;
+  const int64_t g_end = total * (blockIdx.x + 1) / gridDim.x;
+
+  __shared__ float tail[kTraceThreads / 32][5];
+  float acc_z = 0.f, wac_z = 0.f, m_s1 = 0.f, m_s2 = 0.f, m_n = 0.f;
+  GenTable tab;
+  float y0 = 0.f, xy_scale = 1.0f;
+  int row = -1, seg = 0, b = 0, f = 0, w = 0;
+
+  auto flush = [&]() {
+    __syncthreads();
+    double *dst = args.partial + ((int64_t)blockIdx.x * args.max_seg + seg) * n_acc;
+    if (kAdjoint) {
+      for (int i = tid; i < S * kGenSlots; i += kTraceThreads) {
+        const int k = i / kGenSlots, j = i % kGenSlots;
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < kWarps; ++q) s += (double)acc_rows[((size_t)q * S + k) * kGenRow + j];
+        dst[i] = s;
+      }
+    }
+    // the five per-thread scalars: warp shuffle -> smem -> fp64
+    const float vals[5] = {wac_z, acc_z, m_s1, m_s2, m_n};
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const float v = warp_sum(vals[j]);
+      if (lane == 0) tail[warp][j] = v;
+    }
+    __syncthreads();
+    const int base = kAdjoint ? S * kGenSlots : 0;
+    const int first = kAdjoint ? 0 : 2;          // EVAL keeps only S1, S2, n_ok
+    if (tid < 5 - first) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < kWarps; ++q) s += (double)tail[q][first + tid];
+      dst[base + tid] = s;
+    }
+    ++seg;
+    __syncthreads();
+  };
+
+  for (int64_t g = g_begin; g < g_end; ++g) {
+    const int r = (int)(g / args.groups_per_row);
+    const int j = (int)(g % args.groups_per_row);
+    if (r != row) {
+      if (row >= 0) flush();
+      row = r;
+      w = r % pb.W;
+      f = (r / pb.W) % pb.F;
+      b = r / (pb.W * pb.F);
+      tab = load_gen_table(smem, pb, b, w);
+      xy_scale = pb.xy_scale ? pb.xy_scale[b] : 1.0f;
+      y0 = args.ref_y[b * pb.F + f];
+      if (kAdjoint)
+        for (int i = lane; i < S * kGenRow; i += 32) my_rows[i] = 0.f;
+      acc_z = wac_z = m_s1 = m_s2 = m_n = 0.f;
+      __syncwarp();
+    }
+    const int p_base = pb.p_begin + j * (kTraceThreads * N) + tid;
+    bool has[N];
+    V x, y, z, cx, cy;
+#pragma unroll
+    for (int l = 0; l < N; ++l) {
+      const int p = p_base + l * kTraceThreads;
+      has[l] = p < pb.p_end;
+      const int q = has[l] ? p : min(p_base, pb.p_end - 1);
+      lane_set(x, l, __fmul_rn(pb.x.ptr[offset_of(pb.x, b, f, q, w)], xy_scale));
+      lane_set(y, l, __fmul_rn(pb.y.ptr[offset_of(pb.y, b, f, q, w)], xy_scale));
+      lane_set(z, l, pb.z.ptr[offset_of(pb.z, b, f, q, w)]);
+      lane_set(cx, l, pb.cx.ptr[offset_of(pb.cx, b, f, q, w)]);
+      lane_set(cy, l, pb.cy.ptr[offset_of(pb.cy, b, f, q, w)]);
+    }
+    // NOTE: no early `continue` for threads past the end of the row -- every lane of the warp
+    // takes part in the shuffles below; such threads simply carry dead lanes.
+    TracedGenN<V> tr = trace_guarded_gen<kAdjoint, V>(x, y, z, cx, cy, tab, S, allow_backward, pb.arith,
+                                                      state, stride);
+    bool live[N], any_live = false, all_ok = true;
+    V alive, wgt(0.f);
+#pragma unroll
+    for (int l = 0; l < N; ++l) {
+      live[l] = tr.ok[l] && has[l];
+      any_live = any_live || live[l];
+      all_ok = all_ok && tr.ok[l];
+      lane_set(alive, l, live[l] ? 1.0f : 0.0f);
+    }
+    wgt = (tr.y - V(y0)) * alive;
+#pragma unroll
+    for (int l = 0; l < N; ++l)
+      if (!live[l]) lane_set(wgt, l, 0.f);
+    m_s1 += lane_sum(wgt);
+    m_s2 = lane_dot(wgt, wgt, m_s2);
+    m_n += lane_sum(alive);
+    if (kAdjoint) {
+      // the sweep is executed by whole warps (shuffles inside): a warp skips it only if none of
+      // its lanes has a live ray
+      const bool warp_live = __any_sync(0xffffffffu, any_live);
+      if (warp_live) {
+        if (!any_live) {
+          // this thread has no live ray: run the sweep on a harmless axial ray, seeded with 0
+          for (int i = 0; i < S * 4; ++i) state[(size_t)i * stride] = V(0.f);
+          tr.pre = Ray<V>{V(0.f), V(0.f), V(-tab.t[S - 1]), V(0.f), V(0.f), V(1.f)};
+          tr.x = V(0.f);
+          tr.y = V(0.f);
+          z = V(0.f);
+        } else if (!all_ok) {
+          mirror_live_lane<V>(state, stride, S, tr.ok, tr.pre, z, tr.x, tr.y);
+        }
+        Sweep<V> sw = sweep_begin(tr.pre, tr.x, tr.y, V(0.f), alive, V(0.f), V(0.f));
+#pragma unroll 1
+        for (int k = S - 1; k >= 0; --k) {
+          const V *slot = state + (size_t)k * 4 * stride;
+          const AsphGrad<V> g = sweep_asphere(sw, slot[0], slot[stride], slot[2 * stride],
+                                              slot[3 * stride], gen_surface(tab, k));
+          float v[32];
+#pragma unroll
+          for (int q = 0; q < kAsphParams; ++q) {
+            v[q] = lane_dot(wgt, g.p[q], 0.f);
+            v[kGenPar + q] = lane_sum(g.p[q]);
+          }
+          v[kAsphParams] = lane_dot(wgt, g.t, 0.f);
+          v[kAsphParams + 1] = lane_dot(wgt, g.mu, 0.f);
+          v[kGenPar + kAsphParams] = lane_sum(g.t);
+          v[kGenPar + kAsphParams + 1] = lane_sum(g.mu);
+#pragma unroll
+          for (int q = kGenSlots; q < 32; ++q) v[q] = 0.f;
+          const float total_of_lane = warp_transpose_sum(v, lane);
+          my_rows[k * kGenRow + lane] += total_of_lane;
+        }
+        V vx, vy, vz, vcx, vcy;
+        sweep_end(sw, z, vx, vy, vz, vcx, vcy);
+        acc_z += lane_sum(vz);
+        wac_z = lane_dot(wgt, vz, wac_z);
+      }
+    }
+  }
+  if (row >= 0) flush();
+}
+
+// moments[b,f,w][22 S + 5] -> rms, rms_field, gradients of the general-surface spot pass
+__global__ void k_spot_finalize_gen(const double *mom_global, const float *ref_y, int B, int F, int W,
+                                    int S, double n_rays, int want_grad, TlSpotOut out) {
+  extern __shared__ double sh[];
+  double *alpha = sh, *shift = sh + F, *rmsf = sh + 2 * F;
+  const int b = blockIdx.x;
+  const int n_acc = want_grad ? kGenSlots * S + 5 : 3;
+  const int m0 = want_grad ? kGenSlots * S + 2 : 0;
+  const double *mom = mom_global + (int64_t)b * F * W * n_acc;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    double s1 = 0.0, s2 = 0.0, n_ok = 0.0;
+    for (int w = 0; w < W; ++w) {
+      const double *row = mom + ((int64_t)f * W + w) * n_acc + m0;
+      s1 += row[0];
+      s2 += row[1];
+      n_ok += row[2];
+    }
+    const double y0 = (double)ref_y[b * F + f];
+    const double mean_rel = (s1 - (n_rays - n_ok) * y0) / n_rays;
+    double ss = s2 - 2.0 * mean_rel * s1 + n_ok * mean_rel * mean_rel;
+    if (ss < 0.0) ss = 0.0;
+    const double rms = sqrt(ss / n_rays);
+    rmsf[f] = rms;
+    alpha[f] = 1.0 / ((double)F * n_rays * rms);
+    shift[f] = mean_rel + (s1 - n_ok * mean_rel) / n_rays;
+    out.rms_field[b * F + f] = (float)rms;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int f = 0; f < F; ++f) s += rmsf[f];
+    out.rms[b] = (float)(s / F);
+  }
+  if (!want_grad) return;
+  // outputs: per surface c, k, a[7], t summed over (f, w); mu per wavelength; z
+  const int n_out = S * (kGenPar - 1) + W * S + 1;
+  for (int j = threadIdx.x; j < n_out; j += blockDim.x) {
+    double s = 0.0;
+    if (j < S * (kGenPar - 1)) {
+      const int k = j / (kGenPar - 1), q = j % (kGenPar - 1);     // q: 0 c, 1 k, 2..8 a, 9 t
+      for (int f = 0; f < F; ++f) {
+        double a = 0.0, bsum = 0.0;
+        for (int w = 0; w < W; ++w) {
+          const double *row = mom + ((int64_t)f * W + w) * n_acc + k * kGenSlots;
+          a += row[q];
+          bsum += row[kGenPar + q];
+        }
+        s += alpha[f] * (a - shift[f] * bsum);
+      }
+      const int64_t i = (int64_t)b * S + k;
+      if (q == 0) out.gc[i] = (float)s;
+      else if (q == 1) out.gk[i] = (float)s;
+      else if (q == kGenPar - 2) out.gt[i] = (float)s;
+      else out.ga[i * kAsphCoefs + (q - 2)] = (float)s;
+    } else if (j < S * (kGenPar - 1) + W * S) {
+      const int jj = j - S * (kGenPar - 1), w = jj / S, k = jj % S;
+      for (int f = 0; f < F; ++f) {
+        const double *row = mom + ((int64_t)f * W + w) * n_acc + k * kGenSlots;
+        s += alpha[f] * (row[kGenPar - 1] - shift[f] * row[2 * kGenPar - 1]);
+      }
+      out.gmu[((int64_t)b * W + w) * S + k] = (float)s;
+    } else {
+      for (int f = 0; f < F; ++f) {
+        double a = 0.0, bsum = 0.0;
+        for (int w = 0; w < W; ++w) {
+          const double *row = mom + ((int64_t)f * W + w) * n_acc + kGenSlots * S;
+          a += row[0];
+          bsum += row[1];
+        }
+        s += alpha[f] * (a - shift[f] * bsum);
+      }
+      out.gz[b] = (float)s;
+    }
+  }
+}

@@ -23,7 +23,7 @@ _GRAD_PER_RAY = ('x', 'y', 'z', 'cx', 'cy')
 class _Layout:
     """Shapes and flat device views of one trace_skew argument set."""
 
-    def __init__(self, x, y, z, cx, cy, c, t, mu, mask):
+    def __init__(self, x, y, z, cx, cy, c, t, mu, mask, k=None, a=None, sd=None):
         for name, v in (('x', x), ('y', y), ('z', z), ('cx', cx), ('cy', cy), ('c', c), ('t', t),
                         ('mu', mu), ('mask', mask)):
             nat.require_cuda(v, name)
@@ -55,6 +55,23 @@ class _Layout:
         self.mu3 = torch.broadcast_to(mu.detach(), (B, 1, 1, W, S)).reshape(B, W, S).contiguous()
         self.live = torch.broadcast_to(mask, (B, 1, 1, 1, S)).reshape(B, S).to(torch.uint8).contiguous()
         self.rays = [v.detach() for v in (x, y, z, cx, cy)]
+        # extension surfaces (no reference behaviour): conic k [B,1,1,1,S], asphere coefficients
+        # a [B,1,1,1,S,7], clear semi-diameter sd [B,1,1,1,S]; any of them selects the general kernels
+        self.general = k is not None or a is not None or sd is not None
+        self.k2 = self.a3 = self.sd2 = None
+        if self.general:
+            if S > nat.MAX_SURFACES_GEN:
+                raise ValueError(f'general-surface lenses support at most {nat.MAX_SURFACES_GEN} surfaces')
+            dev = self.device
+            def table(v, tail, fill):
+                if v is None:
+                    return torch.full((B, S) + tail, fill, dtype=torch.float32, device=dev)
+                nat.require_cuda(v, 'asphere table')
+                return torch.broadcast_to(v.detach().to(torch.float32), (B, 1, 1, 1, S) + tail) \
+                    .reshape((B, S) + tail).contiguous()
+            self.k2 = table(k, (), 0.0)
+            self.a3 = table(a, (nat.N_ASPHERE_TERMS,), 0.0)
+            self.sd2 = table(sd, (), float('inf'))
 
     def problem(self, allow_backward_rays, arith, p_begin=0, p_end=None):
         pb = nat.TlProblem()
@@ -69,6 +86,8 @@ class _Layout:
         pb.arith = int(arith)
         pb.p_begin = int(p_begin)
         pb.p_end = int(self.P if p_end is None else p_end)
+        if self.general:
+            pb.k, pb.a, pb.sd = self.k2.data_ptr(), self.a3.data_ptr(), self.sd2.data_ptr()
         return pb
 
 
@@ -78,8 +97,11 @@ def _ptr(t):
 
 class _TraceSkew(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays, arith):
-        lay = _Layout(x, y, z, cx, cy, c, t, mu, mask)
+    def forward(ctx, x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays, arith, k=None, a=None,
+                sd=None):
+        lay = _Layout(x, y, z, cx, cy, c, t, mu, mask, k, a, sd)
+        if lay.general:
+            return _TraceSkew._forward_general(ctx, lay, allow_backward_rays, arith)
         if lay.S > nat.MAX_SURFACES_FWD:
             raise ValueError(f'at most {nat.MAX_SURFACES_FWD} surfaces are supported')
         lib = nat.load()
@@ -88,7 +110,7 @@ class _TraceSkew(torch.autograd.Function):
             ok = torch.empty(lay.shape, dtype=torch.bool, device=lay.device)
             backward = torch.empty(lay.shape, dtype=torch.bool, device=lay.device)
             pb = lay.problem(allow_backward_rays, arith)
-            out = nat.TlTraceOut(*[o.data_ptr() for o in outs], ok.data_ptr(), backward.data_ptr())
+            out = nat.TlTraceOut(*[o.data_ptr() for o in outs], ok.data_ptr(), backward.data_ptr(), None)
             nat.check(lib.tl_trace_fwd(ctypes.byref(pb), ctypes.byref(out), nat.stream_ptr(lay.device)),
                       'tl_trace_fwd')
         ctx.save_for_backward(x, y, z, cx, cy, c, t, mu, mask)
@@ -97,7 +119,30 @@ class _TraceSkew(torch.autograd.Function):
         return (*outs, ok, backward)
 
     @staticmethod
-    def backward(ctx, gx, gy, gcx, gcy, _gok, _gbw):
+    def _forward_general(ctx, lay, allow_backward_rays, arith):
+        """Forward of a lens with extension surfaces: also returns the optical path length.
+        Not differentiable here -- gradients of such lenses come from the fused spot pass."""
+        lib = nat.load()
+        with torch.cuda.device(lay.device):
+            outs = [torch.empty(lay.shape, dtype=torch.float32, device=lay.device) for _ in range(4)]
+            ok = torch.empty(lay.shape, dtype=torch.bool, device=lay.device)
+            backward = torch.empty(lay.shape, dtype=torch.bool, device=lay.device)
+            opl = torch.empty(lay.shape, dtype=torch.float32, device=lay.device)
+            pb = lay.problem(allow_backward_rays, arith)
+            out = nat.TlTraceOut(*[o.data_ptr() for o in outs], ok.data_ptr(), backward.data_ptr(),
+                                 opl.data_ptr())
+            nat.check(lib.tl_trace_fwd(ctypes.byref(pb), ctypes.byref(out), nat.stream_ptr(lay.device)),
+                      'tl_trace_fwd')
+        ctx.general = True
+        ctx.mark_non_differentiable(ok, backward)
+        return (*outs, ok, backward, opl)
+
+    @staticmethod
+    def backward(ctx, gx, gy, gcx, gcy, _gok, _gbw, *_gopl):
+        if getattr(ctx, 'general', False):
+            raise NotImplementedError(
+                'trace_skew with conic / asphere / clipped surfaces is forward-only; gradients of such '
+                'lenses are produced by the fused spot pass (RayTracer.spot_rms / ops.spot_rms)')
         x, y, z, cx, cy, c, t, mu, mask = ctx.saved_tensors
         allow_backward_rays, arith = ctx.flags
         lay = _Layout(x, y, z, cx, cy, c, t, mu, mask)
@@ -140,11 +185,13 @@ class _TraceSkew(torch.autograd.Function):
         grads.append(gc.reshape(lay.B, 1, 1, 1, lay.S).sum_to_size(c.shape) if need[5] else None)
         grads.append(gt.reshape(lay.B, 1, 1, 1, lay.S).sum_to_size(t.shape) if need[6] else None)
         grads.append(gmu.reshape(lay.B, 1, 1, lay.W, lay.S).sum_to_size(mu.shape) if need[7] else None)
-        return (*grads, None, None, None)
+        return (*grads, None, None, None, None, None, None)
 
 
-def trace(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arith=nat.ARITH_GUARDED):
-    """CUDA ``trace_skew``: returns (x, y, cx, cy, ray_ok, ray_backward), all [B,F,P,W]."""
+def trace(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arith=nat.ARITH_GUARDED,
+          k=None, a=None, sd=None):
+    """CUDA ``trace_skew``: returns (x, y, cx, cy, ray_ok, ray_backward), all [B,F,P,W]; with any of
+    the extension tables k / a / sd also the optical path length as a 7th output."""
     full = torch.broadcast_shapes(x.shape, y.shape, z.shape, cx.shape, cy.shape, c.shape[:-1],
                                   t.shape[:-1], mu.shape[:-1], mask.shape[:-1])
     if 0 in full:       # empty ray set: nothing to launch, same (empty) results as the reference
@@ -155,7 +202,8 @@ def trace(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arith=nat.A
         flags = [torch.zeros(full, dtype=torch.bool, device=y.device) for _ in range(2)]
         flags[0] = ~flags[0]
         return (*outs, *flags)
-    return _TraceSkew.apply(x, y, z, cx, cy, c, t, mu, mask, bool(allow_backward_rays), int(arith))
+    return _TraceSkew.apply(x, y, z, cx, cy, c, t, mu, mask, bool(allow_backward_rays), int(arith),
+                            k, a, sd)
 
 
 class _RmsFromRays(torch.autograd.Function):
@@ -221,7 +269,8 @@ def reduce_moments(moments, group=None):
 def _accumulate(lay, allow_backward_rays, arith, want_grad, p_begin, p_end):
     lib = nat.load()
     dev = lay.device
-    n_acc = lib.tl_spot_moment_count(lay.S, int(want_grad))
+    count = lib.tl_spot_moment_count_general if lay.general else lib.tl_spot_moment_count
+    n_acc = count(lay.S, int(want_grad))
     moments = torch.empty((lay.B, lay.F, lay.W, n_acc), dtype=torch.float64, device=dev)
     ref_y = torch.empty((lay.B, lay.F), dtype=torch.float32, device=dev)
     pb = lay.problem(allow_backward_rays, arith, p_begin, p_end)
@@ -236,9 +285,9 @@ def _accumulate(lay, allow_backward_rays, arith, want_grad, p_begin, p_end):
 
 
 def spot_moments(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arith=nat.ARITH_GUARDED,
-                 want_grad=True, shard=(0, 1)):
+                 want_grad=True, shard=(0, 1), k=None, a=None, sd=None):
     """Raw additive sums of one pupil slice (no autograd): (moments [B,F,W,n], ref_y [B,F])."""
-    lay = _Layout(x, y, z, cx, cy, c, t, mu, mask)
+    lay = _Layout(x, y, z, cx, cy, c, t, mu, mask, k, a, sd)
     p_begin, p_end = pupil_slice(lay.P, *shard)
     with torch.cuda.device(lay.device):
         return _accumulate(lay, allow_backward_rays, arith, want_grad, p_begin, p_end)
@@ -246,15 +295,21 @@ def spot_moments(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arit
 
 class _SpotRms(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays, arith, shard, group):
+    def forward(ctx, x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays, arith, shard, group,
+                k, a, sd):
         if any(ctx.needs_input_grad[i] for i in (0, 1, 3, 4)):
-            raise ValueError('the fused spot pass differentiates w.r.t. z, c, t and mu only; '
+            raise ValueError('the fused spot pass differentiates w.r.t. z, c, t, mu (and k, a) only; '
                              'use trace() + spot_rms_from_rays() for gradients of x, y, cx, cy')
-        lay = _Layout(x, y, z, cx, cy, c, t, mu, mask)
+        if ctx.needs_input_grad[15]:
+            raise ValueError('the clear semi-diameter sd is not differentiable')
+        lay = _Layout(x, y, z, cx, cy, c, t, mu, mask, k, a, sd)
         if z.numel() != z.shape[0]:
             raise ValueError('the fused spot pass needs a per-lens pupil position z of shape [B,1,1,1]')
-        want_grad = any(ctx.needs_input_grad[i] for i in (2, 5, 6, 7))
-        limit = nat.MAX_SURFACES_SPOT if want_grad else nat.MAX_SURFACES_FWD
+        want_grad = any(ctx.needs_input_grad[i] for i in (2, 5, 6, 7, 13, 14))
+        if lay.general:
+            limit = nat.MAX_SURFACES_GEN
+        else:
+            limit = nat.MAX_SURFACES_SPOT if want_grad else nat.MAX_SURFACES_FWD
         if lay.S > limit:
             raise ValueError(f'the fused spot pass supports at most {limit} surfaces '
                              f'({"with" if want_grad else "without"} gradients)')
@@ -271,31 +326,41 @@ class _SpotRms(torch.autograd.Function):
                 reduce_moments(moments, group)
             rms = torch.empty((lay.B,), dtype=torch.float32, device=dev)
             rms_field = torch.empty((lay.B, lay.F), dtype=torch.float32, device=dev)
+            saved = []
             if want_grad:
                 gc = torch.empty((lay.B, lay.S), dtype=torch.float32, device=dev)
                 gt = torch.empty_like(gc)
                 gmu = torch.empty((lay.B, lay.W, lay.S), dtype=torch.float32, device=dev)
                 gz = torch.empty((lay.B,), dtype=torch.float32, device=dev)
+                saved = [gc, gt, gmu, gz]
+                extra = [None, None]
+                if lay.general:
+                    gk = torch.empty_like(gc)
+                    ga = torch.empty((lay.B, lay.S, nat.N_ASPHERE_TERMS), dtype=torch.float32, device=dev)
+                    saved += [gk, ga]
+                    extra = [gk.data_ptr(), ga.data_ptr()]
                 out = nat.TlSpotOut(rms.data_ptr(), rms_field.data_ptr(), gc.data_ptr(), gt.data_ptr(),
-                                    gmu.data_ptr(), gz.data_ptr())
+                                    gmu.data_ptr(), gz.data_ptr(), *extra)
             else:
-                out = nat.TlSpotOut(rms.data_ptr(), rms_field.data_ptr(), None, None, None, None)
+                out = nat.TlSpotOut(rms.data_ptr(), rms_field.data_ptr(), None, None, None, None, None, None)
             nat.check(lib.tl_spot_finalize(moments.data_ptr(), ref_y.data_ptr(), lay.B, lay.F, lay.W,
                                            lay.S, lay.P, int(want_grad), ctypes.byref(out), stream),
                       'tl_spot_finalize')
         if want_grad:
-            ctx.save_for_backward(gc, gt, gmu, gz)
-        ctx.meta = (lay.B, lay.W, lay.S, z.shape, c.shape, t.shape, mu.shape)
+            ctx.save_for_backward(*saved)
+        ctx.meta = (lay.B, lay.W, lay.S, z.shape, c.shape, t.shape, mu.shape,
+                    None if k is None else k.shape, None if a is None else a.shape)
         ctx.mark_non_differentiable(rms_field)
         return rms, rms_field
 
     @staticmethod
     def backward(ctx, grad_rms, _grad_field):
-        gc, gt, gmu, gz = ctx.saved_tensors
-        B, W, S, z_shape, c_shape, t_shape, mu_shape = ctx.meta
+        saved = ctx.saved_tensors
+        gc, gt, gmu, gz = saved[:4]
+        B, W, S, z_shape, c_shape, t_shape, mu_shape, k_shape, a_shape = ctx.meta
         need = ctx.needs_input_grad
         g = grad_rms.to(torch.float32).reshape(B)
-        out = [None] * 13
+        out = [None] * 16
         if need[2]:
             out[2] = (gz * g).reshape(B, 1, 1, 1).sum_to_size(z_shape)
         if need[5]:
@@ -304,11 +369,15 @@ class _SpotRms(torch.autograd.Function):
             out[6] = (gt * g[:, None]).reshape(B, 1, 1, 1, S).sum_to_size(t_shape)
         if need[7]:
             out[7] = (gmu * g[:, None, None]).reshape(B, 1, 1, W, S).sum_to_size(mu_shape)
+        if need[13] and len(saved) > 4:
+            out[13] = (saved[4] * g[:, None]).reshape(B, 1, 1, 1, S).sum_to_size(k_shape)
+        if need[14] and len(saved) > 4:
+            out[14] = (saved[5] * g[:, None, None]).reshape(B, 1, 1, 1, S, -1).sum_to_size(a_shape)
         return tuple(out)
 
 
 def spot_rms(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arith=nat.ARITH_GUARDED,
-             shard=(0, 1), group=None):
+             shard=(0, 1), group=None, k=None, a=None, sd=None):
     """Fused ``trace_skew`` -> ``compute_rms2d`` (and, when any of z, c, t, mu
     requires grad, its backward) in one pass over the rays.
 
@@ -317,7 +386,7 @@ def spot_rms(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arith=na
     (rms [B], rms_field [B,F]) and, after ``.backward()``, the same gradients.
     """
     return _SpotRms.apply(x, y, z, cx, cy, c, t, mu, mask, bool(allow_backward_rays), int(arith),
-                          (int(shard[0]), int(shard[1])), group)
+                          (int(shard[0]), int(shard[1])), group, k, a, sd)
 
 
 # ---------------------------------------------------------------------------

@@ -210,7 +210,7 @@ def compute_magnification(lens):
 # The hot path
 # ---------------------------------------------------------------------------
 def trace_skew(x, y, z, cx, cy, c, t, mu, mask, aggregate=False, allow_backward_rays=True,
-               arith=None):
+               arith=None, k=None, a=None, sd=None):
     """Trace rays from the entrance pupil to the image plane (rtl:594-675).
 
     Inputs broadcast to [B,F,P,W] (c, t, mask: [B,1,1,1,S]; mu: [B,1,1,W,S]).
@@ -218,12 +218,18 @@ def trace_skew(x, y, z, cx, cy, c, t, mu, mask, aggregate=False, allow_backward_
     [B,F,P,W].  Differentiable w.r.t. x, y, z, cx, cy, c, t and mu.  ``arith``
     selects the arithmetic policy (default: guarded fast path; ``'exact'`` =
     bit-identical to the reference's fp32 evaluation order).
+
+    Extension (no reference behaviour): ``k`` [B,1,1,1,S] conic constants, ``a``
+    [B,1,1,1,S,7] even-asphere coefficients a4..a16, ``sd`` [B,1,1,1,S] clear
+    semi-diameters.  With any of them the surfaces are intersected by Newton
+    iteration, rays outside ``sd`` fail, and a 7th output, the optical path length
+    [B,F,P,W], is returned; this variant is forward-only (see RayTracer.spot_rms).
     """
     if aggregate:
         raise NotImplementedError(
             'aggregate=True (per-surface penalty stacks, rtl:641-657) is not part of the CUDA '
             'hot path yet')
-    return ops.trace(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays, _arith_code(arith))
+    return ops.trace(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays, _arith_code(arith), k, a, sd)
 
 
 def compute_rms2d(x, y, ray_ok):
@@ -336,10 +342,20 @@ class RayTracer:
         vig_x = self.vig_fn(fields, specs.vig_x)
         return apply_vignetting(xp_rel, vig_x, vig_x), apply_vignetting(yp_rel, vig_up, vig_down)
 
+    @staticmethod
+    def _extension_tables(lens):
+        """k / a / sd of a lens as [B,1,1,1,S(,7)] views (None where the lens has none)."""
+        def view(v, tail=()):
+            return None if v is None else v.reshape(v.shape[0], 1, 1, 1, v.shape[1], *tail)
+        a = getattr(lens, 'a', None)
+        return dict(k=view(getattr(lens, 'k', None)), a=view(a, (a.shape[-1],)) if a is not None else None,
+                    sd=view(getattr(lens, 'sd', None)))
+
     def trace_rays(self, specs, lens, use_vig=True, aggregate=False, xy=None, up_to_stop=False):
         """Trace the configured ray set; returns what :func:`trace_skew` returns."""
         args = self._ray_set(specs, lens, use_vig, xy, up_to_stop)
-        return trace_skew(*args, aggregate, self.allow_backward_rays, arith=self.arith)
+        return trace_skew(*args, aggregate, self.allow_backward_rays, arith=self.arith,
+                          **self._extension_tables(lens))
 
     def spot_rms(self, specs, lens, use_vig=True, shard=(0, 1), group=None, staged=True):
         """RMS spot size of every lens -- ``compute_rms2d(*trace_rays(...))`` fused
@@ -352,7 +368,9 @@ class RayTracer:
         vignetting function, no ray aiming and a deterministic pupil sampler, otherwise the
         torch front end of :meth:`trace_rays` feeds the fused pass."""
         plain = (self.vig_fn is None or not use_vig) and self.n_ray_aiming_iter == 0
-        if staged and plain and self.mode != 'skew_random' and lens.c.shape[1] <= 64:
+        ext = self._extension_tables(lens)
+        general = any(v is not None for v in ext.values())
+        if staged and plain and not general and self.mode != 'skew_random' and lens.c.shape[1] <= 64:
             key = ('tables', id(lens.structure))
             if key not in self._cache:
                 self._cache[key] = ops.LensTables(lens.structure, self.rel_fields, self.wavelengths,
@@ -362,7 +380,7 @@ class RayTracer:
                                      y_rel, self._cache[key], self.allow_backward_rays,
                                      _arith_code(self.arith), shard, group)
         args = self._ray_set(specs, lens, use_vig)
-        return ops.spot_rms(*args, self.allow_backward_rays, _arith_code(self.arith), shard, group)
+        return ops.spot_rms(*args, self.allow_backward_rays, _arith_code(self.arith), shard, group, **ext)
 
     # -- ray aiming (rtl:129-208) ---------------------------------------------
     def ray_aiming(self, specs, lens, use_vig):
