@@ -118,3 +118,51 @@ def test_general_kernels_reduce_to_the_spherical_ones():
     out_g = rt.trace_skew(*[a_.detach() for a_ in args], k=zeros)
     assert torch.equal(out_s[4], out_g[4]) and torch.equal(out_s[5], out_g[5])
     assert float((out_s[1] - out_g[1]).abs().max()) <= 1e-5 * float(out_s[1].abs().max())
+
+
+def test_config3_lens_at_3m_rays_against_the_oracle_on_device():
+    """The synthetic 12-surface asphere lens (BASELINE config 3 shape) at 3.1 M rays: masks of the
+    exact policy identical to the extension oracle evaluated by torch on the same GPU, fused RMS and
+    its gradients within tolerance, >= 99 % of the rays traced."""
+    from torchoptics_b200 import prescriptions
+    # masks on the f/4 variant (0.3 % of the rays fail or are flagged) ...
+    specs4, lens4 = prescriptions.asphere_12(DEV, f_number=4.0)
+    tracer4 = rt.RayTracer(mode='circular', n_rays=(128, 128), rel_fields=tuple(np.linspace(0, 1, 16).tolist()),
+                           wavelengths=('C', 'd', 'F'), default_device=DEV)
+    args4 = tracer4._ray_set(specs4, lens4)
+    ext4 = tracer4._extension_tables(lens4)
+    ref4 = gen.trace(*args4, **ext4)
+    assert 0.99 <= float(ref4[4].float().mean()) < 1.0
+    for policy in ('exact', 'guarded'):
+        out4 = rt.trace_skew(*args4, arith=policy, **ext4)
+        assert torch.equal(out4[4], ref4[4]) and torch.equal(out4[5], ref4[5]), policy
+    # ... values and gradients on the default f/5 lens, where every ray traces
+    specs, lens = prescriptions.asphere_12(DEV)
+    for name in ('c', 't', 'k', 'a'):
+        getattr(lens, name).requires_grad_(True)
+    tracer = rt.RayTracer(mode='circular', n_rays=(256, 256), rel_fields=tuple(np.linspace(0, 1, 16).tolist()),
+                          wavelengths=('C', 'd', 'F'), default_device=DEV)
+    rms, _ = tracer.spot_rms(specs, lens)
+    grads = torch.autograd.grad(rms[0], [lens.c, lens.t, lens.k, lens.a])
+    args = tracer._ray_set(specs, lens)
+    ext = tracer._extension_tables(lens)
+    ref = gen.trace(*args, **ext)
+    assert float(ref[4].float().mean()) >= 0.99
+    out = rt.trace_skew(*[a_.detach() for a_ in args], arith='exact', **{k: v.detach() for k, v in ext.items() if v is not None})
+    assert torch.equal(out[4], ref[4]) and torch.equal(out[5], ref[5])
+    # truth for the values: the same oracle in fp64 on the device
+    dbl = [a_.detach().double() if a_.is_floating_point() else a_ for a_ in args]
+    leaves = {n_: getattr(lens, n_).detach().double().requires_grad_(True) for n_ in ('c', 't', 'k', 'a')}
+    dbl[5] = leaves['c'].reshape(1, 1, 1, 1, -1)
+    dbl[6] = leaves['t'].reshape(1, 1, 1, 1, -1)
+    ref64 = gen.trace(*dbl, k=leaves['k'].reshape(1, 1, 1, 1, -1), a=leaves['a'].reshape(1, 1, 1, 1, 12, 7))
+    assert torch.equal(ref64[4], ref[4])
+    ref_rms = sph.spot_rms_all_lenses(ref64[1], ref64[4])[0]
+    assert abs(rms[0].item() - ref_rms.item()) <= 2e-5 * ref_rms.item()
+    ref_grads = torch.autograd.grad(ref_rms, [leaves[n_] for n_ in ('c', 't', 'k', 'a')])
+    for name, g, r in zip(('c', 't', 'k'), grads, ref_grads):
+        err = _rel(g.cpu().numpy(), r.cpu().numpy())
+        assert err <= 2e-4, (name, err)
+    for i in range(7):
+        err = _rel(grads[3][..., i].cpu().numpy(), ref_grads[3][..., i].cpu().numpy())
+        assert err <= 2e-4, ('a', i, err)

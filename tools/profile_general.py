@@ -1,0 +1,35 @@
+"""Timing of the general-surface fused spot pass on the config-3 lens (12 even-asphere surfaces).
+python tools/profile_general.py [n_side]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from torchoptics_b200 import RayTracer, ops, prescriptions   # noqa: E402
+
+side = int(sys.argv[1]) if len(sys.argv) > 1 else 296
+dev = 'cuda:0'
+specs, lens = prescriptions.asphere_12(dev)
+tracer = RayTracer(mode='circular', n_rays=(side, side), rel_fields=tuple(np.linspace(0, 1, 16).tolist()),
+                   wavelengths=('C', 'd', 'F'), default_device=dev)
+args = [a.detach() for a in tracer._ray_set(specs, lens)]
+ext = {k: v.detach() for k, v in tracer._extension_tables(lens).items() if v is not None}
+events = 16 * 3 * side * side * 12
+for want_grad in (True, False):
+    for _ in range(3):
+        m, _ = ops.spot_moments(*args, want_grad=want_grad, **ext)
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        m, _ = ops.spot_moments(*args, want_grad=want_grad, **ext)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flops = 511 if want_grad else 261      # provisional asphere flop model, BASELINE.md section 3
+    print(f'general spot pass want_grad={want_grad}: {ms:.4f} ms -> {events / ms / 1e6:.1f} G events/s '
+          f'({events * flops / ms / 1e9 / 74.45 * 100:.1f}% of 74.45 TFLOP/s at {flops} flop/event), '
+          f'ok fraction {float(m[..., -1].sum()) / (16 * 3 * side * side):.4f}')

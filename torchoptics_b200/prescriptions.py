@@ -59,3 +59,40 @@ DOUBLE_GAUSS = {
 
 def double_gauss(device='cuda'):
     return from_dict(DOUBLE_GAUSS, device)
+
+
+def asphere_12(device='cuda', seed=0, amplitude=0.03, f_number=5.0):
+    """Synthetic 12-surface even-asphere lens for BASELINE.json config 3:
+    six air-spaced elements ('GAGAGAGAGAGA', stop at the first surface) obtained from the
+    Double-Gauss by splitting its two cemented interfaces with 0.1 mm air gaps and dropping the
+    stop surface, then given random conic constants in [-0.6, 0.6] and coefficients a4..a16
+    sized so that each polynomial term contributes at most `amplitude`/7 of the base sag at the
+    marginal height.  8 deg half field; at the default f/5 every ray of a 16-field x 3-wavelength
+    x 160^2 set traces (extension oracle), at f/4 99.7 % do -- the remainder runs into the rim of
+    the asphere terms, and the few rays next to it dominate (and ill-condition) the gradients."""
+    gap = 0.1
+    r, th = _DG_RADII, _DG_THICK
+    nd, v = DOUBLE_GAUSS['nd'], DOUBLE_GAUSS['v']
+    rows = [(r[0], th[0], 0), (r[1], th[1], None), (r[2], th[2], 1), (r[3], 2 * gap, None),
+            (r[3], th[3], 2), (r[4], th[4] + th[5], None), (r[6], th[6], 3), (r[7], 2 * gap, None),
+            (r[7], th[7], 4), (r[8], th[8], None), (r[9], th[9], 5), (r[10], th[10], None)]
+    d = {'stop_idx': [0], 'sequence': [''.join('A' if g is None else 'G' for _, _, g in rows)],
+         'hfov': [8.0], 'f_number': [f_number],
+         'c': [0.0 if np.isinf(rr) else 1.0 / (0.5 * rr) for rr, _, _ in rows],
+         't': [0.5 * tt for _, tt, _ in rows],
+         'nd': [nd[g] for _, _, g in rows if g is not None],
+         'v': [v[g] for _, _, g in rows if g is not None]}
+    specs, lens = from_dict(d, device)
+    rng = np.random.default_rng(seed)
+    n_surf = len(rows)
+    k = rng.uniform(-0.6, 0.6, n_surf)
+    a = np.zeros((n_surf, 7))
+    height = 7.0
+    for s in range(n_surf):
+        base = abs(d['c'][s]) * height * height / 2
+        for i in range(7):
+            draw = rng.uniform(-1, 1)
+            a[s, i] = draw * amplitude * base / 7 / height ** (2 * (i + 2)) if base > 0 else 0.0
+    lens.k = torch.tensor(k, dtype=torch.float32, device=device).reshape(1, n_surf)
+    lens.a = torch.tensor(a, dtype=torch.float32, device=device).reshape(1, n_surf, 7)
+    return specs, lens
