@@ -166,3 +166,18 @@ def test_config3_lens_at_3m_rays_against_the_oracle_on_device():
     for i in range(7):
         err = _rel(grads[3][..., i].cpu().numpy(), ref_grads[3][..., i].cpu().numpy())
         assert err <= 2e-4, ('a', i, err)
+
+
+def test_adam_loop_reduces_the_spot_size():
+    """Config-5 shape in miniature: Adam on c, t, k, a of the asphere lens through the fused pass."""
+    from torchoptics_b200 import prescriptions
+    from torchoptics_b200.optimize import optimize_spot
+    specs, lens = prescriptions.asphere_12(DEV)
+    tracer = rt.RayTracer(mode='circular', n_rays=(48, 48), rel_fields=tuple(np.linspace(0, 1, 8).tolist()),
+                          wavelengths=('C', 'd', 'F'), default_device=DEV)
+    best, history = optimize_spot(tracer, specs, lens, steps=60, lr=5e-5)
+    assert np.isfinite(history).all()
+    assert min(history[-5:]) < 0.9 * history[0], (history[0], history[-5:])
+    rms, _ = tracer.spot_rms(specs, best)
+    assert abs(rms[0].item() - history[-1]) < 0.2 * history[0]
+    assert best.a.shape == lens.a.shape and not torch.equal(best.k, lens.k)

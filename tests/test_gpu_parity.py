@@ -320,3 +320,41 @@ def test_staging_kernels_equal_torch_front_end(lens_file):
     for name, a, b in zip(('c', 't', 'nd', 'v'), g_a, g_b):
         a, b = np.nan_to_num(a.cpu().numpy()), np.nan_to_num(b.cpu().numpy())
         assert _rel(a, b) <= 2e-5, (name, _rel(a, b))
+
+
+def test_thirty_surface_lens_forward_sweep_and_backward():
+    """BASELINE config-4 shape: 30 spherical surfaces.  Forward trace and the gradient-free spot
+    sweep (any surface count), and the split backward (S <= 32), against the oracle on device."""
+    specs, lens = prescriptions.wide_zoom_30(DEV)
+    assert lens.c.shape == (1, 30)
+    tracer = rt.RayTracer(mode='circular', n_rays=(96, 96), rel_fields=tuple(np.linspace(0, 1, 16).tolist()),
+                          wavelengths=('C', 'd', 'F'), default_device=DEV)
+    args = tracer._ray_set(specs, lens)
+    ref = oracle.trace(*args)
+    for policy in ('exact', 'guarded'):
+        out = rt.trace_skew(*args, arith=policy)
+        assert torch.equal(out[4], ref[4]) and torch.equal(out[5], torch.broadcast_to(ref[5], out[5].shape))
+        if policy == 'exact':
+            assert torch.equal(out[1], torch.broadcast_to(ref[1], out[1].shape))
+    assert bool(ref[4].all()) and 0 < int(ref[5].sum())
+    with torch.no_grad():
+        rms, field = tracer.spot_rms(specs, lens)            # forward-only fused sweep, S = 30
+    want = oracle.spot_rms_all_lenses(ref[1], ref[4])
+    assert abs(rms[0].item() - want[0].item()) <= RMS_TOL * want[0].item()
+    # two pupil shards of the sweep add up
+    m, _ = ops.spot_moments(*args, want_grad=False)
+    m0, _ = ops.spot_moments(*args, want_grad=False, shard=(0, 2))
+    m1, _ = ops.spot_moments(*args, want_grad=False, shard=(1, 2))
+    denom = m.abs().amax(dim=(0, 1, 2)).clamp_min(1e-30)       # per slot: sum(y-y0) itself can cancel to ~0
+    assert float(((m0 + m1 - m).abs().amax(dim=(0, 1, 2)) / denom).max()) <= 1e-5
+    # split path with gradients: trace + rms + autograd through the 32-surface backward kernel
+    leaves = [getattr(lens, k_).detach().clone().requires_grad_(True) for k_ in ('c', 't', 'nd', 'v')]
+    lens_g = lm.Lens(lens.structure, *leaves)
+    out = tracer.trace_rays(specs, lens_g)
+    rms_s = rt.compute_rms2d(out[0], out[1], out[4])
+    g = torch.autograd.grad(rms_s, leaves[:3])
+    ref_leaves = [l_.detach().clone().requires_grad_(True) for l_ in leaves]
+    ref_out = oracle.trace(*tracer._ray_set(specs, lm.Lens(lens.structure, *ref_leaves)))
+    ref_g = torch.autograd.grad(oracle.spot_rms_all_lenses(ref_out[1], ref_out[4])[0], ref_leaves[:3])
+    for name, a_, b_ in zip(('c', 't', 'nd'), g, ref_g):
+        assert _rel(a_.cpu().numpy(), b_.cpu().numpy()) <= 2e-4, (name, _rel(a_.cpu().numpy(), b_.cpu().numpy()))

@@ -96,3 +96,24 @@ def asphere_12(device='cuda', seed=0, amplitude=0.03, f_number=5.0):
     lens.k = torch.tensor(k, dtype=torch.float32, device=device).reshape(1, n_surf)
     lens.a = torch.tensor(a, dtype=torch.float32, device=device).reshape(1, n_surf, 7)
     return specs, lens
+
+
+def wide_zoom_30(device='cuda'):
+    """Synthetic 30-surface spherical lens for BASELINE.json config 4: a weak,
+    nearly afocal front group of 19 thin surfaces (alternating curvature +-0.005, BK7-like
+    singlets 2 mm thick, 1.5 mm air gaps) ahead of the Double-Gauss; stop inside the rear group.
+    12 deg half field, f/3.5: every ray traces, ~0.1 % are flagged backward in the front group."""
+    n_front, curv = 19, 0.005
+    c, t, seq, nd, v = [], [], '', [], []
+    for i in range(n_front):
+        glass = i % 2 == 0 and i < n_front - 1
+        c.append((curv if (i // 2) % 2 == 0 else -curv) * (1.0 if i % 2 == 0 else 0.9))
+        t.append(2.0 if glass else 1.5)
+        seq += 'G' if glass else 'A'
+        if glass:
+            nd.append(1.5168)
+            v.append(64.17)
+    d = DOUBLE_GAUSS
+    return from_dict({'stop_idx': [n_front + d['stop_idx'][0]], 'sequence': [seq + d['sequence'][0]],
+                      'hfov': [12.0], 'f_number': [3.5], 'c': c + d['c'], 't': t + d['t'],
+                      'nd': nd + d['nd'], 'v': v + d['v']}, device)
