@@ -952,7 +952,8 @@ typedef AdjKernelPtr AdjKernel;
 
 struct AdjVariant {
   AdjKernel kernel = nullptr;
-  int lanes = 2;          // rays per thread
+  int lanes = 2;          // rays per thread and group
+  int state_lanes = 2;    // lanes' worth of parked state per thread
 };
 
 // Rays per thread.  Four (two interleaved pairs) hides the latency of the
@@ -995,6 +996,7 @@ AdjVariant select_adj(int mode, int S) {
   } else {
     v.kernel = v.lanes == 4 ? adj_kernel_for<MODE_BWD, f4>(S) : adj_kernel_for<MODE_BWD, f2>(S);
   }
+  v.state_lanes = v.lanes;
   return v;
 }
 
@@ -1015,7 +1017,8 @@ int plan_adj(const TlProblem &pb, int mode, AdjPlan &pl) {
   pl.n_acc = n_acc_of(mode, pb.S);
   const int lanes = pl.variant.lanes;
   const size_t table = ((5 * (size_t)pb.S + 3) & ~(size_t)3) * sizeof(float);
-  const size_t state = mode != MODE_SPOT_EVAL ? (size_t)4 * pb.S * kTraceThreads * lanes * sizeof(float) : 0;
+  const size_t state = mode != MODE_SPOT_EVAL
+                           ? (size_t)4 * pb.S * kTraceThreads * pl.variant.state_lanes * sizeof(float) : 0;
   const size_t red = (size_t)(kTraceThreads / 32) * pl.n_acc * sizeof(float) + 16;
   pl.smem = table + (state > red ? state : red);
   if (pl.smem > 227 * 1024) return fail(TL_ERR_INVALID, "surface count needs too much shared memory%s");
