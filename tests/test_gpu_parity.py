@@ -358,3 +358,19 @@ def test_thirty_surface_lens_forward_sweep_and_backward():
     ref_g = torch.autograd.grad(oracle.spot_rms_all_lenses(ref_out[1], ref_out[4])[0], ref_leaves[:3])
     for name, a_, b_ in zip(('c', 't', 'nd'), g, ref_g):
         assert _rel(a_.cpu().numpy(), b_.cpu().numpy()) <= 2e-4, (name, _rel(a_.cpu().numpy(), b_.cpu().numpy()))
+
+
+def test_no_grad_sweep_with_grad_requiring_lens():
+    """Regression: under torch.no_grad() the fused pass must take its gradient-free variant
+    (any surface count) even when the lens tensors require grad."""
+    specs, lens = prescriptions.wide_zoom_30(DEV)
+    for k_ in ('c', 't', 'nd'):
+        getattr(lens, k_).requires_grad_(True)
+    tracer = rt.RayTracer(mode='circular', n_rays=(13, 11), rel_fields=(0., 0.6, 1.), wavelengths=('C', 'd', 'F'),
+                          default_device=DEV)
+    with torch.no_grad():
+        rms, _ = tracer.spot_rms(specs, lens)
+        rms_t, _ = tracer.spot_rms(specs, lens, staged=False)
+    assert not rms.requires_grad and abs(rms[0].item() - rms_t[0].item()) <= 1e-5 * rms_t[0].item()
+    with pytest.raises(ValueError):
+        tracer.spot_rms(specs, lens)          # with gradients: at most 16 surfaces in the fused pass

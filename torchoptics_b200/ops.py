@@ -296,7 +296,7 @@ def spot_moments(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arit
 class _SpotRms(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays, arith, shard, group,
-                k, a, sd):
+                k, a, sd, grad_on):
         if any(ctx.needs_input_grad[i] for i in (0, 1, 3, 4)):
             raise ValueError('the fused spot pass differentiates w.r.t. z, c, t, mu (and k, a) only; '
                              'use trace() + spot_rms_from_rays() for gradients of x, y, cx, cy')
@@ -305,7 +305,8 @@ class _SpotRms(torch.autograd.Function):
         lay = _Layout(x, y, z, cx, cy, c, t, mu, mask, k, a, sd)
         if z.numel() != z.shape[0]:
             raise ValueError('the fused spot pass needs a per-lens pupil position z of shape [B,1,1,1]')
-        want_grad = any(ctx.needs_input_grad[i] for i in (2, 5, 6, 7, 13, 14))
+        # (grad mode is sampled by the caller: inside forward() autograd is always off)
+        want_grad = grad_on and any(ctx.needs_input_grad[i] for i in (2, 5, 6, 7, 13, 14))
         if lay.general:
             limit = nat.MAX_SURFACES_GEN
         else:
@@ -360,7 +361,7 @@ class _SpotRms(torch.autograd.Function):
         B, W, S, z_shape, c_shape, t_shape, mu_shape, k_shape, a_shape = ctx.meta
         need = ctx.needs_input_grad
         g = grad_rms.to(torch.float32).reshape(B)
-        out = [None] * 16
+        out = [None] * 17
         if need[2]:
             out[2] = (gz * g).reshape(B, 1, 1, 1).sum_to_size(z_shape)
         if need[5]:
@@ -386,7 +387,7 @@ def spot_rms(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arith=na
     (rms [B], rms_field [B,F]) and, after ``.backward()``, the same gradients.
     """
     return _SpotRms.apply(x, y, z, cx, cy, c, t, mu, mask, bool(allow_backward_rays), int(arith),
-                          (int(shard[0]), int(shard[1])), group, k, a, sd)
+                          (int(shard[0]), int(shard[1])), group, k, a, sd, torch.is_grad_enabled())
 
 
 # ---------------------------------------------------------------------------
@@ -424,7 +425,7 @@ class _LensSpotRms(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, shard,
-                group):
+                group, grad_on):
         for name, val in (('c', c), ('t', t), ('nd', nd), ('v', v), ('hfov', hfov), ('epd', epd),
                           ('x', x_rel), ('y', y_rel)):
             nat.require_cuda(val, name)
@@ -437,7 +438,7 @@ class _LensSpotRms(torch.autograd.Function):
         B, L, F, W = tables.B, tables.L, tables.F, tables.W
         if tuple(c.shape) != (B, L):
             raise ValueError(f'lens tensors must be [B={B}, L={L}], got {tuple(c.shape)}')
-        want_grad = any(ctx.needs_input_grad[:4])
+        want_grad = grad_on and any(ctx.needs_input_grad[:4])
         if L > (nat.MAX_SURFACES_SPOT if want_grad else 64):
             raise ValueError('too many surfaces for the fused lens pass')
         P = x_rel.shape[2]
@@ -508,7 +509,7 @@ class _LensSpotRms(torch.autograd.Function):
         need = ctx.needs_input_grad
         grads = [(gc * g) if need[0] else None, (gt * g) if need[1] else None,
                  (gnd * g) if need[2] else None, (gv * g) if need[3] else None]
-        return (*grads, None, None, None, None, None, None, None, None, None)
+        return (*grads, None, None, None, None, None, None, None, None, None, None)
 
 
 def lens_spot_rms(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays=True,
@@ -516,4 +517,4 @@ def lens_spot_rms(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_r
     """(rms [B], rms_field [B,F]) of a lens batch given as padded [B,L] tensors, differentiable
     w.r.t. c, t, nd, v.  x_rel, y_rel: relative pupil coordinates [1,1,P,1]."""
     return _LensSpotRms.apply(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, bool(allow_backward_rays),
-                              int(arith), (int(shard[0]), int(shard[1])), group)
+                              int(arith), (int(shard[0]), int(shard[1])), group, torch.is_grad_enabled())
