@@ -38,6 +38,10 @@ N_FIELDS, N_SIDE = 16, 296
 WAVELENGTHS = ('C', 'd', 'F')
 CPU_SAMPLE_SIDE = 160                    # bounded CPU sample: 16 x 3 x 160^2 rays
 METRIC = 'ray-surface events/sec fwd+bwd'
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_trace_adj launch of this workload, from the
+# ncu --set full capture summarised in profiles/r1d_spot_grad_f4_geometric.txt (805 120 B + 0 B):
+# the pupil grid and the surface tables; the algorithmic HBM traffic of the fused pass is ~0.
+NCU_DRAM_BYTES_PER_LAUNCH = 805120
 
 
 def workload_name(n_theta):
@@ -150,7 +154,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-graph', action='store_true', help='time eager launches instead of a CUDA graph')
@@ -288,6 +292,46 @@ def main():
     torch.cuda.synchronize()
     kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in zip(k_starts, k_stops))
     events_rank = events_total // world
+
+    # ---- forward-only figures (the metric is quoted forward and forward+backward) ----
+    def timed_graph(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        run = fn
+        try:
+            side2 = torch.cuda.Stream()
+            side2.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side2):
+                fn()
+            torch.cuda.current_stream().wait_stream(side2)
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                fn()
+            run = gph.replay
+        except Exception as exc:
+            print(f'[bench] forward graph capture failed: {exc}', file=sys.stderr)
+        a = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+        b = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+        for i in range(reps):
+            flush.zero_()
+            a[i].record()
+            run()
+            b[i].record()
+        torch.cuda.synchronize()
+        return statistics.mean(x.elapsed_time(y) for x, y in zip(a, b))
+
+    note('forward-only timing')
+    fwd_reps = max(5, min(args.steps, 20))
+    sweep_ms = timed_graph(lambda: ops.spot_moments(*plain, want_grad=False, shard=shard), fwd_reps)
+    p_lo, p_hi = ops.pupil_slice(plain[0].shape[2], rank, world)
+    sliced = [plain[0][:, :, p_lo:p_hi], plain[1][:, :, p_lo:p_hi]] + plain[2:]
+    trace_ms = timed_graph(lambda: ops.trace(*sliced), fwd_reps)
+    forward = {'fused_sweep': {'value': events_rank * world / (sweep_ms * 1e-3), 'unit': 'events/s',
+                               'ms': sweep_ms, 'frac_fp32_peak': None,
+                               'what': 'trace + per-field spot moments, nothing materialised'},
+               'trace_skew': {'value': events_rank * world / (trace_ms * 1e-3), 'unit': 'events/s',
+                              'ms': trace_ms, 'what': 'tl_trace_fwd writing x, y, cx, cy, ok, backward (18 B/ray)'}}
     sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
     peaks = {}
     try:
@@ -298,8 +342,11 @@ def main():
     sm_max_mhz = peaks.get('sm_max_mhz') or clocks.summary().get('sm_max_mhz') or 1965.0
     peak_tflops = sms * 128 * 2 * sm_max_mhz * 1e6 / 1e12
     achieved = events_rank * (FLOPS_FWD + FLOPS_BWD) / (kernel_ms * 1e-3) / 1e12
+    for entry in forward.values():
+        entry['frac_fp32_peak'] = entry['value'] / world * FLOPS_FWD / 1e12 / peak_tflops
     roofline = {'bound': 'fp32_fma', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
-                'frac': achieved / peak_tflops, 'traffic': None,
+                'frac': achieved / peak_tflops,
+                'traffic': NCU_DRAM_BYTES_PER_LAUNCH if world == 1 else None,
                 'kernel': 'k_trace_adj<12,SPOT_GRAD,f4> (+k_chief_rays, k_reduce_rows: ~2% of the time)', 'kernel_ms': kernel_ms,
                 'flops_per_event': FLOPS_FWD + FLOPS_BWD,
                 'peak_source': f'{sms} SMs x 128 lanes x 2 flop x {sm_max_mhz:.0f} MHz '
@@ -381,7 +428,7 @@ def main():
                         'eager_api_value': events_total * eager_steps / eager_secs,
                         'eager_api_ms_per_step': eager_secs / eager_steps * 1e3},
                 'gpu_launches': launches_per_step * args.steps,
-                'roofline': roofline}
+                'roofline': roofline, 'forward': forward}
         if world == 1 and not args.no_cpu_baseline:
             base = cpu_arm(5, 1)
             line['cpu_baseline'] = {k: base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
