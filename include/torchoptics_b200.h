@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TL_ABI_VERSION 3
+#define TL_ABI_VERSION 4
 
 enum {
   TL_OK = 0,
@@ -108,6 +108,7 @@ typedef struct TlGrads {
   float *gmu;                  /* [B,W,S]                                          */
   float *gz_sum;               /* [B]   d/dz summed over the lens' rays            */
   float *gx, *gy, *gz, *gcx, *gcy;  /* per ray, optional                           */
+  float *gk, *ga;              /* [B,S], [B,S,7]: general-surface lenses (required there)  */
 } TlGrads;
 
 /* Results of the fused spot pass for each lens. */

@@ -181,3 +181,30 @@ def test_adam_loop_reduces_the_spot_size():
     rms, _ = tracer.spot_rms(specs, best)
     assert abs(rms[0].item() - history[-1]) < 0.2 * history[0]
     assert best.a.shape == lens.a.shape and not torch.equal(best.k, lens.k)
+
+
+@pytest.mark.parametrize('arith', ['guarded', 'exact'])
+def test_split_backward_general_surfaces(arith):
+    """trace_skew with extension tables is differentiable w.r.t. x, y, z, cx, cy, c, t, mu, k, a."""
+    p = _problem(n=300, clip=True)
+    wrt = ('x', 'y', 'z', 'cx', 'cy', 'c', 't', 'mu', 'k', 'a')
+    gen_ = torch.Generator().manual_seed(2)
+    o = {k: (v if k == 'mask' else v.double()) for k, v in p.items()}
+    for k in wrt:
+        o[k] = o[k].clone().requires_grad_(True)
+    ref_out = _call(gen.trace, o, k=o['k'], a=o['a'], sd=o['sd'])
+    seeds = [0.5 + torch.rand(ref_out[4].shape, generator=gen_) for _ in range(4)]
+    ref_loss = sum((s.double() * v).sum() for s, v in zip(seeds, ref_out[:4]))
+    ref = torch.autograd.grad(ref_loss, [o[k] for k in wrt])
+    q = _to(p, DEV, grad=wrt)
+    out = _call(rt.trace_skew, q, arith=arith, k=q['k'], a=q['a'], sd=q['sd'])
+    loss = sum((s.to(DEV) * v).sum() for s, v in zip(seeds, out[:4]))
+    got = torch.autograd.grad(loss, [q[k] for k in wrt])
+    for name, g, r in zip(wrt, got, ref):
+        assert g.shape == r.shape, name
+        g, r = g.cpu().numpy(), r.numpy()
+        if name == 'a':
+            for i in range(7):
+                assert _rel(g[..., i], r[..., i]) <= 2e-4, (name, i, _rel(g[..., i], r[..., i]))
+        else:
+            assert _rel(g, r) <= 2e-4, (name, _rel(g, r))

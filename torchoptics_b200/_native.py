@@ -51,7 +51,8 @@ class TlSeeds(ctypes.Structure):
 
 
 class TlGrads(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_void_p) for n in ('gc', 'gt', 'gmu', 'gz_sum', 'gx', 'gy', 'gz', 'gcx', 'gcy')]
+    _fields_ = [(n, ctypes.c_void_p) for n in ('gc', 'gt', 'gmu', 'gz_sum', 'gx', 'gy', 'gz', 'gcx', 'gcy',
+                                               'gk', 'ga')]
 
 
 class TlLens(ctypes.Structure):
@@ -108,7 +109,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.tl_abi_version() != 3:
+    if lib.tl_abi_version() != 4:
         raise NativeLibraryError('libtorchoptics_b200.so: ABI version mismatch, rebuild it')
     _lib = lib
     return lib

@@ -523,8 +523,8 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
 #pragma unroll
         for (int l = 0; l < N; ++l) {
           if (!has[l]) continue;
-          if (args.grads.gx) args.grads.gx[o[l]] = lane_get(a.x, l);
-          if (args.grads.gy) args.grads.gy[o[l]] = lane_get(a.y, l);
+          if (args.grads.gx) args.grads.gx[o[l]] = lane_get(a.x, l) * xy_scale;
+          if (args.grads.gy) args.grads.gy[o[l]] = lane_get(a.y, l) * xy_scale;
           if (args.grads.gz) args.grads.gz[o[l]] = lane_get(a.z, l);
           if (args.grads.gcx) args.grads.gcx[o[l]] = lane_get(a.cx, l);
           if (args.grads.gcy) args.grads.gcy[o[l]] = lane_get(a.cy, l);
@@ -1065,13 +1065,14 @@ int reduce_rows(const AdjPlan &pl, const double *partial, double *rows_out, int 
   return TL_OK;
 }
 
-int plan_gen(const TlProblem &pb, int want_grad, GenPlan &pl) {
+int plan_gen(const TlProblem &pb, int want_grad, GenPlan &pl, bool seeded = false) {
   DeviceInfo info;
   int rc = device_info(info);
   if (rc) return rc;
   pl.lanes = want_grad ? 2 : 4;
-  pl.kernel = want_grad ? (AdjKernelPtr)k_trace_gen<MODE_SPOT_GRAD, f2>
-                        : (AdjKernelPtr)k_trace_gen<MODE_SPOT_EVAL, f4>;
+  pl.kernel = seeded ? (AdjKernelPtr)k_trace_gen<MODE_BWD, f2>
+              : want_grad ? (AdjKernelPtr)k_trace_gen<MODE_SPOT_GRAD, f2>
+                          : (AdjKernelPtr)k_trace_gen<MODE_SPOT_EVAL, f4>;
   pl.n_acc = n_acc_gen(pb.S, want_grad);
   const size_t table = ((14 * (size_t)pb.S + 2 + 3) & ~(size_t)3) * sizeof(float);
   const size_t rows = want_grad ? (size_t)(kTraceThreads / 32) * pb.S * kGenRow * sizeof(float) : 0;
@@ -1134,7 +1135,15 @@ int tl_trace_fwd(const TlProblem *pb, const TlTraceOut *out, void *stream_) {
 }
 
 size_t tl_trace_bwd_workspace(const TlProblem *pb) {
-  if (validate(pb, TL_MAX_SURFACES_BWD) || is_general(*pb)) return 0;
+  if (validate(pb, TL_MAX_SURFACES_BWD)) return 0;
+  if (is_general(*pb)) {
+    TlProblem full = *pb;
+    full.p_begin = 0;
+    full.p_end = pb->P;
+    GenPlan gp;
+    if (plan_gen(full, 1, gp, true)) return 0;
+    return gp.partial_bytes + align8((size_t)pb->B * pb->F * pb->W * gp.n_acc * sizeof(double));
+  }
   TlProblem full = *pb;
   full.p_begin = 0;
   full.p_end = pb->P;
@@ -1149,9 +1158,44 @@ int tl_trace_bwd(const TlProblem *pb_, const TlSeeds *seeds, const TlGrads *grad
   if (rc) return rc;
   if (!seeds || !grads || !grads->gc || !grads->gt || !grads->gmu || !grads->gz_sum)
     return fail(TL_ERR_INVALID, "NULL seeds/grads%s");
-  if (is_general(*pb_))
-    return fail(TL_ERR_INVALID, "tl_trace_bwd: general-surface lenses are differentiated by the fused "
-                                "spot pass only (tl_spot_accumulate)%s");
+  if (is_general(*pb_)) {
+    if (!grads->gk || !grads->ga) return fail(TL_ERR_INVALID, "general-surface lens: gk and ga are required%s");
+    TlProblem pb = *pb_;
+    pb.p_begin = 0;
+    pb.p_end = pb.P;
+    GenPlan gp;
+    rc = plan_gen(pb, 1, gp, true);
+    if (rc) return rc;
+    const int rows = pb.B * pb.F * pb.W;
+    const size_t rows_bytes = align8((size_t)rows * gp.n_acc * sizeof(double));
+    if (!workspace || workspace_bytes < gp.partial_bytes + rows_bytes)
+      return fail(TL_ERR_WORKSPACE, "workspace too small for tl_trace_bwd%s");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    AdjArgs args;
+    memset(&args, 0, sizeof(args));
+    args.seeds = *seeds;
+    args.grads = *grads;
+    args.partial = (double *)workspace;
+    args.groups_per_row = gp.groups_per_row;
+    args.max_seg = gp.max_seg;
+    args.n_acc = gp.n_acc;
+    void *params[] = {(void *)&pb, (void *)&args};
+    TL_CHECK_CUDA(cudaLaunchKernel((const void *)gp.kernel, dim3(gp.n_blocks), dim3(kTraceThreads), params,
+                                   gp.smem, stream));
+    g_launches++;
+    double *rowbuf = (double *)((char *)workspace + gp.partial_bytes);
+    const int64_t n = (int64_t)rows * gp.n_acc;
+    k_reduce_rows<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(args.partial, rowbuf, rows,
+                                                                   gp.groups_per_row, gp.n_blocks,
+                                                                   gp.max_seg, gp.n_acc);
+    g_launches++;
+    const int outs = pb.B * (pb.S * (kGenPar - 1) + pb.W * pb.S + 1);
+    k_bwd_finalize_gen<<<(outs + 127) / 128, 128, 0, stream>>>(rowbuf, *grads, grads->gk, grads->ga, pb.B,
+                                                               pb.F, pb.W, pb.S);
+    g_launches++;
+    TL_CHECK_CUDA(cudaGetLastError());
+    return TL_OK;
+  }
   TlProblem pb = *pb_;
   pb.p_begin = 0;
   pb.p_end = pb.P;

@@ -259,16 +259,18 @@ __global__ void k_chief_rays_gen(TlProblem pb, float *ref_y) {
 }
 
 // --------------------------------------------------------------------------
-// fused spot pass, general surfaces.  MODE_SPOT_GRAD / MODE_SPOT_EVAL.
-// moments row layout: per surface 22 = [11 weighted | 11 plain] (c, k, a4..a16, t, mu),
-// then {weighted z, plain z, S1, S2, n_ok}: n_acc = 22 S + 5  (EVAL: 3).
+// fused spot pass (MODE_SPOT_GRAD / MODE_SPOT_EVAL) and split backward (MODE_BWD), general
+// surfaces.  Row layout: per surface 22 = [11 weighted | 11 plain] (c, k, a4..a16, t, mu), then
+// {weighted z, plain z, S1, S2, n_ok}: n_acc = 22 S + 5  (EVAL: 3).  MODE_BWD uses the same
+// layout with the caller's seeds as the only weights (the "plain" half stays zero).
 // --------------------------------------------------------------------------
 template <int MODE, class V>
 __global__ void __launch_bounds__(kTraceThreads)
 k_trace_gen(TlProblem pb, AdjArgs args) {
   extern __shared__ float smem[];
   constexpr int N = LaneCount<V>::value;
-  constexpr bool kAdjoint = MODE == MODE_SPOT_GRAD;
+  constexpr bool kAdjoint = MODE != MODE_SPOT_EVAL;
+  constexpr bool kSeeded = MODE == MODE_BWD;
   constexpr int kWarps = kTraceThreads / 32;
   const int S = pb.S;
   const int tid = threadIdx.x;
@@ -336,7 +338,7 @@ k_trace_gen(TlProblem pb, AdjArgs args) {
       b = r / (pb.W * pb.F);
       tab = load_gen_table(smem, pb, b, w);
       xy_scale = pb.xy_scale ? pb.xy_scale[b] : 1.0f;
-      y0 = args.ref_y[b * pb.F + f];
+      y0 = kSeeded ? 0.f : args.ref_y[b * pb.F + f];
       if (kAdjoint)
         for (int i = lane; i < S * kGenRow; i += 32) my_rows[i] = 0.f;
       acc_z = wac_z = m_s1 = m_s2 = m_n = 0.f;
@@ -344,12 +346,14 @@ k_trace_gen(TlProblem pb, AdjArgs args) {
     }
     const int p_base = pb.p_begin + j * (kTraceThreads * N) + tid;
     bool has[N];
+    int64_t o[N];
     V x, y, z, cx, cy;
 #pragma unroll
     for (int l = 0; l < N; ++l) {
       const int p = p_base + l * kTraceThreads;
       has[l] = p < pb.p_end;
       const int q = has[l] ? p : min(p_base, pb.p_end - 1);
+      o[l] = (((int64_t)b * pb.F + f) * pb.P + q) * pb.W + w;
       lane_set(x, l, __fmul_rn(pb.x.ptr[offset_of(pb.x, b, f, q, w)], xy_scale));
       lane_set(y, l, __fmul_rn(pb.y.ptr[offset_of(pb.y, b, f, q, w)], xy_scale));
       lane_set(z, l, pb.z.ptr[offset_of(pb.z, b, f, q, w)]);
@@ -380,6 +384,17 @@ k_trace_gen(TlProblem pb, AdjArgs args) {
       // the sweep is executed by whole warps (shuffles inside): a warp skips it only if none of
       // its lanes has a live ray
       const bool warp_live = __any_sync(0xffffffffu, any_live);
+      if (kSeeded && !warp_live) {
+#pragma unroll
+        for (int l = 0; l < N; ++l) {
+          if (!has[l]) continue;
+          if (args.grads.gx) args.grads.gx[o[l]] = 0.f;
+          if (args.grads.gy) args.grads.gy[o[l]] = 0.f;
+          if (args.grads.gz) args.grads.gz[o[l]] = 0.f;
+          if (args.grads.gcx) args.grads.gcx[o[l]] = 0.f;
+          if (args.grads.gcy) args.grads.gcy[o[l]] = 0.f;
+        }
+      }
       if (warp_live) {
         if (!any_live) {
           // this thread has no live ray: run the sweep on a harmless axial ray, seeded with 0
@@ -391,7 +406,20 @@ k_trace_gen(TlProblem pb, AdjArgs args) {
         } else if (!all_ok) {
           mirror_live_lane<V>(state, stride, S, tr.ok, tr.pre, z, tr.x, tr.y);
         }
-        Sweep<V> sw = sweep_begin(tr.pre, tr.x, tr.y, V(0.f), alive, V(0.f), V(0.f));
+        V sx(0.f), sy = alive, scx(0.f), scy(0.f);
+        if (kSeeded) {
+          sy = V(0.f);
+#pragma unroll
+          for (int l = 0; l < N; ++l) {
+            if (!live[l]) continue;
+            if (args.seeds.gx) lane_set(sx, l, args.seeds.gx[o[l]]);
+            if (args.seeds.gy) lane_set(sy, l, args.seeds.gy[o[l]]);
+            if (args.seeds.gcx) lane_set(scx, l, args.seeds.gcx[o[l]]);
+            if (args.seeds.gcy) lane_set(scy, l, args.seeds.gcy[o[l]]);
+          }
+          wgt = alive;                        // weights: the seeds already carry everything
+        }
+        Sweep<V> sw = sweep_begin(tr.pre, tr.x, tr.y, sx, sy, scx, scy);
 #pragma unroll 1
         for (int k = S - 1; k >= 0; --k) {
           const V *slot = state + (size_t)k * 4 * stride;
@@ -416,6 +444,18 @@ k_trace_gen(TlProblem pb, AdjArgs args) {
         sweep_end(sw, z, vx, vy, vz, vcx, vcy);
         acc_z += lane_sum(vz);
         wac_z = lane_dot(wgt, vz, wac_z);
+        if (kSeeded) {
+#pragma unroll
+          for (int l = 0; l < N; ++l) {
+            if (!has[l]) continue;
+            const float keep = live[l] ? 1.0f : 0.0f;    // dead rays have zero gradients
+            if (args.grads.gx) args.grads.gx[o[l]] = keep * lane_get(vx, l) * xy_scale;
+            if (args.grads.gy) args.grads.gy[o[l]] = keep * lane_get(vy, l) * xy_scale;
+            if (args.grads.gz) args.grads.gz[o[l]] = keep * lane_get(vz, l);
+            if (args.grads.gcx) args.grads.gcx[o[l]] = keep * lane_get(vcx, l);
+            if (args.grads.gcy) args.grads.gcy[o[l]] = keep * lane_get(vcy, l);
+          }
+        }
       }
     }
   }
@@ -495,5 +535,37 @@ __global__ void k_spot_finalize_gen(const double *mom_global, const float *ref_y
       }
       out.gz[b] = (float)s;
     }
+  }
+}
+
+// rows[b,f,w][22 S + 5] (weighted half) -> gc, gk, ga, gt [b,S(,7)], gmu [b,w,S], gz_sum [b]
+__global__ void k_bwd_finalize_gen(const double *rows, TlGrads g, float *gk, float *ga, int B, int F,
+                                   int W, int S) {
+  const int n_acc = kGenSlots * S + 5;
+  const int per_lens = S * (kGenPar - 1) + W * S + 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * per_lens) return;
+  const int b = i / per_lens;
+  int j = i % per_lens;
+  double s = 0.0;
+  if (j < S * (kGenPar - 1)) {
+    const int k = j / (kGenPar - 1), q = j % (kGenPar - 1);
+    for (int f = 0; f < F; ++f)
+      for (int w = 0; w < W; ++w) s += rows[(((int64_t)b * F + f) * W + w) * n_acc + k * kGenSlots + q];
+    const int64_t o = (int64_t)b * S + k;
+    if (q == 0) g.gc[o] = (float)s;
+    else if (q == 1) gk[o] = (float)s;
+    else if (q == kGenPar - 2) g.gt[o] = (float)s;
+    else ga[o * kAsphCoefs + (q - 2)] = (float)s;
+  } else if (j < S * (kGenPar - 1) + W * S) {
+    j -= S * (kGenPar - 1);
+    const int w = j / S, k = j % S;
+    for (int f = 0; f < F; ++f)
+      s += rows[(((int64_t)b * F + f) * W + w) * n_acc + k * kGenSlots + (kGenPar - 1)];
+    g.gmu[((int64_t)b * W + w) * S + k] = (float)s;
+  } else {
+    for (int f = 0; f < F; ++f)
+      for (int w = 0; w < W; ++w) s += rows[(((int64_t)b * F + f) * W + w) * n_acc + kGenSlots * S];
+    g.gz_sum[b] = (float)s;
   }
 }

@@ -101,6 +101,10 @@ class _TraceSkew(torch.autograd.Function):
                 sd=None):
         lay = _Layout(x, y, z, cx, cy, c, t, mu, mask, k, a, sd)
         if lay.general:
+            ctx.save_for_backward(x, y, z, cx, cy, c, t, mu, mask,
+                                  *(v for v in (k, a, sd) if v is not None))
+            ctx.flags = (allow_backward_rays, arith)
+            ctx.ext = (k is not None, a is not None, sd is not None)
             return _TraceSkew._forward_general(ctx, lay, allow_backward_rays, arith)
         if lay.S > nat.MAX_SURFACES_FWD:
             raise ValueError(f'at most {nat.MAX_SURFACES_FWD} surfaces are supported')
@@ -120,8 +124,8 @@ class _TraceSkew(torch.autograd.Function):
 
     @staticmethod
     def _forward_general(ctx, lay, allow_backward_rays, arith):
-        """Forward of a lens with extension surfaces: also returns the optical path length.
-        Not differentiable here -- gradients of such lenses come from the fused spot pass."""
+        """Forward of a lens with extension surfaces: also returns the optical path length
+        (itself not differentiable; x, y, cx, cy are)."""
         lib = nat.load()
         with torch.cuda.device(lay.device):
             outs = [torch.empty(lay.shape, dtype=torch.float32, device=lay.device) for _ in range(4)]
@@ -134,19 +138,24 @@ class _TraceSkew(torch.autograd.Function):
             nat.check(lib.tl_trace_fwd(ctypes.byref(pb), ctypes.byref(out), nat.stream_ptr(lay.device)),
                       'tl_trace_fwd')
         ctx.general = True
-        ctx.mark_non_differentiable(ok, backward)
+        ctx.mark_non_differentiable(ok, backward, opl)
         return (*outs, ok, backward, opl)
 
     @staticmethod
     def backward(ctx, gx, gy, gcx, gcy, _gok, _gbw, *_gopl):
+        saved = ctx.saved_tensors
+        k = a = sd = None
         if getattr(ctx, 'general', False):
-            raise NotImplementedError(
-                'trace_skew with conic / asphere / clipped surfaces is forward-only; gradients of such '
-                'lenses are produced by the fused spot pass (RayTracer.spot_rms / ops.spot_rms)')
-        x, y, z, cx, cy, c, t, mu, mask = ctx.saved_tensors
+            extra = list(saved[9:])
+            has_k, has_a, has_sd = ctx.ext
+            k = extra.pop(0) if has_k else None
+            a = extra.pop(0) if has_a else None
+            sd = extra.pop(0) if has_sd else None
+            saved = saved[:9]
+        x, y, z, cx, cy, c, t, mu, mask = saved
         allow_backward_rays, arith = ctx.flags
-        lay = _Layout(x, y, z, cx, cy, c, t, mu, mask)
-        if lay.S > nat.MAX_SURFACES_BWD:
+        lay = _Layout(x, y, z, cx, cy, c, t, mu, mask, k, a, sd)
+        if lay.S > (nat.MAX_SURFACES_GEN if lay.general else nat.MAX_SURFACES_BWD):
             raise ValueError(f'backward supports at most {nat.MAX_SURFACES_BWD} surfaces')
         lib = nat.load()
         dev = lay.device
@@ -165,8 +174,12 @@ class _TraceSkew(torch.autograd.Function):
                     per_ray[name] = torch.empty(lay.shape, dtype=torch.float32, device=dev)
             pb = lay.problem(allow_backward_rays, arith)
             sd = nat.TlSeeds(*[_ptr(s) for s in seeds])
+            gk = ga = None
+            if lay.general:
+                gk = torch.empty_like(gc)
+                ga = torch.empty((lay.B, lay.S, nat.N_ASPHERE_TERMS), dtype=torch.float32, device=dev)
             gr = nat.TlGrads(gc.data_ptr(), gt.data_ptr(), gmu.data_ptr(), gz_sum.data_ptr(),
-                             *[_ptr(per_ray.get(n)) for n in _GRAD_PER_RAY])
+                             *[_ptr(per_ray.get(n)) for n in _GRAD_PER_RAY], _ptr(gk), _ptr(ga))
             ws_bytes = lib.tl_trace_bwd_workspace(ctypes.byref(pb))
             if ws_bytes == 0:
                 nat.check(-1, 'tl_trace_bwd_workspace')
@@ -185,7 +198,12 @@ class _TraceSkew(torch.autograd.Function):
         grads.append(gc.reshape(lay.B, 1, 1, 1, lay.S).sum_to_size(c.shape) if need[5] else None)
         grads.append(gt.reshape(lay.B, 1, 1, 1, lay.S).sum_to_size(t.shape) if need[6] else None)
         grads.append(gmu.reshape(lay.B, 1, 1, lay.W, lay.S).sum_to_size(mu.shape) if need[7] else None)
-        return (*grads, None, None, None, None, None, None)
+        g_k = g_a = None
+        if lay.general and k is not None and need[11]:
+            g_k = gk.reshape(lay.B, 1, 1, 1, lay.S).sum_to_size(k.shape)
+        if lay.general and a is not None and need[12]:
+            g_a = ga.reshape(lay.B, 1, 1, 1, lay.S, -1).sum_to_size(a.shape)
+        return (*grads, None, None, None, g_k, g_a, None)
 
 
 def trace(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arith=nat.ARITH_GUARDED,

@@ -223,7 +223,7 @@ def trace_skew(x, y, z, cx, cy, c, t, mu, mask, aggregate=False, allow_backward_
     [B,1,1,1,S,7] even-asphere coefficients a4..a16, ``sd`` [B,1,1,1,S] clear
     semi-diameters.  With any of them the surfaces are intersected by Newton
     iteration, rays outside ``sd`` fail, and a 7th output, the optical path length
-    [B,F,P,W], is returned; this variant is forward-only (see RayTracer.spot_rms).
+    [B,F,P,W] (not differentiable), is returned; gradients also flow to ``k`` and ``a``.
     """
     if aggregate:
         raise NotImplementedError(
