@@ -393,10 +393,22 @@ def main():
             dist.all_reduce(secs, op=dist.ReduceOp.MAX)
         return float(secs.item())
 
+    def drop_in_step():
+        """The reference's own call sequence, unchanged: trace_rays -> compute_rms2d -> backward."""
+        dl = {k: v.to(dev, non_blocking=True) for k, v in host_lens.items()}
+        for k in ('c', 't', 'nd'):
+            dl[k].requires_grad_(True)
+        lens_i = lm.Lens(lens.structure, dl['c'], dl['t'], dl['nd'], dl['v'])
+        out = tracer.trace_rays(specs, lens_i)
+        rms = rt.compute_rms2d(out[0], out[1], out[4])
+        rms.backward()
+        return rms.item(), [dl[k].grad.cpu() for k in ('c', 't', 'nd')]
+
     e2e_secs = time_e2e(e2e_step, args.steps)
     e2e_value = events_total * args.steps / e2e_secs
     eager_steps = max(3, min(args.steps, 20))
     eager_secs = time_e2e(e2e_eager_step, eager_steps)
+    drop_in_secs = time_e2e(drop_in_step, eager_steps) if world == 1 else None
     if graphed is not None:
         h2d, d2h = graphed.h2d_bytes, graphed.d2h_bytes
     else:
@@ -426,7 +438,9 @@ def main():
                         'api': 'GraphedSpotStep (CUDA graph of the public RayTracer.spot_rms path)'
                                if graphed is not None else 'RayTracer.spot_rms (eager)',
                         'eager_api_value': events_total * eager_steps / eager_secs,
-                        'eager_api_ms_per_step': eager_secs / eager_steps * 1e3},
+                        'eager_api_ms_per_step': eager_secs / eager_steps * 1e3,
+                        'drop_in_api_value': (events_total * eager_steps / drop_in_secs) if drop_in_secs else None,
+                        'drop_in_api': 'trace_rays + compute_rms2d + backward (unfused, materialises [B,F,P,W])'},
                 'gpu_launches': launches_per_step * args.steps,
                 'roofline': roofline, 'forward': forward}
         if world == 1 and not args.no_cpu_baseline:
