@@ -290,12 +290,12 @@ TL_HD void fast_surface(Ray<T> &r, T c, T mu, T mu2, T t, T &min_cos2, T &travel
   r.x = ffma(dist, r.cx, r.x);
   r.y = ffma(dist, r.cy, r.y);
   r.z = r.z + travel;
-  const T qo = ffma(-mu2, T(1) - q, T(1));                              // cos^2 out
+  const T qo = ffma(mu2, q, T(1) - mu2);                                // cos^2 out = 1 - mu^2 (1 - q)
   const T co = qo * frsqrt(qo);
   const T gc = ffma(-mu, ci, co) * c;
   r.cx = ffma(-gc, r.x, mu * r.cx);
   r.cy = ffma(-gc, r.y, mu * r.cy);
-  const T w = T(1) - ffma(r.cy, r.cy, r.cx * r.cx);
+  const T w = ffma(-r.cy, r.cy, ffma(-r.cx, r.cx, T(1)));
   r.cz = w * frsqrt(w);
   min_cos2 = fmin2(min_cos2, fmin2(q, fmin2(qo, w)));
   r.z = r.z - t;
