@@ -197,6 +197,17 @@ def main():
     rays_total = N_FIELDS * len(WAVELENGTHS) * N_SIDE * n_theta
     events_total = rays_total * S
     shard = (rank, world)
+    # the one collective of the data path: our peer-memory exchange kernel (NVLink P2P stores,
+    # rank-ordered sum) unless TL_BENCH_COLLECTIVE=nccl asks for torch.distributed.all_reduce
+    exchange = None
+    collective = 'none (1 rank)'
+    if world > 1:
+        if os.environ.get('TL_BENCH_COLLECTIVE', 'peer') == 'nccl':
+            collective = 'nccl all_reduce (27 KB fp64) inside the CUDA graph'
+        else:
+            from torchoptics_b200.peer import PeerExchange
+            exchange = PeerExchange(capacity=1 << 16)
+            collective = 'k_peer_allreduce: one-shot all-reduce over NVLink peer memory (CUDA IPC windows), inside the CUDA graph'
 
     # ---- device-resident step: inputs already in HBM ------------------------
     ray_args = [a.detach() for a in tracer._ray_set(specs, lens)]
@@ -205,7 +216,7 @@ def main():
     leaves = [ray_args[i] for i in (2, 5, 6, 7)]
 
     def step():
-        rms, _ = ops.spot_rms(*ray_args, True, _native.ARITH_GUARDED, shard, None)
+        rms, _ = ops.spot_rms(*ray_args, True, _native.ARITH_GUARDED, shard, exchange)
         return rms, torch.autograd.grad(rms[0], leaves)
 
     note('first eager step')
@@ -361,7 +372,7 @@ def main():
     host_lens = {k: getattr(lens, k).detach().cpu() for k in ('c', 't', 'nd', 'v')}
     graphed = None
     try:
-        graphed = GraphedSpotStep(tracer, specs, lens, shard=shard)
+        graphed = GraphedSpotStep(tracer, specs, lens, shard=shard, group=exchange)
     except Exception as exc:
         print(f'[bench] GraphedSpotStep capture failed, e2e uses the eager API: {exc}', file=sys.stderr)
 
@@ -370,7 +381,7 @@ def main():
         for k in ('c', 't', 'nd'):
             dl[k].requires_grad_(True)
         lens_i = lm.Lens(lens.structure, dl['c'], dl['t'], dl['nd'], dl['v'])
-        rms, _ = tracer.spot_rms(specs, lens_i, shard=shard)
+        rms, _ = tracer.spot_rms(specs, lens_i, shard=shard, group=exchange)
         rms[0].backward()
         return rms[0].item(), [dl[k].grad.cpu() for k in ('c', 't', 'nd')]
 
@@ -428,7 +439,7 @@ def main():
                            'surfaces': S, 'fields': N_FIELDS, 'wavelengths': len(WAVELENGTHS),
                            'rays': rays_total, 'events_per_step': events_total,
                            'rays_per_gpu': rays_total // world,
-                           'parallelism': f'pupil-sharded dp{world}',
+                           'parallelism': f'pupil-sharded dp{world}', 'collective': collective,
                            'l2': 'flushed between timed steps (256 MiB write)',
                            'launch': 'cuda_graph' if graph is not None else 'eager',
                            'arith': 'guarded'},
@@ -453,6 +464,10 @@ def main():
         # forever: drop the graphs, meet at a barrier and leave without the destructor chain
         graph = graphed = k_graph = None
         barrier()
+        if exchange is not None:
+            status, epoch = exchange.status()
+            if status != 0:
+                print(f'[bench rank {rank}] peer exchange timed out (epoch {epoch})', file=sys.stderr)
         sys.stdout.flush()
         sys.stderr.flush()
         os._exit(0)

@@ -9,7 +9,7 @@
  * the legacy default stream).  All functions return 0 on success or a negative
  * TL_ERR_* code and never throw; tl_last_error() gives the message of the last
  * failure on the calling thread.  Nothing allocates, synchronises or copies to
- * the host.
+ * the host (exception: tl_peer_create / tl_peer_destroy own the peer-exchange window).
  *
  * Tensor convention (rtl:4-9): ray tensors are [B lenses, F fields, P pupil
  * points, W wavelengths]; prescriptions carry a trailing surface axis S.
@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TL_ABI_VERSION 4
+#define TL_ABI_VERSION 5
 
 enum {
   TL_OK = 0,
@@ -184,6 +184,27 @@ int tl_stage_fwd(const TlLens *lens, float *mu, float *z, float *cy, float *half
  * gc, gt, gnd, gv [B,L] (which the caller pre-fills, e.g. with the direct c / t gradients). */
 int tl_stage_bwd(const TlLens *lens, const float *gmu, const float *gz, float *gc, float *gt,
                  float *gnd, float *gv, void *stream);
+
+/* Peer-memory exchange: the one collective of the pupil-sharded spot pass (SUM all-reduce of the
+ * `moments` buffer of tl_spot_accumulate over the ranks of ONE node) as a single kernel that
+ * stores into every peer's window over NVLink / NVSwitch and sums in rank order (bit-identical
+ * result on every rank), instead of an NCCL call.  The reference is single-GPU (no counterpart).
+ *   tl_peer_create   allocates this rank's window (the one allocation this library makes: CUDA IPC
+ *                    needs a cudaMalloc base pointer) on the CURRENT device and writes its IPC
+ *                    handle (tl_peer_handle_bytes() bytes) to handle_out.
+ *   tl_peer_connect  takes the handles of all ranks (world x handle bytes, rank order; the caller
+ *                    exchanges them, e.g. with torch.distributed.all_gather) and maps the windows.
+ *   tl_peer_allreduce_f64  out[i] = sum over ranks of data[i], i < n <= capacity; every rank must
+ *                    call it the same number of times; graph-capturable (no per-call state on the
+ *                    host); data != out when world > 1.
+ *   tl_peer_status   (synchronising) status 0 = ok, 1 = a wait for a peer timed out (4 s). */
+typedef struct TlPeerComm TlPeerComm;
+size_t tl_peer_handle_bytes(void);
+int tl_peer_create(int32_t rank, int32_t world, int64_t capacity, TlPeerComm **comm, void *handle_out);
+int tl_peer_connect(TlPeerComm *comm, const void *all_handles);
+int tl_peer_allreduce_f64(TlPeerComm *comm, const double *data, double *out, int64_t n, void *stream);
+int tl_peer_status(TlPeerComm *comm, int32_t *status_out, uint32_t *epoch_out);
+int tl_peer_destroy(TlPeerComm *comm);
 
 /* Number of kernels this library has launched since it was loaded (bench.py's
  * gpu_launches counter). */

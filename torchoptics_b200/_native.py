@@ -90,6 +90,15 @@ EXPORTS = {
     'tl_stage_bwd': (ctypes.c_int, [ctypes.POINTER(TlLens)] + [ctypes.c_void_p] * 7),
     'tl_spot_finalize': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int32] * 4 +
                          [ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(TlSpotOut), ctypes.c_void_p]),
+    'tl_peer_handle_bytes': (ctypes.c_size_t, []),
+    'tl_peer_create': (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
+                                      ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
+    'tl_peer_connect': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    'tl_peer_allreduce_f64': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_int64, ctypes.c_void_p]),
+    'tl_peer_status': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32),
+                                      ctypes.POINTER(ctypes.c_uint32)]),
+    'tl_peer_destroy': (ctypes.c_int, [ctypes.c_void_p]),
 }
 
 _lib = None
@@ -109,7 +118,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.tl_abi_version() != 4:
+    if lib.tl_abi_version() != 5:
         raise NativeLibraryError('libtorchoptics_b200.so: ABI version mismatch, rebuild it')
     _lib = lib
     return lib

@@ -1412,3 +1412,5 @@ int tl_stage_bwd(const TlLens *lens, const float *gmu, const float *gz, float *g
 }
 
 }  // extern "C"
+
+#include "peer_exchange.cuh"

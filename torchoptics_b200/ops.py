@@ -279,7 +279,12 @@ def pupil_slice(n_pupil, rank, world):
 def reduce_moments(moments, group=None):
     """The one data-path collective of the sharded spot pass: per-(lens, field,
     wavelength) sums are additive over pupil slices -> SUM all-reduce (fp64,
-    a few KB; NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+    a few KB).  ``group`` is a :class:`~torchoptics_b200.peer.PeerExchange` (one kernel storing
+    into the peers' memory over NVLink, rank-ordered sum) or a torch process group / None
+    (``all_reduce``: NCCL on GPUs, gloo in the CPU tests).  Returns the reduced tensor."""
+    from .peer import PeerExchange
+    if isinstance(group, PeerExchange):
+        return group.all_reduce(moments)
     torch.distributed.all_reduce(moments, op=torch.distributed.ReduceOp.SUM, group=group)
     return moments
 
@@ -342,7 +347,7 @@ class _SpotRms(torch.autograd.Function):
             moments, ref_y = _accumulate(lay, allow_backward_rays, arith, want_grad, p_begin, p_end)
             stream = nat.stream_ptr(dev)
             if world > 1:
-                reduce_moments(moments, group)
+                moments = reduce_moments(moments, group)
             rms = torch.empty((lay.B,), dtype=torch.float32, device=dev)
             rms_field = torch.empty((lay.B, lay.F), dtype=torch.float32, device=dev)
             saved = []
@@ -496,7 +501,7 @@ class _LensSpotRms(torch.autograd.Function):
                                              ref_y.data_ptr(), ws.data_ptr(), ws_bytes, stream),
                       'tl_spot_accumulate')
             if world > 1:
-                reduce_moments(moments, group)
+                moments = reduce_moments(moments, group)
             rms = torch.empty((B,), dtype=torch.float32, device=dev)
             rms_field = torch.empty((B, F), dtype=torch.float32, device=dev)
             if want_grad:

@@ -1,0 +1,85 @@
+"""Peer-memory exchange of the pupil-sharded spot pass (``tl_peer_*`` of the C ABI).
+
+One process per GPU; ``torch.distributed`` is used ONCE, to hand every rank the CUDA IPC
+handles of the other ranks' windows.  After that the per-step SUM all-reduce of the moment
+sums is a single kernel that stores into the peers' memory over NVLink / NVSwitch and adds
+the contributions in rank order -- no NCCL call on the data path, graph-capturable, and
+bit-identical on every rank.
+
+    ex = PeerExchange(capacity=moments.numel())          # collective: every rank calls it
+    rms, _ = tracer.spot_rms(specs, lens, shard=(rank, world), group=ex)
+
+``ops.reduce_moments`` dispatches on the type of ``group``: a :class:`PeerExchange` uses
+the kernel, a ``ProcessGroup`` (or None) uses ``torch.distributed.all_reduce`` (NCCL on
+GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _native as nat
+
+
+class PeerExchange:
+    """A window on every rank of ``group`` (ranks must be GPUs of one node)."""
+
+    def __init__(self, capacity, group=None, device=None):
+        import torch.distributed as dist
+        lib = nat.load()
+        if dist.is_available() and dist.is_initialized():
+            self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        else:
+            self.rank, self.world = 0, 1
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        self.capacity = int(capacity)
+        self._comm = ctypes.c_void_p()
+        nbytes = lib.tl_peer_handle_bytes()
+        handle = ctypes.create_string_buffer(nbytes)
+        with torch.cuda.device(self.device):
+            nat.check(lib.tl_peer_create(self.rank, self.world, self.capacity, ctypes.byref(self._comm),
+                                         handle), 'tl_peer_create')
+            if self.world > 1:
+                mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(self.device)
+                everyone = [torch.empty_like(mine) for _ in range(self.world)]
+                dist.all_gather(everyone, mine, group=group)
+                blob = b''.join(bytes(h.cpu().numpy().tobytes()) for h in everyone)
+                nat.check(lib.tl_peer_connect(self._comm, blob), 'tl_peer_connect')
+                dist.barrier(group=group)        # every window is mapped before the first push
+        self._group = group
+
+    def all_reduce(self, data):
+        """Sum of ``data`` (float64, contiguous, CUDA) over the ranks; returns a new tensor."""
+        if data.dtype != torch.float64 or not data.is_contiguous():
+            raise ValueError('PeerExchange.all_reduce needs a contiguous float64 tensor')
+        nat.require_cuda(data, 'data')
+        if data.numel() > self.capacity:
+            raise ValueError(f'{data.numel()} values exceed the window capacity {self.capacity}')
+        out = torch.empty_like(data)
+        with torch.cuda.device(data.device):
+            nat.check(nat.load().tl_peer_allreduce_f64(self._comm, data.data_ptr(), out.data_ptr(),
+                                                       data.numel(), nat.stream_ptr(data.device)),
+                      'tl_peer_allreduce_f64')
+        return out
+
+    def status(self):
+        """(status, epoch): status 0 = ok, 1 = a peer did not show up within the spin limit.
+        Synchronises the device."""
+        st, ep = ctypes.c_int32(), ctypes.c_uint32()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            nat.check(nat.load().tl_peer_status(self._comm, ctypes.byref(st), ctypes.byref(ep)),
+                      'tl_peer_status')
+        return st.value, ep.value
+
+    def close(self):
+        """Collective: no rank may free its window while a peer can still write into it."""
+        if self._comm:
+            import torch.distributed as dist
+            with torch.cuda.device(self.device):
+                torch.cuda.synchronize()
+                if self.world > 1 and dist.is_initialized():
+                    dist.barrier(group=self._group)
+                nat.load().tl_peer_destroy(self._comm)
+            self._comm = ctypes.c_void_p()
