@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TL_ABI_VERSION 5
+#define TL_ABI_VERSION 6
 
 enum {
   TL_OK = 0,
@@ -92,12 +92,23 @@ typedef struct TlTraceOut {
   uint8_t *ok, *backward;      /* 0/1 bytes (torch.bool storage)                   */
   float *opl;                  /* optional: optical path length entrance -> image
                                   (general-surface lenses only; NULL = not wanted)  */
+  /* trace_skew(aggregate=True), rtl:641-657: the three penalty stacks, each a contiguous
+   * [S,B,F,P,W] array (surface-major; the reference returns them as S-long lists).  All three
+   * NULL = aggregate=False; spherical lenses only.
+   *   z_relu      = max(z, 0) of the ray behind surface k, in the next vertex frame
+   *   theta       = acos(clamp(cos theta))  / (pi/2), 1 for a ray that is not ok behind surface k
+   *   theta_prime = acos(clamp(cos theta')) / (pi/2), likewise                                   */
+  float *z_relu, *theta, *theta_prime;
 } TlTraceOut;
 
 /* Upstream gradients of the four differentiable outputs; contiguous [B,F,P,W]
  * or NULL (= zero). */
 typedef struct TlSeeds {
   const float *gx, *gy, *gcx, *gcy;
+  /* upstream gradients of the aggregate=True stacks, contiguous [S,B,F,P,W] or NULL (= zero).
+   * Where the reference's own gradient is NaN (it takes sqrt of a failed ray's negative cos^2
+   * before masking it, rtl:646-654) a failed ray contributes 0 here. */
+  const float *gz_relu, *gtheta, *gtheta_prime;
 } TlSeeds;
 
 /* Gradients produced by tl_trace_bwd.  Prescription gradients are summed over

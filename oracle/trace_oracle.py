@@ -56,6 +56,45 @@ def ieee_sqrt():
         _IEEE_SQRT = previous
 
 
+# rtl:646-654 computes sqrt(cos2) for every ray and only afterwards overwrites the failed rays'
+# angles with 1; a failed ray's cos2 can be negative, and the backward of that masked-out NaN
+# (0 / NaN) poisons every gradient of the penalty with NaN.  Inside
+# ``with finite_penalty_gradients():`` the oracle feeds cos2 = 1 to the failed rays instead: the
+# forward values and the gradients of the ok rays are unchanged, failed rays contribute 0.  This is
+# the behaviour the CUDA path implements (and the only one a test can compare against when rays
+# fail); without the switch the oracle is the reference verbatim, NaN included.
+_FINITE_PENALTY = False
+
+
+@contextlib.contextmanager
+def finite_penalty_gradients():
+    global _FINITE_PENALTY
+    previous, _FINITE_PENALTY = _FINITE_PENALTY, True
+    try:
+        yield
+    finally:
+        _FINITE_PENALTY = previous
+
+
+# rtl:645-647 clamps the cosines to +-(1 - 1e-7).  In the reference's fp32 run that bound is the
+# float32 nearest to 0.9999999, i.e. 1 - 2^-23 = 0.99999988; an fp64 run of the same code uses
+# 0.9999999.  Rays whose angle lies between the two bounds (4.47e-4 .. 4.88e-4 rad) are clamped
+# (zero gradient) by one and not by the other, and an unclamped ray there carries a 1 / sin(theta)
+# > 2000 gradient.  ``with fp32_clamp_bound():`` makes an fp64 run use the fp32 program's constant,
+# so that it is the high-precision evaluation of the fp32 program.
+_CLAMP_HI = None
+
+
+@contextlib.contextmanager
+def fp32_clamp_bound():
+    global _CLAMP_HI
+    previous, _CLAMP_HI = _CLAMP_HI, float(np.float32(1.0) - np.float32(1e-7))
+    try:
+        yield
+    finally:
+        _CLAMP_HI = previous
+
+
 def _sqrt(v):
     if _IEEE_SQRT and v.device.type == 'cpu' and not v.requires_grad:
         return torch.from_numpy(np.sqrt(v.numpy()))
@@ -154,8 +193,12 @@ def trace(x, y, z, cx, cy, c, t, mu, mask, aggregate: bool = False,
             z_pos = z.clone()
             z_pos[z_pos <= 0] = 0.
             tiny = 1e-7
-            ang_in = torch.acos(torch.clamp(_sqrt(cos2_inc), min=-1.0 + tiny, max=1.0 - tiny))
-            ang_out = torch.acos(torch.clamp(_sqrt(cos2_out), min=-1.0 + tiny, max=1.0 - tiny))
+            if _FINITE_PENALTY:
+                cos2_inc = torch.where(ray_ok, cos2_inc, torch.ones_like(cos2_inc))
+                cos2_out = torch.where(ray_ok, cos2_out, torch.ones_like(cos2_out))
+            hi = 1.0 - tiny if _CLAMP_HI is None else _CLAMP_HI
+            ang_in = torch.acos(torch.clamp(_sqrt(cos2_inc), min=-hi, max=hi))
+            ang_out = torch.acos(torch.clamp(_sqrt(cos2_out), min=-hi, max=hi))
             ang_in = ang_in / (1 / 2 * math.pi)
             ang_out = ang_out / (1 / 2 * math.pi)
             ang_in[~ray_ok] = 1.

@@ -88,3 +88,56 @@ def asph_fast(dtype, x, y, z, cx, cy, c, k, a, t, mu, sd, seeds=None):
     return dict(x=outs[0], y=outs[1], cx=outs[2], cy=outs[3], opl=outs[4], min_cos2=outs[5],
                 min_clip=outs[6], gx=grads[0], gy=grads[1], gz=grads[2], gcx=grads[3], gcy=grads[4],
                 gp=gp.reshape(S, 9), gt=gt, gmu=gmu)
+
+
+def trace_exact_pen(x, y, z, cx, cy, c, t, mu, live, allow_backward=True):
+    """Exact-policy aggregate=True terms: z_relu, theta, theta_prime [S, n], ok [n], ok bits [n]."""
+    n = x.size
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    x, y, z, cx, cy, c, t, mu = map(f, (x, y, z, cx, cy, c, t, mu))
+    live = np.ascontiguousarray(live, dtype=np.uint8)
+    S = c.size
+    stacks = [np.empty((S, n), np.float32) for _ in range(3)]
+    ok = np.empty(n, np.uint8)
+    bits = np.empty(n, np.uint32)
+    lib().hc_trace_exact_pen(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(cx), _p(cy), ctypes.c_int(S),
+                             _p(c), _p(t), _p(mu), _p(live), ctypes.c_int(int(allow_backward)),
+                             *[_p(s) for s in stacks], _p(ok), _p(bits))
+    return stacks, ok, bits
+
+
+def fast_pen(dtype, x, y, z, cx, cy, c, t, mu, seed_y, seed_zr, seed_th, seed_thp):
+    """Fast-policy aggregate=True terms and the adjoint with per-surface seeds [S, n]."""
+    n = x.size
+    f = lambda a: np.ascontiguousarray(a, dtype=dtype)
+    x, y, z, cx, cy, c, t, mu, seed_y, seed_zr, seed_th, seed_thp = map(
+        f, (x, y, z, cx, cy, c, t, mu, seed_y, seed_zr, seed_th, seed_thp))
+    S = c.size
+    stacks = [np.zeros((S, n), dtype) for _ in range(3)]
+    grads = [np.zeros(n, dtype) for _ in range(5)]
+    pg = [np.zeros(S, np.float64) for _ in range(3)]
+    fn = lib().hc_fast_pen_f32 if dtype == np.float32 else lib().hc_fast_pen_f64
+    fn(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(cx), _p(cy), ctypes.c_int(S), _p(c), _p(t), _p(mu),
+       _p(seed_y), _p(seed_zr), _p(seed_th), _p(seed_thp), *[_p(s) for s in stacks],
+       *[_p(g) for g in grads], *[_p(g) for g in pg])
+    return dict(z_relu=stacks[0], theta=stacks[1], theta_prime=stacks[2], gx=grads[0], gy=grads[1],
+                gz=grads[2], gcx=grads[3], gcy=grads[4], gc=pg[0], gt=pg[1], gmu=pg[2])
+
+
+def exact_pen_adjoint(dtype, x, y, z, cx, cy, c, t, mu, live, allow_backward, seed_y, seed_zr, seed_th, seed_thp):
+    """The PEN backward of the kernels for exact-policy rays (failed rays included)."""
+    n = x.size
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    d = lambda a: np.ascontiguousarray(a, dtype=dtype)
+    x, y, z, cx, cy, c, t, mu = map(f, (x, y, z, cx, cy, c, t, mu))
+    seed_y, seed_zr, seed_th, seed_thp = map(d, (seed_y, seed_zr, seed_th, seed_thp))
+    live = np.ascontiguousarray(live, dtype=np.uint8)
+    S = c.size
+    grads = [np.zeros(n, dtype) for _ in range(5)]
+    pg = [np.zeros(S, np.float64) for _ in range(3)]
+    fn = lib().hc_exact_pen_adjoint_f32 if dtype == np.float32 else lib().hc_exact_pen_adjoint_f64
+    fn(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(cx), _p(cy), ctypes.c_int(S), _p(c), _p(t), _p(mu),
+       _p(live), ctypes.c_int(int(allow_backward)), _p(seed_y), _p(seed_zr), _p(seed_th), _p(seed_thp),
+       *[_p(g) for g in grads], *[_p(g) for g in pg])
+    return dict(gx=grads[0], gy=grads[1], gz=grads[2], gcx=grads[3], gcy=grads[4],
+                gc=pg[0], gt=pg[1], gmu=pg[2])

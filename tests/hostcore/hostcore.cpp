@@ -162,3 +162,126 @@ static void asph_fast_and_adjoint(int64_t n, const T *x, const T *y, const T *z,
                  min_cos2, min_clip, gx, gy, gz, gcx, gcy, gp, gt, gmu
 extern "C" void hc_asph_fast_f32(HCA_ARGS(float)) { asph_fast_and_adjoint<float>(HCA_PASS); }
 extern "C" void hc_asph_fast_f64(HCA_ARGS(double)) { asph_fast_and_adjoint<double>(HCA_PASS); }
+
+
+// ---------------------------------------------------------------------------
+// aggregate=True penalty terms (rtl:641-657): exact policy, fast policy and the adjoint with
+// per-surface seeds.  Stacks are [S, n] (surface-major).
+// ---------------------------------------------------------------------------
+extern "C" void hc_trace_exact_pen(int64_t n, const float *x, const float *y, const float *z,
+                                   const float *cx, const float *cy, int S, const float *c,
+                                   const float *t, const float *mu, const uint8_t *live,
+                                   int allow_backward, float *zr, float *th, float *thp, uint8_t *ook,
+                                   uint32_t *okbits) {
+  for (int64_t i = 0; i < n; ++i) {
+    Ray<float> r{x[i], y[i], z[i], cx[i], cy[i], exact_cz0(cx[i], cy[i])};
+    bool ok = true, bw = false;
+    uint32_t bits = 0;
+    for (int k = 0; k < S; ++k) {
+      Surface s{c[k], t[k], mu[k]};
+      Penalty pen;
+      exact_surface_t<true>(r, s, k > 0 && live[k - 1], allow_backward != 0, ok, bw, &pen);
+      zr[k * n + i] = pen.z_relu; th[k * n + i] = pen.theta; thp[k * n + i] = pen.theta_prime;
+      if (ok) bits |= 1u << k;
+    }
+    exact_image(r, live[S - 1] != 0, allow_backward != 0, ok, bw);
+    ook[i] = ok;
+    okbits[i] = bits;
+  }
+}
+
+template <class T>
+static void fast_pen_and_adjoint(int64_t n, const T *x, const T *y, const T *z, const T *cx, const T *cy,
+                                 int S, const T *c, const T *t, const T *mu, const T *sy,
+                                 const T *szr, const T *sth, const T *sthp, T *zr, T *th, T *thp,
+                                 T *gx, T *gy, T *gz, T *gcx, T *gcy, double *gc, double *gt,
+                                 double *gmu) {
+  std::vector<Ray<T>> st(S + 1);
+  for (int k = 0; k < S; ++k) gc[k] = gt[k] = gmu[k] = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    Ray<T> r{x[i], y[i], z[i], cx[i], cy[i], fast_cz0(cx[i], cy[i])};
+    T mq = T(1);
+    for (int k = 0; k < S; ++k) {
+      st[k] = r;
+      T travel, ci, co;
+      fast_surface(r, c[k], mu[k], mu[k] * mu[k], t[k], mq, travel, ci, co);
+      zr[k * n + i] = r.z > T(0) ? r.z : T(0);
+      th[k * n + i] = fast_angle_norm(ci);
+      thp[k * n + i] = fast_angle_norm(co);
+    }
+    st[S] = r;
+    Ray<T> pre = r;
+    fast_image(r);
+    Sweep<T> sw = sweep_begin(pre, r.x, r.y, T(0), sy[i], T(0), T(0));
+    for (int k = S - 1; k >= 0; --k) {
+      SurfaceGrad<T> g = sweep_sphere_pen(sw, st[k + 1].x, st[k + 1].y, st[k].cx, st[k].cy, c[k], t[k],
+                                          mu[k], mu[k] * mu[k], szr[k * n + i], sth[k * n + i],
+                                          sthp[k * n + i], T(1));
+      gc[k] += (double)g.c; gt[k] += (double)g.t; gmu[k] += (double)g.mu;
+    }
+    sweep_end(sw, z[i], gx[i], gy[i], gz[i], gcx[i], gcy[i]);
+  }
+}
+
+#define HCP_ARGS(T)                                                                             \
+  int64_t n, const T *x, const T *y, const T *z, const T *cx, const T *cy, int S, const T *c,  \
+      const T *t, const T *mu, const T *sy, const T *szr, const T *sth, const T *sthp, T *zr,  \
+      T *th, T *thp, T *gx, T *gy, T *gz, T *gcx, T *gcy, double *gc, double *gt, double *gmu
+#define HCP_PASS n, x, y, z, cx, cy, S, c, t, mu, sy, szr, sth, sthp, zr, th, thp, gx, gy, gz, gcx, gcy, \
+                 gc, gt, gmu
+extern "C" void hc_fast_pen_f32(HCP_ARGS(float)) { fast_pen_and_adjoint<float>(HCP_PASS); }
+extern "C" void hc_fast_pen_f64(HCP_ARGS(double)) { fast_pen_and_adjoint<double>(HCP_PASS); }
+
+// The penalty backward exactly as k_trace_adj<.., MODE_BWD, .., PEN> runs it for a ray that took
+// the exact policy: exact trace with parked (hit, incoming direction) and ok bits, then the sweep
+// with seeds only where the ray is ok behind the surface and every other lane state forced to zero.
+template <class T>
+static void exact_pen_adjoint(int64_t n, const float *x, const float *y, const float *z, const float *cx,
+                              const float *cy, int S, const float *c, const float *t, const float *mu,
+                              const uint8_t *live, int allow_backward, const T *sy, const T *szr,
+                              const T *sth, const T *sthp, T *gx, T *gy, T *gz, T *gcx, T *gcy,
+                              double *gc, double *gt, double *gmu) {
+  std::vector<float> hx(S), hy(S), dx(S), dy(S);
+  for (int k = 0; k < S; ++k) gc[k] = gt[k] = gmu[k] = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    Ray<float> r{x[i], y[i], z[i], cx[i], cy[i], exact_cz0(cx[i], cy[i])};
+    bool ok = true, bw = false;
+    uint32_t bits = 0, flips = 0;
+    for (int k = 0; k < S; ++k) {
+      const float in_cx = r.cx, in_cy = r.cy;
+      Surface s{c[k], t[k], mu[k]};
+      exact_surface(r, s, k > 0 && live[k - 1], allow_backward != 0, ok, bw);
+      hx[k] = r.x; hy[k] = r.y; dx[k] = in_cx; dy[k] = in_cy;
+      if (ok) bits |= 1u << k;
+      if (beyond_equator(c[k], r.z, t[k])) flips |= 1u << k;
+    }
+    Ray<T> pre{T(r.x), T(r.y), T(r.z), T(r.cx), T(r.cy), T(r.cz)};
+    exact_image(r, live[S - 1] != 0, allow_backward != 0, ok, bw);
+    Sweep<T> sw = sweep_begin(pre, T(r.x), T(r.y), T(0), ok ? sy[i] : T(0), T(0), T(0));
+    for (int k = S - 1; k >= 0; --k) {
+      const bool ok_k = (bits >> k) & 1u;
+      SurfaceGrad<T> g = sweep_sphere_pen(sw, T(hx[k]), T(hy[k]), T(dx[k]), T(dy[k]), T(c[k]), T(t[k]),
+                                          T(mu[k]), T(mu[k]) * T(mu[k]), ok_k ? szr[k * n + i] : T(0),
+                                          ok_k ? sth[k * n + i] : T(0), ok_k ? sthp[k * n + i] : T(0),
+                                          ((flips >> k) & 1u) ? T(-1) : T(1));
+      if (!ok_k) {
+        g.c = T(0); g.mu = T(0);
+        g.t = (-t[k] > 0.f) ? -szr[k * n + i] : T(0);
+        sw.gr = Vec3<T>{T(0), T(0), T(0)};
+        sw.gd = Vec3<T>{T(0), T(0), T(0)};
+      }
+      gc[k] += (double)g.c; gt[k] += (double)g.t; gmu[k] += (double)g.mu;
+    }
+    sweep_end(sw, T(z[i]), gx[i], gy[i], gz[i], gcx[i], gcy[i]);
+  }
+}
+
+#define HCE_ARGS(T)                                                                                  \
+  int64_t n, const float *x, const float *y, const float *z, const float *cx, const float *cy, int S, \
+      const float *c, const float *t, const float *mu, const uint8_t *live, int allow_backward,       \
+      const T *sy, const T *szr, const T *sth, const T *sthp, T *gx, T *gy, T *gz, T *gcx, T *gcy,   \
+      double *gc, double *gt, double *gmu
+#define HCE_PASS n, x, y, z, cx, cy, S, c, t, mu, live, allow_backward, sy, szr, sth, sthp, gx, gy, gz, \
+                 gcx, gcy, gc, gt, gmu
+extern "C" void hc_exact_pen_adjoint_f32(HCE_ARGS(float)) { exact_pen_adjoint<float>(HCE_PASS); }
+extern "C" void hc_exact_pen_adjoint_f64(HCE_ARGS(double)) { exact_pen_adjoint<double>(HCE_PASS); }

@@ -1,0 +1,242 @@
+"""trace_skew(aggregate=True) on the GPU (rtl:641-657): the three penalty stacks and their
+gradients, through the C ABI, against the oracle and the golden vectors made by the reference
+(tests/golden/aggregate).
+
+Tolerances: z_RELU like points (1e-5 of the lens scale); theta = acos(cos)/(pi/2) is compared
+through its cosine (1e-6 abs: acos is ill-conditioned at normal incidence, where one ULP of the
+cosine moves theta by 3e-4) and directly (1e-5) where sin(theta) > 0.05; masks (theta == 1) exact;
+gradients ||dg|| / ||g|| <= 1e-4 per parameter group against the fp64 oracle -- or, where the
+reference's own fp32 arithmetic is further than that from fp64 (the angle terms amplify rounding
+by 1 / sin(theta)), no further than 1.5x what the reference's fp32 evaluation is.  Exact policy: z_RELU bit-identical, angles
+within 4 ULP (two acos implementations on identical cos^2 bits).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import trace_oracle as oracle
+from tests.test_penalty_cpu import AGG_CASES, KEYS, load_aggregate
+from torchoptics_b200 import ray_tracing_lite as rt
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+GRAD_TOL = 1e-4
+PENALTY_RATE = 0.2
+
+
+def _inputs(rec, device, broadcast, grad=(), dtype=torch.float32):
+    shape = rec['out_ok'].shape
+    t = {}
+    for k in ('x', 'y', 'z', 'cx', 'cy', 'c', 't', 'mu'):
+        v = rec['in_' + k]
+        if broadcast and k in ('x', 'y', 'cx', 'cy'):
+            v = np.ascontiguousarray(np.broadcast_to(v, shape))
+        t[k] = torch.from_numpy(v).to(device=device, dtype=dtype)
+    t['mask'] = torch.from_numpy(rec['in_mask']).to(device)
+    for k in grad:
+        t[k] = t[k].clone().requires_grad_(True)
+    return t
+
+
+def _args(i):
+    return [i[k] for k in ('x', 'y', 'z', 'cx', 'cy', 'c', 't', 'mu', 'mask')]
+
+
+def _stack(stacks, shape):
+    return {k: torch.stack([torch.broadcast_to(s, shape) for s in stacks[k]]) for k in KEYS}
+
+
+def _rel(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    return np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-30)
+
+
+def _check_stacks(got, want, scale, exact):
+    zr, zr_ref = got['z_RELU'], want['z_RELU']
+    if exact:
+        assert np.array_equal(zr.view(np.uint32), zr_ref.view(np.uint32))
+    assert np.abs(zr - zr_ref).max() <= 1e-5 * scale
+    for key in ('theta_norm', 'theta_prime_norm'):
+        a, b = got[key].astype(np.float64), want[key].astype(np.float64)
+        assert np.array_equal(a == 1.0, b == 1.0), key                    # failed-ray marks
+        assert np.abs(np.cos(a * np.pi / 2) - np.cos(b * np.pi / 2)).max() <= 1e-6, key
+        steep = np.sin(b * np.pi / 2) > 0.05
+        assert np.abs(a - b)[steep].max(initial=0.0) <= 1e-5, key
+        if exact:
+            np.testing.assert_allclose(a, b, rtol=5e-7, atol=1e-7)
+
+
+@pytest.mark.parametrize('arith', ['guarded', 'exact'])
+@pytest.mark.parametrize('name', AGG_CASES)
+def test_stacks_match_reference_and_oracle(name, arith):
+    rec, agg = load_aggregate(name)
+    allow = bool(rec['allow_backward_rays'])
+    shape = rec['out_ok'].shape
+    scale = max(np.abs(rec['out_x']).max(), np.abs(rec['out_y']).max(), np.abs(rec['in_t']).max())
+    # un-broadcast pupil grids as trace_rays hands them over (the reference raises there for W > 1)
+    i = _inputs(rec, DEV, broadcast=False)
+    out = rt.trace_skew(*_args(i), aggregate=True, allow_backward_rays=allow, arith=arith)
+    assert len(out) == 7 and set(out[6]) == set(KEYS)
+    assert all(len(out[6][k]) == rec['in_t'].shape[-1] and out[6][k][0].shape == shape for k in KEYS)
+    got = {k: v.cpu().numpy() for k, v in _stack(out[6], shape).items()}
+    assert np.array_equal(out[4].cpu().numpy(), rec['out_ok'])
+    # the reference's own stacks (CPU sqrt: within the float32 budget)
+    _check_stacks(got, {k: agg[k] for k in KEYS}, scale, exact=False)
+    # the oracle with the correctly rounded sqrt: what the exact policy reproduces
+    cpu = _inputs(rec, 'cpu', broadcast=True)
+    with oracle.ieee_sqrt():
+        ref = oracle.trace(*_args(cpu), True, allow)
+    want = {k: v.numpy() for k, v in _stack(ref[6], shape).items()}
+    _check_stacks(got, want, scale, exact=(arith == 'exact'))
+    # the six regular outputs are those of aggregate=False
+    plain = rt.trace_skew(*_args(i), allow_backward_rays=allow, arith=arith)
+    for a, b in zip(out[:6], plain):
+        assert torch.equal(a, b)
+
+
+def _loss(out, oracle_side, n_seq):
+    stacks = out[6]
+    q = (torch.stack(stacks['theta_norm']).sum(0) + torch.stack(stacks['theta_prime_norm']).sum(0) +
+         torch.stack(stacks['z_RELU']).sum(0)) / n_seq
+    q = torch.where(torch.isnan(q), torch.zeros_like(q), q)
+    penalty = q.sum()
+    rms = oracle.spot_rms(out[0], out[1], out[4]) if oracle_side else rt.compute_rms2d(out[0], out[1], out[4])
+    return rms, penalty
+
+
+@pytest.mark.parametrize('arith', ['guarded', 'exact'])
+@pytest.mark.parametrize('name', AGG_CASES)
+def test_penalty_and_loss_gradients(name, arith):
+    """d penalty / d (z, c, t, mu) and d (rms + 0.2 penalty) / d (...) as compute_loss_out builds
+    them (optics_simulator_lite.py:430-450)."""
+    rec, agg = load_aggregate(name)
+    allow = bool(rec['allow_backward_rays'])
+    n_seq = int(agg['n_seq'])
+    names = ('z', 'c', 't', 'mu')
+    i = _inputs(rec, DEV, broadcast=False, grad=names)
+    out = rt.trace_skew(*_args(i), aggregate=True, allow_backward_rays=allow, arith=arith)
+    rms, penalty = _loss(out, False, n_seq)
+    leaves = [i[k] for k in names]
+    g_pen = torch.autograd.grad(penalty, leaves, retain_graph=True)
+    g_loss = torch.autograd.grad(rms + PENALTY_RATE * penalty, leaves)
+    assert abs(float(penalty) - float(agg['penalty'])) <= 2e-5 * abs(float(agg['penalty']))
+    # fp64 oracle with finite penalty gradients: the truth both fp32 evaluations approximate
+    cpu = _inputs(rec, 'cpu', broadcast=True, grad=names, dtype=torch.float64)
+    with oracle.finite_penalty_gradients(), oracle.fp32_clamp_bound():
+        ref = oracle.trace(*_args(cpu), True, allow)
+    all_ok = bool(rec['out_ok'].all())
+    same_masks = torch.equal(ref[4], torch.from_numpy(rec['out_ok']))
+    rms64, pen64 = _loss(ref, True, n_seq)
+    ref_leaves = [cpu[k] for k in names]
+    want_pen = torch.autograd.grad(pen64, ref_leaves, retain_graph=True)
+    want_loss = torch.autograd.grad(rms64 + PENALTY_RATE * pen64, ref_leaves)
+    def rel(got, want, group_with=None):
+        # d/dz is the heavily cancelled sum of two axial shifts: like the RMS
+        # tests, that one scalar is held to 1e-4 of the {z, t} group scale
+        got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+        scale = np.linalg.norm(want) if group_with is None else \
+            np.linalg.norm(np.concatenate([want.ravel(), np.asarray(group_with, np.float64).ravel()]))
+        return np.linalg.norm(got - want) / max(scale, 1e-30)
+
+    # The angle terms are ill-conditioned at normal incidence (d theta / d cos = 1 / sin theta), so
+    # the REFERENCE's own fp32 gradient sits up to 4e-4 from its fp64 evaluation on these cases
+    # (cooke_8x8: c 4.2e-4, tessar_8x8: t 2.8e-4).  The bar is therefore: within 1e-4 of the fp64
+    # truth, or no further from it than 1.5x the reference's fp32 arithmetic is.
+    cpu32 = _inputs(rec, 'cpu', broadcast=True, grad=names)
+    with oracle.finite_penalty_gradients():
+        ref32 = oracle.trace(*_args(cpu32), True, allow)
+    rms32, pen32 = _loss(ref32, True, n_seq)
+    leaves32 = [cpu32[k] for k in names]
+    ref32_pen = torch.autograd.grad(pen32, leaves32, retain_graph=True)
+    ref32_loss = torch.autograd.grad(rms32 + PENALTY_RATE * pen32, leaves32)
+    for j, (k, got, want, want_l, got_l) in enumerate(zip(names, g_pen, want_pen, want_loss, g_loss)):
+        assert torch.isfinite(got).all() and torch.isfinite(got_l).all(), k
+        gw, gwl = (want_pen[2].numpy(), want_loss[2].numpy()) if k == 'z' else (None, None)
+        if same_masks:       # fp64 takes the same branch for every ray
+            bar = max(GRAD_TOL, 1.5 * rel(ref32_pen[j].numpy(), want.numpy(), gw))
+            bar_l = max(GRAD_TOL, 1.5 * rel(ref32_loss[j].numpy(), want_l.numpy(), gwl))
+            assert bar <= 1e-3 and bar_l <= 1e-3
+            assert rel(got.cpu().numpy(), want.numpy(), gw) <= bar, (k, 'penalty vs fp64 oracle')
+            assert rel(got_l.cpu().numpy(), want_l.numpy(), gwl) <= bar_l, (k, 'loss vs fp64 oracle')
+            if all_ok:       # the reference's own gradient is finite only when no ray fails
+                gwa, gwla = (agg['gpen_t'], agg['gloss_t']) if k == 'z' else (None, None)
+                assert rel(got.cpu().numpy(), agg['gpen_' + k], gwa) <= 2 * bar, (k, 'penalty vs reference')
+                assert rel(got_l.cpu().numpy(), agg['gloss_' + k], gwla) <= 2 * bar_l, (k, 'loss vs reference')
+    if not same_masks:       # rays on a threshold: compare with the fp32 oracle, same masks by construction
+        cpu32 = _inputs(rec, 'cpu', broadcast=True, grad=names)
+        with oracle.finite_penalty_gradients(), oracle.ieee_sqrt():
+            ref32 = oracle.trace(*_args(cpu32), True, allow)
+        _, pen32 = _loss(ref32, True, n_seq)
+        want32 = torch.autograd.grad(pen32, [cpu32[k] for k in names])
+        for k, got, want in zip(names, g_pen, want32):
+            assert _rel(got.cpu().numpy(), want.numpy()) <= 10 * GRAD_TOL, (k, 'penalty vs fp32 oracle')
+
+
+def test_partial_seeds_and_per_ray_gradients():
+    """Only one stack used, and gradients w.r.t. the per-ray inputs x, y (the ray-aiming
+    contract, rtl:170-180) through the penalty terms."""
+    rec, agg = load_aggregate('cooke_16x16_epd2.6')
+    names = ('x', 'y', 'z', 'c', 't', 'mu')
+    i = _inputs(rec, DEV, broadcast=True, grad=names)
+    out = rt.trace_skew(*_args(i), aggregate=True)
+    g = torch.Generator(device='cpu').manual_seed(5)
+    S = rec['in_t'].shape[-1]
+    seed = torch.rand((S,) + rec['out_ok'].shape, generator=g) + 0.2
+    loss = (torch.stack(out[6]['theta_prime_norm']) * seed.to(DEV)).sum()
+    got = torch.autograd.grad(loss, [i[k] for k in names])
+    cpu = _inputs(rec, 'cpu', broadcast=True, grad=names, dtype=torch.float64)
+    with oracle.finite_penalty_gradients():
+        ref = oracle.trace(*_args(cpu), True)
+    want = torch.autograd.grad((torch.stack(ref[6]['theta_prime_norm']) * seed.double()).sum(),
+                               [cpu[k] for k in names])
+    if torch.equal(ref[4], torch.from_numpy(rec['out_ok'])):
+        for k, a, b in zip(names, got, want):
+            assert torch.isfinite(a).all()
+            assert _rel(a.cpu().numpy(), b.numpy()) <= GRAD_TOL, k
+
+
+def test_large_pupil_penalty_matches_oracle_on_device():
+    """Config-2 lens, 0.5 M rays: stacks against the oracle evaluated by torch on the same GPU
+    (correctly rounded sqrt there), loss gradient against fp64."""
+    from torchoptics_b200 import RayTracer, prescriptions
+    specs, lens = prescriptions.double_gauss(DEV)
+    tracer = RayTracer(mode='circular', n_rays=(104, 104), rel_fields=tuple(np.linspace(0, 1, 16).tolist()),
+                       wavelengths=('C', 'd', 'F'), default_device=DEV)
+    args = [a.detach() for a in tracer._ray_set(specs, lens)]
+    shape = (1, 16, 104 * 104, 3)
+    full = [torch.broadcast_to(a, shape).contiguous() if j in (0, 1, 3, 4) else a for j, a in enumerate(args)]
+    out = rt.trace_skew(*args, aggregate=True, arith='exact')
+    ref = oracle.trace(*full, True)
+    assert torch.equal(out[4], ref[4])
+    for k in KEYS:
+        a, b = torch.stack(out[6][k]), torch.stack([torch.broadcast_to(s, shape) for s in ref[6][k]])
+        if k == 'z_RELU':
+            assert torch.equal(a, b)
+        else:
+            assert float((torch.cos(a.double() * np.pi / 2) - torch.cos(b.double() * np.pi / 2)).abs().max()) <= 1e-6
+    # gradients of the summed penalty w.r.t. c, t, mu: guarded policy against fp64 autograd
+    leaves = [args[j].clone().requires_grad_(True) for j in (5, 6, 7)]
+    call = list(args)
+    call[5], call[6], call[7] = leaves
+    o2 = rt.trace_skew(*call, aggregate=True)
+    pen = sum(torch.stack(o2[6][k]).sum() for k in KEYS)
+    got = torch.autograd.grad(pen, leaves)
+    leaves64 = [args[j].double().clone().requires_grad_(True) for j in (5, 6, 7)]
+    call64 = [a.double() if a.dtype == torch.float32 else a for a in full]
+    call64[5], call64[6], call64[7] = leaves64
+    with oracle.finite_penalty_gradients(), oracle.fp32_clamp_bound():
+        r64 = oracle.trace(*call64, True)
+    pen64 = sum(torch.stack([torch.broadcast_to(s, shape) for s in r64[6][k]]).sum() for k in KEYS)
+    want = torch.autograd.grad(pen64, leaves64)
+    # the bar of test_penalty_and_loss_gradients: the oracle in fp32 on the same device sets it
+    leaves32 = [args[j].clone().requires_grad_(True) for j in (5, 6, 7)]
+    call32 = list(full)
+    call32[5], call32[6], call32[7] = leaves32
+    with oracle.finite_penalty_gradients():
+        r32 = oracle.trace(*call32, True)
+    pen32 = sum(torch.stack([torch.broadcast_to(s, shape) for s in r32[6][k]]).sum() for k in KEYS)
+    noise = torch.autograd.grad(pen32, leaves32)
+    for label, a, b, c32 in zip(('c', 't', 'mu'), got, want, noise):
+        bar = max(GRAD_TOL, 1.5 * _rel(c32.cpu().numpy(), b.cpu().numpy()))
+        assert bar <= 1e-3
+        assert _rel(a.cpu().numpy(), b.cpu().numpy()) <= bar, (label, bar)

@@ -43,11 +43,12 @@ class TlProblem(ctypes.Structure):
 
 
 class TlTraceOut(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_void_p) for n in ('x', 'y', 'cx', 'cy', 'ok', 'backward', 'opl')]
+    _fields_ = [(n, ctypes.c_void_p) for n in ('x', 'y', 'cx', 'cy', 'ok', 'backward', 'opl',
+                                               'z_relu', 'theta', 'theta_prime')]
 
 
 class TlSeeds(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_void_p) for n in ('gx', 'gy', 'gcx', 'gcy')]
+    _fields_ = [(n, ctypes.c_void_p) for n in ('gx', 'gy', 'gcx', 'gcy', 'gz_relu', 'gtheta', 'gtheta_prime')]
 
 
 class TlGrads(ctypes.Structure):
@@ -118,7 +119,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.tl_abi_version() != 5:
+    if lib.tl_abi_version() != 6:
         raise NativeLibraryError('libtorchoptics_b200.so: ABI version mismatch, rebuild it')
     _lib = lib
     return lib

@@ -212,10 +212,29 @@ TL_HD void exact_park(bool ok, Ray<float> &r) {         // rtl:574-591
   }
 }
 
+// Penalty terms of trace_skew(aggregate=True) for one ray at one surface, rtl:641-657:
+// z_RELU, theta_norm, theta_prime_norm.
+struct Penalty {
+  float z_relu, theta, theta_prime;
+};
+
+constexpr float kClampCos = 1.0f - 1e-7f;          // rtl:645-647: clamp(.., max=1-1e-7) in fp32
+constexpr float kHalfPi = 1.5707963267948966f;     // rtl:651: theta / (1/2*pi)
+
+// acos(clamp(sqrt(cos2), -1+1e-7, 1-1e-7)) / (pi/2), rtl:646-652 (a NaN from a negative cos2 only
+// occurs on failed rays, whose angle is overwritten with 1, rtl:653-654)
+TL_HD float exact_angle_norm(float cos2) {
+  float v = xsqrt(cos2);
+  v = v > kClampCos ? kClampCos : v;
+  v = v < -kClampCos ? -kClampCos : v;
+  return xdiv(acosf(v), kHalfPi);
+}
+
 // Trace one surface.  `count_travel`: this surface takes part in the backward-ray
-// test (k > 0 and mask[k-1], rtl:626-628).
-TL_HD void exact_surface(Ray<float> &r, const Surface s, bool count_travel, bool allow_backward,
-                         bool &ok, bool &backward) {
+// test (k > 0 and mask[k-1], rtl:626-628).  PEN: also return the aggregate=True terms.
+template <bool PEN>
+TL_HD void exact_surface_t(Ray<float> &r, const Surface s, bool count_travel, bool allow_backward,
+                           bool &ok, bool &backward, Penalty *pen) {
   // rtl:531-535
   const float e = -xadd(xadd(xmul(r.x, r.cx), xmul(r.y, r.cy)), xmul(r.z, r.cz));
   const float mz = xadd(r.z, xmul(e, r.cz));
@@ -251,6 +270,16 @@ TL_HD void exact_surface(Ray<float> &r, const Surface s, bool count_travel, bool
   ok = ok && !lost;                                                       // rtl:635
   exact_park(ok, r);
   r.z = xsub(r.z, s.t);                                                   // rtl:639
+  if (PEN) {                                                              // rtl:641-657
+    pen->z_relu = r.z <= 0.0f ? 0.0f : r.z;
+    pen->theta = ok ? exact_angle_norm(cos2_in) : 1.0f;
+    pen->theta_prime = ok ? exact_angle_norm(cos2_out) : 1.0f;
+  }
+}
+
+TL_HD void exact_surface(Ray<float> &r, const Surface s, bool count_travel, bool allow_backward,
+                         bool &ok, bool &backward) {
+  exact_surface_t<false>(r, s, count_travel, allow_backward, ok, backward, nullptr);
 }
 
 // Image plane, rtl:660-670.  Returns through r.x, r.y; direction unchanged.
@@ -278,7 +307,8 @@ TL_HD T fast_cz0(T cx, T cy) {
 }
 
 template <class T>
-TL_HD void fast_surface(Ray<T> &r, T c, T mu, T mu2, T t, T &min_cos2, T &travel) {
+TL_HD void fast_surface(Ray<T> &r, T c, T mu, T mu2, T t, T &min_cos2, T &travel, T &cos_in,
+                        T &cos_out) {
   const T ne = ffma(r.z, r.cz, ffma(r.y, r.cy, r.x * r.cx));          // -e
   const T mz = ffma(-ne, r.cz, r.z);
   const T m2 = ffma(-ne, ne, ffma(r.z, r.z, ffma(r.y, r.y, r.x * r.x)));
@@ -299,7 +329,28 @@ TL_HD void fast_surface(Ray<T> &r, T c, T mu, T mu2, T t, T &min_cos2, T &travel
   r.cz = w * frsqrt(w);
   min_cos2 = fmin2(min_cos2, fmin2(q, fmin2(qo, w)));
   r.z = r.z - t;
+  cos_in = ci;
+  cos_out = co;
 }
+
+template <class T>
+TL_HD void fast_surface(Ray<T> &r, T c, T mu, T mu2, T t, T &min_cos2, T &travel) {
+  T cos_in, cos_out;
+  fast_surface(r, c, mu, mu2, t, min_cos2, travel, cos_in, cos_out);
+}
+
+// Fast-policy penalty terms of a ray that is clear of every threshold (so it is ok): the angles
+// from the cosines the trace already has, z_RELU from the shifted z.
+TL_HD float fast_angle_norm(float cosv) {
+  return acosf(fminf(cosv, kClampCos)) * (1.0f / kHalfPi);
+}
+TL_HD double fast_angle_norm(double cosv) {      // fp64 check build: the clamp bound in fp64
+  return acos(fmin(cosv, 1.0 - 1e-7)) * (1.0 / 1.5707963267948966);
+}
+// sin^2 of the clamp angle: cos > bound  <=>  sin^2 < 1 - bound^2 (fp32 bound 1 - 2^-23; the fp64
+// check build uses the fp64 bound 1 - 1e-7)
+template <class T> TL_HD T clamp_sin2() { return T(2.3841856e-07f); }
+template <> TL_HD double clamp_sin2<double>() { return 1.0 - (1.0 - 1e-7) * (1.0 - 1e-7); }
 
 // Image plane; returns the z travel (for the backward-ray margin).
 template <class T>
@@ -397,6 +448,85 @@ TL_HD SurfaceGrad<T> sweep_sphere(Sweep<T> &s, T hx, T hy, T dx, T dy, T c, T t,
   const Vec3<T> gh{ffma(-c, gn.x, s.gr.x), ffma(-c, gn.y, s.gr.y), ffma(-c, gn.z, s.gr.z)};
   const T gc_n = ffma(gn.z, hz, ffma(gn.y, hy, gn.x * hx));
   // transfer onto the sphere
+  const T sd = -dot3(gh, d) * frcp(a);
+  s.gr = Vec3<T>{ffma(sd, n.x, gh.x), ffma(sd, n.y, gh.y), ffma(sd, n.z, gh.z)};
+  g.c = -ffma(sd * T(0.5), ffma(hz, hz, rho), gc_n);
+  s.gd = gdi;
+  s.hit = Vec3<T>{hx, hy, hz};
+  s.dir = d;
+  return g;
+}
+
+// Did the ray hit the sphere beyond its equator?  `z_shifted` = h_z - t (the state behind the
+// surface, rtl:639).
+TL_HD bool beyond_equator(float c, float z_shifted, float t) { return c * (z_shifted + t) > 1.0f; }
+
+// Lane-wise selects for the penalty seeds.
+TL_HD float keep_if(bool cond, float v) { return cond ? v : 0.0f; }
+TL_HD double keep_if(bool cond, double v) { return cond ? v : 0.0; }
+TL_HD float keep_pos(float cond, float v) { return cond > 0.0f ? v : 0.0f; }
+TL_HD double keep_pos(double cond, double v) { return cond > 0.0 ? v : 0.0; }
+TL_HD f2 keep_pos(f2 cond, f2 v) { return f2(keep_pos(cond.v.x, v.v.x), keep_pos(cond.v.y, v.v.y)); }
+TL_HD f4 keep_pos(f4 cond, f4 v) { return f4(keep_pos(cond.a, v.a), keep_pos(cond.b, v.b)); }
+
+// sweep_sphere with the seeds of the aggregate=True terms of this surface (rtl:641-657):
+//   pz   on z_RELU = relu(h_z - t)            -> joins the adjoint of the point behind the surface
+//   pth  on theta_norm  = acos(min(a, 1-1e-7)) / (pi/2),   a  = n.d  = cos(theta)
+//   pthp on theta_prime_norm, same of a' = sqrt(1 - mu^2 (1 - a^2)) = cos(theta')
+// The two angle seeds enter where the refraction's own adjoint of a enters (ga) plus a direct
+// term on mu.  Seeds must already be zero for lanes that are not ok behind this surface.
+// `branch` = +1, or -1 for a hit BEYOND THE EQUATOR of the sphere (c h_z > 1, possible for very
+// oblique rays): there n_z = 1 - c h_z = -sqrt(1 - c^2 rho), which the parked (hx, hy) alone cannot
+// tell.  (sweep_sphere assumes +1: a ray with such a hit that still reaches the image is outside
+// its validity; the penalty terms exist to punish exactly such rays, so this one carries the sign.)
+template <class T>
+TL_HD SurfaceGrad<T> sweep_sphere_pen(Sweep<T> &s, T hx, T hy, T dx, T dy, T c, T t, T mu, T mu2,
+                                      T pz, T pth, T pthp, T branch) {
+  SurfaceGrad<T> g;
+  const T rho = ffma(hy, hy, hx * hx);
+  const T w = ffma(-(c * c), rho, T(1));
+  const T root = branch * (w * frsqrt(w));
+  const T hz = (c * rho) * frcp(T(1) + root);
+  const T wd = ffma(-dy, dy, ffma(-dx, dx, T(1)));
+  const T dz = wd * frsqrt(wd);
+  const T dist = ffma((s.hit.z - hz) + t, s.dir.z, ffma(s.hit.y - hy, s.dir.y, (s.hit.x - hx) * s.dir.x));
+  const Vec3<T> gdo{ffma(dist, s.gr.x, s.gd.x), ffma(dist, s.gr.y, s.gd.y), ffma(dist, s.gr.z, s.gd.z)};
+  // z_RELU = relu(z'), z' = h_z - t: a seed on the START point of the ray behind the surface (it
+  // joins the point adjoint after the direction adjoint above has taken its dist * gr share)
+  s.gr.z = s.gr.z + keep_pos(hz - t, pz);
+  g.t = -s.gr.z;
+  const Vec3<T> n{-c * hx, -c * hy, root};
+  const Vec3<T> d{dx, dy, dz};
+  const T a = dot3(n, d);
+  const T ap = dot3(n, s.dir);
+  const T gsn = ffma(-mu, a, ap);
+  const T gdd = dot3(gdo, d);
+  const T rap = frcp(ap);
+  const T u = dot3(gdo, n) * rap;
+  // angle seeds: d theta / d a = -(2/pi) / sqrt(1 - a^2) inside the clamp, 0 outside
+  // cos(theta') as the reference forms it, sqrt(1 - mu^2 (1 - a^2)) (rtl:553): equal to n.d' for a
+  // physical ray, but not when the reference's always-positive cz' (rtl:566) has flipped d'
+  // sin^2(theta) = |n x d|^2 rather than 1 - a^2: near normal incidence, where d theta / d a =
+  // 1 / sin(theta) amplifies everything, 1 - a^2 has lost its digits to cancellation
+  const T kx = ffma(n.y, d.z, -(n.z * d.y)), ky = ffma(n.z, d.x, -(n.x * d.z)), kz = ffma(n.x, d.y, -(n.y * d.x));
+  const T sin2 = ffma(kz, kz, ffma(ky, ky, kx * kx));
+  const T sin2p = mu2 * sin2;
+  const T cos2p = T(1) - sin2p;
+  const T rapp = frsqrt(cos2p);                       // 1 / cos(theta')
+  const T clamp_s2 = clamp_sin2<T>();
+  // (torch's clamp passes the gradient on the boundary: keep cos <= bound, drop cos > bound -- decided
+  // on the well-conditioned sin^2, not on a cosine that is within an ULP of 1 -- and keep the rsqrt
+  // argument away from 0 on the dropped lanes)
+  const T over = keep_pos(clamp_s2 - sin2, T(1)), overp = keep_pos(clamp_s2 - sin2p, T(1));
+  const T dth = (pth - over * pth) * frsqrt(sin2 + over);
+  const T dthp = (pthp - overp * pthp) * frsqrt(sin2p + overp);
+  const T gap = T(-0.63661977236758134) * dthp;                           // adjoint of a'
+  const T ga = ffma(gap * mu2, a * rapp, ffma(T(-0.63661977236758134), dth, -(mu * gsn) * u));
+  g.mu = ffma(-(gap * mu), sin2 * rapp, ffma(-u, ffma(a, ap, mu * sin2), gdd));
+  const Vec3<T> gn{ffma(ga, d.x, gsn * gdo.x), ffma(ga, d.y, gsn * gdo.y), ffma(ga, d.z, gsn * gdo.z)};
+  const Vec3<T> gdi{ffma(ga, n.x, mu * gdo.x), ffma(ga, n.y, mu * gdo.y), ffma(ga, n.z, mu * gdo.z)};
+  const Vec3<T> gh{ffma(-c, gn.x, s.gr.x), ffma(-c, gn.y, s.gr.y), ffma(-c, gn.z, s.gr.z)};
+  const T gc_n = ffma(gn.z, hz, ffma(gn.y, hy, gn.x * hx));
   const T sd = -dot3(gh, d) * frcp(a);
   s.gr = Vec3<T>{ffma(sd, n.x, gh.x), ffma(sd, n.y, gh.y), ffma(sd, n.z, gh.z)};
   g.c = -ffma(sd * T(0.5), ffma(hz, hz, rho), gc_n);

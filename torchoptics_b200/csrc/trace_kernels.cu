@@ -130,17 +130,26 @@ __device__ __forceinline__ void park(V *state, int stride, int k, V hit_x, V hit
 
 // Exact-policy trace of one ray (rtl:594-675 statement by statement).  When SAVE,
 // parks this ray's lane of the V-wide slots (scalar view: `stride` in floats).
-template <bool SAVE>
+// BITS: also report, as bit k of ok_bits[0], whether the ray was ok behind surface k, and as bit k
+// of ok_bits[1] whether it hit surface k beyond the equator (S <= 32).
+template <bool SAVE, bool BITS = false>
 __device__ __noinline__ Traced trace_exact(float x, float y, float z, float cx, float cy,
                                            const Table &tab, int S, bool allow_backward,
-                                           float *state, int stride) {
+                                           float *state, int stride, unsigned *ok_bits = nullptr) {
   Ray<float> r{x, y, z, cx, cy, exact_cz0(cx, cy)};
   bool ok = true, backward = false;
+  unsigned bits = 0, flips = 0;
   for (int k = 0; k < S; ++k) {
     const float in_cx = r.cx, in_cy = r.cy;
     const Surface s{tab.c[k], tab.t[k], tab.mu[k]};
     exact_surface(r, s, k > 0 && tab.live[k - 1], allow_backward, ok, backward);
     park<SAVE, float>(state, stride, k, r.x, r.y, in_cx, in_cy);
+    if (BITS && ok) bits |= 1u << (k & 31);
+    if (BITS && beyond_equator(s.c, r.z, s.t)) flips |= 1u << (k & 31);
+  }
+  if (BITS) {
+    ok_bits[0] = bits;
+    ok_bits[1] = flips;      // surfaces hit beyond the equator (branch of sweep_sphere_pen)
   }
   Traced out;
   out.pre = r;
@@ -158,12 +167,13 @@ struct TracedN {
   Ray<V> pre;
   V x, y;
   bool ok[LaneCount<V>::value], backward[LaneCount<V>::value];
+  unsigned ok_bits[LaneCount<V>::value][2];   // trace_guarded<.., BITS = true> only: ok / equator bits
 };
 
 // Guarded policy: contracted (and, for f2/f4, packed) fast path for all lanes; each
 // lane that was not clearly good everywhere is then re-traced alone with the exact
 // policy, overwriting its lane of the parked states.
-template <bool SAVE, class V>
+template <bool SAVE, class V, bool BITS = false>
 __device__ __forceinline__ TracedN<V> trace_guarded(V x, V y, V z, V cx, V cy, const Table &tab,
                                                     int S, bool allow_backward, int arith,
                                                     V *state, int stride) {
@@ -181,6 +191,8 @@ __device__ __forceinline__ TracedN<V> trace_guarded(V x, V y, V z, V cx, V cy, c
       fast_surface(r, V(tab.c[k]), V(tab.mu[k]), V(tab.mu2[k]), V(tab.t[k]), min_cos2, travel);
       park<SAVE, V>(state, stride, k, r.x, r.y, in_cx, in_cy);
       if (k > 0 && tab.live[k - 1]) min_travel = fmin2(min_travel, travel);
+      // BITS: a fast-path ray carries no branch bits, so it must be clear of the equator too
+      if (BITS) min_cos2 = fmin2(min_cos2, ffma(-V(tab.c[k]), r.z + V(tab.t[k]), V(1.0f)));
     }
     out.pre = r;
     const V travel = fast_image(r);
@@ -199,10 +211,15 @@ __device__ __forceinline__ TracedN<V> trace_guarded(V x, V y, V z, V cx, V cy, c
   for (int l = 0; l < N; ++l) {
     out.ok[l] = true;
     out.backward[l] = false;
+    if (BITS) {
+      out.ok_bits[l][0] = 0xffffffffu;
+      out.ok_bits[l][1] = 0u;
+    }
     if (!clear[l]) {
-      const Traced one = trace_exact<SAVE>(lane_get(x, l), lane_get(y, l), lane_get(z, l),
-                                           lane_get(cx, l), lane_get(cy, l), tab, S, allow_backward,
-                                           reinterpret_cast<float *>(state) + l, N * stride);
+      const Traced one = trace_exact<SAVE, BITS>(lane_get(x, l), lane_get(y, l), lane_get(z, l),
+                                                 lane_get(cx, l), lane_get(cy, l), tab, S, allow_backward,
+                                                 reinterpret_cast<float *>(state) + l, N * stride,
+                                                 BITS ? out.ok_bits[l] : nullptr);
       lane_set(out.pre.x, l, one.pre.x);
       lane_set(out.pre.y, l, one.pre.y);
       lane_set(out.pre.z, l, one.pre.z);
@@ -295,6 +312,87 @@ k_trace_fwd(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
   }
 }
 
+// K1b: trace_skew(aggregate=True): the forward trace that also writes the three penalty stacks
+// z_RELU, theta_norm, theta_prime_norm of every surface (rtl:641-657) as [S,B,F,P,W] arrays.
+// One ray per thread: the kernel is bound by its 12 S + 18 bytes of stores per ray, not by math.
+// Guarded policy: the fast path writes its stacks as it goes; a ray that was not clearly good is
+// re-traced with the exact policy, which overwrites them.
+__global__ void __launch_bounds__(kFwdThreads)
+k_trace_fwd_pen(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
+  extern __shared__ float smem[];
+  int blk = blockIdx.x;
+  const int chunk = blk % nchunks; blk /= nchunks;
+  const int w = blk % pb.W; blk /= pb.W;
+  const int f = blk % pb.F;
+  const int b = blk / pb.F;
+  const int S = pb.S;
+  const Table tab = load_table(smem, pb, b, w);
+  const int p_lo = chunk * chunk_len;
+  const int p_hi = min(pb.P, p_lo + chunk_len);
+  const bool allow_backward = pb.allow_backward_rays != 0;
+  const int64_t plane = (int64_t)pb.B * pb.F * pb.P * pb.W;
+  const float xy_scale = pb.xy_scale ? pb.xy_scale[b] : 1.0f;
+  for (int p = p_lo + threadIdx.x; p < p_hi; p += kFwdThreads) {
+    float x = pb.x.ptr[offset_of(pb.x, b, f, p, w)];
+    float y = pb.y.ptr[offset_of(pb.y, b, f, p, w)];
+    if (pb.xy_scale) {
+      x = __fmul_rn(x, xy_scale);
+      y = __fmul_rn(y, xy_scale);
+    }
+    const float z = pb.z.ptr[offset_of(pb.z, b, f, p, w)];
+    const float cx = pb.cx.ptr[offset_of(pb.cx, b, f, p, w)];
+    const float cy = pb.cy.ptr[offset_of(pb.cy, b, f, p, w)];
+    const int64_t o = (((int64_t)b * pb.F + f) * pb.P + p) * pb.W + w;
+    bool clear = false;
+    if (pb.arith == TL_ARITH_GUARDED) {
+      Ray<float> r{x, y, z, cx, cy, fast_cz0(cx, cy)};
+      float min_cos2 = 1.0f, min_travel = 3.0e38f;
+      for (int k = 0; k < S; ++k) {
+        float travel, ci, co;
+        fast_surface(r, tab.c[k], tab.mu[k], tab.mu2[k], tab.t[k], min_cos2, travel, ci, co);
+        if (k > 0 && tab.live[k - 1]) min_travel = fminf(min_travel, travel);
+        out.z_relu[k * plane + o] = r.z <= 0.0f ? 0.0f : r.z;
+        out.theta[k * plane + o] = fast_angle_norm(ci);
+        out.theta_prime[k * plane + o] = fast_angle_norm(co);
+      }
+      const float pre_cx = r.cx, pre_cy = r.cy;
+      const float travel = fast_image(r);
+      if (tab.live[S - 1]) min_travel = fminf(min_travel, travel);
+      const float band = kBandTravelRel * fmaxf(1.0f, tab.length + fabsf(z));
+      clear = (min_cos2 > kGuard + kBandCos2) && (min_travel > band) &&
+              (fabsf((r.x + r.y) + (pre_cx + pre_cy)) < 3.0e38f);
+      if (clear) {
+        out.x[o] = r.x;
+        out.y[o] = r.y;
+        out.cx[o] = pre_cx;
+        out.cy[o] = pre_cy;
+        out.ok[o] = 1;
+        out.backward[o] = 0;
+      }
+    }
+    if (!clear) {
+      Ray<float> r{x, y, z, cx, cy, exact_cz0(cx, cy)};
+      bool ok = true, backward = false;
+      for (int k = 0; k < S; ++k) {
+        const Surface s{tab.c[k], tab.t[k], tab.mu[k]};
+        Penalty pen;
+        exact_surface_t<true>(r, s, k > 0 && tab.live[k - 1], allow_backward, ok, backward, &pen);
+        out.z_relu[k * plane + o] = pen.z_relu;
+        out.theta[k * plane + o] = pen.theta;
+        out.theta_prime[k * plane + o] = pen.theta_prime;
+      }
+      const float pre_cx = r.cx, pre_cy = r.cy;
+      exact_image(r, tab.live[S - 1] != 0, allow_backward, ok, backward);
+      out.x[o] = r.x;
+      out.y[o] = r.y;
+      out.cx[o] = pre_cx;
+      out.cy[o] = pre_cy;
+      out.ok[o] = ok;
+      out.backward[o] = backward;
+    }
+  }
+}
+
 // Reference height of every (lens, field): the image height of the chief ray (pupil
 // centre) at wavelength 0, traced with the fast policy.  The spot sums are centred on
 // it; any value near the centroid does (it cancels exactly in k_spot_finalize), it only
@@ -342,7 +440,11 @@ struct AdjArgs {
 #define TL_ADJ_MIN_BLOCKS 1
 #endif
 
-template <int NS_MAX, int MODE, class V>
+// PEN (MODE_BWD only): the caller also seeds the aggregate=True stacks (z_RELU, theta_norm,
+// theta_prime_norm of every surface, rtl:641-657).  A ray that fails at surface j still feeds the
+// stacks of the surfaces in front of j, so the sweep runs per-lane on "ok behind surface k" bits
+// instead of the final ok flag, and lanes that are not ok are forced to exact zeros (no mirroring).
+template <int NS_MAX, int MODE, class V, bool PEN = false>
 __global__ void __launch_bounds__(kTraceThreads, TL_ADJ_MIN_BLOCKS)
 k_trace_adj(TlProblem pb, AdjArgs args) {
   extern __shared__ float smem[];
@@ -461,8 +563,8 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
       lane_set(cy, l, pb.cy.ptr[offset_of(pb.cy, b, f, q, w)]);
     }
     if (p_base >= pb.p_end) continue;   // whole thread past the end of the row
-    TracedN<V> tr = trace_guarded<kAdjoint, V>(x, y, z, cx, cy, tab, S, allow_backward, pb.arith,
-                                               state, stride);
+    TracedN<V> tr = trace_guarded<kAdjoint, V, PEN>(x, y, z, cx, cy, tab, S, allow_backward, pb.arith,
+                                                    state, stride);
     bool live[N], any_live = false, all_ok = true;
     V alive, wgt(0.f);
 #pragma unroll
@@ -483,8 +585,18 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
     }
     if (kAdjoint) {
       Ray<V> a{V(0.f), V(0.f), V(0.f), V(0.f), V(0.f), V(0.f)};
-      if (any_live) {
-        if (!all_ok) mirror_live_lane<V>(state, stride, S, tr.ok, tr.pre, z, tr.x, tr.y);
+      unsigned bits[N], flips[N];
+      bool any_bits = false;
+      if (PEN) {
+#pragma unroll
+        for (int l = 0; l < N; ++l) {
+          bits[l] = has[l] ? tr.ok_bits[l][0] : 0u;
+          flips[l] = tr.ok_bits[l][1];
+          any_bits = any_bits || bits[l] != 0u || (has[l] && args.seeds.gz_relu != nullptr);
+        }
+      }
+      if (any_live || (PEN && any_bits)) {
+        if (!PEN && !all_ok) mirror_live_lane<V>(state, stride, S, tr.ok, tr.pre, z, tr.x, tr.y);
         V sx(0.f), sy(0.f), scx(0.f), scy(0.f);
         if (MODE == MODE_SPOT_GRAD) {
           sy = alive;
@@ -503,9 +615,42 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
         for (int k = NS_MAX - 1; k >= 0; --k) {
           if (k >= S) continue;
           const V *slot = state + (size_t)k * 4 * stride;
-          const SurfaceGrad<V> g = sweep_sphere(sw, slot[0], slot[stride], slot[2 * stride],
-                                                slot[3 * stride], V(tab.c[k]), V(tab.t[k]),
-                                                V(tab.mu[k]), V(tab.mu2[k]));
+          SurfaceGrad<V> g;
+          if constexpr (PEN) {
+            // seeds of this surface's stacks ([S,B,F,P,W]); only lanes ok behind surface k carry
+            // angle seeds, and their z_RELU seed enters through the hit point
+            const int64_t plane = (int64_t)pb.B * pb.F * pb.P * pb.W;
+            V pz(0.f), pth(0.f), pthp(0.f), branch(1.0f);
+            float dead_gt[N];
+#pragma unroll
+            for (int l = 0; l < N; ++l) {
+              dead_gt[l] = 0.f;
+              if ((flips[l] >> k) & 1u) lane_set(branch, l, -1.0f);
+              if (!has[l]) continue;
+              const int64_t at = (int64_t)k * plane + o[l];
+              if ((bits[l] >> k) & 1u) {
+                if (args.seeds.gz_relu) lane_set(pz, l, args.seeds.gz_relu[at]);
+                if (args.seeds.gtheta) lane_set(pth, l, args.seeds.gtheta[at]);
+                if (args.seeds.gtheta_prime) lane_set(pthp, l, args.seeds.gtheta_prime[at]);
+              } else if (args.seeds.gz_relu && -tab.t[k] > 0.f) {
+                dead_gt[l] = -args.seeds.gz_relu[at];     // a failed ray sits at z = 0 - t[k] (rtl:639)
+              }
+            }
+            g = sweep_sphere_pen(sw, slot[0], slot[stride], slot[2 * stride], slot[3 * stride],
+                                 V(tab.c[k]), V(tab.t[k]), V(tab.mu[k]), V(tab.mu2[k]), pz, pth, pthp, branch);
+#pragma unroll
+            for (int l = 0; l < N; ++l) {
+              if ((bits[l] >> k) & 1u) continue;
+              lane_set(g.c, l, 0.f);
+              lane_set(g.mu, l, 0.f);
+              lane_set(g.t, l, dead_gt[l]);
+              lane_set(sw.gr.x, l, 0.f); lane_set(sw.gr.y, l, 0.f); lane_set(sw.gr.z, l, 0.f);
+              lane_set(sw.gd.x, l, 0.f); lane_set(sw.gd.y, l, 0.f); lane_set(sw.gd.z, l, 0.f);
+            }
+          } else {
+            g = sweep_sphere(sw, slot[0], slot[stride], slot[2 * stride], slot[3 * stride],
+                             V(tab.c[k]), V(tab.t[k]), V(tab.mu[k]), V(tab.mu2[k]));
+          }
           acc_c[k] += lane_sum(g.c);
           acc_t[k] += lane_sum(g.t);
           acc_mu[k] += lane_sum(g.mu);
@@ -984,8 +1129,22 @@ AdjKernel adj_kernel_for(int S) {
   }
 }
 
-AdjVariant select_adj(int mode, int S) {
+// MODE_BWD with seeds on the aggregate=True stacks: two rays per thread
+AdjKernel pen_kernel_for(int S) {
+  if (S <= 4) return k_trace_adj<4, MODE_BWD, f2, true>;
+  if (S <= 8) return k_trace_adj<8, MODE_BWD, f2, true>;
+  if (S <= 12) return k_trace_adj<12, MODE_BWD, f2, true>;
+  if (S <= 16) return k_trace_adj<16, MODE_BWD, f2, true>;
+  return k_trace_adj<32, MODE_BWD, f2, true>;
+}
+
+AdjVariant select_adj(int mode, int S, bool pen = false) {
   AdjVariant v;
+  if (pen && mode == MODE_BWD) {
+    v.lanes = v.state_lanes = 2;
+    v.kernel = pen_kernel_for(S);
+    return v;
+  }
   v.lanes = pick_lanes(mode, S);
   if (mode == MODE_SPOT_EVAL) {
     v.kernel = adj_kernel_for<MODE_SPOT_EVAL, f4>(S);
@@ -1009,11 +1168,11 @@ struct AdjPlan {
 
 size_t align8(size_t v) { return (v + 7) & ~(size_t)7; }
 
-int plan_adj(const TlProblem &pb, int mode, AdjPlan &pl) {
+int plan_adj(const TlProblem &pb, int mode, AdjPlan &pl, bool pen = false) {
   DeviceInfo info;
   int rc = device_info(info);
   if (rc) return rc;
-  pl.variant = select_adj(mode, pb.S);
+  pl.variant = select_adj(mode, pb.S, pen);
   pl.n_acc = n_acc_of(mode, pb.S);
   const int lanes = pl.variant.lanes;
   const size_t table = ((5 * (size_t)pb.S + 3) & ~(size_t)3) * sizeof(float);
@@ -1117,6 +1276,19 @@ int tl_trace_fwd(const TlProblem *pb, const TlTraceOut *out, void *stream_) {
   DeviceInfo info;
   rc = device_info(info);
   if (rc) return rc;
+  const bool stacks = out->z_relu || out->theta || out->theta_prime;
+  if (stacks && !(out->z_relu && out->theta && out->theta_prime))
+    return fail(TL_ERR_INVALID, "the three aggregate=True stacks come together: z_relu, theta, theta_prime%s");
+  if (stacks && is_general(*pb))
+    return fail(TL_ERR_INVALID, "the aggregate=True stacks exist for spherical lenses only (not with k / a / sd)%s");
+  if (stacks) {
+    const FwdPlan pp = make_fwd_plan(info.sms, pb->B * pb->F * pb->W, pb->P, kFwdThreads, 4);
+    k_trace_fwd_pen<<<pp.n_blocks, kFwdThreads, 5 * (size_t)pb->S * sizeof(float), (cudaStream_t)stream_>>>(
+        *pb, *out, pp.nchunks, pp.chunk_len);
+    g_launches++;
+    TL_CHECK_CUDA(cudaGetLastError());
+    return TL_OK;
+  }
   const FwdPlan pl = make_fwd_plan(info.sms, pb->B * pb->F * pb->W, pb->P, 2 * kFwdThreads, 4);
   if (is_general(*pb)) {
     const size_t smem = (14 * (size_t)pb->S + 2) * sizeof(float);
@@ -1147,9 +1319,10 @@ size_t tl_trace_bwd_workspace(const TlProblem *pb) {
   TlProblem full = *pb;
   full.p_begin = 0;
   full.p_end = pb->P;
-  AdjPlan pl;
-  if (plan_adj(full, MODE_BWD, pl)) return 0;
-  return pl.partial_bytes + align8((size_t)pb->B * pb->F * pb->W * pl.n_acc * sizeof(double));
+  AdjPlan pl, pl_pen;
+  if (plan_adj(full, MODE_BWD, pl) || plan_adj(full, MODE_BWD, pl_pen, true)) return 0;
+  const size_t partial = pl.partial_bytes > pl_pen.partial_bytes ? pl.partial_bytes : pl_pen.partial_bytes;
+  return partial + align8((size_t)pb->B * pb->F * pb->W * pl.n_acc * sizeof(double));
 }
 
 int tl_trace_bwd(const TlProblem *pb_, const TlSeeds *seeds, const TlGrads *grads, void *workspace,
@@ -1159,6 +1332,8 @@ int tl_trace_bwd(const TlProblem *pb_, const TlSeeds *seeds, const TlGrads *grad
   if (!seeds || !grads || !grads->gc || !grads->gt || !grads->gmu || !grads->gz_sum)
     return fail(TL_ERR_INVALID, "NULL seeds/grads%s");
   if (is_general(*pb_)) {
+    if (seeds->gz_relu || seeds->gtheta || seeds->gtheta_prime)
+      return fail(TL_ERR_INVALID, "the aggregate=True stacks exist for spherical lenses only (no seeds on them with k / a / sd)%s");
     if (!grads->gk || !grads->ga) return fail(TL_ERR_INVALID, "general-surface lens: gk and ga are required%s");
     TlProblem pb = *pb_;
     pb.p_begin = 0;
@@ -1199,8 +1374,9 @@ int tl_trace_bwd(const TlProblem *pb_, const TlSeeds *seeds, const TlGrads *grad
   TlProblem pb = *pb_;
   pb.p_begin = 0;
   pb.p_end = pb.P;
+  const bool pen = seeds->gz_relu || seeds->gtheta || seeds->gtheta_prime;
   AdjPlan pl;
-  rc = plan_adj(pb, MODE_BWD, pl);
+  rc = plan_adj(pb, MODE_BWD, pl, pen);
   if (rc) return rc;
   const int rows = pb.B * pb.F * pb.W;
   const size_t rows_bytes = align8((size_t)rows * pl.n_acc * sizeof(double));

@@ -98,8 +98,15 @@ def _ptr(t):
 class _TraceSkew(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays, arith, k=None, a=None,
-                sd=None):
+                sd=None, aggregate=False):
         lay = _Layout(x, y, z, cx, cy, c, t, mu, mask, k, a, sd)
+        ctx.set_materialize_grads(False)      # unused outputs arrive as None, not as zero tensors
+        ctx.aggregate = bool(aggregate)
+        if aggregate and lay.general:
+            raise ValueError('aggregate=True (the penalty stacks of rtl:641-657) exists for spherical '
+                             'lenses only, not with the extension tables k / a / sd')
+        if aggregate and lay.S > nat.MAX_SURFACES_BWD and any(ctx.needs_input_grad[:8]):
+            raise ValueError(f'differentiable aggregate=True supports at most {nat.MAX_SURFACES_BWD} surfaces')
         if lay.general:
             ctx.save_for_backward(x, y, z, cx, cy, c, t, mu, mask,
                                   *(v for v in (k, a, sd) if v is not None))
@@ -114,13 +121,18 @@ class _TraceSkew(torch.autograd.Function):
             ok = torch.empty(lay.shape, dtype=torch.bool, device=lay.device)
             backward = torch.empty(lay.shape, dtype=torch.bool, device=lay.device)
             pb = lay.problem(allow_backward_rays, arith)
-            out = nat.TlTraceOut(*[o.data_ptr() for o in outs], ok.data_ptr(), backward.data_ptr(), None)
+            stacks = []
+            if aggregate:      # z_RELU, theta_norm, theta_prime_norm of every surface: [S,B,F,P,W]
+                stacks = [torch.empty((lay.S,) + lay.shape, dtype=torch.float32, device=lay.device)
+                          for _ in range(3)]
+            out = nat.TlTraceOut(*[o.data_ptr() for o in outs], ok.data_ptr(), backward.data_ptr(), None,
+                                 *[v.data_ptr() for v in stacks])
             nat.check(lib.tl_trace_fwd(ctypes.byref(pb), ctypes.byref(out), nat.stream_ptr(lay.device)),
                       'tl_trace_fwd')
         ctx.save_for_backward(x, y, z, cx, cy, c, t, mu, mask)
         ctx.flags = (allow_backward_rays, arith)
         ctx.mark_non_differentiable(ok, backward)
-        return (*outs, ok, backward)
+        return (*outs, ok, backward, *stacks)
 
     @staticmethod
     def _forward_general(ctx, lay, allow_backward_rays, arith):
@@ -142,8 +154,9 @@ class _TraceSkew(torch.autograd.Function):
         return (*outs, ok, backward, opl)
 
     @staticmethod
-    def backward(ctx, gx, gy, gcx, gcy, _gok, _gbw, *_gopl):
+    def backward(ctx, gx, gy, gcx, gcy, _gok, _gbw, *extra_grads):
         saved = ctx.saved_tensors
+        stack_grads = extra_grads if ctx.aggregate else (None, None, None)
         k = a = sd = None
         if getattr(ctx, 'general', False):
             extra = list(saved[9:])
@@ -173,7 +186,9 @@ class _TraceSkew(torch.autograd.Function):
                 if need[i] and not (name == 'z' and z_per_lens):
                     per_ray[name] = torch.empty(lay.shape, dtype=torch.float32, device=dev)
             pb = lay.problem(allow_backward_rays, arith)
-            sd = nat.TlSeeds(*[_ptr(s) for s in seeds])
+            stack_seeds = [None if g is None else
+                           g.to(torch.float32).expand((lay.S,) + lay.shape).contiguous() for g in stack_grads]
+            sd = nat.TlSeeds(*[_ptr(s) for s in seeds], *[_ptr(s) for s in stack_seeds])
             gk = ga = None
             if lay.general:
                 gk = torch.empty_like(gc)
@@ -203,13 +218,18 @@ class _TraceSkew(torch.autograd.Function):
             g_k = gk.reshape(lay.B, 1, 1, 1, lay.S).sum_to_size(k.shape)
         if lay.general and a is not None and need[12]:
             g_a = ga.reshape(lay.B, 1, 1, 1, lay.S, -1).sum_to_size(a.shape)
-        return (*grads, None, None, None, g_k, g_a, None)
+        return (*grads, None, None, None, g_k, g_a, None, None)
+
+
+STACK_KEYS = ('z_RELU', 'theta_norm', 'theta_prime_norm')      # rtl:598
 
 
 def trace(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arith=nat.ARITH_GUARDED,
-          k=None, a=None, sd=None):
+          k=None, a=None, sd=None, aggregate=False):
     """CUDA ``trace_skew``: returns (x, y, cx, cy, ray_ok, ray_backward), all [B,F,P,W]; with any of
-    the extension tables k / a / sd also the optical path length as a 7th output."""
+    the extension tables k / a / sd also the optical path length as a 7th output; with
+    ``aggregate=True`` (rtl:641-657) a 7th output ``stacks``: a dict of three S-long lists of
+    [B,F,P,W] tensors (views of one [S,B,F,P,W] tensor per key), differentiable like the rest."""
     full = torch.broadcast_shapes(x.shape, y.shape, z.shape, cx.shape, cy.shape, c.shape[:-1],
                                   t.shape[:-1], mu.shape[:-1], mask.shape[:-1])
     if 0 in full:       # empty ray set: nothing to launch, same (empty) results as the reference
@@ -219,9 +239,15 @@ def trace(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arith=nat.A
         outs = [zero.expand(full).clone() for _ in range(4)]
         flags = [torch.zeros(full, dtype=torch.bool, device=y.device) for _ in range(2)]
         flags[0] = ~flags[0]
+        if aggregate:
+            S = t.shape[-1]
+            return (*outs, *flags, {key: [zero.expand(full).clone() for _ in range(S)] for key in STACK_KEYS})
         return (*outs, *flags)
-    return _TraceSkew.apply(x, y, z, cx, cy, c, t, mu, mask, bool(allow_backward_rays), int(arith),
-                            k, a, sd)
+    res = _TraceSkew.apply(x, y, z, cx, cy, c, t, mu, mask, bool(allow_backward_rays), int(arith),
+                           k, a, sd, bool(aggregate))
+    if aggregate:
+        return (*res[:6], {key: list(res[6 + i].unbind(0)) for i, key in enumerate(STACK_KEYS)})
+    return res
 
 
 class _RmsFromRays(torch.autograd.Function):

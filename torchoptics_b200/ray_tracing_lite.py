@@ -224,12 +224,17 @@ def trace_skew(x, y, z, cx, cy, c, t, mu, mask, aggregate=False, allow_backward_
     semi-diameters.  With any of them the surfaces are intersected by Newton
     iteration, rays outside ``sd`` fail, and a 7th output, the optical path length
     [B,F,P,W] (not differentiable), is returned; gradients also flow to ``k`` and ``a``.
+
+    ``aggregate=True`` (rtl:641-657, spherical lenses): also returns ``stacks``, the dict of
+    per-surface penalty terms ``z_RELU``, ``theta_norm``, ``theta_prime_norm`` (S-long lists of
+    [B,F,P,W] tensors) that ``compute_loss_out`` sums into its penalty Q
+    (optics_simulator_lite.py:430-450).  Unlike the reference it accepts un-broadcast pupil grids
+    with W > 1 (rtl:653 raises there) and its gradients stay finite when rays fail (the
+    reference's turn NaN: it takes the square root of a failed ray's negative cos^2 before
+    masking it); failed rays contribute 0.
     """
-    if aggregate:
-        raise NotImplementedError(
-            'aggregate=True (per-surface penalty stacks, rtl:641-657) is not part of the CUDA '
-            'hot path yet')
-    return ops.trace(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays, _arith_code(arith), k, a, sd)
+    return ops.trace(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays, _arith_code(arith), k, a, sd,
+                     aggregate=aggregate)
 
 
 def compute_rms2d(x, y, ray_ok):
