@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TL_ABI_VERSION 6
+#define TL_ABI_VERSION 7
 
 enum {
   TL_OK = 0,
@@ -171,6 +171,27 @@ int tl_spot_accumulate(const TlProblem *pb, int32_t want_grad, double *moments, 
 int tl_spot_finalize(const double *moments, const float *ref_y, int32_t B, int32_t F, int32_t W,
                      int32_t S, int64_t P_total, int32_t want_grad, const TlSpotOut *out,
                      void *stream);
+
+/* Fused penalty pass: value and gradient of the ray-angle / ray-path penalty that compute_loss_out
+ * (optics_simulator_lite.py:430-450) builds from trace_skew(aggregate=True):
+ *     penalty[b] = scale * sum over rays and surfaces of (theta_norm + theta_prime_norm + z_RELU),
+ * scale = 1 / numSequence, as ONE pass that materialises no stack (the reference stacks 3 S
+ * [B,F,P,W] tensors).  Like the spot pass it is split so that ranks can shard the pupil:
+ * tl_penalty_accumulate traces the slice [p_begin,p_end) and leaves sums that are additive over
+ * slices in `moments` ([B,F,W,tl_penalty_moment_count(S)] doubles; all-reduce them);
+ * tl_penalty_finalize turns them into the penalty and d penalty / d{c, t, mu, z}.  Failed rays
+ * count as the reference counts them (theta = theta' = 1, z = -t) and contribute no gradient
+ * (the reference's gradient is NaN there, see TlSeeds). */
+typedef struct TlPenaltyOut {
+  float *penalty;              /* [B]                                                */
+  float *gc, *gt, *gmu, *gz;   /* [B,S], [B,S], [B,W,S], [B]                          */
+} TlPenaltyOut;
+int32_t tl_penalty_moment_count(int32_t S);
+size_t tl_penalty_workspace(const TlProblem *pb);
+int tl_penalty_accumulate(const TlProblem *pb, double *moments, void *workspace, size_t workspace_bytes,
+                          void *stream);
+int tl_penalty_finalize(const double *moments, int32_t B, int32_t F, int32_t W, int32_t S, double scale,
+                        const TlPenaltyOut *out, void *stream);
 
 /* Ray-set staging of RayTracer.trace_rays (rtl:80-124) and its chain rule, as two small
  * kernels instead of ~60 eager tensor ops: the two-term dispersion model n(lambda) of

@@ -76,9 +76,10 @@ def _worker(rank, world, port, out_dir):
     def evaluate(shard, group):
         leaves = [getattr(lens, k).detach().clone().requires_grad_(True) for k in ('c', 't', 'nd', 'v')]
         from torchoptics_b200.lens_modeling import Lens
-        rms, _ = tracer.spot_rms(specs, Lens(lens.structure, *leaves), shard=shard, group=group)
-        grads = torch.autograd.grad(rms.sum(), leaves)
-        return torch.cat([rms.detach().reshape(-1)] + [x.reshape(-1) for x in grads])
+        res = tracer.loss_unsup(specs, Lens(lens.structure, *leaves), shard=shard, group=group)
+        grads = torch.autograd.grad(res['loss_unsup'].sum(), leaves)     # spot pass + penalty pass
+        return torch.cat([res['rms'].detach().reshape(-1), res['penalty'].detach().reshape(-1)] +
+                         [x.reshape(-1) for x in grads])
 
     via_peer = evaluate((rank, world), ex)
     via_nccl = evaluate((rank, world), None)

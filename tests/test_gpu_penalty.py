@@ -240,3 +240,91 @@ def test_large_pupil_penalty_matches_oracle_on_device():
         bar = max(GRAD_TOL, 1.5 * _rel(c32.cpu().numpy(), b.cpu().numpy()))
         assert bar <= 1e-3
         assert _rel(a.cpu().numpy(), b.cpu().numpy()) <= bar, (label, bar)
+
+
+@pytest.mark.parametrize('arith', ['guarded', 'exact'])
+@pytest.mark.parametrize('name', AGG_CASES)
+def test_fused_penalty_pass_matches_reference_and_unfused(name, arith):
+    """ops.penalty_sum: value and gradients of sum(Q) in one pass with no stacks, against the
+    reference's number (golden), the fp64 oracle, and the unfused aggregate=True path; sharded over
+    two pupil slices the sums add up to the same result."""
+    from torchoptics_b200 import _native, ops
+    rec, agg = load_aggregate(name)
+    allow = bool(rec['allow_backward_rays'])
+    n_seq = int(agg['n_seq'])
+    names = ('z', 'c', 't', 'mu')
+    code = _native.ARITH_EXACT if arith == 'exact' else _native.ARITH_GUARDED
+    i = _inputs(rec, DEV, broadcast=False, grad=names)
+    pen = ops.penalty_sum(*_args(i), n_seq, allow, code)
+    assert pen.shape == (1,)
+    assert abs(float(pen[0]) - float(agg['penalty'])) <= 2e-5 * abs(float(agg['penalty']))
+    got = torch.autograd.grad(pen[0], [i[k] for k in names])
+    # unfused path of this package
+    j = _inputs(rec, DEV, broadcast=False, grad=names)
+    out = rt.trace_skew(*_args(j), aggregate=True, allow_backward_rays=allow, arith=arith)
+    _, pen_u = _loss(out, False, n_seq)
+    unfused = torch.autograd.grad(pen_u, [j[k] for k in names])
+    assert abs(float(pen[0]) - float(pen_u)) <= 2e-6 * abs(float(pen_u))
+    group = np.linalg.norm(np.concatenate([unfused[0].cpu().numpy().ravel(), unfused[2].cpu().numpy().ravel()]))
+    for k, a, b in zip(names, got, unfused):
+        a, b = a.cpu().numpy().astype(np.float64), b.cpu().numpy().astype(np.float64)
+        scale = group if k == 'z' else np.linalg.norm(b)
+        assert np.linalg.norm(a - b) <= 2e-5 * scale, (k, 'fused vs unfused')
+    # fp64 oracle (fp32 clamp constant, finite gradients)
+    cpu = _inputs(rec, 'cpu', broadcast=True, grad=names, dtype=torch.float64)
+    with oracle.finite_penalty_gradients(), oracle.fp32_clamp_bound():
+        ref = oracle.trace(*_args(cpu), True, allow)
+    if torch.equal(ref[4], torch.from_numpy(rec['out_ok'])):
+        _, pen64 = _loss(ref, True, n_seq)
+        want = torch.autograd.grad(pen64, [cpu[k] for k in names])
+        assert abs(float(pen[0]) - float(pen64)) <= 2e-5 * abs(float(pen64))
+        group64 = np.linalg.norm(np.concatenate([want[0].numpy().ravel(), want[2].numpy().ravel()]))
+        for k, a, b in zip(names, got, want):
+            a, b = a.cpu().numpy().astype(np.float64), b.numpy()
+            scale = group64 if k == 'z' else np.linalg.norm(b)
+            assert np.linalg.norm(a - b) <= GRAD_TOL * scale, (k, 'fused vs fp64 oracle')
+    # two pupil slices: additive moments -> same numbers
+    P = rec['out_ok'].shape[2]
+    if P >= 2:
+        parts = []
+        for rank in range(2):
+            lo, hi = ops.pupil_slice(P, rank, 2)
+            s = _inputs(rec, DEV, broadcast=True, grad=names)
+            for key in ('x', 'y', 'cx', 'cy'):
+                s[key] = s[key][:, :, lo:hi].contiguous()
+            p_r = ops.penalty_sum(*_args(s), n_seq, allow, code)
+            parts.append((p_r, torch.autograd.grad(p_r[0], [s[k] for k in names])))
+        assert abs(float(parts[0][0] + parts[1][0]) - float(pen[0])) <= 2e-6 * abs(float(pen[0]))
+        for idx, k in enumerate(names):
+            both = parts[0][1][idx] + parts[1][1][idx]
+            scale = group if k == 'z' else float(got[idx].norm())
+            assert float((both - got[idx]).norm()) <= 2e-5 * scale, (k, 'sliced')
+
+
+def test_loss_unsup_front_end_matches_compute_loss_out():
+    """RayTracer.loss_unsup == the reference's compute_loss_out numbers on the Cooke triplet
+    (rms 0.01862689, golden penalty), with gradients w.r.t. the lens through the front end."""
+    from torchoptics_b200 import lens_modeling as lm
+    from tests.conftest import load_golden
+    golden = load_golden('cooke_8x8')
+    _, agg = load_aggregate('cooke_8x8')
+    structure = lm.Structure(golden['stop_idx'], sequence=golden['sequence'], default_device=DEV)
+    lens = lm.Lens(structure, *[torch.from_numpy(golden[k]).to(DEV).requires_grad_(True)
+                                for k in ('lens_c', 'lens_t', 'lens_nd', 'lens_v')])
+    specs = lm.Specs(structure, torch.from_numpy(golden['epd']).to(DEV), torch.from_numpy(golden['hfov']).to(DEV))
+    tracer = rt.RayTracer(mode='circular', n_rays=(8, 8), rel_fields=(0., 0.707, 1.), wavelengths=('C', 'd', 'F'),
+                          default_device=DEV)
+    res = tracer.loss_unsup(specs, lens, penalty_rate=PENALTY_RATE)
+    assert abs(float(res['rms'][0]) - float(agg['rms'])) <= 1e-5 * float(agg['rms'])
+    assert abs(float(res['penalty'][0]) - float(agg['penalty'])) <= 2e-5 * float(agg['penalty'])
+    want = float(agg['rms']) + PENALTY_RATE * float(agg['penalty'])
+    assert abs(float(res['loss_unsup'][0]) - want) <= 2e-5 * want
+    grads = torch.autograd.grad(res['loss_unsup'][0], [lens.c, lens.t, lens.nd])
+    # the same loss through the unfused API
+    lens2 = lm.Lens(structure, *[torch.from_numpy(golden[k]).to(DEV).requires_grad_(True)
+                                 for k in ('lens_c', 'lens_t', 'lens_nd', 'lens_v')])
+    out = tracer.trace_rays(specs, lens2, aggregate=True)
+    rms, pen = _loss(out, False, int(agg['n_seq']))
+    ref = torch.autograd.grad(rms + PENALTY_RATE * pen, [lens2.c, lens2.t, lens2.nd])
+    for a, b in zip(grads, ref):
+        assert _rel(a.cpu().numpy(), b.cpu().numpy()) <= GRAD_TOL

@@ -62,6 +62,10 @@ class TlLens(ctypes.Structure):
                [(n, ctypes.c_int32) for n in ('B', 'L', 'F', 'W')]
 
 
+class TlPenaltyOut(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ('penalty', 'gc', 'gt', 'gmu', 'gz')]
+
+
 class TlSpotOut(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ('rms', 'rms_field', 'gc', 'gt', 'gmu', 'gz', 'gk', 'ga')]
 
@@ -91,6 +95,12 @@ EXPORTS = {
     'tl_stage_bwd': (ctypes.c_int, [ctypes.POINTER(TlLens)] + [ctypes.c_void_p] * 7),
     'tl_spot_finalize': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int32] * 4 +
                          [ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(TlSpotOut), ctypes.c_void_p]),
+    'tl_penalty_moment_count': (ctypes.c_int32, [ctypes.c_int32]),
+    'tl_penalty_workspace': (ctypes.c_size_t, [ctypes.POINTER(TlProblem)]),
+    'tl_penalty_accumulate': (ctypes.c_int, [ctypes.POINTER(TlProblem), ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_size_t, ctypes.c_void_p]),
+    'tl_penalty_finalize': (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int32] * 4 +
+                            [ctypes.c_double, ctypes.POINTER(TlPenaltyOut), ctypes.c_void_p]),
     'tl_peer_handle_bytes': (ctypes.c_size_t, []),
     'tl_peer_create': (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int64,
                                       ctypes.POINTER(ctypes.c_void_p), ctypes.c_void_p]),
@@ -119,7 +129,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.tl_abi_version() != 6:
+    if lib.tl_abi_version() != 7:
         raise NativeLibraryError('libtorchoptics_b200.so: ABI version mismatch, rebuild it')
     _lib = lib
     return lib

@@ -479,9 +479,12 @@ TL_HD f4 keep_pos(f4 cond, f4 v) { return f4(keep_pos(cond.a, v.a), keep_pos(con
 // oblique rays): there n_z = 1 - c h_z = -sqrt(1 - c^2 rho), which the parked (hx, hy) alone cannot
 // tell.  (sweep_sphere assumes +1: a ray with such a hit that still reaches the image is outside
 // its validity; the penalty terms exist to punish exactly such rays, so this one carries the sign.)
+// Also hands back the three quantities the terms are made of -- cos(theta), cos(theta') as the
+// reference forms them and z' = h_z - t -- for callers that accumulate the penalty value itself.
 template <class T>
 TL_HD SurfaceGrad<T> sweep_sphere_pen(Sweep<T> &s, T hx, T hy, T dx, T dy, T c, T t, T mu, T mu2,
-                                      T pz, T pth, T pthp, T branch) {
+                                      T pz, T pth, T pthp, T branch, T &cos_in, T &cos_out,
+                                      T &z_behind) {
   SurfaceGrad<T> g;
   const T rho = ffma(hy, hy, hx * hx);
   const T w = ffma(-(c * c), rho, T(1));
@@ -513,6 +516,9 @@ TL_HD SurfaceGrad<T> sweep_sphere_pen(Sweep<T> &s, T hx, T hy, T dx, T dy, T c, 
   const T sin2p = mu2 * sin2;
   const T cos2p = T(1) - sin2p;
   const T rapp = frsqrt(cos2p);                       // 1 / cos(theta')
+  cos_in = a;
+  cos_out = cos2p * rapp;
+  z_behind = hz - t;
   const T clamp_s2 = clamp_sin2<T>();
   // (torch's clamp passes the gradient on the boundary: keep cos <= bound, drop cos > bound -- decided
   // on the well-conditioned sin^2, not on a cosine that is within an ULP of 1 -- and keep the rsqrt
@@ -534,6 +540,13 @@ TL_HD SurfaceGrad<T> sweep_sphere_pen(Sweep<T> &s, T hx, T hy, T dx, T dy, T c, 
   s.hit = Vec3<T>{hx, hy, hz};
   s.dir = d;
   return g;
+}
+
+template <class T>
+TL_HD SurfaceGrad<T> sweep_sphere_pen(Sweep<T> &s, T hx, T hy, T dx, T dy, T c, T t, T mu, T mu2,
+                                      T pz, T pth, T pthp, T branch) {
+  T cos_in, cos_out, z_behind;
+  return sweep_sphere_pen(s, hx, hy, dx, dy, c, t, mu, mu2, pz, pth, pthp, branch, cos_in, cos_out, z_behind);
 }
 
 // Entrance: the ray starts at (x, y, z_in) with direction (cx, cy, sqrt(1 - cx^2 - cy^2)).

@@ -444,7 +444,11 @@ struct AdjArgs {
 // theta_prime_norm of every surface, rtl:641-657).  A ray that fails at surface j still feeds the
 // stacks of the surfaces in front of j, so the sweep runs per-lane on "ok behind surface k" bits
 // instead of the final ok flag, and lanes that are not ok are forced to exact zeros (no mirroring).
-template <int NS_MAX, int MODE, class V, bool PEN = false>
+// PEN = PEN_SUM: no seed arrays -- every term of every ray is seeded with 1 and the kernel also sums
+// the terms themselves (slot 3S+1 of the row): value and gradient of the penalty sum(Q) of
+// compute_loss_out (optics_simulator_lite.py:430-450) in one pass that materialises nothing.
+enum { PEN_NONE = 0, PEN_SEEDED = 1, PEN_SUM = 2 };
+template <int NS_MAX, int MODE, class V, int PEN = PEN_NONE>
 __global__ void __launch_bounds__(kTraceThreads, TL_ADJ_MIN_BLOCKS)
 k_trace_adj(TlProblem pb, AdjArgs args) {
   extern __shared__ float smem[];
@@ -471,7 +475,7 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
   float acc_c[NA], acc_t[NA], acc_mu[NA];      // sum J        (BWD: sum of gradients)
   float wac_c[NA], wac_t[NA], wac_mu[NA];      // sum (y-y0) J (SPOT_GRAD only)
   float acc_z = 0.f, wac_z = 0.f;
-  float m_s1 = 0.f, m_s2 = 0.f, m_n = 0.f;
+  float m_s1 = 0.f, m_s2 = 0.f, m_n = 0.f, m_pen = 0.f;
   Table tab;
   float y0 = 0.f, xy_scale = 1.0f;
   int row = -1, seg = 0, b = 0, f = 0, w = 0;
@@ -492,6 +496,7 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
           put(2 * S + k, acc_mu[k]);
         }
       put(3 * S, acc_z);
+      if (PEN == PEN_SUM) put(3 * S + 1, m_pen);
     } else if (MODE == MODE_SPOT_GRAD) {
 #pragma unroll
       for (int k = 0; k < NA; ++k)
@@ -543,7 +548,7 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
         wac_c[k] = wac_t[k] = wac_mu[k] = 0.f;
       }
       acc_z = wac_z = 0.f;
-      m_s1 = m_s2 = m_n = 0.f;
+      m_s1 = m_s2 = m_n = m_pen = 0.f;
     }
     // lane l of this thread = pupil point p_base + l * threads + tid
     const int p_base = pb.p_begin + j * (kTraceThreads * N) + tid;
@@ -563,7 +568,7 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
       lane_set(cy, l, pb.cy.ptr[offset_of(pb.cy, b, f, q, w)]);
     }
     if (p_base >= pb.p_end) continue;   // whole thread past the end of the row
-    TracedN<V> tr = trace_guarded<kAdjoint, V, PEN>(x, y, z, cx, cy, tab, S, allow_backward, pb.arith,
+    TracedN<V> tr = trace_guarded<kAdjoint, V, PEN != PEN_NONE>(x, y, z, cx, cy, tab, S, allow_backward, pb.arith,
                                                     state, stride);
     bool live[N], any_live = false, all_ok = true;
     V alive, wgt(0.f);
@@ -587,23 +592,23 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
       Ray<V> a{V(0.f), V(0.f), V(0.f), V(0.f), V(0.f), V(0.f)};
       unsigned bits[N], flips[N];
       bool any_bits = false;
-      if (PEN) {
+      if (PEN != PEN_NONE) {
 #pragma unroll
         for (int l = 0; l < N; ++l) {
           bits[l] = has[l] ? tr.ok_bits[l][0] : 0u;
           flips[l] = tr.ok_bits[l][1];
-          any_bits = any_bits || bits[l] != 0u || (has[l] && args.seeds.gz_relu != nullptr);
+          any_bits = any_bits || bits[l] != 0u || (has[l] && (PEN == PEN_SUM || args.seeds.gz_relu != nullptr));
         }
       }
-      if (any_live || (PEN && any_bits)) {
-        if (!PEN && !all_ok) mirror_live_lane<V>(state, stride, S, tr.ok, tr.pre, z, tr.x, tr.y);
+      if (any_live || (PEN != PEN_NONE && any_bits)) {
+        if (PEN == PEN_NONE && !all_ok) mirror_live_lane<V>(state, stride, S, tr.ok, tr.pre, z, tr.x, tr.y);
         V sx(0.f), sy(0.f), scx(0.f), scy(0.f);
         if (MODE == MODE_SPOT_GRAD) {
           sy = alive;
         } else {
 #pragma unroll
           for (int l = 0; l < N; ++l) {
-            if (!live[l]) continue;
+            if (!live[l] || PEN == PEN_SUM) continue;
             if (args.seeds.gx) lane_set(sx, l, args.seeds.gx[o[l]]);
             if (args.seeds.gy) lane_set(sy, l, args.seeds.gy[o[l]]);
             if (args.seeds.gcx) lane_set(scx, l, args.seeds.gcx[o[l]]);
@@ -616,7 +621,7 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
           if (k >= S) continue;
           const V *slot = state + (size_t)k * 4 * stride;
           SurfaceGrad<V> g;
-          if constexpr (PEN) {
+          if constexpr (PEN != PEN_NONE) {
             // seeds of this surface's stacks ([S,B,F,P,W]); only lanes ok behind surface k carry
             // angle seeds, and their z_RELU seed enters through the hit point
             const int64_t plane = (int64_t)pb.B * pb.F * pb.P * pb.W;
@@ -628,7 +633,17 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
               if ((flips[l] >> k) & 1u) lane_set(branch, l, -1.0f);
               if (!has[l]) continue;
               const int64_t at = (int64_t)k * plane + o[l];
-              if ((bits[l] >> k) & 1u) {
+              if (PEN == PEN_SUM) {
+                if ((bits[l] >> k) & 1u) {
+                  lane_set(pz, l, 1.0f);
+                  lane_set(pth, l, 1.0f);
+                  lane_set(pthp, l, 1.0f);
+                } else {      // failed ray: theta = theta' = 1, z = 0 - t[k] (rtl:639, :653-654)
+                  const float z_dead = -tab.t[k];
+                  m_pen += 2.0f + fmaxf(z_dead, 0.0f);
+                  if (z_dead > 0.f) dead_gt[l] = -1.0f;
+                }
+              } else if ((bits[l] >> k) & 1u) {
                 if (args.seeds.gz_relu) lane_set(pz, l, args.seeds.gz_relu[at]);
                 if (args.seeds.gtheta) lane_set(pth, l, args.seeds.gtheta[at]);
                 if (args.seeds.gtheta_prime) lane_set(pthp, l, args.seeds.gtheta_prime[at]);
@@ -636,8 +651,17 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
                 dead_gt[l] = -args.seeds.gz_relu[at];     // a failed ray sits at z = 0 - t[k] (rtl:639)
               }
             }
+            V cos_in, cos_out, z_behind;
             g = sweep_sphere_pen(sw, slot[0], slot[stride], slot[2 * stride], slot[3 * stride],
-                                 V(tab.c[k]), V(tab.t[k]), V(tab.mu[k]), V(tab.mu2[k]), pz, pth, pthp, branch);
+                                 V(tab.c[k]), V(tab.t[k]), V(tab.mu[k]), V(tab.mu2[k]), pz, pth, pthp, branch,
+                                 cos_in, cos_out, z_behind);
+            if (PEN == PEN_SUM) {
+#pragma unroll
+              for (int l = 0; l < N; ++l)
+                if (has[l] && ((bits[l] >> k) & 1u))
+                  m_pen += (fast_angle_norm(lane_get(cos_in, l)) + fast_angle_norm(lane_get(cos_out, l))) +
+                           fmaxf(lane_get(z_behind, l), 0.0f);
+            }
 #pragma unroll
             for (int l = 0; l < N; ++l) {
               if ((bits[l] >> k) & 1u) continue;
@@ -727,6 +751,36 @@ __global__ void k_bwd_finalize(const double *rows, TlGrads g, int B, int F, int 
     for (int f = 0; f < F; ++f)
       for (int w = 0; w < W; ++w) s += rows[(((int64_t)b * F + f) * W + w) * n_acc + 3 * S];
     g.gz_sum[b] = (float)s;
+  }
+}
+
+// rows[b,f,w][3S+2] of the penalty pass -> penalty[b] and its gradients, all times `scale`
+// (= 1 / numSequence of compute_loss_out)
+__global__ void k_penalty_finalize(const double *rows, TlPenaltyOut out, int B, int F, int W, int S,
+                                   double scale) {
+  const int n_acc = 3 * S + 2;
+  const int per_lens = 2 * S + W * S + 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * per_lens) return;
+  const int b = i / per_lens;
+  int j = i % per_lens;
+  double s = 0.0;
+  if (j < 2 * S) {                       // c (j < S) or t
+    for (int f = 0; f < F; ++f)
+      for (int w = 0; w < W; ++w) s += rows[(((int64_t)b * F + f) * W + w) * n_acc + j];
+    if (j < S) out.gc[b * S + j] = (float)(s * scale);
+    else out.gt[b * S + (j - S)] = (float)(s * scale);
+  } else if (j < 2 * S + W * S) {
+    j -= 2 * S;
+    const int w = j / S, k = j % S;
+    for (int f = 0; f < F; ++f) s += rows[(((int64_t)b * F + f) * W + w) * n_acc + 2 * S + k];
+    out.gmu[((int64_t)b * W + w) * S + k] = (float)(s * scale);
+  } else {
+    const int slot = (j == 2 * S + W * S) ? 3 * S : 3 * S + 1;
+    for (int f = 0; f < F; ++f)
+      for (int w = 0; w < W; ++w) s += rows[(((int64_t)b * F + f) * W + w) * n_acc + slot];
+    if (slot == 3 * S) out.gz[b] = (float)(s * scale);
+    else out.penalty[b] = (float)(s * scale);
   }
 }
 
@@ -1130,19 +1184,20 @@ AdjKernel adj_kernel_for(int S) {
 }
 
 // MODE_BWD with seeds on the aggregate=True stacks: two rays per thread
+template <int PEN>
 AdjKernel pen_kernel_for(int S) {
-  if (S <= 4) return k_trace_adj<4, MODE_BWD, f2, true>;
-  if (S <= 8) return k_trace_adj<8, MODE_BWD, f2, true>;
-  if (S <= 12) return k_trace_adj<12, MODE_BWD, f2, true>;
-  if (S <= 16) return k_trace_adj<16, MODE_BWD, f2, true>;
-  return k_trace_adj<32, MODE_BWD, f2, true>;
+  if (S <= 4) return k_trace_adj<4, MODE_BWD, f2, PEN>;
+  if (S <= 8) return k_trace_adj<8, MODE_BWD, f2, PEN>;
+  if (S <= 12) return k_trace_adj<12, MODE_BWD, f2, PEN>;
+  if (S <= 16) return k_trace_adj<16, MODE_BWD, f2, PEN>;
+  return k_trace_adj<32, MODE_BWD, f2, PEN>;
 }
 
-AdjVariant select_adj(int mode, int S, bool pen = false) {
+AdjVariant select_adj(int mode, int S, int pen = PEN_NONE) {
   AdjVariant v;
-  if (pen && mode == MODE_BWD) {
+  if (pen != PEN_NONE && mode == MODE_BWD) {
     v.lanes = v.state_lanes = 2;
-    v.kernel = pen_kernel_for(S);
+    v.kernel = pen == PEN_SUM ? pen_kernel_for<PEN_SUM>(S) : pen_kernel_for<PEN_SEEDED>(S);
     return v;
   }
   v.lanes = pick_lanes(mode, S);
@@ -1168,12 +1223,12 @@ struct AdjPlan {
 
 size_t align8(size_t v) { return (v + 7) & ~(size_t)7; }
 
-int plan_adj(const TlProblem &pb, int mode, AdjPlan &pl, bool pen = false) {
+int plan_adj(const TlProblem &pb, int mode, AdjPlan &pl, int pen = PEN_NONE) {
   DeviceInfo info;
   int rc = device_info(info);
   if (rc) return rc;
   pl.variant = select_adj(mode, pb.S, pen);
-  pl.n_acc = n_acc_of(mode, pb.S);
+  pl.n_acc = n_acc_of(mode, pb.S) + (pen == PEN_SUM ? 1 : 0);
   const int lanes = pl.variant.lanes;
   const size_t table = ((5 * (size_t)pb.S + 3) & ~(size_t)3) * sizeof(float);
   const size_t state = mode != MODE_SPOT_EVAL
@@ -1320,7 +1375,7 @@ size_t tl_trace_bwd_workspace(const TlProblem *pb) {
   full.p_begin = 0;
   full.p_end = pb->P;
   AdjPlan pl, pl_pen;
-  if (plan_adj(full, MODE_BWD, pl) || plan_adj(full, MODE_BWD, pl_pen, true)) return 0;
+  if (plan_adj(full, MODE_BWD, pl) || plan_adj(full, MODE_BWD, pl_pen, PEN_SEEDED)) return 0;
   const size_t partial = pl.partial_bytes > pl_pen.partial_bytes ? pl.partial_bytes : pl_pen.partial_bytes;
   return partial + align8((size_t)pb->B * pb->F * pb->W * pl.n_acc * sizeof(double));
 }
@@ -1374,7 +1429,7 @@ int tl_trace_bwd(const TlProblem *pb_, const TlSeeds *seeds, const TlGrads *grad
   TlProblem pb = *pb_;
   pb.p_begin = 0;
   pb.p_end = pb.P;
-  const bool pen = seeds->gz_relu || seeds->gtheta || seeds->gtheta_prime;
+  const int pen = (seeds->gz_relu || seeds->gtheta || seeds->gtheta_prime) ? PEN_SEEDED : PEN_NONE;
   AdjPlan pl;
   rc = plan_adj(pb, MODE_BWD, pl, pen);
   if (rc) return rc;
@@ -1518,6 +1573,51 @@ int tl_spot_accumulate(const TlProblem *pb, int32_t want_grad, double *moments, 
   rc = launch_adj(*pb, args, pl, stream);
   if (rc) return rc;
   return reduce_rows(pl, args.partial, moments, pb->B * pb->F * pb->W, stream);
+}
+
+int32_t tl_penalty_moment_count(int32_t S) { return 3 * S + 2; }
+
+size_t tl_penalty_workspace(const TlProblem *pb) {
+  if (validate(pb, TL_MAX_SURFACES_BWD) || is_general(*pb)) return 0;
+  if (pb->p_begin < 0 || pb->p_end > pb->P || pb->p_end <= pb->p_begin) return 0;
+  AdjPlan pl;
+  if (plan_adj(*pb, MODE_BWD, pl, PEN_SUM)) return 0;
+  return pl.partial_bytes;
+}
+
+int tl_penalty_accumulate(const TlProblem *pb, double *moments, void *workspace, size_t workspace_bytes,
+                          void *stream_) {
+  int rc = validate(pb, TL_MAX_SURFACES_BWD);
+  if (rc) return rc;
+  if (is_general(*pb))
+    return fail(TL_ERR_INVALID, "the penalty terms exist for spherical lenses only (not with k / a / sd)%s");
+  if (pb->p_begin < 0 || pb->p_end > pb->P || pb->p_end <= pb->p_begin)
+    return fail(TL_ERR_INVALID, "empty or out-of-range pupil slice%s");
+  if (!moments) return fail(TL_ERR_INVALID, "NULL moments%s");
+  AdjPlan pl;
+  rc = plan_adj(*pb, MODE_BWD, pl, PEN_SUM);
+  if (rc) return rc;
+  if (!workspace || workspace_bytes < pl.partial_bytes)
+    return fail(TL_ERR_WORKSPACE, "workspace too small for tl_penalty_accumulate%s");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  AdjArgs args;
+  memset(&args, 0, sizeof(args));
+  args.partial = (double *)workspace;
+  rc = launch_adj(*pb, args, pl, stream);
+  if (rc) return rc;
+  return reduce_rows(pl, args.partial, moments, pb->B * pb->F * pb->W, stream);
+}
+
+int tl_penalty_finalize(const double *moments, int32_t B, int32_t F, int32_t W, int32_t S, double scale,
+                        const TlPenaltyOut *out, void *stream_) {
+  if (!moments || !out || !out->penalty || !out->gc || !out->gt || !out->gmu || !out->gz || B < 1 ||
+      F < 1 || W < 1 || S < 1 || S > TL_MAX_SURFACES_BWD)
+    return fail(TL_ERR_INVALID, "bad argument to tl_penalty_finalize%s");
+  const int outs = B * (2 * S + W * S + 2);
+  k_penalty_finalize<<<(outs + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(moments, *out, B, F, W, S, scale);
+  g_launches++;
+  TL_CHECK_CUDA(cudaGetLastError());
+  return TL_OK;
 }
 
 int tl_spot_finalize(const double *moments, const float *ref_y, int32_t B, int32_t F, int32_t W,

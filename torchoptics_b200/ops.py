@@ -442,6 +442,78 @@ def spot_rms(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arith=na
 # ---------------------------------------------------------------------------
 # Lens-level fused pass: ray-set staging kernels + spot pass + chain rule
 # ---------------------------------------------------------------------------
+class _PenaltySum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays, arith, shard, group, scale):
+        if any(ctx.needs_input_grad[i] for i in (0, 1, 3, 4)):
+            raise ValueError('the fused penalty pass differentiates w.r.t. z, c, t, mu only; use '
+                             'trace(..., aggregate=True) for gradients of x, y, cx, cy')
+        lay = _Layout(x, y, z, cx, cy, c, t, mu, mask)
+        if z.numel() != z.shape[0]:
+            raise ValueError('the fused penalty pass needs a per-lens pupil position z of shape [B,1,1,1]')
+        if lay.S > nat.MAX_SURFACES_BWD:
+            raise ValueError(f'the fused penalty pass supports at most {nat.MAX_SURFACES_BWD} surfaces')
+        lib = nat.load()
+        dev = lay.device
+        rank, world = shard
+        p_begin, p_end = pupil_slice(lay.P, rank, world)
+        if p_end <= p_begin:
+            raise ValueError(f'pupil axis ({lay.P}) is too short to shard over {world} ranks')
+        with torch.cuda.device(dev):
+            n_acc = lib.tl_penalty_moment_count(lay.S)
+            moments = torch.empty((lay.B, lay.F, lay.W, n_acc), dtype=torch.float64, device=dev)
+            pb = lay.problem(allow_backward_rays, arith, p_begin, p_end)
+            ws_bytes = lib.tl_penalty_workspace(ctypes.byref(pb))
+            if ws_bytes == 0:
+                nat.check(-1, 'tl_penalty_workspace')
+            ws = torch.empty((ws_bytes // 8,), dtype=torch.float64, device=dev)
+            stream = nat.stream_ptr(dev)
+            nat.check(lib.tl_penalty_accumulate(ctypes.byref(pb), moments.data_ptr(), ws.data_ptr(), ws_bytes,
+                                                stream), 'tl_penalty_accumulate')
+            if world > 1:
+                moments = reduce_moments(moments, group)
+            penalty = torch.empty((lay.B,), dtype=torch.float32, device=dev)
+            gc = torch.empty((lay.B, lay.S), dtype=torch.float32, device=dev)
+            gt = torch.empty_like(gc)
+            gmu = torch.empty((lay.B, lay.W, lay.S), dtype=torch.float32, device=dev)
+            gz = torch.empty((lay.B,), dtype=torch.float32, device=dev)
+            out = nat.TlPenaltyOut(penalty.data_ptr(), gc.data_ptr(), gt.data_ptr(), gmu.data_ptr(),
+                                   gz.data_ptr())
+            nat.check(lib.tl_penalty_finalize(moments.data_ptr(), lay.B, lay.F, lay.W, lay.S, float(scale),
+                                              ctypes.byref(out), stream), 'tl_penalty_finalize')
+        ctx.save_for_backward(gc, gt, gmu, gz)
+        ctx.meta = (lay.B, lay.W, lay.S, z.shape, c.shape, t.shape, mu.shape)
+        return penalty
+
+    @staticmethod
+    def backward(ctx, grad_penalty):
+        gc, gt, gmu, gz = ctx.saved_tensors
+        B, W, S, z_shape, c_shape, t_shape, mu_shape = ctx.meta
+        need = ctx.needs_input_grad
+        g = grad_penalty.to(torch.float32).reshape(B)
+        out = [None] * 14
+        if need[2]:
+            out[2] = (gz * g).reshape(B, 1, 1, 1).sum_to_size(z_shape)
+        if need[5]:
+            out[5] = (gc * g[:, None]).reshape(B, 1, 1, 1, S).sum_to_size(c_shape)
+        if need[6]:
+            out[6] = (gt * g[:, None]).reshape(B, 1, 1, 1, S).sum_to_size(t_shape)
+        if need[7]:
+            out[7] = (gmu * g[:, None, None]).reshape(B, 1, 1, W, S).sum_to_size(mu_shape)
+        return tuple(out)
+
+
+def penalty_sum(x, y, z, cx, cy, c, t, mu, mask, n_seq, allow_backward_rays=True, arith=nat.ARITH_GUARDED,
+                shard=(0, 1), group=None):
+    """The penalty of ``compute_loss_out`` (optics_simulator_lite.py:430-450) for every lens, as one
+    fused pass: ``sum over rays of Q``, ``Q = (sum_k theta_norm + sum_k theta_prime_norm +
+    sum_k z_RELU) / n_seq`` with the per-surface terms of ``trace_skew(aggregate=True)``
+    (rtl:641-657).  Returns a [B] tensor, differentiable w.r.t. z, c, t, mu; no stack is
+    materialised.  ``shard`` / ``group`` as in :func:`spot_rms`."""
+    return _PenaltySum.apply(x, y, z, cx, cy, c, t, mu, mask, bool(allow_backward_rays), int(arith),
+                             (int(shard[0]), int(shard[1])), group, 1.0 / float(n_seq))
+
+
 class LensTables:
     """Device-side constants of a (structure, specs, tracer) triple that the staging
     kernels read: masks, stop indices, fields, wavelengths.  Built once."""

@@ -362,6 +362,28 @@ class RayTracer:
         return trace_skew(*args, aggregate, self.allow_backward_rays, arith=self.arith,
                           **self._extension_tables(lens))
 
+    def penalty(self, specs, lens, use_vig=True, shard=(0, 1), group=None, n_seq=None):
+        """The ray-angle / ray-path penalty ``sum(Q)`` that ``compute_loss_out`` adds to the RMS
+        (optics_simulator_lite.py:430-450), for every lens [B], fused: equal to summing
+        ``(sum_k theta_norm + sum_k theta_prime_norm + sum_k z_RELU) / n_seq`` over the stacks of
+        ``trace_rays(..., aggregate=True)`` but without materialising them.  ``n_seq`` defaults to
+        the number of surfaces of the (first) lens' sequence, as in the reference (osl:441)."""
+        args = self._ray_set(specs, lens, use_vig)
+        if any(v is not None for v in self._extension_tables(lens).values()):
+            raise ValueError('the penalty terms exist for spherical lenses only')
+        if n_seq is None:
+            n_seq = int(np.asarray(lens.structure.mask)[0].sum())      # host-side constant: no sync
+        return ops.penalty_sum(*args, n_seq, self.allow_backward_rays, _arith_code(self.arith), shard, group)
+
+    def loss_unsup(self, specs, lens, penalty_rate=0.2, use_vig=True, shard=(0, 1), group=None, n_seq=None):
+        """``compute_loss_out`` (optics_simulator_lite.py:430-450) as two fused passes:
+        ``{'loss_unsup': rms + penalty_rate * penalty, 'rms': rms, 'penalty': penalty}``, each a [B]
+        tensor (the reference evaluates lens 0's RMS and sums the penalty over the batch; a
+        one-lens batch gives its numbers)."""
+        rms, _ = self.spot_rms(specs, lens, use_vig, shard, group)
+        pen = self.penalty(specs, lens, use_vig, shard, group, n_seq)
+        return {'loss_unsup': rms + penalty_rate * pen, 'rms': rms, 'penalty': pen}
+
     def spot_rms(self, specs, lens, use_vig=True, shard=(0, 1), group=None, staged=True):
         """RMS spot size of every lens -- ``compute_rms2d(*trace_rays(...))`` fused
         into one pass that also produces the gradients w.r.t. the lens
