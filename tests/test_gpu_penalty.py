@@ -328,3 +328,27 @@ def test_loss_unsup_front_end_matches_compute_loss_out():
     ref = torch.autograd.grad(rms + PENALTY_RATE * pen, [lens2.c, lens2.t, lens2.nd])
     for a, b in zip(grads, ref):
         assert _rel(a.cpu().numpy(), b.cpu().numpy()) <= GRAD_TOL
+
+
+def test_graphed_loss_step_matches_eager():
+    """GraphedSpotStep(penalty_rate=...): the CUDA-graph replay of compute_loss_out's loss gives
+    the eager front end's numbers, replay after replay, and follows new prescriptions."""
+    from torchoptics_b200 import GraphedSpotStep, RayTracer, prescriptions
+    from torchoptics_b200.lens_modeling import Lens
+    specs, lens = prescriptions.double_gauss(DEV)
+    tracer = RayTracer(mode='circular', n_rays=(48, 48), rel_fields=(0., 0.6, 1.), wavelengths=('C', 'd', 'F'),
+                       default_device=DEV)
+    step = GraphedSpotStep(tracer, specs, lens, penalty_rate=PENALTY_RATE)
+    host = {k: getattr(lens, k).detach().cpu().clone() for k in ('c', 't', 'nd', 'v')}
+    for trial in range(3):
+        if trial:
+            host['c'] = host['c'] * (1.0 + 0.002 * trial)
+        rms, grads = step(**host)
+        leaves = {k: host[k].to(DEV).requires_grad_(True) for k in ('c', 't', 'nd')}
+        res = tracer.loss_unsup(specs, Lens(lens.structure, leaves['c'], leaves['t'], leaves['nd'], host['v'].to(DEV)),
+                                penalty_rate=PENALTY_RATE)
+        want = torch.autograd.grad(res['loss_unsup'].sum(), list(leaves.values()))
+        assert abs(float(rms[0]) - float(res['rms'][0])) <= 1e-6 * float(res['rms'][0])
+        assert abs(float(step.host_penalty[0]) - float(res['penalty'][0])) <= 1e-6 * float(res['penalty'][0])
+        for k, w in zip(('c', 't', 'nd'), want):
+            assert _rel(grads[k].numpy(), w.cpu().numpy()) <= 1e-5, k

@@ -85,3 +85,16 @@ print(f'fused penalty pass (value + gradient, nothing materialised): {ms_pen:.3f
       f'{events / ms_pen / 1e6:.1f} G events/s')
 print(f'RayTracer.loss_unsup fwd+bwd (spot pass + penalty pass, eager front end): {ms_fused:.3f} ms  '
       f'{events / ms_fused / 1e6:.1f} G events/s')
+
+from torchoptics_b200 import GraphedSpotStep   # noqa: E402
+import time                                      # noqa: E402
+step = GraphedSpotStep(tracer, specs, lens, penalty_rate=0.2)
+host = {k: getattr(lens, k).detach().cpu() for k in ('c', 't', 'nd', 'v')}
+for _ in range(3):
+    step(**host)
+t0 = time.perf_counter()
+for _ in range(50):
+    rms, grads = step(**host)
+secs = (time.perf_counter() - t0) / 50
+print(f'GraphedSpotStep(penalty_rate=0.2): host prescription in, loss + gradients out: {secs * 1e3:.3f} ms  '
+      f'{events / secs / 1e9:.1f} G events/s  (rms {float(rms[0]):.6f}, penalty {float(step.host_penalty[0]):.3f})')

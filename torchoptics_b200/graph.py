@@ -26,17 +26,24 @@ class GraphedSpotStep:
     ``tracer`` / ``specs`` / ``lens`` fix the structure and sizes; the prescription
     values themselves are inputs of every call (CPU tensors of the lens' 2-D padded
     shapes, or None to keep the previous value).  With ``shard=(rank, world)`` every
-    rank traces its slice of the pupil and the graph contains the NCCL all-reduce.
+    rank traces its slice of the pupil and the graph contains the all-reduce (NCCL, or the
+    peer-memory exchange kernel when ``group`` is a :class:`~torchoptics_b200.peer.PeerExchange`).
+
+    ``penalty_rate`` (e.g. 0.2): the step evaluates ``compute_loss_out``'s loss
+    ``rms + penalty_rate * penalty`` (optics_simulator_lite.py:430-450) -- the fused spot pass plus
+    the fused penalty pass -- returns the gradients of that loss, and ``host_penalty`` holds the
+    penalty of every lens after a call.
     """
 
     PARAMS = ('c', 't', 'nd', 'v')
 
-    def __init__(self, tracer, specs, lens, shard=(0, 1), group=None, warmup=3):
+    def __init__(self, tracer, specs, lens, shard=(0, 1), group=None, warmup=3, penalty_rate=None):
         dev = torch.device(tracer.default_device)
         if dev.type != 'cuda':
             raise ValueError('GraphedSpotStep needs a CUDA tracer')
         self.device = dev
         self.tracer, self.shard, self.group = tracer, shard, group
+        self.penalty_rate = penalty_rate
         self.structure = lens.structure
         self.host_in = {k: getattr(lens, k).detach().to('cpu', torch.float32).contiguous().pin_memory()
                         for k in self.PARAMS}
@@ -47,8 +54,10 @@ class GraphedSpotStep:
         n_lens = len(lens)
         self.host_out = {k: torch.empty_like(v).pin_memory() for k, v in self.host_in.items()}
         self.host_rms = torch.empty((n_lens,), dtype=torch.float32).pin_memory()
+        self.host_penalty = torch.zeros((n_lens,), dtype=torch.float32).pin_memory()
         self.h2d_bytes = sum(v.numel() * 4 for v in self.host_in.values())
-        self.d2h_bytes = sum(v.numel() * 4 for v in self.host_out.values()) + n_lens * 4
+        self.d2h_bytes = sum(v.numel() * 4 for v in self.host_out.values()) + n_lens * 4 * \
+            (2 if penalty_rate is not None else 1)
         with torch.cuda.device(dev):
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -66,8 +75,15 @@ class GraphedSpotStep:
             self.dev_in[k].copy_(self.host_in[k], non_blocking=True)
         leaves = {k: self.dev_in[k].detach().requires_grad_(True) for k in self.PARAMS}
         lens = Lens(self.structure, leaves['c'], leaves['t'], leaves['nd'], leaves['v'])
-        rms, _ = self.tracer.spot_rms(self.specs, lens, shard=self.shard, group=self.group)
-        grads = torch.autograd.grad(rms.sum(), [leaves[k] for k in self.PARAMS], allow_unused=True)
+        if self.penalty_rate is None:
+            rms, _ = self.tracer.spot_rms(self.specs, lens, shard=self.shard, group=self.group)
+            loss = rms
+        else:
+            res = self.tracer.loss_unsup(self.specs, lens, penalty_rate=self.penalty_rate,
+                                         shard=self.shard, group=self.group)
+            rms, loss = res['rms'], res['loss_unsup']
+            self.host_penalty.copy_(res['penalty'].detach(), non_blocking=True)
+        grads = torch.autograd.grad(loss.sum(), [leaves[k] for k in self.PARAMS], allow_unused=True)
         self.host_rms.copy_(rms.detach(), non_blocking=True)
         for k, g in zip(self.PARAMS, grads):
             if g is None:
