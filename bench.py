@@ -420,6 +420,28 @@ def main():
     eager_steps = max(3, min(args.steps, 20))
     eager_secs = time_e2e(e2e_eager_step, eager_steps)
     drop_in_secs = time_e2e(drop_in_step, eager_steps) if world == 1 else None
+    # ---- the penalty of compute_loss_out (rtl:641-657, osl:430-450) ----
+    # fused penalty pass alone (device resident) and the graphed loss step rms + 0.2 * penalty
+    # from host buffers; all ranks run it (it contains the collective), rank 0 reports
+    note('penalty pass timing')
+    penalty_row = None
+    try:
+        pen_reps = max(5, min(args.steps, 20))
+        pen_ms = timed_graph(lambda: ops.penalty_sum(*plain, S, shard=shard, group=exchange), pen_reps)
+        loss_step = GraphedSpotStep(tracer, specs, lens, shard=shard, group=exchange, penalty_rate=0.2)
+        loss_secs = time_e2e(lambda: loss_step(**host_lens), pen_reps)
+        penalty_row = {'penalty_pass': {'value': events_total / (pen_ms * 1e-3), 'unit': 'events/s', 'ms': pen_ms,
+                                        'what': 'tl_penalty_accumulate + finalize: value and gradient of sum(Q), '
+                                                'no stack materialised'},
+                       'loss_step_e2e': {'value': events_total * pen_reps / loss_secs, 'unit': 'events/s',
+                                         'ms': loss_secs / pen_reps * 1e3,
+                                         'what': 'GraphedSpotStep(penalty_rate=0.2): host prescription -> '
+                                                 'rms + 0.2 penalty and its gradients -> host',
+                                         'penalty': float(loss_step.host_penalty[0])}}
+        loss_step = None
+    except Exception as exc:
+        print(f'[bench] penalty timing failed: {exc}', file=sys.stderr)
+
     if graphed is not None:
         h2d, d2h = graphed.h2d_bytes, graphed.d2h_bytes
     else:
@@ -453,7 +475,7 @@ def main():
                         'drop_in_api_value': (events_total * eager_steps / drop_in_secs) if drop_in_secs else None,
                         'drop_in_api': 'trace_rays + compute_rms2d + backward (unfused, materialises [B,F,P,W])'},
                 'gpu_launches': launches_per_step * args.steps,
-                'roofline': roofline, 'forward': forward}
+                'roofline': roofline, 'forward': forward, 'penalty': penalty_row}
         if world == 1 and not args.no_cpu_baseline:
             base = cpu_arm(5, 1)
             line['cpu_baseline'] = {k: base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}

@@ -314,25 +314,43 @@ k_trace_fwd(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
 
 // K1b: trace_skew(aggregate=True): the forward trace that also writes the three penalty stacks
 // z_RELU, theta_norm, theta_prime_norm of every surface (rtl:641-657) as [S,B,F,P,W] arrays.
-// One ray per thread: the kernel is bound by its 12 S + 18 bytes of stores per ray, not by math.
-// Guarded policy: the fast path writes its stacks as it goes; a ray that was not clearly good is
-// re-traced with the exact policy, which overwrites them.
+// The kernel is bound by its 12 S + 18 bytes of stores per ray, not by math, so the thread map
+// follows the OUTPUT layout: a CTA works on one (lens, field) and its threads run over the
+// flattened (pupil, wavelength) index -- W is the innermost axis of every output, so a warp's
+// stores are 128 contiguous bytes -- with the W surface tables of the lens side by side in shared
+// memory.  Guarded policy: the fast path writes its stacks as it goes; a ray that was not clearly
+// good is re-traced with the exact policy, which overwrites them.
+template <bool STACKS>
 __global__ void __launch_bounds__(kFwdThreads)
-k_trace_fwd_pen(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
+k_trace_fwd_pw(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
   extern __shared__ float smem[];
   int blk = blockIdx.x;
   const int chunk = blk % nchunks; blk /= nchunks;
-  const int w = blk % pb.W; blk /= pb.W;
   const int f = blk % pb.F;
   const int b = blk / pb.F;
-  const int S = pb.S;
-  const Table tab = load_table(smem, pb, b, w);
-  const int p_lo = chunk * chunk_len;
-  const int p_hi = min(pb.P, p_lo + chunk_len);
+  const int S = pb.S, W = pb.W;
+  const size_t table_stride = (table_floats(S) + 3) & ~(size_t)3;
+  float length = 0.f;                                         // sum |t|: the same for every wavelength
+  for (int w = 0; w < W; ++w) length = load_table(smem + w * table_stride, pb, b, w).length;   // (syncs inside)
+  const int64_t row_len = (int64_t)pb.P * W;                  // (p, w) flattened
+  const int64_t i_lo = (int64_t)chunk * chunk_len;
+  const int64_t i_hi = min(row_len, i_lo + (int64_t)chunk_len);
   const bool allow_backward = pb.allow_backward_rays != 0;
-  const int64_t plane = (int64_t)pb.B * pb.F * pb.P * pb.W;
+  const int64_t plane = (int64_t)pb.B * pb.F * row_len;
+  const int64_t row0 = ((int64_t)b * pb.F + f) * row_len;
   const float xy_scale = pb.xy_scale ? pb.xy_scale[b] : 1.0f;
-  for (int p = p_lo + threadIdx.x; p < p_hi; p += kFwdThreads) {
+  for (int64_t i = i_lo + threadIdx.x; i < i_hi; i += kFwdThreads) {
+    const int p = (int)(i / W), w = (int)(i % W);
+    Table tab;
+    {
+      float *base = smem + w * table_stride;
+      tab.c = base;
+      tab.t = base + S;
+      tab.mu = base + 2 * S;
+      tab.mu2 = base + 3 * S;
+      tab.live = reinterpret_cast<int *>(base + 4 * S);
+      tab.length = length;
+    }
     float x = pb.x.ptr[offset_of(pb.x, b, f, p, w)];
     float y = pb.y.ptr[offset_of(pb.y, b, f, p, w)];
     if (pb.xy_scale) {
@@ -342,7 +360,7 @@ k_trace_fwd_pen(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
     const float z = pb.z.ptr[offset_of(pb.z, b, f, p, w)];
     const float cx = pb.cx.ptr[offset_of(pb.cx, b, f, p, w)];
     const float cy = pb.cy.ptr[offset_of(pb.cy, b, f, p, w)];
-    const int64_t o = (((int64_t)b * pb.F + f) * pb.P + p) * pb.W + w;
+    const int64_t o = row0 + i;
     bool clear = false;
     if (pb.arith == TL_ARITH_GUARDED) {
       Ray<float> r{x, y, z, cx, cy, fast_cz0(cx, cy)};
@@ -351,9 +369,11 @@ k_trace_fwd_pen(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
         float travel, ci, co;
         fast_surface(r, tab.c[k], tab.mu[k], tab.mu2[k], tab.t[k], min_cos2, travel, ci, co);
         if (k > 0 && tab.live[k - 1]) min_travel = fminf(min_travel, travel);
-        out.z_relu[k * plane + o] = r.z <= 0.0f ? 0.0f : r.z;
-        out.theta[k * plane + o] = fast_angle_norm(ci);
-        out.theta_prime[k * plane + o] = fast_angle_norm(co);
+        if (STACKS) {
+          out.z_relu[k * plane + o] = r.z <= 0.0f ? 0.0f : r.z;
+          out.theta[k * plane + o] = fast_angle_norm(ci);
+          out.theta_prime[k * plane + o] = fast_angle_norm(co);
+        }
       }
       const float pre_cx = r.cx, pre_cy = r.cy;
       const float travel = fast_image(r);
@@ -376,10 +396,12 @@ k_trace_fwd_pen(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
       for (int k = 0; k < S; ++k) {
         const Surface s{tab.c[k], tab.t[k], tab.mu[k]};
         Penalty pen;
-        exact_surface_t<true>(r, s, k > 0 && tab.live[k - 1], allow_backward, ok, backward, &pen);
-        out.z_relu[k * plane + o] = pen.z_relu;
-        out.theta[k * plane + o] = pen.theta;
-        out.theta_prime[k * plane + o] = pen.theta_prime;
+        exact_surface_t<STACKS>(r, s, k > 0 && tab.live[k - 1], allow_backward, ok, backward, &pen);
+        if (STACKS) {
+          out.z_relu[k * plane + o] = pen.z_relu;
+          out.theta[k * plane + o] = pen.theta;
+          out.theta_prime[k * plane + o] = pen.theta_prime;
+        }
       }
       const float pre_cx = r.cx, pre_cy = r.cy;
       exact_image(r, tab.live[S - 1] != 0, allow_backward, ok, backward);
@@ -1337,9 +1359,13 @@ int tl_trace_fwd(const TlProblem *pb, const TlTraceOut *out, void *stream_) {
   if (stacks && is_general(*pb))
     return fail(TL_ERR_INVALID, "the aggregate=True stacks exist for spherical lenses only (not with k / a / sd)%s");
   if (stacks) {
-    const FwdPlan pp = make_fwd_plan(info.sms, pb->B * pb->F * pb->W, pb->P, kFwdThreads, 4);
-    k_trace_fwd_pen<<<pp.n_blocks, kFwdThreads, 5 * (size_t)pb->S * sizeof(float), (cudaStream_t)stream_>>>(
-        *pb, *out, pp.nchunks, pp.chunk_len);
+    const int64_t row_len = (int64_t)pb->P * pb->W;
+    if (row_len > 0x7fffffff) return fail(TL_ERR_INVALID, "P * W exceeds 2^31 - 1%s");
+    const size_t smem = (size_t)pb->W * ((5 * (size_t)pb->S + 3) & ~(size_t)3) * sizeof(float);
+    if (smem > 48 * 1024) return fail(TL_ERR_INVALID, "aggregate=True: W * S surface tables exceed 48 KB of shared memory%s");
+    const FwdPlan pp = make_fwd_plan(info.sms, pb->B * pb->F, (int)row_len, kFwdThreads, 4);
+    k_trace_fwd_pw<true><<<pp.n_blocks, kFwdThreads, smem, (cudaStream_t)stream_>>>(*pb, *out, pp.nchunks,
+                                                                                   pp.chunk_len);
     g_launches++;
     TL_CHECK_CUDA(cudaGetLastError());
     return TL_OK;
