@@ -374,3 +374,46 @@ def test_no_grad_sweep_with_grad_requiring_lens():
     assert not rms.requires_grad and abs(rms[0].item() - rms_t[0].item()) <= 1e-5 * rms_t[0].item()
     with pytest.raises(ValueError):
         tracer.spot_rms(specs, lens)          # with gradients: at most 16 surfaces in the fused pass
+
+
+# ---------------------------------------------------------------------------
+# many short rows: the warp-per-row spot kernel
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['cooke_8x8', 'cooke_16x16_epd2.6', 'tessar_16x16_epd2.0'])
+def test_rows_kernel_matches_cta_kernel_on_a_batch_of_lenses(name, monkeypatch):
+    """B = 12 perturbed copies of a golden lens (rows = B*F*W >= 64, P <= 512) take the
+    warp-per-row kernel; with TL_NO_ROWS the same call takes the CTA-per-row kernel.  Same sums
+    (fp32 summation order differs), and lens 0 (unperturbed) reproduces the reference's RMS."""
+    rec = load_golden(name)
+    allow = bool(rec['allow_backward_rays'])
+    B = 12
+    g = torch.Generator(device='cpu').manual_seed(7)
+    base = _inputs(rec, DEV)
+    S = base['c'].shape[-1]
+    jitter = 1.0 + 0.01 * torch.randn((B, 1, 1, 1, S), generator=g)
+    jitter[0] = 1.0
+
+    def run():
+        i = dict(base)
+        i['c'] = (base['c'] * jitter.to(DEV)).requires_grad_(True)
+        i['t'] = base['t'].expand(B, 1, 1, 1, S).clone().requires_grad_(True)
+        i['mu'] = base['mu'].expand(B, 1, 1, -1, S).clone().requires_grad_(True)
+        i['z'] = base['z'].expand(B, 1, 1, 1).clone().requires_grad_(True)
+        i['cy'] = base['cy'].expand(B, -1, 1, 1).contiguous()
+        i['mask'] = base['mask'].expand(B, 1, 1, 1, S).contiguous()
+        rms, rms_field = ops.spot_rms(*_args(i), allow_backward_rays=allow)
+        grads = torch.autograd.grad(rms.sum(), [i['c'], i['t'], i['mu'], i['z']])
+        no_grad_rms, _ = ops.spot_rms(*[a.detach() for a in _args(i)], allow_backward_rays=allow)
+        return rms.detach(), rms_field, grads, no_grad_rms
+
+    monkeypatch.delenv('TL_NO_ROWS', raising=False)
+    rows = run()
+    monkeypatch.setenv('TL_NO_ROWS', '1')
+    cta = run()
+    assert float(((rows[0] - cta[0]).abs() / cta[0]).max()) <= 2e-6
+    assert float(((rows[1] - cta[1]).abs() / cta[1].clamp_min(1e-12)).max()) <= 2e-6
+    assert float(((rows[3] - cta[3]).abs() / cta[3]).max()) <= 2e-6          # forward-only (EVAL) variant
+    assert float(((rows[3] - rows[0]).abs() / rows[0]).max()) <= 2e-6
+    for a, b in zip(rows[2], cta[2]):
+        assert _rel(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5
+    assert abs(float(rows[0][0]) - float(rec['rms'])) <= RMS_TOL * float(rec['rms'])

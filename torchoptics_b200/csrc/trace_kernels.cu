@@ -750,6 +750,176 @@ __global__ void k_reduce_rows(const double *partial, double *dst, int n_rows, in
 
 #include "trace_kernels_gen.cuh"
 
+// --------------------------------------------------------------------------
+// K3b: the fused spot pass for MANY SMALL rows -- the reference's real workload shape (SURVEY
+// section 8f-3: hundreds of lenses, 8 fields x 3 wavelengths x 8x8 pupil = 64 rays per row).
+// k_trace_adj gives a whole CTA (128 threads x N rays) to one (lens, field, wavelength) row and
+// pays a CTA-wide table load, two barriers and a 71-value block reduction per row: with 64 rays
+// per row most lanes idle and the per-row overhead dominates (measured 15 G events/s).
+// Here a WARP owns a row: its own surface table and parked states in shared memory, no
+// __syncthreads anywhere, and the row's sums leave through a halving-butterfly transpose
+// (warp_transpose_sum: 31 shuffles per 32 values) straight into `moments` -- no partial rows,
+// no k_reduce_rows.  Rows are dealt to the warps of a persistent grid round-robin.
+// Same arithmetic (trace_guarded, sweep_sphere), same moment layout as k_trace_adj.
+// --------------------------------------------------------------------------
+__device__ __forceinline__ Table load_table_warp(float *base, const TlProblem &pb, int b, int w, int lane) {
+  Table tab;
+  const int S = pb.S;
+  tab.c = base;
+  tab.t = base + S;
+  tab.mu = base + 2 * S;
+  tab.mu2 = base + 3 * S;
+  tab.live = reinterpret_cast<int *>(base + 4 * S);
+  __syncwarp();                                   // the previous row's readers are done
+  for (int k = lane; k < S; k += 32) {
+    const float m = pb.mu[((int64_t)b * pb.W + w) * S + k];
+    tab.c[k] = pb.c[(int64_t)b * S + k];
+    tab.t[k] = pb.t[(int64_t)b * S + k];
+    tab.mu[k] = m;
+    tab.mu2[k] = m * m;
+    tab.live[k] = pb.live[(int64_t)b * S + k] != 0;
+  }
+  __syncwarp();
+  float len = 0.f;
+  for (int k = 0; k < S; ++k) len += fabsf(tab.t[k]);
+  tab.length = len;
+  return tab;
+}
+
+template <int NS_MAX, bool GRAD, class V>
+__global__ void __launch_bounds__(kTraceThreads)
+k_spot_rows(TlProblem pb, const float *ref_y, double *moments, int n_acc) {
+  extern __shared__ float smem[];
+  constexpr int N = LaneCount<V>::value;
+  constexpr int NA = GRAD ? NS_MAX : 1;
+  constexpr int kWarps = kTraceThreads / 32;
+  const int S = pb.S;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool allow_backward = pb.allow_backward_rays != 0;
+  const size_t tab_floats = (table_floats(S) + 3) & ~(size_t)3;
+  const size_t state_floats = GRAD ? (size_t)4 * S * 32 * N : 0;
+  float *wbase = smem + warp * (tab_floats + state_floats);
+  V *state = reinterpret_cast<V *>(wbase + tab_floats) + lane;
+  constexpr int stride = 32;
+  const int n_rows = pb.B * pb.F * pb.W;
+  const int groups = (pb.p_end - pb.p_begin + 32 * N - 1) / (32 * N);
+
+  for (int row = blockIdx.x * kWarps + warp; row < n_rows; row += gridDim.x * kWarps) {
+    const int w = row % pb.W;
+    const int f = (row / pb.W) % pb.F;
+    const int b = row / (pb.W * pb.F);
+    const Table tab = load_table_warp(wbase, pb, b, w, lane);
+    const float xy_scale = pb.xy_scale ? pb.xy_scale[b] : 1.0f;
+    const float y0 = ref_y[b * pb.F + f];
+    float acc_c[NA], acc_t[NA], acc_mu[NA], wac_c[NA], wac_t[NA], wac_mu[NA];
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+      acc_c[k] = acc_t[k] = acc_mu[k] = 0.f;
+      wac_c[k] = wac_t[k] = wac_mu[k] = 0.f;
+    }
+    float acc_z = 0.f, wac_z = 0.f, m_s1 = 0.f, m_s2 = 0.f, m_n = 0.f;
+
+    for (int j = 0; j < groups; ++j) {
+      const int p_base = pb.p_begin + j * (32 * N) + lane;
+      if (p_base >= pb.p_end) continue;            // whole thread past the end of the row
+      bool has[N];
+      V x, y, z, cx, cy;
+#pragma unroll
+      for (int l = 0; l < N; ++l) {
+        const int p = p_base + l * 32;
+        has[l] = p < pb.p_end;
+        const int q = has[l] ? p : p_base;
+        lane_set(x, l, __fmul_rn(pb.x.ptr[offset_of(pb.x, b, f, q, w)], xy_scale));
+        lane_set(y, l, __fmul_rn(pb.y.ptr[offset_of(pb.y, b, f, q, w)], xy_scale));
+        lane_set(z, l, pb.z.ptr[offset_of(pb.z, b, f, q, w)]);
+        lane_set(cx, l, pb.cx.ptr[offset_of(pb.cx, b, f, q, w)]);
+        lane_set(cy, l, pb.cy.ptr[offset_of(pb.cy, b, f, q, w)]);
+      }
+      TracedN<V> tr = trace_guarded<GRAD, V>(x, y, z, cx, cy, tab, S, allow_backward, pb.arith, state, stride);
+      bool live[N], any_live = false, all_ok = true;
+      V alive;
+#pragma unroll
+      for (int l = 0; l < N; ++l) {
+        live[l] = tr.ok[l] && has[l];
+        any_live = any_live || live[l];
+        all_ok = all_ok && tr.ok[l];
+        lane_set(alive, l, live[l] ? 1.0f : 0.0f);
+      }
+      V wgt = (tr.y - V(y0)) * alive;
+#pragma unroll
+      for (int l = 0; l < N; ++l)
+        if (!live[l]) lane_set(wgt, l, 0.f);
+      m_s1 += lane_sum(wgt);
+      m_s2 = lane_dot(wgt, wgt, m_s2);
+      m_n += lane_sum(alive);
+      if (GRAD && any_live) {
+        if (!all_ok) mirror_live_lane<V>(state, stride, S, tr.ok, tr.pre, z, tr.x, tr.y);
+        Sweep<V> sw = sweep_begin(tr.pre, tr.x, tr.y, V(0.f), alive, V(0.f), V(0.f));
+#pragma unroll
+        for (int k = NS_MAX - 1; k >= 0; --k) {
+          if (k >= S) continue;
+          const V *slot = state + (size_t)k * 4 * stride;
+          const SurfaceGrad<V> g = sweep_sphere(sw, slot[0], slot[stride], slot[2 * stride], slot[3 * stride],
+                                                V(tab.c[k]), V(tab.t[k]), V(tab.mu[k]), V(tab.mu2[k]));
+          acc_c[k] += lane_sum(g.c);
+          acc_t[k] += lane_sum(g.t);
+          acc_mu[k] += lane_sum(g.mu);
+          wac_c[k] = lane_dot(wgt, g.c, wac_c[k]);
+          wac_t[k] = lane_dot(wgt, g.t, wac_t[k]);
+          wac_mu[k] = lane_dot(wgt, g.mu, wac_mu[k]);
+        }
+        V ax, ay, az, acx, acy;
+        sweep_end(sw, z, ax, ay, az, acx, acy);
+        acc_z += lane_sum(az);
+        wac_z = lane_dot(wgt, az, wac_z);
+      }
+    }
+
+    // the row's sums: 6 values per surface go through the transpose five surfaces at a time
+    // (lane 6 q + typ of batch i ends with the warp total of value typ of surface 5 i + q: slot
+    // typ * S + k of the row, exactly k_trace_adj's layout), the five scalars through plain sums
+    double *dst = moments + (int64_t)row * n_acc;
+    if (GRAD) {
+      constexpr int kPerBatch = 5;
+#pragma unroll
+      for (int i = 0; i < (NS_MAX + kPerBatch - 1) / kPerBatch; ++i) {
+        float v[32];
+#pragma unroll
+        for (int q = 0; q < kPerBatch; ++q) {
+          const int k = i * kPerBatch + q;
+          const bool in = k < NA;
+          v[6 * q + 0] = in ? wac_c[k < NA ? k : 0] : 0.f;
+          v[6 * q + 1] = in ? acc_c[k < NA ? k : 0] : 0.f;
+          v[6 * q + 2] = in ? wac_t[k < NA ? k : 0] : 0.f;
+          v[6 * q + 3] = in ? acc_t[k < NA ? k : 0] : 0.f;
+          v[6 * q + 4] = in ? wac_mu[k < NA ? k : 0] : 0.f;
+          v[6 * q + 5] = in ? acc_mu[k < NA ? k : 0] : 0.f;
+        }
+        v[30] = v[31] = 0.f;
+        const float total = warp_transpose_sum(v, lane);
+        const int k = i * kPerBatch + lane / 6, typ = lane % 6;
+        if (lane < 30 && k < S) dst[typ * S + k] = (double)total;
+      }
+      const float t0 = warp_sum(wac_z), t1 = warp_sum(acc_z), t2 = warp_sum(m_s1), t3 = warp_sum(m_s2),
+                  t4 = warp_sum(m_n);
+      if (lane == 0) {
+        dst[6 * S] = (double)t0;
+        dst[6 * S + 1] = (double)t1;
+        dst[6 * S + 2] = (double)t2;
+        dst[6 * S + 3] = (double)t3;
+        dst[6 * S + 4] = (double)t4;
+      }
+    } else {
+      const float t2 = warp_sum(m_s1), t3 = warp_sum(m_s2), t4 = warp_sum(m_n);
+      if (lane == 0) {
+        dst[0] = (double)t2;
+        dst[1] = (double)t3;
+        dst[2] = (double)t4;
+      }
+    }
+  }
+}
+
 // rows[b,f,w][3S+1] -> gc[b,S], gt[b,S], gmu[b,w,S], gz[b]
 __global__ void k_bwd_finalize(const double *rows, TlGrads g, int B, int F, int W, int S) {
   const int n_acc = 3 * S + 1;
@@ -1301,6 +1471,56 @@ int reduce_rows(const AdjPlan &pl, const double *partial, double *rows_out, int 
   return TL_OK;
 }
 
+// ---- K3b dispatch: warp-per-row spot pass for short pupil slices -------------------------
+typedef void (*RowsKernelPtr)(TlProblem, const float *, double *, int);
+constexpr int kRowsMaxPupil = 512;      // up to 8 groups of 64 rays per row; beyond that a CTA per row wins
+
+RowsKernelPtr rows_kernel_for(int S, int want_grad) {
+  if (!want_grad) return k_spot_rows<1, false, f2>;
+  if (S <= 4) return k_spot_rows<4, true, f2>;
+  if (S <= 8) return k_spot_rows<8, true, f2>;
+  if (S <= 12) return k_spot_rows<12, true, f2>;
+  return k_spot_rows<16, true, f2>;
+}
+
+bool use_rows_kernel(const TlProblem &pb, int want_grad) {
+  if (getenv("TL_NO_ROWS")) return false;
+  const int n_pupil = pb.p_end - pb.p_begin;
+  const int64_t rows = (int64_t)pb.B * pb.F * pb.W;
+  if (want_grad && pb.S > TL_MAX_SURFACES_SPOT) return false;
+  return n_pupil <= kRowsMaxPupil && rows >= 64;
+}
+
+int launch_spot_rows(const TlProblem &pb, int want_grad, const float *ref_y, double *moments,
+                     cudaStream_t stream) {
+  DeviceInfo info;
+  int rc = device_info(info);
+  if (rc) return rc;
+  RowsKernelPtr kernel = rows_kernel_for(pb.S, want_grad);
+  const size_t tab_floats = (5 * (size_t)pb.S + 3) & ~(size_t)3;
+  const size_t state_floats = want_grad ? (size_t)4 * pb.S * 32 * 2 : 0;
+  const size_t smem = (kTraceThreads / 32) * (tab_floats + state_floats) * sizeof(float);
+  if (smem > 227 * 1024) return fail(TL_ERR_INVALID, "surface count needs too much shared memory%s");
+  if (smem > 48 * 1024)
+    TL_CHECK_CUDA(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+  int per_sm = 0;
+  TL_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)kernel, kTraceThreads,
+                                                              smem));
+  if (per_sm < 1) return fail(TL_ERR_CUDA, "kernel does not fit on an SM%s");
+  const int64_t rows = (int64_t)pb.B * pb.F * pb.W;
+  int64_t n_blocks = (int64_t)info.sms * per_sm;
+  const int64_t need = (rows + kTraceThreads / 32 - 1) / (kTraceThreads / 32);
+  if (n_blocks > need) n_blocks = need;
+  const int n_acc = n_acc_of(want_grad ? MODE_SPOT_GRAD : MODE_SPOT_EVAL, pb.S);
+  TlProblem pb_copy = pb;
+  void *params[] = {(void *)&pb_copy, (void *)&ref_y, (void *)&moments, (void *)&n_acc};
+  TL_CHECK_CUDA(cudaLaunchKernel((const void *)kernel, dim3((unsigned)n_blocks), dim3(kTraceThreads), params,
+                                 smem, stream));
+  g_launches++;
+  return TL_OK;
+}
+
 int plan_gen(const TlProblem &pb, int want_grad, GenPlan &pl, bool seeded = false) {
   DeviceInfo info;
   int rc = device_info(info);
@@ -1592,6 +1812,8 @@ int tl_spot_accumulate(const TlProblem *pb, int32_t want_grad, double *moments, 
   const int n_bf = pb->B * pb->F;
   k_chief_rays<<<(n_bf + 127) / 128, 128, 0, stream>>>(*pb, ref_y);
   g_launches++;
+  if (use_rows_kernel(*pb, want_grad))      // many short rows: a warp per row, sums straight into `moments`
+    return launch_spot_rows(*pb, want_grad, ref_y, moments, stream);
   AdjArgs args;
   memset(&args, 0, sizeof(args));
   args.partial = (double *)workspace;
