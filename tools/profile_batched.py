@@ -11,9 +11,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from torchoptics_b200 import RayTracer, ops, prescriptions   # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+SIDE = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 dev = 'cuda:0'
 specs, lens = prescriptions.load_yaml('baseline_cooke.yml', dev)
-tracer = RayTracer(mode='circular', n_rays=(8, 8), rel_fields=tuple(np.linspace(0, 1, 8).tolist()),
+tracer = RayTracer(mode='circular', n_rays=(SIDE, SIDE), rel_fields=tuple(np.linspace(0, 1, 8).tolist()),
                    wavelengths=('C', 'd', 'F'), default_device=dev)
 x, y, z, cx, cy, c, t, mu, mask = [a.detach() for a in tracer._ray_set(specs, lens)]
 g = torch.Generator(device='cpu').manual_seed(0)
@@ -22,7 +23,7 @@ args = [x, y, z.expand(B, 1, 1, 1).contiguous(), cx, cy.expand(B, -1, 1, 1).cont
         (c * jit).contiguous(), t.expand(B, 1, 1, 1, -1).contiguous(),
         mu.expand(B, 1, 1, -1, -1).contiguous(), mask.expand(B, 1, 1, 1, -1).contiguous()]
 S = c.shape[-1]
-rays = B * 8 * 3 * 64
+rays = B * 8 * 3 * SIDE * SIDE
 events = rays * S
 for _ in range(3):
     m, _ = ops.spot_moments(*args)
@@ -42,5 +43,5 @@ for _ in range(20):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 20
-print(f'{B} lenses x 1536 rays, S={S}: fused spot pass {ms:.4f} ms -> {events / ms / 1e6:.1f} G events/s '
+print(f'{B} lenses x {8 * 3 * SIDE * SIDE} rays (pupil {SIDE * SIDE}), S={S}: fused spot pass {ms:.4f} ms -> {events / ms / 1e6:.1f} G events/s '
       f'({events * 166 / ms / 1e9 / 74.45 * 100:.1f}% of FP32 peak), n_ok={float(m[..., -1].sum()):.0f} of {rays}')

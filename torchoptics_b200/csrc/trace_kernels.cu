@@ -1473,7 +1473,8 @@ int reduce_rows(const AdjPlan &pl, const double *partial, double *rows_out, int 
 
 // ---- K3b dispatch: warp-per-row spot pass for short pupil slices -------------------------
 typedef void (*RowsKernelPtr)(TlProblem, const float *, double *, int);
-constexpr int kRowsMaxPupil = 512;      // up to 8 groups of 64 rays per row; beyond that a CTA per row wins
+constexpr int kRowsMaxPupil = 1024;     // measured crossover (S = 7, 1.5 M rays): rows 112 vs CTA 92 G events/s at
+                                        // P = 1024, 77 vs 102 at P = 2025 (tools/rows_crossover.sh)
 
 RowsKernelPtr rows_kernel_for(int S, int want_grad) {
   if (!want_grad) return k_spot_rows<1, false, f2>;
@@ -1488,7 +1489,9 @@ bool use_rows_kernel(const TlProblem &pb, int want_grad) {
   const int n_pupil = pb.p_end - pb.p_begin;
   const int64_t rows = (int64_t)pb.B * pb.F * pb.W;
   if (want_grad && pb.S > TL_MAX_SURFACES_SPOT) return false;
-  return n_pupil <= kRowsMaxPupil && rows >= 64;
+  int max_pupil = kRowsMaxPupil;
+  if (const char *env = getenv("TL_ROWS_MAX_PUPIL")) max_pupil = atoi(env);     // crossover experiments
+  return n_pupil <= max_pupil && rows >= 64;
 }
 
 int launch_spot_rows(const TlProblem &pb, int want_grad, const float *ref_y, double *moments,
