@@ -1581,14 +1581,24 @@ int tl_trace_fwd(const TlProblem *pb, const TlTraceOut *out, void *stream_) {
     return fail(TL_ERR_INVALID, "the three aggregate=True stacks come together: z_relu, theta, theta_prime%s");
   if (stacks && is_general(*pb))
     return fail(TL_ERR_INVALID, "the aggregate=True stacks exist for spherical lenses only (not with k / a / sd)%s");
-  if (stacks) {
+  // short pupil axis (the batched-lens workload: 64 rays per (lens, field, wavelength)): the
+  // (pupil, wavelength)-flattened map keeps a CTA's threads busy where a CTA per row would idle
+  const size_t smem_pw = (size_t)pb->W * ((5 * (size_t)pb->S + 3) & ~(size_t)3) * sizeof(float);
+  const bool short_rows = !is_general(*pb) && pb->P < 2 * kFwdThreads && smem_pw <= 48 * 1024 &&
+                          !getenv("TL_NO_ROWS");
+  if (stacks || short_rows) {
     const int64_t row_len = (int64_t)pb->P * pb->W;
     if (row_len > 0x7fffffff) return fail(TL_ERR_INVALID, "P * W exceeds 2^31 - 1%s");
-    const size_t smem = (size_t)pb->W * ((5 * (size_t)pb->S + 3) & ~(size_t)3) * sizeof(float);
-    if (smem > 48 * 1024) return fail(TL_ERR_INVALID, "aggregate=True: W * S surface tables exceed 48 KB of shared memory%s");
+    const size_t smem = smem_pw;
+    if (smem > 48 * 1024)
+      return fail(TL_ERR_INVALID, "aggregate=True: W * S surface tables exceed 48 KB of shared memory%s");
     const FwdPlan pp = make_fwd_plan(info.sms, pb->B * pb->F, (int)row_len, kFwdThreads, 4);
-    k_trace_fwd_pw<true><<<pp.n_blocks, kFwdThreads, smem, (cudaStream_t)stream_>>>(*pb, *out, pp.nchunks,
-                                                                                   pp.chunk_len);
+    if (stacks)
+      k_trace_fwd_pw<true><<<pp.n_blocks, kFwdThreads, smem, (cudaStream_t)stream_>>>(*pb, *out, pp.nchunks,
+                                                                                     pp.chunk_len);
+    else
+      k_trace_fwd_pw<false><<<pp.n_blocks, kFwdThreads, smem, (cudaStream_t)stream_>>>(*pb, *out, pp.nchunks,
+                                                                                      pp.chunk_len);
     g_launches++;
     TL_CHECK_CUDA(cudaGetLastError());
     return TL_OK;
