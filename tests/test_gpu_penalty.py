@@ -352,3 +352,41 @@ def test_graphed_loss_step_matches_eager():
         assert abs(float(step.host_penalty[0]) - float(res['penalty'][0])) <= 1e-6 * float(res['penalty'][0])
         for k, w in zip(('c', 't', 'nd'), want):
             assert _rel(grads[k].numpy(), w.cpu().numpy()) <= 1e-5, k
+
+
+@pytest.mark.parametrize('name', ['cooke_8x8', 'cooke_16x16_epd2.6', 'tessar_16x16_epd2.0'])
+def test_penalty_rows_kernel_matches_cta_kernel(name, monkeypatch):
+    """A batch of 12 perturbed lenses (>= 64 short rows) takes the warp-per-row penalty kernel;
+    with TL_NO_ROWS the CTA-per-row one.  Same value and gradients, failing rays included."""
+    from torchoptics_b200 import ops
+    rec, agg = load_aggregate(name)
+    allow = bool(rec['allow_backward_rays'])
+    n_seq = int(agg['n_seq'])
+    B = 12
+    g = torch.Generator(device='cpu').manual_seed(11)
+    base = _inputs(rec, DEV, broadcast=False)
+    S = base['c'].shape[-1]
+    jitter = 1.0 + 0.01 * torch.randn((B, 1, 1, 1, S), generator=g)
+    jitter[0] = 1.0
+
+    def run():
+        i = dict(base)
+        i['c'] = (base['c'] * jitter.to(DEV)).requires_grad_(True)
+        i['t'] = base['t'].expand(B, 1, 1, 1, S).clone().requires_grad_(True)
+        i['mu'] = base['mu'].expand(B, 1, 1, -1, S).clone().requires_grad_(True)
+        i['z'] = base['z'].expand(B, 1, 1, 1).clone().requires_grad_(True)
+        i['cy'] = base['cy'].expand(B, -1, 1, 1).contiguous()
+        i['mask'] = base['mask'].expand(B, 1, 1, 1, S).contiguous()
+        pen = ops.penalty_sum(*_args(i), n_seq, allow)
+        return pen.detach(), torch.autograd.grad(pen.sum(), [i['c'], i['t'], i['mu'], i['z']])
+
+    monkeypatch.delenv('TL_NO_ROWS', raising=False)
+    rows = run()
+    monkeypatch.setenv('TL_NO_ROWS', '1')
+    cta = run()
+    assert float(((rows[0] - cta[0]).abs() / cta[0]).max()) <= 2e-6
+    group = float(torch.cat([cta[1][1].reshape(-1), cta[1][3].reshape(-1)]).norm())
+    for k, a, b in zip(('c', 't', 'mu', 'z'), rows[1], cta[1]):
+        scale = group if k == 'z' else float(b.norm())
+        assert float((a - b).norm()) <= 2e-5 * scale, k
+    assert abs(float(rows[0][0]) - float(agg['penalty'])) <= 2e-5 * float(agg['penalty'])

@@ -1471,6 +1471,135 @@ int reduce_rows(const AdjPlan &pl, const double *partial, double *rows_out, int 
   return TL_OK;
 }
 
+// K3c: the fused penalty pass (PEN_SUM of k_trace_adj) with a warp per row, for the same
+// many-short-rows workload as k_spot_rows.  Row layout [3S+2]: c, t, mu per surface, z, penalty.
+template <int NS_MAX, class V>
+__global__ void __launch_bounds__(kTraceThreads)
+k_penalty_rows(TlProblem pb, double *moments, int n_acc) {
+  extern __shared__ float smem[];
+  constexpr int N = LaneCount<V>::value;
+  constexpr int kWarps = kTraceThreads / 32;
+  const int S = pb.S;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool allow_backward = pb.allow_backward_rays != 0;
+  const size_t tab_floats = (table_floats(S) + 3) & ~(size_t)3;
+  const size_t state_floats = (size_t)4 * S * 32 * N;
+  float *wbase = smem + warp * (tab_floats + state_floats);
+  V *state = reinterpret_cast<V *>(wbase + tab_floats) + lane;
+  constexpr int stride = 32;
+  const int n_rows = pb.B * pb.F * pb.W;
+  const int groups = (pb.p_end - pb.p_begin + 32 * N - 1) / (32 * N);
+
+  for (int row = blockIdx.x * kWarps + warp; row < n_rows; row += gridDim.x * kWarps) {
+    const int w = row % pb.W;
+    const int f = (row / pb.W) % pb.F;
+    const int b = row / (pb.W * pb.F);
+    const Table tab = load_table_warp(wbase, pb, b, w, lane);
+    const float xy_scale = pb.xy_scale ? pb.xy_scale[b] : 1.0f;
+    float acc_c[NS_MAX], acc_t[NS_MAX], acc_mu[NS_MAX];
+#pragma unroll
+    for (int k = 0; k < NS_MAX; ++k) acc_c[k] = acc_t[k] = acc_mu[k] = 0.f;
+    float acc_z = 0.f, m_pen = 0.f;
+
+    for (int j = 0; j < groups; ++j) {
+      const int p_base = pb.p_begin + j * (32 * N) + lane;
+      if (p_base >= pb.p_end) continue;
+      bool has[N];
+      V x, y, z, cx, cy;
+#pragma unroll
+      for (int l = 0; l < N; ++l) {
+        const int p = p_base + l * 32;
+        has[l] = p < pb.p_end;
+        const int q = has[l] ? p : p_base;
+        lane_set(x, l, __fmul_rn(pb.x.ptr[offset_of(pb.x, b, f, q, w)], xy_scale));
+        lane_set(y, l, __fmul_rn(pb.y.ptr[offset_of(pb.y, b, f, q, w)], xy_scale));
+        lane_set(z, l, pb.z.ptr[offset_of(pb.z, b, f, q, w)]);
+        lane_set(cx, l, pb.cx.ptr[offset_of(pb.cx, b, f, q, w)]);
+        lane_set(cy, l, pb.cy.ptr[offset_of(pb.cy, b, f, q, w)]);
+      }
+      TracedN<V> tr = trace_guarded<true, V, true>(x, y, z, cx, cy, tab, S, allow_backward, pb.arith, state,
+                                                   stride);
+      unsigned bits[N], flips[N];
+#pragma unroll
+      for (int l = 0; l < N; ++l) {
+        bits[l] = has[l] ? tr.ok_bits[l][0] : 0u;
+        flips[l] = tr.ok_bits[l][1];
+      }
+      Sweep<V> sw = sweep_begin(tr.pre, tr.x, tr.y, V(0.f), V(0.f), V(0.f), V(0.f));
+#pragma unroll
+      for (int k = NS_MAX - 1; k >= 0; --k) {
+        if (k >= S) continue;
+        const V *slot = state + (size_t)k * 4 * stride;
+        V pz(0.f), pth(0.f), pthp(0.f), branch(1.0f);
+        float dead_gt[N];
+#pragma unroll
+        for (int l = 0; l < N; ++l) {
+          dead_gt[l] = 0.f;
+          if ((flips[l] >> k) & 1u) lane_set(branch, l, -1.0f);
+          if (!has[l]) continue;
+          if ((bits[l] >> k) & 1u) {
+            lane_set(pz, l, 1.0f);
+            lane_set(pth, l, 1.0f);
+            lane_set(pthp, l, 1.0f);
+          } else {      // failed ray: theta = theta' = 1, z = 0 - t[k] (rtl:639, :653-654)
+            const float z_dead = -tab.t[k];
+            m_pen += 2.0f + fmaxf(z_dead, 0.0f);
+            if (z_dead > 0.f) dead_gt[l] = -1.0f;
+          }
+        }
+        V cos_in, cos_out, z_behind;
+        SurfaceGrad<V> g = sweep_sphere_pen(sw, slot[0], slot[stride], slot[2 * stride], slot[3 * stride],
+                                            V(tab.c[k]), V(tab.t[k]), V(tab.mu[k]), V(tab.mu2[k]), pz, pth, pthp,
+                                            branch, cos_in, cos_out, z_behind);
+#pragma unroll
+        for (int l = 0; l < N; ++l) {
+          if ((bits[l] >> k) & 1u) {
+            m_pen += (fast_angle_norm(lane_get(cos_in, l)) + fast_angle_norm(lane_get(cos_out, l))) +
+                     fmaxf(lane_get(z_behind, l), 0.0f);
+            continue;
+          }
+          lane_set(g.c, l, 0.f);
+          lane_set(g.mu, l, 0.f);
+          lane_set(g.t, l, dead_gt[l]);
+          lane_set(sw.gr.x, l, 0.f); lane_set(sw.gr.y, l, 0.f); lane_set(sw.gr.z, l, 0.f);
+          lane_set(sw.gd.x, l, 0.f); lane_set(sw.gd.y, l, 0.f); lane_set(sw.gd.z, l, 0.f);
+        }
+        acc_c[k] += lane_sum(g.c);
+        acc_t[k] += lane_sum(g.t);
+        acc_mu[k] += lane_sum(g.mu);
+      }
+      V ax, ay, az, acx, acy;
+      sweep_end(sw, z, ax, ay, az, acx, acy);
+      acc_z += lane_sum(az);
+    }
+
+    // three values per surface, ten surfaces per transpose: lane 3 q + typ -> slot typ * S + k
+    double *dst = moments + (int64_t)row * n_acc;
+    constexpr int kPerBatch = 10;
+#pragma unroll
+    for (int i = 0; i < (NS_MAX + kPerBatch - 1) / kPerBatch; ++i) {
+      float v[32];
+#pragma unroll
+      for (int q = 0; q < kPerBatch; ++q) {
+        const int k = i * kPerBatch + q;
+        const bool in = k < NS_MAX;
+        v[3 * q + 0] = in ? acc_c[k < NS_MAX ? k : 0] : 0.f;
+        v[3 * q + 1] = in ? acc_t[k < NS_MAX ? k : 0] : 0.f;
+        v[3 * q + 2] = in ? acc_mu[k < NS_MAX ? k : 0] : 0.f;
+      }
+      v[30] = v[31] = 0.f;
+      const float total = warp_transpose_sum(v, lane);
+      const int k = i * kPerBatch + lane / 3, typ = lane % 3;
+      if (lane < 30 && k < S) dst[typ * S + k] = (double)total;
+    }
+    const float t0 = warp_sum(acc_z), t1 = warp_sum(m_pen);
+    if (lane == 0) {
+      dst[3 * S] = (double)t0;
+      dst[3 * S + 1] = (double)t1;
+    }
+  }
+}
+
 // ---- K3b dispatch: warp-per-row spot pass for short pupil slices -------------------------
 typedef void (*RowsKernelPtr)(TlProblem, const float *, double *, int);
 constexpr int kRowsMaxPupil = 1024;     // measured crossover (S = 7, 1.5 M rays): rows 112 vs CTA 92 G events/s at
@@ -1518,6 +1647,36 @@ int launch_spot_rows(const TlProblem &pb, int want_grad, const float *ref_y, dou
   const int n_acc = n_acc_of(want_grad ? MODE_SPOT_GRAD : MODE_SPOT_EVAL, pb.S);
   TlProblem pb_copy = pb;
   void *params[] = {(void *)&pb_copy, (void *)&ref_y, (void *)&moments, (void *)&n_acc};
+  TL_CHECK_CUDA(cudaLaunchKernel((const void *)kernel, dim3((unsigned)n_blocks), dim3(kTraceThreads), params,
+                                 smem, stream));
+  g_launches++;
+  return TL_OK;
+}
+
+typedef void (*PenRowsKernelPtr)(TlProblem, double *, int);
+
+int launch_penalty_rows(const TlProblem &pb, double *moments, cudaStream_t stream) {
+  DeviceInfo info;
+  int rc = device_info(info);
+  if (rc) return rc;
+  PenRowsKernelPtr kernel = pb.S <= 4 ? k_penalty_rows<4, f2> : pb.S <= 8 ? k_penalty_rows<8, f2>
+                            : pb.S <= 12 ? k_penalty_rows<12, f2> : k_penalty_rows<16, f2>;
+  const size_t tab_floats = (5 * (size_t)pb.S + 3) & ~(size_t)3;
+  const size_t smem = (kTraceThreads / 32) * (tab_floats + (size_t)4 * pb.S * 32 * 2) * sizeof(float);
+  if (smem > 48 * 1024)
+    TL_CHECK_CUDA(cudaFuncSetAttribute((const void *)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+  int per_sm = 0;
+  TL_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)kernel, kTraceThreads,
+                                                              smem));
+  if (per_sm < 1) return fail(TL_ERR_CUDA, "kernel does not fit on an SM%s");
+  const int64_t rows = (int64_t)pb.B * pb.F * pb.W;
+  int64_t n_blocks = (int64_t)info.sms * per_sm;
+  const int64_t need = (rows + kTraceThreads / 32 - 1) / (kTraceThreads / 32);
+  if (n_blocks > need) n_blocks = need;
+  const int n_acc = 3 * pb.S + 2;
+  TlProblem pb_copy = pb;
+  void *params[] = {(void *)&pb_copy, (void *)&moments, (void *)&n_acc};
   TL_CHECK_CUDA(cudaLaunchKernel((const void *)kernel, dim3((unsigned)n_blocks), dim3(kTraceThreads), params,
                                  smem, stream));
   g_launches++;
@@ -1855,6 +2014,8 @@ int tl_penalty_accumulate(const TlProblem *pb, double *moments, void *workspace,
   if (pb->p_begin < 0 || pb->p_end > pb->P || pb->p_end <= pb->p_begin)
     return fail(TL_ERR_INVALID, "empty or out-of-range pupil slice%s");
   if (!moments) return fail(TL_ERR_INVALID, "NULL moments%s");
+  if (pb->S <= TL_MAX_SURFACES_SPOT && use_rows_kernel(*pb, 1))     // many short rows: a warp per row
+    return launch_penalty_rows(*pb, moments, (cudaStream_t)stream_);
   AdjPlan pl;
   rc = plan_adj(*pb, MODE_BWD, pl, PEN_SUM);
   if (rc) return rc;
