@@ -45,19 +45,31 @@ class GraphedSpotStep:
         self.tracer, self.shard, self.group = tracer, shard, group
         self.penalty_rate = penalty_rate
         self.structure = lens.structure
-        self.host_in = {k: getattr(lens, k).detach().to('cpu', torch.float32).contiguous().pin_memory()
-                        for k in self.PARAMS}
-        self.dev_in = {k: v.to(dev) for k, v in self.host_in.items()}
+        # ONE pinned staging buffer each way: the four prescription tensors travel in one H2D copy,
+        # gradients + rms (+ penalty) come back in one D2H copy (a step is latency-bound: every
+        # separate small copy costs a few microseconds of a 0.3 ms step)
+        shape = tuple(lens.c.shape)
+        n_par, n_lens = len(self.PARAMS), len(lens)
+        per = int(lens.c.numel())
+        self._host_in_buf = torch.empty((n_par * per,), dtype=torch.float32).pin_memory()
+        self._dev_in_buf = torch.empty((n_par * per,), dtype=torch.float32, device=dev)
+        self.host_in = {k: self._host_in_buf[i * per:(i + 1) * per].view(shape) for i, k in enumerate(self.PARAMS)}
+        self.dev_in = {k: self._dev_in_buf[i * per:(i + 1) * per].view(shape) for i, k in enumerate(self.PARAMS)}
+        for k in self.PARAMS:
+            self.host_in[k].copy_(getattr(lens, k).detach().to('cpu', torch.float32))
+        self._dev_in_buf.copy_(self._host_in_buf)
+        self._host_out_buf = torch.zeros((n_par * per + 2 * n_lens,), dtype=torch.float32).pin_memory()
+        self._dev_out_buf = torch.zeros((n_par * per + 2 * n_lens,), dtype=torch.float32, device=dev)
         self.specs = Specs(specs.structure, specs.epd.detach().to(dev), specs.hfov.detach().to(dev),
                            specs.vig_up.detach().to(dev), specs.vig_down.detach().to(dev),
                            specs.vig_x.detach().to(dev))
-        n_lens = len(lens)
-        self.host_out = {k: torch.empty_like(v).pin_memory() for k, v in self.host_in.items()}
-        self.host_rms = torch.empty((n_lens,), dtype=torch.float32).pin_memory()
-        self.host_penalty = torch.zeros((n_lens,), dtype=torch.float32).pin_memory()
-        self.h2d_bytes = sum(v.numel() * 4 for v in self.host_in.values())
-        self.d2h_bytes = sum(v.numel() * 4 for v in self.host_out.values()) + n_lens * 4 * \
-            (2 if penalty_rate is not None else 1)
+        self.host_out = {k: self._host_out_buf[i * per:(i + 1) * per].view(shape)
+                         for i, k in enumerate(self.PARAMS)}
+        self.host_rms = self._host_out_buf[n_par * per:n_par * per + n_lens]
+        self.host_penalty = self._host_out_buf[n_par * per + n_lens:]
+        self._out_slices = (per, n_par * per, n_lens)
+        self.h2d_bytes = self._host_in_buf.numel() * 4
+        self.d2h_bytes = self._host_out_buf.numel() * 4
         with torch.cuda.device(dev):
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -71,8 +83,8 @@ class GraphedSpotStep:
                 self._body()
 
     def _body(self):
-        for k in self.PARAMS:
-            self.dev_in[k].copy_(self.host_in[k], non_blocking=True)
+        self._dev_in_buf.copy_(self._host_in_buf, non_blocking=True)
+        per, grads_end, n_lens = self._out_slices
         leaves = {k: self.dev_in[k].detach().requires_grad_(True) for k in self.PARAMS}
         lens = Lens(self.structure, leaves['c'], leaves['t'], leaves['nd'], leaves['v'])
         if self.penalty_rate is None:
@@ -82,13 +94,13 @@ class GraphedSpotStep:
             res = self.tracer.loss_unsup(self.specs, lens, penalty_rate=self.penalty_rate,
                                          shard=self.shard, group=self.group)
             rms, loss = res['rms'], res['loss_unsup']
-            self.host_penalty.copy_(res['penalty'].detach(), non_blocking=True)
+            self._dev_out_buf[grads_end + n_lens:].copy_(res['penalty'].detach())
         grads = torch.autograd.grad(loss.sum(), [leaves[k] for k in self.PARAMS], allow_unused=True)
-        self.host_rms.copy_(rms.detach(), non_blocking=True)
-        for k, g in zip(self.PARAMS, grads):
-            if g is None:
-                g = torch.zeros_like(leaves[k])
-            self.host_out[k].copy_(g, non_blocking=True)
+        self._dev_out_buf[grads_end:grads_end + n_lens].copy_(rms.detach())
+        for i, g in enumerate(grads):
+            if g is not None:                    # (an unused parameter keeps its zeros)
+                self._dev_out_buf[i * per:(i + 1) * per].copy_(g.reshape(-1))
+        self._host_out_buf.copy_(self._dev_out_buf, non_blocking=True)
 
     def __call__(self, c=None, t=None, nd=None, v=None):
         for k, val in (('c', c), ('t', t), ('nd', nd), ('v', v)):
