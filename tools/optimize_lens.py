@@ -18,7 +18,7 @@ from torchoptics_b200.optimize import optimize_spot     # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--steps', type=int, default=500)
 ap.add_argument('--side', type=int, default=296)
-ap.add_argument('--lr', type=float, default=2e-4)
+ap.add_argument('--lr', type=float, default=5e-5)
 args = ap.parse_args()
 rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
 local = int(os.environ.get('LOCAL_RANK', 0))
