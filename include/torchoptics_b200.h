@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TL_ABI_VERSION 7
+#define TL_ABI_VERSION 8
 
 enum {
   TL_OK = 0,
@@ -237,6 +237,17 @@ int tl_peer_connect(TlPeerComm *comm, const void *all_handles);
 int tl_peer_allreduce_f64(TlPeerComm *comm, const double *data, double *out, int64_t n, void *stream);
 int tl_peer_status(TlPeerComm *comm, int32_t *status_out, uint32_t *epoch_out);
 int tl_peer_destroy(TlPeerComm *comm);
+
+/* Ray aiming (RayTracer.ray_aiming rtl:129-208; one iteration, ray_aiming_mode 'real', no pupil
+ * vignetting function) as one kernel instead of three nested eager traces and two autograd
+ * backward calls: from the staged mu, z, cy, half_epd of tl_stage_fwd it traces the marginal ray
+ * (stop radius, compute_pupil_radius rtl:834-844) and the three 'tee' rays of every (lens, field,
+ * wavelength) to the stop in forward mode and writes the affine pupil map
+ *     aim[b,f,w] = (x_gain, y_gain, y_shift):  x_rel -> x_rel * x_gain,  y_rel -> y_rel * y_gain + y_shift
+ * (rtl:196-206).  Like the reference's (it traces a detached lens, rtl:111) the map carries no
+ * gradient. */
+int tl_aim(const TlLens *lens, const float *mu, const float *z, const float *cy, const float *half_epd,
+           int32_t allow_backward_rays, float *aim, void *stream);
 
 /* Number of kernels this library has launched since it was loaded (bench.py's
  * gpu_launches counter). */

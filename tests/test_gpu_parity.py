@@ -417,3 +417,39 @@ def test_rows_kernel_matches_cta_kernel_on_a_batch_of_lenses(name, monkeypatch):
     for a, b in zip(rows[2], cta[2]):
         assert _rel(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5
     assert abs(float(rows[0][0]) - float(rec['rms'])) <= RMS_TOL * float(rec['rms'])
+
+
+# ---------------------------------------------------------------------------
+# ray aiming on the device
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['cooke_8x8_aimed', 'tessar_8x8_aimed'])
+def test_device_ray_aiming_matches_reference_and_torch_path(name):
+    """tl_aim (one kernel) against (1) the aimed pupil the unmodified reference handed to trace_skew
+    (golden in_x / in_y) and (2) this package's torch mirror of rtl:129-208 (three nested traces +
+    autograd), on the same lens."""
+    golden = load_golden(name)
+    structure = lm.Structure(golden['stop_idx'], sequence=golden['sequence'], default_device=DEV)
+    lens = lm.Lens(structure, *[torch.from_numpy(golden[k]).to(DEV) for k in ('lens_c', 'lens_t', 'lens_nd', 'lens_v')])
+    specs = lm.Specs(structure, torch.from_numpy(golden['epd']).to(DEV), torch.from_numpy(golden['hfov']).to(DEV))
+    kw = dict(mode='circular', n_rays=tuple(int(v) for v in golden['n_rays']),
+              rel_fields=tuple(float(v) for v in golden['rel_fields']),
+              wavelengths=tuple(float(v) for v in golden['wavelengths']), n_ray_aiming_iter=1, default_device=DEV)
+    on_device = rt.RayTracer(**kw)
+    mirror = rt.RayTracer(**kw)
+    mirror.device_aiming = False
+    before = rt.ops.nat.launch_count()
+    args_dev = on_device._ray_set(specs, lens)
+    launched = rt.ops.nat.launch_count() - before
+    args_ref = mirror._ray_set(specs, lens)
+    assert launched == 2                                  # tl_stage_fwd + tl_aim, nothing else of ours
+    scale = float(np.abs(golden['in_y']).max())
+    for j, key in ((0, 'in_x'), (1, 'in_y')):
+        got = args_dev[j].cpu().numpy()
+        assert got.shape == golden[key].shape
+        assert np.abs(got - golden[key]).max() <= 2e-5 * scale, key            # vs the reference
+        assert np.abs(got - args_ref[j].cpu().numpy()).max() <= 2e-5 * scale, key    # vs the torch mirror
+    out = on_device.trace_rays(specs, lens)
+    assert np.array_equal(out[4].cpu().numpy(), golden['out_ok'])
+    assert np.abs(out[1].cpu().numpy() - golden['out_y']).max() <= 5e-5 * np.abs(golden['out_y']).max()
+    rms = rt.compute_rms2d(out[0], out[1], out[4])
+    assert abs(rms.item() - float(golden['rms'])) <= 5e-5 * float(golden['rms'])

@@ -93,6 +93,8 @@ EXPORTS = {
                                           ctypes.c_void_p]),
     'tl_stage_fwd': (ctypes.c_int, [ctypes.POINTER(TlLens)] + [ctypes.c_void_p] * 5),
     'tl_stage_bwd': (ctypes.c_int, [ctypes.POINTER(TlLens)] + [ctypes.c_void_p] * 7),
+    'tl_aim': (ctypes.c_int, [ctypes.POINTER(TlLens)] + [ctypes.c_void_p] * 4 +
+               [ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
     'tl_spot_finalize': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int32] * 4 +
                          [ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(TlSpotOut), ctypes.c_void_p]),
     'tl_penalty_moment_count': (ctypes.c_int32, [ctypes.c_int32]),
@@ -129,7 +131,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.tl_abi_version() != 7:
+    if lib.tl_abi_version() != 8:
         raise NativeLibraryError('libtorchoptics_b200.so: ABI version mismatch, rebuild it')
     _lib = lib
     return lib

@@ -187,6 +187,35 @@ TL_HD double frsqrt(double a) { return 1.0 / sqrt(a); }
 TL_HD float fmin2(float a, float b) { return fminf(a, b); }
 TL_HD double fmin2(double a, double b) { return fmin(a, b); }
 
+// Forward-mode pair: a value with its derivatives along two input directions (the pupil's x and
+// y).  fast_surface / fast_image instantiate with it unchanged, which is how the on-device ray
+// aiming (rtl:129-208) gets d(stop point)/d(pupil point) of its three 'tee' rays without a
+// backward pass.
+struct D2 {
+  float v, a, b;
+  TL_HD D2() {}
+  TL_HD D2(float s) : v(s), a(0.f), b(0.f) {}
+  TL_HD D2(float v_, float a_, float b_) : v(v_), a(a_), b(b_) {}
+};
+TL_HD D2 operator-(D2 p) { return D2(-p.v, -p.a, -p.b); }
+TL_HD D2 operator+(D2 p, D2 q) { return D2(p.v + q.v, p.a + q.a, p.b + q.b); }
+TL_HD D2 operator-(D2 p, D2 q) { return D2(p.v - q.v, p.a - q.a, p.b - q.b); }
+TL_HD D2 operator*(D2 p, D2 q) {
+  return D2(p.v * q.v, ffma(p.a, q.v, p.v * q.a), ffma(p.b, q.v, p.v * q.b));
+}
+TL_HD D2 ffma(D2 p, D2 q, D2 r) {
+  return D2(ffma(p.v, q.v, r.v), ffma(p.a, q.v, ffma(p.v, q.a, r.a)), ffma(p.b, q.v, ffma(p.v, q.b, r.b)));
+}
+TL_HD D2 frcp(D2 p) {
+  const float r = 1.0f / p.v, d = -r * r;
+  return D2(r, d * p.a, d * p.b);
+}
+TL_HD D2 frsqrt(D2 p) {
+  const float r = 1.0f / sqrtf(p.v), d = -0.5f * r / p.v;
+  return D2(r, d * p.a, d * p.b);
+}
+TL_HD D2 fmin2(D2 p, D2 q) { return p.v <= q.v ? p : q; }
+
 template <class T>
 struct Ray {
   T x, y, z, cx, cy, cz;

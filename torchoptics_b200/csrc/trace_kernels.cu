@@ -1223,6 +1223,81 @@ __global__ void k_stage_fwd(TlLens ln, float *mu, float *z, float *cy, float *ha
   }
 }
 
+// Ray aiming on the device (RayTracer.ray_aiming, rtl:129-208, one iteration, 'real' stop radius).
+// One thread per (lens, field, wavelength): trace the on-axis marginal ray at the d line to the stop
+// (the stop radius rs, compute_pupil_radius rtl:834-844), then the three 'tee' rays (lower / upper
+// meridional, sagittal; rtl:353-360) through the surfaces in front of the stop in forward mode (D2:
+// value + derivatives along the pupil's x and y), and from where they land on the stop, in units
+// of rs, build the affine map of the relative pupil coordinates
+//     x_rel -> x_rel * x_gain,   y_rel -> y_rel * y_gain + y_shift            (rtl:196-206)
+// The reference does this with three nested eager traces and two autograd backward calls.
+// A tee ray that fails contributes a zero step, like the reference's isfinite() guard (rtl:189-190).
+template <class T>
+__device__ __forceinline__ bool trace_to_stop(const TlLens &ln, const float *mu_row, bool d_line, int b,
+                                              int n_front, bool allow_backward, Ray<T> &r) {
+  T min_cos2(1.0f);
+  float min_travel = 3.0e38f;
+  bool prev_live = false;
+  float n_prev = 1.0f;
+  for (int s = 0; s < n_front; ++s) {
+    const int64_t i = (int64_t)b * ln.L + s;
+    const bool live = ln.mask[i] != 0;
+    float ratio = 1.0f;
+    if (d_line) {                               // compute_pupil_radius traces at the d line: n = nd
+      const float n_here = live ? nd_at(ln, b, s) : 1.0f;
+      ratio = n_prev / n_here;
+      n_prev = n_here;
+    } else if (live) {
+      ratio = mu_row[s];
+    }
+    T travel;
+    fast_surface(r, T(live ? ln.c[i] : 0.f), T(ratio), T(ratio * ratio), T(live ? ln.t[i] : 0.f), min_cos2,
+                 travel);
+    if (s > 0 && prev_live) min_travel = fminf(min_travel, travel.v);
+    prev_live = live;
+  }
+  const T travel = fast_image(r);
+  if (n_front > 0 && prev_live) min_travel = fminf(min_travel, travel.v);
+  bool ok = min_cos2.v > kGuard && fabsf(r.x.v + r.y.v) < 3.0e38f;
+  if (!allow_backward && min_travel < 0.f) ok = false;
+  return ok;
+}
+
+__global__ void k_aim(TlLens ln, const float *mu, const float *z, const float *cy, const float *half_epd,
+                      int allow_backward, float *aim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ln.B * ln.F * ln.W) return;
+  const int w = i % ln.W, f = (i / ln.W) % ln.F, b = i / (ln.W * ln.F);
+  const int n_front = min(ln.stop_idx[b], ln.L);
+  const float h = half_epd[b], z0 = z[b];
+  const float *mu_row = mu + ((int64_t)b * ln.W + w) * ln.L;
+  // stop radius: marginal ray of the axial field at the d line
+  Ray<D2> m{D2(0.f), D2(h), D2(z0), D2(0.f), D2(0.f), D2(1.0f)};
+  trace_to_stop<D2>(ln, mu_row, true, b, n_front, allow_backward != 0, m);
+  const float rs = m.y.v;
+  // the tee rays of this (field, wavelength)
+  const float dir_y = cy[(int64_t)b * ln.F + f];
+  const float tee_x[3] = {0.f, 0.f, 1.f}, tee_y[3] = {-1.f, 1.f, 0.f};
+  float step_x[3], step_y[3];
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    Ray<D2> r{D2(tee_x[q] * h, h, 0.f), D2(tee_y[q] * h, 0.f, h), D2(z0), D2(0.f), D2(dir_y),
+              fast_cz0(D2(0.f), D2(dir_y))};
+    const bool ok = trace_to_stop<D2>(ln, mu_row, false, b, n_front, allow_backward != 0, r);
+    // d(xs_rel)/d(pupil) summed over the two outputs, as the reference's two backward calls leave it
+    const float xs = ok ? r.x.v / rs : 0.f, ys = ok ? r.y.v / rs : 0.f;
+    const float slope_x = ok ? (r.x.a + r.y.a) / rs : 0.f, slope_y = ok ? (r.x.b + r.y.b) / rs : 0.f;
+    const float sx = -(xs - tee_x[q]) / slope_x, sy = -(ys - tee_y[q]) / slope_y;
+    step_x[q] = (fabsf(sx) <= 3.0e38f) ? sx : 0.f;            // not finite -> no correction
+    step_y[q] = (fabsf(sy) <= 3.0e38f) ? sy : 0.f;
+  }
+  const float y_lo = tee_y[0], y_hi = tee_y[1], x_sag = tee_x[2];
+  float *out = aim + (int64_t)i * 3;
+  out[0] = (x_sag + step_x[2]) / x_sag;
+  out[1] = (y_hi + step_y[1] - (y_lo + step_y[0])) / (y_hi - y_lo);
+  out[2] = (y_lo * step_y[1] - y_hi * step_y[0]) / (y_lo - y_hi);
+}
+
 __global__ void k_stage_bwd(TlLens ln, const float *gmu, const float *gz, float *gc, float *gt,
                             float *gnd, float *gv) {
   const int b = blockIdx.x;
@@ -2093,6 +2168,18 @@ int tl_stage_fwd(const TlLens *lens, float *mu, float *z, float *cy, float *half
   if (rc) return rc;
   if (!mu || !z || !cy || !half_epd) return fail(TL_ERR_INVALID, "NULL output of tl_stage_fwd%s");
   k_stage_fwd<<<lens->B, 128, 0, (cudaStream_t)stream_>>>(*lens, mu, z, cy, half_epd);
+  g_launches++;
+  TL_CHECK_CUDA(cudaGetLastError());
+  return TL_OK;
+}
+
+int tl_aim(const TlLens *lens, const float *mu, const float *z, const float *cy, const float *half_epd,
+           int32_t allow_backward_rays, float *aim, void *stream_) {
+  int rc = validate_lens(lens);
+  if (rc) return rc;
+  if (!mu || !z || !cy || !half_epd || !aim) return fail(TL_ERR_INVALID, "NULL argument of tl_aim%s");
+  const int n = lens->B * lens->F * lens->W;
+  k_aim<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(*lens, mu, z, cy, half_epd, allow_backward_rays, aim);
   g_launches++;
   TL_CHECK_CUDA(cudaGetLastError());
   return TL_OK;

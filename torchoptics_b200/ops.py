@@ -539,6 +539,39 @@ class LensTables:
         return ln
 
 
+def aim_table(c, t, nd, v, hfov, epd, tables, allow_backward_rays=True):
+    """Ray aiming on the device (``RayTracer.ray_aiming`` rtl:129-208: one iteration, 'real' stop
+    radius, no pupil vignetting function): returns ``aim [B,F,W,3] = (x_gain, y_gain, y_shift)`` of
+    the affine pupil map ``x_rel * x_gain, y_rel * y_gain + y_shift`` (rtl:196-206).  Two kernel
+    launches (tl_stage_fwd, tl_aim); no gradient, like the reference's (rtl:111 detaches the lens)."""
+    for name, val in (('c', c), ('t', t), ('nd', nd), ('v', v), ('hfov', hfov), ('epd', epd)):
+        nat.require_cuda(val, name)
+        if val.dtype != torch.float32:
+            raise TypeError(f'{name} must be float32')
+    lib = nat.load()
+    dev = c.device
+    B, L, F, W = tables.B, tables.L, tables.F, tables.W
+    if tuple(c.shape) != (B, L):
+        raise ValueError(f'lens tensors must be [B={B}, L={L}], got {tuple(c.shape)}')
+    if L > 64:
+        raise ValueError('too many surfaces for the staging kernels')
+    with torch.cuda.device(dev), torch.no_grad():
+        cc, tt, ndd, vv = (a.detach().contiguous() for a in (c, t, nd, v))
+        hf, ep = hfov.detach().contiguous(), epd.detach().contiguous()
+        mu = torch.empty((B, W, L), dtype=torch.float32, device=dev)
+        z = torch.empty((B,), dtype=torch.float32, device=dev)
+        cy = torch.empty((B, F), dtype=torch.float32, device=dev)
+        half_epd = torch.empty((B,), dtype=torch.float32, device=dev)
+        aim = torch.empty((B, F, W, 3), dtype=torch.float32, device=dev)
+        ln = tables.lens_struct(cc, tt, ndd, vv, hf, ep)
+        stream = nat.stream_ptr(dev)
+        nat.check(lib.tl_stage_fwd(ctypes.byref(ln), mu.data_ptr(), z.data_ptr(), cy.data_ptr(),
+                                   half_epd.data_ptr(), stream), 'tl_stage_fwd')
+        nat.check(lib.tl_aim(ctypes.byref(ln), mu.data_ptr(), z.data_ptr(), cy.data_ptr(), half_epd.data_ptr(),
+                             int(bool(allow_backward_rays)), aim.data_ptr(), stream), 'tl_aim')
+    return aim
+
+
 class _LensSpotRms(torch.autograd.Function):
     """RayTracer.spot_rms as ONE autograd node over the lens tensors: staging kernel ->
     chief rays -> fused trace+adjoint -> row reduction -> (all-reduce) -> finalize ->

@@ -296,6 +296,7 @@ class RayTracer:
             raise NotImplementedError('the CUDA ray-trace kernels compute in fp32 only')
         self.double_precision = False
         self.arith = arith
+        self.device_aiming = True      # ray aiming as one CUDA kernel where it applies (see ray_aiming)
         self._cache = {}
 
     def _fields(self):
@@ -398,16 +399,19 @@ class RayTracer:
         ext = self._extension_tables(lens)
         general = any(v is not None for v in ext.values())
         if staged and plain and not general and self.mode != 'skew_random' and lens.c.shape[1] <= 64:
-            key = ('tables', id(lens.structure))
-            if key not in self._cache:
-                self._cache[key] = ops.LensTables(lens.structure, self.rel_fields, self.wavelengths,
-                                                  self.default_device)
             x_rel, y_rel = self._pupil(None)
             return ops.lens_spot_rms(lens.c, lens.t, lens.nd, lens.v, specs.hfov, specs.epd, x_rel,
-                                     y_rel, self._cache[key], self.allow_backward_rays,
+                                     y_rel, self._tables(lens), self.allow_backward_rays,
                                      _arith_code(self.arith), shard, group)
         args = self._ray_set(specs, lens, use_vig)
         return ops.spot_rms(*args, self.allow_backward_rays, _arith_code(self.arith), shard, group, **ext)
+
+    def _tables(self, lens):
+        key = ('tables', id(lens.structure))
+        if key not in self._cache:
+            self._cache[key] = ops.LensTables(lens.structure, self.rel_fields, self.wavelengths,
+                                              self.default_device)
+        return self._cache[key]
 
     # -- ray aiming (rtl:129-208) ---------------------------------------------
     def ray_aiming(self, specs, lens, use_vig):
@@ -416,9 +420,19 @@ class RayTracer:
         Returns a function (xp_rel, yp_rel) -> corrected (xp_rel, yp_rel)."""
         if (lens.structure.stop_idx == 0).all():
             return lambda xp_rel, yp_rel: (xp_rel, yp_rel)
+        dev = self.default_device
+        on_device = (self.device_aiming and self.ray_aiming_mode == 'real' and self.n_ray_aiming_iter == 1
+                     and not (use_vig and self.vig_fn) and lens.c.is_cuda and lens.c.shape[1] <= 64
+                     and getattr(lens, 'k', None) is None and getattr(lens, 'a', None) is None
+                     and getattr(lens, 'sd', None) is None)
+        if on_device:
+            # one kernel (tl_aim) instead of three nested traces and two backward calls
+            gains = ops.aim_table(lens.c, lens.t, lens.nd, lens.v, specs.hfov, specs.epd, self._tables(lens),
+                                  self.allow_backward_rays)                       # [B,F,W,3]
+            x_gain, y_gain, y_shift = (gains[..., j].unsqueeze(2) for j in range(3))   # [B,F,1,W]
+            return lambda xp_rel, yp_rel: (xp_rel * x_gain, yp_rel * y_gain + y_shift)
         specs2stop = specs.up_to_stop()
         lens2stop = lens.up_to_stop()
-        dev = self.default_device
         if self.ray_aiming_mode == 'paraxial':
             stop_radius = compute_magnification(lens2stop) * specs2stop.epd / 2
         elif self.ray_aiming_mode == 'real':
