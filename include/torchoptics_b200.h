@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TL_ABI_VERSION 8
+#define TL_ABI_VERSION 9
 
 enum {
   TL_OK = 0,
@@ -84,6 +84,12 @@ typedef struct TlProblem {
   const float *k;              /* [B,S]   conic constants (NULL = 0)                */
   const float *a;              /* [B,S,7] a4, a6, ..., a16 (NULL = 0)               */
   const float *sd;             /* [B,S]   clear semi-diameters (NULL = +inf)        */
+  /* Ray-aiming map of tl_aim, [B,F,W,3] = (x_gain, y_gain, y_shift), or NULL: x and y are then
+   * RELATIVE pupil coordinates and every kernel forms clamp(x * x_gain, -2, 2) * xy_scale[b] and
+   * clamp(y * y_gain + y_shift, -2, 2) * xy_scale[b] on load (rtl:109-114), so that an aimed ray
+   * set never has to be materialised as [B,F,P,W] tensors.  Spherical lenses only; not together
+   * with per-ray gradients of x / y. */
+  const float *aim;
 } TlProblem;
 
 /* Outputs of trace_skew, each a contiguous [B,F,P,W] array. */

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_argument_checks():
     lib = _native.load()
-    assert lib.tl_abi_version() == 8
+    assert lib.tl_abi_version() == 9
     assert lib.tl_spot_moment_count(11, 1) == 6 * 11 + 5
     assert lib.tl_spot_moment_count(11, 0) == 3
     assert lib.tl_rms_workspace(1, 3, 64, 3) > 0
@@ -40,6 +40,6 @@ def test_abi_version_and_argument_checks():
 def test_struct_layout_matches_header():
     # TlStrided = pointer + 4 x int64; TlProblem packs 5 of them, 4 pointers, 9 int32
     assert ctypes.sizeof(_native.TlStrided) == 40
-    assert ctypes.sizeof(_native.TlProblem) == 5 * 40 + 4 * 8 + 9 * 4 + 4 + 8 + 3 * 8
+    assert ctypes.sizeof(_native.TlProblem) == 5 * 40 + 4 * 8 + 9 * 4 + 4 + 8 + 3 * 8 + 8
     assert ctypes.sizeof(_native.TlLens) == 11 * 8 + 4 * 4
     assert ctypes.sizeof(_native.TlGrads) == 11 * 8

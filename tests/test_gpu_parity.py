@@ -453,3 +453,33 @@ def test_device_ray_aiming_matches_reference_and_torch_path(name):
     assert np.abs(out[1].cpu().numpy() - golden['out_y']).max() <= 5e-5 * np.abs(golden['out_y']).max()
     rms = rt.compute_rms2d(out[0], out[1], out[4])
     assert abs(rms.item() - float(golden['rms'])) <= 5e-5 * float(golden['rms'])
+
+
+@pytest.mark.parametrize('name', ['cooke_8x8_aimed', 'tessar_8x8_aimed'])
+def test_staged_fused_pass_with_ray_aiming(name):
+    """RayTracer.spot_rms with ray aiming stays on the staged path (tl_stage_fwd -> tl_aim -> fused
+    kernel applying the map on load): same RMS and gradients as the unstaged path that
+    materialises the aimed [B,F,P,W] pupil, and the reference's RMS."""
+    golden = load_golden(name)
+    structure = lm.Structure(golden['stop_idx'], sequence=golden['sequence'], default_device=DEV)
+    specs = lm.Specs(structure, torch.from_numpy(golden['epd']).to(DEV), torch.from_numpy(golden['hfov']).to(DEV))
+    tracer = rt.RayTracer(mode='circular', n_rays=tuple(int(v) for v in golden['n_rays']),
+                          rel_fields=tuple(float(v) for v in golden['rel_fields']),
+                          wavelengths=tuple(float(v) for v in golden['wavelengths']), n_ray_aiming_iter=1,
+                          default_device=DEV)
+
+    def run(staged):
+        lens = lm.Lens(structure, *[torch.from_numpy(golden[k]).to(DEV).requires_grad_(True)
+                                    for k in ('lens_c', 'lens_t', 'lens_nd', 'lens_v')])
+        before = rt.ops.nat.launch_count()
+        rms, _ = tracer.spot_rms(specs, lens, staged=staged)
+        grads = torch.autograd.grad(rms[0], [lens.c, lens.t, lens.nd])
+        return rms.detach(), grads, rt.ops.nat.launch_count() - before
+
+    rms_s, g_s, n_s = run(True)
+    rms_u, g_u, n_u = run(False)
+    assert n_s <= 8                                   # stage, aim, chief, trace+adjoint, reduce, finalize, chain rule
+    assert abs(float(rms_s[0]) - float(rms_u[0])) <= RMS_TOL * float(rms_u[0])
+    assert abs(float(rms_s[0]) - float(golden['rms'])) <= 5e-5 * float(golden['rms'])
+    for a, b in zip(g_s, g_u):
+        assert _rel(a.cpu().numpy(), b.cpu().numpy()) <= GRAD_TOL

@@ -39,7 +39,8 @@ class TlProblem(ctypes.Structure):
                 ('allow_backward_rays', ctypes.c_int32), ('arith', ctypes.c_int32),
                 ('p_begin', ctypes.c_int32), ('p_end', ctypes.c_int32),
                 ('xy_scale', ctypes.c_void_p),
-                ('k', ctypes.c_void_p), ('a', ctypes.c_void_p), ('sd', ctypes.c_void_p)]
+                ('k', ctypes.c_void_p), ('a', ctypes.c_void_p), ('sd', ctypes.c_void_p),
+                ('aim', ctypes.c_void_p)]
 
 
 class TlTraceOut(ctypes.Structure):
@@ -131,7 +132,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.tl_abi_version() != 8:
+    if lib.tl_abi_version() != 9:
         raise NativeLibraryError('libtorchoptics_b200.so: ABI version mismatch, rebuild it')
     _lib = lib
     return lib

@@ -75,6 +75,25 @@ __device__ __forceinline__ int64_t offset_of(const TlStrided &s, int b, int f, i
          (int64_t)w * s.stride[3];
 }
 
+// Entrance-pupil point of ray (b, f, q, w): the caller's x, y, through the ray-aiming map of
+// (lens, field, wavelength) when there is one -- x_rel * x_gain, y_rel * y_gain + y_shift, clamped
+// to [-2, 2] (rtl:109-112, :196-206) -- and scaled to the entrance pupil (scale_to_epd rtl:497-507).
+// Every step is one individually rounded operation, like the reference's eager ops.
+__device__ __forceinline__ void load_pupil_point(const TlProblem &pb, int b, int f, int q, int w,
+                                                 float xy_scale, float &x, float &y) {
+  x = pb.x.ptr[offset_of(pb.x, b, f, q, w)];
+  y = pb.y.ptr[offset_of(pb.y, b, f, q, w)];
+  if (pb.aim) {
+    const float *a = pb.aim + (((int64_t)b * pb.F + f) * pb.W + w) * 3;
+    x = fminf(fmaxf(__fmul_rn(x, a[0]), -2.0f), 2.0f);
+    y = fminf(fmaxf(__fadd_rn(__fmul_rn(y, a[1]), a[2]), -2.0f), 2.0f);
+  }
+  if (pb.xy_scale) {
+    x = __fmul_rn(x, xy_scale);
+    y = __fmul_rn(y, xy_scale);
+  }
+}
+
 // Surface table of one (lens, wavelength) in shared memory.
 struct Table {
   float *c, *t, *mu, *mu2;
@@ -287,12 +306,9 @@ k_trace_fwd(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
     const bool has1 = p1 < p_hi;
     const int q1 = has1 ? p1 : p0;
     const float xy_scale = pb.xy_scale ? pb.xy_scale[b] : 1.0f;
-    f2 x(pb.x.ptr[offset_of(pb.x, b, f, p0, w)], pb.x.ptr[offset_of(pb.x, b, f, q1, w)]);
-    f2 y(pb.y.ptr[offset_of(pb.y, b, f, p0, w)], pb.y.ptr[offset_of(pb.y, b, f, q1, w)]);
-    if (pb.xy_scale) {          // one rounding per coordinate, like y * epd / 2 (rtl:505)
-      x = x * f2(xy_scale);
-      y = y * f2(xy_scale);
-    }
+    f2 x, y;
+    load_pupil_point(pb, b, f, p0, w, xy_scale, x.v.x, y.v.x);
+    load_pupil_point(pb, b, f, q1, w, xy_scale, x.v.y, y.v.y);
     const f2 z(pb.z.ptr[offset_of(pb.z, b, f, p0, w)], pb.z.ptr[offset_of(pb.z, b, f, q1, w)]);
     const f2 cx(pb.cx.ptr[offset_of(pb.cx, b, f, p0, w)], pb.cx.ptr[offset_of(pb.cx, b, f, q1, w)]);
     const f2 cy(pb.cy.ptr[offset_of(pb.cy, b, f, p0, w)], pb.cy.ptr[offset_of(pb.cy, b, f, q1, w)]);
@@ -351,12 +367,8 @@ k_trace_fwd_pw(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
       tab.live = reinterpret_cast<int *>(base + 4 * S);
       tab.length = length;
     }
-    float x = pb.x.ptr[offset_of(pb.x, b, f, p, w)];
-    float y = pb.y.ptr[offset_of(pb.y, b, f, p, w)];
-    if (pb.xy_scale) {
-      x = __fmul_rn(x, xy_scale);
-      y = __fmul_rn(y, xy_scale);
-    }
+    float x, y;
+    load_pupil_point(pb, b, f, p, w, xy_scale, x, y);
     const float z = pb.z.ptr[offset_of(pb.z, b, f, p, w)];
     const float cx = pb.cx.ptr[offset_of(pb.cx, b, f, p, w)];
     const float cy = pb.cy.ptr[offset_of(pb.cy, b, f, p, w)];
@@ -583,8 +595,10 @@ k_trace_adj(TlProblem pb, AdjArgs args) {
       has[l] = p < pb.p_end;
       const int q = has[l] ? p : p_base;          // past the end: a copy of lane 0 (p_base is valid)
       o[l] = (((int64_t)b * pb.F + f) * pb.P + q) * pb.W + w;
-      lane_set(x, l, __fmul_rn(pb.x.ptr[offset_of(pb.x, b, f, q, w)], xy_scale));
-      lane_set(y, l, __fmul_rn(pb.y.ptr[offset_of(pb.y, b, f, q, w)], xy_scale));
+      float px, py;
+      load_pupil_point(pb, b, f, q, w, xy_scale, px, py);
+      lane_set(x, l, px);
+      lane_set(y, l, py);
       lane_set(z, l, pb.z.ptr[offset_of(pb.z, b, f, q, w)]);
       lane_set(cx, l, pb.cx.ptr[offset_of(pb.cx, b, f, q, w)]);
       lane_set(cy, l, pb.cy.ptr[offset_of(pb.cy, b, f, q, w)]);
@@ -829,8 +843,10 @@ k_spot_rows(TlProblem pb, const float *ref_y, double *moments, int n_acc) {
         const int p = p_base + l * 32;
         has[l] = p < pb.p_end;
         const int q = has[l] ? p : p_base;
-        lane_set(x, l, __fmul_rn(pb.x.ptr[offset_of(pb.x, b, f, q, w)], xy_scale));
-        lane_set(y, l, __fmul_rn(pb.y.ptr[offset_of(pb.y, b, f, q, w)], xy_scale));
+        float px, py;
+        load_pupil_point(pb, b, f, q, w, xy_scale, px, py);
+        lane_set(x, l, px);
+        lane_set(y, l, py);
         lane_set(z, l, pb.z.ptr[offset_of(pb.z, b, f, q, w)]);
         lane_set(cx, l, pb.cx.ptr[offset_of(pb.cx, b, f, q, w)]);
         lane_set(cy, l, pb.cy.ptr[offset_of(pb.cy, b, f, q, w)]);
@@ -1379,6 +1395,8 @@ int validate(const TlProblem *pb, int max_s) {
     return fail(TL_ERR_INVALID, "unknown arithmetic policy%s");
   if ((int64_t)pb->B * pb->F * pb->W > (1 << 24))
     return fail(TL_ERR_INVALID, "B*F*W too large%s");
+  if (pb->aim && is_general(*pb))
+    return fail(TL_ERR_INVALID, "the ray-aiming map is for spherical lenses only (not with k / a / sd)%s");
   return TL_OK;
 }
 
@@ -1586,8 +1604,10 @@ k_penalty_rows(TlProblem pb, double *moments, int n_acc) {
         const int p = p_base + l * 32;
         has[l] = p < pb.p_end;
         const int q = has[l] ? p : p_base;
-        lane_set(x, l, __fmul_rn(pb.x.ptr[offset_of(pb.x, b, f, q, w)], xy_scale));
-        lane_set(y, l, __fmul_rn(pb.y.ptr[offset_of(pb.y, b, f, q, w)], xy_scale));
+        float px, py;
+        load_pupil_point(pb, b, f, q, w, xy_scale, px, py);
+        lane_set(x, l, px);
+        lane_set(y, l, py);
         lane_set(z, l, pb.z.ptr[offset_of(pb.z, b, f, q, w)]);
         lane_set(cx, l, pb.cx.ptr[offset_of(pb.cx, b, f, q, w)]);
         lane_set(cy, l, pb.cy.ptr[offset_of(pb.cy, b, f, q, w)]);
@@ -1879,6 +1899,8 @@ int tl_trace_bwd(const TlProblem *pb_, const TlSeeds *seeds, const TlGrads *grad
   if (rc) return rc;
   if (!seeds || !grads || !grads->gc || !grads->gt || !grads->gmu || !grads->gz_sum)
     return fail(TL_ERR_INVALID, "NULL seeds/grads%s");
+  if (pb_->aim && (grads->gx || grads->gy))
+    return fail(TL_ERR_INVALID, "per-ray gradients of x / y are not available through a ray-aiming map%s");
   if (is_general(*pb_)) {
     if (seeds->gz_relu || seeds->gtheta || seeds->gtheta_prime)
       return fail(TL_ERR_INVALID, "the aggregate=True stacks exist for spherical lenses only (no seeds on them with k / a / sd)%s");

@@ -579,7 +579,7 @@ class _LensSpotRms(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, shard,
-                group, grad_on):
+                group, grad_on, aimed=False):
         for name, val in (('c', c), ('t', t), ('nd', nd), ('v', v), ('hfov', hfov), ('epd', epd),
                           ('x', x_rel), ('y', y_rel)):
             nat.require_cuda(val, name)
@@ -609,8 +609,15 @@ class _LensSpotRms(torch.autograd.Function):
             stream = nat.stream_ptr(dev)
             nat.check(lib.tl_stage_fwd(ctypes.byref(ln), mu.data_ptr(), z.data_ptr(), cy.data_ptr(),
                                        half_epd.data_ptr(), stream), 'tl_stage_fwd')
+            aim = None
+            if aimed:      # ray aiming (rtl:129-208) as one more kernel; the map is applied on load
+                aim = torch.empty((B, F, W, 3), dtype=torch.float32, device=dev)
+                nat.check(lib.tl_aim(ctypes.byref(ln), mu.data_ptr(), z.data_ptr(), cy.data_ptr(),
+                                     half_epd.data_ptr(), int(bool(allow_backward_rays)), aim.data_ptr(),
+                                     stream), 'tl_aim')
             shape = (B, F, P, W)
             pb = nat.TlProblem()
+            pb.aim = _ptr(aim)
             pb.x = nat.strided(x_rel.detach(), shape)
             pb.y = nat.strided(y_rel.detach(), shape)
             pb.z = nat.strided(z.reshape(B, 1, 1, 1), shape)
@@ -663,12 +670,14 @@ class _LensSpotRms(torch.autograd.Function):
         need = ctx.needs_input_grad
         grads = [(gc * g) if need[0] else None, (gt * g) if need[1] else None,
                  (gnd * g) if need[2] else None, (gv * g) if need[3] else None]
-        return (*grads, None, None, None, None, None, None, None, None, None, None)
+        return (*grads, None, None, None, None, None, None, None, None, None, None, None)
 
 
 def lens_spot_rms(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays=True,
-                  arith=nat.ARITH_GUARDED, shard=(0, 1), group=None):
+                  arith=nat.ARITH_GUARDED, shard=(0, 1), group=None, aimed=False):
     """(rms [B], rms_field [B,F]) of a lens batch given as padded [B,L] tensors, differentiable
-    w.r.t. c, t, nd, v.  x_rel, y_rel: relative pupil coordinates [1,1,P,1]."""
+    w.r.t. c, t, nd, v.  x_rel, y_rel: relative pupil coordinates [1,1,P,1].  ``aimed``: with one
+    iteration of 'real' ray aiming (rtl:129-208) done by tl_aim and applied inside the kernels."""
     return _LensSpotRms.apply(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, bool(allow_backward_rays),
-                              int(arith), (int(shard[0]), int(shard[1])), group, torch.is_grad_enabled())
+                              int(arith), (int(shard[0]), int(shard[1])), group, torch.is_grad_enabled(),
+                              bool(aimed))

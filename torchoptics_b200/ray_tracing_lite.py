@@ -393,16 +393,23 @@ class RayTracer:
 
         ``staged`` (default): the ray set (index model, pupil position, field cosines) and its
         chain rule also run as two small CUDA kernels; it applies when there is no pupil
-        vignetting function, no ray aiming and a deterministic pupil sampler, otherwise the
-        torch front end of :meth:`trace_rays` feeds the fused pass."""
-        plain = (self.vig_fn is None or not use_vig) and self.n_ray_aiming_iter == 0
+        vignetting function, a deterministic pupil sampler and either no ray aiming or the aiming
+        the device kernel covers (one iteration, 'real' stop radius: tl_aim, applied on load inside
+        the trace kernels); otherwise the torch front end of :meth:`trace_rays` feeds the fused pass."""
+        no_vig = self.vig_fn is None or not use_vig
+        # ray aiming stays on the staged path when the device kernel covers it (one iteration,
+        # 'real' stop radius); a lens batch whose stops are all in front needs none (rtl:131-133)
+        stops_in_front = bool((np.asarray(lens.structure.stop_idx) == 0).all())
+        aimed = (self.n_ray_aiming_iter == 1 and self.ray_aiming_mode == 'real' and self.device_aiming
+                 and not stops_in_front)
+        plain = no_vig and (self.n_ray_aiming_iter == 0 or aimed or stops_in_front)
         ext = self._extension_tables(lens)
         general = any(v is not None for v in ext.values())
         if staged and plain and not general and self.mode != 'skew_random' and lens.c.shape[1] <= 64:
             x_rel, y_rel = self._pupil(None)
             return ops.lens_spot_rms(lens.c, lens.t, lens.nd, lens.v, specs.hfov, specs.epd, x_rel,
                                      y_rel, self._tables(lens), self.allow_backward_rays,
-                                     _arith_code(self.arith), shard, group)
+                                     _arith_code(self.arith), shard, group, aimed=aimed)
         args = self._ray_set(specs, lens, use_vig)
         return ops.spot_rms(*args, self.allow_backward_rays, _arith_code(self.arith), shard, group, **ext)
 
