@@ -483,3 +483,26 @@ def test_staged_fused_pass_with_ray_aiming(name):
     assert abs(float(rms_s[0]) - float(golden['rms'])) <= 5e-5 * float(golden['rms'])
     for a, b in zip(g_s, g_u):
         assert _rel(a.cpu().numpy(), b.cpu().numpy()) <= GRAD_TOL
+
+
+def test_spot_rms_and_grads_matches_autograd_and_writes_into_given_buffers():
+    """The autograd-free staged call (what GraphedSpotStep replays) against autograd over spot_rms,
+    with and without caller-provided output views of one packed buffer."""
+    specs, lens = prescriptions.double_gauss(DEV)
+    tracer = rt.RayTracer(mode='circular', n_rays=(40, 40), rel_fields=(0., 0.5, 1.), wavelengths=('C', 'd', 'F'),
+                          default_device=DEV)
+    leaves = {k: getattr(lens, k).detach().clone().requires_grad_(True) for k in ('c', 't', 'nd', 'v')}
+    rms, _ = tracer.spot_rms(specs, lm.Lens(lens.structure, *leaves.values()))
+    want = torch.autograd.grad(rms.sum(), list(leaves.values()))
+    got_rms, got = tracer.spot_rms_and_grads(specs, lens)
+    assert torch.equal(got_rms, rms.detach())
+    for k, w in zip(('c', 't', 'nd', 'v'), want):
+        assert torch.equal(got[k], w), k
+    per, B = lens.c.numel(), lens.c.shape[0]
+    buf = torch.full((4 * per + B,), float('nan'), device=DEV)
+    out = {name: buf[i * per:(i + 1) * per].view(lens.c.shape) for i, name in enumerate(('gc', 'gt', 'gnd', 'gv'))}
+    out['rms'] = buf[4 * per:]
+    tracer.spot_rms_and_grads(specs, lens, out=out)
+    assert torch.equal(buf[4 * per:], rms.detach())
+    for i, w in enumerate(want):
+        assert torch.equal(buf[i * per:(i + 1) * per].view(lens.c.shape), w)

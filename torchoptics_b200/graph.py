@@ -85,16 +85,23 @@ class GraphedSpotStep:
     def _body(self):
         self._dev_in_buf.copy_(self._host_in_buf, non_blocking=True)
         per, grads_end, n_lens = self._out_slices
+        if self.penalty_rate is None:
+            # the bare kernel sequence writing straight into the packed result buffer: no autograd
+            # node, no elementwise glue, no per-tensor copies
+            buf = self._dev_out_buf
+            out = {'rms': buf[grads_end:grads_end + n_lens]}
+            for i, name in enumerate(('gc', 'gt', 'gnd', 'gv')):
+                out[name] = buf[i * per:(i + 1) * per].view(self.dev_in['c'].shape)
+            lens = Lens(self.structure, *(self.dev_in[k] for k in self.PARAMS))
+            self.tracer.spot_rms_and_grads(self.specs, lens, shard=self.shard, group=self.group, out=out)
+            self._host_out_buf.copy_(buf, non_blocking=True)
+            return
         leaves = {k: self.dev_in[k].detach().requires_grad_(True) for k in self.PARAMS}
         lens = Lens(self.structure, leaves['c'], leaves['t'], leaves['nd'], leaves['v'])
-        if self.penalty_rate is None:
-            rms, _ = self.tracer.spot_rms(self.specs, lens, shard=self.shard, group=self.group)
-            loss = rms
-        else:
-            res = self.tracer.loss_unsup(self.specs, lens, penalty_rate=self.penalty_rate,
-                                         shard=self.shard, group=self.group)
-            rms, loss = res['rms'], res['loss_unsup']
-            self._dev_out_buf[grads_end + n_lens:].copy_(res['penalty'].detach())
+        res = self.tracer.loss_unsup(self.specs, lens, penalty_rate=self.penalty_rate,
+                                     shard=self.shard, group=self.group)
+        rms, loss = res['rms'], res['loss_unsup']
+        self._dev_out_buf[grads_end + n_lens:].copy_(res['penalty'].detach())
         grads = torch.autograd.grad(loss.sum(), [leaves[k] for k in self.PARAMS], allow_unused=True)
         self._dev_out_buf[grads_end:grads_end + n_lens].copy_(rms.detach())
         for i, g in enumerate(grads):

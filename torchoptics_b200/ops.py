@@ -572,94 +572,123 @@ def aim_table(c, t, nd, v, hfov, epd, tables, allow_backward_rays=True):
     return aim
 
 
+def _lens_spot_core(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, shard, group,
+                    want_grad, aimed, out=None):
+    """The staged fused pass itself (no autograd): staging kernel -> (ray aiming) -> chief rays ->
+    fused trace+adjoint -> row reduction -> (all-reduce) -> finalize -> staging chain rule.
+    Returns (rms [B], rms_field [B,F], gc, gt, gnd, gv) -- the four gradients of sum(rms) w.r.t. the
+    padded [B,L] lens tensors, or None without ``want_grad``.  ``out``: optional dict of
+    preallocated float32 tensors 'rms' [B] and 'gc', 'gt', 'gnd', 'gv' [B,L] to write into (a
+    caller that owns a packed staging buffer passes views of it and saves the copies)."""
+    for name, val in (('c', c), ('t', t), ('nd', nd), ('v', v), ('hfov', hfov), ('epd', epd),
+                      ('x', x_rel), ('y', y_rel)):
+        nat.require_cuda(val, name)
+        if val.dtype != torch.float32:
+            raise TypeError(f'{name} must be float32')
+    lib = nat.load()
+    dev = c.device
+    out = out or {}
+    B, L, F, W = tables.B, tables.L, tables.F, tables.W
+    if tuple(c.shape) != (B, L):
+        raise ValueError(f'lens tensors must be [B={B}, L={L}], got {tuple(c.shape)}')
+    if L > (nat.MAX_SURFACES_SPOT if want_grad else 64):
+        raise ValueError('too many surfaces for the fused lens pass')
+    P = x_rel.shape[2]
+    rank, world = shard
+    p_begin, p_end = pupil_slice(P, rank, world)
+
+    def buffer(name, shape):
+        given = out.get(name)
+        if given is None:
+            return torch.empty(shape, dtype=torch.float32, device=dev)
+        if tuple(given.shape) != tuple(shape) or given.dtype != torch.float32 or not given.is_contiguous():
+            raise ValueError(f'out[{name!r}] must be a contiguous float32 tensor of shape {tuple(shape)}')
+        return given
+
+    with torch.cuda.device(dev):
+        cc, tt, ndd, vv = (a.detach().contiguous() for a in (c, t, nd, v))
+        hf, ep = hfov.detach().contiguous(), epd.detach().contiguous()
+        mu = torch.empty((B, W, L), dtype=torch.float32, device=dev)
+        z = torch.empty((B,), dtype=torch.float32, device=dev)
+        cy = torch.empty((B, F), dtype=torch.float32, device=dev)
+        half_epd = torch.empty((B,), dtype=torch.float32, device=dev)
+        ln = tables.lens_struct(cc, tt, ndd, vv, hf, ep)
+        stream = nat.stream_ptr(dev)
+        nat.check(lib.tl_stage_fwd(ctypes.byref(ln), mu.data_ptr(), z.data_ptr(), cy.data_ptr(),
+                                   half_epd.data_ptr(), stream), 'tl_stage_fwd')
+        aim = None
+        if aimed:      # ray aiming (rtl:129-208) as one more kernel; the map is applied on load
+            aim = torch.empty((B, F, W, 3), dtype=torch.float32, device=dev)
+            nat.check(lib.tl_aim(ctypes.byref(ln), mu.data_ptr(), z.data_ptr(), cy.data_ptr(),
+                                 half_epd.data_ptr(), int(bool(allow_backward_rays)), aim.data_ptr(),
+                                 stream), 'tl_aim')
+        shape = (B, F, P, W)
+        pb = nat.TlProblem()
+        pb.aim = _ptr(aim)
+        pb.x = nat.strided(x_rel.detach(), shape)
+        pb.y = nat.strided(y_rel.detach(), shape)
+        pb.z = nat.strided(z.reshape(B, 1, 1, 1), shape)
+        pb.cx = nat.strided(tables.zero, shape)
+        pb.cy = nat.strided(cy.reshape(B, F, 1, 1), shape)
+        pb.c, pb.t, pb.mu, pb.live = cc.data_ptr(), tt.data_ptr(), mu.data_ptr(), tables.mask.data_ptr()
+        pb.B, pb.F, pb.P, pb.W, pb.S = B, F, P, W, L
+        pb.allow_backward_rays, pb.arith = int(bool(allow_backward_rays)), int(arith)
+        pb.p_begin, pb.p_end = p_begin, p_end
+        pb.xy_scale = half_epd.data_ptr()
+        n_acc = lib.tl_spot_moment_count(L, int(want_grad))
+        moments = torch.empty((B, F, W, n_acc), dtype=torch.float64, device=dev)
+        ref_y = torch.empty((B, F), dtype=torch.float32, device=dev)
+        ws_bytes = lib.tl_spot_workspace(ctypes.byref(pb), int(want_grad))
+        if ws_bytes == 0:
+            nat.check(-1, 'tl_spot_workspace')
+        ws = torch.empty((ws_bytes // 8,), dtype=torch.float64, device=dev)
+        nat.check(lib.tl_spot_accumulate(ctypes.byref(pb), int(want_grad), moments.data_ptr(),
+                                         ref_y.data_ptr(), ws.data_ptr(), ws_bytes, stream),
+                  'tl_spot_accumulate')
+        if world > 1:
+            moments = reduce_moments(moments, group)
+        rms = buffer('rms', (B,))
+        rms_field = torch.empty((B, F), dtype=torch.float32, device=dev)
+        gc = gt = gnd = gv = None
+        if want_grad:
+            gc, gt = buffer('gc', (B, L)), buffer('gt', (B, L))
+            gmu = torch.empty((B, W, L), dtype=torch.float32, device=dev)
+            gz = torch.empty((B,), dtype=torch.float32, device=dev)
+            spot_out = nat.TlSpotOut(rms.data_ptr(), rms_field.data_ptr(), gc.data_ptr(), gt.data_ptr(),
+                                     gmu.data_ptr(), gz.data_ptr())
+        else:
+            spot_out = nat.TlSpotOut(rms.data_ptr(), rms_field.data_ptr(), None, None, None, None)
+        nat.check(lib.tl_spot_finalize(moments.data_ptr(), ref_y.data_ptr(), B, F, W, L, P,
+                                       int(want_grad), ctypes.byref(spot_out), stream), 'tl_spot_finalize')
+        if want_grad:
+            gnd, gv = buffer('gnd', (B, L)), buffer('gv', (B, L))
+            if (out.get('gnd') is not None and out.get('gv') is not None
+                    and gv.data_ptr() == gnd.data_ptr() + gnd.numel() * 4):
+                torch.as_strided(gnd, (2 * gnd.numel(),), (1,)).zero_()      # adjacent views: one fill
+            else:
+                gnd.zero_()
+                gv.zero_()
+            nat.check(lib.tl_stage_bwd(ctypes.byref(ln), gmu.data_ptr(), gz.data_ptr(), gc.data_ptr(),
+                                       gt.data_ptr(), gnd.data_ptr(), gv.data_ptr(), stream),
+                      'tl_stage_bwd')
+    return rms, rms_field, gc, gt, gnd, gv
+
+
 class _LensSpotRms(torch.autograd.Function):
-    """RayTracer.spot_rms as ONE autograd node over the lens tensors: staging kernel ->
-    chief rays -> fused trace+adjoint -> row reduction -> (all-reduce) -> finalize ->
-    staging chain rule.  Seven kernel launches, no per-ray tensor."""
+    """RayTracer.spot_rms as ONE autograd node over the lens tensors (see _lens_spot_core).
+    Seven kernel launches (eight with ray aiming), no per-ray tensor."""
 
     @staticmethod
     def forward(ctx, c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, shard,
                 group, grad_on, aimed=False):
-        for name, val in (('c', c), ('t', t), ('nd', nd), ('v', v), ('hfov', hfov), ('epd', epd),
-                          ('x', x_rel), ('y', y_rel)):
-            nat.require_cuda(val, name)
-            if val.dtype != torch.float32:
-                raise TypeError(f'{name} must be float32')
         if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
             raise ValueError('the fused lens pass does not differentiate w.r.t. hfov / epd')
-        lib = nat.load()
-        dev = c.device
-        B, L, F, W = tables.B, tables.L, tables.F, tables.W
-        if tuple(c.shape) != (B, L):
-            raise ValueError(f'lens tensors must be [B={B}, L={L}], got {tuple(c.shape)}')
         want_grad = grad_on and any(ctx.needs_input_grad[:4])
-        if L > (nat.MAX_SURFACES_SPOT if want_grad else 64):
-            raise ValueError('too many surfaces for the fused lens pass')
-        P = x_rel.shape[2]
-        rank, world = shard
-        p_begin, p_end = pupil_slice(P, rank, world)
-        with torch.cuda.device(dev):
-            cc, tt, ndd, vv = (a.detach().contiguous() for a in (c, t, nd, v))
-            hf, ep = hfov.detach().contiguous(), epd.detach().contiguous()
-            mu = torch.empty((B, W, L), dtype=torch.float32, device=dev)
-            z = torch.empty((B,), dtype=torch.float32, device=dev)
-            cy = torch.empty((B, F), dtype=torch.float32, device=dev)
-            half_epd = torch.empty((B,), dtype=torch.float32, device=dev)
-            ln = tables.lens_struct(cc, tt, ndd, vv, hf, ep)
-            stream = nat.stream_ptr(dev)
-            nat.check(lib.tl_stage_fwd(ctypes.byref(ln), mu.data_ptr(), z.data_ptr(), cy.data_ptr(),
-                                       half_epd.data_ptr(), stream), 'tl_stage_fwd')
-            aim = None
-            if aimed:      # ray aiming (rtl:129-208) as one more kernel; the map is applied on load
-                aim = torch.empty((B, F, W, 3), dtype=torch.float32, device=dev)
-                nat.check(lib.tl_aim(ctypes.byref(ln), mu.data_ptr(), z.data_ptr(), cy.data_ptr(),
-                                     half_epd.data_ptr(), int(bool(allow_backward_rays)), aim.data_ptr(),
-                                     stream), 'tl_aim')
-            shape = (B, F, P, W)
-            pb = nat.TlProblem()
-            pb.aim = _ptr(aim)
-            pb.x = nat.strided(x_rel.detach(), shape)
-            pb.y = nat.strided(y_rel.detach(), shape)
-            pb.z = nat.strided(z.reshape(B, 1, 1, 1), shape)
-            pb.cx = nat.strided(tables.zero, shape)
-            pb.cy = nat.strided(cy.reshape(B, F, 1, 1), shape)
-            pb.c, pb.t, pb.mu, pb.live = cc.data_ptr(), tt.data_ptr(), mu.data_ptr(), tables.mask.data_ptr()
-            pb.B, pb.F, pb.P, pb.W, pb.S = B, F, P, W, L
-            pb.allow_backward_rays, pb.arith = int(bool(allow_backward_rays)), int(arith)
-            pb.p_begin, pb.p_end = p_begin, p_end
-            pb.xy_scale = half_epd.data_ptr()
-            n_acc = lib.tl_spot_moment_count(L, int(want_grad))
-            moments = torch.empty((B, F, W, n_acc), dtype=torch.float64, device=dev)
-            ref_y = torch.empty((B, F), dtype=torch.float32, device=dev)
-            ws_bytes = lib.tl_spot_workspace(ctypes.byref(pb), int(want_grad))
-            if ws_bytes == 0:
-                nat.check(-1, 'tl_spot_workspace')
-            ws = torch.empty((ws_bytes // 8,), dtype=torch.float64, device=dev)
-            nat.check(lib.tl_spot_accumulate(ctypes.byref(pb), int(want_grad), moments.data_ptr(),
-                                             ref_y.data_ptr(), ws.data_ptr(), ws_bytes, stream),
-                      'tl_spot_accumulate')
-            if world > 1:
-                moments = reduce_moments(moments, group)
-            rms = torch.empty((B,), dtype=torch.float32, device=dev)
-            rms_field = torch.empty((B, F), dtype=torch.float32, device=dev)
-            if want_grad:
-                gc = torch.empty((B, L), dtype=torch.float32, device=dev)
-                gt = torch.empty_like(gc)
-                gmu = torch.empty((B, W, L), dtype=torch.float32, device=dev)
-                gz = torch.empty((B,), dtype=torch.float32, device=dev)
-                out = nat.TlSpotOut(rms.data_ptr(), rms_field.data_ptr(), gc.data_ptr(), gt.data_ptr(),
-                                    gmu.data_ptr(), gz.data_ptr())
-            else:
-                out = nat.TlSpotOut(rms.data_ptr(), rms_field.data_ptr(), None, None, None, None)
-            nat.check(lib.tl_spot_finalize(moments.data_ptr(), ref_y.data_ptr(), B, F, W, L, P,
-                                           int(want_grad), ctypes.byref(out), stream), 'tl_spot_finalize')
-            if want_grad:
-                gnd = torch.zeros((B, L), dtype=torch.float32, device=dev)
-                gv = torch.zeros((B, L), dtype=torch.float32, device=dev)
-                nat.check(lib.tl_stage_bwd(ctypes.byref(ln), gmu.data_ptr(), gz.data_ptr(), gc.data_ptr(),
-                                           gt.data_ptr(), gnd.data_ptr(), gv.data_ptr(), stream),
-                          'tl_stage_bwd')
-                ctx.save_for_backward(gc, gt, gnd, gv)
+        rms, rms_field, gc, gt, gnd, gv = _lens_spot_core(c, t, nd, v, hfov, epd, x_rel, y_rel, tables,
+                                                          allow_backward_rays, arith, shard, group,
+                                                          want_grad, aimed)
+        if want_grad:
+            ctx.save_for_backward(gc, gt, gnd, gv)
         ctx.mark_non_differentiable(rms_field)
         return rms, rms_field
 
@@ -671,6 +700,18 @@ class _LensSpotRms(torch.autograd.Function):
         grads = [(gc * g) if need[0] else None, (gt * g) if need[1] else None,
                  (gnd * g) if need[2] else None, (gv * g) if need[3] else None]
         return (*grads, None, None, None, None, None, None, None, None, None, None, None)
+
+
+def lens_spot_rms_and_grads(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays=True,
+                            arith=nat.ARITH_GUARDED, shard=(0, 1), group=None, aimed=False, out=None):
+    """:func:`lens_spot_rms` and the gradients of ``sum(rms)`` in one call, outside autograd:
+    returns ``(rms [B], rms_field [B,F], {'c','t','nd','v': [B,L] gradients})``.  ``out`` may hold
+    preallocated 'rms', 'gc', 'gt', 'gnd', 'gv' tensors (e.g. views of one staging buffer)."""
+    rms, rms_field, gc, gt, gnd, gv = _lens_spot_core(c, t, nd, v, hfov, epd, x_rel, y_rel, tables,
+                                                      bool(allow_backward_rays), int(arith),
+                                                      (int(shard[0]), int(shard[1])), group, True,
+                                                      bool(aimed), out)
+    return rms, rms_field, {'c': gc, 't': gt, 'nd': gnd, 'v': gv}
 
 
 def lens_spot_rms(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays=True,

@@ -396,6 +396,18 @@ class RayTracer:
         vignetting function, a deterministic pupil sampler and either no ray aiming or the aiming
         the device kernel covers (one iteration, 'real' stop radius: tl_aim, applied on load inside
         the trace kernels); otherwise the torch front end of :meth:`trace_rays` feeds the fused pass."""
+        can_stage, aimed = self._staging(lens, use_vig)
+        ext = self._extension_tables(lens)
+        if staged and can_stage:
+            x_rel, y_rel = self._pupil(None)
+            return ops.lens_spot_rms(lens.c, lens.t, lens.nd, lens.v, specs.hfov, specs.epd, x_rel,
+                                     y_rel, self._tables(lens), self.allow_backward_rays,
+                                     _arith_code(self.arith), shard, group, aimed=aimed)
+        args = self._ray_set(specs, lens, use_vig)
+        return ops.spot_rms(*args, self.allow_backward_rays, _arith_code(self.arith), shard, group, **ext)
+
+    def _staging(self, lens, use_vig=True):
+        """(can the staged kernels build this ray set?, with the ray-aiming kernel?)"""
         no_vig = self.vig_fn is None or not use_vig
         # ray aiming stays on the staged path when the device kernel covers it (one iteration,
         # 'real' stop radius); a lens batch whose stops are all in front needs none (rtl:131-133)
@@ -403,15 +415,38 @@ class RayTracer:
         aimed = (self.n_ray_aiming_iter == 1 and self.ray_aiming_mode == 'real' and self.device_aiming
                  and not stops_in_front)
         plain = no_vig and (self.n_ray_aiming_iter == 0 or aimed or stops_in_front)
-        ext = self._extension_tables(lens)
-        general = any(v is not None for v in ext.values())
-        if staged and plain and not general and self.mode != 'skew_random' and lens.c.shape[1] <= 64:
+        general = any(v is not None for v in self._extension_tables(lens).values())
+        ok = plain and not general and self.mode != 'skew_random' and lens.c.shape[1] <= 64
+        return ok, aimed
+
+    def spot_rms_and_grads(self, specs, lens, use_vig=True, shard=(0, 1), group=None, out=None):
+        """:meth:`spot_rms` together with the gradients of ``sum(rms)`` w.r.t. the lens tensors, as
+        one call outside autograd: ``(rms [B], {'c','t','nd','v': [B,L]})``.  On the staged path this
+        is the bare kernel sequence (no autograd node, no elementwise glue) and ``out`` may supply
+        the result tensors (see ``ops.lens_spot_rms_and_grads``); otherwise it falls back to
+        autograd over :meth:`spot_rms`."""
+        can_stage, aimed = self._staging(lens, use_vig)
+        if can_stage and lens.c.shape[1] <= nat.MAX_SURFACES_SPOT:
             x_rel, y_rel = self._pupil(None)
-            return ops.lens_spot_rms(lens.c, lens.t, lens.nd, lens.v, specs.hfov, specs.epd, x_rel,
-                                     y_rel, self._tables(lens), self.allow_backward_rays,
-                                     _arith_code(self.arith), shard, group, aimed=aimed)
-        args = self._ray_set(specs, lens, use_vig)
-        return ops.spot_rms(*args, self.allow_backward_rays, _arith_code(self.arith), shard, group, **ext)
+            rms, _, grads = ops.lens_spot_rms_and_grads(lens.c, lens.t, lens.nd, lens.v, specs.hfov, specs.epd,
+                                                        x_rel, y_rel, self._tables(lens), self.allow_backward_rays,
+                                                        _arith_code(self.arith), shard, group, aimed, out)
+            return rms, grads
+        leaves = {k: getattr(lens, k).detach().requires_grad_(True) for k in ('c', 't', 'nd', 'v')}
+        from .lens_modeling import Lens
+        trial = Lens(lens.structure, leaves['c'], leaves['t'], leaves['nd'], leaves['v'],
+                     *(getattr(lens, k, None) for k in ('k', 'a', 'sd')))
+        with torch.enable_grad():
+            rms, _ = self.spot_rms(specs, trial, use_vig, shard, group)
+            grads = torch.autograd.grad(rms.sum(), list(leaves.values()), allow_unused=True)
+        grads = {k: (torch.zeros_like(leaves[k]) if g is None else g) for k, g in zip(leaves, grads)}
+        if out:
+            for name, key in (('gc', 'c'), ('gt', 't'), ('gnd', 'nd'), ('gv', 'v')):
+                if out.get(name) is not None:
+                    out[name].copy_(grads[key])
+            if out.get('rms') is not None:
+                out['rms'].copy_(rms.detach())
+        return rms.detach(), grads
 
     def _tables(self, lens):
         key = ('tables', id(lens.structure))
