@@ -216,8 +216,10 @@ def main():
     leaves = [ray_args[i] for i in (2, 5, 6, 7)]
 
     def step():
-        rms, _ = ops.spot_rms(*ray_args, True, _native.ARITH_GUARDED, shard, exchange)
-        return rms, torch.autograd.grad(rms[0], leaves)
+        # the fused lens pass as its bare kernel sequence: staging (index model, pupil position,
+        # field cosines) -> chief rays -> trace + adjoint -> row reduction -> (exchange) -> finalize ->
+        # chain rule to (c, t, nd, v): RMS and its gradients, nothing per-ray materialised
+        return tracer.spot_rms_and_grads(specs, lens, shard=shard, group=exchange)
 
     note('first eager step')
     before = _native.launch_count()
@@ -464,6 +466,8 @@ def main():
                            'parallelism': f'pupil-sharded dp{world}', 'collective': collective,
                            'l2': 'flushed between timed steps (256 MiB write)',
                            'launch': 'cuda_graph' if graph is not None else 'eager',
+                           'step': 'RayTracer.spot_rms_and_grads: staging -> chief rays -> fused trace+adjoint -> '
+                                   'reduce -> (exchange) -> finalize -> chain rule; rms + d rms/d(c,t,nd,v)',
                            'arith': 'guarded'},
                 'clocks': clocks.summary(),
                 'e2e': {'value': e2e_value, 'unit': 'events/s', 'h2d_bytes_per_step': h2d,

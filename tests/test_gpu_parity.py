@@ -506,3 +506,55 @@ def test_spot_rms_and_grads_matches_autograd_and_writes_into_given_buffers():
     assert torch.equal(buf[4 * per:], rms.detach())
     for i, w in enumerate(want):
         assert torch.equal(buf[i * per:(i + 1) * per].view(lens.c.shape), w)
+
+
+def test_new_entry_points_reject_what_they_do_not_cover():
+    """Loud failures, never a silent wrong answer: the aiming map / penalty terms with extension
+    surfaces, per-ray x/y gradients through an aiming map, undersized peer windows."""
+    import ctypes
+    from torchoptics_b200 import _native
+    from torchoptics_b200.peer import PeerExchange
+    rec = load_golden('cooke_8x8')
+    i = _inputs(rec, DEV)
+    S = i['c'].shape[-1]
+    k = torch.zeros((1, 1, 1, 1, S), device=DEV)
+    with pytest.raises(ValueError):                      # stacks are defined for spherical lenses only
+        rt.trace_skew(*_args(i), aggregate=True, k=k)
+    with pytest.raises(_native.NativeLibraryError):      # same at the C ABI
+        lay = ops._Layout(*_args(i), k=k)
+        pb = lay.problem(True, _native.ARITH_GUARDED)
+        assert _native.load().tl_penalty_workspace(ctypes.byref(pb)) == 0
+        mom = torch.empty(3 * 3 * (3 * S + 2), dtype=torch.float64, device=DEV)
+        _native.check(_native.load().tl_penalty_accumulate(ctypes.byref(pb), mom.data_ptr(), mom.data_ptr(), 8,
+                                                           None), 'tl_penalty_accumulate')
+    i['x'], i['y'] = i['x'] * 0.25, i['y'] * 0.25     # inside the map's clamp to [-2, 2] (rtl:111)
+    assert float(i['y'].abs().max()) < 2.0
+    lay = ops._Layout(*_args(i))
+    pb = lay.problem(True, _native.ARITH_GUARDED)
+    aim = torch.ones((1, 3, 3, 3), device=DEV)
+    pb.aim = aim.data_ptr()
+    ws_bytes = _native.load().tl_trace_bwd_workspace(ctypes.byref(pb))
+    ws = torch.empty(ws_bytes // 8, dtype=torch.float64, device=DEV)
+    g = [torch.zeros(n, device=DEV) for n in (S, S, 3 * S, 1)]
+    gx = torch.zeros(lay.shape, device=DEV)
+    seeds = _native.TlSeeds()
+    grads = _native.TlGrads(g[0].data_ptr(), g[1].data_ptr(), g[2].data_ptr(), g[3].data_ptr(), gx.data_ptr())
+    rc = _native.load().tl_trace_bwd(ctypes.byref(pb), ctypes.byref(seeds), ctypes.byref(grads), ws.data_ptr(),
+                                     ws_bytes, None)
+    assert rc == -1 and b'ray-aiming' in _native.load().tl_last_error()
+    # an aiming map of ones with a zero shift is the identity
+    out_plain = rt.trace_skew(*_args(i))
+    aim[..., 2] = 0.0
+    o = [torch.empty(lay.shape, device=DEV) for _ in range(4)] + \
+        [torch.empty(lay.shape, dtype=torch.bool, device=DEV) for _ in range(2)]
+    tout = _native.TlTraceOut(*[t.data_ptr() for t in o])
+    _native.check(_native.load().tl_trace_fwd(ctypes.byref(pb), ctypes.byref(tout), None), 'tl_trace_fwd')
+    torch.cuda.synchronize()
+    for a, b in zip(o, out_plain):
+        assert torch.equal(a, b)
+    ex = PeerExchange(capacity=16)
+    with pytest.raises(ValueError):
+        ex.all_reduce(torch.zeros(17, dtype=torch.float64, device=DEV))
+    with pytest.raises(ValueError):
+        ex.all_reduce(torch.zeros(8, dtype=torch.float32, device=DEV))
+    ex.close()
