@@ -558,3 +558,45 @@ def test_new_entry_points_reject_what_they_do_not_cover():
     with pytest.raises(ValueError):
         ex.all_reduce(torch.zeros(8, dtype=torch.float32, device=DEV))
     ex.close()
+
+
+@pytest.mark.parametrize('aggregate', [False, True])
+@pytest.mark.parametrize('name', ['cooke_8x8', 'cooke_16x16_epd2.6'])
+def test_unfused_backward_rows_kernel_matches_cta_kernel(name, aggregate, monkeypatch):
+    """trace_skew(...).backward() on a batch of 12 lenses (>= 64 short rows): the warp-per-row
+    backward (with and without seeds on the aggregate=True stacks) against the CTA-per-row one,
+    per-ray gradients of x, y, cx, cy included."""
+    rec = load_golden(name)
+    allow = bool(rec['allow_backward_rays'])
+    B = 12
+    shape = (B,) + rec['out_ok'].shape[1:]
+    g = torch.Generator(device='cpu').manual_seed(3)
+    base = _inputs(rec, DEV)
+    S = base['c'].shape[-1]
+    jitter = 1.0 + 0.01 * torch.randn((B, 1, 1, 1, S), generator=g)
+    seeds = [torch.rand(shape, generator=g).to(DEV) + 0.1 for _ in range(4)]
+    stack_seed = (torch.rand((S,) + shape, generator=g) + 0.1).to(DEV)
+
+    def run():
+        i = {}
+        for key in ('x', 'y', 'cx'):
+            i[key] = torch.broadcast_to(base[key], shape).contiguous().requires_grad_(True)
+        i['cy'] = torch.broadcast_to(base['cy'], shape).contiguous().requires_grad_(True)
+        i['z'] = base['z'].expand(B, 1, 1, 1).clone().requires_grad_(True)
+        i['c'] = (base['c'] * jitter.to(DEV)).requires_grad_(True)
+        i['t'] = base['t'].expand(B, 1, 1, 1, S).clone().requires_grad_(True)
+        i['mu'] = base['mu'].expand(B, 1, 1, -1, S).clone().requires_grad_(True)
+        i['mask'] = base['mask'].expand(B, 1, 1, 1, S).contiguous()
+        out = rt.trace_skew(*_args(i), aggregate=aggregate, allow_backward_rays=allow)
+        loss = sum((s * o).sum() for s, o in zip(seeds, out[:4]))
+        if aggregate:
+            loss = loss + sum((torch.stack(out[6][k]) * stack_seed).sum() for k in out[6])
+        return torch.autograd.grad(loss, [i[k] for k in ('x', 'y', 'z', 'cx', 'cy', 'c', 't', 'mu')])
+
+    monkeypatch.delenv('TL_NO_ROWS', raising=False)
+    rows = run()
+    monkeypatch.setenv('TL_NO_ROWS', '1')
+    cta = run()
+    for k, a, b in zip(('x', 'y', 'z', 'cx', 'cy', 'c', 't', 'mu'), rows, cta):
+        assert torch.isfinite(a).all(), k
+        assert float((a - b).norm()) <= 2e-5 * float(b.norm()), k

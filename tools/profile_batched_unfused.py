@@ -44,3 +44,17 @@ def timed(fn, reps=20):
 
 ms = timed(lambda: ops.trace(*args))
 print(f'{B} lenses x 1536 rays: tl_trace_fwd {ms:.4f} ms -> {events / ms / 1e6:.1f} G events/s')
+leaves = [args[j].clone().requires_grad_(True) for j in (2, 5, 6, 7)]
+call = list(args)
+call[2], call[5], call[6], call[7] = leaves
+
+
+def drop_in():
+    out = ops.trace(*call)
+    rms, _ = ops.spot_rms_from_rays(out[1], out[4])
+    return torch.autograd.grad(rms.sum(), leaves)
+
+
+ms = timed(drop_in)
+print(f'{B} lenses x 1536 rays: unfused trace_skew -> compute_rms2d -> backward {ms:.4f} ms -> '
+      f'{events / ms / 1e6:.1f} G events/s')

@@ -1564,11 +1564,13 @@ int reduce_rows(const AdjPlan &pl, const double *partial, double *rows_out, int 
   return TL_OK;
 }
 
-// K3c: the fused penalty pass (PEN_SUM of k_trace_adj) with a warp per row, for the same
-// many-short-rows workload as k_spot_rows.  Row layout [3S+2]: c, t, mu per surface, z, penalty.
-template <int NS_MAX, class V>
+// K3c: the backward kernels (MODE_BWD of k_trace_adj: plain, with seeded stacks, and the fused
+// penalty pass PEN_SUM) with a warp per row, for the same many-short-rows workload as k_spot_rows.
+// Row layout [3S+1 (+1)]: c, t, mu per surface, z (, penalty) -- what k_bwd_finalize /
+// k_penalty_finalize read.
+template <int NS_MAX, class V, int PEN>
 __global__ void __launch_bounds__(kTraceThreads)
-k_penalty_rows(TlProblem pb, double *moments, int n_acc) {
+k_bwd_rows(TlProblem pb, AdjArgs args, double *rows, int n_acc) {
   extern __shared__ float smem[];
   constexpr int N = LaneCount<V>::value;
   constexpr int kWarps = kTraceThreads / 32;
@@ -1582,6 +1584,7 @@ k_penalty_rows(TlProblem pb, double *moments, int n_acc) {
   constexpr int stride = 32;
   const int n_rows = pb.B * pb.F * pb.W;
   const int groups = (pb.p_end - pb.p_begin + 32 * N - 1) / (32 * N);
+  const int64_t plane = (int64_t)pb.B * pb.F * pb.P * pb.W;
 
   for (int row = blockIdx.x * kWarps + warp; row < n_rows; row += gridDim.x * kWarps) {
     const int w = row % pb.W;
@@ -1598,12 +1601,14 @@ k_penalty_rows(TlProblem pb, double *moments, int n_acc) {
       const int p_base = pb.p_begin + j * (32 * N) + lane;
       if (p_base >= pb.p_end) continue;
       bool has[N];
+      int64_t o[N];
       V x, y, z, cx, cy;
 #pragma unroll
       for (int l = 0; l < N; ++l) {
         const int p = p_base + l * 32;
         has[l] = p < pb.p_end;
         const int q = has[l] ? p : p_base;
+        o[l] = (((int64_t)b * pb.F + f) * pb.P + q) * pb.W + w;
         float px, py;
         load_pupil_point(pb, b, f, q, w, xy_scale, px, py);
         lane_set(x, l, px);
@@ -1612,64 +1617,109 @@ k_penalty_rows(TlProblem pb, double *moments, int n_acc) {
         lane_set(cx, l, pb.cx.ptr[offset_of(pb.cx, b, f, q, w)]);
         lane_set(cy, l, pb.cy.ptr[offset_of(pb.cy, b, f, q, w)]);
       }
-      TracedN<V> tr = trace_guarded<true, V, true>(x, y, z, cx, cy, tab, S, allow_backward, pb.arith, state,
-                                                   stride);
+      TracedN<V> tr = trace_guarded<true, V, PEN != PEN_NONE>(x, y, z, cx, cy, tab, S, allow_backward, pb.arith,
+                                                            state, stride);
+      bool live[N], any_live = false, all_ok = true;
       unsigned bits[N], flips[N];
 #pragma unroll
       for (int l = 0; l < N; ++l) {
-        bits[l] = has[l] ? tr.ok_bits[l][0] : 0u;
-        flips[l] = tr.ok_bits[l][1];
+        live[l] = tr.ok[l] && has[l];
+        any_live = any_live || live[l];
+        all_ok = all_ok && tr.ok[l];
+        bits[l] = (PEN != PEN_NONE && has[l]) ? tr.ok_bits[l][0] : 0u;
+        flips[l] = PEN != PEN_NONE ? tr.ok_bits[l][1] : 0u;
       }
-      Sweep<V> sw = sweep_begin(tr.pre, tr.x, tr.y, V(0.f), V(0.f), V(0.f), V(0.f));
+      Ray<V> a{V(0.f), V(0.f), V(0.f), V(0.f), V(0.f), V(0.f)};
+      if (PEN != PEN_NONE || any_live) {
+        if (PEN == PEN_NONE && !all_ok) mirror_live_lane<V>(state, stride, S, tr.ok, tr.pre, z, tr.x, tr.y);
+        V sx(0.f), sy(0.f), scx(0.f), scy(0.f);
+        if (PEN != PEN_SUM) {
 #pragma unroll
-      for (int k = NS_MAX - 1; k >= 0; --k) {
-        if (k >= S) continue;
-        const V *slot = state + (size_t)k * 4 * stride;
-        V pz(0.f), pth(0.f), pthp(0.f), branch(1.0f);
-        float dead_gt[N];
+          for (int l = 0; l < N; ++l) {
+            if (!live[l]) continue;
+            if (args.seeds.gx) lane_set(sx, l, args.seeds.gx[o[l]]);
+            if (args.seeds.gy) lane_set(sy, l, args.seeds.gy[o[l]]);
+            if (args.seeds.gcx) lane_set(scx, l, args.seeds.gcx[o[l]]);
+            if (args.seeds.gcy) lane_set(scy, l, args.seeds.gcy[o[l]]);
+          }
+        }
+        Sweep<V> sw = sweep_begin(tr.pre, tr.x, tr.y, sx, sy, scx, scy);
+#pragma unroll
+        for (int k = NS_MAX - 1; k >= 0; --k) {
+          if (k >= S) continue;
+          const V *slot = state + (size_t)k * 4 * stride;
+          SurfaceGrad<V> g;
+          if constexpr (PEN != PEN_NONE) {
+            V pz(0.f), pth(0.f), pthp(0.f), branch(1.0f);
+            float dead_gt[N];
+#pragma unroll
+            for (int l = 0; l < N; ++l) {
+              dead_gt[l] = 0.f;
+              if ((flips[l] >> k) & 1u) lane_set(branch, l, -1.0f);
+              if (!has[l]) continue;
+              const int64_t at = (int64_t)k * plane + o[l];
+              if (PEN == PEN_SUM) {
+                if ((bits[l] >> k) & 1u) {
+                  lane_set(pz, l, 1.0f);
+                  lane_set(pth, l, 1.0f);
+                  lane_set(pthp, l, 1.0f);
+                } else {      // failed ray: theta = theta' = 1, z = 0 - t[k] (rtl:639, :653-654)
+                  const float z_dead = -tab.t[k];
+                  m_pen += 2.0f + fmaxf(z_dead, 0.0f);
+                  if (z_dead > 0.f) dead_gt[l] = -1.0f;
+                }
+              } else if ((bits[l] >> k) & 1u) {
+                if (args.seeds.gz_relu) lane_set(pz, l, args.seeds.gz_relu[at]);
+                if (args.seeds.gtheta) lane_set(pth, l, args.seeds.gtheta[at]);
+                if (args.seeds.gtheta_prime) lane_set(pthp, l, args.seeds.gtheta_prime[at]);
+              } else if (args.seeds.gz_relu && -tab.t[k] > 0.f) {
+                dead_gt[l] = -args.seeds.gz_relu[at];
+              }
+            }
+            V cos_in, cos_out, z_behind;
+            g = sweep_sphere_pen(sw, slot[0], slot[stride], slot[2 * stride], slot[3 * stride], V(tab.c[k]),
+                                 V(tab.t[k]), V(tab.mu[k]), V(tab.mu2[k]), pz, pth, pthp, branch, cos_in, cos_out,
+                                 z_behind);
+#pragma unroll
+            for (int l = 0; l < N; ++l) {
+              if ((bits[l] >> k) & 1u) {
+                if (PEN == PEN_SUM)
+                  m_pen += (fast_angle_norm(lane_get(cos_in, l)) + fast_angle_norm(lane_get(cos_out, l))) +
+                           fmaxf(lane_get(z_behind, l), 0.0f);
+                continue;
+              }
+              lane_set(g.c, l, 0.f);
+              lane_set(g.mu, l, 0.f);
+              lane_set(g.t, l, dead_gt[l]);
+              lane_set(sw.gr.x, l, 0.f); lane_set(sw.gr.y, l, 0.f); lane_set(sw.gr.z, l, 0.f);
+              lane_set(sw.gd.x, l, 0.f); lane_set(sw.gd.y, l, 0.f); lane_set(sw.gd.z, l, 0.f);
+            }
+          } else {
+            g = sweep_sphere(sw, slot[0], slot[stride], slot[2 * stride], slot[3 * stride], V(tab.c[k]),
+                             V(tab.t[k]), V(tab.mu[k]), V(tab.mu2[k]));
+          }
+          acc_c[k] += lane_sum(g.c);
+          acc_t[k] += lane_sum(g.t);
+          acc_mu[k] += lane_sum(g.mu);
+        }
+        sweep_end(sw, z, a.x, a.y, a.z, a.cx, a.cy);
+        acc_z += lane_sum(a.z);
+      }
+      if (PEN != PEN_SUM) {
 #pragma unroll
         for (int l = 0; l < N; ++l) {
-          dead_gt[l] = 0.f;
-          if ((flips[l] >> k) & 1u) lane_set(branch, l, -1.0f);
           if (!has[l]) continue;
-          if ((bits[l] >> k) & 1u) {
-            lane_set(pz, l, 1.0f);
-            lane_set(pth, l, 1.0f);
-            lane_set(pthp, l, 1.0f);
-          } else {      // failed ray: theta = theta' = 1, z = 0 - t[k] (rtl:639, :653-654)
-            const float z_dead = -tab.t[k];
-            m_pen += 2.0f + fmaxf(z_dead, 0.0f);
-            if (z_dead > 0.f) dead_gt[l] = -1.0f;
-          }
+          if (args.grads.gx) args.grads.gx[o[l]] = lane_get(a.x, l) * xy_scale;
+          if (args.grads.gy) args.grads.gy[o[l]] = lane_get(a.y, l) * xy_scale;
+          if (args.grads.gz) args.grads.gz[o[l]] = lane_get(a.z, l);
+          if (args.grads.gcx) args.grads.gcx[o[l]] = lane_get(a.cx, l);
+          if (args.grads.gcy) args.grads.gcy[o[l]] = lane_get(a.cy, l);
         }
-        V cos_in, cos_out, z_behind;
-        SurfaceGrad<V> g = sweep_sphere_pen(sw, slot[0], slot[stride], slot[2 * stride], slot[3 * stride],
-                                            V(tab.c[k]), V(tab.t[k]), V(tab.mu[k]), V(tab.mu2[k]), pz, pth, pthp,
-                                            branch, cos_in, cos_out, z_behind);
-#pragma unroll
-        for (int l = 0; l < N; ++l) {
-          if ((bits[l] >> k) & 1u) {
-            m_pen += (fast_angle_norm(lane_get(cos_in, l)) + fast_angle_norm(lane_get(cos_out, l))) +
-                     fmaxf(lane_get(z_behind, l), 0.0f);
-            continue;
-          }
-          lane_set(g.c, l, 0.f);
-          lane_set(g.mu, l, 0.f);
-          lane_set(g.t, l, dead_gt[l]);
-          lane_set(sw.gr.x, l, 0.f); lane_set(sw.gr.y, l, 0.f); lane_set(sw.gr.z, l, 0.f);
-          lane_set(sw.gd.x, l, 0.f); lane_set(sw.gd.y, l, 0.f); lane_set(sw.gd.z, l, 0.f);
-        }
-        acc_c[k] += lane_sum(g.c);
-        acc_t[k] += lane_sum(g.t);
-        acc_mu[k] += lane_sum(g.mu);
       }
-      V ax, ay, az, acx, acy;
-      sweep_end(sw, z, ax, ay, az, acx, acy);
-      acc_z += lane_sum(az);
     }
 
     // three values per surface, ten surfaces per transpose: lane 3 q + typ -> slot typ * S + k
-    double *dst = moments + (int64_t)row * n_acc;
+    double *dst = rows + (int64_t)row * n_acc;
     constexpr int kPerBatch = 10;
 #pragma unroll
     for (int i = 0; i < (NS_MAX + kPerBatch - 1) / kPerBatch; ++i) {
@@ -1690,7 +1740,7 @@ k_penalty_rows(TlProblem pb, double *moments, int n_acc) {
     const float t0 = warp_sum(acc_z), t1 = warp_sum(m_pen);
     if (lane == 0) {
       dst[3 * S] = (double)t0;
-      dst[3 * S + 1] = (double)t1;
+      if (PEN == PEN_SUM) dst[3 * S + 1] = (double)t1;
     }
   }
 }
@@ -1748,14 +1798,24 @@ int launch_spot_rows(const TlProblem &pb, int want_grad, const float *ref_y, dou
   return TL_OK;
 }
 
-typedef void (*PenRowsKernelPtr)(TlProblem, double *, int);
+typedef void (*BwdRowsKernelPtr)(TlProblem, AdjArgs, double *, int);
 
-int launch_penalty_rows(const TlProblem &pb, double *moments, cudaStream_t stream) {
+template <int PEN>
+BwdRowsKernelPtr bwd_rows_kernel_for(int S) {
+  if (S <= 4) return k_bwd_rows<4, f2, PEN>;
+  if (S <= 8) return k_bwd_rows<8, f2, PEN>;
+  if (S <= 12) return k_bwd_rows<12, f2, PEN>;
+  return k_bwd_rows<16, f2, PEN>;
+}
+
+// warp-per-row backward (S <= 16): rows[B*F*W][3S+1 (+1 for PEN_SUM)]
+int launch_bwd_rows(const TlProblem &pb, const AdjArgs &args, int pen, double *rows, cudaStream_t stream) {
   DeviceInfo info;
   int rc = device_info(info);
   if (rc) return rc;
-  PenRowsKernelPtr kernel = pb.S <= 4 ? k_penalty_rows<4, f2> : pb.S <= 8 ? k_penalty_rows<8, f2>
-                            : pb.S <= 12 ? k_penalty_rows<12, f2> : k_penalty_rows<16, f2>;
+  BwdRowsKernelPtr kernel = pen == PEN_SUM ? bwd_rows_kernel_for<PEN_SUM>(pb.S)
+                            : pen == PEN_SEEDED ? bwd_rows_kernel_for<PEN_SEEDED>(pb.S)
+                                                : bwd_rows_kernel_for<PEN_NONE>(pb.S);
   const size_t tab_floats = (5 * (size_t)pb.S + 3) & ~(size_t)3;
   const size_t smem = (kTraceThreads / 32) * (tab_floats + (size_t)4 * pb.S * 32 * 2) * sizeof(float);
   if (smem > 48 * 1024)
@@ -1765,13 +1825,14 @@ int launch_penalty_rows(const TlProblem &pb, double *moments, cudaStream_t strea
   TL_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)kernel, kTraceThreads,
                                                               smem));
   if (per_sm < 1) return fail(TL_ERR_CUDA, "kernel does not fit on an SM%s");
-  const int64_t rows = (int64_t)pb.B * pb.F * pb.W;
+  const int64_t n_rows = (int64_t)pb.B * pb.F * pb.W;
   int64_t n_blocks = (int64_t)info.sms * per_sm;
-  const int64_t need = (rows + kTraceThreads / 32 - 1) / (kTraceThreads / 32);
+  const int64_t need = (n_rows + kTraceThreads / 32 - 1) / (kTraceThreads / 32);
   if (n_blocks > need) n_blocks = need;
-  const int n_acc = 3 * pb.S + 2;
+  const int n_acc = 3 * pb.S + 1 + (pen == PEN_SUM ? 1 : 0);
   TlProblem pb_copy = pb;
-  void *params[] = {(void *)&pb_copy, (void *)&moments, (void *)&n_acc};
+  AdjArgs args_copy = args;
+  void *params[] = {(void *)&pb_copy, (void *)&args_copy, (void *)&rows, (void *)&n_acc};
   TL_CHECK_CUDA(cudaLaunchKernel((const void *)kernel, dim3((unsigned)n_blocks), dim3(kTraceThreads), params,
                                  smem, stream));
   g_launches++;
@@ -1958,11 +2019,16 @@ int tl_trace_bwd(const TlProblem *pb_, const TlSeeds *seeds, const TlGrads *grad
   args.seeds = *seeds;
   args.grads = *grads;
   args.partial = (double *)workspace;
-  rc = launch_adj(pb, args, pl, stream);
-  if (rc) return rc;
   double *rowbuf = (double *)((char *)workspace + pl.partial_bytes);
-  rc = reduce_rows(pl, args.partial, rowbuf, rows, stream);
-  if (rc) return rc;
+  if (pb.S <= TL_MAX_SURFACES_SPOT && use_rows_kernel(pb, 1)) {     // many short rows: a warp per row
+    rc = launch_bwd_rows(pb, args, pen, rowbuf, stream);
+    if (rc) return rc;
+  } else {
+    rc = launch_adj(pb, args, pl, stream);
+    if (rc) return rc;
+    rc = reduce_rows(pl, args.partial, rowbuf, rows, stream);
+    if (rc) return rc;
+  }
   const int outs = pb.B * (2 * pb.S + pb.W * pb.S + 1);
   k_bwd_finalize<<<(outs + 127) / 128, 128, 0, stream>>>(rowbuf, *grads, pb.B, pb.F, pb.W, pb.S);
   g_launches++;
@@ -2111,8 +2177,11 @@ int tl_penalty_accumulate(const TlProblem *pb, double *moments, void *workspace,
   if (pb->p_begin < 0 || pb->p_end > pb->P || pb->p_end <= pb->p_begin)
     return fail(TL_ERR_INVALID, "empty or out-of-range pupil slice%s");
   if (!moments) return fail(TL_ERR_INVALID, "NULL moments%s");
-  if (pb->S <= TL_MAX_SURFACES_SPOT && use_rows_kernel(*pb, 1))     // many short rows: a warp per row
-    return launch_penalty_rows(*pb, moments, (cudaStream_t)stream_);
+  if (pb->S <= TL_MAX_SURFACES_SPOT && use_rows_kernel(*pb, 1)) {   // many short rows: a warp per row
+    AdjArgs none;
+    memset(&none, 0, sizeof(none));
+    return launch_bwd_rows(*pb, none, PEN_SUM, moments, (cudaStream_t)stream_);
+  }
   AdjPlan pl;
   rc = plan_adj(*pb, MODE_BWD, pl, PEN_SUM);
   if (rc) return rc;
