@@ -79,11 +79,13 @@ __device__ __forceinline__ int64_t offset_of(const TlStrided &s, int b, int f, i
 // (lens, field, wavelength) when there is one -- x_rel * x_gain, y_rel * y_gain + y_shift, clamped
 // to [-2, 2] (rtl:109-112, :196-206) -- and scaled to the entrance pupil (scale_to_epd rtl:497-507).
 // Every step is one individually rounded operation, like the reference's eager ops.
+// (AIM = false: for the one kernel that never sees a map -- there the branch costs 27 registers)
+template <bool AIM = true>
 __device__ __forceinline__ void load_pupil_point(const TlProblem &pb, int b, int f, int q, int w,
                                                  float xy_scale, float &x, float &y) {
   x = pb.x.ptr[offset_of(pb.x, b, f, q, w)];
   y = pb.y.ptr[offset_of(pb.y, b, f, q, w)];
-  if (pb.aim) {
+  if (AIM && pb.aim) {
     const float *a = pb.aim + (((int64_t)b * pb.F + f) * pb.W + w) * 3;
     x = fminf(fmaxf(__fmul_rn(x, a[0]), -2.0f), 2.0f);
     y = fminf(fmaxf(__fadd_rn(__fmul_rn(y, a[1]), a[2]), -2.0f), 2.0f);
@@ -306,9 +308,10 @@ k_trace_fwd(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
     const bool has1 = p1 < p_hi;
     const int q1 = has1 ? p1 : p0;
     const float xy_scale = pb.xy_scale ? pb.xy_scale[b] : 1.0f;
-    f2 x, y;
-    load_pupil_point(pb, b, f, p0, w, xy_scale, x.v.x, y.v.x);
-    load_pupil_point(pb, b, f, q1, w, xy_scale, x.v.y, y.v.y);
+    float x0, y0, x1, y1;
+    load_pupil_point<false>(pb, b, f, p0, w, xy_scale, x0, y0);     // (an aimed problem takes k_trace_fwd_pw)
+    load_pupil_point<false>(pb, b, f, q1, w, xy_scale, x1, y1);
+    const f2 x(x0, x1), y(y0, y1);
     const f2 z(pb.z.ptr[offset_of(pb.z, b, f, p0, w)], pb.z.ptr[offset_of(pb.z, b, f, q1, w)]);
     const f2 cx(pb.cx.ptr[offset_of(pb.cx, b, f, p0, w)], pb.cx.ptr[offset_of(pb.cx, b, f, q1, w)]);
     const f2 cy(pb.cy.ptr[offset_of(pb.cy, b, f, p0, w)], pb.cy.ptr[offset_of(pb.cy, b, f, q1, w)]);
@@ -1899,8 +1902,10 @@ int tl_trace_fwd(const TlProblem *pb, const TlTraceOut *out, void *stream_) {
   // short pupil axis (the batched-lens workload: 64 rays per (lens, field, wavelength)): the
   // (pupil, wavelength)-flattened map keeps a CTA's threads busy where a CTA per row would idle
   const size_t smem_pw = (size_t)pb->W * ((5 * (size_t)pb->S + 3) & ~(size_t)3) * sizeof(float);
-  const bool short_rows = !is_general(*pb) && pb->P < 2 * kFwdThreads && smem_pw <= 48 * 1024 &&
-                          !getenv("TL_NO_ROWS");
+  const bool short_rows = !is_general(*pb) && smem_pw <= 48 * 1024 &&
+                          ((pb->P < 2 * kFwdThreads && !getenv("TL_NO_ROWS")) || pb->aim);
+  if (pb->aim && !short_rows)
+    return fail(TL_ERR_INVALID, "an aimed forward trace needs W * S surface tables within 48 KB of shared memory%s");
   if (stacks || short_rows) {
     const int64_t row_len = (int64_t)pb->P * pb->W;
     if (row_len > 0x7fffffff) return fail(TL_ERR_INVALID, "P * W exceeds 2^31 - 1%s");
