@@ -3,7 +3,7 @@
 N=${1:-2}
 STEPS=${2:-200}
 mkdir -p gpurun_out
-for mode in peer nccl; do
+for mode in ${MODES:-peer nccl}; do
   TL_BENCH_COLLECTIVE=$mode TL_BENCH_WATCHDOG_S=150 timeout 240 python -m torch.distributed.run --nnodes=1 \
     --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29500 + RANDOM % 200)) bench.py --gpus $N \
     --steps $STEPS --warmup 5 --no-cpu-baseline > gpurun_out/bench_n${N}_${mode}.json 2> gpurun_out/bench_n${N}_${mode}.err
