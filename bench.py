@@ -206,8 +206,13 @@ def main():
             collective = 'nccl all_reduce (27 KB fp64) inside the CUDA graph'
         else:
             from torchoptics_b200.peer import PeerExchange
-            exchange = PeerExchange(capacity=1 << 16)
-            collective = 'k_peer_allreduce: one-shot all-reduce over NVLink peer memory (CUDA IPC windows), inside the CUDA graph'
+            try:       # (raises on EVERY rank together if any rank cannot create / map a window)
+                exchange = PeerExchange(capacity=1 << 16)
+                collective = ('k_peer_allreduce: one-shot all-reduce over NVLink peer memory (CUDA IPC '
+                              'windows), inside the CUDA graph')
+            except _native.NativeLibraryError as exc:
+                print(f'[bench rank {rank}] {exc}; using the NCCL all_reduce', file=sys.stderr)
+                collective = f'nccl all_reduce inside the CUDA graph (peer exchange unavailable: {exc})'
 
     # ---- device-resident step: inputs already in HBM ------------------------
     ray_args = [a.detach() for a in tracer._ray_set(specs, lens)]

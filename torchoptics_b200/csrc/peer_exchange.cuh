@@ -153,6 +153,7 @@ int tl_peer_create(int32_t rank, int32_t world, int64_t capacity, TlPeerComm **c
     err = cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t *>(handle_out), ptr);
   if (err != cudaSuccess) {
     cudaFree(ptr);
+    cudaGetLastError();
     delete comm;
     return fail(TL_ERR_CUDA, "tl_peer_create: %s", cudaGetErrorString(err));
   }
@@ -178,7 +179,11 @@ int tl_peer_connect(TlPeerComm *comm_, const void *all_handles) {
       continue;
     }
     void *ptr = nullptr;
-    TL_CHECK_CUDA(cudaIpcOpenMemHandle(&ptr, handles[q], cudaIpcMemLazyEnablePeerAccess));
+    const cudaError_t err = cudaIpcOpenMemHandle(&ptr, handles[q], cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) {
+      cudaGetLastError();      // not sticky: later launches must not inherit it
+      return fail(TL_ERR_CUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(err));
+    }
     comm->peers.win[q] = static_cast<Window *>(ptr);
     comm->opened[q] = true;
   }

@@ -35,18 +35,39 @@ class PeerExchange:
         self.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
         self.capacity = int(capacity)
         self._comm = ctypes.c_void_p()
+        self._group = group
         nbytes = lib.tl_peer_handle_bytes()
         handle = ctypes.create_string_buffer(nbytes)
+        # Every rank walks the same collective sequence (all_gather, all_reduce) whether or not
+        # its local steps succeed, so a rank that cannot create or map a window (no CUDA IPC in
+        # this container, no peer access) makes ALL ranks raise together instead of deadlocking.
+        failure = None
         with torch.cuda.device(self.device):
-            nat.check(lib.tl_peer_create(self.rank, self.world, self.capacity, ctypes.byref(self._comm),
-                                         handle), 'tl_peer_create')
+            rc = lib.tl_peer_create(self.rank, self.world, self.capacity, ctypes.byref(self._comm), handle)
+            if rc != 0:
+                failure = f'tl_peer_create: {lib.tl_last_error().decode(errors="replace")}'
+                self._comm = ctypes.c_void_p()
             if self.world > 1:
-                mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(self.device)
+                mine = torch.frombuffer(bytearray(handle.raw) + bytearray([0 if failure else 1]),
+                                        dtype=torch.uint8).to(self.device)
                 everyone = [torch.empty_like(mine) for _ in range(self.world)]
                 dist.all_gather(everyone, mine, group=group)
-                blob = b''.join(bytes(h.cpu().numpy().tobytes()) for h in everyone)
-                nat.check(lib.tl_peer_connect(self._comm, blob), 'tl_peer_connect')
-                dist.barrier(group=group)        # every window is mapped before the first push
+                blobs = [bytes(h.cpu().numpy().tobytes()) for h in everyone]
+                if failure is None and all(b[-1] == 1 for b in blobs):
+                    rc = lib.tl_peer_connect(self._comm, b''.join(b[:-1] for b in blobs))
+                    if rc != 0:
+                        failure = f'tl_peer_connect: {lib.tl_last_error().decode(errors="replace")}'
+                elif failure is None:
+                    failure = 'a peer could not create its window'
+                ok = torch.tensor([0 if failure else 1], dtype=torch.int32, device=self.device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # also: every window is mapped
+                if int(ok.item()) == 0 and failure is None:
+                    failure = 'a peer could not map the windows'
+            if failure is not None:
+                if self._comm:
+                    lib.tl_peer_destroy(self._comm)
+                    self._comm = ctypes.c_void_p()
+                raise nat.NativeLibraryError(f'peer-memory exchange unavailable on rank {self.rank}: {failure}')
         self._group = group
 
     def all_reduce(self, data):
