@@ -52,8 +52,16 @@ def _worker(rank, world, port, out_dir):
     # additive per-(lens, field, wavelength) sums of this slice: [sum y, sum y^2, n_ok]
     okf = ok.double()
     moments = torch.stack(((yy * okf).sum(2), (yy * yy * okf).sum(2), okf.sum(2)), dim=-1)
+    # the penalty of compute_loss_out (rtl:641-657) is additive over pupil slices as well: one
+    # more column rides in the same all-reduce
+    ray_shape = (mu.shape[0], cy.shape[1], hi - lo, mu.shape[3])                      # [B,F,p,W]
+    full = [torch.broadcast_to(a, ray_shape).contiguous() for a in (x[:, :, lo:hi], y[:, :, lo:hi], cx, cy)]
+    stacks = oracle.trace(full[0], full[1], z, full[2], full[3], c, t, mu, mask, True)[6]
+    terms = sum(torch.stack(stacks[k]).double().sum(0) for k in stacks)           # [B,F,p,W]
+    moments = torch.cat((moments, terms.sum(2)[..., None]), dim=-1)
     ops.reduce_moments(moments)                        # the data path's one collective
-    s1, s2, n_ok = moments.sum(2).unbind(-1)           # -> per (lens, field)
+    np.save(os.path.join(out_dir, f'pen_{rank}.npy'), moments[..., 3].sum().numpy())
+    s1, s2, n_ok, _ = moments.sum(2).unbind(-1)        # -> per (lens, field)
     n = float(n_pupil * yy.shape[3])
     mean = s1 / n                                      # failed rays sit at y = 0
     rms = torch.sqrt((s2 - 2 * mean * s1 + n_ok * mean * mean) / n).mean(1)
@@ -74,3 +82,11 @@ def test_two_rank_moment_allreduce_matches_single_process(tmp_path):
     out = oracle.trace(*tracer._ray_set(specs, lens))
     want = oracle.spot_rms(out[0], out[1], out[4]).item()
     assert abs(got[0][0] - want) <= 1e-5 * want
+    pens = [float(np.load(tmp_path / f'pen_{r}.npy')) for r in range(world)]
+    assert pens[0] == pens[1]
+    args = tracer._ray_set(specs, lens)
+    shape = out[4].shape
+    full = [torch.broadcast_to(a, shape).contiguous() if j in (0, 1, 3, 4) else a for j, a in enumerate(args)]
+    stacks = oracle.trace(*full, True)[6]
+    whole = float(sum(torch.stack(stacks[k]).double().sum() for k in stacks))
+    assert abs(pens[0] - whole) <= 1e-9 * whole
