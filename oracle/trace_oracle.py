@@ -25,7 +25,15 @@ Pinning: the reference ships no tests or golden vectors, s
 the pins are outputs of the unmodified reference itself, generated in the build
 container by ``tests/golden/make_golden.py`` and committed under
 ``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` holds this oracle to
-them bit-for-bit (masks, points, cosines) and to 1e-6 on gradients.
+them bit-for-bit (masks, points, cosines) and to 1e-6 on gradients.  The
+``aggregate=True`` branch (penalty stacks rtl:641-657 and the loss that
+``compute_loss_out`` builds on them) is pinned the same way by
+``tests/golden/make_golden_aggregate.py`` -> ``tests/golden/aggregate/*.npz`` and
+``tests/test_penalty_cpu.py`` (stacks bit-for-bit, penalty / loss gradients to 1e-6,
+the reference's NaN pattern included).  Three switches document where a test has to
+leave the verbatim reference: ``ieee_sqrt`` (torch's CPU sqrt is not correctly
+rounded), ``finite_penalty_gradients`` (the reference's penalty gradient is NaN once a
+ray fails) and ``fp32_clamp_bound`` (fp64 runs clamp at 1 - 1e-7, fp32 runs at 1 - 2^-23).
 """
 from __future__ import annotations
 
