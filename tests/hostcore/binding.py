@@ -141,3 +141,15 @@ def exact_pen_adjoint(dtype, x, y, z, cx, cy, c, t, mu, live, allow_backward, se
        *[_p(g) for g in grads], *[_p(g) for g in pg])
     return dict(gx=grads[0], gy=grads[1], gz=grads[2], gcx=grads[3], gcy=grads[4],
                 gc=pg[0], gt=pg[1], gmu=pg[2])
+
+
+def forward_mode(x, y, z, cx, cy, c, t, mu):
+    """Fast-policy image point and its 2x2 Jacobian w.r.t. the pupil point via the D2 pair."""
+    n = x.size
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    x, y, z, cx, cy, c, t, mu = map(f, (x, y, z, cx, cy, c, t, mu))
+    ox, oy = np.empty(n, np.float32), np.empty(n, np.float32)
+    jac = np.empty((n, 4), np.float32)
+    lib().hc_forward_mode(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(cx), _p(cy), ctypes.c_int(c.size), _p(c),
+                          _p(t), _p(mu), _p(ox), _p(oy), _p(jac))
+    return ox, oy, jac

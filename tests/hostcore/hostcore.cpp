@@ -285,3 +285,19 @@ static void exact_pen_adjoint(int64_t n, const float *x, const float *y, const f
                  gcx, gcy, gc, gt, gmu
 extern "C" void hc_exact_pen_adjoint_f32(HCE_ARGS(float)) { exact_pen_adjoint<float>(HCE_PASS); }
 extern "C" void hc_exact_pen_adjoint_f64(HCE_ARGS(double)) { exact_pen_adjoint<double>(HCE_PASS); }
+
+// Forward-mode pair D2 through the fast policy (what k_aim runs for its tee rays): image point
+// and its Jacobian w.r.t. the entrance-pupil point, one lens, one wavelength.
+extern "C" void hc_forward_mode(int64_t n, const float *x, const float *y, const float *z, const float *cx,
+                                const float *cy, int S, const float *c, const float *t, const float *mu,
+                                float *ox, float *oy, float *jac /* [n,4]: dx/dxp, dx/dyp, dy/dxp, dy/dyp */) {
+  for (int64_t i = 0; i < n; ++i) {
+    Ray<D2> r{D2(x[i], 1.f, 0.f), D2(y[i], 0.f, 1.f), D2(z[i]), D2(cx[i]), D2(cy[i]),
+              fast_cz0(D2(cx[i]), D2(cy[i]))};
+    D2 mq(1.0f), travel;
+    for (int k = 0; k < S; ++k) fast_surface(r, D2(c[k]), D2(mu[k]), D2(mu[k] * mu[k]), D2(t[k]), mq, travel);
+    fast_image(r);
+    ox[i] = r.x.v; oy[i] = r.y.v;
+    jac[4 * i + 0] = r.x.a; jac[4 * i + 1] = r.x.b; jac[4 * i + 2] = r.y.a; jac[4 * i + 3] = r.y.b;
+  }
+}

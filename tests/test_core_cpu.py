@@ -94,3 +94,30 @@ def test_adjoint_matches_autograd_fp64(golden):
             assert err < 1e-9, err
         # the forward itself, in fp64, equals the oracle in fp64
         assert np.abs(r['y'] - out[1].detach().numpy().ravel()).max() < 1e-11
+
+
+def test_forward_mode_pair_matches_autograd(golden):
+    """D2 (value + derivatives along the pupil's x and y), the arithmetic of the on-device ray
+    aiming (tl_aim): Jacobian d(image point)/d(pupil point) against autograd of the oracle in fp64."""
+    if not golden['out_ok'].all():
+        return
+    shape = golden['out_ok'].shape
+    full = {k: np.broadcast_to(golden['in_' + k], shape) for k in ('x', 'y', 'z', 'cx', 'cy')}
+    w = 1
+    rays = {k: np.ascontiguousarray(v[0, :, :, w]).ravel()[:96] for k, v in full.items()}
+    c, t, mu = golden['in_c'][0, 0, 0, 0], golden['in_t'][0, 0, 0, 0], golden['in_mu'][0, 0, 0, w]
+    ox, oy, jac = hc.forward_mode(rays['x'], rays['y'], rays['z'], rays['cx'], rays['cy'], c, t, mu)
+    ti = {k: torch.tensor(v.astype(np.float64).reshape(1, 1, -1, 1), requires_grad=k in ('x', 'y'))
+          for k, v in rays.items()}
+    tc, tt, tmu = (torch.tensor(v.astype(np.float64).reshape(1, 1, 1, 1, -1)) for v in (c, t, mu))
+    mask = torch.ones((1, 1, 1, 1, c.size), dtype=torch.bool)
+    out = oracle.trace(ti['x'], ti['y'], ti['z'], ti['cx'], ti['cy'], tc, tt, tmu, mask)
+    scale = max(np.abs(golden['out_x']).max(), np.abs(golden['out_y']).max())
+    assert np.abs(ox - out[0].detach().numpy().ravel()).max() <= 1e-5 * scale
+    assert np.abs(oy - out[1].detach().numpy().ravel()).max() <= 1e-5 * scale
+    want = []
+    for o in (out[0], out[1]):
+        gx, gy = torch.autograd.grad(o.sum(), [ti['x'], ti['y']], retain_graph=True)
+        want += [gx.numpy().ravel(), gy.numpy().ravel()]
+    want = np.stack(want, axis=1)                     # [n, 4]: dx/dxp, dx/dyp, dy/dxp, dy/dyp
+    assert np.abs(jac - want).max() <= 2e-5 * max(1.0, np.abs(want).max())
