@@ -97,3 +97,35 @@ def test_cpu_tensors_are_rejected_loudly():
     tracer = rt.RayTracer(mode='circular', n_rays=(4, 4), default_device='cpu')
     with pytest.raises(_native.NativeLibraryError):
         tracer.trace_rays(specs, lens)
+
+
+def test_staging_decision_of_the_front_end():
+    """Which ray sets the staged kernels (tl_stage_fwd, tl_aim) build, decided on the host:
+    (can_stage, aimed) for the tracer settings the reference offers."""
+    from tests.conftest import load_golden
+    specs, lens = _lens_from(load_golden('cooke_8x8'))          # stop inside the lens (stop_idx 4)
+    base = dict(mode='circular', n_rays=(8, 8), rel_fields=(0., 1.), wavelengths=('d',), default_device='cpu')
+    assert rt.RayTracer(**base)._staging(lens) == (True, False)
+    assert rt.RayTracer(n_ray_aiming_iter=1, **base)._staging(lens) == (True, True)
+    mirror = rt.RayTracer(n_ray_aiming_iter=1, **base)
+    mirror.device_aiming = False
+    assert mirror._staging(lens) == (False, False)
+    assert rt.RayTracer(n_ray_aiming_iter=1, ray_aiming_mode='paraxial', **base)._staging(lens) == (False, False)
+    vig = rt.RayTracer(vig_fn=lambda fields, v: v[:, None] * fields, **base)
+    assert vig._staging(lens)[0] is False and vig._staging(lens, use_vig=False)[0] is True
+    rnd = dict(base, mode='skew_random')
+    assert rt.RayTracer(**rnd)._staging(lens)[0] is False
+    # a stop in front of the lens needs no aiming at all (rtl:131-133)
+    structure = lm.Structure(np.array([0]), sequence=np.array(['GA']), default_device='cpu')
+    front = lm.Lens(structure, torch.tensor([[0.05, -0.05]]), torch.tensor([[2.0, 10.0]]),
+                    torch.tensor([[1.5, 1.0]]), torch.tensor([[60.0, 0.0]]))
+    assert rt.RayTracer(n_ray_aiming_iter=1, **base)._staging(front) == (True, False)
+
+
+def test_stack_keys_and_exchange_module_import_without_a_gpu():
+    from torchoptics_b200 import ops, peer
+    assert ops.STACK_KEYS == ('z_RELU', 'theta_norm', 'theta_prime_norm')       # rtl:598
+    assert hasattr(peer, 'PeerExchange')
+    with pytest.raises(Exception):       # CPU tensors never reach a kernel
+        ops.penalty_sum(*[torch.zeros(1, 1, 1, 1)] * 5, *[torch.zeros(1, 1, 1, 1, 2)] * 3,
+                        torch.ones(1, 1, 1, 1, 2, dtype=torch.bool), 2)
