@@ -121,3 +121,59 @@ def test_forward_mode_pair_matches_autograd(golden):
         want += [gx.numpy().ravel(), gy.numpy().ravel()]
     want = np.stack(want, axis=1)                     # [n, 4]: dx/dxp, dx/dyp, dy/dxp, dy/dyp
     assert np.abs(jac - want).max() <= 2e-5 * max(1.0, np.abs(want).max())
+
+
+def _random_problem(rng, n_surf, n_rays):
+    """A random spherical system (curvatures of both signs, flat and dummy surfaces, glass / air
+    alternation with random indices) and a ray bundle wide enough that a good part of it misses,
+    reflects totally or runs backward."""
+    c = rng.uniform(-0.12, 0.12, n_surf).astype(np.float32)
+    c[rng.random(n_surf) < 0.2] = 0.0
+    t = rng.uniform(0.3, 6.0, n_surf).astype(np.float32)
+    t[rng.random(n_surf) < 0.1] *= -0.2                      # a few negative gaps
+    n = np.ones(n_surf + 1, np.float32)
+    n[1:] = np.where(rng.random(n_surf) < 0.5, rng.uniform(1.45, 1.9, n_surf), 1.0).astype(np.float32)
+    mu = (n[:-1] / n[1:]).astype(np.float32)
+    live = (rng.random(n_surf) < 0.85)
+    live[0] = True
+    x = rng.uniform(-9, 9, n_rays).astype(np.float32)
+    y = rng.uniform(-9, 9, n_rays).astype(np.float32)
+    z = np.full(n_rays, rng.uniform(-3, 3), np.float32)
+    cx = rng.uniform(-0.3, 0.3, n_rays).astype(np.float32)
+    cy = rng.uniform(-0.5, 0.5, n_rays).astype(np.float32)
+    return dict(x=x, y=y, z=z, cx=cx, cy=cy), c, t, mu, live
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize('seed', range(24))
+@pytest.mark.parametrize('allow', [True, False])
+def test_exact_policy_bit_identical_on_random_systems(seed, allow):
+    """Beyond the 12 golden cases: 24 random systems x {allow_backward_rays}, 300 wild rays each.
+    The exact policy (masks, points, cosines, and the aggregate=True stacks) against the oracle
+    with the correctly rounded sqrt, bit for bit (angles: two libms, a few ULP)."""
+    rng = np.random.default_rng(1000 + seed)
+    n_surf = int(rng.integers(1, 9))
+    rays, c, t, mu, live = _random_problem(rng, n_surf, 300)
+    ti = {k: torch.from_numpy(v).reshape(1, 1, -1, 1) for k, v in rays.items()}
+    tc, tt, tmu = (torch.from_numpy(v).reshape(1, 1, 1, 1, -1) for v in (c, t, mu))
+    tmask = torch.from_numpy(live).reshape(1, 1, 1, 1, -1)
+    with oracle.ieee_sqrt():
+        ref = oracle.trace(ti['x'], ti['y'], ti['z'], ti['cx'], ti['cy'], tc, tt, tmu, tmask, True, allow)
+    got = hc.trace_exact(rays['x'], rays['y'], rays['z'], rays['cx'], rays['cy'], c, t, mu, live, allow)
+    for j in range(4):
+        want = ref[j].reshape(-1).numpy()
+        assert np.array_equal(got[j].view(np.uint32), want.view(np.uint32)), j
+    assert np.array_equal(got[4].astype(bool), ref[4].reshape(-1).numpy())
+    assert np.array_equal(got[5].astype(bool), torch.broadcast_to(ref[5], ref[4].shape).reshape(-1).numpy())
+    (zr, th, thp), ok, bits = hc.trace_exact_pen(rays['x'], rays['y'], rays['z'], rays['cx'], rays['cy'], c, t, mu,
+                                                 live, allow)
+    stacks = {k: torch.stack(ref[6][k]).reshape(n_surf, -1).numpy() for k in ref[6]}
+    assert np.array_equal(zr.view(np.uint32), stacks['z_RELU'].view(np.uint32))
+    np.testing.assert_allclose(th, stacks['theta_norm'], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(thp, stacks['theta_prime_norm'], rtol=1e-6, atol=1e-7)
+    assert np.array_equal(ok.astype(bool), ref[4].reshape(-1).numpy())
+    # the bundle really exercises the failure paths
+    frac_ok = ref[4].float().mean().item()
+    assert 0.0 <= frac_ok <= 1.0

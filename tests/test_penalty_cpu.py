@@ -184,3 +184,45 @@ def test_penalty_backward_with_failing_rays_matches_finite_oracle(name):
     for got, ref in ((np.array([gz]), want[0]), (gc, want[1]), (gt, want[2]), (np.stack(gmu), want[3])):
         ref = ref.numpy().reshape(got.shape)
         assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 2e-5      # fp32 states, fp64 sweep
+
+
+@pytest.mark.parametrize('seed', range(16))
+def test_penalty_backward_on_random_systems(seed):
+    """The kernels' penalty backward (ok bits per surface, failed lanes forced to zero, equator
+    branch) on random systems with wild ray bundles, in fp64 on the fp32-traced states, against
+    autograd of the oracle with finite penalty gradients.  Seeds whose fp64 oracle takes another
+    branch than the fp32 trace for some ray (a ray on a threshold) compare the remaining rays."""
+    from tests.test_core_cpu import _random_problem
+    rng = np.random.default_rng(2000 + seed)
+    n_surf = int(rng.integers(2, 8))
+    rays, c, t, mu, live = _random_problem(rng, n_surf, 200)
+    n = rays['x'].size
+    ti = {k: torch.from_numpy(v.astype(np.float64)).reshape(1, 1, -1, 1).requires_grad_(True) for k, v in rays.items()}
+    tc, tt, tmu = (torch.from_numpy(v.astype(np.float64)).reshape(1, 1, 1, 1, -1).requires_grad_(True)
+                   for v in (c, t, mu))
+    tmask = torch.from_numpy(live).reshape(1, 1, 1, 1, -1)
+    with oracle.finite_penalty_gradients(), oracle.fp32_clamp_bound():
+        ref = oracle.trace(ti['x'], ti['y'], ti['z'], ti['cx'], ti['cy'], tc, tt, tmu, tmask, True)
+    (zr, th, thp), ok32, bits = hc.trace_exact_pen(rays['x'], rays['y'], rays['z'], rays['cx'], rays['cy'], c, t,
+                                                   mu, live, True)
+    thp64 = torch.stack(ref[6]['theta_prime_norm']).reshape(n_surf, n).detach().numpy()
+    same = np.all((thp64 < 1.0) == (thp < 1.0), axis=0)          # same ok history in fp32 and fp64
+    # keep away from the clamp window and from grazing incidence, where fp32 states limit the match
+    th64 = torch.stack(ref[6]['theta_norm']).reshape(n_surf, n).detach().numpy()
+    calm = np.all((np.minimum(th64, thp64) > 2e-3) & (np.maximum(np.where(th64 < 1, th64, 0),
+                                                                np.where(thp64 < 1, thp64, 0)) < 0.93), axis=0)
+    keep = same & calm
+    assert keep.sum() >= 20
+    seed_w = np.zeros(n)
+    seed_w[keep] = 1.0
+    seeds = np.tile(seed_w, (n_surf, 1))
+    r = hc.exact_pen_adjoint(np.float64, rays['x'], rays['y'], rays['z'], rays['cx'], rays['cy'], c, t, mu, live,
+                             True, np.zeros(n), seeds, seeds, seeds)
+    w = torch.from_numpy(seeds)
+    loss = sum((torch.stack(ref[6][k]).reshape(n_surf, n) * w).sum() for k in KEYS)
+    want = torch.autograd.grad(loss, [ti['x'], ti['y'], ti['z'], ti['cx'], ti['cy'], tc, tt, tmu])
+    for label, got, ref_g in zip(('x', 'y', 'z', 'cx', 'cy', 'c', 't', 'mu'),
+                                 (r['gx'], r['gy'], r['gz'], r['gcx'], r['gcy'], r['gc'], r['gt'], r['gmu']), want):
+        ref_g = ref_g.numpy().ravel()
+        scale = max(np.abs(ref_g).max(), 1e-6)
+        assert np.abs(got - ref_g).max() <= 2e-4 * scale, (label, np.abs(got - ref_g).max() / scale)
