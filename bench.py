@@ -477,7 +477,7 @@ def main():
                 'clocks': clocks.summary(),
                 'e2e': {'value': e2e_value, 'unit': 'events/s', 'h2d_bytes_per_step': h2d,
                         'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_secs / args.steps * 1e3,
-                        'api': 'GraphedSpotStep (CUDA graph of the public RayTracer.spot_rms path)'
+                        'api': 'GraphedSpotStep (CUDA graph of the public RayTracer.spot_rms_and_grads path: one pinned H2D copy, the kernel sequence, one D2H copy)'
                                if graphed is not None else 'RayTracer.spot_rms (eager)',
                         'eager_api_value': events_total * eager_steps / eager_secs,
                         'eager_api_ms_per_step': eager_secs / eager_steps * 1e3,
