@@ -36,7 +36,6 @@ if ROOT not in sys.path:
 FLOPS_FWD, FLOPS_BWD = 61, 105          # per spherical ray-surface event
 N_FIELDS, N_SIDE = 16, 296
 WAVELENGTHS = ('C', 'd', 'F')
-CPU_SAMPLE_SIDE = 160                    # bounded CPU sample: 16 x 3 x 160^2 rays
 METRIC = 'ray-surface events/sec fwd+bwd'
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_trace_adj launch of this workload, from the
 # ncu --set full capture summarised in profiles/r1d_spot_grad_f4_geometric.txt (805 120 B + 0 B):
@@ -101,47 +100,81 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path on the host cores
+# CPU arm: the reference's own path on the host cores
 # ----------------------------------------------------------------------------
-def cpu_arm(steps, warmup, side=CPU_SAMPLE_SIDE):
-    from oracle import trace_oracle as oracle
-    from torchoptics_b200 import RayTracer, prescriptions
-    specs, lens = prescriptions.double_gauss('cpu')
-    for name in ('c', 't', 'nd'):
-        getattr(lens, name).requires_grad_(True)
-    tracer = RayTracer(mode='circular', n_rays=(side, side),
-                       rel_fields=tuple(np.linspace(0, 1, N_FIELDS).tolist()),
-                       wavelengths=WAVELENGTHS, default_device='cpu')
-    events = N_FIELDS * len(WAVELENGTHS) * side * side * lens.c.shape[1]
-    times = []
+def cpu_arm(steps, warmup, side=N_SIDE):
+    """trace_rays -> compute_rms2d -> backward of the config-2 lens at the configured pupil
+    (side^2 points, 16 fields, 3 wavelengths) on the host cores, all threads.  Runs the UNMODIFIED
+    reference staged under oracle/_ref (oracle/make_ref.py; kind "reference") when it travelled with
+    the snapshot, else the oracle port of it (kind "port")."""
+    n_threads = os.cpu_count() or 1
+    torch.set_num_threads(n_threads)          # torchrun exports OMP_NUM_THREADS=1: undo it for this arm
+    fields = tuple(np.linspace(0, 1, N_FIELDS).tolist())
+    from oracle import make_ref
+    if make_ref.available():
+        from torchoptics_b200.prescriptions import DOUBLE_GAUSS as d      # plain prescription data
+        rtl, lm = make_ref.load_reference()
+        kind = 'reference'
+        structure = lm.Structure(np.array(d['stop_idx']), sequence=np.array(d['sequence']), default_device='cpu')
+        lens = lm.Lens(structure, *(torch.tensor(d[k], dtype=torch.float32) for k in ('c', 't', 'nd', 'v')))
+        epd = lens.efl.detach() / torch.tensor(d['f_number'])
+        specs = lm.Specs(structure, epd, torch.deg2rad(torch.tensor(d['hfov'])))
+        for name in ('c', 't', 'nd'):
+            getattr(lens, name).requires_grad_(True)
+        tracer = rtl.RayTracer(mode='circular', n_rays=(side, side), rel_fields=fields, wavelengths=WAVELENGTHS,
+                               default_device='cpu')
+
+        def one_step():
+            x, y, cx, cy, ok, bw = tracer.trace_rays(specs, lens)
+            rms = rtl.compute_rms2d(x, y, ok)
+            torch.autograd.grad(rms, [lens.c, lens.t, lens.nd])
+            return float(rms)
+        what = 'the unmodified reference (oracle/_ref: torchlens.ray_tracing_lite RayTracer.trace_rays + compute_rms2d + autograd)'
+    else:
+        from oracle import trace_oracle as oracle
+        from torchoptics_b200 import RayTracer, prescriptions
+        kind = 'port'
+        specs, lens = prescriptions.double_gauss('cpu')
+        for name in ('c', 't', 'nd'):
+            getattr(lens, name).requires_grad_(True)
+        tracer = RayTracer(mode='circular', n_rays=(side, side), rel_fields=fields, wavelengths=WAVELENGTHS,
+                           default_device='cpu')
+
+        def one_step():
+            out = oracle.trace(*tracer._ray_set(specs, lens))
+            rms = oracle.spot_rms(out[0], out[1], out[4])
+            torch.autograd.grad(rms, [lens.c, lens.t, lens.nd])
+            return float(rms)
+        what = 'oracle (torch CPU eager port of trace_skew + compute_rms2d + autograd; oracle/_ref not staged)'
+    S = int(lens.c.shape[1])
+    events = N_FIELDS * len(WAVELENGTHS) * side * side * S
+    times, rms = [], None
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        args = tracer._ray_set(specs, lens)
-        out = oracle.trace(*args)
-        rms = oracle.spot_rms(out[0], out[1], out[4])
-        torch.autograd.grad(rms, [lens.c, lens.t, lens.nd])
+        rms = one_step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
     best = min(times)
-    return {'value': events / best, 'unit': 'events/s', 'cores': torch.get_num_threads(),
-            'kind': 'port',
-            'sample': f'oracle (torch CPU eager port of trace_skew+compute_rms2d+autograd), '
-                      f'double-gauss S11, {N_FIELDS} fields x {len(WAVELENGTHS)} wavelengths x '
-                      f'{side}^2 pupil = {events // lens.c.shape[1]} rays, best of {steps} '
-                      f'after {warmup} warm-up',
-            'ms_per_step': statistics.mean(times) * 1e3, 'host_cpus': os.cpu_count()}
+    return {'value': events / best, 'unit': 'events/s', 'cores': torch.get_num_threads(), 'kind': kind,
+            'sample': f'{what}, double-gauss S{S}, {N_FIELDS} fields x {len(WAVELENGTHS)} wavelengths x '
+                      f'{side}^2 pupil = {events // S} rays ({events} events) per step, best of {steps} after '
+                      f'{warmup} warm-up, rms {rms:.6f}',
+            'ms_per_step': statistics.mean(times) * 1e3, 'host_cpus': os.cpu_count(), 'rays': events // S}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 10))
-    base = cpu_arm(steps, max(1, min(args.warmup, 2)))
+    steps = max(1, min(args.steps, 5))
+    warmup = max(1, min(args.warmup, 1))
+    base = cpu_arm(steps, warmup)
     line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'events/s',
-            'n_gpus': args.gpus, 'steps': steps, 'warmup': max(1, min(args.warmup, 2)),
+            'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup,
             'ms_per_step': base['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': workload_name(N_SIDE), 'cpu_sample': base['sample']},
+            'config': {'workload': workload_name(N_SIDE), 'lens': 'double_gauss_50mm_f3', 'fields': N_FIELDS,
+                       'wavelengths': len(WAVELENGTHS), 'rays': base['rays'],
+                       'note': 'one host runs one CPU copy of the per-GPU workload (4.2 M rays) whatever --gpus is'},
             'cpu_baseline': {k: base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
             'e2e': {'value': base['value'], 'unit': 'events/s', 'h2d_bytes_per_step': 0,
                     'd2h_bytes_per_step': 0}}
@@ -486,7 +519,7 @@ def main():
                 'gpu_launches': launches_per_step * args.steps,
                 'roofline': roofline, 'forward': forward, 'penalty': penalty_row}
         if world == 1 and not args.no_cpu_baseline:
-            base = cpu_arm(5, 1)
+            base = cpu_arm(3, 1)
             line['cpu_baseline'] = {k: base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
         print(json.dumps(line), flush=True)
     faulthandler.cancel_dump_traceback_later()

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TL_ABI_VERSION 9
+#define TL_ABI_VERSION 10
 
 enum {
   TL_OK = 0,
@@ -235,7 +235,10 @@ int tl_stage_bwd(const TlLens *lens, const float *gmu, const float *gz, float *g
  *   tl_peer_allreduce_f64  out[i] = sum over ranks of data[i], i < n <= capacity; every rank must
  *                    call it the same number of times; graph-capturable (no per-call state on the
  *                    host); data != out when world > 1.
- *   tl_peer_status   (synchronising) status 0 = ok, 1 = a wait for a peer timed out (4 s). */
+ *                    Every all-reduce of one communicator must be issued on ONE stream (the epoch is
+ *                    device state).  A wait for a peer that times out (4 s) is loud and sticky: this
+ *                    and every later call write NaN to `out` and set the status word.
+ *   tl_peer_status   (synchronising) status 0 = ok, 1 = a wait for a peer timed out. */
 typedef struct TlPeerComm TlPeerComm;
 size_t tl_peer_handle_bytes(void);
 int tl_peer_create(int32_t rank, int32_t world, int64_t capacity, TlPeerComm **comm, void *handle_out);
@@ -254,6 +257,12 @@ int tl_peer_destroy(TlPeerComm *comm);
  * gradient. */
 int tl_aim(const TlLens *lens, const float *mu, const float *z, const float *cy, const float *half_epd,
            int32_t allow_backward_rays, float *aim, void *stream);
+
+/* Layout self-description, so that a binding can check itself against the library it loaded:
+ * for struct `which` (0 TlStrided, 1 TlProblem, 2 TlTraceOut, 3 TlSeeds, 4 TlGrads, 5 TlSpotOut,
+ * 6 TlPenaltyOut, 7 TlLens) returns "Name:sizeof;field@offsetof;field@offsetof;..." in declaration
+ * order (thread-local storage, valid until the next call), or NULL for an unknown struct. */
+const char *tl_abi_describe(int32_t which);
 
 /* Number of kernels this library has launched since it was loaded (bench.py's
  * gpu_launches counter). */

@@ -52,14 +52,37 @@ def load_lens(lm, path, dtype=torch.float32):
     return d, structure, lens
 
 
+F64_KEYS = ('rms', 'grad_c', 'grad_t', 'grad_nd', 'grad_in_z', 'grad_in_c', 'grad_in_t', 'grad_in_mu',
+            'in_x', 'in_y')
+
+
 def run_case(rtl, lm, yml, n_rays, rel_fields, wavelengths, epd_scale=1.0, n_ray_aiming_iter=0,
              allow_backward_rays=True, mode='circular'):
-    d, structure, lens = load_lens(lm, yml)
+    """One golden record: the reference in fp32 (every key) and, under the prefix ``f64_``, the RMS,
+    the gradients and the (possibly ray-aimed) pupil of the SAME reference code run in float64 --
+    the yardstick for "no farther from the truth than the reference's own fp32"."""
+    rec = _run_case(rtl, lm, yml, n_rays, rel_fields, wavelengths, epd_scale, n_ray_aiming_iter,
+                    allow_backward_rays, mode, torch.float32)
+    torch.set_default_dtype(torch.float64)
+    try:
+        rec64 = _run_case(rtl, lm, yml, n_rays, rel_fields, wavelengths, epd_scale, n_ray_aiming_iter,
+                          allow_backward_rays, mode, torch.float64)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    assert np.array_equal(rec['out_ok'], rec64['out_ok']), 'fp32 and fp64 masks of the reference differ'
+    for k in F64_KEYS + (('out_x', 'out_y') if n_ray_aiming_iter > 0 else ()):
+        rec['f64_' + k] = rec64[k]
+    return rec
+
+
+def _run_case(rtl, lm, yml, n_rays, rel_fields, wavelengths, epd_scale, n_ray_aiming_iter,
+              allow_backward_rays, mode, dtype):
+    d, structure, lens = load_lens(lm, yml, dtype)
     for name in ('c', 't', 'nd', 'v'):
         getattr(lens, name).requires_grad_(True)
     efl = lens.efl.detach()
-    epd = efl / torch.tensor(d['f_number']) * epd_scale
-    hfov = torch.deg2rad(torch.tensor(d['hfov']))
+    epd = efl / torch.tensor(d['f_number'], dtype=dtype) * epd_scale
+    hfov = torch.deg2rad(torch.tensor(d['hfov'], dtype=dtype))
     specs = lm.Specs(structure, epd, hfov)
 
     captured = {}
@@ -147,6 +170,9 @@ def main():
     cases['tessar_8x8_aimed'] = run_case(rtl, lm, tessar, n_ray_aiming_iter=1, **std)  # >1 iteration raises in the reference (rtl:170)
     cases['cooke_32x32'] = run_case(rtl, lm, cooke, n_rays=(32, 32), rel_fields=(0., 0.5, 0.707, 1.),
                                     wavelengths=(656.3, 587.6, 546.1, 486.1))
+    # BASELINE.json configs[0] at its exact shape: Cooke triplet, 3 fields x 3 wavelengths, 96 x 76
+    # pupil = 65 664 rays
+    cases['cooke_96x76_config1'] = run_case(rtl, lm, cooke, n_rays=(96, 76), **{k: std[k] for k in ('rel_fields', 'wavelengths')})
     for name, rec in cases.items():
         np.savez_compressed(os.path.join(HERE, f'{name}.npz'), **rec)
         print(f"{name:34s} S={rec['in_t'].shape[-1]} rays={rec['out_ok'].size:6d} "

@@ -51,6 +51,26 @@ def fast(dtype, x, y, z, cx, cy, c, t, mu, live, seeds=None):
                 gc=pg[0], gt=pg[1], gmu=pg[2])
 
 
+def rev(dtype, x, y, z, cx, cy, c, t, mu, live, seeds=None, exact_park=False, two_comp=False):
+    """Reversible formulation: fast_surface_rev forward (+ sweep_sphere_rev adjoint with seeds)."""
+    n = x.size
+    f = lambda a: np.ascontiguousarray(a, dtype=dtype)
+    x, y, z, cx, cy, c, t, mu = map(f, (x, y, z, cx, cy, c, t, mu))
+    live = np.ascontiguousarray(live, dtype=np.uint8)
+    S = c.size
+    outs = [np.zeros(n, dtype) for _ in range(6)]
+    grads = [np.zeros(n, dtype) for _ in range(5)]
+    pg = [np.zeros(S, np.float64) for _ in range(3)]
+    sd = [None] * 4 if seeds is None else [f(s) for s in seeds]
+    fn = lib().hc_rev_f32 if dtype == np.float32 else lib().hc_rev_f64
+    fn(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(cx), _p(cy), ctypes.c_int(S), _p(c), _p(t), _p(mu),
+       _p(live), *[_p(s) for s in sd], *[_p(o) for o in outs], *[_p(g) for g in grads],
+       *[_p(g) for g in pg], ctypes.c_int(int(exact_park) | (2 if two_comp else 0)))
+    return dict(x=outs[0], y=outs[1], cx=outs[2], cy=outs[3], min_cos2=outs[4], min_travel=outs[5],
+                gx=grads[0], gy=grads[1], gz=grads[2], gcx=grads[3], gcy=grads[4],
+                gc=pg[0], gt=pg[1], gmu=pg[2])
+
+
 def _asph_tables(dtype, c, k, a, t, mu, sd):
     f = lambda v: np.ascontiguousarray(v, dtype=dtype)
     sd2 = np.square(np.asarray(sd, dtype=np.float64)).astype(dtype)

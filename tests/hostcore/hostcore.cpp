@@ -84,6 +84,63 @@ void hc_fast_f64(HC_ARGS(double)) { fast_and_adjoint<double>(HC_PASS); }
 }  // extern "C"
 
 
+// Reversible formulation (fast_surface_rev / sweep_sphere_rev): the forward parks (dist, cos, cos')
+// per surface and the sweep walks the ray backwards.  EXACT_PARK: the parked values come from the
+// exact-policy trace instead (what the kernels do for a lane that was re-traced).
+template <class T>
+static void rev_and_adjoint(int64_t n, const T *x, const T *y, const T *z, const T *cx, const T *cy,
+                            int S, const T *c, const T *t, const T *mu, const uint8_t *live,
+                            const T *sx, const T *sy, const T *scx, const T *scy,
+                            T *ox, T *oy, T *ocx, T *ocy, T *min_cos2, T *min_travel,
+                            T *gx, T *gy, T *gz, T *gcx, T *gcy, double *gc, double *gt,
+                            double *gmu, int exact_park) {
+  std::vector<Parked<T>> st(S);
+  for (int k = 0; k < S; ++k) gc[k] = gt[k] = gmu[k] = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    Ray<T> r{x[i], y[i], z[i], cx[i], cy[i], fast_cz0(cx[i], cy[i])};
+    T mq = T(1), mcz = T(1), mtr = T(1e30);
+    for (int k = 0; k < S; ++k) {
+      T travel;
+      fast_surface_rev(r, c[k], mu[k], mu[k] * mu[k], T(1) - mu[k] * mu[k], t[k], mq, mcz, travel, st[k]);
+      if (k > 0 && live[k - 1]) mtr = fmin2(mtr, travel);
+    }
+    Ray<T> pre = r;
+    T travel = fast_image(r);
+    if (live[S - 1]) mtr = fmin2(mtr, travel);
+    if (exact_park & 1) {      // float only: re-trace with the exact policy, park its values
+      Ray<float> e{(float)x[i], (float)y[i], (float)z[i], (float)cx[i], (float)cy[i],
+                   exact_cz0((float)cx[i], (float)cy[i])};
+      bool ok = true, bw = false;
+      for (int k = 0; k < S; ++k) {
+        Surface sf{(float)c[k], (float)t[k], (float)mu[k]};
+        Parked<float> pk;
+        exact_surface_t<false>(e, sf, k > 0 && live[k - 1], true, ok, bw, nullptr, &pk);
+        st[k].dist = pk.dist; st[k].ci = pk.ci; st[k].co = pk.co;
+      }
+      pre = Ray<T>{T(e.x), T(e.y), T(e.z), T(e.cx), T(e.cy), T(e.cz)};
+      exact_image(e, live[S - 1] != 0, true, ok, bw);
+      r.x = e.x; r.y = e.y;
+    }
+    ox[i] = r.x; oy[i] = r.y; ocx[i] = pre.cx; ocy[i] = pre.cy;
+    min_cos2[i] = fmin2(mq, mcz > T(kBandCz) ? T(1) : T(0)); min_travel[i] = mtr;
+    if (!sx) continue;
+    SweepRev<T> sw = sweep_begin_rev(pre, r.x, r.y, sx[i], sy[i], scx[i], scy[i]);
+    for (int k = S - 1; k >= 0; --k) {
+      SurfaceGrad<T> g = (exact_park & 2)
+          ? sweep_sphere_rev2(sw, st[k].dist, st[k].ci, c[k], t[k], mu[k], mu[k] * mu[k], T(1) - mu[k] * mu[k],
+                              T(1) / mu[k])
+          : sweep_sphere_rev(sw, st[k], c[k], t[k], mu[k], T(1) / mu[k]);
+      gc[k] += (double)g.c; gt[k] += (double)g.t; gmu[k] += (double)g.mu;
+    }
+    sweep_end_rev(sw, gx[i], gy[i], gz[i], gcx[i], gcy[i]);
+  }
+}
+
+extern "C" {
+void hc_rev_f32(HC_ARGS(float), int exact_park) { rev_and_adjoint<float>(HC_PASS, exact_park); }
+void hc_rev_f64(HC_ARGS(double), int exact_park) { rev_and_adjoint<double>(HC_PASS, exact_park); }
+}
+
 // ---------------------------------------------------------------------------
 // extension surfaces (one lens, one wavelength); surface tables: c,k,t,mu,sd2 [S], a [S,7]
 // ---------------------------------------------------------------------------

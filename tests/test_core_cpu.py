@@ -224,3 +224,125 @@ def test_fast_policy_and_adjoint_on_random_systems(seed):
     # is grossly off (not subtly): few such rays survive as clear rays even in these wild bundles
     assert bad.sum() <= 0.1 * keep.size, bad.sum()
     assert np.all(per_ray_err[bad] > 1e-4) if bad.any() else True
+
+
+# ---------------------------------------------------------------------------
+# Reversible formulation (fast_surface_rev / sweep_sphere_rev): what k_spot_rev runs
+# ---------------------------------------------------------------------------
+def _clear_rev(r, t, z):
+    length = np.abs(t).sum() + np.abs(z).max()
+    return (r['min_cos2'] > 1e-6 + 1e-4) & (r['min_travel'] > 1e-5 * max(1.0, length)) & \
+        np.isfinite(r['x'] + r['y'] + r['cx'] + r['cy'])
+
+
+def test_rev_fast_policy_close_on_clear_rays(golden):
+    """The reversible forward (near-root marching distance, cz' from the refraction formula instead
+    of a renormalising sqrt) against the reference's golden outputs, fp32."""
+    scale = max(np.abs(golden['out_x']).max(), np.abs(golden['out_y']).max())
+    n_clear = 0
+    for w, rays, c, t, mu, live in _per_wavelength(golden):
+        r = hc.rev(np.float32, rays['x'], rays['y'], rays['z'], rays['cx'], rays['cy'], c, t, mu, live)
+        clear = _clear_rev(r, t, rays['z'])
+        ok = golden['out_ok'][0, :, :, w].ravel()
+        bw = np.broadcast_to(golden['out_backward'], golden['out_ok'].shape)[0, :, :, w].ravel()
+        assert np.all(ok[clear]) and not np.any(bw[clear])
+        n_clear += clear.sum()
+        for key, ref_key, tol in (('x', 'out_x', 1e-5 * scale), ('y', 'out_y', 1e-5 * scale),
+                                  ('cx', 'out_cx', 1e-5), ('cy', 'out_cy', 1e-5)):
+            want = golden[ref_key][0, :, :, w].ravel()
+            assert np.abs(r[key][clear] - want[clear]).max(initial=0.0) <= tol, (key, w)
+    if golden['out_ok'].all() and not golden['out_backward'].any():
+        assert n_clear == golden['out_ok'].size
+
+
+def _autograd_fp64(rays, c, t, mu, live, seeds):
+    ti = {k: torch.tensor(v.astype(np.float64).reshape(1, 1, -1, 1), requires_grad=True) for k, v in rays.items()}
+    tc = torch.tensor(c.astype(np.float64).reshape(1, 1, 1, 1, -1), requires_grad=True)
+    tt = torch.tensor(t.astype(np.float64).reshape(1, 1, 1, 1, -1), requires_grad=True)
+    tmu = torch.tensor(mu.astype(np.float64).reshape(1, 1, 1, 1, -1), requires_grad=True)
+    tmask = torch.tensor(np.asarray(live).reshape(1, 1, 1, 1, -1))
+    out = oracle.trace(ti['x'], ti['y'], ti['z'], ti['cx'], ti['cy'], tc, tt, tmu, tmask)
+    loss = sum((torch.tensor(s.reshape(1, 1, -1, 1)) * o).sum() for s, o in zip(seeds, out[:4]))
+    g = torch.autograd.grad(loss, [ti['x'], ti['y'], ti['z'], ti['cx'], ti['cy'], tc, tt, tmu])
+    return out, [v.numpy().ravel() for v in g]
+
+
+@pytest.mark.parametrize('two_comp', [False, True])
+def test_rev_adjoint_matches_autograd_fp64(golden, two_comp):
+    """Backward walk from (dist, cos, cos') -- or from (dist, cos) alone, cos' rebuilt -- in fp64 ==
+    autograd of the oracle in fp64."""
+    rng = np.random.default_rng(0)
+    for w, rays, c, t, mu, live in _per_wavelength(golden):
+        ok = golden['out_ok'][0, :, :, w].ravel()
+        keep = np.nonzero(ok)[0][:200]
+        if keep.size == 0:
+            continue
+        rays = {k: v[keep].astype(np.float64) for k, v in rays.items()}
+        seeds = [rng.standard_normal(keep.size) for _ in range(4)]
+        r = hc.rev(np.float64, rays['x'], rays['y'], rays['z'], rays['cx'], rays['cy'],
+                   c.astype(np.float64), t.astype(np.float64), mu.astype(np.float64), live, seeds,
+                   two_comp=two_comp)
+        out, g = _autograd_fp64(rays, c, t, mu, live, seeds)
+        assert bool(out[4].all())
+        for got, want in zip((r['gx'], r['gy'], r['gz'], r['gcx'], r['gcy'], r['gc'], r['gt'], r['gmu']), g):
+            err = np.abs(got - want).max() / max(np.abs(want).max(), 1e-3)
+            assert err < 1e-9, err
+        assert np.abs(r['y'] - out[1].detach().numpy().ravel()).max() < 1e-11
+        assert np.abs(r['cx'] - out[2].detach().numpy().ravel()).max() < 1e-12
+
+
+@pytest.mark.parametrize('two_comp', [False, True])
+@pytest.mark.parametrize('exact_park', [False, True])
+def test_rev_adjoint_fp32_within_budget(golden, exact_park, two_comp):
+    """The same sweep in fp32 (as the kernel runs it; parked values from the fast forward or from
+    the exact-policy re-trace) against fp64 autograd: parameter gradients to 1e-4 (north_star),
+    positive seeds like the kernel's unit seed on y."""
+    rng = np.random.default_rng(1)
+    for w, rays, c, t, mu, live in _per_wavelength(golden):
+        ok = golden['out_ok'][0, :, :, w].ravel()
+        keep = np.nonzero(ok)[0][:400]
+        if keep.size == 0:
+            continue
+        rays = {k: v[keep] for k, v in rays.items()}
+        seeds = [np.zeros(keep.size), rng.uniform(0.5, 1.5, keep.size), np.zeros(keep.size), np.zeros(keep.size)]
+        r = hc.rev(np.float32, rays['x'], rays['y'], rays['z'], rays['cx'], rays['cy'], c, t, mu, live,
+                   [s.astype(np.float32) for s in seeds], exact_park=exact_park, two_comp=two_comp)
+        out, g = _autograd_fp64(rays, c, t, mu, live, seeds)
+        for name, got, want in zip(('c', 't', 'mu'), (r['gc'], r['gt'], r['gmu']), g[5:]):
+            err = np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-12)
+            assert err < 1e-4, (name, w, err)
+
+
+@pytest.mark.parametrize('seed', range(16))
+def test_rev_adjoint_on_random_systems_including_equator_hits(seed):
+    """Random systems with wild bundles: EVERY clear ray's reversible adjoint equals fp64 autograd of
+    the oracle -- including the rays that hit a sphere beyond its equator, where sweep_sphere (which
+    rebuilds n_z = +sqrt(1 - c^2 rho)) is grossly wrong: the backward walk carries the true h_z."""
+    rng = np.random.default_rng(3000 + seed)
+    n_surf = int(rng.integers(1, 9))
+    rays, c, t, mu, live = _random_problem(rng, n_surf, 400)
+    ti = {k: torch.from_numpy(v).reshape(1, 1, -1, 1) for k, v in rays.items()}
+    tc, tt, tmu = (torch.from_numpy(v).reshape(1, 1, 1, 1, -1) for v in (c, t, mu))
+    tmask = torch.from_numpy(live).reshape(1, 1, 1, 1, -1)
+    ref = oracle.trace(ti['x'], ti['y'], ti['z'], ti['cx'], ti['cy'], tc, tt, tmu, tmask)
+    r = hc.rev(np.float32, rays['x'], rays['y'], rays['z'], rays['cx'], rays['cy'], c, t, mu, live)
+    clear = _clear_rev(r, t, rays['z'])
+    ok = ref[4].reshape(-1).numpy()
+    bw = torch.broadcast_to(ref[5], ref[4].shape).reshape(-1).numpy()
+    assert np.all(ok[clear]) and not np.any(bw[clear])
+    if clear.sum() == 0:
+        return
+    scale = max(1.0, np.abs(ref[0].numpy()).max(), np.abs(ref[1].numpy()).max())
+    for key, j, tol in (('x', 0, 2e-5 * scale), ('y', 1, 2e-5 * scale), ('cx', 2, 2e-5), ('cy', 3, 2e-5)):
+        assert np.abs(r[key][clear] - ref[j].reshape(-1).numpy()[clear]).max() <= tol, key
+    keep = np.nonzero(clear)[0][:120]
+    r64 = {k: rays[k][keep].astype(np.float64) for k in rays}
+    seeds = [rng.standard_normal(keep.size) for _ in range(4)]
+    rr = hc.rev(np.float64, r64['x'], r64['y'], r64['z'], r64['cx'], r64['cy'], c.astype(np.float64),
+                t.astype(np.float64), mu.astype(np.float64), live, seeds)
+    out, g = _autograd_fp64(r64, c, t, mu, live, seeds)
+    for got, want in zip((rr['gx'], rr['gy'], rr['gz'], rr['gcx'], rr['gcy']), g[:5]):
+        err = np.abs(got - want) / np.maximum(np.abs(want), 1e-3)
+        assert err.max() < 1e-8, err.max()
+    for got, want in zip((rr['gc'], rr['gt'], rr['gmu']), g[5:]):
+        assert np.abs(got - want).max() <= 1e-8 * max(1.0, np.abs(want).max())

@@ -40,6 +40,27 @@ def _rel(got, want):
     return np.linalg.norm(got - want) / max(np.linalg.norm(want), 1e-30)
 
 
+def _close_or_no_worse_than_reference(got, ref32, ref64, tol, what):
+    """The north_star tolerance against the reference's fp32 value -- or, where that value is itself
+    farther than `tol` from the truth, no farther from the reference run in float64 than the
+    reference's own fp32 is.  Both distances are printed (pytest -s / on failure)."""
+    got, ref32, ref64 = (np.nan_to_num(np.asarray(v, dtype=np.float64)) for v in (got, ref32, ref64))
+    vs32, ours, theirs = _rel(got, ref32), _rel(got, ref64), _rel(ref32, ref64)
+    print(f'{what}: ours-vs-reference-fp32 {vs32:.2e}, ours-vs-fp64 {ours:.2e}, reference-fp32-vs-fp64 {theirs:.2e}')
+    assert vs32 <= tol or ours <= theirs, (what, vs32, ours, theirs)
+
+
+def oracle_lens_gradients(tracer, specs, lens, dtype=torch.float32):
+    """(rms, [d rms/d c, d rms/d t, d rms/d nd]) of lens 0 from the ORACLE evaluated by torch on the
+    device in `dtype` (autograd through the ray-set construction, the trace and the RMS)."""
+    leaves = [getattr(lens, k).detach().to(dtype).clone().requires_grad_(True) for k in ('c', 't', 'nd')]
+    lens_d = lm.Lens(lens.structure, *leaves, lens.v.detach().to(dtype))
+    specs_d = lm.Specs(specs.structure, specs.epd.detach().to(dtype), specs.hfov.detach().to(dtype))
+    out = oracle.trace(*tracer._ray_set(specs_d, lens_d))
+    rms = oracle.spot_rms_all_lenses(out[1], out[4])[0]
+    return rms.detach(), torch.autograd.grad(rms, leaves), out
+
+
 def _check_outputs(out, rec, exact_ref=None):
     ok_shape = rec['out_ok'].shape
     scale = max(np.abs(rec['out_x']).max(), np.abs(rec['out_y']).max())
@@ -120,14 +141,11 @@ def test_fused_spot_pass(golden, arith):
     for name, g in zip(('z', 'c', 't', 'mu'), got):
         ref = golden['grad_in_' + name]
         assert g.shape == ref.shape
-        if name == 'z':
-            # d rms / d z is a single, heavily cancelled number (~1e-3 of d rms / d t, also an
-            # axial shift): the reference's own fp32 value is only good to ~1e-3 of itself, so
-            # it is held to the tolerance of the axial-shift group {z, t}
-            scale = max(abs(float(ref.ravel()[0])), float(np.abs(golden['grad_in_t']).max()))
-            assert abs(float(g.cpu().numpy().ravel()[0]) - float(ref.ravel()[0])) <= GRAD_TOL * scale
-            continue
-        assert _rel(g.cpu().numpy(), ref) <= GRAD_TOL, (name, _rel(g.cpu().numpy(), ref))
+        # (d rms / d z is a single, heavily cancelled number, ~1e-3 of d rms / d t: where the
+        # reference's own fp32 value is farther than 1e-4 from its float64 run, the bar is "no farther
+        # from float64 than the reference")
+        _close_or_no_worse_than_reference(g.cpu().numpy(), ref, golden['f64_grad_in_' + name], GRAD_TOL,
+                                          f"{golden['name']} d rms/d {name}")
     # the forward-only (no grad) variant gives the same value
     plain = _inputs(golden, DEV)
     rms2, _ = ops.spot_rms(*_args(plain), allow, rt._arith_code(arith))
@@ -150,21 +168,27 @@ def test_raytracer_end_to_end(golden):
                           allow_backward_rays=bool(golden['allow_backward_rays']), default_device=DEV)
     out = tracer.trace_rays(specs, lens)
     if aimed:
-        # the aimed pupil goes through a division by a traced slope: compare values only
-        scale = np.abs(golden['out_y']).max()
+        # the aimed pupil goes through a division by a traced slope, which amplifies fp32 noise on
+        # either side: north_star tolerance, or no farther from the reference's float64 run than its fp32
         assert np.array_equal(out[4].cpu().numpy(), golden['out_ok'])
-        assert np.abs(out[1].detach().cpu().numpy() - golden['out_y']).max() <= 5e-5 * scale
+        for j, key in ((0, 'out_x'), (1, 'out_y')):
+            got = out[j].detach().cpu().numpy().astype(np.float64)
+            scale = max(np.abs(golden['out_x']).max(), np.abs(golden['out_y']).max())
+            vs32 = np.abs(got - golden[key]).max() / scale
+            ours = np.abs(got - golden['f64_' + key]).max() / scale
+            theirs = np.abs(golden[key] - golden['f64_' + key]).max() / scale
+            print(f"{golden['name']} {key}: ours-vs-fp32 {vs32:.2e} ours-vs-fp64 {ours:.2e} reference-fp32-vs-fp64 {theirs:.2e}")
+            assert vs32 <= POINT_TOL or ours <= theirs, (key, vs32, ours, theirs)
     else:
         _check_outputs([o.detach() for o in out], golden)
     rms = rt.compute_rms2d(out[0], out[1], out[4])
-    assert abs(rms.item() - float(golden['rms'])) <= (5e-5 if aimed else RMS_TOL) * float(golden['rms'])
+    _close_or_no_worse_than_reference(rms.item(), golden['rms'], golden['f64_rms'], RMS_TOL, f"{golden['name']} rms")
     grads = torch.autograd.grad(rms, [lens.c, lens.t, lens.nd, lens.v])
-    tol = 5e-4 if aimed else GRAD_TOL
-    for name, g in zip(('c', 't', 'nd', 'v'), grads):
+    for name, g in zip(('c', 't', 'nd'), grads):
         # (the reference's nd / v gradients are 0 * NaN at air slots; ours are 0 there)
-        ref = np.nan_to_num(golden['grad_' + name])
-        g = np.nan_to_num(g.cpu().numpy())
-        assert _rel(g, ref) <= tol, (name, _rel(g, ref))
+        _close_or_no_worse_than_reference(g.cpu().numpy(), golden['grad_' + name], golden['f64_grad_' + name],
+                                          GRAD_TOL, f"{golden['name']} d rms/d {name}")
+    assert _rel(np.nan_to_num(grads[3].cpu().numpy()), np.nan_to_num(golden['grad_v'])) <= (5e-4 if aimed else GRAD_TOL)
     # fused pass through the same front end
     lens2 = lm.Lens(structure, *[torch.from_numpy(golden[k]).to(DEV).requires_grad_(True)
                                  for k in ('lens_c', 'lens_t', 'lens_nd', 'lens_v')])
@@ -356,8 +380,12 @@ def test_thirty_surface_lens_forward_sweep_and_backward():
     ref_leaves = [l_.detach().clone().requires_grad_(True) for l_ in leaves]
     ref_out = oracle.trace(*tracer._ray_set(specs, lm.Lens(lens.structure, *ref_leaves)))
     ref_g = torch.autograd.grad(oracle.spot_rms_all_lenses(ref_out[1], ref_out[4])[0], ref_leaves[:3])
-    for name, a_, b_ in zip(('c', 't', 'nd'), g, ref_g):
-        assert _rel(a_.cpu().numpy(), b_.cpu().numpy()) <= 2e-4, (name, _rel(a_.cpu().numpy(), b_.cpu().numpy()))
+    # 30 surfaces accumulate fp32 noise on either side: north_star tolerance against the oracle's fp32
+    # gradients, or no farther from the oracle run in float64 than its fp32 run is
+    g64 = oracle_lens_gradients(tracer, specs, lens, torch.float64)[1]
+    for name, a_, b_, c_ in zip(('c', 't', 'nd'), g, ref_g, g64):
+        _close_or_no_worse_than_reference(a_.cpu().numpy(), b_.cpu().numpy(), c_.cpu().numpy(), GRAD_TOL,
+                                          f'wide_zoom_30 d rms/d {name}')
 
 
 def test_no_grad_sweep_with_grad_requiring_lens():

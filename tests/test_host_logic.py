@@ -129,3 +129,32 @@ def test_stack_keys_and_exchange_module_import_without_a_gpu():
     with pytest.raises(Exception):       # CPU tensors never reach a kernel
         ops.penalty_sum(*[torch.zeros(1, 1, 1, 1)] * 5, *[torch.zeros(1, 1, 1, 1, 2)] * 3,
                         torch.ones(1, 1, 1, 1, 2, dtype=torch.bool), 2)
+
+
+def test_lens_tables_follow_the_structure_not_its_id():
+    """Regression: the staged pass' device tables were cached under
+    id(structure); CPython reuses ids, so a loop over freshly built structures of one shape got
+    stale masks / stop indices.  They now live on the Structure, stamped with its content."""
+    import gc
+    from torchoptics_b200 import RayTracer
+    from torchoptics_b200.lens_modeling import Lens, Structure
+    tracer = RayTracer(mode='circular', n_rays=(4, 4), default_device='cpu')
+    seqs = (np.array(['GAGAAGA']), np.array(['GAAGAGA']))
+    stops = (np.array([4]), np.array([2]))
+    for i in range(50):
+        structure = Structure(stops[i % 2], sequence=seqs[i % 2], default_device='cpu')
+        z = torch.zeros((1, 7))
+        lens = Lens(structure, z, z, z + 1.5, z + 50.0)
+        tab = tracer._tables(lens)
+        assert np.array_equal(tab.mask_g.numpy().astype(bool), structure.mask_G), i
+        assert int(tab.stop_idx[0]) == int(structure.stop_idx[0]), i
+        assert tracer._tables(lens) is tab                       # cached while the structure lives
+        del structure, lens, tab
+        gc.collect()
+    # an in-place edit of the structure invalidates both caches
+    structure = Structure(np.array([4]), sequence=seqs[0], default_device='cpu')
+    lens = Lens(structure, z, z, z + 1.5, z + 50.0)
+    first, front = tracer._tables(lens), structure.up_to_stop()
+    structure.stop_idx[0] = 2
+    assert int(tracer._tables(lens).stop_idx[0]) == 2 and tracer._tables(lens) is not first
+    assert structure.up_to_stop() is not front and structure.up_to_stop().mask.shape[1] == 2

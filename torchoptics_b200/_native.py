@@ -12,6 +12,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('TL_LIB_OVERRIDE') or os.path.join(_PKG, 'libtorchoptics_b200.so')   # override: kernel experiments only
 
+ABI_VERSION = 10
 ARITH_GUARDED = 0
 ARITH_EXACT = 1
 MAX_SURFACES_FWD = 256
@@ -76,6 +77,7 @@ EXPORTS = {
     'tl_abi_version': (ctypes.c_int, []),
     'tl_last_error': (ctypes.c_char_p, []),
     'tl_launch_count': (ctypes.c_int64, []),
+    'tl_abi_describe': (ctypes.c_char_p, [ctypes.c_int32]),
     'tl_trace_fwd': (ctypes.c_int, [ctypes.POINTER(TlProblem), ctypes.POINTER(TlTraceOut), ctypes.c_void_p]),
     'tl_trace_bwd_workspace': (ctypes.c_size_t, [ctypes.POINTER(TlProblem)]),
     'tl_trace_bwd': (ctypes.c_int, [ctypes.POINTER(TlProblem), ctypes.POINTER(TlSeeds),
@@ -115,7 +117,28 @@ EXPORTS = {
     'tl_peer_destroy': (ctypes.c_int, [ctypes.c_void_p]),
 }
 
+# struct ids of tl_abi_layout
+LAYOUT_STRUCTS = (TlStrided, TlProblem, TlTraceOut, TlSeeds, TlGrads, TlSpotOut, TlPenaltyOut, TlLens)
+
 _lib = None
+
+
+def describe(struct):
+    """'Name:size;field@offset;...' of a ctypes struct, the format of tl_abi_describe."""
+    return f'{struct.__name__}:{ctypes.sizeof(struct)}' + ''.join(
+        f';{name}@{getattr(struct, name).offset}' for name, _ in struct._fields_)
+
+
+def check_layout(lib, structs=None):
+    """Every ctypes struct of this binding -- size, field NAMES in order and offsets -- against what
+    the LOADED library reports (tl_abi_describe): a reordered, renamed, resized or re-typed field
+    raises instead of corrupting a call."""
+    for which, struct in enumerate(structs or LAYOUT_STRUCTS):
+        got = lib.tl_abi_describe(which)
+        got = got.decode() if got else None
+        if got != describe(struct):
+            raise NativeLibraryError(f'binding layout {describe(struct)!r} != library layout {got!r}; '
+                                     'rebuild libtorchoptics_b200.so or fix _native.py')
 
 
 def load():
@@ -132,8 +155,9 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.tl_abi_version() != 9:
+    if lib.tl_abi_version() != ABI_VERSION:
         raise NativeLibraryError('libtorchoptics_b200.so: ABI version mismatch, rebuild it')
+    check_layout(lib)
     _lib = lib
     return lib
 

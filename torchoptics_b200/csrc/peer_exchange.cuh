@@ -76,11 +76,15 @@ k_peer_allreduce(Peers peers, int rank, int world, long long capacity, const dou
   __syncthreads();
   if (threadIdx.x == 0) store_release_sys(&peers.win[q]->flags[p][rank], want);
 
-  // wait for every source to have pushed into this rank's window
+  // wait for every source to have pushed into this rank's window.  A wait that times out (a late
+  // or dead peer) makes the failure LOUD and STICKY: status = 1, this and every later step write
+  // NaN instead of a sum of stale slots (the NaN reaches the host with the loss, also through a
+  // replayed CUDA graph), and later steps do not wait again (epochs may be out of step for good).
   __shared__ int timed_out;
-  if (threadIdx.x == 0) timed_out = 0;
+  if (threadIdx.x == 0) timed_out = *reinterpret_cast<volatile unsigned int *>(&mine->status) != 0u;
   __syncthreads();
-  if (threadIdx.x < world) {
+  const bool poisoned_before = timed_out != 0;
+  if (!poisoned_before && threadIdx.x < world) {
     const unsigned int *flag = &mine->flags[p][threadIdx.x];
     const unsigned long long t0 = now_ns();
     while ((int)(load_acquire_sys(flag) - want) < 0) {
@@ -88,17 +92,19 @@ k_peer_allreduce(Peers peers, int rank, int world, long long capacity, const dou
     }
   }
   __syncthreads();
-  if (timed_out && threadIdx.x == 0) atomicExch(&mine->status, 1u);
+  const bool poisoned = timed_out != 0;
+  if (poisoned && !poisoned_before && threadIdx.x == 0) atomicExch(&mine->status, 1u);
 
   // sum chunk q over the ranks, in rank order
   {
     const long long per = (n + world - 1) / world;
     const long long lo = per * q, hi = (lo + per < n) ? lo + per : n;
     const double *src = slots_of(mine) + (long long)p * world * capacity;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
     for (long long i = lo + threadIdx.x; i < hi; i += kThreads) {
       double acc = __ldcv(src + i);
       for (int s = 1; s < world; ++s) acc += __ldcv(src + s * capacity + i);
-      out[i] = acc;
+      out[i] = poisoned ? nan : acc;
     }
   }
 

@@ -221,6 +221,15 @@ struct Ray {
   T x, y, z, cx, cy, cz;
 };
 
+// What the reversible adjoint sweep (sweep_sphere_rev below) needs from the forward pass, per
+// ray-surface event.
+template <class T>
+struct Parked {
+  T dist;   // marching distance from the previous vertex-shifted point to this surface (rtl:543)
+  T ci;     // cos(theta)  at this surface (rtl:541)
+  T co;     // cos(theta') at this surface (rtl:556)
+};
+
 // One surface as a ray of a given wavelength sees it.
 struct Surface {
   float c;    // curvature
@@ -263,7 +272,7 @@ TL_HD float exact_angle_norm(float cos2) {
 // test (k > 0 and mask[k-1], rtl:626-628).  PEN: also return the aggregate=True terms.
 template <bool PEN>
 TL_HD void exact_surface_t(Ray<float> &r, const Surface s, bool count_travel, bool allow_backward,
-                           bool &ok, bool &backward, Penalty *pen) {
+                           bool &ok, bool &backward, Penalty *pen, Parked<float> *pk = nullptr) {
   // rtl:531-535
   const float e = -xadd(xadd(xmul(r.x, r.cx), xmul(r.y, r.cy)), xmul(r.z, r.cz));
   const float mz = xadd(r.z, xmul(e, r.cz));
@@ -299,6 +308,11 @@ TL_HD void exact_surface_t(Ray<float> &r, const Surface s, bool count_travel, bo
   ok = ok && !lost;                                                       // rtl:635
   exact_park(ok, r);
   r.z = xsub(r.z, s.t);                                                   // rtl:639
+  if (pk) {
+    pk->dist = dist;
+    pk->ci = cos_in;
+    pk->co = cos_out;
+  }
   if (PEN) {                                                              // rtl:641-657
     pen->z_relu = r.z <= 0.0f ? 0.0f : r.z;
     pen->theta = ok ? exact_angle_norm(cos2_in) : 1.0f;
@@ -508,6 +522,153 @@ TL_HD SurfaceGrad<T> sweep_sphere(Sweep<T> &s, T hx, T hy, T dx, T dy, T c, T t,
   s.hit = Vec3<T>{hx, hy, hz};
   s.dir = d;
   return g;
+}
+
+// ---------------------------------------------------------------------------
+// REVERSIBLE formulation (round 2; what the fused spot kernel k_spot_rev runs).
+//
+// A traced ray can be walked backwards: refraction and transfer are invertible maps.  The adjoint
+// sweep therefore does not need the hit points and directions of the forward pass -- it rebuilds
+// them surface by surface on its way back from the image plane,
+//     h_k = h_{k+1} + t_k z^ - D_{k+1} d'_k             (undo the transfer)
+//     d_k = (d'_k - g_k n_k) / mu_k,  g_k = a'_k - mu_k a_k   (undo the refraction)
+// from the three scalars per ray-surface event that are NOT cheap to recompute: the marching
+// distance D_k and the two cosines a_k = cos(theta), a'_k = cos(theta') (each is behind a square
+// root).  Against parking (hx, hy, dx, dy) and rebuilding h_z, d_z, n.d, n.d' this is 12 B instead
+// of 16 B per event of parked state, 2 instead of 5 MUFU and ~61 instead of ~72 FMA-pipe
+// operations per event in the sweep -- and n_z = 1 - c h_z comes from the true h_z, so a hit
+// beyond the equator of the sphere needs no branch bit.
+//
+// The forward differs from fast_surface in two places (fast policy only; the exact policy is the
+// reference's statement order, untouched): the marching distance is the near root of
+// c s^2 - 2 beta s + gamma = 0 (beta = cz - c r.d, gamma = c |r|^2 - 2 z; its discriminant IS
+// cos^2(theta), rtl:535), one operation shorter than rtl:531-543; and, with TL_REV_NO_RENORM
+// (experiment, off by default), cz' = mu cz + g n_z instead of sqrt(1 - cx'^2 - cy'^2) (rtl:566),
+// which saves a MUFU: the two agree to rounding whenever the refracted ray still runs forward, and
+// a fast-path ray must then clear cz' > sqrt(1e-6 + band) to stay on the fast path.
+// ---------------------------------------------------------------------------
+template <class T>
+TL_HD void fast_surface_rev(Ray<T> &r, T c, T mu, T mu2, T om2, T t, T &min_cos2, T &min_cz,
+                            T &travel, Parked<T> &pk) {
+  const T rd = ffma(r.z, r.cz, ffma(r.y, r.cy, r.x * r.cx));            // r.d
+  const T beta = ffma(-c, rd, r.cz);
+  const T r2 = ffma(r.z, r.z, ffma(r.y, r.y, r.x * r.x));
+  const T gamma = ffma(c, r2, T(-2) * r.z);
+  const T q = ffma(-c, gamma, beta * beta);                              // cos^2 in
+  const T ci = q * frsqrt(q);
+  const T dist = gamma * frcp(beta + ci);
+  travel = dist * r.cz;
+  r.x = ffma(dist, r.cx, r.x);
+  r.y = ffma(dist, r.cy, r.y);
+  r.z = r.z + travel;
+  const T qo = ffma(mu2, q, om2);                                        // cos^2 out, om2 = 1 - mu^2
+  const T co = qo * frsqrt(qo);
+  const T g = ffma(-mu, ci, co);
+  const T gc = g * c;
+  r.cx = ffma(-gc, r.x, mu * r.cx);
+  r.cy = ffma(-gc, r.y, mu * r.cy);
+#ifdef TL_REV_NO_RENORM
+  // cz' = mu cz + g n_z: no MUFU, but |d| drifts by an ULP per surface (measured: the RMS of an 8x8
+  // pupil moves by up to 1.2e-5 of itself against 5e-6 for the renormalised form)
+  r.cz = ffma(-gc, r.z, ffma(mu, r.cz, g));
+  min_cos2 = fmin2(min_cos2, fmin2(q, qo));
+  min_cz = fmin2(min_cz, r.cz);
+#else
+  const T w = ffma(-r.cy, r.cy, ffma(-r.cx, r.cx, T(1)));                // rtl:566, renormalised
+  r.cz = w * frsqrt(w);
+  min_cos2 = fmin2(min_cos2, fmin2(q, fmin2(qo, w)));
+#endif
+  r.z = r.z - t;
+  pk.dist = dist;
+  pk.ci = ci;
+  pk.co = co;
+}
+
+// cz' must clear this to stay on the fast path: sqrt(kGuard + kBandCos2), rounded up
+constexpr float kBandCz = 0.01006f;
+
+template <class T>
+struct SweepRev {
+  Vec3<T> hit;   // hit point on surface k+1 (its vertex coordinates; image plane: z = 0)
+  Vec3<T> dir;   // direction of the ray between surfaces k and k+1
+  Vec3<T> gr;    // adjoint of a point of that ray
+  Vec3<T> gd;    // adjoint of its direction, still missing the (distance to `hit`) * gr term
+  T dnext;       // distance from the hit on surface k to `hit`
+};
+
+template <class T>
+TL_HD SweepRev<T> sweep_begin_rev(const Ray<T> &pre, T x_img, T y_img, T gx, T gy, T gcx, T gcy) {
+  SweepRev<T> s;
+  const T rcz = frcp(pre.cz);
+  s.hit = Vec3<T>{x_img, y_img, T(0)};
+  s.dir = Vec3<T>{pre.cx, pre.cy, pre.cz};
+  s.gr = Vec3<T>{gx, gy, -ffma(gy, pre.cy, gx * pre.cx) * rcz};         // plane: n = z^
+  s.gd = Vec3<T>{gcx, gcy, T(0)};
+  s.dnext = -pre.z * rcz;
+  return s;
+}
+
+// One surface of the backward walk.  a = cos(theta), ap = cos(theta'), rap = 1 / ap, rmu = 1 / mu;
+// `dist` = the parked marching distance of THIS surface (handed on to the next step).
+template <class T>
+TL_HD SurfaceGrad<T> sweep_sphere_rev_core(SweepRev<T> &s, T dist, T a, T ap, T rap, T c, T t, T mu, T rmu) {
+  SurfaceGrad<T> g;
+  const T dn = s.dnext;
+  // undo the transfer: the hit point on this surface
+  const Vec3<T> h{ffma(-dn, s.dir.x, s.hit.x), ffma(-dn, s.dir.y, s.hit.y), ffma(-dn, s.dir.z, s.hit.z + t)};
+  const Vec3<T> gdo{ffma(dn, s.gr.x, s.gd.x), ffma(dn, s.gr.y, s.gd.y), ffma(dn, s.gr.z, s.gd.z)};
+  g.t = -s.gr.z;
+  const Vec3<T> n{-c * h.x, -c * h.y, ffma(-c, h.z, T(1))};
+  const T gsn = ffma(-mu, a, ap);
+  // undo the refraction: the incoming direction d = (d' - g n) / mu
+  const T grm = gsn * rmu;
+  const Vec3<T> d{ffma(-grm, n.x, rmu * s.dir.x), ffma(-grm, n.y, rmu * s.dir.y), ffma(-grm, n.z, rmu * s.dir.z)};
+  const T gdd = dot3(gdo, d);
+  const T u = dot3(gdo, n) * rap;
+  const T ga = -(mu * gsn) * u;
+  g.mu = ffma(-u, ffma(a, ap, mu * ffma(-a, a, T(1))), gdd);
+  const Vec3<T> gn{ffma(ga, d.x, gsn * gdo.x), ffma(ga, d.y, gsn * gdo.y), ffma(ga, d.z, gsn * gdo.z)};
+  const Vec3<T> gdi{ffma(ga, n.x, mu * gdo.x), ffma(ga, n.y, mu * gdo.y), ffma(ga, n.z, mu * gdo.z)};
+  const Vec3<T> gh{ffma(-c, gn.x, s.gr.x), ffma(-c, gn.y, s.gr.y), ffma(-c, gn.z, s.gr.z)};
+  const T gc_n = dot3(gn, h);
+  const T sd = -dot3(gh, d) * frcp(a);
+  s.gr = Vec3<T>{ffma(sd, n.x, gh.x), ffma(sd, n.y, gh.y), ffma(sd, n.z, gh.z)};
+  g.c = -ffma(sd * T(0.5), dot3(h, h), gc_n);
+  s.gd = gdi;
+  s.hit = h;
+  s.dir = d;
+  s.dnext = dist;
+  return g;
+}
+
+// ... from all three parked values
+template <class T>
+TL_HD SurfaceGrad<T> sweep_sphere_rev(SweepRev<T> &s, const Parked<T> &pk, T c, T t, T mu, T rmu) {
+  return sweep_sphere_rev_core(s, pk.dist, pk.ci, pk.co, frcp(pk.co), c, t, mu, rmu);
+}
+
+// ... from (dist, cos theta) alone: cos theta' = sqrt(1 - mu^2 (1 - cos^2 theta)) (rtl:553-556) is
+// rebuilt -- three more FMA-pipe operations per event, but its rsqrt IS the 1 / cos theta' the sweep
+// needs anyway (no extra MUFU) and the parked state shrinks to 8 bytes per event.
+template <class T>
+TL_HD SurfaceGrad<T> sweep_sphere_rev2(SweepRev<T> &s, T dist, T ci, T c, T t, T mu, T mu2, T om2, T rmu) {
+  const T qo = ffma(mu2, ci * ci, om2);
+  const T rap = frsqrt(qo);
+  return sweep_sphere_rev_core(s, dist, ci, qo * rap, rap, c, t, mu, rmu);
+}
+
+// Entrance: the ray starts at (x, y, z_in) with direction (cx, cy, sqrt(1 - cx^2 - cy^2)); the
+// distance to the first hit is the parked one.
+template <class T>
+TL_HD void sweep_end_rev(const SweepRev<T> &s, T &gx, T &gy, T &gz, T &gcx, T &gcy) {
+  const T rdz = frcp(s.dir.z);
+  const T dist = s.dnext;
+  const T gdz = ffma(dist, s.gr.z, s.gd.z) * rdz;
+  gx = s.gr.x;
+  gy = s.gr.y;
+  gz = s.gr.z;
+  gcx = ffma(-gdz, s.dir.x, ffma(dist, s.gr.x, s.gd.x));     // cz is a function of (cx, cy)
+  gcy = ffma(-gdz, s.dir.y, ffma(dist, s.gr.y, s.gd.y));
 }
 
 // Did the ray hit the sphere beyond its equator?  `z_shifted` = h_z - t (the state behind the

@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <stddef.h>
 #include <string.h>
 #include <atomic>
 
@@ -1567,6 +1568,8 @@ int reduce_rows(const AdjPlan &pl, const double *partial, double *rows_out, int 
   return TL_OK;
 }
 
+#include "spot_rev.cuh"
+
 // K3c: the backward kernels (MODE_BWD of k_trace_adj: plain, with seeded stacks, and the fused
 // penalty pass PEN_SUM) with a warp per row, for the same many-short-rows workload as k_spot_rows.
 // Row layout [3S+1 (+1)]: c, t, mu per surface, z (, penalty) -- what k_bwd_finalize /
@@ -1886,6 +1889,28 @@ int tl_abi_version(void) { return TL_ABI_VERSION; }
 const char *tl_last_error(void) { return g_error; }
 int64_t tl_launch_count(void) { return (int64_t)g_launches.load(); }
 
+const char *tl_abi_describe(int32_t which) {
+  static thread_local char text[1024];
+  int n = 0;
+  text[0] = 0;
+#define TL_SIZE(T) n += snprintf(text + n, sizeof(text) - n, #T ":%zu", sizeof(T))
+#define TL_OFF(T, f) n += snprintf(text + n, sizeof(text) - n, ";" #f "@%zu", offsetof(T, f))
+  switch (which) {
+    case 0: TL_SIZE(TlStrided); TL_OFF(TlStrided, ptr); TL_OFF(TlStrided, stride); break;
+    case 1: TL_SIZE(TlProblem); TL_OFF(TlProblem, x); TL_OFF(TlProblem, y); TL_OFF(TlProblem, z); TL_OFF(TlProblem, cx); TL_OFF(TlProblem, cy); TL_OFF(TlProblem, c); TL_OFF(TlProblem, t); TL_OFF(TlProblem, mu); TL_OFF(TlProblem, live); TL_OFF(TlProblem, B); TL_OFF(TlProblem, F); TL_OFF(TlProblem, P); TL_OFF(TlProblem, W); TL_OFF(TlProblem, S); TL_OFF(TlProblem, allow_backward_rays); TL_OFF(TlProblem, arith); TL_OFF(TlProblem, p_begin); TL_OFF(TlProblem, p_end); TL_OFF(TlProblem, xy_scale); TL_OFF(TlProblem, k); TL_OFF(TlProblem, a); TL_OFF(TlProblem, sd); TL_OFF(TlProblem, aim); break;
+    case 2: TL_SIZE(TlTraceOut); TL_OFF(TlTraceOut, x); TL_OFF(TlTraceOut, y); TL_OFF(TlTraceOut, cx); TL_OFF(TlTraceOut, cy); TL_OFF(TlTraceOut, ok); TL_OFF(TlTraceOut, backward); TL_OFF(TlTraceOut, opl); TL_OFF(TlTraceOut, z_relu); TL_OFF(TlTraceOut, theta); TL_OFF(TlTraceOut, theta_prime); break;
+    case 3: TL_SIZE(TlSeeds); TL_OFF(TlSeeds, gx); TL_OFF(TlSeeds, gy); TL_OFF(TlSeeds, gcx); TL_OFF(TlSeeds, gcy); TL_OFF(TlSeeds, gz_relu); TL_OFF(TlSeeds, gtheta); TL_OFF(TlSeeds, gtheta_prime); break;
+    case 4: TL_SIZE(TlGrads); TL_OFF(TlGrads, gc); TL_OFF(TlGrads, gt); TL_OFF(TlGrads, gmu); TL_OFF(TlGrads, gz_sum); TL_OFF(TlGrads, gx); TL_OFF(TlGrads, gy); TL_OFF(TlGrads, gz); TL_OFF(TlGrads, gcx); TL_OFF(TlGrads, gcy); TL_OFF(TlGrads, gk); TL_OFF(TlGrads, ga); break;
+    case 5: TL_SIZE(TlSpotOut); TL_OFF(TlSpotOut, rms); TL_OFF(TlSpotOut, rms_field); TL_OFF(TlSpotOut, gc); TL_OFF(TlSpotOut, gt); TL_OFF(TlSpotOut, gmu); TL_OFF(TlSpotOut, gz); TL_OFF(TlSpotOut, gk); TL_OFF(TlSpotOut, ga); break;
+    case 6: TL_SIZE(TlPenaltyOut); TL_OFF(TlPenaltyOut, penalty); TL_OFF(TlPenaltyOut, gc); TL_OFF(TlPenaltyOut, gt); TL_OFF(TlPenaltyOut, gmu); TL_OFF(TlPenaltyOut, gz); break;
+    case 7: TL_SIZE(TlLens); TL_OFF(TlLens, c); TL_OFF(TlLens, t); TL_OFF(TlLens, nd); TL_OFF(TlLens, v); TL_OFF(TlLens, mask); TL_OFF(TlLens, mask_g); TL_OFF(TlLens, stop_idx); TL_OFF(TlLens, hfov); TL_OFF(TlLens, epd); TL_OFF(TlLens, rel_fields); TL_OFF(TlLens, wavelengths); TL_OFF(TlLens, B); TL_OFF(TlLens, L); TL_OFF(TlLens, F); TL_OFF(TlLens, W); break;
+    default: return nullptr;
+  }
+#undef TL_SIZE
+#undef TL_OFF
+  return text;
+}
+
 int tl_trace_fwd(const TlProblem *pb, const TlTraceOut *out, void *stream_) {
   int rc = validate(pb, TL_MAX_SURFACES_FWD);
   if (rc) return rc;
@@ -2101,7 +2126,13 @@ size_t tl_spot_workspace(const TlProblem *pb, int32_t want_grad) {
   }
   AdjPlan pl;
   if (plan_adj(*pb, want_grad ? MODE_SPOT_GRAD : MODE_SPOT_EVAL, pl)) return 0;
-  return pl.partial_bytes;
+  size_t bytes = pl.partial_bytes;
+  if (want_grad && use_rev_kernel(*pb)) {
+    RevPlan rp;
+    if (plan_rev(*pb, rp)) return 0;
+    if (rp.partial_bytes > bytes) bytes = rp.partial_bytes;
+  }
+  return bytes;
 }
 
 int tl_spot_accumulate(const TlProblem *pb, int32_t want_grad, double *moments, float *ref_y,
@@ -2154,6 +2185,14 @@ int tl_spot_accumulate(const TlProblem *pb, int32_t want_grad, double *moments, 
   g_launches++;
   if (use_rows_kernel(*pb, want_grad))      // many short rows: a warp per row, sums straight into `moments`
     return launch_spot_rows(*pb, want_grad, ref_y, moments, stream);
+  if (want_grad && use_rev_kernel(*pb)) {   // the reversible fused pass (spot_rev.cuh)
+    RevPlan rp;
+    rc = plan_rev(*pb, rp);
+    if (rc) return rc;
+    if (workspace_bytes < rp.partial_bytes)
+      return fail(TL_ERR_WORKSPACE, "workspace too small for tl_spot_accumulate%s");
+    return launch_spot_rev(*pb, rp, ref_y, (double *)workspace, moments, stream);
+  }
   AdjArgs args;
   memset(&args, 0, sizeof(args));
   args.partial = (double *)workspace;

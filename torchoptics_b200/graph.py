@@ -115,4 +115,16 @@ class GraphedSpotStep:
                 self.host_in[k].copy_(val)
         self.graph.replay()
         torch.cuda.current_stream(self.device).synchronize()
+        self.check_exchange()
         return self.host_rms, self.host_out
+
+    def check_exchange(self):
+        """A peer that did not show up within the exchange kernel's spin limit poisons the sums with
+        NaN (csrc/peer_exchange.cuh); turn that into an exception instead of a silently wrong step."""
+        from .peer import PeerExchange
+        if isinstance(self.group, PeerExchange) and bool(torch.isnan(self.host_rms).any()):
+            status, epoch = self.group.status()
+            if status != 0:
+                from ._native import NativeLibraryError
+                raise NativeLibraryError(f'peer-memory exchange timed out on rank {self.group.rank} '
+                                         f'(epoch {epoch}): a peer is late or dead; results are poisoned')

@@ -122,15 +122,29 @@ class Structure:
 
     def up_to_stop(self):
         """Sub-structure in front of the aperture stop (lm:185-192)."""
+        # built once per value of stop_idx (a fresh host->device copy per call could not be
+        # graph-captured); an in-place edit of stop_idx rebuilds it, like the reference's per-call build
+        key = self.stop_idx.tobytes()
         cached = getattr(self, '_front', None)
-        if cached is None:       # built once: masks are immutable, and a fresh host->device
-            n_keep = int(self.stop_idx.max())          # copy per call could not be graph-captured
+        if cached is None or cached[0] != key:
+            n_keep = int(self.stop_idx.max())
             before_stop = np.arange(n_keep)[None, :] < self.stop_idx[:, None]
-            cached = Structure(self.stop_idx, self.mask[:, :n_keep] & before_stop,
-                               self.mask_G[:, :n_keep] & before_stop,
-                               default_device=self.default_device)
-            self._front = cached
-        return cached
+            front = Structure(self.stop_idx.copy(), self.mask[:, :n_keep] & before_stop,
+                              self.mask_G[:, :n_keep] & before_stop,
+                              default_device=self.default_device)
+            cached = self._front = (key, front)
+        return cached[1]
+
+    def device_tables(self, key, build):
+        """Per-structure cache of device-side constants (the staged kernels' masks / stop indices):
+        lives and dies with this object -- never keyed by ``id()``, which CPython reuses -- and is
+        rebuilt when the masks or stop indices were edited in place."""
+        stamp = (self.stop_idx.tobytes(), self.mask.tobytes(), self.mask_G.tobytes())
+        cache = self.__dict__.setdefault('_device_tables', {})
+        hit = cache.get(key)
+        if hit is None or hit[0] != stamp:
+            hit = cache[key] = (stamp, build())
+        return hit[1]
 
     def clone(self):
         return Structure(self.stop_idx.copy(), self.mask.copy(), self.mask_G.copy(),

@@ -406,6 +406,8 @@ class _SpotRms(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_rms, _grad_field):
         saved = ctx.saved_tensors
+        if len(saved) < 4:      # forward ran without gradients (nothing it differentiates required one)
+            return (None,) * 17
         gc, gt, gmu, gz = saved[:4]
         B, W, S, z_shape, c_shape, t_shape, mu_shape, k_shape, a_shape = ctx.meta
         need = ctx.needs_input_grad
@@ -683,6 +685,9 @@ class _LensSpotRms(torch.autograd.Function):
                 group, grad_on, aimed=False):
         if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
             raise ValueError('the fused lens pass does not differentiate w.r.t. hfov / epd')
+        if ctx.needs_input_grad[6] or ctx.needs_input_grad[7]:
+            raise ValueError('the fused lens pass does not differentiate w.r.t. the pupil coordinates x_rel / '
+                             'y_rel; use trace() + spot_rms_from_rays() for those gradients')
         want_grad = grad_on and any(ctx.needs_input_grad[:4])
         rms, rms_field, gc, gt, gnd, gv = _lens_spot_core(c, t, nd, v, hfov, epd, x_rel, y_rel, tables,
                                                           allow_backward_rays, arith, shard, group,
@@ -694,6 +699,8 @@ class _LensSpotRms(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_rms, _grad_field):
+        if len(ctx.saved_tensors) < 4:      # forward ran without gradients
+            return (None,) * 15
         gc, gt, gnd, gv = ctx.saved_tensors
         g = grad_rms.to(torch.float32).reshape(-1, 1)
         need = ctx.needs_input_grad

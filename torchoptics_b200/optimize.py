@@ -58,6 +58,11 @@ def optimize_spot(tracer, specs, lens, variables=('c', 't', 'k', 'a'), steps=100
         loss.backward()
         opt.step()
         history.append(float(loss.detach()))
+        if history[-1] != history[-1]:      # NaN: a poisoned peer exchange (a late or dead rank) must not pass silently
+            from .peer import PeerExchange
+            if isinstance(group, PeerExchange) and group.status()[0] != 0:
+                from ._native import NativeLibraryError
+                raise NativeLibraryError(f'peer-memory exchange timed out on rank {group.rank} at step {step}')
         if callback is not None:
             callback(step, history[-1])
     final = dict(fields)

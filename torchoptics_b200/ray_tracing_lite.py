@@ -449,11 +449,14 @@ class RayTracer:
         return rms.detach(), grads
 
     def _tables(self, lens):
-        key = ('tables', id(lens.structure))
-        if key not in self._cache:
-            self._cache[key] = ops.LensTables(lens.structure, self.rel_fields, self.wavelengths,
-                                              self.default_device)
-        return self._cache[key]
+        # cached ON the structure (content-stamped), not under id(structure) in the tracer: ids are
+        # reused once a structure is freed, and `tracer.spot_rms(specs[i], lens[i])` builds a fresh
+        # Structure per index
+        structure = lens.structure
+        key = (tuple(float(f) for f in self.rel_fields), tuple(float(w) for w in self.wavelengths),
+               str(self.default_device))
+        return structure.device_tables(key, lambda: ops.LensTables(structure, self.rel_fields, self.wavelengths,
+                                                                   self.default_device))
 
     # -- ray aiming (rtl:129-208) ---------------------------------------------
     def ray_aiming(self, specs, lens, use_vig):
