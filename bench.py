@@ -291,14 +291,19 @@ def main():
         torch.cuda.synchronize()
 
     note('warm-up')
-    for _ in range(args.warmup):
-        flush.zero_()
-        run_step()
-    barrier()
-    note('timed region')
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    with ClockSampler(local_rank) as clocks:
+    with ClockSampler(local_rank) as clocks:     # (sampled through the warm-up too: the timed region is milliseconds)
+        for _ in range(args.warmup):
+            flush.zero_()
+            run_step()
+        barrier()
+        # the host barrier leaves the ranks tens of microseconds apart, and the first exchange would bill
+        # that skew to the first timed steps: a few UNTIMED steps let the exchange itself align the ranks
+        for _ in range(3 if world > 1 else 0):
+            flush.zero_()
+            run_step()
+        note('timed region')
         for i in range(args.steps):
             flush.zero_()                        # evict L2 between timed iterations
             starts[i].record()
@@ -312,6 +317,7 @@ def main():
     total_ms = float(total_ms.item())
     ms_per_step = total_ms / args.steps
     value = events_total / (ms_per_step * 1e-3)
+    step_stats = {'min': min(step_ms), 'median': statistics.median(step_ms), 'max': max(step_ms), 'rank': rank}
 
     note('kernel-only timing')
     # ---- dominant kernel alone (tl_spot_accumulate), live CUDA events --------
@@ -398,7 +404,8 @@ def main():
     roofline = {'bound': 'fp32_fma', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
                 'frac': achieved / peak_tflops,
                 'traffic': NCU_DRAM_BYTES_PER_LAUNCH if world == 1 else None,
-                'kernel': 'k_trace_adj<12,SPOT_GRAD,f4> (+k_chief_rays, k_reduce_rows: ~2% of the time)', 'kernel_ms': kernel_ms,
+                'kernel': f'{ops.spot_kernel_name(*plain, shard=shard)} (+k_chief_rays, k_reduce_rows: ~2% of the time)',
+                'kernel_ms': kernel_ms,
                 'flops_per_event': FLOPS_FWD + FLOPS_BWD,
                 'peak_source': f'{sms} SMs x 128 lanes x 2 flop x {sm_max_mhz:.0f} MHz '
                                f'(sm_max_mhz of MEASURED_PEAKS.json); algorithmic HBM bytes ~0, '
@@ -516,8 +523,13 @@ def main():
                         'eager_api_ms_per_step': eager_secs / eager_steps * 1e3,
                         'drop_in_api_value': (events_total * eager_steps / drop_in_secs) if drop_in_secs else None,
                         'drop_in_api': 'trace_rays + compute_rms2d + backward (unfused, materialises [B,F,P,W])'},
+                'step_ms': step_stats,
                 'gpu_launches': launches_per_step * args.steps,
                 'roofline': roofline, 'forward': forward, 'penalty': penalty_row}
+        if value < 0.97 * e2e_value:      # device-timed slower than host-timed end to end: timed wait (rank skew)
+            line['warning'] = ('value < e2e.value: the device-timed steps include waiting for the slowest rank '
+                               '(see step_ms min / median / max)')
+            print(f"[bench] warning: {line['warning']}", file=sys.stderr)
         if world == 1 and not args.no_cpu_baseline:
             base = cpu_arm(3, 1)
             line['cpu_baseline'] = {k: base[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}

@@ -177,6 +177,9 @@ int tl_spot_accumulate(const TlProblem *pb, int32_t want_grad, double *moments, 
 int tl_spot_finalize(const double *moments, const float *ref_y, int32_t B, int32_t F, int32_t W,
                      int32_t S, int64_t P_total, int32_t want_grad, const TlSpotOut *out,
                      void *stream);
+/* Name of the kernel tl_spot_accumulate would launch for this problem (diagnostics / bench.py;
+ * thread-local storage, valid until the next call). */
+const char *tl_spot_kernel_name(const TlProblem *pb, int32_t want_grad);
 
 /* Fused penalty pass: value and gradient of the ray-angle / ray-path penalty that compute_loss_out
  * (optics_simulator_lite.py:430-450) builds from trace_skew(aggregate=True):

@@ -85,7 +85,10 @@ def main():
                     row[tag + '_rays'] = int(np.prod(args[0].shape[2:3])) * m.shape[1] * m.shape[2]
                 else:
                     scale = np.abs(ref[tag]).max(axis=(0, 1, 2), keepdims=True) + 1e-30
-                    row[tag + '_max_rel_diff_vs_round1'] = float((np.abs(m - ref[tag]) / scale).max())
+                    per_slot = (np.abs(m - ref[tag]) / scale).max(axis=(0, 1, 2))
+                    row[tag + '_max_rel_diff_vs_round1'] = float(per_slot.max())
+                    worst = int(per_slot.argmax())
+                    row[tag + '_worst_slot'] = [worst, float(scale.ravel()[worst]), float(np.sort(per_slot)[-4])]
                     row[tag + '_n_ok_equal'] = bool(np.array_equal(m[..., -1], ref[tag][..., -1]))
                     row[tag + '_finite'] = bool(np.isfinite(m).all())
             mean_ms, min_ms = timed(lambda: ops.spot_moments(*big), 30, flush)

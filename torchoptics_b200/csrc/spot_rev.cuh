@@ -55,8 +55,8 @@ __device__ __forceinline__ RevTable load_rev_table(float *base, const TlProblem 
     r.c = pb.c[(int64_t)b * S + k];
     r.t = pb.t[(int64_t)b * S + k];
     r.mu = m;
-    r.mu2 = m * m;
-    r.om2 = 1.0f - m * m;
+    r.mu2 = __fmul_rn(m, m);
+    r.om2 = __fsub_rn(1.0f, r.mu2);      // (individually rounded: the same number fast_surface forms per thread)
     r.rmu = 1.0f / m;
     r.live = pb.live[(int64_t)b * S + k] != 0;
     r.live_prev = k > 0 && pb.live[(int64_t)b * S + k - 1] != 0;
@@ -454,6 +454,7 @@ typedef void (*RevKernelPtr)(TlProblem, RevArgs);
 
 struct RevPlan {
   RevKernelPtr kernel = nullptr;
+  const char *name = "";
   int n_warps_cta = 8, n_blocks = 1, groups_per_row = 1, max_seg = 1, n_acc = 0;
   size_t smem = 0, partial_bytes = 0;
 };
@@ -472,12 +473,15 @@ int plan_rev(const TlProblem &pb, RevPlan &pl) {
   int rc = device_info(info);
   if (rc) return rc;
   const int S = pb.S;
+  // in the order measured on the B200 (config 2, ms per launch, tools/rev_variants.py): reg8 0.254,
+  // tmem12c2 0.258, tmem8 0.262, tmem12 0.263, tmem16 0.265 -- residency does NOT matter (8, 12 and 16
+  // warps per SM are within 4 %): the pass is bound by register-operand bandwidth (tools/microbench4.cu)
   const RevVariant variants[] = {
-      {"tmem16", k_spot_rev<16, 16, ACC_TMEM, 2>, 16, 2},
-      {"tmem12", k_spot_rev<16, 12, ACC_TMEM, 3>, 12, 3},
+      {"reg8", S <= 12 ? k_spot_rev<12, 8, ACC_REG, 3> : k_spot_rev<16, 8, ACC_REG, 3>, 8, 3},
       {"tmem12c2", k_spot_rev<16, 12, ACC_TMEM, 2>, 12, 2},
       {"tmem8", k_spot_rev<16, 8, ACC_TMEM, 3>, 8, 3},
-      {"reg8", S <= 12 ? k_spot_rev<12, 8, ACC_REG, 3> : k_spot_rev<16, 8, ACC_REG, 3>, 8, 3},
+      {"tmem12", k_spot_rev<16, 12, ACC_TMEM, 3>, 12, 3},
+      {"tmem16", k_spot_rev<16, 16, ACC_TMEM, 2>, 16, 2},
   };
   const char *env = getenv("TL_REV");
   const RevVariant *pick = nullptr;
@@ -492,6 +496,7 @@ int plan_rev(const TlProblem &pb, RevPlan &pl) {
   }
   if (!pick) return fail(TL_ERR_INVALID, "no variant of the reversible spot kernel fits (or unknown TL_REV)%s");
   pl.kernel = pick->kernel;
+  pl.name = pick->name;
   const int nw = pick->nw;
   pl.n_warps_cta = nw;
   pl.n_acc = n_acc_of(MODE_SPOT_GRAD, S);

@@ -349,31 +349,48 @@ TL_HD T fast_cz0(T cx, T cy) {
   return w * frsqrt(w);
 }
 
+// One surface, fast policy.  Round 2: the marching distance is the near root of
+//     c s^2 - 2 beta s + gamma = 0,   beta = cz - c (r.d),   gamma = c |r|^2 - 2 z,
+// whose discriminant beta^2 - c gamma IS cos^2(theta) of rtl:535 (expand both: identical
+// polynomials) -- one operation shorter than the e / mz / m2 / temp chain of rtl:531-543 and without
+// its cancellation between `e` and `temp / (cz + cos)` for a ray that starts close to the surface.
+// Every fast-path kernel shares this arithmetic, so a loss evaluated with and without gradients, fused
+// or split, sees bit-identical ray heights.  (`Parked`: what the reversible adjoint needs, below.)
 template <class T>
-TL_HD void fast_surface(Ray<T> &r, T c, T mu, T mu2, T t, T &min_cos2, T &travel, T &cos_in,
-                        T &cos_out) {
-  const T ne = ffma(r.z, r.cz, ffma(r.y, r.cy, r.x * r.cx));          // -e
-  const T mz = ffma(-ne, r.cz, r.z);
-  const T m2 = ffma(-ne, ne, ffma(r.z, r.z, ffma(r.y, r.y, r.x * r.x)));
-  const T tmp = ffma(c, m2, T(-2) * mz);
-  const T q = ffma(-c, tmp, r.cz * r.cz);                               // cos^2 in
+TL_HD void fast_surface_core(Ray<T> &r, T c, T mu, T mu2, T om2, T t, T &min_cos2, T &travel, Parked<T> &pk) {
+  const T rd = ffma(r.z, r.cz, ffma(r.y, r.cy, r.x * r.cx));            // r.d
+  const T beta = ffma(-c, rd, r.cz);
+  const T r2 = ffma(r.z, r.z, ffma(r.y, r.y, r.x * r.x));
+  const T gamma = ffma(c, r2, T(-2) * r.z);
+  const T q = ffma(-c, gamma, beta * beta);                              // cos^2 in
   const T ci = q * frsqrt(q);
-  const T dist = ffma(tmp, frcp(r.cz + ci), -ne);
+  const T dist = gamma * frcp(beta + ci);
   travel = dist * r.cz;
   r.x = ffma(dist, r.cx, r.x);
   r.y = ffma(dist, r.cy, r.y);
   r.z = r.z + travel;
-  const T qo = ffma(mu2, q, T(1) - mu2);                                // cos^2 out = 1 - mu^2 (1 - q)
+  const T qo = ffma(mu2, q, om2);                                        // cos^2 out, om2 = 1 - mu^2
   const T co = qo * frsqrt(qo);
-  const T gc = ffma(-mu, ci, co) * c;
+  const T g = ffma(-mu, ci, co);
+  const T gc = g * c;
   r.cx = ffma(-gc, r.x, mu * r.cx);
   r.cy = ffma(-gc, r.y, mu * r.cy);
-  const T w = ffma(-r.cy, r.cy, ffma(-r.cx, r.cx, T(1)));
+  const T w = ffma(-r.cy, r.cy, ffma(-r.cx, r.cx, T(1)));                // rtl:566, renormalised
   r.cz = w * frsqrt(w);
   min_cos2 = fmin2(min_cos2, fmin2(q, fmin2(qo, w)));
   r.z = r.z - t;
-  cos_in = ci;
-  cos_out = co;
+  pk.dist = dist;
+  pk.ci = ci;
+  pk.co = co;
+}
+
+template <class T>
+TL_HD void fast_surface(Ray<T> &r, T c, T mu, T mu2, T t, T &min_cos2, T &travel, T &cos_in,
+                        T &cos_out) {
+  Parked<T> pk;
+  fast_surface_core(r, c, mu, mu2, T(1) - mu2, t, min_cos2, travel, pk);
+  cos_in = pk.ci;
+  cos_out = pk.co;
 }
 
 template <class T>
@@ -539,49 +556,16 @@ TL_HD SurfaceGrad<T> sweep_sphere(Sweep<T> &s, T hx, T hy, T dx, T dy, T c, T t,
 // operations per event in the sweep -- and n_z = 1 - c h_z comes from the true h_z, so a hit
 // beyond the equator of the sphere needs no branch bit.
 //
-// The forward differs from fast_surface in two places (fast policy only; the exact policy is the
-// reference's statement order, untouched): the marching distance is the near root of
-// c s^2 - 2 beta s + gamma = 0 (beta = cz - c r.d, gamma = c |r|^2 - 2 z; its discriminant IS
-// cos^2(theta), rtl:535), one operation shorter than rtl:531-543; and, with TL_REV_NO_RENORM
-// (experiment, off by default), cz' = mu cz + g n_z instead of sqrt(1 - cx'^2 - cy'^2) (rtl:566),
-// which saves a MUFU: the two agree to rounding whenever the refracted ray still runs forward, and
-// a fast-path ray must then clear cz' > sqrt(1e-6 + band) to stay on the fast path.
+// The forward is fast_surface_core (every fast-path kernel's), handing out what it computed anyway.
+// (Tried and dropped: cz' = mu cz + g n_z instead of the renormalising sqrt of rtl:566 saves a MUFU,
+// but |d| then drifts by an ULP per surface and the RMS of an 8x8 pupil moved by up to 1.2e-5 of
+// itself against 5e-6 for the renormalised form -- outside the 1e-5 budget.)
 // ---------------------------------------------------------------------------
 template <class T>
 TL_HD void fast_surface_rev(Ray<T> &r, T c, T mu, T mu2, T om2, T t, T &min_cos2, T &min_cz,
                             T &travel, Parked<T> &pk) {
-  const T rd = ffma(r.z, r.cz, ffma(r.y, r.cy, r.x * r.cx));            // r.d
-  const T beta = ffma(-c, rd, r.cz);
-  const T r2 = ffma(r.z, r.z, ffma(r.y, r.y, r.x * r.x));
-  const T gamma = ffma(c, r2, T(-2) * r.z);
-  const T q = ffma(-c, gamma, beta * beta);                              // cos^2 in
-  const T ci = q * frsqrt(q);
-  const T dist = gamma * frcp(beta + ci);
-  travel = dist * r.cz;
-  r.x = ffma(dist, r.cx, r.x);
-  r.y = ffma(dist, r.cy, r.y);
-  r.z = r.z + travel;
-  const T qo = ffma(mu2, q, om2);                                        // cos^2 out, om2 = 1 - mu^2
-  const T co = qo * frsqrt(qo);
-  const T g = ffma(-mu, ci, co);
-  const T gc = g * c;
-  r.cx = ffma(-gc, r.x, mu * r.cx);
-  r.cy = ffma(-gc, r.y, mu * r.cy);
-#ifdef TL_REV_NO_RENORM
-  // cz' = mu cz + g n_z: no MUFU, but |d| drifts by an ULP per surface (measured: the RMS of an 8x8
-  // pupil moves by up to 1.2e-5 of itself against 5e-6 for the renormalised form)
-  r.cz = ffma(-gc, r.z, ffma(mu, r.cz, g));
-  min_cos2 = fmin2(min_cos2, fmin2(q, qo));
-  min_cz = fmin2(min_cz, r.cz);
-#else
-  const T w = ffma(-r.cy, r.cy, ffma(-r.cx, r.cx, T(1)));                // rtl:566, renormalised
-  r.cz = w * frsqrt(w);
-  min_cos2 = fmin2(min_cos2, fmin2(q, fmin2(qo, w)));
-#endif
-  r.z = r.z - t;
-  pk.dist = dist;
-  pk.ci = ci;
-  pk.co = co;
+  (void)min_cz;
+  fast_surface_core(r, c, mu, mu2, om2, t, min_cos2, travel, pk);
 }
 
 // cz' must clear this to stay on the fast path: sqrt(kGuard + kBandCos2), rounded up

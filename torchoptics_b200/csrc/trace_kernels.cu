@@ -431,17 +431,21 @@ k_trace_fwd_pw(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
   }
 }
 
-// Reference height of every (lens, field): the image height of the chief ray (pupil
-// centre) at wavelength 0, traced with the fast policy.  The spot sums are centred on
-// it; any value near the centroid does (it cancels exactly in k_spot_finalize), it only
-// has to be the same number on every CTA and every rank -- it depends on nothing but the
-// prescription and is computed by the same instruction sequence everywhere.
+// Reference height of every (lens, field): the image height of the FIRST ray of the bundle (pupil
+// point 0 -- the pupil centre, i.e. the chief ray, for the polar grids of `circle` -- wavelength 0),
+// traced with the fast policy.  The spot sums are centred on it; any value near the centroid does
+// (it cancels exactly in k_spot_finalize), it only has to be the same number on every CTA and every
+// rank -- it depends on nothing but the prescription and the (whole, unsharded) pupil array and is
+// computed by the same instruction sequence everywhere.  (A member of the bundle rather than the
+// point (0, 0): a bundle that does not surround the pupil centre stays well centred too.)
 __global__ void k_chief_rays(TlProblem pb, float *ref_y) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= pb.B * pb.F) return;
   const int b = i / pb.F, f = i % pb.F, S = pb.S;
   const float cx = pb.cx.ptr[offset_of(pb.cx, b, f, 0, 0)], cy = pb.cy.ptr[offset_of(pb.cy, b, f, 0, 0)];
-  Ray<float> r{0.f, 0.f, pb.z.ptr[offset_of(pb.z, b, f, 0, 0)], cx, cy, fast_cz0(cx, cy)};
+  float x0, y0;
+  load_pupil_point(pb, b, f, 0, 0, pb.xy_scale ? pb.xy_scale[b] : 1.0f, x0, y0);
+  Ray<float> r{x0, y0, pb.z.ptr[offset_of(pb.z, b, f, 0, 0)], cx, cy, fast_cz0(cx, cy)};
   float min_cos2 = 1.0f, travel;
   for (int k = 0; k < S; ++k) {
     const float mu = pb.mu[((int64_t)b * pb.W) * S + k];
@@ -760,7 +764,9 @@ __global__ void k_reduce_rows(const double *partial, double *dst, int n_rows, in
   const int64_t last = owner_of((int64_t)(row + 1) * groups_per_row - 1, total, n_blocks);
   double s = 0.0;
   for (int64_t blk = first; blk <= last; ++blk) {
-    const int64_t first_row = (total * blk / n_blocks) / groups_per_row;
+    const int64_t lo = total * blk / n_blocks, hi = total * (blk + 1) / n_blocks;
+    if (hi <= lo) continue;                      // an owner with an empty slice wrote nothing
+    const int64_t first_row = lo / groups_per_row;
     s += partial[((blk * max_seg) + (row - first_row)) * n_acc + slot];
   }
   dst[i] = s;
@@ -2200,6 +2206,20 @@ int tl_spot_accumulate(const TlProblem *pb, int32_t want_grad, double *moments, 
   rc = launch_adj(*pb, args, pl, stream);
   if (rc) return rc;
   return reduce_rows(pl, args.partial, moments, pb->B * pb->F * pb->W, stream);
+}
+
+const char *tl_spot_kernel_name(const TlProblem *pb, int32_t want_grad) {
+  static thread_local char text[96];
+  if (validate(pb, want_grad ? TL_MAX_SURFACES_SPOT : TL_MAX_SURFACES_FWD)) return "invalid";
+  if (is_general(*pb)) return want_grad ? "k_trace_gen<SPOT_GRAD,f2>" : "k_trace_gen<SPOT_EVAL,f4>";
+  if (use_rows_kernel(*pb, want_grad)) return want_grad ? "k_spot_rows<GRAD,f2>" : "k_spot_rows<EVAL,f2>";
+  if (want_grad && use_rev_kernel(*pb)) {
+    RevPlan rp;
+    if (plan_rev(*pb, rp)) return "invalid";
+    snprintf(text, sizeof(text), "k_spot_rev<%s,f4>", rp.name);
+    return text;
+  }
+  return want_grad ? "k_trace_adj<SPOT_GRAD>" : "k_trace_adj<SPOT_EVAL,f4>";
 }
 
 int32_t tl_penalty_moment_count(int32_t S) { return 3 * S + 2; }

@@ -241,7 +241,9 @@ __global__ void k_chief_rays_gen(TlProblem pb, float *ref_y) {
   if (i >= pb.B * pb.F) return;
   const int b = i / pb.F, f = i % pb.F, S = pb.S;
   const float cx = pb.cx.ptr[offset_of(pb.cx, b, f, 0, 0)], cy = pb.cy.ptr[offset_of(pb.cy, b, f, 0, 0)];
-  Ray<float> r{0.f, 0.f, pb.z.ptr[offset_of(pb.z, b, f, 0, 0)], cx, cy, fast_cz0(cx, cy)};
+  float x0, y0;      // the first ray of the bundle (see k_chief_rays)
+  load_pupil_point<false>(pb, b, f, 0, 0, pb.xy_scale ? pb.xy_scale[b] : 1.0f, x0, y0);
+  Ray<float> r{x0, y0, pb.z.ptr[offset_of(pb.z, b, f, 0, 0)], cx, cy, fast_cz0(cx, cy)};
   float min_cos2 = 1.0f, travel, min_clip = 3.0e38f, opl = 0.f;
   for (int k = 0; k < S; ++k) {
     const int64_t j = (int64_t)b * S + k;

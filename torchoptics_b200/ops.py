@@ -12,6 +12,7 @@ rtl = /root/reference/torchlens/ray_tracing_lite.py.  No CPU path exists.
 from __future__ import annotations
 
 import ctypes
+import weakref
 
 import torch
 
@@ -245,6 +246,13 @@ def trace(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arith=nat.A
         return (*outs, *flags)
     res = _TraceSkew.apply(x, y, z, cx, cy, c, t, mu, mask, bool(allow_backward_rays), int(arith),
                            k, a, sd, bool(aggregate))
+    # provenance: lets rms_of_trace() recognise un-modified trace outputs and evaluate the RMS (and
+    # its backward) with the fused pass on the trace's INPUTS instead of reading [B,F,P,W] tensors back
+    tensors = [v for v in (x, y, z, cx, cy, c, t, mu, mask, k, a, sd) if v is not None]
+    res[1]._tl_prov = {'kind': 'rays', 'args': (x, y, z, cx, cy, c, t, mu, mask),
+                       'ext': {'k': k, 'a': a, 'sd': sd}, 'allow': bool(allow_backward_rays), 'arith': int(arith),
+                       'tensors': tensors, 'versions': [v._version for v in tensors],
+                       'ok': weakref.ref(res[4]), 'ok_version': res[4]._version, 'y_version': res[1]._version}
     if aggregate:
         return (*res[:6], {key: list(res[6 + i].unbind(0)) for i, key in enumerate(STACK_KEYS)})
     return res
@@ -295,6 +303,45 @@ def spot_rms_from_rays(y, ray_ok):
     return _RmsFromRays.apply(y, ray_ok)
 
 
+def _provenance_of(y, ray_ok):
+    """The provenance record of `y` if (y, ray_ok) are the untouched outputs of one trace call whose
+    inputs have not been modified in place since; else None."""
+    prov = getattr(y, '_tl_prov', None)
+    if prov is None or prov['ok']() is not ray_ok:
+        return None
+    if y._version != prov['y_version'] or ray_ok._version != prov['ok_version']:
+        return None
+    if any(t._version != v for t, v in zip(prov['tensors'], prov['versions'])):
+        return None
+    return prov
+
+
+def rms_of_trace(y, ray_ok):
+    """``compute_rms2d`` for every lens, [B] (rtl:678-702).  When (y, ray_ok) are the unmodified outputs
+    of :func:`trace` (or ``RayTracer.trace_rays``) the value AND its gradient come from the fused
+    spot pass evaluated on that trace's inputs -- one pass over the rays, nothing per-ray read back or
+    written in backward -- which is what makes the reference's own call sequence ``trace_rays ->
+    compute_rms2d -> backward`` fast without changing it.  Anything else (a modified, sliced or
+    foreign y) takes the reduction over the materialised tensors."""
+    prov = _provenance_of(y, ray_ok)
+    if prov is not None:
+        if prov['kind'] == 'lens':
+            fused = prov['fused']()
+            if fused is not None:
+                return fused
+        else:
+            x, yy, z, cx, cy, c, t, mu, mask = prov['args']
+            ext = prov['ext']
+            general = any(v is not None for v in ext.values())
+            wants = torch.is_grad_enabled() and any(v is not None and v.requires_grad
+                                                    for v in (z, c, t, mu, ext['k'], ext['a']))
+            limit = nat.MAX_SURFACES_GEN if general else (nat.MAX_SURFACES_SPOT if wants else nat.MAX_SURFACES_FWD)
+            per_ray_grad = torch.is_grad_enabled() and any(v.requires_grad for v in (x, yy, cx, cy))
+            if z.numel() == z.shape[0] and t.shape[-1] <= limit and not per_ray_grad:
+                return spot_rms(x, yy, z, cx, cy, c, t, mu, mask, prov['allow'], prov['arith'], **ext)[0]
+    return spot_rms_from_rays(y, ray_ok)[0]
+
+
 def pupil_slice(n_pupil, rank, world):
     """Contiguous slice [begin, end) of the pupil axis traced by ``rank`` of ``world``."""
     if not 0 <= rank < world:
@@ -340,6 +387,14 @@ def spot_moments(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arit
     p_begin, p_end = pupil_slice(lay.P, *shard)
     with torch.cuda.device(lay.device):
         return _accumulate(lay, allow_backward_rays, arith, want_grad, p_begin, p_end)
+
+
+def spot_kernel_name(x, y, z, cx, cy, c, t, mu, mask, want_grad=True, shard=(0, 1), k=None, a=None, sd=None):
+    """Which kernel the fused spot pass launches for this problem (diagnostics)."""
+    lay = _Layout(x, y, z, cx, cy, c, t, mu, mask, k, a, sd)
+    p_begin, p_end = pupil_slice(lay.P, *shard)
+    pb = lay.problem(True, nat.ARITH_GUARDED, p_begin, p_end)
+    return nat.load().tl_spot_kernel_name(ctypes.byref(pb), int(want_grad)).decode()
 
 
 class _SpotRms(torch.autograd.Function):
@@ -574,30 +629,79 @@ def aim_table(c, t, nd, v, hfov, epd, tables, allow_backward_rays=True):
     return aim
 
 
+class _Staged:
+    """Ray set of a lens batch built by the staging kernel (tl_stage_fwd, optionally tl_aim): the
+    index ratios mu [B,W,L], pupil position z [B], field cosines cy [B,F], half EPD [B] and the
+    TlProblem that points at them (relative pupil grid + xy_scale / aim applied on load).  Holds
+    every buffer alive for as long as the problem is in use."""
+
+    def __init__(self, c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, aimed,
+                 p_begin=0, p_end=None, max_surfaces=64):
+        for name, val in (('c', c), ('t', t), ('nd', nd), ('v', v), ('hfov', hfov), ('epd', epd),
+                          ('x', x_rel), ('y', y_rel)):
+            nat.require_cuda(val, name)
+            if val.dtype != torch.float32:
+                raise TypeError(f'{name} must be float32')
+        lib = nat.load()
+        dev = c.device
+        B, L, F, W = tables.B, tables.L, tables.F, tables.W
+        if tuple(c.shape) != (B, L):
+            raise ValueError(f'lens tensors must be [B={B}, L={L}], got {tuple(c.shape)}')
+        if L > max_surfaces:
+            raise ValueError('too many surfaces for the staged lens pass')
+        P = x_rel.shape[2]
+        self.device, self.B, self.L, self.F, self.W, self.P = dev, B, L, F, W, P
+        self.shape = (B, F, P, W)
+        self.keep = [a.detach().contiguous() for a in (c, t, nd, v, hfov, epd)]
+        cc, tt, ndd, vv, hf, ep = self.keep
+        self.mu = torch.empty((B, W, L), dtype=torch.float32, device=dev)
+        packed = torch.empty((2 * B + B * F,), dtype=torch.float32, device=dev)      # one allocation: z, half_epd, cy
+        self.z, self.half_epd, self.cy = packed[:B], packed[B:2 * B], packed[2 * B:].view(B, F)
+        self.ln = tables.lens_struct(cc, tt, ndd, vv, hf, ep)
+        stream = nat.stream_ptr(dev)
+        nat.check(lib.tl_stage_fwd(ctypes.byref(self.ln), self.mu.data_ptr(), self.z.data_ptr(), self.cy.data_ptr(),
+                                   self.half_epd.data_ptr(), stream), 'tl_stage_fwd')
+        self.aim = None
+        if aimed:      # ray aiming (rtl:129-208) as one more kernel; the map is applied on load
+            self.aim = torch.empty((B, F, W, 3), dtype=torch.float32, device=dev)
+            nat.check(lib.tl_aim(ctypes.byref(self.ln), self.mu.data_ptr(), self.z.data_ptr(), self.cy.data_ptr(),
+                                 self.half_epd.data_ptr(), int(bool(allow_backward_rays)), self.aim.data_ptr(),
+                                 stream), 'tl_aim')
+        self.xy = (x_rel.detach(), y_rel.detach())
+        pb = nat.TlProblem()
+        pb.aim = _ptr(self.aim)
+        pb.x = nat.strided(self.xy[0], self.shape)
+        pb.y = nat.strided(self.xy[1], self.shape)
+        pb.z = nat.strided(self.z.reshape(B, 1, 1, 1), self.shape)
+        pb.cx = nat.strided(tables.zero, self.shape)
+        pb.cy = nat.strided(self.cy.reshape(B, F, 1, 1), self.shape)
+        pb.c, pb.t, pb.mu, pb.live = cc.data_ptr(), tt.data_ptr(), self.mu.data_ptr(), tables.mask.data_ptr()
+        pb.B, pb.F, pb.P, pb.W, pb.S = B, F, P, W, L
+        pb.allow_backward_rays, pb.arith = int(bool(allow_backward_rays)), int(arith)
+        pb.p_begin, pb.p_end = int(p_begin), int(P if p_end is None else p_end)
+        pb.xy_scale = self.half_epd.data_ptr()
+        self.pb = pb
+        self.tables = tables
+
+    def chain_rule(self, gmu, gz, gc, gt, gnd, gv):
+        """ADDS the gradients induced through mu and z to gc, gt, gnd, gv [B,L] (tl_stage_bwd)."""
+        nat.check(nat.load().tl_stage_bwd(ctypes.byref(self.ln), gmu.data_ptr(), gz.data_ptr(), gc.data_ptr(),
+                                          gt.data_ptr(), gnd.data_ptr(), gv.data_ptr(), nat.stream_ptr(self.device)),
+                  'tl_stage_bwd')
+
+
 def _lens_spot_core(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, shard, group,
-                    want_grad, aimed, out=None):
+                    want_grad, aimed, out=None, staged=None):
     """The staged fused pass itself (no autograd): staging kernel -> (ray aiming) -> chief rays ->
     fused trace+adjoint -> row reduction -> (all-reduce) -> finalize -> staging chain rule.
     Returns (rms [B], rms_field [B,F], gc, gt, gnd, gv) -- the four gradients of sum(rms) w.r.t. the
     padded [B,L] lens tensors, or None without ``want_grad``.  ``out``: optional dict of
     preallocated float32 tensors 'rms' [B] and 'gc', 'gt', 'gnd', 'gv' [B,L] to write into (a
     caller that owns a packed staging buffer passes views of it and saves the copies)."""
-    for name, val in (('c', c), ('t', t), ('nd', nd), ('v', v), ('hfov', hfov), ('epd', epd),
-                      ('x', x_rel), ('y', y_rel)):
-        nat.require_cuda(val, name)
-        if val.dtype != torch.float32:
-            raise TypeError(f'{name} must be float32')
     lib = nat.load()
-    dev = c.device
     out = out or {}
-    B, L, F, W = tables.B, tables.L, tables.F, tables.W
-    if tuple(c.shape) != (B, L):
-        raise ValueError(f'lens tensors must be [B={B}, L={L}], got {tuple(c.shape)}')
-    if L > (nat.MAX_SURFACES_SPOT if want_grad else 64):
-        raise ValueError('too many surfaces for the fused lens pass')
-    P = x_rel.shape[2]
     rank, world = shard
-    p_begin, p_end = pupil_slice(P, rank, world)
+    p_begin, p_end = pupil_slice(x_rel.shape[2], rank, world)
 
     def buffer(name, shape):
         given = out.get(name)
@@ -607,36 +711,20 @@ def _lens_spot_core(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward
             raise ValueError(f'out[{name!r}] must be a contiguous float32 tensor of shape {tuple(shape)}')
         return given
 
+    nat.require_cuda(c, 'c')
+    dev = c.device
     with torch.cuda.device(dev):
-        cc, tt, ndd, vv = (a.detach().contiguous() for a in (c, t, nd, v))
-        hf, ep = hfov.detach().contiguous(), epd.detach().contiguous()
-        mu = torch.empty((B, W, L), dtype=torch.float32, device=dev)
-        z = torch.empty((B,), dtype=torch.float32, device=dev)
-        cy = torch.empty((B, F), dtype=torch.float32, device=dev)
-        half_epd = torch.empty((B,), dtype=torch.float32, device=dev)
-        ln = tables.lens_struct(cc, tt, ndd, vv, hf, ep)
+        if staged is not None:      # the ray set a staged trace_rays of the same lens already built
+            st = staged
+            if want_grad and st.L > nat.MAX_SURFACES_SPOT:
+                raise ValueError('too many surfaces for the staged lens pass')
+            st.pb.p_begin, st.pb.p_end = int(p_begin), int(p_end)
+        else:
+            st = _Staged(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, aimed, p_begin,
+                         p_end, max_surfaces=nat.MAX_SURFACES_SPOT if want_grad else 64)
+        B, L, F, W, P = st.B, st.L, st.F, st.W, st.P
+        pb = st.pb
         stream = nat.stream_ptr(dev)
-        nat.check(lib.tl_stage_fwd(ctypes.byref(ln), mu.data_ptr(), z.data_ptr(), cy.data_ptr(),
-                                   half_epd.data_ptr(), stream), 'tl_stage_fwd')
-        aim = None
-        if aimed:      # ray aiming (rtl:129-208) as one more kernel; the map is applied on load
-            aim = torch.empty((B, F, W, 3), dtype=torch.float32, device=dev)
-            nat.check(lib.tl_aim(ctypes.byref(ln), mu.data_ptr(), z.data_ptr(), cy.data_ptr(),
-                                 half_epd.data_ptr(), int(bool(allow_backward_rays)), aim.data_ptr(),
-                                 stream), 'tl_aim')
-        shape = (B, F, P, W)
-        pb = nat.TlProblem()
-        pb.aim = _ptr(aim)
-        pb.x = nat.strided(x_rel.detach(), shape)
-        pb.y = nat.strided(y_rel.detach(), shape)
-        pb.z = nat.strided(z.reshape(B, 1, 1, 1), shape)
-        pb.cx = nat.strided(tables.zero, shape)
-        pb.cy = nat.strided(cy.reshape(B, F, 1, 1), shape)
-        pb.c, pb.t, pb.mu, pb.live = cc.data_ptr(), tt.data_ptr(), mu.data_ptr(), tables.mask.data_ptr()
-        pb.B, pb.F, pb.P, pb.W, pb.S = B, F, P, W, L
-        pb.allow_backward_rays, pb.arith = int(bool(allow_backward_rays)), int(arith)
-        pb.p_begin, pb.p_end = p_begin, p_end
-        pb.xy_scale = half_epd.data_ptr()
         n_acc = lib.tl_spot_moment_count(L, int(want_grad))
         moments = torch.empty((B, F, W, n_acc), dtype=torch.float64, device=dev)
         ref_y = torch.empty((B, F), dtype=torch.float32, device=dev)
@@ -670,10 +758,74 @@ def _lens_spot_core(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward
             else:
                 gnd.zero_()
                 gv.zero_()
-            nat.check(lib.tl_stage_bwd(ctypes.byref(ln), gmu.data_ptr(), gz.data_ptr(), gc.data_ptr(),
-                                       gt.data_ptr(), gnd.data_ptr(), gv.data_ptr(), stream),
-                      'tl_stage_bwd')
+            st.chain_rule(gmu, gz, gc, gt, gnd, gv)
     return rms, rms_field, gc, gt, gnd, gv
+
+
+class _LensTrace(torch.autograd.Function):
+    """``RayTracer.trace_rays`` (rtl:80-127) as ONE autograd node over the lens tensors: the staging
+    kernel builds the ray set (index model, pupil position, field cosines; ~60 eager tensor ops in
+    the reference), tl_trace_fwd traces it; backward = tl_trace_bwd on the upstream gradients of
+    x, y, cx, cy + the staging chain rule.  Outputs as trace_skew's: x, y, cx, cy, ray_ok, ray_backward."""
+
+    @staticmethod
+    def forward(ctx, c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, aimed):
+        if any(ctx.needs_input_grad[4:8]):
+            raise ValueError('the staged trace does not differentiate w.r.t. hfov / epd / pupil coordinates')
+        lib = nat.load()
+        ctx.set_materialize_grads(False)
+        dev = c.device
+        with torch.cuda.device(dev):
+            st = _Staged(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, aimed,
+                         max_surfaces=nat.MAX_SURFACES_FWD)
+            outs = torch.empty((4,) + st.shape, dtype=torch.float32, device=dev)
+            flags = torch.empty((2,) + st.shape, dtype=torch.bool, device=dev)
+            out = nat.TlTraceOut(*[outs[i].data_ptr() for i in range(4)], flags[0].data_ptr(), flags[1].data_ptr(),
+                                 None, None, None, None)
+            nat.check(lib.tl_trace_fwd(ctypes.byref(st.pb), ctypes.byref(out), nat.stream_ptr(dev)), 'tl_trace_fwd')
+        ctx.staged = st
+        _LensTrace.last_staged = st      # (picked up by lens_trace right after apply)
+        x, y, cx, cy = outs.unbind(0)
+        ok, backward = flags.unbind(0)
+        ctx.mark_non_differentiable(ok, backward)
+        return x, y, cx, cy, ok, backward
+
+    @staticmethod
+    def backward(ctx, gx, gy, gcx, gcy, _gok, _gbw):
+        st = ctx.staged
+        if st.L > nat.MAX_SURFACES_BWD:
+            raise ValueError(f'backward supports at most {nat.MAX_SURFACES_BWD} surfaces')
+        lib = nat.load()
+        dev = st.device
+        B, L, W = st.B, st.L, st.W
+        with torch.cuda.device(dev):
+            seeds = [None if g is None else g.to(torch.float32).expand(st.shape).contiguous()
+                     for g in (gx, gy, gcx, gcy)]
+            grads = torch.zeros((4, B, L), dtype=torch.float32, device=dev)      # gc, gt, gnd, gv
+            gmu = torch.empty((B, W, L), dtype=torch.float32, device=dev)
+            gz = torch.empty((B,), dtype=torch.float32, device=dev)
+            sd = nat.TlSeeds(*[_ptr(s) for s in seeds], None, None, None)
+            gr = nat.TlGrads(grads[0].data_ptr(), grads[1].data_ptr(), gmu.data_ptr(), gz.data_ptr(),
+                             None, None, None, None, None, None, None)
+            ws_bytes = lib.tl_trace_bwd_workspace(ctypes.byref(st.pb))
+            if ws_bytes == 0:
+                nat.check(-1, 'tl_trace_bwd_workspace')
+            ws = torch.empty((ws_bytes // 8,), dtype=torch.float64, device=dev)
+            nat.check(lib.tl_trace_bwd(ctypes.byref(st.pb), ctypes.byref(sd), ctypes.byref(gr), ws.data_ptr(),
+                                       ws_bytes, nat.stream_ptr(dev)), 'tl_trace_bwd')
+            st.chain_rule(gmu, gz, grads[0], grads[1], grads[2], grads[3])
+        need = ctx.needs_input_grad
+        return (*[grads[i] if need[i] else None for i in range(4)], None, None, None, None, None, None, None, None)
+
+
+def lens_trace(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays=True, arith=nat.ARITH_GUARDED,
+               aimed=False):
+    """Staged ``trace_rays``: (x, y, cx, cy, ray_ok, ray_backward), differentiable w.r.t. c, t, nd, v."""
+    out = _LensTrace.apply(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, bool(allow_backward_rays), int(arith),
+                           bool(aimed))
+    out[1]._tl_staged = _LensTrace.last_staged      # the ray set, reusable by the fused pass of the same lens
+    _LensTrace.last_staged = None
+    return out
 
 
 class _LensSpotRms(torch.autograd.Function):
@@ -682,7 +834,7 @@ class _LensSpotRms(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, shard,
-                group, grad_on, aimed=False):
+                group, grad_on, aimed=False, staged=None):
         if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
             raise ValueError('the fused lens pass does not differentiate w.r.t. hfov / epd')
         if ctx.needs_input_grad[6] or ctx.needs_input_grad[7]:
@@ -691,7 +843,7 @@ class _LensSpotRms(torch.autograd.Function):
         want_grad = grad_on and any(ctx.needs_input_grad[:4])
         rms, rms_field, gc, gt, gnd, gv = _lens_spot_core(c, t, nd, v, hfov, epd, x_rel, y_rel, tables,
                                                           allow_backward_rays, arith, shard, group,
-                                                          want_grad, aimed)
+                                                          want_grad, aimed, staged=staged)
         if want_grad:
             ctx.save_for_backward(gc, gt, gnd, gv)
         ctx.mark_non_differentiable(rms_field)
@@ -700,13 +852,13 @@ class _LensSpotRms(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_rms, _grad_field):
         if len(ctx.saved_tensors) < 4:      # forward ran without gradients
-            return (None,) * 15
+            return (None,) * 16
         gc, gt, gnd, gv = ctx.saved_tensors
         g = grad_rms.to(torch.float32).reshape(-1, 1)
         need = ctx.needs_input_grad
         grads = [(gc * g) if need[0] else None, (gt * g) if need[1] else None,
                  (gnd * g) if need[2] else None, (gv * g) if need[3] else None]
-        return (*grads, None, None, None, None, None, None, None, None, None, None, None)
+        return (*grads, None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 def lens_spot_rms_and_grads(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays=True,
@@ -722,10 +874,10 @@ def lens_spot_rms_and_grads(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_
 
 
 def lens_spot_rms(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays=True,
-                  arith=nat.ARITH_GUARDED, shard=(0, 1), group=None, aimed=False):
+                  arith=nat.ARITH_GUARDED, shard=(0, 1), group=None, aimed=False, staged=None):
     """(rms [B], rms_field [B,F]) of a lens batch given as padded [B,L] tensors, differentiable
     w.r.t. c, t, nd, v.  x_rel, y_rel: relative pupil coordinates [1,1,P,1].  ``aimed``: with one
     iteration of 'real' ray aiming (rtl:129-208) done by tl_aim and applied inside the kernels."""
     return _LensSpotRms.apply(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, bool(allow_backward_rays),
                               int(arith), (int(shard[0]), int(shard[1])), group, torch.is_grad_enabled(),
-                              bool(aimed))
+                              bool(aimed), staged)

@@ -240,9 +240,14 @@ def trace_skew(x, y, z, cx, cy, c, t, mu, mask, aggregate=False, allow_backward_
 def compute_rms2d(x, y, ray_ok):
     """Mean over fields of the y-RMS spot radius of lens 0 (rtl:678-702): per field
     the centroid is the mean over *all* rays, deviations are summed over
-    surviving rays and divided by P*W.  ``x`` is unused, as in the reference."""
-    rms, _ = ops.spot_rms_from_rays(y, ray_ok)
-    return rms[0]
+    surviving rays and divided by P*W.  ``x`` is unused, as in the reference.
+
+    When ``y`` and ``ray_ok`` are the untouched outputs of :func:`trace_skew` /
+    ``RayTracer.trace_rays`` the value and its gradient come from the fused spot pass on that
+    trace's inputs (``ops.rms_of_trace``): the reference's own call sequence ``trace_rays ->
+    compute_rms2d -> backward`` then costs one forward trace plus one fused pass, with no per-ray
+    tensor read back or written in backward."""
+    return ops.rms_of_trace(y, ray_ok)[0]
 
 
 def compute_rms2d_all(y, ray_ok):
@@ -357,11 +362,40 @@ class RayTracer:
         return dict(k=view(getattr(lens, 'k', None)), a=view(a, (a.shape[-1],)) if a is not None else None,
                     sd=view(getattr(lens, 'sd', None)))
 
-    def trace_rays(self, specs, lens, use_vig=True, aggregate=False, xy=None, up_to_stop=False):
-        """Trace the configured ray set; returns what :func:`trace_skew` returns."""
+    def trace_rays(self, specs, lens, use_vig=True, aggregate=False, xy=None, up_to_stop=False, staged=True):
+        """Trace the configured ray set; returns what :func:`trace_skew` returns.
+
+        ``staged`` (default): where the staging kernels can build the ray set (see :meth:`spot_rms`)
+        the whole call is ONE autograd node over the lens tensors -- staging kernel (+ ray-aiming
+        kernel) + trace kernel, three launches instead of the ~60 eager tensor ops of rtl:80-124 --
+        and its outputs remember where they came from, so that ``compute_rms2d`` on them runs the
+        fused pass (:func:`compute_rms2d`)."""
+        can_stage, aimed = self._staging(lens, use_vig)
+        if (staged and can_stage and not aggregate and xy is None and not up_to_stop
+                and lens.c.is_cuda and lens.c.shape[1] <= nat.MAX_SURFACES_FWD and lens.c.shape[1] <= 64):
+            x_rel, y_rel = self._pupil(None)
+            out = ops.lens_trace(lens.c, lens.t, lens.nd, lens.v, specs.hfov, specs.epd, x_rel, y_rel,
+                                 self._tables(lens), self.allow_backward_rays, _arith_code(self.arith), aimed)
+            self._remember(out, specs, lens, use_vig)
+            return out
         args = self._ray_set(specs, lens, use_vig, xy, up_to_stop)
         return trace_skew(*args, aggregate, self.allow_backward_rays, arith=self.arith,
                           **self._extension_tables(lens))
+
+    def _remember(self, out, specs, lens, use_vig):
+        """Provenance of a staged trace (ops.rms_of_trace): the fused pass of the same (specs, lens)."""
+        import weakref
+        tensors = [lens.c, lens.t, lens.nd, lens.v, specs.hfov, specs.epd]
+        ray_set = getattr(out[1], '_tl_staged', None)      # (not `out` itself: no reference cycle through y)
+
+        def fused():
+            if torch.is_grad_enabled() and any(v.requires_grad for v in tensors[:4]) \
+                    and lens.c.shape[1] > nat.MAX_SURFACES_SPOT:
+                return None
+            return self.spot_rms(specs, lens, use_vig, _ray_set=ray_set)[0]
+        out[1]._tl_prov = {'kind': 'lens', 'fused': fused, 'tensors': tensors,
+                           'versions': [v._version for v in tensors], 'ok': weakref.ref(out[4]),
+                           'ok_version': out[4]._version, 'y_version': out[1]._version}
 
     def penalty(self, specs, lens, use_vig=True, shard=(0, 1), group=None, n_seq=None):
         """The ray-angle / ray-path penalty ``sum(Q)`` that ``compute_loss_out`` adds to the RMS
@@ -385,7 +419,7 @@ class RayTracer:
         pen = self.penalty(specs, lens, use_vig, shard, group, n_seq)
         return {'loss_unsup': rms + penalty_rate * pen, 'rms': rms, 'penalty': pen}
 
-    def spot_rms(self, specs, lens, use_vig=True, shard=(0, 1), group=None, staged=True):
+    def spot_rms(self, specs, lens, use_vig=True, shard=(0, 1), group=None, staged=True, _ray_set=None):
         """RMS spot size of every lens -- ``compute_rms2d(*trace_rays(...))`` fused
         into one pass that also produces the gradients w.r.t. the lens
         (no [B,F,P,W] tensor is ever materialised).  Returns (rms [B], rms_field [B,F]).
@@ -402,7 +436,7 @@ class RayTracer:
             x_rel, y_rel = self._pupil(None)
             return ops.lens_spot_rms(lens.c, lens.t, lens.nd, lens.v, specs.hfov, specs.epd, x_rel,
                                      y_rel, self._tables(lens), self.allow_backward_rays,
-                                     _arith_code(self.arith), shard, group, aimed=aimed)
+                                     _arith_code(self.arith), shard, group, aimed=aimed, staged=_ray_set)
         args = self._ray_set(specs, lens, use_vig)
         return ops.spot_rms(*args, self.allow_backward_rays, _arith_code(self.arith), shard, group, **ext)
 
