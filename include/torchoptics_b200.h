@@ -221,6 +221,20 @@ typedef struct TlLens {
 
 /* mu [B,W,L], z [B], cy [B,F], half_epd [B] (= the xy_scale of TlProblem) */
 int tl_stage_fwd(const TlLens *lens, float *mu, float *z, float *cy, float *half_epd, void *stream);
+/* tl_stage_fwd, (aim != NULL) tl_aim and (ref_y != NULL) the reference heights of tl_spot_accumulate as
+ * ONE launch: `pb` is the problem the fused pass will run (its mu, z, cy, xy_scale, aim pointers
+ * are the very buffers written here; read only when ref_y != NULL).  Pair it with
+ * tl_spot_accumulate_ref, which takes ref_y as an input. */
+int tl_stage_ref(const TlLens *lens, const TlProblem *pb, float *mu, float *z, float *cy, float *half_epd,
+                 float *aim, int32_t allow_backward_rays, float *ref_y, void *stream);
+int tl_spot_accumulate_ref(const TlProblem *pb, int32_t want_grad, double *moments, const float *ref_y,
+                           void *workspace, size_t workspace_bytes, void *stream);
+/* tl_spot_finalize (with gradients) + the chain rule of tl_stage_bwd as ONE launch: from the (reduced)
+ * moments to rms, rms_field and d rms[b] / d{c, t, nd, v} [B,L] (out->gc, out->gt, gnd, gv; written,
+ * not added to).  out->gmu [B,W,L] and out->gz [B] are scratch. */
+int tl_lens_spot_finalize(const double *moments, const float *ref_y, const TlLens *lens, int64_t P_total,
+                          const TlSpotOut *out, float *gnd, float *gv, void *stream);
+
 /* Chain rule: given d loss / d mu [B,W,L] and d loss / d z [B], ADDS the induced gradients to
  * gc, gt, gnd, gv [B,L] (which the caller pre-fills, e.g. with the direct c / t gradients). */
 int tl_stage_bwd(const TlLens *lens, const float *gmu, const float *gz, float *gc, float *gt,

@@ -97,6 +97,13 @@ EXPORTS = {
                                           ctypes.c_void_p]),
     'tl_stage_fwd': (ctypes.c_int, [ctypes.POINTER(TlLens)] + [ctypes.c_void_p] * 5),
     'tl_stage_bwd': (ctypes.c_int, [ctypes.POINTER(TlLens)] + [ctypes.c_void_p] * 7),
+    'tl_stage_ref': (ctypes.c_int, [ctypes.POINTER(TlLens), ctypes.POINTER(TlProblem)] + [ctypes.c_void_p] * 5 +
+                     [ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
+    'tl_spot_accumulate_ref': (ctypes.c_int, [ctypes.POINTER(TlProblem), ctypes.c_int32, ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    'tl_lens_spot_finalize': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(TlLens), ctypes.c_int64,
+                                             ctypes.POINTER(TlSpotOut), ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p]),
     'tl_aim': (ctypes.c_int, [ctypes.POINTER(TlLens)] + [ctypes.c_void_p] * 4 +
                [ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
     'tl_spot_finalize': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int32] * 4 +

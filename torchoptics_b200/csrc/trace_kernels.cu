@@ -438,9 +438,7 @@ k_trace_fwd_pw(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
 // rank -- it depends on nothing but the prescription and the (whole, unsharded) pupil array and is
 // computed by the same instruction sequence everywhere.  (A member of the bundle rather than the
 // point (0, 0): a bundle that does not surround the pupil centre stays well centred too.)
-__global__ void k_chief_rays(TlProblem pb, float *ref_y) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= pb.B * pb.F) return;
+__device__ __forceinline__ void chief_ray_one(const TlProblem &pb, int i, float *ref_y) {
   const int b = i / pb.F, f = i % pb.F, S = pb.S;
   const float cx = pb.cx.ptr[offset_of(pb.cx, b, f, 0, 0)], cy = pb.cy.ptr[offset_of(pb.cy, b, f, 0, 0)];
   float x0, y0;
@@ -453,6 +451,11 @@ __global__ void k_chief_rays(TlProblem pb, float *ref_y) {
   }
   fast_image(r);
   ref_y[i] = (min_cos2 > kGuard && fabsf(r.y) < 3.0e38f) ? r.y : 0.f;
+}
+
+__global__ void k_chief_rays(TlProblem pb, float *ref_y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < pb.B * pb.F) chief_ray_one(pb, i, ref_y);
 }
 
 // --------------------------------------------------------------------------
@@ -1006,8 +1009,8 @@ __global__ void k_penalty_finalize(const double *rows, TlPenaltyOut out, int B, 
 // The lens' rows are first staged in shared memory with coalesced loads (STAGED), so the
 // dependent fp64 sums below do not each wait for a global-memory round trip.
 template <bool STAGED>
-__global__ void k_spot_finalize(const double *mom_global, const float *ref_y, int B, int F, int W,
-                                int S, double n_rays, int want_grad, TlSpotOut out) {
+__device__ __forceinline__ void spot_finalize_lens(const double *mom_global, const float *ref_y, int B, int F, int W,
+                                                   int S, double n_rays, int want_grad, const TlSpotOut &out) {
   extern __shared__ double sh[];   // alpha[F], shift[F], rms[F], then (STAGED) the rows
   double *alpha = sh, *shift = sh + F, *rmsf = sh + 2 * F;
   const int b = blockIdx.x;
@@ -1083,6 +1086,12 @@ __global__ void k_spot_finalize(const double *mom_global, const float *ref_y, in
       out.gz[b] = (float)s;
     }
   }
+}
+
+template <bool STAGED>
+__global__ void k_spot_finalize(const double *mom_global, const float *ref_y, int B, int F, int W,
+                                int S, double n_rays, int want_grad, TlSpotOut out) {
+  spot_finalize_lens<STAGED>(mom_global, ref_y, B, F, W, S, n_rays, want_grad, out);
 }
 
 // --------------------------------------------------------------------------
@@ -1226,8 +1235,8 @@ __device__ __forceinline__ Abcd slot_matrix(const TlLens &ln, int b, int s, floa
   return Abcd{1.0f + power * tt, ratio * tt, power, ratio};
 }
 
-__global__ void k_stage_fwd(TlLens ln, float *mu, float *z, float *cy, float *half_epd) {
-  const int b = blockIdx.x;
+__device__ __forceinline__ void stage_fwd_lens(const TlLens &ln, int b, float *mu, float *z, float *cy,
+                                               float *half_epd) {
   if (threadIdx.x == 1 % blockDim.x) half_epd[b] = ln.epd[b] * 0.5f;
   for (int i = threadIdx.x; i < ln.W * ln.L; i += blockDim.x) {
     const int w = i / ln.L, s = i % ln.L;
@@ -1247,6 +1256,10 @@ __global__ void k_stage_fwd(TlLens ln, float *mu, float *z, float *cy, float *ha
     }
     z[b] = n_front > 0 ? m.b / m.a : 0.f;
   }
+}
+
+__global__ void k_stage_fwd(TlLens ln, float *mu, float *z, float *cy, float *half_epd) {
+  stage_fwd_lens(ln, blockIdx.x, mu, z, cy, half_epd);
 }
 
 // Ray aiming on the device (RayTracer.ray_aiming, rtl:129-208, one iteration, 'real' stop radius).
@@ -1289,10 +1302,8 @@ __device__ __forceinline__ bool trace_to_stop(const TlLens &ln, const float *mu_
   return ok;
 }
 
-__global__ void k_aim(TlLens ln, const float *mu, const float *z, const float *cy, const float *half_epd,
-                      int allow_backward, float *aim) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= ln.B * ln.F * ln.W) return;
+__device__ __forceinline__ void aim_one(const TlLens &ln, const float *mu, const float *z, const float *cy,
+                                        const float *half_epd, int allow_backward, float *aim, int i) {
   const int w = i % ln.W, f = (i / ln.W) % ln.F, b = i / (ln.W * ln.F);
   const int n_front = min(ln.stop_idx[b], ln.L);
   const float h = half_epd[b], z0 = z[b];
@@ -1324,9 +1335,36 @@ __global__ void k_aim(TlLens ln, const float *mu, const float *z, const float *c
   out[2] = (y_lo * step_y[1] - y_hi * step_y[0]) / (y_lo - y_hi);
 }
 
-__global__ void k_stage_bwd(TlLens ln, const float *gmu, const float *gz, float *gc, float *gt,
-                            float *gnd, float *gv) {
+__global__ void k_aim(TlLens ln, const float *mu, const float *z, const float *cy, const float *half_epd,
+                      int allow_backward, float *aim) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ln.B * ln.F * ln.W) aim_one(ln, mu, z, cy, half_epd, allow_backward, aim, i);
+}
+
+// Staging, ray aiming and the reference heights of a lens as ONE launch (a step of the fused lens
+// pass is a handful of launches of which only one is long: every launch saved is ~3 us of a ~270 us
+// step).  One CTA per lens; the phases see each other's global writes through the barriers.
+__global__ void __launch_bounds__(128)
+k_stage_ref(TlLens ln, TlProblem pb, float *mu, float *z, float *cy, float *half_epd, float *aim,
+            int allow_backward, float *ref_y) {
   const int b = blockIdx.x;
+  stage_fwd_lens(ln, b, mu, z, cy, half_epd);
+  __threadfence_block();
+  __syncthreads();
+  if (aim) {
+    for (int i = threadIdx.x; i < ln.F * ln.W; i += blockDim.x)
+      aim_one(ln, mu, z, cy, half_epd, allow_backward, aim, b * ln.F * ln.W + i);
+    __threadfence_block();
+    __syncthreads();
+  }
+  if (ref_y)
+    for (int f = threadIdx.x; f < pb.F; f += blockDim.x) chief_ray_one(pb, b * pb.F + f, ref_y);
+}
+
+// Chain rule of the staging for lens b: `gmu_b` = d loss / d mu[b] ([W,L]), `gz_b` = d loss / d z[b]; ADDS
+// to gc, gt, gnd, gv (global [B,L] arrays).
+__device__ __forceinline__ void stage_bwd_lens(const TlLens &ln, int b, const float *gmu_b, float gz_b, float *gc,
+                                               float *gt, float *gnd, float *gv) {
   // ---- through mu[w,s] = n[w,s-1] / n[w,s]: one thread per slot gathers over wavelengths
   for (int s = threadIdx.x; s < ln.L; s += blockDim.x) {
     const int64_t i = (int64_t)b * ln.L + s;
@@ -1337,10 +1375,10 @@ __global__ void k_stage_bwd(TlLens ln, const float *gmu, const float *gz, float 
       float dn_dnd, dn_dv;
       const float n_s = index_at(ln, b, s, wl, &dn_dnd, &dn_dv);
       const float n_in = (s == 0) ? 1.0f : index_at(ln, b, s - 1, wl, nullptr, nullptr);
-      const int64_t j = ((int64_t)b * ln.W + w) * ln.L + s;
-      float g_n = -gmu[j] * n_in / (n_s * n_s);                     // as denominator of mu[s]
+      const int j = w * ln.L + s;
+      float g_n = -gmu_b[j] * n_in / (n_s * n_s);                   // as denominator of mu[s]
       if (s + 1 < ln.L)                                             // as numerator of mu[s+1]
-        g_n += gmu[j + 1] / index_at(ln, b, s + 1, wl, nullptr, nullptr);
+        g_n += gmu_b[j + 1] / index_at(ln, b, s + 1, wl, nullptr, nullptr);
       g_nd += g_n * dn_dnd;
       g_v += g_n * dn_dv;
     }
@@ -1360,7 +1398,7 @@ __global__ void k_stage_bwd(TlLens ln, const float *gmu, const float *gz, float 
     m = Abcd{q.a * m.a + q.b * m.c, q.a * m.b + q.b * m.d, q.c * m.a + q.d * m.c,
              q.c * m.b + q.d * m.d};
   }
-  const float gzz = gz[b];
+  const float gzz = gz_b;
   Abcd g{-gzz * m.b / (m.a * m.a), gzz / m.a, 0.f, 0.f};        // adjoint of the full product
   for (int s = n_front - 1; s >= 0; --s) {
     // total = Q_s M_s P_s ; g holds Q_s^T G ; d M_s = g P_s^T
@@ -1383,6 +1421,29 @@ __global__ void k_stage_bwd(TlLens ln, const float *gmu, const float *gz, float 
     g = Abcd{q.a * g.a + q.c * g.c, q.a * g.b + q.c * g.d, q.b * g.a + q.d * g.c,
              q.b * g.b + q.d * g.d};                             // M_s^T g
   }
+}
+
+__global__ void k_stage_bwd(TlLens ln, const float *gmu, const float *gz, float *gc, float *gt,
+                            float *gnd, float *gv) {
+  const int b = blockIdx.x;
+  stage_bwd_lens(ln, b, gmu + (int64_t)b * ln.W * ln.L, gz[b], gc, gt, gnd, gv);
+}
+
+// Finalize + staging chain rule of a lens as ONE launch: moments -> rms, rms_field and the gradients
+// of rms[b] w.r.t. the padded lens tensors c, t, nd, v [B,L] (what k_spot_finalize, two fills and
+// k_stage_bwd did in four).  out.gmu / out.gz are scratch here.
+template <bool STAGED>
+__global__ void k_lens_finalize(const double *mom_global, const float *ref_y, int B, int F, int W, int S,
+                                double n_rays, TlSpotOut out, TlLens ln, float *gnd, float *gv) {
+  spot_finalize_lens<STAGED>(mom_global, ref_y, B, F, W, S, n_rays, 1, out);
+  const int b = blockIdx.x;
+  for (int s_ = threadIdx.x; s_ < ln.L; s_ += blockDim.x) {
+    gnd[(int64_t)b * ln.L + s_] = 0.f;
+    gv[(int64_t)b * ln.L + s_] = 0.f;
+  }
+  __threadfence_block();
+  __syncthreads();
+  stage_bwd_lens(ln, b, out.gmu + (int64_t)b * ln.W * ln.L, out.gz[b], out.gc, out.gt, gnd, gv);
 }
 
 // --------------------------------------------------------------------------
@@ -2141,8 +2202,22 @@ size_t tl_spot_workspace(const TlProblem *pb, int32_t want_grad) {
   return bytes;
 }
 
+static int spot_accumulate(const TlProblem *pb, int32_t want_grad, double *moments, float *ref_y, bool ref_ready,
+                           void *workspace, size_t workspace_bytes, void *stream_);
+
 int tl_spot_accumulate(const TlProblem *pb, int32_t want_grad, double *moments, float *ref_y,
                        void *workspace, size_t workspace_bytes, void *stream_) {
+  return spot_accumulate(pb, want_grad, moments, ref_y, false, workspace, workspace_bytes, stream_);
+}
+
+int tl_spot_accumulate_ref(const TlProblem *pb, int32_t want_grad, double *moments, const float *ref_y,
+                           void *workspace, size_t workspace_bytes, void *stream_) {
+  return spot_accumulate(pb, want_grad, moments, const_cast<float *>(ref_y), true, workspace, workspace_bytes,
+                         stream_);
+}
+
+static int spot_accumulate(const TlProblem *pb, int32_t want_grad, double *moments, float *ref_y, bool ref_ready,
+                           void *workspace, size_t workspace_bytes, void *stream_) {
   int rc = validate(pb, want_grad ? TL_MAX_SURFACES_SPOT : TL_MAX_SURFACES_FWD);
   if (rc) return rc;
   if (pb->p_begin < 0 || pb->p_end > pb->P || pb->p_end <= pb->p_begin)
@@ -2156,8 +2231,10 @@ int tl_spot_accumulate(const TlProblem *pb, int32_t want_grad, double *moments, 
       return fail(TL_ERR_WORKSPACE, "workspace too small for tl_spot_accumulate%s");
     cudaStream_t stream = (cudaStream_t)stream_;
     const int n_bf = pb->B * pb->F;
-    k_chief_rays_gen<<<(n_bf + 127) / 128, 128, 0, stream>>>(*pb, ref_y);
-    g_launches++;
+    if (!ref_ready) {
+      k_chief_rays_gen<<<(n_bf + 127) / 128, 128, 0, stream>>>(*pb, ref_y);
+      g_launches++;
+    }
     AdjArgs args;
     memset(&args, 0, sizeof(args));
     args.partial = (double *)workspace;
@@ -2187,8 +2264,10 @@ int tl_spot_accumulate(const TlProblem *pb, int32_t want_grad, double *moments, 
     return fail(TL_ERR_WORKSPACE, "workspace too small for tl_spot_accumulate%s");
   cudaStream_t stream = (cudaStream_t)stream_;
   const int n_bf = pb->B * pb->F;
-  k_chief_rays<<<(n_bf + 127) / 128, 128, 0, stream>>>(*pb, ref_y);
-  g_launches++;
+  if (!ref_ready) {
+    k_chief_rays<<<(n_bf + 127) / 128, 128, 0, stream>>>(*pb, ref_y);
+    g_launches++;
+  }
   if (use_rows_kernel(*pb, want_grad))      // many short rows: a warp per row, sums straight into `moments`
     return launch_spot_rows(*pb, want_grad, ref_y, moments, stream);
   if (want_grad && use_rev_kernel(*pb)) {   // the reversible fused pass (spot_rev.cuh)
@@ -2323,6 +2402,56 @@ int tl_stage_fwd(const TlLens *lens, float *mu, float *z, float *cy, float *half
   if (rc) return rc;
   if (!mu || !z || !cy || !half_epd) return fail(TL_ERR_INVALID, "NULL output of tl_stage_fwd%s");
   k_stage_fwd<<<lens->B, 128, 0, (cudaStream_t)stream_>>>(*lens, mu, z, cy, half_epd);
+  g_launches++;
+  TL_CHECK_CUDA(cudaGetLastError());
+  return TL_OK;
+}
+
+int tl_stage_ref(const TlLens *lens, const TlProblem *pb, float *mu, float *z, float *cy, float *half_epd,
+                 float *aim, int32_t allow_backward_rays, float *ref_y, void *stream_) {
+  int rc = validate_lens(lens);
+  if (rc) return rc;
+  if (!mu || !z || !cy || !half_epd) return fail(TL_ERR_INVALID, "NULL output of tl_stage_ref%s");
+  TlProblem none;
+  memset(&none, 0, sizeof(none));
+  if (ref_y) {
+    rc = validate(pb, TL_MAX_SURFACES_FWD);
+    if (rc) return rc;
+    if (is_general(*pb)) return fail(TL_ERR_INVALID, "tl_stage_ref: spherical lenses only%s");
+    if (pb->B != lens->B || pb->F != lens->F || pb->W != lens->W || pb->S != lens->L)
+      return fail(TL_ERR_INVALID, "tl_stage_ref: problem and lens sizes differ%s");
+  }
+  k_stage_ref<<<lens->B, 128, 0, (cudaStream_t)stream_>>>(*lens, ref_y ? *pb : none, mu, z, cy, half_epd, aim,
+                                                          allow_backward_rays, ref_y);
+  g_launches++;
+  TL_CHECK_CUDA(cudaGetLastError());
+  return TL_OK;
+}
+
+int tl_lens_spot_finalize(const double *moments, const float *ref_y, const TlLens *lens, int64_t P_total,
+                          const TlSpotOut *out, float *gnd, float *gv, void *stream_) {
+  int rc = validate_lens(lens);
+  if (rc) return rc;
+  if (!moments || !ref_y || !out || !out->rms || !out->rms_field || !out->gc || !out->gt || !out->gmu ||
+      !out->gz || !gnd || !gv || P_total < 1)
+    return fail(TL_ERR_INVALID, "bad argument to tl_lens_spot_finalize%s");
+  const int B = lens->B, F = lens->F, W = lens->W, S = lens->L;
+  if (S > TL_MAX_SURFACES_SPOT) return fail(TL_ERR_INVALID, "too many surfaces for tl_lens_spot_finalize%s");
+  if ((size_t)F * 3 * sizeof(double) > 40 * 1024) return fail(TL_ERR_INVALID, "too many fields%s");
+  const int n_acc = n_acc_of(MODE_SPOT_GRAD, S);
+  const size_t base = (size_t)F * 3 * sizeof(double);
+  const size_t staged = base + (size_t)F * W * n_acc * sizeof(double);
+  const double n_rays = (double)P_total * (double)W;
+  if (staged <= 160 * 1024) {
+    if (staged > 48 * 1024)
+      TL_CHECK_CUDA(cudaFuncSetAttribute((const void *)k_lens_finalize<true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged));
+    k_lens_finalize<true><<<B, 256, staged, (cudaStream_t)stream_>>>(moments, ref_y, B, F, W, S, n_rays, *out, *lens,
+                                                                     gnd, gv);
+  } else {
+    k_lens_finalize<false><<<B, 256, base, (cudaStream_t)stream_>>>(moments, ref_y, B, F, W, S, n_rays, *out, *lens,
+                                                                    gnd, gv);
+  }
   g_launches++;
   TL_CHECK_CUDA(cudaGetLastError());
   return TL_OK;

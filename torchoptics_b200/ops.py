@@ -636,7 +636,7 @@ class _Staged:
     every buffer alive for as long as the problem is in use."""
 
     def __init__(self, c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, aimed,
-                 p_begin=0, p_end=None, max_surfaces=64):
+                 p_begin=0, p_end=None, max_surfaces=64, want_ref=False):
         for name, val in (('c', c), ('t', t), ('nd', nd), ('v', v), ('hfov', hfov), ('epd', epd),
                           ('x', x_rel), ('y', y_rel)):
             nat.require_cuda(val, name)
@@ -655,18 +655,17 @@ class _Staged:
         self.keep = [a.detach().contiguous() for a in (c, t, nd, v, hfov, epd)]
         cc, tt, ndd, vv, hf, ep = self.keep
         self.mu = torch.empty((B, W, L), dtype=torch.float32, device=dev)
-        packed = torch.empty((2 * B + B * F,), dtype=torch.float32, device=dev)      # one allocation: z, half_epd, cy
-        self.z, self.half_epd, self.cy = packed[:B], packed[B:2 * B], packed[2 * B:].view(B, F)
+        # one allocation: z, half_epd, cy, (reference heights), (aiming map)
+        n_small = 2 * B + B * F + (B * F if want_ref else 0) + (B * F * W * 3 if aimed else 0)
+        packed = torch.empty((n_small,), dtype=torch.float32, device=dev)
+        self.z, self.half_epd, self.cy = packed[:B], packed[B:2 * B], packed[2 * B:2 * B + B * F].view(B, F)
+        at = 2 * B + B * F
+        self.ref_y = None
+        if want_ref:
+            self.ref_y = packed[at:at + B * F].view(B, F)
+            at += B * F
+        self.aim = packed[at:at + B * F * W * 3].view(B, F, W, 3) if aimed else None
         self.ln = tables.lens_struct(cc, tt, ndd, vv, hf, ep)
-        stream = nat.stream_ptr(dev)
-        nat.check(lib.tl_stage_fwd(ctypes.byref(self.ln), self.mu.data_ptr(), self.z.data_ptr(), self.cy.data_ptr(),
-                                   self.half_epd.data_ptr(), stream), 'tl_stage_fwd')
-        self.aim = None
-        if aimed:      # ray aiming (rtl:129-208) as one more kernel; the map is applied on load
-            self.aim = torch.empty((B, F, W, 3), dtype=torch.float32, device=dev)
-            nat.check(lib.tl_aim(ctypes.byref(self.ln), self.mu.data_ptr(), self.z.data_ptr(), self.cy.data_ptr(),
-                                 self.half_epd.data_ptr(), int(bool(allow_backward_rays)), self.aim.data_ptr(),
-                                 stream), 'tl_aim')
         self.xy = (x_rel.detach(), y_rel.detach())
         pb = nat.TlProblem()
         pb.aim = _ptr(self.aim)
@@ -682,6 +681,12 @@ class _Staged:
         pb.xy_scale = self.half_epd.data_ptr()
         self.pb = pb
         self.tables = tables
+        # staging, ray aiming (rtl:129-208; the map is applied on load) and the reference heights of the
+        # fused pass: ONE launch
+        nat.check(lib.tl_stage_ref(ctypes.byref(self.ln), ctypes.byref(pb), self.mu.data_ptr(), self.z.data_ptr(),
+                                   self.cy.data_ptr(), self.half_epd.data_ptr(), _ptr(self.aim),
+                                   int(bool(allow_backward_rays)), _ptr(self.ref_y), nat.stream_ptr(dev)),
+                  'tl_stage_ref')
 
     def chain_rule(self, gmu, gz, gc, gt, gnd, gv):
         """ADDS the gradients induced through mu and z to gc, gt, gnd, gv [B,L] (tl_stage_bwd)."""
@@ -721,44 +726,43 @@ def _lens_spot_core(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward
             st.pb.p_begin, st.pb.p_end = int(p_begin), int(p_end)
         else:
             st = _Staged(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, aimed, p_begin,
-                         p_end, max_surfaces=nat.MAX_SURFACES_SPOT if want_grad else 64)
+                         p_end, max_surfaces=nat.MAX_SURFACES_SPOT if want_grad else 64, want_ref=True)
         B, L, F, W, P = st.B, st.L, st.F, st.W, st.P
         pb = st.pb
         stream = nat.stream_ptr(dev)
         n_acc = lib.tl_spot_moment_count(L, int(want_grad))
         moments = torch.empty((B, F, W, n_acc), dtype=torch.float64, device=dev)
-        ref_y = torch.empty((B, F), dtype=torch.float32, device=dev)
         ws_bytes = lib.tl_spot_workspace(ctypes.byref(pb), int(want_grad))
         if ws_bytes == 0:
             nat.check(-1, 'tl_spot_workspace')
         ws = torch.empty((ws_bytes // 8,), dtype=torch.float64, device=dev)
-        nat.check(lib.tl_spot_accumulate(ctypes.byref(pb), int(want_grad), moments.data_ptr(),
-                                         ref_y.data_ptr(), ws.data_ptr(), ws_bytes, stream),
-                  'tl_spot_accumulate')
+        if st.ref_y is not None:
+            ref_y = st.ref_y
+            nat.check(lib.tl_spot_accumulate_ref(ctypes.byref(pb), int(want_grad), moments.data_ptr(),
+                                                 ref_y.data_ptr(), ws.data_ptr(), ws_bytes, stream),
+                      'tl_spot_accumulate_ref')
+        else:
+            ref_y = torch.empty((B, F), dtype=torch.float32, device=dev)
+            nat.check(lib.tl_spot_accumulate(ctypes.byref(pb), int(want_grad), moments.data_ptr(),
+                                             ref_y.data_ptr(), ws.data_ptr(), ws_bytes, stream),
+                      'tl_spot_accumulate')
         if world > 1:
             moments = reduce_moments(moments, group)
         rms = buffer('rms', (B,))
         rms_field = torch.empty((B, F), dtype=torch.float32, device=dev)
         gc = gt = gnd = gv = None
-        if want_grad:
-            gc, gt = buffer('gc', (B, L)), buffer('gt', (B, L))
-            gmu = torch.empty((B, W, L), dtype=torch.float32, device=dev)
-            gz = torch.empty((B,), dtype=torch.float32, device=dev)
+        if want_grad:      # finalize + chain rule to (c, t, nd, v): one launch
+            gc, gt, gnd, gv = buffer('gc', (B, L)), buffer('gt', (B, L)), buffer('gnd', (B, L)), buffer('gv', (B, L))
+            scratch = torch.empty((B * W * L + B,), dtype=torch.float32, device=dev)      # gmu, gz
             spot_out = nat.TlSpotOut(rms.data_ptr(), rms_field.data_ptr(), gc.data_ptr(), gt.data_ptr(),
-                                     gmu.data_ptr(), gz.data_ptr())
+                                     scratch.data_ptr(), scratch[B * W * L:].data_ptr())
+            nat.check(lib.tl_lens_spot_finalize(moments.data_ptr(), ref_y.data_ptr(), ctypes.byref(st.ln), P,
+                                                ctypes.byref(spot_out), gnd.data_ptr(), gv.data_ptr(), stream),
+                      'tl_lens_spot_finalize')
         else:
             spot_out = nat.TlSpotOut(rms.data_ptr(), rms_field.data_ptr(), None, None, None, None)
-        nat.check(lib.tl_spot_finalize(moments.data_ptr(), ref_y.data_ptr(), B, F, W, L, P,
-                                       int(want_grad), ctypes.byref(spot_out), stream), 'tl_spot_finalize')
-        if want_grad:
-            gnd, gv = buffer('gnd', (B, L)), buffer('gv', (B, L))
-            if (out.get('gnd') is not None and out.get('gv') is not None
-                    and gv.data_ptr() == gnd.data_ptr() + gnd.numel() * 4):
-                torch.as_strided(gnd, (2 * gnd.numel(),), (1,)).zero_()      # adjacent views: one fill
-            else:
-                gnd.zero_()
-                gv.zero_()
-            st.chain_rule(gmu, gz, gc, gt, gnd, gv)
+            nat.check(lib.tl_spot_finalize(moments.data_ptr(), ref_y.data_ptr(), B, F, W, L, P, 0,
+                                           ctypes.byref(spot_out), stream), 'tl_spot_finalize')
     return rms, rms_field, gc, gt, gnd, gv
 
 
