@@ -320,25 +320,13 @@ def main():
     step_stats = {'min': min(step_ms), 'median': statistics.median(step_ms), 'max': max(step_ms), 'rank': rank}
 
     note('kernel-only timing')
-    # ---- dominant kernel alone (tl_spot_accumulate), live CUDA events --------
-    # (replayed from a CUDA graph so that Python's launch preparation is not in the timing)
+    # ---- dominant kernel ALONE (k_spot_rev: one launch, no reference-height or row-reduction launch
+    # around it), live CUDA events on the launching stream, L2 flushed before every launch ----
     plain = [a.detach() for a in ray_args]
+    k_run = ops.spot_kernel_runner(*plain, shard=shard)
     for _ in range(3):
-        ops.spot_moments(*plain, shard=shard)
+        k_run()
     torch.cuda.synchronize()
-    k_run = lambda: ops.spot_moments(*plain, shard=shard)
-    try:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            k_run()
-        torch.cuda.current_stream().wait_stream(side)
-        k_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(k_graph):
-            k_run()
-        k_run = k_graph.replay
-    except Exception as exc:
-        print(f'[bench] kernel graph capture failed: {exc}', file=sys.stderr)
     k_starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     k_stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     for i in range(args.steps):
@@ -404,7 +392,7 @@ def main():
     roofline = {'bound': 'fp32_fma', 'achieved': achieved, 'peak': peak_tflops, 'unit': 'TFLOP/s',
                 'frac': achieved / peak_tflops,
                 'traffic': NCU_DRAM_BYTES_PER_LAUNCH if world == 1 else None,
-                'kernel': f'{ops.spot_kernel_name(*plain, shard=shard)} (+k_chief_rays, k_reduce_rows: ~2% of the time)',
+                'kernel': f'{ops.spot_kernel_name(*plain, shard=shard)} (that one launch alone)',
                 'kernel_ms': kernel_ms,
                 'flops_per_event': FLOPS_FWD + FLOPS_BWD,
                 'peak_source': f'{sms} SMs x 128 lanes x 2 flop x {sm_max_mhz:.0f} MHz '

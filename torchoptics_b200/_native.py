@@ -92,6 +92,8 @@ EXPORTS = {
     'tl_spot_moment_count_general': (ctypes.c_int32, [ctypes.c_int32, ctypes.c_int32]),
     'tl_spot_workspace': (ctypes.c_size_t, [ctypes.POINTER(TlProblem), ctypes.c_int32]),
     'tl_spot_kernel_name': (ctypes.c_char_p, [ctypes.POINTER(TlProblem), ctypes.c_int32]),
+    'tl_spot_kernel_only': (ctypes.c_int, [ctypes.POINTER(TlProblem), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                           ctypes.c_void_p]),
     'tl_spot_accumulate': (ctypes.c_int, [ctypes.POINTER(TlProblem), ctypes.c_int32, ctypes.c_void_p,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                           ctypes.c_void_p]),

@@ -24,9 +24,9 @@
 enum { ACC_REG = 0, ACC_TMEM = 1 };
 
 struct RevArgs {
-  double *partial;      // [total_warps, max_seg, n_acc]
+  double *partial;      // [rows, max_owners, n_acc]: row-major by (row, rank of the owning warp within the row)
   const float *ref_y;   // [B,F]
-  int groups_per_row, max_seg, n_acc;
+  int groups_per_row, max_owners, n_acc;
 };
 
 // Surface table of one (lens, wavelength): one 32-byte record per surface, so that a step of either
@@ -174,7 +174,10 @@ k_spot_rev(TlProblem pb, RevArgs args) {
   constexpr int NA = (ACC == ACC_REG) ? NS_MAX : 1;
   constexpr uint32_t kTmemCols = 512;
   const int S = pb.S;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // (a broadcast from lane 0: the compiler then knows the warp index -- and every table / TMEM address
+  // derived from it -- is warp-uniform and keeps them in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const bool allow_backward = pb.allow_backward_rays != 0;
   const int n_acc = args.n_acc;
 
@@ -209,7 +212,7 @@ k_spot_rev(TlProblem pb, RevArgs args) {
   float acc_z = 0.f, wac_z = 0.f, m_s1 = 0.f, m_s2 = 0.f, m_n = 0.f;
   RevTable tab;
   float y0 = 0.f, xy_scale = 1.0f;
-  int row = -1, seg = 0, b = 0, f = 0, w = 0;
+  int row = -1, b = 0, f = 0, w = 0;
 
   auto reset = [&]() {
     if constexpr (ACC == ACC_REG) {
@@ -229,7 +232,10 @@ k_spot_rev(TlProblem pb, RevArgs args) {
 
   // the warp's sums of this row segment -> one fp64 partial row
   auto flush = [&]() {
-    double *dst = args.partial + ((int64_t)wg * args.max_seg + seg) * n_acc;
+    // partial row of (row, this warp's rank among the warps that own a piece of the row): the reducer
+    // then sums a row's partials from consecutive memory, without recomputing any slice bounds
+    const int64_t first_owner = owner_of((int64_t)row * args.groups_per_row, total, n_warps);
+    double *dst = args.partial + ((int64_t)row * args.max_owners + (wg - first_owner)) * n_acc;
     if constexpr (ACC == ACC_REG) {
       constexpr int kPerBatch = 5;             // 6 values per surface, five surfaces per transpose
 #pragma unroll
@@ -272,7 +278,6 @@ k_spot_rev(TlProblem pb, RevArgs args) {
       dst[6 * S + 3] = (double)t3;
       dst[6 * S + 4] = (double)t4;
     }
-    ++seg;
   };
 
   for (int64_t g = g_begin; g < g_end; ++g) {
@@ -318,13 +323,14 @@ k_spot_rev(TlProblem pb, RevArgs args) {
     if (pb.arith == TL_ARITH_GUARDED) {
       Ray<V> ray{x, y, z, cx, cy, fast_cz0(cx, cy)};
       V min_cos2(1.0f), min_cz(1.0f), min_travel(3.0e38f);
-      for (int k = 0; k < S; ++k) {
-        const float4 s0 = *reinterpret_cast<const float4 *>(&tab.s[k]);           // c, t, mu, mu2
-        const float4 s1 = *reinterpret_cast<const float4 *>(&tab.s[k].om2);       // om2, rmu, live, live_prev
+      const float4 *rec = reinterpret_cast<const float4 *>(tab.s);                // running pointers: no index
+      f2 *slot = state;                                                           // multiplications in the loop
+      for (int k = 0; k < S; ++k, rec += 2, slot += NCOMP * 64) {
+        const float4 s0 = rec[0];           // c, t, mu, mu2
+        const float4 s1 = rec[1];           // om2, rmu, live, live_prev
         V travel;
         Parked<V> pk;
         fast_surface_rev(ray, V(s0.x), V(s0.z), V(s0.w), V(s1.x), V(s0.y), min_cos2, min_cz, travel, pk);
-        f2 *slot = state + (size_t)k * NCOMP * 64;
         slot[0] = pk.dist.a;
         slot[32] = pk.dist.b;
         slot[64] = pk.ci.a;
@@ -385,10 +391,9 @@ k_spot_rev(TlProblem pb, RevArgs args) {
     // (a thread none of whose rays is alive still runs the sweep -- the accumulator accesses are
     // collective -- but adds nothing: its state may hold non-finite values)
     SweepRev<V> sw = sweep_begin_rev(pre, x_img, y_img, V(0.f), alive, V(0.f), V(0.f));
-    auto step = [&](int k) {
-      const float4 s0 = *reinterpret_cast<const float4 *>(&tab.s[k]);
-      const float4 s1 = *reinterpret_cast<const float4 *>(&tab.s[k].om2);
-      const f2 *slot = state + (size_t)k * NCOMP * 64;
+    auto step = [&](const float4 *rec, const f2 *slot) {
+      const float4 s0 = rec[0];
+      const float4 s1 = rec[1];
       const V dist(slot[0], slot[32]), ci(slot[64], slot[96]);
       if constexpr (NCOMP > 2) {
         const V co(slot[128], slot[160]);
@@ -401,7 +406,7 @@ k_spot_rev(TlProblem pb, RevArgs args) {
 #pragma unroll
       for (int k = NS_MAX - 1; k >= 0; --k) {
         if (k >= S) continue;
-        const SurfaceGrad<V> gr = step(k);
+        const SurfaceGrad<V> gr = step(reinterpret_cast<const float4 *>(tab.s) + 2 * k, state + (size_t)k * NCOMP * 64);
         if (any_live) {
           acc[0][k] = lane_dot(wgt, gr.c, acc[0][k]);
           acc[1][k] += lane_sum(gr.c);
@@ -412,11 +417,14 @@ k_spot_rev(TlProblem pb, RevArgs args) {
         }
       }
     } else {
-      for (int k = S - 1; k >= 0; --k) {
+      const float4 *rec = reinterpret_cast<const float4 *>(tab.s) + 2 * (S - 1);
+      const f2 *slot = state + (size_t)(S - 1) * NCOMP * 64;
+      uint32_t tcol = tacc + 6 * (S - 1);
+      for (int k = S - 1; k >= 0; --k, rec -= 2, slot -= NCOMP * 64, tcol -= 6) {
         uint32_t a4[4], a2[2];
-        tm_ld4(tacc + 6 * k, a4);
-        tm_ld2(tacc + 6 * k + 4, a2);
-        const SurfaceGrad<V> gr = step(k);
+        tm_ld4(tcol, a4);
+        tm_ld2(tcol + 4, a2);
+        const SurfaceGrad<V> gr = step(rec, slot);
         tm_wait_ld6(a4, a2);
         float s0 = __uint_as_float(a4[0]), s1 = __uint_as_float(a4[1]), s2 = __uint_as_float(a4[2]),
               s3 = __uint_as_float(a4[3]), s4 = __uint_as_float(a2[0]), s5 = __uint_as_float(a2[1]);
@@ -428,8 +436,8 @@ k_spot_rev(TlProblem pb, RevArgs args) {
           s4 = lane_dot(wgt, gr.mu, s4);
           s5 += lane_sum(gr.mu);
         }
-        tm_st4(tacc + 6 * k, s0, s1, s2, s3);
-        tm_st2(tacc + 6 * k + 4, s4, s5);
+        tm_st4(tcol, s0, s1, s2, s3);
+        tm_st2(tcol + 4, s4, s5);
       }
       tm_wait_st();
     }
@@ -450,12 +458,44 @@ k_spot_rev(TlProblem pb, RevArgs args) {
   }
 }
 
+// partial[row, owner rank, n_acc] -> dst[row, n_acc], fixed summation order (rank order = pupil order).
+// One CTA per row, a thread per slot: a row's partials are consecutive, the loads of a warp
+// coalesce and four are in flight per thread.  (The first version walked [warp, segment] records with
+// two 64-bit divisions per term: 23 us of a 270 us step.)
+__global__ void __launch_bounds__(128)
+k_reduce_owner_rows(const double *partial, double *dst, int n_rows, int groups_per_row, int64_t n_warps, int max_owners,
+                    int n_acc) {
+  __shared__ double part[4][256];                  // (n_acc <= 6 * 32 + 5)
+  const int row = blockIdx.x;
+  const int lane = threadIdx.x & 31, quarter = threadIdx.x >> 5;
+  const int64_t total = (int64_t)n_rows * groups_per_row;
+  const int64_t first = owner_of((int64_t)row * groups_per_row, total, n_warps);
+  const int64_t last = owner_of((int64_t)(row + 1) * groups_per_row - 1, total, n_warps);
+  const int count = (int)(last - first + 1);
+  const bool sparse = n_warps > total;             // some warps own nothing: their records were never written
+  const double *src = partial + (int64_t)row * max_owners * n_acc;
+  // warp `quarter` sums the owners quarter, quarter + 4, ... of every slot (all loads independent), then
+  // the four partial sums are added in a fixed order
+  for (int slot = lane; slot < n_acc; slot += 32) {
+    double acc = 0.0;
+    for (int q = quarter; q < count; q += 4) {
+      const int64_t wgq = first + q;
+      if (sparse && !(total * (wgq + 1) / n_warps > total * wgq / n_warps)) continue;
+      acc += src[(int64_t)q * n_acc + slot];
+    }
+    part[quarter][slot] = acc;
+  }
+  __syncthreads();
+  for (int slot = threadIdx.x; slot < n_acc; slot += blockDim.x)
+    dst[(int64_t)row * n_acc + slot] = (part[0][slot] + part[1][slot]) + (part[2][slot] + part[3][slot]);
+}
+
 typedef void (*RevKernelPtr)(TlProblem, RevArgs);
 
 struct RevPlan {
   RevKernelPtr kernel = nullptr;
   const char *name = "";
-  int n_warps_cta = 8, n_blocks = 1, groups_per_row = 1, max_seg = 1, n_acc = 0;
+  int n_warps_cta = 8, n_blocks = 1, groups_per_row = 1, max_owners = 1, n_acc = 0;
   size_t smem = 0, partial_bytes = 0;
 };
 
@@ -473,15 +513,16 @@ int plan_rev(const TlProblem &pb, RevPlan &pl) {
   int rc = device_info(info);
   if (rc) return rc;
   const int S = pb.S;
-  // in the order measured on the B200 (config 2, ms per launch, tools/rev_variants.py): reg8 0.254,
-  // tmem12c2 0.258, tmem8 0.262, tmem12 0.263, tmem16 0.265 -- residency does NOT matter (8, 12 and 16
-  // warps per SM are within 4 %): the pass is bound by register-operand bandwidth (tools/microbench4.cu)
+  // in the order measured on the B200 (config 2; that kernel alone, CUDA events, L2 flushed, bench.py):
+  // tmem16 0.2115 ms, tmem12c2 0.2145, tmem12 0.2187, tmem8 0.2198, reg8 0.2253 (round 1's k_trace_adj:
+  // 0.289).  Residency matters little (8 -> 16 warps per SM: 4 %): the pass is bound by register-operand
+  // bandwidth (tools/microbench4.cu), so the variant with the fewest instructions per event wins.
   const RevVariant variants[] = {
-      {"reg8", S <= 12 ? k_spot_rev<12, 8, ACC_REG, 3> : k_spot_rev<16, 8, ACC_REG, 3>, 8, 3},
-      {"tmem12c2", k_spot_rev<16, 12, ACC_TMEM, 2>, 12, 2},
-      {"tmem8", k_spot_rev<16, 8, ACC_TMEM, 3>, 8, 3},
-      {"tmem12", k_spot_rev<16, 12, ACC_TMEM, 3>, 12, 3},
       {"tmem16", k_spot_rev<16, 16, ACC_TMEM, 2>, 16, 2},
+      {"tmem12c2", k_spot_rev<16, 12, ACC_TMEM, 2>, 12, 2},
+      {"tmem12", k_spot_rev<16, 12, ACC_TMEM, 3>, 12, 3},
+      {"tmem8", k_spot_rev<16, 8, ACC_TMEM, 3>, 8, 3},
+      {"reg8", S <= 12 ? k_spot_rev<12, 8, ACC_REG, 3> : k_spot_rev<16, 8, ACC_REG, 3>, 8, 3},
   };
   const char *env = getenv("TL_REV");
   const RevVariant *pick = nullptr;
@@ -511,9 +552,13 @@ int plan_rev(const TlProblem &pb, RevPlan &pl) {
   if (n_blocks > need) n_blocks = need;
   pl.n_blocks = (int)n_blocks;
   const int64_t n_warps = n_blocks * nw;
-  const int64_t len = (total + n_warps - 1) / n_warps;          // longest slice
-  pl.max_seg = (int)((len - 1 + pl.groups_per_row - 1) / pl.groups_per_row + 1);
-  pl.partial_bytes = align8((size_t)n_warps * pl.max_seg * pl.n_acc * sizeof(double));
+  // warps that own a piece of one row: a row is groups_per_row consecutive items, a slice at least
+  // floor(total / n_warps) of them (when that is 0, some slices are empty: the reducer checks)
+  const int64_t shortest = total / n_warps;
+  const int64_t owners = shortest > 0 ? (pl.groups_per_row + shortest - 1) / shortest + 1
+                                      : 2 * (int64_t)pl.groups_per_row + 2;      // (ranks count the empty slices too)
+  pl.max_owners = (int)(owners < n_warps ? owners : n_warps);
+  pl.partial_bytes = align8((size_t)pb.B * pb.F * pb.W * pl.max_owners * pl.n_acc * sizeof(double));
   return TL_OK;
 }
 
@@ -525,7 +570,7 @@ int launch_spot_rev(const TlProblem &pb, const RevPlan &pl, const float *ref_y, 
   args.partial = partial;
   args.ref_y = ref_y;
   args.groups_per_row = pl.groups_per_row;
-  args.max_seg = pl.max_seg;
+  args.max_owners = pl.max_owners;
   args.n_acc = pl.n_acc;
   TlProblem pb_copy = pb;
   void *params[] = {(void *)&pb_copy, (void *)&args};
@@ -533,9 +578,8 @@ int launch_spot_rev(const TlProblem &pb, const RevPlan &pl, const float *ref_y, 
                                  pl.smem, stream));
   g_launches++;
   const int rows = pb.B * pb.F * pb.W;
-  const int64_t n = (int64_t)rows * pl.n_acc;
-  k_reduce_rows<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(partial, moments, rows, pl.groups_per_row,
-                                                                 pl.n_blocks * pl.n_warps_cta, pl.max_seg, pl.n_acc);
+  k_reduce_owner_rows<<<rows, 128, 0, stream>>>(partial, moments, rows, pl.groups_per_row,
+                                                pl.n_blocks * pl.n_warps_cta, pl.max_owners, pl.n_acc);
   g_launches++;
   TL_CHECK_CUDA(cudaGetLastError());
   return TL_OK;

@@ -438,16 +438,22 @@ k_trace_fwd_pw(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
 // rank -- it depends on nothing but the prescription and the (whole, unsharded) pupil array and is
 // computed by the same instruction sequence everywhere.  (A member of the bundle rather than the
 // point (0, 0): a bundle that does not surround the pupil centre stays well centred too.)
-__device__ __forceinline__ void chief_ray_one(const TlProblem &pb, int i, float *ref_y) {
+// (c_row / t_row / mu_row: the lens' surface rows and its index ratios at wavelength 0, wherever the
+// caller has them closest -- global memory by default)
+__device__ __forceinline__ void chief_ray_one(const TlProblem &pb, int i, float *ref_y, const float *c_row = nullptr,
+                                              const float *t_row = nullptr, const float *mu_row = nullptr) {
   const int b = i / pb.F, f = i % pb.F, S = pb.S;
+  if (!c_row) c_row = pb.c + (int64_t)b * S;
+  if (!t_row) t_row = pb.t + (int64_t)b * S;
+  if (!mu_row) mu_row = pb.mu + ((int64_t)b * pb.W) * S;
   const float cx = pb.cx.ptr[offset_of(pb.cx, b, f, 0, 0)], cy = pb.cy.ptr[offset_of(pb.cy, b, f, 0, 0)];
   float x0, y0;
   load_pupil_point(pb, b, f, 0, 0, pb.xy_scale ? pb.xy_scale[b] : 1.0f, x0, y0);
   Ray<float> r{x0, y0, pb.z.ptr[offset_of(pb.z, b, f, 0, 0)], cx, cy, fast_cz0(cx, cy)};
   float min_cos2 = 1.0f, travel;
   for (int k = 0; k < S; ++k) {
-    const float mu = pb.mu[((int64_t)b * pb.W) * S + k];
-    fast_surface(r, pb.c[(int64_t)b * S + k], mu, mu * mu, pb.t[(int64_t)b * S + k], min_cos2, travel);
+    const float mu = mu_row[k];
+    fast_surface(r, c_row[k], mu, mu * mu, t_row[k], min_cos2, travel);
   }
   fast_image(r);
   ref_y[i] = (min_cos2 > kGuard && fabsf(r.y) < 3.0e38f) ? r.y : 0.f;
@@ -1019,7 +1025,16 @@ __device__ __forceinline__ void spot_finalize_lens(const double *mom_global, con
   const double *mom = mom_global + (int64_t)b * F * W * n_acc;    // this lens' rows
   if (STAGED) {
     double *rows = sh + 3 * F;
-    for (int i = threadIdx.x; i < F * W * n_acc; i += blockDim.x) rows[i] = mom[i];
+    const int n = F * W * n_acc, bd = blockDim.x;
+    int i = threadIdx.x;
+    for (; i + 7 * bd < n; i += 8 * bd) {      // eight loads in flight per thread: one round trip, not eight
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = mom[i + u * bd];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) rows[i + u * bd] = v[u];
+    }
+    for (; i < n; i += bd) rows[i] = mom[i];
     __syncthreads();
     mom = rows;
   }
@@ -1235,14 +1250,59 @@ __device__ __forceinline__ Abcd slot_matrix(const TlLens &ln, int b, int s, floa
   return Abcd{1.0f + power * tt, ratio * tt, power, ratio};
 }
 
+// The small kernels around the fused pass are single-CTA chains of dependent loads: with the lens in
+// global memory every step of a serial loop pays a ~0.6 us round trip (k_stage_ref 8 us, the finalize
+// kernel 21 us of a 270 us step).  This copies lens b -- c, t, nd, v, the two masks, its stop index,
+// field angle and pupil diameter, and the wavelength list -- into shared memory in ONE parallel round
+// trip and returns a view of it: a TlLens whose pointers are biased so that the usual [b * L + s] /
+// [b] / [w] indexing lands in the copy.  Ends with a barrier.
+struct LensCopy {
+  float f[4 * kStageMaxSurfaces + 2 + 16];      // c, t, nd, v, hfov, epd, wavelengths (first 16)
+  uint8_t m[2 * kStageMaxSurfaces];
+  int stop;
+};
+
+__device__ __forceinline__ TlLens lens_in_shared(const TlLens &ln, int b, LensCopy &buf) {
+  const int L = ln.L;
+  for (int i = threadIdx.x; i < 4 * L; i += blockDim.x) {
+    const int which = i / L, s_ = i % L;
+    const float *src = which == 0 ? ln.c : which == 1 ? ln.t : which == 2 ? ln.nd : ln.v;
+    buf.f[i] = src[(int64_t)b * L + s_];
+  }
+  for (int i = threadIdx.x; i < 2 * L; i += blockDim.x)
+    buf.m[i] = (i < L ? ln.mask : ln.mask_g)[(int64_t)b * L + i % L];
+  if (threadIdx.x == 0) {
+    buf.stop = ln.stop_idx[b];
+    buf.f[4 * L] = ln.hfov[b];
+    buf.f[4 * L + 1] = ln.epd[b];
+  }
+  for (int w = threadIdx.x; w < ln.W && w < 16; w += blockDim.x) buf.f[4 * L + 2 + w] = ln.wavelengths[w];
+  __syncthreads();
+  TlLens v = ln;
+  const int64_t bias = (int64_t)b * L;
+  v.c = buf.f - bias;
+  v.t = buf.f + L - bias;
+  v.nd = buf.f + 2 * L - bias;
+  v.v = buf.f + 3 * L - bias;
+  v.mask = buf.m - bias;
+  v.mask_g = buf.m + L - bias;
+  v.stop_idx = &buf.stop - b;
+  v.hfov = buf.f + 4 * L - b;
+  v.epd = buf.f + 4 * L + 1 - b;
+  if (ln.W <= 16) v.wavelengths = buf.f + 4 * L + 2;
+  return v;
+}
+
 __device__ __forceinline__ void stage_fwd_lens(const TlLens &ln, int b, float *mu, float *z, float *cy,
-                                               float *half_epd) {
+                                               float *half_epd, float *mu0_shared = nullptr) {
   if (threadIdx.x == 1 % blockDim.x) half_epd[b] = ln.epd[b] * 0.5f;
   for (int i = threadIdx.x; i < ln.W * ln.L; i += blockDim.x) {
     const int w = i / ln.L, s = i % ln.L;
     const float wl = ln.wavelengths[w];
     const float n_in = (s == 0) ? 1.0f : index_at(ln, b, s - 1, wl, nullptr, nullptr);
-    mu[((int64_t)b * ln.W + w) * ln.L + s] = n_in / index_at(ln, b, s, wl, nullptr, nullptr);
+    const float ratio = n_in / index_at(ln, b, s, wl, nullptr, nullptr);
+    mu[((int64_t)b * ln.W + w) * ln.L + s] = ratio;
+    if (mu0_shared && w == 0) mu0_shared[s] = ratio;      // (the reference-height rays run at wavelength 0)
   }
   for (int f = threadIdx.x; f < ln.F; f += blockDim.x)
     cy[(int64_t)b * ln.F + f] = sinf(ln.hfov[b] * ln.rel_fields[f]);
@@ -1347,18 +1407,22 @@ __global__ void k_aim(TlLens ln, const float *mu, const float *z, const float *c
 __global__ void __launch_bounds__(128)
 k_stage_ref(TlLens ln, TlProblem pb, float *mu, float *z, float *cy, float *half_epd, float *aim,
             int allow_backward, float *ref_y) {
+  __shared__ LensCopy copy;
+  __shared__ float mu0[kStageMaxSurfaces];
   const int b = blockIdx.x;
-  stage_fwd_lens(ln, b, mu, z, cy, half_epd);
+  const TlLens lens = lens_in_shared(ln, b, copy);
+  stage_fwd_lens(lens, b, mu, z, cy, half_epd, mu0);
   __threadfence_block();
   __syncthreads();
   if (aim) {
     for (int i = threadIdx.x; i < ln.F * ln.W; i += blockDim.x)
-      aim_one(ln, mu, z, cy, half_epd, allow_backward, aim, b * ln.F * ln.W + i);
+      aim_one(lens, mu, z, cy, half_epd, allow_backward, aim, b * ln.F * ln.W + i);
     __threadfence_block();
     __syncthreads();
   }
-  if (ref_y)
-    for (int f = threadIdx.x; f < pb.F; f += blockDim.x) chief_ray_one(pb, b * pb.F + f, ref_y);
+  if (ref_y)      // (pb.c / pb.t are the lens' own rows: the shared copy serves the per-surface loop)
+    for (int f = threadIdx.x; f < pb.F; f += blockDim.x)
+      chief_ray_one(pb, b * pb.F + f, ref_y, copy.f, copy.f + ln.L, mu0);
 }
 
 // Chain rule of the staging for lens b: `gmu_b` = d loss / d mu[b] ([W,L]), `gz_b` = d loss / d z[b]; ADDS
@@ -1442,8 +1506,9 @@ __global__ void k_lens_finalize(const double *mom_global, const float *ref_y, in
     gv[(int64_t)b * ln.L + s_] = 0.f;
   }
   __threadfence_block();
-  __syncthreads();
-  stage_bwd_lens(ln, b, out.gmu + (int64_t)b * ln.W * ln.L, out.gz[b], out.gc, out.gt, gnd, gv);
+  __shared__ LensCopy copy;
+  const TlLens lens = lens_in_shared(ln, b, copy);        // (ends with the barrier the phases need)
+  stage_bwd_lens(lens, b, out.gmu + (int64_t)b * ln.W * ln.L, out.gz[b], out.gc, out.gt, gnd, gv);
 }
 
 // --------------------------------------------------------------------------
@@ -2299,6 +2364,34 @@ const char *tl_spot_kernel_name(const TlProblem *pb, int32_t want_grad) {
     return text;
   }
   return want_grad ? "k_trace_adj<SPOT_GRAD>" : "k_trace_adj<SPOT_EVAL,f4>";
+}
+
+// Diagnostics for bench.py's roofline line: the dominant kernel of the fused pass ALONE (the chief-ray
+// and row-reduction launches that tl_spot_accumulate adds around it are left out), so that CUDA
+// events around this call time exactly one kernel.  `ref_y` must hold the reference heights.
+int tl_spot_kernel_only(const TlProblem *pb, const float *ref_y, void *workspace, size_t workspace_bytes,
+                        void *stream_) {
+  int rc = validate(pb, TL_MAX_SURFACES_SPOT);
+  if (rc) return rc;
+  if (!ref_y || !workspace) return fail(TL_ERR_INVALID, "tl_spot_kernel_only: NULL argument%s");
+  if (is_general(*pb) || use_rows_kernel(*pb, 1) || !use_rev_kernel(*pb))
+    return fail(TL_ERR_INVALID, "tl_spot_kernel_only: this problem does not take k_spot_rev%s");
+  RevPlan pl;
+  rc = plan_rev(*pb, pl);
+  if (rc) return rc;
+  if (workspace_bytes < pl.partial_bytes) return fail(TL_ERR_WORKSPACE, "workspace too small%s");
+  RevArgs args;
+  args.partial = (double *)workspace;
+  args.ref_y = ref_y;
+  args.groups_per_row = pl.groups_per_row;
+  args.max_owners = pl.max_owners;
+  args.n_acc = pl.n_acc;
+  TlProblem pb_copy = *pb;
+  void *params[] = {(void *)&pb_copy, (void *)&args};
+  TL_CHECK_CUDA(cudaLaunchKernel((const void *)pl.kernel, dim3(pl.n_blocks), dim3(pl.n_warps_cta * 32), params,
+                                 pl.smem, (cudaStream_t)stream_));
+  g_launches++;
+  return TL_OK;
 }
 
 int32_t tl_penalty_moment_count(int32_t S) { return 3 * S + 2; }

@@ -397,6 +397,25 @@ def spot_kernel_name(x, y, z, cx, cy, c, t, mu, mask, want_grad=True, shard=(0, 
     return nat.load().tl_spot_kernel_name(ctypes.byref(pb), int(want_grad)).decode()
 
 
+def spot_kernel_runner(x, y, z, cx, cy, c, t, mu, mask, shard=(0, 1)):
+    """A closure that launches the dominant kernel of the fused pass ALONE on the current stream
+    (tl_spot_kernel_only; bench.py times it with CUDA events for its roofline line)."""
+    lay = _Layout(x, y, z, cx, cy, c, t, mu, mask)
+    p_begin, p_end = pupil_slice(lay.P, *shard)
+    lib = nat.load()
+    with torch.cuda.device(lay.device):
+        _, ref_y = _accumulate(lay, True, nat.ARITH_GUARDED, True, p_begin, p_end)
+        pb = lay.problem(True, nat.ARITH_GUARDED, p_begin, p_end)
+        ws_bytes = lib.tl_spot_workspace(ctypes.byref(pb), 1)
+        ws = torch.empty((ws_bytes // 8,), dtype=torch.float64, device=lay.device)
+
+    def run():
+        nat.check(lib.tl_spot_kernel_only(ctypes.byref(pb), ref_y.data_ptr(), ws.data_ptr(), ws_bytes,
+                                          nat.stream_ptr(lay.device)), 'tl_spot_kernel_only')
+    run.keep = (lay, ref_y, ws)
+    return run
+
+
 class _SpotRms(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays, arith, shard, group,
