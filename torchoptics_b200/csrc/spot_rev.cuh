@@ -478,10 +478,14 @@ k_reduce_owner_rows(const double *partial, double *dst, int n_rows, int groups_p
   // the four partial sums are added in a fixed order
   for (int slot = lane; slot < n_acc; slot += 32) {
     double acc = 0.0;
-    for (int q = quarter; q < count; q += 4) {
-      const int64_t wgq = first + q;
-      if (sparse && !(total * (wgq + 1) / n_warps > total * wgq / n_warps)) continue;
-      acc += src[(int64_t)q * n_acc + slot];
+    if (!sparse) {
+#pragma unroll 8
+      for (int q = quarter; q < count; q += 4) acc += src[(int64_t)q * n_acc + slot];      // (loads in flight together)
+    } else {
+      for (int q = quarter; q < count; q += 4) {
+        const int64_t wgq = first + q;
+        if (total * (wgq + 1) / n_warps > total * wgq / n_warps) acc += src[(int64_t)q * n_acc + slot];
+      }
     }
     part[quarter][slot] = acc;
   }

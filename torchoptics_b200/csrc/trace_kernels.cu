@@ -1501,14 +1501,30 @@ __global__ void k_lens_finalize(const double *mom_global, const float *ref_y, in
                                 double n_rays, TlSpotOut out, TlLens ln, float *gnd, float *gv) {
   spot_finalize_lens<STAGED>(mom_global, ref_y, B, F, W, S, n_rays, 1, out);
   const int b = blockIdx.x;
-  for (int s_ = threadIdx.x; s_ < ln.L; s_ += blockDim.x) {
-    gnd[(int64_t)b * ln.L + s_] = 0.f;
-    gv[(int64_t)b * ln.L + s_] = 0.f;
-  }
-  __threadfence_block();
+  // The chain rule's reverse sweep over the surfaces in front of the stop is serial (thread 0) and adds
+  // into gc / gt / gnd as it goes: on global memory every `+=` is a ~0.7 us round trip of a dependent
+  // chain (12 us of a 240 us step).  It runs on a shared-memory copy of the four gradient rows instead.
+  __shared__ float rows4[4][kStageMaxSurfaces];
   __shared__ LensCopy copy;
+  __threadfence_block();
+  __syncthreads();
+  const int64_t bias = (int64_t)b * ln.L;
+  for (int s_ = threadIdx.x; s_ < ln.L; s_ += blockDim.x) {
+    rows4[0][s_] = out.gc[bias + s_];
+    rows4[1][s_] = out.gt[bias + s_];
+    rows4[2][s_] = 0.f;
+    rows4[3][s_] = 0.f;
+  }
   const TlLens lens = lens_in_shared(ln, b, copy);        // (ends with the barrier the phases need)
-  stage_bwd_lens(lens, b, out.gmu + (int64_t)b * ln.W * ln.L, out.gz[b], out.gc, out.gt, gnd, gv);
+  stage_bwd_lens(lens, b, out.gmu + (int64_t)b * ln.W * ln.L, out.gz[b], rows4[0] - bias, rows4[1] - bias,
+                 rows4[2] - bias, rows4[3] - bias);
+  __syncthreads();
+  for (int s_ = threadIdx.x; s_ < ln.L; s_ += blockDim.x) {
+    out.gc[bias + s_] = rows4[0][s_];
+    out.gt[bias + s_] = rows4[1][s_];
+    gnd[bias + s_] = rows4[2][s_];
+    gv[bias + s_] = rows4[3][s_];
+  }
 }
 
 // --------------------------------------------------------------------------
