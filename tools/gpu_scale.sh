@@ -10,7 +10,7 @@ run() {   # steps warmup tag
   python - <<PY
 import json
 try:
-    d=json.load(open('gpurun_out/bench_r2_n${N}_$3.json'))
+    d=json.loads(open('gpurun_out/bench_r2_n${N}_$3.json').read().strip().splitlines()[-1])
     print('N=$N $3: value %.1f G  ms %.4f  e2e %.1f G (%.4f ms)  step_ms %s  %s' % (d['value']/1e9, d['ms_per_step'], d['e2e']['value']/1e9, d['e2e']['ms_per_step'], d.get('step_ms'), d.get('warning','')))
 except Exception as e:
     print('no line', e); print(open('gpurun_out/bench_r2_n${N}_$3.err').read()[-1500:])

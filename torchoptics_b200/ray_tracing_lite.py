@@ -52,9 +52,55 @@ def meridional_uniform(tensor, n_rays, device='cuda'):
 
 
 def sagittal_uniform(tensor, n_rays, device='cuda'):
-    """``n_rays`` equidistant points on the pupil's x axis (rt_tf:368-375)."""
-    x = torch.linspace(-1., 1., n_rays, device=device).reshape(1, 1, -1, 1)
+    """``n_rays`` equidistant points on the POSITIVE half of the pupil's x axis, 0 ... 1
+    (rt_tf:368-375; the system is symmetric about the meridional plane)."""
+    x = torch.linspace(0., 1., n_rays, device=device).reshape(1, 1, -1, 1)
     return x, torch.zeros_like(x)
+
+
+def _half_shells(n_r, n_i):
+    """Shell index and polar angle of the (n_r ** 2) * n_i points both half-pupil samplers share
+    (rt_tf:425-428, :440-445): shell i carries n_i * (2 i + 1) points, equidistant in angle over the
+    right half circle (-pi/2, pi/2)."""
+    per_shell = [n_i * (2 * i + 1) for i in range(n_r)]
+    shell = np.array([i for i in range(n_r) for _ in range(per_shell[i])])
+    theta = np.array([(j / n - 0.5) * np.pi for n in per_shell for j in (np.arange(n) + 0.5)])
+    return shell, theta
+
+
+def _points(r, theta, device):
+    x = torch.from_numpy((r * np.cos(theta)).astype(np.float32)).to(device)
+    y = torch.from_numpy((r * np.sin(theta)).astype(np.float32)).to(device)
+    return x.reshape(1, 1, -1, 1), y.reshape(1, 1, -1, 1)
+
+
+def skew_uniform_half_equidistant(tensor, n_r, n_i, device='cuda'):
+    """(n_r ** 2) * n_i points spanning the right half of the pupil uniformly: shell i at radius
+    (i + 1/2) / n_r (rt_tf:421-433)."""
+    shell, theta = _half_shells(n_r, n_i)
+    return _points(((np.arange(n_r) + 0.5) / n_r)[shell], theta, device)
+
+
+def skew_uniform_half_jittered(tensor, n_r, n_i, device='cuda'):
+    """The same shells with the radius alternating between the inner and the outer edge of each shell,
+    so that the pupil rim is sampled (rt_tf:436-451) -- the default sampler of the reference's
+    ``RaytracedOptics`` (optics_simulator_lite.py:360)."""
+    shell, theta = _half_shells(n_r, n_i)
+    inner = np.linspace(0, 1, n_r * 2)[::2]
+    step = 1 / (2 * n_r - 1)
+    r = inner[shell] + step * ((np.arange(len(shell)) + shell) % 2)
+    return _points(r, theta, device)
+
+
+def skew_inner_square_half(tensor, n_y, _=None, device='cuda'):
+    """n_y x n_y grid on the right half of the square inscribed in the pupil (rt_tf:454-465):
+    x in (0, 1/sqrt 2], y in [-1/sqrt 2, 1/sqrt 2], row-major in y."""
+    x = (np.linspace(-1, 1, n_y * 2)[-n_y:] / np.sqrt(2)).astype(np.float32)
+    y = (np.linspace(-1, 1, n_y) / np.sqrt(2)).astype(np.float32)
+    xx = np.broadcast_to(x[None, :], (n_y, n_y)).reshape(-1).copy()
+    yy = np.broadcast_to(y[:, None], (n_y, n_y)).reshape(-1).copy()
+    return (torch.from_numpy(xx).to(device).reshape(1, 1, -1, 1),
+            torch.from_numpy(yy).to(device).reshape(1, 1, -1, 1))
 
 
 def circle(tensor, n_r, n_theta, default_device='cuda'):
@@ -87,7 +133,7 @@ def circle_pseudo_random(tensor, n_r, n_theta, device='cuda'):
 
 def circle_outer_edge_uniform(tensor, n_rays, device='cuda'):
     """``n_rays`` points on the pupil rim (rt_tf:468-476)."""
-    angle = torch.arange(n_rays, dtype=torch.float32, device=device) * (2 * math.pi / n_rays)
+    angle = torch.from_numpy(np.linspace(0, 2 * np.pi, n_rays, endpoint=False, dtype=np.float32)).to(device)
     return torch.cos(angle).reshape(1, 1, -1, 1), torch.sin(angle).reshape(1, 1, -1, 1)
 
 
@@ -197,13 +243,14 @@ def compute_last_curvature(structures, c, t, nd):
 
 
 def compute_magnification(lens):
-    """Paraxial pupil magnification of the system in front of the stop
-    (rt_tf:765-777): stop height per unit entrance-pupil height."""
+    """First-order magnification of the system in front of the stop (rt_tf:765-777): height at the
+    stop plane per unit height of a ray entering parallel to the axis -- the A element of the ABCD
+    product (used by ``ray_aiming_mode='paraxial'``, rtl:138-140)."""
     if lens.structure.mask.shape[1] == 0:
         return torch.ones(len(lens), device=lens.c.device)
     nd = torch.cat((torch.ones_like(lens.nd[:, 0:1]), lens.nd), dim=1)
     system = reduce_abcd(interface_propagation_abcd(lens.c, lens.t, nd))
-    return 1 / system[:, 1, 1]
+    return system[:, 0, 0]             # "the magnification corresponds to the A element" (rt_tf:774-775)
 
 
 # ---------------------------------------------------------------------------
@@ -284,10 +331,13 @@ class RayTracer:
             'meridional_uniform': lambda ref: meridional_uniform(ref, n_rays, dev),
             'sagittal_uniform': lambda ref: sagittal_uniform(ref, n_rays, dev),
             'skew_outer_edge_uniform': lambda ref: circle_outer_edge_uniform(ref, n_rays, dev),
+            'skew_uniform_half_equidistant': lambda ref: skew_uniform_half_equidistant(ref, *n_rays, device=dev),
+            'skew_uniform_half_jittered': lambda ref: skew_uniform_half_jittered(ref, *n_rays, device=dev),
+            'skew_inner_square_half': lambda ref: skew_inner_square_half(ref, *n_rays, device=dev),
         }
         if mode not in samplers:
             raise ValueError(f'Ray tracing mode must be one of {sorted(samplers)}, got {mode!r}')
-        if mode in ('skew_random', 'circular'):
+        if mode in ('skew_random', 'circular', 'skew_uniform_half_equidistant', 'skew_uniform_half_jittered'):
             assert len(n_rays) == 2
         self.pupil_span = samplers[mode]
         self.n_rays = n_rays
