@@ -90,6 +90,12 @@ typedef struct TlProblem {
    * set never has to be materialised as [B,F,P,W] tensors.  Spherical lenses only; not together
    * with per-ray gradients of x / y. */
   const float *aim;
+  /* Pupil vignetting (apply_vignetting, ray_tracing.py:479-490 of the TensorFlow original; use sites
+   * rtl:98-104, :154-160), [B,F,3] = (x_scale, y_scale, y_offset), or NULL: the relative pupil
+   * coordinates become x * x_scale and y * y_scale + y_offset BEFORE the ray-aiming map, with
+   * x_scale = 1 - vig_x, y_scale = 1 - (vig_up + vig_down) / 2, y_offset = (vig_down - vig_up) / 2
+   * evaluated by the caller's vignetting function per (lens, field).  Same kernels as `aim`. */
+  const float *vig;
 } TlProblem;
 
 /* Outputs of trace_skew, each a contiguous [B,F,P,W] array. */
@@ -231,7 +237,8 @@ int tl_stage_fwd(const TlLens *lens, float *mu, float *z, float *cy, float *half
  * are the very buffers written here; read only when ref_y != NULL).  Pair it with
  * tl_spot_accumulate_ref, which takes ref_y as an input. */
 int tl_stage_ref(const TlLens *lens, const TlProblem *pb, float *mu, float *z, float *cy, float *half_epd,
-                 float *aim, int32_t allow_backward_rays, float *ref_y, void *stream);
+                 float *aim, const float *vig, int32_t aim_mode, int32_t allow_backward_rays, float *ref_y,
+                 void *stream);
 int tl_spot_accumulate_ref(const TlProblem *pb, int32_t want_grad, double *moments, const float *ref_y,
                            void *workspace, size_t workspace_bytes, void *stream);
 /* tl_spot_finalize (with gradients) + the chain rule of tl_stage_bwd as ONE launch: from the (reduced)
@@ -275,14 +282,38 @@ int tl_peer_destroy(TlPeerComm *comm);
  * (stop radius, compute_pupil_radius rtl:834-844) and the three 'tee' rays of every (lens, field,
  * wavelength) to the stop in forward mode and writes the affine pupil map
  *     aim[b,f,w] = (x_gain, y_gain, y_shift):  x_rel -> x_rel * x_gain,  y_rel -> y_rel * y_gain + y_shift
- * (rtl:196-206).  Like the reference's (it traces a detached lens, rtl:111) the map carries no
- * gradient. */
+ * (rtl:196-206).  `vig` ([B,F,3] as TlProblem.vig, or NULL): the tee rays and their targets are the
+ * vignetted ones (rtl:154-160).  `aim_mode`: TL_AIM_REAL takes the stop radius from the traced
+ * marginal ray, TL_AIM_PARAXIAL from the first-order magnification of the front group times EPD / 2
+ * (compute_magnification, ray_tracing.py:765-777; rtl:138-140).  Like the reference's (it traces a
+ * detached lens, rtl:111) the map carries no gradient. */
+enum { TL_AIM_REAL = 0, TL_AIM_PARAXIAL = 1 };
 int tl_aim(const TlLens *lens, const float *mu, const float *z, const float *cy, const float *half_epd,
-           int32_t allow_backward_rays, float *aim, void *stream);
+           const float *vig, int32_t aim_mode, int32_t allow_backward_rays, float *aim, void *stream);
+
+/* Spot-diagram / PSF binning: the Gaussian soft histogram of the reference's compute_psf
+ * (ray_tracing.py:206-270, the TensorFlow original).  Rays are given per
+ * grid g (= lens x field) and colour channel c; bin centres and sigma = half a bin as rt_tf:238-247;
+ * only the non-negative half of the x bins is evaluated (n_xh = n_x_bins / 2, + 1 if odd): the caller
+ * mirrors and normalises (rt_tf:257-263).
+ *   sums      [G, C, n_y_bins, n_xh] doubles: the un-normalised histogram
+ *   inside    [G, C] doubles: rays with |y - y_target| < y_size / 2 and |x| < x_size / 2 (rt_tf:266-267)
+ * Workspace: tl_psf_workspace() bytes. */
+typedef struct TlPsf {
+  const float *x, *y;              /* [G, C, R] image-plane points                            */
+  const float *y_target;           /* [G] grid centre in y (x is centred on 0)                */
+  const float *x_incr, *y_incr;    /* [G] bin pitch                                           */
+  const float *x_size, *y_size;    /* [G] window extent of the accounted-ray count            */
+  int32_t G, C, R;
+  int32_t n_x_bins, n_y_bins;
+} TlPsf;
+size_t tl_psf_workspace(const TlPsf *psf);
+int tl_psf_bin(const TlPsf *psf, double *sums, double *inside, void *workspace, size_t workspace_bytes,
+               void *stream);
 
 /* Layout self-description, so that a binding can check itself against the library it loaded:
  * for struct `which` (0 TlStrided, 1 TlProblem, 2 TlTraceOut, 3 TlSeeds, 4 TlGrads, 5 TlSpotOut,
- * 6 TlPenaltyOut, 7 TlLens) returns "Name:sizeof;field@offsetof;field@offsetof;..." in declaration
+ * 6 TlPenaltyOut, 7 TlLens, 8 TlPsf) returns "Name:sizeof;field@offsetof;field@offsetof;..." in declaration
  * order (thread-local storage, valid until the next call), or NULL for an unknown struct. */
 const char *tl_abi_describe(int32_t which);
 

@@ -57,33 +57,72 @@ F64_KEYS = ('rms', 'grad_c', 'grad_t', 'grad_nd', 'grad_in_z', 'grad_in_c', 'gra
 
 
 def run_case(rtl, lm, yml, n_rays, rel_fields, wavelengths, epd_scale=1.0, n_ray_aiming_iter=0,
-             allow_backward_rays=True, mode='circular'):
+             allow_backward_rays=True, mode='circular', vig=None, ray_aiming_mode='real'):
     """One golden record: the reference in fp32 (every key) and, under the prefix ``f64_``, the RMS,
     the gradients and the (possibly ray-aimed) pupil of the SAME reference code run in float64 --
     the yardstick for "no farther from the truth than the reference's own fp32"."""
     rec = _run_case(rtl, lm, yml, n_rays, rel_fields, wavelengths, epd_scale, n_ray_aiming_iter,
-                    allow_backward_rays, mode, torch.float32)
+                    allow_backward_rays, mode, torch.float32, vig, ray_aiming_mode)
     torch.set_default_dtype(torch.float64)
     try:
         rec64 = _run_case(rtl, lm, yml, n_rays, rel_fields, wavelengths, epd_scale, n_ray_aiming_iter,
-                          allow_backward_rays, mode, torch.float64)
+                          allow_backward_rays, mode, torch.float64, vig, ray_aiming_mode)
     finally:
         torch.set_default_dtype(torch.float32)
     assert np.array_equal(rec['out_ok'], rec64['out_ok']), 'fp32 and fp64 masks of the reference differ'
     for k in F64_KEYS + (('out_x', 'out_y') if n_ray_aiming_iter > 0 else ()):
         rec['f64_' + k] = rec64[k]
+    if vig is not None:
+        rec['vig'] = np.asarray(vig, dtype=np.float32)
+    rec['ray_aiming_mode'] = np.asarray(ray_aiming_mode)
     return rec
 
 
+def linear_vignetting(fields, vig):
+    """The vignetting function of the golden cases: factor growing linearly with the relative field,
+    [1,F] x [B] -> [B,F] (RayTracer calls ``vig_fn(fields, specs.vig_up)``, rtl:100-102)."""
+    return vig[:, None] * fields
+
+
+def restore_commented_out_helpers(rtl):
+    """ray_tracing_lite.py calls two helpers whose definitions it only carries as comments -- and spells
+    one dtype ``tf.float32`` -- so its own vignetting and 'paraxial' ray-aiming branches raise
+    NameError (rtl:98-104, :138-140, :154-160).  To let the reference's control
+    flow produce goldens for those branches, the two helpers are supplied as literal torch
+    transcriptions of the commented text (rtl:483-494 = rt_tf:479-490, rtl:797-809 = rt_tf:765-777; both
+    pinned separately in tests/test_tf_original_functions.py) and ``tf`` is bound to torch."""
+    import torch as _torch
+
+    def apply_vignetting(y, vig_up, vig_down):
+        trailing = [1] * (len(y.shape) - len(vig_down.shape))
+        vig_up = _torch.reshape(vig_up, (*vig_up.shape, *trailing))
+        vig_down = _torch.reshape(vig_down, (*vig_down.shape, *trailing))
+        scale = 1 - (vig_up + vig_down) / 2
+        offset = (vig_down - vig_up) / 2
+        return y * scale + offset
+
+    def compute_magnification(lens):
+        nd = _torch.cat((_torch.ones_like(lens.nd[:, 0:1]), lens.nd), dim=1)
+        abcd = rtl.reduce_abcd(rtl.interface_propagation_abcd(lens.c, lens.t, nd))
+        return abcd[:, 0, 0]
+
+    rtl.apply_vignetting = apply_vignetting
+    rtl.compute_magnification = compute_magnification
+    rtl.tf = _torch
+
+
 def _run_case(rtl, lm, yml, n_rays, rel_fields, wavelengths, epd_scale, n_ray_aiming_iter,
-              allow_backward_rays, mode, dtype):
+              allow_backward_rays, mode, dtype, vig=None, ray_aiming_mode='real'):
     d, structure, lens = load_lens(lm, yml, dtype)
     for name in ('c', 't', 'nd', 'v'):
         getattr(lens, name).requires_grad_(True)
     efl = lens.efl.detach()
     epd = efl / torch.tensor(d['f_number'], dtype=dtype) * epd_scale
     hfov = torch.deg2rad(torch.tensor(d['hfov'], dtype=dtype))
-    specs = lm.Specs(structure, epd, hfov)
+    if vig is None:
+        specs = lm.Specs(structure, epd, hfov)
+    else:
+        specs = lm.Specs(structure, epd, hfov, *(torch.tensor([v], dtype=dtype) for v in vig))
 
     captured = {}
     real_trace = rtl.trace_skew
@@ -96,7 +135,8 @@ def _run_case(rtl, lm, yml, n_rays, rel_fields, wavelengths, epd_scale, n_ray_ai
     try:
         tracer = rtl.RayTracer(mode=mode, n_rays=n_rays, rel_fields=rel_fields,
                                wavelengths=wavelengths, n_ray_aiming_iter=n_ray_aiming_iter,
-                               allow_backward_rays=allow_backward_rays, default_device='cpu')
+                               allow_backward_rays=allow_backward_rays, default_device='cpu',
+                               vig_fn=None if vig is None else linear_vignetting, ray_aiming_mode=ray_aiming_mode)
         x, y, cx, cy, ok, bw = tracer.trace_rays(specs, lens)
     finally:
         rtl.trace_skew = real_trace
@@ -173,6 +213,16 @@ def main():
     # BASELINE.json configs[0] at its exact shape: Cooke triplet, 3 fields x 3 wavelengths, 96 x 76
     # pupil = 65 664 rays
     cases['cooke_96x76_config1'] = run_case(rtl, lm, cooke, n_rays=(96, 76), **{k: std[k] for k in ('rel_fields', 'wavelengths')})
+    # pupil vignetting and the 'paraxial' stop radius: branches the lite reference cannot run as shipped
+    # (see restore_commented_out_helpers); vig = (vig_up, vig_down, vig_x) at full field
+    restore_commented_out_helpers(rtl)
+    vig = (0.30, 0.15, 0.10)
+    cases['cooke_8x8_vig'] = run_case(rtl, lm, cooke, vig=vig, **std)
+    cases['cooke_8x8_vig_aimed'] = run_case(rtl, lm, cooke, vig=vig, n_ray_aiming_iter=1, **std)
+    cases['tessar_8x8_vig_aimed'] = run_case(rtl, lm, tessar, vig=vig, n_ray_aiming_iter=1, **std)
+    cases['cooke_8x8_paraxial_aimed'] = run_case(rtl, lm, cooke, n_ray_aiming_iter=1, ray_aiming_mode='paraxial', **std)
+    cases['tessar_8x8_vig_paraxial_aimed'] = run_case(rtl, lm, tessar, vig=vig, n_ray_aiming_iter=1,
+                                                      ray_aiming_mode='paraxial', **std)
     for name, rec in cases.items():
         np.savez_compressed(os.path.join(HERE, f'{name}.npz'), **rec)
         print(f"{name:34s} S={rec['in_t'].shape[-1]} rays={rec['out_ok'].size:6d} "

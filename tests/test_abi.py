@@ -40,7 +40,7 @@ def test_abi_version_and_argument_checks():
 def test_struct_layout_matches_header():
     # TlStrided = pointer + 4 x int64; TlProblem packs 5 of them, 4 pointers, 9 int32
     assert ctypes.sizeof(_native.TlStrided) == 40
-    assert ctypes.sizeof(_native.TlProblem) == 5 * 40 + 4 * 8 + 9 * 4 + 4 + 8 + 3 * 8 + 8
+    assert ctypes.sizeof(_native.TlProblem) == 5 * 40 + 4 * 8 + 9 * 4 + 4 + 8 + 3 * 8 + 8 + 8
     assert ctypes.sizeof(_native.TlLens) == 11 * 8 + 4 * 4
     assert ctypes.sizeof(_native.TlGrads) == 11 * 8
 

@@ -28,11 +28,8 @@ def test_first_order_matches_reference(golden):
 def test_ray_set_matches_reference(golden):
     if 'aimed' in golden['name']:
         pytest.skip('ray aiming traces rays: covered by the gpu tests')
-    specs, lens = _lens_from(golden)
-    tracer = rt.RayTracer(mode='circular', n_rays=tuple(int(v) for v in golden['n_rays']),
-                          rel_fields=tuple(float(v) for v in golden['rel_fields']),
-                          wavelengths=tuple(float(v) for v in golden['wavelengths']),
-                          default_device='cpu')
+    from tests.conftest import golden_problem
+    tracer, specs, lens = golden_problem(golden, 'cpu', requires_grad=False)      # (incl. pupil vignetting)
     x, y, z, cx, cy, c, t, mu, mask = tracer._ray_set(specs, lens)
     for got, key in ((x, 'in_x'), (y, 'in_y'), (cx, 'in_cx'), (cy, 'in_cy'), (c, 'in_c'), (t, 'in_t')):
         assert got.shape == golden[key].shape, key
@@ -110,9 +107,12 @@ def test_staging_decision_of_the_front_end():
     mirror = rt.RayTracer(n_ray_aiming_iter=1, **base)
     mirror.device_aiming = False
     assert mirror._staging(lens) == (False, False)
-    assert rt.RayTracer(n_ray_aiming_iter=1, ray_aiming_mode='paraxial', **base)._staging(lens) == (False, False)
+    # round 2: the 'paraxial' stop radius and pupil vignetting functions stay on the staged path too
+    assert rt.RayTracer(n_ray_aiming_iter=1, ray_aiming_mode='paraxial', **base)._staging(lens) == (True, True)
     vig = rt.RayTracer(vig_fn=lambda fields, v: v[:, None] * fields, **base)
-    assert vig._staging(lens)[0] is False and vig._staging(lens, use_vig=False)[0] is True
+    assert vig._staging(lens)[0] is True and vig._staging(lens, use_vig=False)[0] is True
+    kw = vig._staged_kwargs(specs, lens)
+    assert kw['vig'].shape == (1, 2, 3) and vig._staged_kwargs(specs, lens, use_vig=False)['vig'] is None
     rnd = dict(base, mode='skew_random')
     assert rt.RayTracer(**rnd)._staging(lens)[0] is False
     # a stop in front of the lens needs no aiming at all (rtl:131-133)

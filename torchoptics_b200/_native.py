@@ -15,6 +15,8 @@ LIB_PATH = os.environ.get('TL_LIB_OVERRIDE') or os.path.join(_PKG, 'libtorchopti
 ABI_VERSION = 10
 ARITH_GUARDED = 0
 ARITH_EXACT = 1
+AIM_REAL = 0
+AIM_PARAXIAL = 1
 MAX_SURFACES_FWD = 256
 MAX_SURFACES_BWD = 32
 MAX_SURFACES_SPOT = 16
@@ -41,7 +43,7 @@ class TlProblem(ctypes.Structure):
                 ('p_begin', ctypes.c_int32), ('p_end', ctypes.c_int32),
                 ('xy_scale', ctypes.c_void_p),
                 ('k', ctypes.c_void_p), ('a', ctypes.c_void_p), ('sd', ctypes.c_void_p),
-                ('aim', ctypes.c_void_p)]
+                ('aim', ctypes.c_void_p), ('vig', ctypes.c_void_p)]
 
 
 class TlTraceOut(ctypes.Structure):
@@ -66,6 +68,11 @@ class TlLens(ctypes.Structure):
 
 class TlPenaltyOut(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ('penalty', 'gc', 'gt', 'gmu', 'gz')]
+
+
+class TlPsf(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ('x', 'y', 'y_target', 'x_incr', 'y_incr', 'x_size', 'y_size')] + \
+               [(n, ctypes.c_int32) for n in ('G', 'C', 'R', 'n_x_bins', 'n_y_bins')]
 
 
 class TlSpotOut(ctypes.Structure):
@@ -99,17 +106,20 @@ EXPORTS = {
                                           ctypes.c_void_p]),
     'tl_stage_fwd': (ctypes.c_int, [ctypes.POINTER(TlLens)] + [ctypes.c_void_p] * 5),
     'tl_stage_bwd': (ctypes.c_int, [ctypes.POINTER(TlLens)] + [ctypes.c_void_p] * 7),
-    'tl_stage_ref': (ctypes.c_int, [ctypes.POINTER(TlLens), ctypes.POINTER(TlProblem)] + [ctypes.c_void_p] * 5 +
-                     [ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
+    'tl_stage_ref': (ctypes.c_int, [ctypes.POINTER(TlLens), ctypes.POINTER(TlProblem)] + [ctypes.c_void_p] * 6 +
+                     [ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
     'tl_spot_accumulate_ref': (ctypes.c_int, [ctypes.POINTER(TlProblem), ctypes.c_int32, ctypes.c_void_p,
                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     'tl_lens_spot_finalize': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(TlLens), ctypes.c_int64,
                                              ctypes.POINTER(TlSpotOut), ctypes.c_void_p, ctypes.c_void_p,
                                              ctypes.c_void_p]),
-    'tl_aim': (ctypes.c_int, [ctypes.POINTER(TlLens)] + [ctypes.c_void_p] * 4 +
-               [ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
+    'tl_aim': (ctypes.c_int, [ctypes.POINTER(TlLens)] + [ctypes.c_void_p] * 5 +
+               [ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]),
     'tl_spot_finalize': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_int32] * 4 +
                          [ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(TlSpotOut), ctypes.c_void_p]),
+    'tl_psf_workspace': (ctypes.c_size_t, [ctypes.POINTER(TlPsf)]),
+    'tl_psf_bin': (ctypes.c_int, [ctypes.POINTER(TlPsf), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                  ctypes.c_void_p]),
     'tl_penalty_moment_count': (ctypes.c_int32, [ctypes.c_int32]),
     'tl_penalty_workspace': (ctypes.c_size_t, [ctypes.POINTER(TlProblem)]),
     'tl_penalty_accumulate': (ctypes.c_int, [ctypes.POINTER(TlProblem), ctypes.c_void_p, ctypes.c_void_p,
@@ -128,7 +138,7 @@ EXPORTS = {
 }
 
 # struct ids of tl_abi_layout
-LAYOUT_STRUCTS = (TlStrided, TlProblem, TlTraceOut, TlSeeds, TlGrads, TlSpotOut, TlPenaltyOut, TlLens)
+LAYOUT_STRUCTS = (TlStrided, TlProblem, TlTraceOut, TlSeeds, TlGrads, TlSpotOut, TlPenaltyOut, TlLens, TlPsf)
 
 _lib = None
 

@@ -106,8 +106,8 @@ k_psf_bin(PsfArgs a) {
   if (threadIdx.x == 0) dst[n_bins] = (double)inside_total;
 }
 
-// partial[gc, chunk, n] -> sums[gc, n] (fixed order)
-__global__ void k_psf_reduce(const double *partial, double *sums, int n_gc, int n_chunks, int n) {
+// partial[gc, chunk, n_bins + 1] -> sums[gc, n_bins], inside[gc] (fixed order)
+__global__ void k_psf_reduce(const double *partial, double *sums, double *inside, int n_gc, int n_chunks, int n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)n_gc * n) return;
   const int gc = (int)(i / n), slot = (int)(i % n);
@@ -118,7 +118,8 @@ __global__ void k_psf_reduce(const double *partial, double *sums, int n_gc, int 
     s1 += partial[((int64_t)gc * n_chunks + c + 1) * n + slot];
   }
   if (c < n_chunks) s0 += partial[((int64_t)gc * n_chunks + c) * n + slot];
-  sums[i] = s0 + s1;
+  if (slot < n - 1) sums[(int64_t)gc * (n - 1) + slot] = s0 + s1;
+  else inside[gc] = s0 + s1;
 }
 
 struct PsfPlan {

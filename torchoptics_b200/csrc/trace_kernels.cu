@@ -86,6 +86,11 @@ __device__ __forceinline__ void load_pupil_point(const TlProblem &pb, int b, int
                                                  float xy_scale, float &x, float &y) {
   x = pb.x.ptr[offset_of(pb.x, b, f, q, w)];
   y = pb.y.ptr[offset_of(pb.y, b, f, q, w)];
+  if (AIM && pb.vig) {      // pupil vignetting first (rtl:98-104), each step individually rounded
+    const float *v = pb.vig + ((int64_t)b * pb.F + f) * 3;
+    x = __fmul_rn(x, v[0]);
+    y = __fadd_rn(__fmul_rn(y, v[1]), v[2]);
+  }
   if (AIM && pb.aim) {
     const float *a = pb.aim + (((int64_t)b * pb.F + f) * pb.W + w) * 3;
     x = fminf(fmaxf(__fmul_rn(x, a[0]), -2.0f), 2.0f);
@@ -1363,18 +1368,39 @@ __device__ __forceinline__ bool trace_to_stop(const TlLens &ln, const float *mu_
 }
 
 __device__ __forceinline__ void aim_one(const TlLens &ln, const float *mu, const float *z, const float *cy,
-                                        const float *half_epd, int allow_backward, float *aim, int i) {
+                                        const float *half_epd, const float *vig, int mode, int allow_backward,
+                                        float *aim, int i) {
   const int w = i % ln.W, f = (i / ln.W) % ln.F, b = i / (ln.W * ln.F);
   const int n_front = min(ln.stop_idx[b], ln.L);
   const float h = half_epd[b], z0 = z[b];
   const float *mu_row = mu + ((int64_t)b * ln.W + w) * ln.L;
-  // stop radius: marginal ray of the axial field at the d line
-  Ray<D2> m{D2(0.f), D2(h), D2(z0), D2(0.f), D2(0.f), D2(1.0f)};
-  trace_to_stop<D2>(ln, mu_row, true, b, n_front, allow_backward != 0, m);
-  const float rs = m.y.v;
-  // the tee rays of this (field, wavelength)
+  float rs;
+  if (mode == TL_AIM_PARAXIAL) {
+    // stop radius = first-order magnification of the front group (the A element of its ABCD product,
+    // compute_magnification rt_tf:765-777) times the pupil radius (rtl:138-140)
+    Abcd m{1.f, 0.f, 0.f, 1.f};
+    for (int s = 0; s < n_front; ++s) {
+      const Abcd q = slot_matrix(ln, b, s, nullptr, nullptr);
+      m = Abcd{q.a * m.a + q.b * m.c, q.a * m.b + q.b * m.d, q.c * m.a + q.d * m.c, q.c * m.b + q.d * m.d};
+    }
+    rs = m.a * h;
+  } else {
+    // stop radius: marginal ray of the axial field at the d line (compute_pupil_radius rtl:834-844)
+    Ray<D2> m{D2(0.f), D2(h), D2(z0), D2(0.f), D2(0.f), D2(1.0f)};
+    trace_to_stop<D2>(ln, mu_row, true, b, n_front, allow_backward != 0, m);
+    rs = m.y.v;
+  }
+  // the tee rays of this (field, wavelength), vignetted like the pupil itself (rtl:154-160)
   const float dir_y = cy[(int64_t)b * ln.F + f];
-  const float tee_x[3] = {0.f, 0.f, 1.f}, tee_y[3] = {-1.f, 1.f, 0.f};
+  float tee_x[3] = {0.f, 0.f, 1.f}, tee_y[3] = {-1.f, 1.f, 0.f};
+  if (vig) {
+    const float *v = vig + ((int64_t)b * ln.F + f) * 3;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      tee_x[q] = __fmul_rn(tee_x[q], v[0]);
+      tee_y[q] = __fadd_rn(__fmul_rn(tee_y[q], v[1]), v[2]);
+    }
+  }
   float step_x[3], step_y[3];
 #pragma unroll
   for (int q = 0; q < 3; ++q) {
@@ -1396,9 +1422,9 @@ __device__ __forceinline__ void aim_one(const TlLens &ln, const float *mu, const
 }
 
 __global__ void k_aim(TlLens ln, const float *mu, const float *z, const float *cy, const float *half_epd,
-                      int allow_backward, float *aim) {
+                      const float *vig, int mode, int allow_backward, float *aim) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < ln.B * ln.F * ln.W) aim_one(ln, mu, z, cy, half_epd, allow_backward, aim, i);
+  if (i < ln.B * ln.F * ln.W) aim_one(ln, mu, z, cy, half_epd, vig, mode, allow_backward, aim, i);
 }
 
 // Staging, ray aiming and the reference heights of a lens as ONE launch (a step of the fused lens
@@ -1406,7 +1432,7 @@ __global__ void k_aim(TlLens ln, const float *mu, const float *z, const float *c
 // step).  One CTA per lens; the phases see each other's global writes through the barriers.
 __global__ void __launch_bounds__(128)
 k_stage_ref(TlLens ln, TlProblem pb, float *mu, float *z, float *cy, float *half_epd, float *aim,
-            int allow_backward, float *ref_y) {
+            const float *vig, int mode, int allow_backward, float *ref_y) {
   __shared__ LensCopy copy;
   __shared__ float mu0[kStageMaxSurfaces];
   const int b = blockIdx.x;
@@ -1416,7 +1442,7 @@ k_stage_ref(TlLens ln, TlProblem pb, float *mu, float *z, float *cy, float *half
   __syncthreads();
   if (aim) {
     for (int i = threadIdx.x; i < ln.F * ln.W; i += blockDim.x)
-      aim_one(lens, mu, z, cy, half_epd, allow_backward, aim, b * ln.F * ln.W + i);
+      aim_one(lens, mu, z, cy, half_epd, vig, mode, allow_backward, aim, b * ln.F * ln.W + i);
     __threadfence_block();
     __syncthreads();
   }
@@ -1547,8 +1573,8 @@ int validate(const TlProblem *pb, int max_s) {
     return fail(TL_ERR_INVALID, "unknown arithmetic policy%s");
   if ((int64_t)pb->B * pb->F * pb->W > (1 << 24))
     return fail(TL_ERR_INVALID, "B*F*W too large%s");
-  if (pb->aim && is_general(*pb))
-    return fail(TL_ERR_INVALID, "the ray-aiming map is for spherical lenses only (not with k / a / sd)%s");
+  if ((pb->aim || pb->vig) && is_general(*pb))
+    return fail(TL_ERR_INVALID, "the ray-aiming / vignetting maps are for spherical lenses only (not with k / a / sd)%s");
   return TL_OK;
 }
 
@@ -1717,6 +1743,7 @@ int reduce_rows(const AdjPlan &pl, const double *partial, double *rows_out, int 
 }
 
 #include "spot_rev.cuh"
+#include "psf_kernels.cuh"
 
 // K3c: the backward kernels (MODE_BWD of k_trace_adj: plain, with seeded stacks, and the fused
 // penalty pass PEN_SUM) with a warp per row, for the same many-short-rows workload as k_spot_rows.
@@ -2045,13 +2072,14 @@ const char *tl_abi_describe(int32_t which) {
 #define TL_OFF(T, f) n += snprintf(text + n, sizeof(text) - n, ";" #f "@%zu", offsetof(T, f))
   switch (which) {
     case 0: TL_SIZE(TlStrided); TL_OFF(TlStrided, ptr); TL_OFF(TlStrided, stride); break;
-    case 1: TL_SIZE(TlProblem); TL_OFF(TlProblem, x); TL_OFF(TlProblem, y); TL_OFF(TlProblem, z); TL_OFF(TlProblem, cx); TL_OFF(TlProblem, cy); TL_OFF(TlProblem, c); TL_OFF(TlProblem, t); TL_OFF(TlProblem, mu); TL_OFF(TlProblem, live); TL_OFF(TlProblem, B); TL_OFF(TlProblem, F); TL_OFF(TlProblem, P); TL_OFF(TlProblem, W); TL_OFF(TlProblem, S); TL_OFF(TlProblem, allow_backward_rays); TL_OFF(TlProblem, arith); TL_OFF(TlProblem, p_begin); TL_OFF(TlProblem, p_end); TL_OFF(TlProblem, xy_scale); TL_OFF(TlProblem, k); TL_OFF(TlProblem, a); TL_OFF(TlProblem, sd); TL_OFF(TlProblem, aim); break;
+    case 1: TL_SIZE(TlProblem); TL_OFF(TlProblem, x); TL_OFF(TlProblem, y); TL_OFF(TlProblem, z); TL_OFF(TlProblem, cx); TL_OFF(TlProblem, cy); TL_OFF(TlProblem, c); TL_OFF(TlProblem, t); TL_OFF(TlProblem, mu); TL_OFF(TlProblem, live); TL_OFF(TlProblem, B); TL_OFF(TlProblem, F); TL_OFF(TlProblem, P); TL_OFF(TlProblem, W); TL_OFF(TlProblem, S); TL_OFF(TlProblem, allow_backward_rays); TL_OFF(TlProblem, arith); TL_OFF(TlProblem, p_begin); TL_OFF(TlProblem, p_end); TL_OFF(TlProblem, xy_scale); TL_OFF(TlProblem, k); TL_OFF(TlProblem, a); TL_OFF(TlProblem, sd); TL_OFF(TlProblem, aim); TL_OFF(TlProblem, vig); break;
     case 2: TL_SIZE(TlTraceOut); TL_OFF(TlTraceOut, x); TL_OFF(TlTraceOut, y); TL_OFF(TlTraceOut, cx); TL_OFF(TlTraceOut, cy); TL_OFF(TlTraceOut, ok); TL_OFF(TlTraceOut, backward); TL_OFF(TlTraceOut, opl); TL_OFF(TlTraceOut, z_relu); TL_OFF(TlTraceOut, theta); TL_OFF(TlTraceOut, theta_prime); break;
     case 3: TL_SIZE(TlSeeds); TL_OFF(TlSeeds, gx); TL_OFF(TlSeeds, gy); TL_OFF(TlSeeds, gcx); TL_OFF(TlSeeds, gcy); TL_OFF(TlSeeds, gz_relu); TL_OFF(TlSeeds, gtheta); TL_OFF(TlSeeds, gtheta_prime); break;
     case 4: TL_SIZE(TlGrads); TL_OFF(TlGrads, gc); TL_OFF(TlGrads, gt); TL_OFF(TlGrads, gmu); TL_OFF(TlGrads, gz_sum); TL_OFF(TlGrads, gx); TL_OFF(TlGrads, gy); TL_OFF(TlGrads, gz); TL_OFF(TlGrads, gcx); TL_OFF(TlGrads, gcy); TL_OFF(TlGrads, gk); TL_OFF(TlGrads, ga); break;
     case 5: TL_SIZE(TlSpotOut); TL_OFF(TlSpotOut, rms); TL_OFF(TlSpotOut, rms_field); TL_OFF(TlSpotOut, gc); TL_OFF(TlSpotOut, gt); TL_OFF(TlSpotOut, gmu); TL_OFF(TlSpotOut, gz); TL_OFF(TlSpotOut, gk); TL_OFF(TlSpotOut, ga); break;
     case 6: TL_SIZE(TlPenaltyOut); TL_OFF(TlPenaltyOut, penalty); TL_OFF(TlPenaltyOut, gc); TL_OFF(TlPenaltyOut, gt); TL_OFF(TlPenaltyOut, gmu); TL_OFF(TlPenaltyOut, gz); break;
     case 7: TL_SIZE(TlLens); TL_OFF(TlLens, c); TL_OFF(TlLens, t); TL_OFF(TlLens, nd); TL_OFF(TlLens, v); TL_OFF(TlLens, mask); TL_OFF(TlLens, mask_g); TL_OFF(TlLens, stop_idx); TL_OFF(TlLens, hfov); TL_OFF(TlLens, epd); TL_OFF(TlLens, rel_fields); TL_OFF(TlLens, wavelengths); TL_OFF(TlLens, B); TL_OFF(TlLens, L); TL_OFF(TlLens, F); TL_OFF(TlLens, W); break;
+    case 8: TL_SIZE(TlPsf); TL_OFF(TlPsf, x); TL_OFF(TlPsf, y); TL_OFF(TlPsf, y_target); TL_OFF(TlPsf, x_incr); TL_OFF(TlPsf, y_incr); TL_OFF(TlPsf, x_size); TL_OFF(TlPsf, y_size); TL_OFF(TlPsf, G); TL_OFF(TlPsf, C); TL_OFF(TlPsf, R); TL_OFF(TlPsf, n_x_bins); TL_OFF(TlPsf, n_y_bins); break;
     default: return nullptr;
   }
 #undef TL_SIZE
@@ -2076,8 +2104,8 @@ int tl_trace_fwd(const TlProblem *pb, const TlTraceOut *out, void *stream_) {
   // (pupil, wavelength)-flattened map keeps a CTA's threads busy where a CTA per row would idle
   const size_t smem_pw = (size_t)pb->W * ((5 * (size_t)pb->S + 3) & ~(size_t)3) * sizeof(float);
   const bool short_rows = !is_general(*pb) && smem_pw <= 48 * 1024 &&
-                          ((pb->P < 2 * kFwdThreads && !getenv("TL_NO_ROWS")) || pb->aim);
-  if (pb->aim && !short_rows)
+                          ((pb->P < 2 * kFwdThreads && !getenv("TL_NO_ROWS")) || pb->aim || pb->vig);
+  if ((pb->aim || pb->vig) && !short_rows)
     return fail(TL_ERR_INVALID, "an aimed forward trace needs W * S surface tables within 48 KB of shared memory%s");
   if (stacks || short_rows) {
     const int64_t row_len = (int64_t)pb->P * pb->W;
@@ -2138,7 +2166,7 @@ int tl_trace_bwd(const TlProblem *pb_, const TlSeeds *seeds, const TlGrads *grad
   if (rc) return rc;
   if (!seeds || !grads || !grads->gc || !grads->gt || !grads->gmu || !grads->gz_sum)
     return fail(TL_ERR_INVALID, "NULL seeds/grads%s");
-  if (pb_->aim && (grads->gx || grads->gy))
+  if ((pb_->aim || pb_->vig) && (grads->gx || grads->gy))
     return fail(TL_ERR_INVALID, "per-ray gradients of x / y are not available through a ray-aiming map%s");
   if (is_general(*pb_)) {
     if (seeds->gz_relu || seeds->gtheta || seeds->gtheta_prime)
@@ -2410,6 +2438,42 @@ int tl_spot_kernel_only(const TlProblem *pb, const float *ref_y, void *workspace
   return TL_OK;
 }
 
+size_t tl_psf_workspace(const TlPsf *psf) {
+  PsfPlan pl;
+  if (!psf || plan_psf(*psf, pl)) return 0;
+  return pl.partial_bytes;
+}
+
+int tl_psf_bin(const TlPsf *psf, double *sums, double *inside, void *workspace, size_t workspace_bytes,
+               void *stream_) {
+  if (!psf || !psf->x || !psf->y || !psf->y_target || !psf->x_incr || !psf->y_incr || !psf->x_size ||
+      !psf->y_size || !sums || !inside)
+    return fail(TL_ERR_INVALID, "tl_psf_bin: NULL argument%s");
+  PsfPlan pl;
+  int rc = plan_psf(*psf, pl);
+  if (rc) return rc;
+  if (!workspace || workspace_bytes < pl.partial_bytes)
+    return fail(TL_ERR_WORKSPACE, "workspace too small for tl_psf_bin%s");
+  if (pl.smem > 48 * 1024)
+    TL_CHECK_CUDA(cudaFuncSetAttribute((const void *)k_psf_bin, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)pl.smem));
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PsfArgs args;
+  args.p = *psf;
+  args.partial = (double *)workspace;
+  args.n_chunks = pl.n_chunks;
+  args.chunk_len = pl.chunk_len;
+  args.n_xh = pl.n_xh;
+  const int n_gc = psf->G * psf->C, n = pl.n_xh * psf->n_y_bins + 1;
+  k_psf_bin<<<n_gc * pl.n_chunks, kPsfThreads, pl.smem, stream>>>(args);
+  g_launches++;
+  k_psf_reduce<<<(unsigned)(((int64_t)n_gc * n + 255) / 256), 256, 0, stream>>>(args.partial, sums, inside, n_gc,
+                                                                                  pl.n_chunks, n);
+  g_launches++;
+  TL_CHECK_CUDA(cudaGetLastError());
+  return TL_OK;
+}
+
 int32_t tl_penalty_moment_count(int32_t S) { return 3 * S + 2; }
 
 size_t tl_penalty_workspace(const TlProblem *pb) {
@@ -2517,7 +2581,8 @@ int tl_stage_fwd(const TlLens *lens, float *mu, float *z, float *cy, float *half
 }
 
 int tl_stage_ref(const TlLens *lens, const TlProblem *pb, float *mu, float *z, float *cy, float *half_epd,
-                 float *aim, int32_t allow_backward_rays, float *ref_y, void *stream_) {
+                 float *aim, const float *vig, int32_t aim_mode, int32_t allow_backward_rays, float *ref_y,
+                 void *stream_) {
   int rc = validate_lens(lens);
   if (rc) return rc;
   if (!mu || !z || !cy || !half_epd) return fail(TL_ERR_INVALID, "NULL output of tl_stage_ref%s");
@@ -2530,8 +2595,9 @@ int tl_stage_ref(const TlLens *lens, const TlProblem *pb, float *mu, float *z, f
     if (pb->B != lens->B || pb->F != lens->F || pb->W != lens->W || pb->S != lens->L)
       return fail(TL_ERR_INVALID, "tl_stage_ref: problem and lens sizes differ%s");
   }
-  k_stage_ref<<<lens->B, 128, 0, (cudaStream_t)stream_>>>(*lens, ref_y ? *pb : none, mu, z, cy, half_epd, aim,
-                                                          allow_backward_rays, ref_y);
+  if (aim_mode != TL_AIM_REAL && aim_mode != TL_AIM_PARAXIAL) return fail(TL_ERR_INVALID, "unknown aim_mode%s");
+  k_stage_ref<<<lens->B, 128, 0, (cudaStream_t)stream_>>>(*lens, ref_y ? *pb : none, mu, z, cy, half_epd, aim, vig,
+                                                          aim_mode, allow_backward_rays, ref_y);
   g_launches++;
   TL_CHECK_CUDA(cudaGetLastError());
   return TL_OK;
@@ -2567,12 +2633,14 @@ int tl_lens_spot_finalize(const double *moments, const float *ref_y, const TlLen
 }
 
 int tl_aim(const TlLens *lens, const float *mu, const float *z, const float *cy, const float *half_epd,
-           int32_t allow_backward_rays, float *aim, void *stream_) {
+           const float *vig, int32_t aim_mode, int32_t allow_backward_rays, float *aim, void *stream_) {
   int rc = validate_lens(lens);
   if (rc) return rc;
   if (!mu || !z || !cy || !half_epd || !aim) return fail(TL_ERR_INVALID, "NULL argument of tl_aim%s");
   const int n = lens->B * lens->F * lens->W;
-  k_aim<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(*lens, mu, z, cy, half_epd, allow_backward_rays, aim);
+  if (aim_mode != TL_AIM_REAL && aim_mode != TL_AIM_PARAXIAL) return fail(TL_ERR_INVALID, "unknown aim_mode%s");
+  k_aim<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(*lens, mu, z, cy, half_epd, vig, aim_mode,
+                                                           allow_backward_rays, aim);
   g_launches++;
   TL_CHECK_CUDA(cudaGetLastError());
   return TL_OK;

@@ -615,7 +615,7 @@ class LensTables:
         return ln
 
 
-def aim_table(c, t, nd, v, hfov, epd, tables, allow_backward_rays=True):
+def aim_table(c, t, nd, v, hfov, epd, tables, allow_backward_rays=True, vig=None, aim_mode=nat.AIM_REAL):
     """Ray aiming on the device (``RayTracer.ray_aiming`` rtl:129-208: one iteration, 'real' stop
     radius, no pupil vignetting function): returns ``aim [B,F,W,3] = (x_gain, y_gain, y_shift)`` of
     the affine pupil map ``x_rel * x_gain, y_rel * y_gain + y_shift`` (rtl:196-206).  Two kernel
@@ -643,8 +643,10 @@ def aim_table(c, t, nd, v, hfov, epd, tables, allow_backward_rays=True):
         stream = nat.stream_ptr(dev)
         nat.check(lib.tl_stage_fwd(ctypes.byref(ln), mu.data_ptr(), z.data_ptr(), cy.data_ptr(),
                                    half_epd.data_ptr(), stream), 'tl_stage_fwd')
+        vig_c = None if vig is None else vig.detach().to(torch.float32).contiguous()
         nat.check(lib.tl_aim(ctypes.byref(ln), mu.data_ptr(), z.data_ptr(), cy.data_ptr(), half_epd.data_ptr(),
-                             int(bool(allow_backward_rays)), aim.data_ptr(), stream), 'tl_aim')
+                             _ptr(vig_c), int(aim_mode), int(bool(allow_backward_rays)), aim.data_ptr(), stream),
+                  'tl_aim')
     return aim
 
 
@@ -655,7 +657,7 @@ class _Staged:
     every buffer alive for as long as the problem is in use."""
 
     def __init__(self, c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, aimed,
-                 p_begin=0, p_end=None, max_surfaces=64, want_ref=False):
+                 p_begin=0, p_end=None, max_surfaces=64, want_ref=False, vig=None, aim_mode=nat.AIM_REAL):
         for name, val in (('c', c), ('t', t), ('nd', nd), ('v', v), ('hfov', hfov), ('epd', epd),
                           ('x', x_rel), ('y', y_rel)):
             nat.require_cuda(val, name)
@@ -686,8 +688,15 @@ class _Staged:
         self.aim = packed[at:at + B * F * W * 3].view(B, F, W, 3) if aimed else None
         self.ln = tables.lens_struct(cc, tt, ndd, vv, hf, ep)
         self.xy = (x_rel.detach(), y_rel.detach())
+        self.vig = None
+        if vig is not None:      # [B,F,3] = (x_scale, y_scale, y_offset) of apply_vignetting, per (lens, field)
+            nat.require_cuda(vig, 'vig')
+            if tuple(vig.shape) != (B, F, 3):
+                raise ValueError(f'vig must be [B={B}, F={F}, 3], got {tuple(vig.shape)}')
+            self.vig = vig.detach().to(torch.float32).contiguous()
         pb = nat.TlProblem()
         pb.aim = _ptr(self.aim)
+        pb.vig = _ptr(self.vig)
         pb.x = nat.strided(self.xy[0], self.shape)
         pb.y = nat.strided(self.xy[1], self.shape)
         pb.z = nat.strided(self.z.reshape(B, 1, 1, 1), self.shape)
@@ -703,9 +712,9 @@ class _Staged:
         # staging, ray aiming (rtl:129-208; the map is applied on load) and the reference heights of the
         # fused pass: ONE launch
         nat.check(lib.tl_stage_ref(ctypes.byref(self.ln), ctypes.byref(pb), self.mu.data_ptr(), self.z.data_ptr(),
-                                   self.cy.data_ptr(), self.half_epd.data_ptr(), _ptr(self.aim),
-                                   int(bool(allow_backward_rays)), _ptr(self.ref_y), nat.stream_ptr(dev)),
-                  'tl_stage_ref')
+                                   self.cy.data_ptr(), self.half_epd.data_ptr(), _ptr(self.aim), _ptr(self.vig),
+                                   int(aim_mode), int(bool(allow_backward_rays)), _ptr(self.ref_y),
+                                   nat.stream_ptr(dev)), 'tl_stage_ref')
 
     def chain_rule(self, gmu, gz, gc, gt, gnd, gv):
         """ADDS the gradients induced through mu and z to gc, gt, gnd, gv [B,L] (tl_stage_bwd)."""
@@ -715,7 +724,7 @@ class _Staged:
 
 
 def _lens_spot_core(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, shard, group,
-                    want_grad, aimed, out=None, staged=None):
+                    want_grad, aimed, out=None, staged=None, vig=None, aim_mode=nat.AIM_REAL):
     """The staged fused pass itself (no autograd): staging kernel -> (ray aiming) -> chief rays ->
     fused trace+adjoint -> row reduction -> (all-reduce) -> finalize -> staging chain rule.
     Returns (rms [B], rms_field [B,F], gc, gt, gnd, gv) -- the four gradients of sum(rms) w.r.t. the
@@ -745,7 +754,8 @@ def _lens_spot_core(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward
             st.pb.p_begin, st.pb.p_end = int(p_begin), int(p_end)
         else:
             st = _Staged(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, aimed, p_begin,
-                         p_end, max_surfaces=nat.MAX_SURFACES_SPOT if want_grad else 64, want_ref=True)
+                         p_end, max_surfaces=nat.MAX_SURFACES_SPOT if want_grad else 64, want_ref=True, vig=vig,
+                         aim_mode=aim_mode)
         B, L, F, W, P = st.B, st.L, st.F, st.W, st.P
         pb = st.pb
         stream = nat.stream_ptr(dev)
@@ -792,7 +802,8 @@ class _LensTrace(torch.autograd.Function):
     x, y, cx, cy + the staging chain rule.  Outputs as trace_skew's: x, y, cx, cy, ray_ok, ray_backward."""
 
     @staticmethod
-    def forward(ctx, c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, aimed):
+    def forward(ctx, c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, aimed, vig=None,
+                aim_mode=nat.AIM_REAL):
         if any(ctx.needs_input_grad[4:8]):
             raise ValueError('the staged trace does not differentiate w.r.t. hfov / epd / pupil coordinates')
         lib = nat.load()
@@ -800,7 +811,7 @@ class _LensTrace(torch.autograd.Function):
         dev = c.device
         with torch.cuda.device(dev):
             st = _Staged(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, aimed,
-                         max_surfaces=nat.MAX_SURFACES_FWD)
+                         max_surfaces=nat.MAX_SURFACES_FWD, vig=vig, aim_mode=aim_mode)
             outs = torch.empty((4,) + st.shape, dtype=torch.float32, device=dev)
             flags = torch.empty((2,) + st.shape, dtype=torch.bool, device=dev)
             out = nat.TlTraceOut(*[outs[i].data_ptr() for i in range(4)], flags[0].data_ptr(), flags[1].data_ptr(),
@@ -838,17 +849,83 @@ class _LensTrace(torch.autograd.Function):
                                        ws_bytes, nat.stream_ptr(dev)), 'tl_trace_bwd')
             st.chain_rule(gmu, gz, grads[0], grads[1], grads[2], grads[3])
         need = ctx.needs_input_grad
-        return (*[grads[i] if need[i] else None for i in range(4)], None, None, None, None, None, None, None, None)
+        return (*[grads[i] if need[i] else None for i in range(4)], *([None] * 10))
 
 
 def lens_trace(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays=True, arith=nat.ARITH_GUARDED,
-               aimed=False):
+               aimed=False, vig=None, aim_mode=nat.AIM_REAL):
     """Staged ``trace_rays``: (x, y, cx, cy, ray_ok, ray_backward), differentiable w.r.t. c, t, nd, v."""
     out = _LensTrace.apply(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, bool(allow_backward_rays), int(arith),
-                           bool(aimed))
+                           bool(aimed), vig, int(aim_mode))
     out[1]._tl_staged = _LensTrace.last_staged      # the ray set, reusable by the fused pass of the same lens
     _LensTrace.last_staged = None
     return out
+
+
+class _LensPenalty(torch.autograd.Function):
+    """``RayTracer.penalty`` as ONE autograd node over the lens tensors: staging kernel (or the ray set
+    a staged pass of the same lens already built) -> fused penalty pass -> finalize -> staging chain
+    rule.  Returns penalty [B] (sum over rays of Q, optics_simulator_lite.py:441-448)."""
+
+    @staticmethod
+    def forward(ctx, c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, shard, group, scale,
+                aimed, staged, vig, aim_mode):
+        if any(ctx.needs_input_grad[4:8]):
+            raise ValueError('the staged penalty pass does not differentiate w.r.t. hfov / epd / pupil coordinates')
+        lib = nat.load()
+        nat.require_cuda(c, 'c')
+        dev = c.device
+        rank, world = shard
+        p_begin, p_end = pupil_slice(x_rel.shape[2], rank, world)
+        with torch.cuda.device(dev):
+            if staged is not None:
+                st = staged
+                st.pb.p_begin, st.pb.p_end = int(p_begin), int(p_end)
+            else:
+                st = _Staged(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, aimed, p_begin,
+                             p_end, max_surfaces=nat.MAX_SURFACES_BWD, vig=vig, aim_mode=aim_mode)
+            if st.L > nat.MAX_SURFACES_BWD:
+                raise ValueError(f'the fused penalty pass supports at most {nat.MAX_SURFACES_BWD} surfaces')
+            B, L, F, W = st.B, st.L, st.F, st.W
+            stream = nat.stream_ptr(dev)
+            n_acc = lib.tl_penalty_moment_count(L)
+            moments = torch.empty((B, F, W, n_acc), dtype=torch.float64, device=dev)
+            ws_bytes = lib.tl_penalty_workspace(ctypes.byref(st.pb))
+            if ws_bytes == 0:
+                nat.check(-1, 'tl_penalty_workspace')
+            ws = torch.empty((ws_bytes // 8,), dtype=torch.float64, device=dev)
+            nat.check(lib.tl_penalty_accumulate(ctypes.byref(st.pb), moments.data_ptr(), ws.data_ptr(), ws_bytes,
+                                                stream), 'tl_penalty_accumulate')
+            if world > 1:
+                moments = reduce_moments(moments, group)
+            penalty = torch.empty((B,), dtype=torch.float32, device=dev)
+            grads = torch.zeros((4, B, L), dtype=torch.float32, device=dev)       # gc, gt, gnd, gv
+            gmu = torch.empty((B, W, L), dtype=torch.float32, device=dev)
+            gz = torch.empty((B,), dtype=torch.float32, device=dev)
+            out = nat.TlPenaltyOut(penalty.data_ptr(), grads[0].data_ptr(), grads[1].data_ptr(), gmu.data_ptr(),
+                                   gz.data_ptr())
+            nat.check(lib.tl_penalty_finalize(moments.data_ptr(), B, F, W, L, float(scale), ctypes.byref(out), stream),
+                      'tl_penalty_finalize')
+            st.chain_rule(gmu, gz, grads[0], grads[1], grads[2], grads[3])
+        ctx.save_for_backward(grads)
+        return penalty
+
+    @staticmethod
+    def backward(ctx, grad_penalty):
+        (grads,) = ctx.saved_tensors
+        g = grad_penalty.to(torch.float32).reshape(1, -1, 1)
+        need = ctx.needs_input_grad
+        scaled = grads * g
+        return (*[scaled[i] if need[i] else None for i in range(4)], *([None] * 14))
+
+
+def lens_penalty(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, n_seq, allow_backward_rays=True,
+                 arith=nat.ARITH_GUARDED, shard=(0, 1), group=None, aimed=False, staged=None, vig=None,
+                 aim_mode=nat.AIM_REAL):
+    """Staged fused penalty pass: sum over rays of Q for every lens, [B], differentiable w.r.t. c, t, nd, v."""
+    return _LensPenalty.apply(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, bool(allow_backward_rays), int(arith),
+                              (int(shard[0]), int(shard[1])), group, 1.0 / float(n_seq), bool(aimed), staged, vig,
+                              int(aim_mode))
 
 
 class _LensSpotRms(torch.autograd.Function):
@@ -857,7 +934,7 @@ class _LensSpotRms(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, shard,
-                group, grad_on, aimed=False, staged=None):
+                group, grad_on, aimed=False, staged=None, vig=None, aim_mode=nat.AIM_REAL):
         if ctx.needs_input_grad[4] or ctx.needs_input_grad[5]:
             raise ValueError('the fused lens pass does not differentiate w.r.t. hfov / epd')
         if ctx.needs_input_grad[6] or ctx.needs_input_grad[7]:
@@ -866,7 +943,8 @@ class _LensSpotRms(torch.autograd.Function):
         want_grad = grad_on and any(ctx.needs_input_grad[:4])
         rms, rms_field, gc, gt, gnd, gv = _lens_spot_core(c, t, nd, v, hfov, epd, x_rel, y_rel, tables,
                                                           allow_backward_rays, arith, shard, group,
-                                                          want_grad, aimed, staged=staged)
+                                                          want_grad, aimed, staged=staged, vig=vig,
+                                                          aim_mode=aim_mode)
         if want_grad:
             ctx.save_for_backward(gc, gt, gnd, gv)
         ctx.mark_non_differentiable(rms_field)
@@ -875,32 +953,71 @@ class _LensSpotRms(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_rms, _grad_field):
         if len(ctx.saved_tensors) < 4:      # forward ran without gradients
-            return (None,) * 16
+            return (None,) * 18
         gc, gt, gnd, gv = ctx.saved_tensors
         g = grad_rms.to(torch.float32).reshape(-1, 1)
         need = ctx.needs_input_grad
         grads = [(gc * g) if need[0] else None, (gt * g) if need[1] else None,
                  (gnd * g) if need[2] else None, (gv * g) if need[3] else None]
-        return (*grads, None, None, None, None, None, None, None, None, None, None, None, None)
+        return (*grads, *([None] * 14))
 
 
 def lens_spot_rms_and_grads(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays=True,
-                            arith=nat.ARITH_GUARDED, shard=(0, 1), group=None, aimed=False, out=None):
+                            arith=nat.ARITH_GUARDED, shard=(0, 1), group=None, aimed=False, out=None, vig=None,
+                            aim_mode=nat.AIM_REAL):
     """:func:`lens_spot_rms` and the gradients of ``sum(rms)`` in one call, outside autograd:
     returns ``(rms [B], rms_field [B,F], {'c','t','nd','v': [B,L] gradients})``.  ``out`` may hold
     preallocated 'rms', 'gc', 'gt', 'gnd', 'gv' tensors (e.g. views of one staging buffer)."""
     rms, rms_field, gc, gt, gnd, gv = _lens_spot_core(c, t, nd, v, hfov, epd, x_rel, y_rel, tables,
                                                       bool(allow_backward_rays), int(arith),
                                                       (int(shard[0]), int(shard[1])), group, True,
-                                                      bool(aimed), out)
+                                                      bool(aimed), out, vig=vig, aim_mode=aim_mode)
     return rms, rms_field, {'c': gc, 't': gt, 'nd': gnd, 'v': gv}
 
 
 def lens_spot_rms(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays=True,
-                  arith=nat.ARITH_GUARDED, shard=(0, 1), group=None, aimed=False, staged=None):
+                  arith=nat.ARITH_GUARDED, shard=(0, 1), group=None, aimed=False, staged=None, vig=None,
+                  aim_mode=nat.AIM_REAL):
     """(rms [B], rms_field [B,F]) of a lens batch given as padded [B,L] tensors, differentiable
     w.r.t. c, t, nd, v.  x_rel, y_rel: relative pupil coordinates [1,1,P,1].  ``aimed``: with one
     iteration of 'real' ray aiming (rtl:129-208) done by tl_aim and applied inside the kernels."""
     return _LensSpotRms.apply(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, bool(allow_backward_rays),
                               int(arith), (int(shard[0]), int(shard[1])), group, torch.is_grad_enabled(),
-                              bool(aimed), staged)
+                              bool(aimed), staged, vig, int(aim_mode))
+
+
+# ---------------------------------------------------------------------------
+# Spot-diagram / PSF binning (compute_psf, ray_tracing.py:206-270 of the reference's TensorFlow original)
+# ---------------------------------------------------------------------------
+def psf_bin(x, y, y_target, x_incr, y_incr, x_size, y_size, n_bins):
+    """Gaussian soft histogram of image-plane points: x, y [G, C, R] (grid = lens x field, colour
+    channel, ray), per-grid centre / pitch / window [G].  Returns (sums [G, C, n_y, n_xh] float64 --
+    un-normalised, non-negative half of the x bins -- and inside [G, C] float64, the rays inside the
+    window).  One binning kernel + one fixed-order reduction; not differentiable."""
+    for name, v in (('x', x), ('y', y), ('y_target', y_target), ('x_incr', x_incr), ('y_incr', y_incr),
+                    ('x_size', x_size), ('y_size', y_size)):
+        nat.require_cuda(v, name)
+        if v.dtype != torch.float32:
+            raise TypeError(f'{name} must be float32')
+    if x.dim() != 3 or x.shape != y.shape:
+        raise ValueError('x and y must be [G, C, R] tensors of one shape')
+    G, C, R = x.shape
+    n_x, n_y = int(n_bins[0]), int(n_bins[1])
+    lib = nat.load()
+    dev = x.device
+    with torch.cuda.device(dev):
+        keep = [v.detach().contiguous() for v in (x, y, y_target, x_incr, y_incr, x_size, y_size)]
+        for v in keep[2:]:
+            if v.numel() != G:
+                raise ValueError('per-grid arguments must have G elements')
+        p = nat.TlPsf(*[v.data_ptr() for v in keep], G, C, R, n_x, n_y)
+        n_xh = n_x // 2 + 1 if n_x % 2 else n_x // 2
+        ws_bytes = lib.tl_psf_workspace(ctypes.byref(p))
+        if ws_bytes == 0:
+            nat.check(-1, 'tl_psf_workspace')
+        ws = torch.empty((ws_bytes // 8,), dtype=torch.float64, device=dev)
+        sums = torch.empty((G, C, n_y, n_xh), dtype=torch.float64, device=dev)
+        inside = torch.empty((G, C), dtype=torch.float64, device=dev)
+        nat.check(lib.tl_psf_bin(ctypes.byref(p), sums.data_ptr(), inside.data_ptr(), ws.data_ptr(), ws_bytes,
+                                 nat.stream_ptr(dev)), 'tl_psf_bin')
+    return sums, inside

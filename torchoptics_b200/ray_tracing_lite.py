@@ -297,6 +297,55 @@ def compute_rms2d(x, y, ray_ok):
     return ops.rms_of_trace(y, ray_ok)[0]
 
 
+def compute_psf(x, y, n_bins=(21, 21), increment=None, y_target=None):
+    """Spot diagram as a Gaussian soft histogram (the reference's ``compute_psf``, ray_tracing.py:206-270
+    of its TensorFlow original; same arguments and return values).
+
+    x, y: [n_lens, n_fields, n_channels, n_rays] image-plane points (the caller concatenates the rays'
+    x-mirror images, optics_simulator_lite.py:667-669: only the non-negative half of the x bins is
+    evaluated and mirrored).  One grid per (lens, field), centred on ``y_target`` (default: the mean
+    of y) in y and on 0 in x; bin pitch ``increment`` (then the extent is ``increment * n_x_bins`` in
+    BOTH directions, as rt_tf:224-226 has it), or -- single grid only, like the reference, whose line
+    267 does not broadcast otherwise -- fitted to the ray extent.  Returns ``(x_size, y_size, y_target
+    [n_grids], kernels [n_grids, n_channels, n_y_bins, n_x_bins] of unit mass, accounted
+    [n_lens, n_fields])`` -- the last the fraction of rays inside the grid.  The binning runs as one
+    CUDA kernel (``tl_psf_bin``); it is not differentiable."""
+    nat.require_cuda(x, 'x')
+    nat.require_cuda(y, 'y')
+    if x.dim() != 4 or x.shape != y.shape:
+        raise ValueError('x and y must be [n_lens, n_fields, n_channels, n_rays]')
+    x = x.detach().to(torch.float32)
+    y = y.detach().to(torch.float32)
+    n_lens, n_fields, n_channels, n_rays = x.shape
+    n_grids = n_lens * n_fields
+    n_x_bins, n_y_bins = int(n_bins[0]), int(n_bins[1])
+    flat_y = y.reshape(n_grids, -1)
+    if y_target is None:
+        y_target = flat_y.mean(dim=1)                                                  # rt_tf:218
+    y_target = torch.as_tensor(y_target, dtype=torch.float32, device=x.device).reshape(n_grids)
+    if increment is not None:                                                          # rt_tf:223-226
+        x_incr = y_incr = torch.full((n_grids,), float(increment), dtype=torch.float32, device=x.device)
+        x_size = y_size = increment * n_x_bins
+        x_win = y_win = torch.full((n_grids,), float(increment * n_x_bins), dtype=torch.float32, device=x.device)
+    else:                                                                              # rt_tf:228-235
+        if n_grids != 1:
+            raise ValueError('compute_psf without `increment` handles a single (lens, field) grid, like the '
+                             'reference (ray_tracing.py:267 does not broadcast over several)')
+        centred = flat_y - y_target[:, None]
+        x_size = x_win = x.reshape(n_grids, -1).amax(dim=1)
+        y_size = y_win = 2 * torch.maximum(centred.amax(dim=1) - y_target, y_target - centred.amin(dim=1))
+        x_incr, y_incr = x_size / n_x_bins, y_size / n_y_bins
+    sums, inside = ops.psf_bin(x.reshape(n_grids, n_channels, n_rays), y.reshape(n_grids, n_channels, n_rays),
+                               y_target, x_incr, y_incr, x_win, y_win, (n_x_bins, n_y_bins))
+    if n_x_bins % 2 == 1:                                                              # rt_tf:257-260
+        full = torch.cat((sums[..., 1:].flip(-1), sums), dim=-1)
+    else:
+        full = torch.cat((sums.flip(-1), sums), dim=-1)
+    kernels = (full / full.sum(dim=(-1, -2), keepdim=True)).to(torch.float32)          # rt_tf:263
+    accounted = (inside.sum(dim=1) / (n_channels * n_rays)).to(torch.float32).reshape(n_lens, n_fields)
+    return x_size, y_size, y_target, kernels, accounted
+
+
 def compute_rms2d_all(y, ray_ok):
     """:func:`compute_rms2d` for every lens of the batch: (rms [B], rms_field [B,F])."""
     return ops.spot_rms_from_rays(y, ray_ok)
@@ -425,7 +474,8 @@ class RayTracer:
                 and lens.c.is_cuda and lens.c.shape[1] <= nat.MAX_SURFACES_FWD and lens.c.shape[1] <= 64):
             x_rel, y_rel = self._pupil(None)
             out = ops.lens_trace(lens.c, lens.t, lens.nd, lens.v, specs.hfov, specs.epd, x_rel, y_rel,
-                                 self._tables(lens), self.allow_backward_rays, _arith_code(self.arith), aimed)
+                                 self._tables(lens), self.allow_backward_rays, _arith_code(self.arith), aimed,
+                                 **self._staged_kwargs(specs, lens, use_vig))
             self._remember(out, specs, lens, use_vig)
             return out
         args = self._ray_set(specs, lens, use_vig, xy, up_to_stop)
@@ -447,24 +497,34 @@ class RayTracer:
                            'versions': [v._version for v in tensors], 'ok': weakref.ref(out[4]),
                            'ok_version': out[4]._version, 'y_version': out[1]._version}
 
-    def penalty(self, specs, lens, use_vig=True, shard=(0, 1), group=None, n_seq=None):
+    def penalty(self, specs, lens, use_vig=True, shard=(0, 1), group=None, n_seq=None, staged=True, _ray_set=None):
         """The ray-angle / ray-path penalty ``sum(Q)`` that ``compute_loss_out`` adds to the RMS
         (optics_simulator_lite.py:430-450), for every lens [B], fused: equal to summing
         ``(sum_k theta_norm + sum_k theta_prime_norm + sum_k z_RELU) / n_seq`` over the stacks of
         ``trace_rays(..., aggregate=True)`` but without materialising them.  ``n_seq`` defaults to
-        the number of surfaces of the (first) lens' sequence, as in the reference (osl:441)."""
-        args = self._ray_set(specs, lens, use_vig)
+        the number of surfaces of the (first) lens' sequence, as in the reference (osl:441).
+        ``staged`` as in :meth:`spot_rms`: the ray set comes from the staging kernel."""
         if any(v is not None for v in self._extension_tables(lens).values()):
             raise ValueError('the penalty terms exist for spherical lenses only')
         if n_seq is None:
             n_seq = int(np.asarray(lens.structure.mask)[0].sum())      # host-side constant: no sync
+        can_stage, aimed = self._staging(lens, use_vig)
+        if staged and can_stage and lens.c.shape[1] <= nat.MAX_SURFACES_BWD:
+            x_rel, y_rel = self._pupil(None)
+            return ops.lens_penalty(lens.c, lens.t, lens.nd, lens.v, specs.hfov, specs.epd, x_rel, y_rel,
+                                    self._tables(lens), n_seq, self.allow_backward_rays, _arith_code(self.arith), shard,
+                                    group, aimed=aimed, staged=_ray_set, **self._staged_kwargs(specs, lens, use_vig))
+        args = self._ray_set(specs, lens, use_vig)
         return ops.penalty_sum(*args, n_seq, self.allow_backward_rays, _arith_code(self.arith), shard, group)
 
     def loss_unsup(self, specs, lens, penalty_rate=0.2, use_vig=True, shard=(0, 1), group=None, n_seq=None):
-        """``compute_loss_out`` (optics_simulator_lite.py:430-450) as two fused passes:
-        ``{'loss_unsup': rms + penalty_rate * penalty, 'rms': rms, 'penalty': penalty}``, each a [B]
-        tensor (the reference evaluates lens 0's RMS and sums the penalty over the batch; a
-        one-lens batch gives its numbers)."""
+        """``compute_loss_out`` (optics_simulator_lite.py:430-450) for EVERY lens of the batch as two
+        fused passes over one staged ray set: ``{'loss_unsup': rms + penalty_rate * penalty, 'rms':
+        rms, 'penalty': penalty}``, each a [B] tensor.  This is the batched form of the reference's
+        per-sample loop ``Optical_Loss.optical_loss_unsupervised`` (optical_loss.py:99-122), which
+        builds a RaytracedOptics per sample and traces 8 fields x 64 pupil points x 3 wavelengths one
+        lens at a time (the reference evaluates lens 0's RMS and sums the penalty over its one-lens
+        batch; a one-lens batch here gives its numbers)."""
         rms, _ = self.spot_rms(specs, lens, use_vig, shard, group)
         pen = self.penalty(specs, lens, use_vig, shard, group, n_seq)
         return {'loss_unsup': rms + penalty_rate * pen, 'rms': rms, 'penalty': pen}
@@ -486,22 +546,42 @@ class RayTracer:
             x_rel, y_rel = self._pupil(None)
             return ops.lens_spot_rms(lens.c, lens.t, lens.nd, lens.v, specs.hfov, specs.epd, x_rel,
                                      y_rel, self._tables(lens), self.allow_backward_rays,
-                                     _arith_code(self.arith), shard, group, aimed=aimed, staged=_ray_set)
+                                     _arith_code(self.arith), shard, group, aimed=aimed, staged=_ray_set,
+                                     **self._staged_kwargs(specs, lens, use_vig))
         args = self._ray_set(specs, lens, use_vig)
         return ops.spot_rms(*args, self.allow_backward_rays, _arith_code(self.arith), shard, group, **ext)
 
     def _staging(self, lens, use_vig=True):
         """(can the staged kernels build this ray set?, with the ray-aiming kernel?)"""
-        no_vig = self.vig_fn is None or not use_vig
-        # ray aiming stays on the staged path when the device kernel covers it (one iteration,
-        # 'real' stop radius); a lens batch whose stops are all in front needs none (rtl:131-133)
+        # ray aiming stays on the staged path when the device kernel covers it (one iteration, 'real' or
+        # 'paraxial' stop radius); a lens batch whose stops are all in front needs none (rtl:131-133)
         stops_in_front = bool((np.asarray(lens.structure.stop_idx) == 0).all())
-        aimed = (self.n_ray_aiming_iter == 1 and self.ray_aiming_mode == 'real' and self.device_aiming
+        aimed = (self.n_ray_aiming_iter == 1 and self.ray_aiming_mode in ('real', 'paraxial') and self.device_aiming
                  and not stops_in_front)
-        plain = no_vig and (self.n_ray_aiming_iter == 0 or aimed or stops_in_front)
+        plain = self.n_ray_aiming_iter == 0 or aimed or stops_in_front
         general = any(v is not None for v in self._extension_tables(lens).values())
-        ok = plain and not general and self.mode != 'skew_random' and lens.c.shape[1] <= 64
+        vignetted = self.vig_fn is not None and use_vig
+        ok = plain and not general and self.mode != 'skew_random' and lens.c.shape[1] <= 64 \
+            and not (vignetted and self.mode == 'chief')
         return ok, aimed
+
+    def _staged_kwargs(self, specs, lens, use_vig=True):
+        """Pupil vignetting table and stop-radius mode for the staged kernels."""
+        vig = self._vig_table(specs) if (self.vig_fn is not None and use_vig and self.mode != 'chief') else None
+        mode = nat.AIM_PARAXIAL if self.ray_aiming_mode == 'paraxial' else nat.AIM_REAL
+        return dict(vig=vig, aim_mode=mode)
+
+    def _vig_table(self, specs):
+        """[B,F,3] = (x_scale, y_scale, y_offset) of apply_vignetting (rt_tf:479-490) with the factors
+        the user's vignetting function gives per (lens, field) (rtl:98-104) -- the form the kernels
+        apply on load, each step individually rounded like the reference's eager ops."""
+        fields = self._fields()[None, :]
+        vig_up = self.vig_fn(fields, specs.vig_up)
+        vig_down = self.vig_fn(fields, specs.vig_down)
+        vig_x = self.vig_fn(fields, specs.vig_x)
+        B, F = specs.epd.shape[0], fields.shape[1]
+        table = torch.stack((1 - (vig_x + vig_x) / 2, 1 - (vig_up + vig_down) / 2, (vig_down - vig_up) / 2), dim=-1)
+        return torch.broadcast_to(table.to(torch.float32), (B, F, 3)).to(self.default_device).contiguous()
 
     def spot_rms_and_grads(self, specs, lens, use_vig=True, shard=(0, 1), group=None, out=None):
         """:meth:`spot_rms` together with the gradients of ``sum(rms)`` w.r.t. the lens tensors, as
@@ -514,7 +594,8 @@ class RayTracer:
             x_rel, y_rel = self._pupil(None)
             rms, _, grads = ops.lens_spot_rms_and_grads(lens.c, lens.t, lens.nd, lens.v, specs.hfov, specs.epd,
                                                         x_rel, y_rel, self._tables(lens), self.allow_backward_rays,
-                                                        _arith_code(self.arith), shard, group, aimed, out)
+                                                        _arith_code(self.arith), shard, group, aimed, out,
+                                                        **self._staged_kwargs(specs, lens, use_vig))
             return rms, grads
         leaves = {k: getattr(lens, k).detach().requires_grad_(True) for k in ('c', 't', 'nd', 'v')}
         from .lens_modeling import Lens
@@ -550,14 +631,14 @@ class RayTracer:
         if (lens.structure.stop_idx == 0).all():
             return lambda xp_rel, yp_rel: (xp_rel, yp_rel)
         dev = self.default_device
-        on_device = (self.device_aiming and self.ray_aiming_mode == 'real' and self.n_ray_aiming_iter == 1
-                     and not (use_vig and self.vig_fn) and lens.c.is_cuda and lens.c.shape[1] <= 64
+        on_device = (self.device_aiming and self.ray_aiming_mode in ('real', 'paraxial') and self.n_ray_aiming_iter == 1
+                     and lens.c.is_cuda and lens.c.shape[1] <= 64
                      and getattr(lens, 'k', None) is None and getattr(lens, 'a', None) is None
                      and getattr(lens, 'sd', None) is None)
         if on_device:
             # one kernel (tl_aim) instead of three nested traces and two backward calls
             gains = ops.aim_table(lens.c, lens.t, lens.nd, lens.v, specs.hfov, specs.epd, self._tables(lens),
-                                  self.allow_backward_rays)                       # [B,F,W,3]
+                                  self.allow_backward_rays, **self._staged_kwargs(specs, lens, use_vig))   # [B,F,W,3]
             x_gain, y_gain, y_shift = (gains[..., j].unsqueeze(2) for j in range(3))   # [B,F,1,W]
             return lambda xp_rel, yp_rel: (xp_rel * x_gain, yp_rel * y_gain + y_shift)
         specs2stop = specs.up_to_stop()
