@@ -164,6 +164,55 @@ __device__ __noinline__ void mirror_live_lane_rev(float *mine, int S, int ncomp,
   }
 }
 
+// Everything about the rays of one (lens, field, wavelength) row that does not depend on the pupil
+// index, gathered once per row: the generic strided load (five tensors x four rays x four 64-bit
+// index products, plus the vignetting / aiming records) cost ~350 instructions per 128-ray group,
+// 6 % of the kernel (profiles/r2c).  With it a ray costs two indexed loads and the few map steps.
+struct RowRays {
+  const float *x, *y;                    // element (b, f, 0, w) of the pupil coordinates
+  float z0, cx0, cy0;                    // z, cx, cy themselves when all three are pupil-invariant
+  float vig[3], aim[3], xy_scale;        // apply_vignetting record, ray-aiming record (load_pupil_point)
+};
+// (strides and the presence of the optional tables are kernel parameters: read from the constant bank
+// where they are used, they cost no registers)
+__device__ __forceinline__ bool row_uniform_zc(const TlProblem &pb) {
+  return pb.z.stride[2] == 0 && pb.cx.stride[2] == 0 && pb.cy.stride[2] == 0;
+}
+
+__device__ __forceinline__ RowRays load_row_rays(const TlProblem &pb, int b, int f, int w) {
+  RowRays r;
+  r.x = pb.x.ptr + offset_of(pb.x, b, f, 0, w);
+  r.y = pb.y.ptr + offset_of(pb.y, b, f, 0, w);
+  r.z0 = pb.z.ptr[offset_of(pb.z, b, f, 0, w)];
+  r.cx0 = pb.cx.ptr[offset_of(pb.cx, b, f, 0, w)];
+  r.cy0 = pb.cy.ptr[offset_of(pb.cy, b, f, 0, w)];
+  r.xy_scale = pb.xy_scale ? pb.xy_scale[b] : 1.0f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    r.vig[j] = pb.vig ? pb.vig[((int64_t)b * pb.F + f) * 3 + j] : 0.f;
+    r.aim[j] = pb.aim ? pb.aim[(((int64_t)b * pb.F + f) * pb.W + w) * 3 + j] : 0.f;
+  }
+  return r;
+}
+
+// load_pupil_point (trace_kernels.cu) on a row record: the same individually rounded steps
+__device__ __forceinline__ void row_pupil_point(const TlProblem &pb, const RowRays &r, int q, float &x, float &y) {
+  x = r.x[q * pb.x.stride[2]];
+  y = r.y[q * pb.y.stride[2]];
+  if (pb.vig) {
+    x = __fmul_rn(x, r.vig[0]);
+    y = __fadd_rn(__fmul_rn(y, r.vig[1]), r.vig[2]);
+  }
+  if (pb.aim) {
+    x = fminf(fmaxf(__fmul_rn(x, r.aim[0]), -2.0f), 2.0f);
+    y = fminf(fmaxf(__fadd_rn(__fmul_rn(y, r.aim[1]), r.aim[2]), -2.0f), 2.0f);
+  }
+  if (pb.xy_scale) {
+    x = __fmul_rn(x, r.xy_scale);
+    y = __fmul_rn(y, r.xy_scale);
+  }
+}
+
 template <int NS_MAX, int NW, int ACC, int NCOMP>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_spot_rev(TlProblem pb, RevArgs args) {
@@ -211,7 +260,8 @@ k_spot_rev(TlProblem pb, RevArgs args) {
   float acc[6][NA];      // wac_c, acc_c, wac_t, acc_t, wac_mu, acc_mu
   float acc_z = 0.f, wac_z = 0.f, m_s1 = 0.f, m_s2 = 0.f, m_n = 0.f;
   RevTable tab;
-  float y0 = 0.f, xy_scale = 1.0f;
+  RowRays rr;
+  float y0 = 0.f;
   int row = -1, b = 0, f = 0, w = 0;
 
   auto reset = [&]() {
@@ -290,7 +340,7 @@ k_spot_rev(TlProblem pb, RevArgs args) {
       f = (r / pb.W) % pb.F;
       b = r / (pb.W * pb.F);
       tab = load_rev_table(wbase, pb, b, w, lane);
-      xy_scale = pb.xy_scale ? pb.xy_scale[b] : 1.0f;
+      rr = load_row_rays(pb, b, f, w);
       y0 = args.ref_y[b * pb.F + f];
       reset();
     }
@@ -306,12 +356,19 @@ k_spot_rev(TlProblem pb, RevArgs args) {
       has[l] = p < pb.p_end;
       const int q = has[l] ? p : pb.p_end - 1;
       float px, py;
-      load_pupil_point(pb, b, f, q, w, xy_scale, px, py);
+      row_pupil_point(pb, rr, q, px, py);
       lane_set(x, l, px);
       lane_set(y, l, py);
-      lane_set(z, l, pb.z.ptr[offset_of(pb.z, b, f, q, w)]);
-      lane_set(cx, l, pb.cx.ptr[offset_of(pb.cx, b, f, q, w)]);
-      lane_set(cy, l, pb.cy.ptr[offset_of(pb.cy, b, f, q, w)]);
+      if (!row_uniform_zc(pb)) {
+        lane_set(z, l, pb.z.ptr[offset_of(pb.z, b, f, q, w)]);
+        lane_set(cx, l, pb.cx.ptr[offset_of(pb.cx, b, f, q, w)]);
+        lane_set(cy, l, pb.cy.ptr[offset_of(pb.cy, b, f, q, w)]);
+      }
+    }
+    if (row_uniform_zc(pb)) {
+      z = V(rr.z0);
+      cx = V(rr.cx0);
+      cy = V(rr.cy0);
     }
 
     // ---- forward: fast policy for all four lanes, parking (dist, cos[, cos']) per surface ----
@@ -385,7 +442,19 @@ k_spot_rev(TlProblem pb, RevArgs args) {
     m_s1 += lane_sum(wgt);
     m_s2 = lane_dot(wgt, wgt, m_s2);
     m_n += lane_sum(alive);
-    if (!all_ok && any_ok) mirror_live_lane_rev(mine, S, NCOMP, ok, pre, x_img, y_img);
+    if (!all_ok && any_ok) {
+      // (copies: the helper takes addresses, and address-taken variables live in local memory -- of `pre`,
+      // `x_img`, `y_img` and `ok` themselves that cost 8 STL.128 + 8 LDL per group on the common path)
+      bool ok_copy[N];
+#pragma unroll
+      for (int l = 0; l < N; ++l) ok_copy[l] = ok[l];
+      Ray<V> pre_copy = pre;
+      V x_copy = x_img, y_copy = y_img;
+      mirror_live_lane_rev(mine, S, NCOMP, ok_copy, pre_copy, x_copy, y_copy);
+      pre = pre_copy;
+      x_img = x_copy;
+      y_img = y_copy;
+    }
 
     // ---- adjoint: unit seed on y, backward walk ----
     // (a thread none of whose rays is alive still runs the sweep -- the accumulator accesses are
