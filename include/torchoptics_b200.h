@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TL_ABI_VERSION 10
+#define TL_ABI_VERSION 11
 
 enum {
   TL_OK = 0,
@@ -311,9 +311,33 @@ size_t tl_psf_workspace(const TlPsf *psf);
 int tl_psf_bin(const TlPsf *psf, double *sums, double *inside, void *workspace, size_t workspace_bytes,
                void *stream);
 
+/* Paraxial (ABCD) front end of a padded lens batch, one thread per lens:
+ * `get_first_order` rtl:772-794 and `compute_last_curvature` rtl:725-769 (over
+ * `interface_propagation_abcd` rtl:314-327 / `reduce_abcd` rtl:301-311), which the reference's
+ * consumer runs once per sample in a Python loop (optical_loss.py:63-64, :99-115).
+ *   c, t [B,L]; n [B,L] = refractive index BEHIND each slot (1 behind air slots and padding);
+ *   live, glass [B,L] bytes = Structure.mask / mask_G (prefix masks, as the reference assumes).
+ * tl_paraxial_fwd writes out [B,2]:
+ *   TL_PARAXIAL_FIRST_ORDER      (EFL, BFL), the last live slot's thickness taken as 0 (rtl:781-783)
+ *   TL_PARAXIAL_LAST_CURVATURE   (the curvature that makes EFL = 1, the slot it belongs to): the slot is the
+ *                                last one, or the one before it when the sequence ends air-air
+ *                                (rtl:735-738); c at and behind that slot is not read.
+ * tl_paraxial_bwd: gout [B,2] (column 1 of LAST_CURVATURE ignored) -> gc, gt, gn [B,L], every element
+ * written.  L <= TL_PARAXIAL_MAX_SLOTS. */
+#define TL_PARAXIAL_MAX_SLOTS 64
+enum { TL_PARAXIAL_FIRST_ORDER = 0, TL_PARAXIAL_LAST_CURVATURE = 1 };
+typedef struct TlParaxial {
+  const float *c, *t, *n;          /* [B,L] */
+  const uint8_t *live, *glass;     /* [B,L] */
+  int32_t B, L;
+  int32_t mode;
+} TlParaxial;
+int tl_paraxial_fwd(const TlParaxial *lens, float *out, void *stream);
+int tl_paraxial_bwd(const TlParaxial *lens, const float *gout, float *gc, float *gt, float *gn, void *stream);
+
 /* Layout self-description, so that a binding can check itself against the library it loaded:
  * for struct `which` (0 TlStrided, 1 TlProblem, 2 TlTraceOut, 3 TlSeeds, 4 TlGrads, 5 TlSpotOut,
- * 6 TlPenaltyOut, 7 TlLens, 8 TlPsf) returns "Name:sizeof;field@offsetof;field@offsetof;..." in declaration
+ * 6 TlPenaltyOut, 7 TlLens, 8 TlPsf, 9 TlParaxial) returns "Name:sizeof;field@offsetof;field@offsetof;..." in declaration
  * order (thread-local storage, valid until the next call), or NULL for an unknown struct. */
 const char *tl_abi_describe(int32_t which);
 

@@ -173,3 +173,18 @@ def forward_mode(x, y, z, cx, cy, c, t, mu):
     lib().hc_forward_mode(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(cx), _p(cy), ctypes.c_int(c.size), _p(c),
                           _p(t), _p(mu), _p(ox), _p(oy), _p(jac))
     return ox, oy, jac
+
+
+def paraxial(mode, c, t, n, live, glass, gout=None):
+    """csrc/paraxial.cuh on the host: out [B,2] (and gc, gt, gn [B,L] when gout [B,2] is given)."""
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    c, t, n = map(f, (c, t, n))
+    live = np.ascontiguousarray(live, dtype=np.uint8)
+    glass = np.ascontiguousarray(glass, dtype=np.uint8)
+    B, L = c.shape
+    out = np.zeros((B, 2), np.float32)
+    grads = [np.zeros((B, L), np.float32) for _ in range(3)]
+    g = None if gout is None else f(gout)
+    lib().hc_paraxial(ctypes.c_int(B), ctypes.c_int(L), ctypes.c_int(mode), _p(c), _p(t), _p(n), _p(live), _p(glass),
+                      _p(g), _p(out), *[_p(v) for v in grads])
+    return (out, *grads) if gout is not None else out

@@ -9,7 +9,8 @@ SO = os.path.join(HERE, '_hostcore.so')
 def build(force=False):
     src = os.path.join(HERE, 'hostcore.cpp')
     csrc = os.path.join(HERE, '..', '..', 'torchoptics_b200', 'csrc')
-    deps = [src, os.path.join(csrc, 'trace_core.cuh'), os.path.join(csrc, 'trace_core_asph.cuh')]
+    deps = [src, os.path.join(csrc, 'trace_core.cuh'), os.path.join(csrc, 'trace_core_asph.cuh'),
+            os.path.join(csrc, 'paraxial.cuh'), os.path.join(HERE, '..', '..', 'include', 'torchoptics_b200.h')]
     if (not force and os.path.exists(SO)
             and os.path.getmtime(SO) >= max(os.path.getmtime(d) for d in deps)):
         return SO

@@ -358,3 +358,16 @@ extern "C" void hc_forward_mode(int64_t n, const float *x, const float *y, const
     jac[4 * i + 0] = r.x.a; jac[4 * i + 1] = r.x.b; jac[4 * i + 2] = r.y.a; jac[4 * i + 3] = r.y.b;
   }
 }
+
+// ---- paraxial front end (csrc/paraxial.cuh): the per-lens functions the kernels k_paraxial_fwd / _bwd call ----
+#include "../../include/torchoptics_b200.h"
+#include "../../torchoptics_b200/csrc/paraxial.cuh"
+extern "C" void hc_paraxial(int B, int L, int mode, const float *c, const float *t, const float *n,
+                            const uint8_t *live, const uint8_t *glass, const float *gout, float *out, float *gc,
+                            float *gt, float *gn) {
+  TlParaxial p{c, t, n, live, glass, B, L, mode};
+  for (int b = 0; b < B; ++b) {
+    paraxial_fwd_one(p, b, out);
+    if (gout) paraxial_bwd_one(p, b, gout, gc, gt, gn);
+  }
+}

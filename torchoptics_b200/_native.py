@@ -12,11 +12,14 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('TL_LIB_OVERRIDE') or os.path.join(_PKG, 'libtorchoptics_b200.so')   # override: kernel experiments only
 
-ABI_VERSION = 10
+ABI_VERSION = 11
 ARITH_GUARDED = 0
 ARITH_EXACT = 1
 AIM_REAL = 0
 AIM_PARAXIAL = 1
+PARAXIAL_FIRST_ORDER = 0
+PARAXIAL_LAST_CURVATURE = 1
+PARAXIAL_MAX_SLOTS = 64
 MAX_SURFACES_FWD = 256
 MAX_SURFACES_BWD = 32
 MAX_SURFACES_SPOT = 16
@@ -75,6 +78,11 @@ class TlPsf(ctypes.Structure):
                [(n, ctypes.c_int32) for n in ('G', 'C', 'R', 'n_x_bins', 'n_y_bins')]
 
 
+class TlParaxial(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ('c', 't', 'n', 'live', 'glass')] + \
+               [(n, ctypes.c_int32) for n in ('B', 'L', 'mode')]
+
+
 class TlSpotOut(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ('rms', 'rms_field', 'gc', 'gt', 'gmu', 'gz', 'gk', 'ga')]
 
@@ -120,6 +128,8 @@ EXPORTS = {
     'tl_psf_workspace': (ctypes.c_size_t, [ctypes.POINTER(TlPsf)]),
     'tl_psf_bin': (ctypes.c_int, [ctypes.POINTER(TlPsf), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                   ctypes.c_void_p]),
+    'tl_paraxial_fwd': (ctypes.c_int, [ctypes.POINTER(TlParaxial), ctypes.c_void_p, ctypes.c_void_p]),
+    'tl_paraxial_bwd': (ctypes.c_int, [ctypes.POINTER(TlParaxial)] + [ctypes.c_void_p] * 5),
     'tl_penalty_moment_count': (ctypes.c_int32, [ctypes.c_int32]),
     'tl_penalty_workspace': (ctypes.c_size_t, [ctypes.POINTER(TlProblem)]),
     'tl_penalty_accumulate': (ctypes.c_int, [ctypes.POINTER(TlProblem), ctypes.c_void_p, ctypes.c_void_p,
@@ -138,7 +148,7 @@ EXPORTS = {
 }
 
 # struct ids of tl_abi_layout
-LAYOUT_STRUCTS = (TlStrided, TlProblem, TlTraceOut, TlSeeds, TlGrads, TlSpotOut, TlPenaltyOut, TlLens, TlPsf)
+LAYOUT_STRUCTS = (TlStrided, TlProblem, TlTraceOut, TlSeeds, TlGrads, TlSpotOut, TlPenaltyOut, TlLens, TlPsf, TlParaxial)
 
 _lib = None
 

@@ -16,7 +16,7 @@ LIB = os.path.join(PKG, 'libtorchoptics_b200.so')
 SOURCES = [os.path.join(CSRC, 'trace_kernels.cu')]
 HEADERS = [os.path.join(CSRC, 'trace_core.cuh'), os.path.join(CSRC, 'trace_core_asph.cuh'),
            os.path.join(CSRC, 'trace_kernels_gen.cuh'), os.path.join(CSRC, 'peer_exchange.cuh'),
-           os.path.join(CSRC, 'spot_rev.cuh'),
+           os.path.join(CSRC, 'spot_rev.cuh'), os.path.join(CSRC, 'psf_kernels.cuh'), os.path.join(CSRC, 'paraxial.cuh'),
            os.path.join(PKG, '..', 'include', 'torchoptics_b200.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',

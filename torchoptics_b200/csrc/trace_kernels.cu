@@ -1744,6 +1744,7 @@ int reduce_rows(const AdjPlan &pl, const double *partial, double *rows_out, int 
 
 #include "spot_rev.cuh"
 #include "psf_kernels.cuh"
+#include "paraxial.cuh"
 
 // K3c: the backward kernels (MODE_BWD of k_trace_adj: plain, with seeded stacks, and the fused
 // penalty pass PEN_SUM) with a warp per row, for the same many-short-rows workload as k_spot_rows.
@@ -2080,6 +2081,7 @@ const char *tl_abi_describe(int32_t which) {
     case 6: TL_SIZE(TlPenaltyOut); TL_OFF(TlPenaltyOut, penalty); TL_OFF(TlPenaltyOut, gc); TL_OFF(TlPenaltyOut, gt); TL_OFF(TlPenaltyOut, gmu); TL_OFF(TlPenaltyOut, gz); break;
     case 7: TL_SIZE(TlLens); TL_OFF(TlLens, c); TL_OFF(TlLens, t); TL_OFF(TlLens, nd); TL_OFF(TlLens, v); TL_OFF(TlLens, mask); TL_OFF(TlLens, mask_g); TL_OFF(TlLens, stop_idx); TL_OFF(TlLens, hfov); TL_OFF(TlLens, epd); TL_OFF(TlLens, rel_fields); TL_OFF(TlLens, wavelengths); TL_OFF(TlLens, B); TL_OFF(TlLens, L); TL_OFF(TlLens, F); TL_OFF(TlLens, W); break;
     case 8: TL_SIZE(TlPsf); TL_OFF(TlPsf, x); TL_OFF(TlPsf, y); TL_OFF(TlPsf, y_target); TL_OFF(TlPsf, x_incr); TL_OFF(TlPsf, y_incr); TL_OFF(TlPsf, x_size); TL_OFF(TlPsf, y_size); TL_OFF(TlPsf, G); TL_OFF(TlPsf, C); TL_OFF(TlPsf, R); TL_OFF(TlPsf, n_x_bins); TL_OFF(TlPsf, n_y_bins); break;
+    case 9: TL_SIZE(TlParaxial); TL_OFF(TlParaxial, c); TL_OFF(TlParaxial, t); TL_OFF(TlParaxial, n); TL_OFF(TlParaxial, live); TL_OFF(TlParaxial, glass); TL_OFF(TlParaxial, B); TL_OFF(TlParaxial, L); TL_OFF(TlParaxial, mode); break;
     default: return nullptr;
   }
 #undef TL_SIZE
@@ -2435,6 +2437,36 @@ int tl_spot_kernel_only(const TlProblem *pb, const float *ref_y, void *workspace
   TL_CHECK_CUDA(cudaLaunchKernel((const void *)pl.kernel, dim3(pl.n_blocks), dim3(pl.n_warps_cta * 32), params,
                                  pl.smem, (cudaStream_t)stream_));
   g_launches++;
+  return TL_OK;
+}
+
+static int check_paraxial(const TlParaxial *p, const char *who) {
+  if (!p || !p->c || !p->t || !p->n || !p->live || !p->glass) return fail(TL_ERR_INVALID, "tl_paraxial: NULL argument%s");
+  if (p->B < 1 || p->L < 1 || p->L > TL_PARAXIAL_MAX_SLOTS)
+    return fail(TL_ERR_INVALID, "tl_paraxial: B >= 1 and 1 <= L <= 64%s");
+  if (p->mode != TL_PARAXIAL_FIRST_ORDER && p->mode != TL_PARAXIAL_LAST_CURVATURE)
+    return fail(TL_ERR_INVALID, "tl_paraxial: unknown mode%s");
+  (void)who;
+  return TL_OK;
+}
+
+int tl_paraxial_fwd(const TlParaxial *lens, float *out, void *stream_) {
+  int rc = check_paraxial(lens, "tl_paraxial_fwd");
+  if (rc) return rc;
+  if (!out) return fail(TL_ERR_INVALID, "tl_paraxial_fwd: NULL output%s");
+  k_paraxial_fwd<<<(lens->B + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(*lens, out);
+  g_launches++;
+  TL_CHECK_CUDA(cudaGetLastError());
+  return TL_OK;
+}
+
+int tl_paraxial_bwd(const TlParaxial *lens, const float *gout, float *gc, float *gt, float *gn, void *stream_) {
+  int rc = check_paraxial(lens, "tl_paraxial_bwd");
+  if (rc) return rc;
+  if (!gout || !gc || !gt || !gn) return fail(TL_ERR_INVALID, "tl_paraxial_bwd: NULL argument%s");
+  k_paraxial_bwd<<<(lens->B + 63) / 64, 64, 0, (cudaStream_t)stream_>>>(*lens, gout, gc, gt, gn);
+  g_launches++;
+  TL_CHECK_CUDA(cudaGetLastError());
   return TL_OK;
 }
 

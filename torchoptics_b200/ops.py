@@ -1021,3 +1021,69 @@ def psf_bin(x, y, y_target, x_incr, y_incr, x_size, y_size, n_bins):
         nat.check(lib.tl_psf_bin(ctypes.byref(p), sums.data_ptr(), inside.data_ptr(), ws.data_ptr(), ws_bytes,
                                  nat.stream_ptr(dev)), 'tl_psf_bin')
     return sums, inside
+
+
+# ---------------------------------------------------------------------------
+# Paraxial front end of a padded lens batch (get_first_order rtl:772-794, compute_last_curvature
+# rtl:725-769): one thread per lens, forward and hand-derived adjoint (csrc/paraxial.cuh)
+# ---------------------------------------------------------------------------
+class _Paraxial(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, c, t, n, live, glass, mode):
+        for name, v in (('c', c), ('t', t), ('n', n)):
+            nat.require_cuda(v, name)
+            if v.dtype != torch.float32 or v.dim() != 2:
+                raise TypeError(f'{name} must be a [B, L] float32 tensor')
+        if not (c.shape == t.shape == n.shape == live.shape == glass.shape):
+            raise ValueError('c, t, n, live, glass must share one [B, L] shape')
+        B, L = c.shape
+        if L > nat.PARAXIAL_MAX_SLOTS:
+            raise ValueError(f'at most {nat.PARAXIAL_MAX_SLOTS} slots per lens')
+        lib = nat.load()
+        dev = c.device
+        with torch.cuda.device(dev):
+            keep = [v.detach().contiguous() for v in (c, t, n)] + [live, glass]
+            p = nat.TlParaxial(*[v.data_ptr() for v in keep], B, L, mode)
+            out = torch.empty((B, 2), dtype=torch.float32, device=dev)
+            nat.check(lib.tl_paraxial_fwd(ctypes.byref(p), out.data_ptr(), nat.stream_ptr(dev)), 'tl_paraxial_fwd')
+        ctx.keep, ctx.mode = keep, mode
+        ctx.mark_non_differentiable(live, glass)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        c, t, n, live, glass = ctx.keep
+        B, L = c.shape
+        lib = nat.load()
+        dev = c.device
+        with torch.cuda.device(dev):
+            gout = gout.detach().to(torch.float32).contiguous()
+            gc, gt, gn = (torch.empty((B, L), dtype=torch.float32, device=dev) for _ in range(3))
+            p = nat.TlParaxial(c.data_ptr(), t.data_ptr(), n.data_ptr(), live.data_ptr(), glass.data_ptr(), B, L, ctx.mode)
+            nat.check(lib.tl_paraxial_bwd(ctypes.byref(p), gout.data_ptr(), gc.data_ptr(), gt.data_ptr(), gn.data_ptr(),
+                                          nat.stream_ptr(dev)), 'tl_paraxial_bwd')
+        return gc, gt, gn, None, None, None
+
+
+def _mask_bytes(structure):
+    """(live, glass) uint8 [B,L] device tensors of a Structure, cached on it."""
+    def build():
+        dev = structure.mask_torch.device
+        return (structure.mask_torch.to(torch.uint8).contiguous(), structure.mask_G_torch.to(torch.uint8).contiguous())
+    return structure.device_tables('paraxial_masks', build)
+
+
+def first_order(structure, c, t, n_after):
+    """(EFL, BFL) [B] of padded lenses: c, t [B,L]; n_after [B,L] the index behind every slot (1 behind
+    air and padding).  One launch; differentiable w.r.t. c, t, n_after (one more launch)."""
+    live, glass = _mask_bytes(structure)
+    out = _Paraxial.apply(c, t, n_after, live, glass, nat.PARAXIAL_FIRST_ORDER)
+    return out[:, 0], out[:, 1]
+
+
+def last_curvature(structure, c, t, n_after):
+    """(solved [B], slot [B] int64): the curvature of the last glass-air surface that makes EFL = 1
+    (rtl:725-769) of padded lenses; c at and behind the solved slot is not read."""
+    live, glass = _mask_bytes(structure)
+    out = _Paraxial.apply(c, t, n_after, live, glass, nat.PARAXIAL_LAST_CURVATURE)
+    return out[:, 0], out[:, 1].detach().to(torch.int64)

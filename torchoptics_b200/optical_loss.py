@@ -1,0 +1,142 @@
+"""The reference's training-loss wrapper, batched.
+
+Reference: ``Optical_Loss`` in ``/root/reference/torchlens/optical_loss.py`` ("ol").  Its unsupervised loss
+(ol:99-122) is a Python loop over the mini-batch; every iteration (``optical_loss_unsupervised_single``,
+ol:20-96) decodes one network output into a lens, builds a ``Structure``, solves the last curvature
+(``compute_last_curvature``, ~30 eager ops), constructs a ``RaytracedOptics`` (which re-reads a glass
+catalogue from disk) and traces 8 fields x 8x8 pupil points x 3 wavelengths = 1 536 rays with one ray-aiming
+iteration -- a few hundred tiny launches per SAMPLE.
+
+Here the whole mini-batch is ONE lens batch: the decode is a handful of batched tensor ops, the last
+curvature one kernel (``tl_paraxial_fwd``), and the loss ``RayTracer.loss_unsup`` -- staging + ray aiming
++ the fused spot pass + the fused penalty pass, each a single launch over all B lenses (rows of 64 rays:
+the warp-per-row kernels ``k_spot_rows`` / ``k_bwd_rows``) -- with the gradient w.r.t. the network output
+through hand-written adjoints, no autograd tape of per-ray temporaries.  Same arguments and return values as
+the reference.  Pinned: ``tests/golden/optical_loss/*.npz``, produced by executing the reference's own
+``optical_loss.py`` / ``optics_simulator_lite.py`` sample by sample (``tests/golden/make_golden_optical_loss.py``).
+
+``preprocessing.process_dataframe`` (ol:9) is absent from the reference repository; ``sequence_encoder`` /
+``sequence_decoder`` are inferred from their use at ol:14-16 (digit count = surfaces, digit sum = glasses):
+'G' -> 1, 'A' -> 0, read as a decimal number.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .lens_modeling import Lens, Specs, Structure, n_v_from_g
+from .ray_tracing_lite import RayTracer, compute_last_curvature_padded
+
+
+def sequence_encoder(sequence: str) -> int:
+    return int(''.join('1' if ch == 'G' else '0' for ch in sequence))
+
+
+def sequence_decoder(code: int) -> str:
+    return ''.join('G' if ch == '1' else 'A' for ch in str(int(code)))
+
+
+class Optical_Loss:
+    """``Optical_Loss(lens_type)`` (ol:11-18): ``lens_type`` is the surface sequence, e.g. ``'GAGA'``."""
+
+    # the ray set of ol:70-91: 8 fields, 8 x 8 circular pupil, three wavelengths, one ray-aiming iteration
+    # (the default of RaytracedOptics, optics_simulator_lite.py:359)
+    N_FIELDS = 8
+    N_PUPIL_RINGS = 8
+    WAVELENGTHS = (459.0, 520.0, 640.0)
+
+    def __init__(self, lens_type):
+        self.lens_type = lens_type
+        self.code_lenstype = sequence_encoder(lens_type)
+        self.numsurf = len(str(self.code_lenstype))
+        self.numglass = sum(map(int, str(self.code_lenstype)))
+        self.numin = 2 + 2 * self.numsurf
+        self.numout = 2 * self.numglass + 2 * self.numsurf - 1
+        self._tracers = {}
+        self._structures = {}
+
+    # -- pieces -------------------------------------------------------------------------------
+    def _tracer(self, device):
+        key = str(device)
+        if key not in self._tracers:
+            self._tracers[key] = RayTracer(
+                mode='circular', n_rays=(self.N_PUPIL_RINGS, self.N_PUPIL_RINGS),
+                rel_fields=list(np.linspace(0, 1, self.N_FIELDS)), vig_fn=None, n_ray_aiming_iter=1,
+                wavelengths=self.WAVELENGTHS, default_device=device)
+        return self._tracers[key]
+
+    def _structure(self, sequence, stop_idx, batch, device):
+        key = (sequence, int(stop_idx), int(batch), str(device))
+        if key not in self._structures:
+            self._structures[key] = Structure(stop_idx=np.full((batch,), int(stop_idx), dtype=np.int64),
+                                              sequence=np.array([sequence] * batch), default_device=device)
+        return self._structures[key]
+
+    def decode(self, input, output, device='cuda', sequence=None, stop_idx=None):
+        """Network vectors -> (specs, lens) of the whole mini-batch (ol:39-66, batched).
+
+        ``input`` [B, numin + 4] = (epd, hfov [deg], ..., sequence_encoded, stop_idx, as_c, as_t), ``output``
+        [B, numout] = (g pairs, curvatures but the last, thicknesses).  ``sequence`` / ``stop_idx`` may be
+        passed to skip the one device -> host read of the four trailing input columns.  All samples of
+        a mini-batch must share them (they come from one dataset of one lens type, ol:196-208)."""
+        if input.dim() != 2 or output.dim() != 2 or input.shape[0] != output.shape[0]:
+            raise ValueError('input and output must be [B, ...] with one B')
+        B, G, S = input.shape[0], self.numglass, self.numsurf
+        if sequence is None or stop_idx is None:
+            tail = input[:, -4:].detach().cpu().numpy()            # the one host read
+            if not (tail == tail[0]).all():
+                raise ValueError('all samples of a mini-batch must share sequence_encoded, stop_idx, as_c, as_t')
+            sequence = sequence_decoder(int(tail[0, 0]))
+            stop_idx = int(tail[0, 1])
+            if sequence[stop_idx - 1] == 'A' and tail[0, 3] != -1:
+                # (the reference splices the stop's c / t into arrays that its Structure has no slot for,
+                # ol:67-68 with :63: the spliced lens no longer matches the masks)
+                raise NotImplementedError('a separate aperture-stop element (as_t != -1) is not supported')
+        if len(sequence) != S:
+            raise ValueError(f'sequence {sequence!r} does not have the {S} surfaces of lens type {self.lens_type!r}')
+        structure = self._structure(sequence, stop_idx, B, device)
+        epd = input[:, 0].to(device)
+        hfov = torch.deg2rad(input[:, 1].to(device))               # optics_simulator_lite.py:123
+        output = output.to(device)
+        n, v = n_v_from_g(output[:, :2 * G].reshape(B * G, 2))     # ol:46-51
+        glass_cols = [k for k, ch in enumerate(sequence) if ch == 'G']
+        nd2d = torch.ones((B, S), dtype=output.dtype, device=device)
+        nd2d[:, glass_cols] = n.reshape(B, G)
+        v2d = torch.full((B, S), float('nan'), dtype=output.dtype, device=device)
+        v2d[:, glass_cols] = v.reshape(B, G)
+        t2d = output[:, 2 * G + S - 1:2 * G + 2 * S - 1]
+        c2d = torch.cat((output[:, 2 * G:2 * G + S - 1], torch.zeros((B, 1), dtype=output.dtype, device=device)), dim=1)
+        c2d = compute_last_curvature_padded(structure, c2d.contiguous(), t2d.contiguous(), nd2d)      # ol:64
+        return Specs(structure, epd, hfov), Lens(structure, c2d, t2d, nd2d, v2d)
+
+    # -- the reference's methods ------------------------------------------------------------------
+    def per_sample(self, input, output, penalty_rate=0.2, device='cuda', sequence=None, stop_idx=None):
+        """(loss_unsup, rms, penalty), each [B]: what ``optical_loss_unsupervised_single`` returns for
+        every sample of the mini-batch, in one batched pass."""
+        specs, lens = self.decode(input, output, device, sequence, stop_idx)
+        out = self._tracer(device).loss_unsup(specs, lens, penalty_rate, n_seq=self.numsurf)
+        return out['loss_unsup'], out['rms'], out['penalty']
+
+    def optical_loss_unsupervised_single(self, input, output, penalty_rate, device='cuda'):
+        """ol:20-96 for one sample (1-D ``input`` / ``output``)."""
+        loss, rms, penalty = self.per_sample(input[None], output[None], penalty_rate, device)
+        return loss[0], rms[0], penalty[0]
+
+    def optical_loss_unsupervised(self, input, output, penalty_rate=0.2, device='cuda', sequence=None, stop_idx=None):
+        """ol:99-122: batch means of (loss_unsup, rms, penalty) -- without the per-sample loop."""
+        loss, rms, penalty = self.per_sample(input, output, penalty_rate, device, sequence, stop_idx)
+        return loss.mean(), rms.mean(), penalty.mean()
+
+    @staticmethod
+    def t_converter(stop_idx, sequence, t, as_t=None):
+        """ol:125-133."""
+        if sequence[stop_idx - 1] == 'A' and (as_t is not None and as_t != -1):
+            return torch.cat((t[:stop_idx - 1], as_t, t[stop_idx - 1:]))
+        return t
+
+    def optical_loss_supervised(self, input, output, device='cuda'):
+        """ol:136-176: mean over designs of the mean squared deviation of (g, c, t)."""
+        S, G = self.numsurf, self.numglass
+        width = 2 * G + 2 * S - 1
+        dev = output[:, :width] - input[:, :width]
+        return torch.mean(torch.sum(dev ** 2, dim=1) / width)

@@ -195,7 +195,10 @@ def compute_pupil_position(lens):
 
 
 def get_first_order(lens):
-    """(EFL, BFL) of every lens (rtl:772-794)."""
+    """(EFL, BFL) of every lens (rtl:772-794).  CUDA lenses: one kernel, one thread per lens
+    (``tl_paraxial_fwd``; its adjoint ``tl_paraxial_bwd`` in backward) instead of ~20 eager ops."""
+    if lens.c.is_cuda and lens.c.shape[1] <= nat.PARAXIAL_MAX_SLOTS:
+        return ops.first_order(lens.structure, lens.c, lens.t, lens.nd)
     nd = torch.cat((torch.ones_like(lens.nd[:, 0:1]), lens.nd), dim=1)
     last = lens.structure.mask_torch.sum(dim=1) - 1
     t = lens.t.clone()
@@ -220,6 +223,15 @@ def compute_last_curvature(structures, c, t, nd):
     device = structures.mask_torch.device
     mask = structures.mask_torch
     B = mask.shape[0]
+    if c.is_cuda and mask.shape[1] <= nat.PARAXIAL_MAX_SLOTS:
+        # host-side masks (no device sync), then the padded solve as one kernel
+        n_surf_h = structures.mask.sum(axis=1)
+        given_h = structures.mask.copy()
+        given_h[np.arange(B), n_surf_h - 1] = False
+        c2d = mask_replace(given_h, torch.zeros(mask.shape, dtype=torch.float32, device=device), c)
+        t2d = mask_replace(structures.mask, torch.zeros(mask.shape, dtype=torch.float32, device=device), t)
+        n2d = mask_replace(structures.mask_G, torch.ones(mask.shape, dtype=torch.float32, device=device), nd)
+        return compute_last_curvature_padded(structures, c2d, t2d, n2d)[mask]
     rows = torch.arange(B, device=device)
     n_surf = mask.sum(dim=1)
     ends_air_air = ~structures.mask_G_torch[rows, n_surf - 2]
@@ -240,6 +252,17 @@ def compute_last_curvature(structures, c, t, nd):
     c2d = c2d.clone()
     c2d[rows, solve_at] = solved
     return c2d[mask]
+
+
+def compute_last_curvature_padded(structures, c2d, t2d, nd2d):
+    """:func:`compute_last_curvature` on the padded ``[B, L]`` layout the batched front end works in
+    (no compact <-> padded boolean indexing, hence no device sync): ``c2d`` with the solved curvature
+    written into its slot (whatever that slot and the ones behind it held is ignored); ``nd2d`` = index
+    behind every slot, 1 for air.  CUDA only: ``tl_paraxial_fwd`` / ``tl_paraxial_bwd``."""
+    solved, slot = ops.last_curvature(structures, c2d, t2d, nd2d)
+    behind = torch.arange(c2d.shape[1], device=c2d.device)[None, :] >= slot[:, None]
+    c_given = torch.where(behind, torch.zeros_like(c2d), c2d)       # the reference leaves 0 behind the solved slot
+    return torch.where(behind & (behind.cumsum(dim=1) == 1), solved[:, None], c_given)
 
 
 def compute_magnification(lens):
