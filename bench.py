@@ -510,6 +510,22 @@ def main():
     except Exception as exc:
         print(f'[bench] penalty timing failed: {exc}', file=sys.stderr)
 
+    # ---- the reference's real workload shape: a mini-batch of B lens designs ->
+    # Optical_Loss.optical_loss_unsupervised (batched; the reference loops over samples) -> backward ----
+    batched_row = None
+    if world == 1:
+        note('batched-lens loss')
+        try:
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tools'))
+            import profile_optical_loss
+            batched_row = {'what': 'Optical_Loss(GAGAGA).optical_loss_unsupervised on B designs (8 fields x 3 wavelengths x '
+                                   '8x8 pupil = 1 536 rays per lens, one ray-aiming iteration) + backward to the network '
+                                   'outputs; events = rays x surfaces x 2 fused passes (spot, penalty), each forward + adjoint',
+                           'runs': [profile_optical_loss.measure('GAGAGA', n_lenses, device=dev, reps=10)
+                                    for n_lenses in (1024, 4096)]}
+        except Exception as exc:
+            print(f'[bench] batched-lens timing failed: {exc}', file=sys.stderr)
+
     if graphed is not None:
         h2d, d2h = graphed.h2d_bytes, graphed.d2h_bytes
     else:
@@ -546,7 +562,7 @@ def main():
                         'drop_in_api': 'the reference\'s own sequence, unchanged: trace_rays (materialises [B,F,P,W]) -> compute_rms2d -> backward; compute_rms2d recognises untouched trace outputs and runs the fused pass on their inputs'},
                 'step_ms': step_stats, 'sustained': sustained,
                 'gpu_launches': launches_per_step * args.steps,
-                'roofline': roofline, 'forward': forward, 'penalty': penalty_row}
+                'roofline': roofline, 'forward': forward, 'penalty': penalty_row, 'batched_lenses': batched_row}
         if value < 0.97 * e2e_value:      # device-timed slower than host-timed end to end: timed wait (rank skew)
             line['warning'] = ('value < e2e.value: the device-timed steps include waiting for the slowest rank '
                                '(see step_ms min / median / max)')

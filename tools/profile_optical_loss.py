@@ -27,7 +27,7 @@ def batch_of(lens_type, B, device, seed=0):
     return torch.from_numpy(x).to(device), torch.from_numpy(y.astype(np.float32)).to(device)
 
 
-def measure(lens_type, B, device='cuda:0', reps=20):
+def measure(lens_type, B, device='cuda:0', reps=20, graph=True):
     loss_fn = Optical_Loss(lens_type)
     x, y = batch_of(lens_type, B, device)
     y.requires_grad_(True)
@@ -53,11 +53,46 @@ def measure(lens_type, B, device='cuda:0', reps=20):
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) / reps
     ms = a.elapsed_time(b) / reps
+    graphed_ms = None
+    # the whole step -- decode, kernels, autograd backward to the network outputs -- as one CUDA graph (the first
+    # capture of a process can be invalidated by one-time initialisation on the autograd thread: one retry)
+    for attempt in range(2 if graph else 0):
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                g_out = step()
+            for _ in range(3):
+                g.replay()
+            torch.cuda.synchronize()
+            ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ga.record()
+            for _ in range(reps):
+                g.replay()
+            gb.record()
+            torch.cuda.synchronize()
+            graphed_ms = ga.elapsed_time(gb) / reps
+            eager = step()
+            assert torch.allclose(g_out[0], eager[0], rtol=1e-6) and torch.allclose(g_out[3], eager[3], rtol=1e-5, atol=1e-7)
+            break
+        except Exception as exc:      # report, do not hide the eager numbers
+            graphed_ms = None
+            print(f'[profile_optical_loss] graph capture failed (attempt {attempt + 1}): {str(exc).splitlines()[0]}',
+                  file=sys.stderr)
+            torch.cuda.synchronize()
     S = loss_fn.numsurf
     rays = B * Optical_Loss.N_FIELDS * 3 * Optical_Loss.N_PUPIL_RINGS ** 2
     events = rays * S * 2          # two fused passes (spot, penalty), each forward + adjoint over every ray-surface event
     return {'lens_type': lens_type, 'lenses': B, 'rays': rays, 'ms_per_step': ms, 'wall_ms_per_step': wall * 1e3,
             'lenses_per_s': B / (ms * 1e-3), 'events_per_s': events / (ms * 1e-3), 'library_launches_per_step': launches,
+            'graphed_ms_per_step': graphed_ms,
+            'graphed_lenses_per_s': None if graphed_ms is None else B / (graphed_ms * 1e-3),
+            'graphed_events_per_s': None if graphed_ms is None else events / (graphed_ms * 1e-3),
             'loss': float(out[0]), 'rms': float(out[1]), 'penalty': float(out[2]),
             'finite_grads': bool(torch.isfinite(out[3]).all())}
 

@@ -19,7 +19,7 @@ from torchoptics_b200 import RayTracer, ops, prescriptions   # noqa: E402
 side = int(sys.argv[1]) if len(sys.argv) > 1 else 296
 dev = 'cuda:0'
 VARIANTS = [('round1', {'TL_NO_REV': '1'})] + [(v, {'TL_REV': v}) for v in
-                                                ('reg8', 'tmem8', 'tmem12', 'tmem12c2', 'tmem16')]
+                                                ('reg8', 'tmem8', 'tmem10', 'tmem12', 'tmem12c2', 'tmem14c2', 'tmem16')]
 
 
 def set_env(env):

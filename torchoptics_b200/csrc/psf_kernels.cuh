@@ -8,20 +8,28 @@
 // with sigma = half a bin (rt_tf:246-247), only the non-negative half of the x bins evaluated
 // (rt_tf:238-243; the caller mirrors and normalises, rt_tf:257-263).  Every ray touches every bin,
 // so per ray the work is (n_xh + n_y) exponentials and n_xh * n_y multiply-adds against 8 bytes of
-// input: for the reference's 21 x 21 grid that is 32 MUFU + 231 FMA per 8 B -- compute-bound on the
-// FP32 / MUFU pipes by a wide margin (the HBM roofline would be 0.8 T rays/s), not a dense
+// input: for the reference's 21 x 21 grid that is 32 MUFU + 231 FMA per 8 B (590 flop per ray counting 4 per
+// exponential) -- compute-bound on the FP32 / MUFU pipes by a wide margin (the HBM roofline would be
+// 0.8 T rays/s, the FP32 one 126 G rays/s, the MUFU one 145 G rays/s), not a dense
 // contraction worth reshaping for the tensor cores (K = rays, but M x N = 21 x 11 and both operands
 // would have to be materialised first: 128 B of exponentials per ray).
 //
-// A CTA takes one (grid, channel) and a contiguous chunk of its rays: tiles of kPsfTile rays, the
-// separable factors of a tile computed once into shared memory (threads over rays x bins), then one
-// accumulator per (iy, ix) bin and thread, the ray index running over the tile -- the factor rows are
-// read as broadcasts (same ix or iy across a quarter warp) from rows padded to an odd stride.  Chunk
-// sums leave as fp64 partials; k_psf_reduce adds them in a fixed order (deterministic).
+// A CTA takes one (grid, channel) and a contiguous chunk of its rays, in tiles of kPsfTile rays:
+//   phase 1  the separable factors of the tile, computed once into shared memory (threads over rays x
+//            bin rows; rows padded to a multiple of the register block with zeros);
+//   phase 2  REGISTER-BLOCKED accumulation: a thread owns a 3 x 4 block of bins and a subset of the
+//            tile's rays, four consecutive rays per step: 3 + 4 128-bit shared loads feed 48 FMAs
+//            (the first version gave a thread one bin: 2 scalar shared loads per FMA, shared-memory
+//            bound at 7 % of the FP32 peak);
+//   end      the ray subsets of a bin block are summed through shared memory; chunk sums leave as fp64
+//            partials and k_psf_reduce adds them in a fixed order (deterministic).
 
 constexpr int kPsfThreads = 256;
-constexpr int kPsfTile = 128;
+constexpr int kPsfTile = 256;            // rays per tile = threads per CTA (phase 1: a ray per thread)
+constexpr int kPsfStride = kPsfTile + 4; // floats per factor row: 16-byte aligned, rows shifted by 4 banks
 constexpr int kPsfMaxBins = 64;          // per axis
+constexpr int kPsfBy = 3, kPsfBx = 4;    // register block of bins per thread
+static_assert(kPsfTile == kPsfThreads, "phase 1 gives every thread one ray of the tile");
 
 struct PsfArgs {
   TlPsf p;
@@ -31,12 +39,15 @@ struct PsfArgs {
 
 __global__ void __launch_bounds__(kPsfThreads)
 k_psf_bin(PsfArgs a) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const TlPsf &p = a.p;
   const int n_xh = a.n_xh, n_y = p.n_y_bins, n_bins = n_xh * n_y;
-  constexpr int kStride = kPsfTile + 1;
-  float *gx = sm;                        // [n_xh][kStride]
-  float *gy = sm + (size_t)n_xh * kStride;      // [n_y][kStride]
+  const int n_by = (n_y + kPsfBy - 1) / kPsfBy, n_bx = (n_xh + kPsfBx - 1) / kPsfBx;
+  const int rows_y = n_by * kPsfBy, rows_x = n_bx * kPsfBx;          // padded row counts
+  const int n_blocks = n_by * n_bx;                                    // bin blocks (<= 22 * 8 = 176)
+  const int n_sub = kPsfThreads / n_blocks;                            // ray subsets per bin block
+  float *gy = sm;                                    // [rows_y][kPsfStride]
+  float *gx = sm + (size_t)rows_y * kPsfStride;      // [rows_x][kPsfStride]
   __shared__ float inside_total;
   const int chunk = blockIdx.x % a.n_chunks;
   const int gc = blockIdx.x / a.n_chunks;
@@ -50,55 +61,88 @@ k_psf_bin(PsfArgs a) {
   const float half_x = 0.5f * p.x_size[g], half_y = 0.5f * p.y_size[g];
   const float *xs = p.x + (int64_t)gc * p.R, *ys = p.y + (int64_t)gc * p.R;
   const int r_lo = chunk * a.chunk_len, r_hi = min(p.R, r_lo + a.chunk_len);
+  __shared__ float centres[2 * kPsfMaxBins + kPsfBy + kPsfBx];      // bin-row centres: y rows, then x rows
   if (threadIdx.x == 0) inside_total = 0.f;
+  for (int row = threadIdx.x; row < rows_y + rows_x; row += kPsfThreads)
+    centres[row] = row < rows_y ? ((float)row + y_first) * y_incr : ((float)(row - rows_y) + x_first) * x_incr;
   float inside = 0.f;
-  constexpr int kPerThread = (kPsfMaxBins * kPsfMaxBins / 2 + kPsfThreads - 1) / kPsfThreads;    // <= 8 bins / thread
-  float acc[kPerThread];
+  const int block_id = threadIdx.x % n_blocks, sub = threadIdx.x / n_blocks;
+  const bool worker = sub < n_sub;
+  const int by = block_id / n_bx, bx = block_id % n_bx;
+  const float *fy = gy + (size_t)by * kPsfBy * kPsfStride, *fx = gx + (size_t)bx * kPsfBx * kPsfStride;
+  float acc[kPsfBy][kPsfBx];
 #pragma unroll
-  for (int q = 0; q < kPerThread; ++q) acc[q] = 0.f;
+  for (int i = 0; i < kPsfBy; ++i)
+#pragma unroll
+    for (int j = 0; j < kPsfBx; ++j) acc[i][j] = 0.f;
+
   for (int r0 = r_lo; r0 < r_hi; r0 += kPsfTile) {
     const int n = min(kPsfTile, r_hi - r0);
     __syncthreads();                                  // the previous tile's readers are done
-    // separable factors of this tile: thread = (bin row, ray)
-    for (int i = threadIdx.x; i < (n_xh + n_y) * kPsfTile; i += kPsfThreads) {
-      const int row = i / kPsfTile, t = i % kPsfTile;
-      float v = 0.f;
-      if (t < n) {
-        if (row < n_xh) {
-          const float d = (xs[r0 + t] - ((float)row + x_first) * x_incr) * kx;
-          v = exp2f(-0.72134752044448170f * d * d);
-        } else {
-          const float d = ((ys[r0 + t] - yt) - ((float)(row - n_xh) + y_first) * y_incr) * ky;
-          v = exp2f(-0.72134752044448170f * d * d);
-        }
+    // phase 1: a thread takes ONE ray of the tile (two coalesced loads) and walks the bin rows: per factor a
+    // broadcast load of the row centre, subtract, scale, square, ex2, store.  Rows past the bin count and rays
+    // past the tile hold zeros.  (ex2.approx.ftz: arguments <= 0; results below 2^-126 flush to 0, which is what
+    // they contribute to a sum of O(1) terms.)
+    {
+      const int t = threadIdx.x;            // kPsfTile == kPsfThreads
+      const bool has = t < n;
+      const float xr = has ? xs[r0 + t] : 0.f;
+      const float yr = has ? ys[r0 + t] - yt : 0.f;
+      inside += (has && fabsf(yr) < half_y && fabsf(xr) < half_x) ? 1.f : 0.f;      // rays inside the window (rt_tf:266-267)
+      for (int row = 0; row < rows_y; ++row) {
+        const float d = (yr - centres[row]) * ky;
+        float v;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(-0.72134752044448170f * d * d));
+        gy[(size_t)row * kPsfStride + t] = (has && row < n_y) ? v : 0.f;
       }
-      (row < n_xh ? gx + (size_t)row * kStride : gy + (size_t)(row - n_xh) * kStride)[t] = v;
+      for (int row = 0; row < rows_x; ++row) {
+        const float d = (xr - centres[rows_y + row]) * kx;
+        float v;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v) : "f"(-0.72134752044448170f * d * d));
+        gx[(size_t)row * kPsfStride + t] = (has && row < n_xh) ? v : 0.f;
+      }
     }
-    // rays inside the window (rt_tf:266-267)
-    for (int t = threadIdx.x; t < n; t += kPsfThreads)
-      inside += (fabsf(ys[r0 + t] - yt) < half_y && fabsf(xs[r0 + t]) < half_x) ? 1.f : 0.f;
     __syncthreads();
+    // phase 2: this thread's ray quads of the tile
+    if (worker) {
+      for (int q = sub; q < kPsfTile / 4; q += n_sub) {
+        float4 vy[kPsfBy], vx[kPsfBx];
 #pragma unroll
-    for (int q = 0; q < kPerThread; ++q) {
-      const int bin = threadIdx.x + q * kPsfThreads;
-      if (bin >= n_bins) break;
-      const float *fx = gx + (size_t)(bin % n_xh) * kStride, *fy = gy + (size_t)(bin / n_xh) * kStride;
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 4
-      for (int t = 0; t < kPsfTile; t += 4) {          // (the tail of a short tile holds zeros)
-        s0 = fmaf(fx[t], fy[t], s0);
-        s1 = fmaf(fx[t + 1], fy[t + 1], s1);
-        s2 = fmaf(fx[t + 2], fy[t + 2], s2);
-        s3 = fmaf(fx[t + 3], fy[t + 3], s3);
+        for (int i = 0; i < kPsfBy; ++i) vy[i] = *reinterpret_cast<const float4 *>(fy + (size_t)i * kPsfStride + 4 * q);
+#pragma unroll
+        for (int j = 0; j < kPsfBx; ++j) vx[j] = *reinterpret_cast<const float4 *>(fx + (size_t)j * kPsfStride + 4 * q);
+#pragma unroll
+        for (int i = 0; i < kPsfBy; ++i)
+#pragma unroll
+          for (int j = 0; j < kPsfBx; ++j) {
+            float s = acc[i][j];
+            s = fmaf(vy[i].x, vx[j].x, s);
+            s = fmaf(vy[i].y, vx[j].y, s);
+            s = fmaf(vy[i].z, vx[j].z, s);
+            s = fmaf(vy[i].w, vx[j].w, s);
+            acc[i][j] = s;
+          }
       }
-      acc[q] += (s0 + s1) + (s2 + s3);
     }
   }
-  double *dst = a.partial + ((int64_t)gc * a.n_chunks + chunk) * (n_bins + 1);
+  // sum the ray subsets of every bin block: scratch[sub][block][3][4] over the factor rows
+  __syncthreads();
+  float *scratch = sm;
+  if (worker) {
 #pragma unroll
-  for (int q = 0; q < kPerThread; ++q) {
-    const int bin = threadIdx.x + q * kPsfThreads;
-    if (bin < n_bins) dst[bin] = (double)acc[q];
+    for (int i = 0; i < kPsfBy; ++i)
+#pragma unroll
+      for (int j = 0; j < kPsfBx; ++j)
+        scratch[((size_t)sub * n_blocks + block_id) * (kPsfBy * kPsfBx) + i * kPsfBx + j] = acc[i][j];
+  }
+  __syncthreads();
+  double *dst = a.partial + ((int64_t)gc * a.n_chunks + chunk) * (n_bins + 1);
+  for (int bin = threadIdx.x; bin < n_bins; bin += kPsfThreads) {
+    const int iy = bin / n_xh, ix = bin % n_xh;
+    const int blk = (iy / kPsfBy) * n_bx + ix / kPsfBx, slot = (iy % kPsfBy) * kPsfBx + ix % kPsfBx;
+    double s = 0.0;
+    for (int u = 0; u < n_sub; ++u) s += (double)scratch[((size_t)u * n_blocks + blk) * (kPsfBy * kPsfBx) + slot];
+    dst[bin] = s;
   }
   inside = warp_sum(inside);
   if ((threadIdx.x & 31) == 0) atomicAdd(&inside_total, inside);      // (integers < 2^24: exact, any order)
@@ -135,10 +179,20 @@ int plan_psf(const TlPsf &p, PsfPlan &pl) {
       p.n_y_bins > kPsfMaxBins)
     return fail(TL_ERR_INVALID, "tl_psf: G, C, R >= 1 and 1 <= bins per axis <= 64%s");
   pl.n_xh = p.n_x_bins % 2 == 1 ? p.n_x_bins / 2 + 1 : p.n_x_bins / 2;
-  pl.smem = (size_t)(pl.n_xh + p.n_y_bins) * (kPsfTile + 1) * sizeof(float);
+  const size_t rows = (size_t)((p.n_y_bins + kPsfBy - 1) / kPsfBy) * kPsfBy + (size_t)((pl.n_xh + kPsfBx - 1) / kPsfBx) * kPsfBx;
+  pl.smem = rows * kPsfStride * sizeof(float);
+  const size_t scratch = (size_t)kPsfThreads * kPsfBy * kPsfBx * sizeof(float);      // the end-of-chunk sum reuses the rows
+  if (pl.smem < scratch) pl.smem = scratch;
   const int64_t n_gc = (int64_t)p.G * p.C;
   const int64_t tiles = ((int64_t)p.R + kPsfTile - 1) / kPsfTile;
-  int64_t chunks = ((int64_t)info.sms * 4 + n_gc - 1) / n_gc;        // ~4 CTAs per SM over the whole grid
+  // ONE wave: as many chunks per (grid, channel) as fit the resident CTAs of the device (a 5 % overshoot of the
+  // residency -- 624 CTAs on 592 slots -- doubled the run time of the first version)
+  if (pl.smem > 48 * 1024)
+    TL_CHECK_CUDA(cudaFuncSetAttribute((const void *)k_psf_bin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  int per_sm = 1;
+  TL_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)k_psf_bin, kPsfThreads, pl.smem));
+  if (per_sm < 1) per_sm = 1;
+  int64_t chunks = (int64_t)info.sms * per_sm / n_gc;
   if (chunks > tiles) chunks = tiles;
   if (chunks < 1) chunks = 1;
   const int64_t tiles_per_chunk = (tiles + chunks - 1) / chunks;

@@ -586,14 +586,17 @@ int plan_rev(const TlProblem &pb, RevPlan &pl) {
   int rc = device_info(info);
   if (rc) return rc;
   const int S = pb.S;
-  // in the order measured on the B200 (config 2; that kernel alone, CUDA events, L2 flushed, bench.py):
-  // tmem16 0.2115 ms, tmem12c2 0.2145, tmem12 0.2187, tmem8 0.2198, reg8 0.2253 (round 1's k_trace_adj:
-  // 0.289).  Residency matters little (8 -> 16 warps per SM: 4 %): the pass is bound by register-operand
-  // bandwidth (tools/microbench4.cu), so the variant with the fewest instructions per event wins.
+  // in the order measured on the B200 (config 2, tools/rev_variants.py: reference heights + this kernel + row
+  // reduction as a graph, L2 flushed; profiles/r2_rev_variants.json): tmem12 0.2147 ms, tmem12c2 0.2188, tmem16
+  // 0.2224 (128 registers: spills), tmem8 0.2263, reg8 0.2338 -- and tmem14c2 0.2467, tmem10 0.2538: warp counts
+  // that are not a multiple of the four schedulers lose 15 %.  (Round 1's k_trace_adj: 0.2988.)  Residency matters
+  // little (8 -> 12 warps per SM: 5 %): the pass is bound by register-operand bandwidth (tools/microbench4.cu).
   const RevVariant variants[] = {
+      {"tmem12", k_spot_rev<16, 12, ACC_TMEM, 3>, 12, 3},
+      {"tmem14c2", k_spot_rev<16, 14, ACC_TMEM, 2>, 14, 2},
       {"tmem16", k_spot_rev<16, 16, ACC_TMEM, 2>, 16, 2},
       {"tmem12c2", k_spot_rev<16, 12, ACC_TMEM, 2>, 12, 2},
-      {"tmem12", k_spot_rev<16, 12, ACC_TMEM, 3>, 12, 3},
+      {"tmem10", k_spot_rev<16, 10, ACC_TMEM, 3>, 10, 3},
       {"tmem8", k_spot_rev<16, 8, ACC_TMEM, 3>, 8, 3},
       {"reg8", S <= 12 ? k_spot_rev<12, 8, ACC_REG, 3> : k_spot_rev<16, 8, ACC_REG, 3>, 8, 3},
   };
@@ -601,7 +604,8 @@ int plan_rev(const TlProblem &pb, RevPlan &pl) {
   const RevVariant *pick = nullptr;
   for (const RevVariant &v : variants) {
     const size_t smem = (size_t)v.nw * (rev_table_floats(S) + (size_t)S * v.ncomp * 2 * 64) * sizeof(float);
-    const bool fits = smem <= 227 * 1024 && (v.nw < 16 || 6 * S <= 128 - 32);   // (flush reads whole 32-column blocks)
+    const int tmem_cols = 512 / ((v.nw + 3) / 4);                               // per warp: TMEM column blocks
+    const bool fits = smem <= 227 * 1024 && 6 * S <= tmem_cols - 32;            // (flush reads whole 32-column blocks)
     if (env ? !strcmp(env, v.name) : fits) {
       if (!fits) return fail(TL_ERR_INVALID, "TL_REV variant does not fit this surface count%s");
       pick = &v;

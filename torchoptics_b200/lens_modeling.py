@@ -57,18 +57,32 @@ _G_TO_NV = ((-0.06668863644654068, 6.3758429552417315),
             (-0.0666886481483064, -6.375841836481304))
 
 
+_GLASS_CONSTANTS = {}
+
+
+def _glass_constant(like: torch.Tensor, name: str):
+    """The glass-map constants as tensors of ``like``'s device and dtype, built once per (device,
+    dtype): a fresh ``new_tensor`` per call is a pageable host -> device copy, which a CUDA graph
+    capture of the caller refuses."""
+    key = (name, like.device, like.dtype)
+    if key not in _GLASS_CONSTANTS:
+        value = {'centre': [_GLASS_CENTRE], 'nv_to_g': _NV_TO_G, 'g_to_nv': _G_TO_NV}[name]
+        _GLASS_CONSTANTS[key] = torch.tensor(value, dtype=like.dtype, device=like.device)
+    return _GLASS_CONSTANTS[key]
+
+
 def g_from_n_v(n: torch.Tensor, v: torch.Tensor):
     """(nd, Abbe) -> whitened glass coordinates ``g`` of shape [N, 2] (lm:29-38)."""
     assert n.dim() == 1 and v.dim() == 1
     assert n.device == v.device and n.dtype == v.dtype
-    centred = torch.stack((n, v), dim=-1) - n.new_tensor([_GLASS_CENTRE])
-    return centred @ n.new_tensor(_NV_TO_G)
+    centred = torch.stack((n, v), dim=-1) - _glass_constant(n, 'centre')
+    return centred @ _glass_constant(n, 'nv_to_g')
 
 
 def n_v_from_g(g: torch.Tensor):
     """Inverse of :func:`g_from_n_v`; returns the tuple (nd, v) (lm:41-46)."""
     assert g.dim() == 2 and g.shape[1] == 2
-    nv = g @ g.new_tensor(_G_TO_NV) + g.new_tensor([_GLASS_CENTRE])
+    nv = g @ _glass_constant(g, 'g_to_nv') + _glass_constant(g, 'centre')
     return torch.unbind(nv, dim=1)
 
 

@@ -723,6 +723,15 @@ class _Staged:
                   'tl_stage_bwd')
 
 
+def stage_lens(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays=True, arith=nat.ARITH_GUARDED,
+               aimed=False, vig=None, aim_mode=nat.AIM_REAL):
+    """The staged ray set of a lens batch (one ``tl_stage_ref`` launch), for callers that run several
+    fused passes over it (``staged=`` of lens_spot_rms / lens_penalty)."""
+    with torch.cuda.device(c.device):
+        return _Staged(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, aimed,
+                       max_surfaces=nat.MAX_SURFACES_SPOT, want_ref=True, vig=vig, aim_mode=aim_mode)
+
+
 def _lens_spot_core(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, shard, group,
                     want_grad, aimed, out=None, staged=None, vig=None, aim_mode=nat.AIM_REAL):
     """The staged fused pass itself (no autograd): staging kernel -> (ray aiming) -> chief rays ->

@@ -72,6 +72,13 @@ class Optical_Loss:
                                               sequence=np.array([sequence] * batch), default_device=device)
         return self._structures[key]
 
+    def _glass_columns(self, sequence, device):
+        key = ('glass', sequence, str(device))
+        if key not in self._structures:
+            self._structures[key] = torch.tensor([k for k, ch in enumerate(sequence) if ch == 'G'], dtype=torch.int64,
+                                                 device=device)
+        return self._structures[key]
+
     def decode(self, input, output, device='cuda', sequence=None, stop_idx=None):
         """Network vectors -> (specs, lens) of the whole mini-batch (ol:39-66, batched).
 
@@ -99,11 +106,9 @@ class Optical_Loss:
         hfov = torch.deg2rad(input[:, 1].to(device))               # optics_simulator_lite.py:123
         output = output.to(device)
         n, v = n_v_from_g(output[:, :2 * G].reshape(B * G, 2))     # ol:46-51
-        glass_cols = [k for k, ch in enumerate(sequence) if ch == 'G']
-        nd2d = torch.ones((B, S), dtype=output.dtype, device=device)
-        nd2d[:, glass_cols] = n.reshape(B, G)
-        v2d = torch.full((B, S), float('nan'), dtype=output.dtype, device=device)
-        v2d[:, glass_cols] = v.reshape(B, G)
+        glass_cols = self._glass_columns(sequence, device)          # (device index tensor, built once: no copy per call)
+        nd2d = torch.ones((B, S), dtype=output.dtype, device=device).index_copy(1, glass_cols, n.reshape(B, G))
+        v2d = torch.full((B, S), float('nan'), dtype=output.dtype, device=device).index_copy(1, glass_cols, v.reshape(B, G))
         t2d = output[:, 2 * G + S - 1:2 * G + 2 * S - 1]
         c2d = torch.cat((output[:, 2 * G:2 * G + S - 1], torch.zeros((B, 1), dtype=output.dtype, device=device)), dim=1)
         c2d = compute_last_curvature_padded(structure, c2d.contiguous(), t2d.contiguous(), nd2d)      # ol:64

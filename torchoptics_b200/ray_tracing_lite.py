@@ -548,8 +548,17 @@ class RayTracer:
         builds a RaytracedOptics per sample and traces 8 fields x 64 pupil points x 3 wavelengths one
         lens at a time (the reference evaluates lens 0's RMS and sums the penalty over its one-lens
         batch; a one-lens batch here gives its numbers)."""
-        rms, _ = self.spot_rms(specs, lens, use_vig, shard, group)
-        pen = self.penalty(specs, lens, use_vig, shard, group, n_seq)
+        ray_set = None
+        can_stage, aimed = self._staging(lens, use_vig)
+        if can_stage and lens.c.is_cuda and lens.c.shape[1] <= nat.MAX_SURFACES_SPOT:
+            # ONE staging launch (index model, pupil position, field cosines, ray aiming, reference heights) feeds
+            # both fused passes
+            x_rel, y_rel = self._pupil(None)
+            ray_set = ops.stage_lens(lens.c, lens.t, lens.nd, lens.v, specs.hfov, specs.epd, x_rel, y_rel,
+                                     self._tables(lens), self.allow_backward_rays, _arith_code(self.arith), aimed,
+                                     **self._staged_kwargs(specs, lens, use_vig))
+        rms, _ = self.spot_rms(specs, lens, use_vig, shard, group, _ray_set=ray_set)
+        pen = self.penalty(specs, lens, use_vig, shard, group, n_seq, _ray_set=ray_set)
         return {'loss_unsup': rms + penalty_rate * pen, 'rms': rms, 'penalty': pen}
 
     def spot_rms(self, specs, lens, use_vig=True, shard=(0, 1), group=None, staged=True, _ray_set=None):
