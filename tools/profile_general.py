@@ -29,7 +29,7 @@ for want_grad in (True, False):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    flops = 511 if want_grad else 261      # provisional asphere flop model, BASELINE.md section 3
+    flops = 566 if want_grad else 316      # n_newton = 4: 61 + 55 n + 35 forward, + 105 + 2 x 55 + 35 adjoint
     print(f'general spot pass want_grad={want_grad}: {ms:.4f} ms -> {events / ms / 1e6:.1f} G events/s '
           f'({events * flops / ms / 1e9 / 74.45 * 100:.1f}% of 74.45 TFLOP/s at {flops} flop/event), '
           f'ok fraction {float(m[..., -1].sum()) / (16 * 3 * side * side):.4f}')

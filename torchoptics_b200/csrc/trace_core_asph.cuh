@@ -12,6 +12,10 @@ namespace tl {
 
 constexpr int kAsphCoefs = 7;     // a4, a6, ..., a16
 constexpr int kNewton = 4;        // fixed iteration count (oracle: N_NEWTON)
+// Work per asphere event at kNewton = 4 (FMA = 2 flop; DESIGN.md section 7b has the table):
+//   algorithmic  61 + 55 * 4 + 35 = 316 forward, 105 + 2 * 55 + 35 = 250 adjoint, 566 together
+//   executed     fast_asph_surface 26 (start) + 4 * 57 (iterations) + 94 (hit, normal, Snell, margins) = 348,
+//                19 MUFU; sweep_asphere 238 + 33 (sums) = 271, 8 MUFU
 constexpr int kAsphParams = 2 + kAsphCoefs;   // c, k, a4..a16
 
 template <class S>
