@@ -11,6 +11,7 @@ two files of the hot path, byte for byte,
     /root/reference/torchlens/ray_tracing_lite.py     (RayTracer, trace_skew, compute_rms2d)
     /root/reference/torchlens/lens_modeling.py        (Structure, Specs, Lens)
 
+(and, for the drop-in test of the reference's own front end, optics_simulator_lite.py and optical_loss.py)
 into the git-ignored directory `oracle/_ref/torchlens/` (kept out of history like the built `.so`,
 but NOT gpurun-ignored, so it travels to the GPU box with the snapshot) and writes next to them a
 stand-in for `shapely`, which ray_tracing_lite.py imports at line 15 and never uses (its one use
@@ -30,7 +31,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_ROOT = '/root/reference'
 DEST = os.path.join(HERE, '_ref')
-FILES = ('torchlens/ray_tracing_lite.py', 'torchlens/lens_modeling.py')
+FILES = ('torchlens/ray_tracing_lite.py', 'torchlens/lens_modeling.py',
+         # the reference's own front end of the path (RaytracedOptics.do_ray_tracing, Optical_Loss): never timed, run by
+         # tests/test_gpu_dropin.py ON TOP of this repo's CUDA path to show that it keeps working unchanged
+         'torchlens/optics_simulator_lite.py', 'torchlens/optical_loss.py')
 SHAPELY_STUB = '''"""Stand-in written by oracle/make_ref.py: the reference imports shapely.geometry.Polygon
 (ray_tracing_lite.py:15) but its only use is commented out (ray_tracing_lite.py:692-694)."""
 

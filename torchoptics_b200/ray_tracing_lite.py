@@ -418,7 +418,8 @@ class RayTracer:
         self.n_ray_aiming_iter = n_ray_aiming_iter
         self.ray_aiming_mode = ray_aiming_mode
         self.allow_backward_rays = allow_backward_rays
-        self.wavelengths = [WAVELENGTH_ALIASES.get(w, w) for w in wavelengths]
+        # (the reference's consumer passes a device tensor, optical_loss.py:83: one read at construction)
+        self.wavelengths = [WAVELENGTH_ALIASES[w] if isinstance(w, str) else float(w) for w in wavelengths]
         if double_precision:
             raise NotImplementedError('the CUDA ray-trace kernels compute in fp32 only')
         self.double_precision = False
