@@ -54,7 +54,7 @@ enum { TL_ARITH_GUARDED = 0, TL_ARITH_EXACT = 1 };
 
 #define TL_MAX_SURFACES_FWD   256  /* tl_trace_fwd                          */
 #define TL_MAX_SURFACES_BWD    32  /* tl_trace_bwd                          */
-#define TL_MAX_SURFACES_SPOT   16  /* tl_spot_accumulate with want_grad     */
+#define TL_MAX_SURFACES_SPOT   32  /* tl_spot_accumulate with want_grad (17..32: 4-8 warps per SM) */
 #define TL_MAX_SURFACES_GEN    48  /* any entry point, general surfaces     */
 
 /* A ray-bundle input broadcastable to [B,F,P,W]: base pointer + element strides

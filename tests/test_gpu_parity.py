@@ -349,7 +349,8 @@ def test_staging_kernels_equal_torch_front_end(lens_file):
 
 def test_thirty_surface_lens_forward_sweep_and_backward():
     """BASELINE config-4 shape: 30 spherical surfaces.  Forward trace and the gradient-free spot
-    sweep (any surface count), and the split backward (S <= 32), against the oracle on device."""
+    sweep (any surface count), the split backward and the fused pass with gradients (S <= 32), against the
+    oracle on device."""
     specs, lens = prescriptions.wide_zoom_30(DEV)
     assert lens.c.shape == (1, 30)
     tracer = rt.RayTracer(mode='circular', n_rays=(96, 96), rel_fields=tuple(np.linspace(0, 1, 16).tolist()),
@@ -387,6 +388,15 @@ def test_thirty_surface_lens_forward_sweep_and_backward():
     for name, a_, b_, c_ in zip(('c', 't', 'nd'), g, ref_g, g64):
         _close_or_no_worse_than_reference(a_.cpu().numpy(), b_.cpu().numpy(), c_.cpu().numpy(), GRAD_TOL,
                                           f'wide_zoom_30 d rms/d {name}')
+    # the FUSED pass with gradients at 30 surfaces (17..32: k_spot_rev<tmem4 / tmem8>, accumulators in tensor memory)
+    assert ops.spot_kernel_name(*[a.detach() for a in args]).startswith('k_spot_rev<tmem')
+    fused_leaves = [l_.detach().clone().requires_grad_(True) for l_ in leaves]
+    rms_f, _ = tracer.spot_rms(specs, lm.Lens(lens.structure, *fused_leaves))
+    assert abs(rms_f[0].item() - want[0].item()) <= RMS_TOL * want[0].item()
+    g_f = torch.autograd.grad(rms_f[0], fused_leaves[:3])
+    for name, a_, b_, c_ in zip(('c', 't', 'nd'), g_f, ref_g, g64):
+        _close_or_no_worse_than_reference(a_.cpu().numpy(), b_.cpu().numpy(), c_.cpu().numpy(), GRAD_TOL,
+                                          f'wide_zoom_30 fused d rms/d {name}')
 
 
 def test_no_grad_sweep_with_grad_requiring_lens():
@@ -401,8 +411,9 @@ def test_no_grad_sweep_with_grad_requiring_lens():
         rms, _ = tracer.spot_rms(specs, lens)
         rms_t, _ = tracer.spot_rms(specs, lens, staged=False)
     assert not rms.requires_grad and abs(rms[0].item() - rms_t[0].item()) <= 1e-5 * rms_t[0].item()
-    with pytest.raises(ValueError):
-        tracer.spot_rms(specs, lens)          # with gradients: at most 16 surfaces in the fused pass
+    # with gradients the 30-surface lens takes k_spot_rev's 4-warp TMEM variant (round 1: ValueError beyond 16)
+    rms_g, _ = tracer.spot_rms(specs, lens)
+    assert rms_g.requires_grad and abs(rms_g[0].item() - rms_t[0].item()) <= 1e-5 * rms_t[0].item()
 
 
 # ---------------------------------------------------------------------------

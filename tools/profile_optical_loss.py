@@ -43,19 +43,12 @@ def measure(lens_type, B, device='cuda:0', reps=20, graph=True):
     before = _native.launch_count()
     step()
     launches = _native.launch_count() - before
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    a.record()
-    for _ in range(reps):
-        out = step()
-    b.record()
-    torch.cuda.synchronize()
-    wall = (time.perf_counter() - t0) / reps
-    ms = a.elapsed_time(b) / reps
     graphed_ms = None
-    # the whole step -- decode, kernels, autograd backward to the network outputs -- as one CUDA graph (the first
-    # capture of a process can be invalidated by one-time initialisation on the autograd thread: one retry)
+    # the whole step -- decode, kernels, autograd backward to the network outputs -- as one CUDA graph.  Results of
+    # earlier EAGER steps must not be alive across the capture: with a previous step's loss (and its autograd graph)
+    # still referenced, torch's capture of the backward pass is invalidated ("operation failed due to a previous
+    # error during capture"; bisected on the B200: decode + autograd.grad alone shows it, forward-only captures do not)
+    out = None
     for attempt in range(2 if graph else 0):
         try:
             side = torch.cuda.Stream()
@@ -85,6 +78,16 @@ def measure(lens_type, B, device='cuda:0', reps=20, graph=True):
             print(f'[profile_optical_loss] graph capture failed (attempt {attempt + 1}): {str(exc).splitlines()[0]}',
                   file=sys.stderr)
             torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    a.record()
+    for _ in range(reps):
+        out = step()
+    b.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / reps
+    ms = a.elapsed_time(b) / reps
     S = loss_fn.numsurf
     rays = B * Optical_Loss.N_FIELDS * 3 * Optical_Loss.N_PUPIL_RINGS ** 2
     events = rays * S * 2          # two fused passes (spot, penalty), each forward + adjoint over every ray-surface event

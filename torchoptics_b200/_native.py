@@ -22,7 +22,7 @@ PARAXIAL_LAST_CURVATURE = 1
 PARAXIAL_MAX_SLOTS = 64
 MAX_SURFACES_FWD = 256
 MAX_SURFACES_BWD = 32
-MAX_SURFACES_SPOT = 16
+MAX_SURFACES_SPOT = 32
 MAX_SURFACES_GEN = 48
 N_ASPHERE_TERMS = 7
 

@@ -598,6 +598,7 @@ int plan_rev(const TlProblem &pb, RevPlan &pl) {
       {"tmem12c2", k_spot_rev<16, 12, ACC_TMEM, 2>, 12, 2},
       {"tmem10", k_spot_rev<16, 10, ACC_TMEM, 3>, 10, 3},
       {"tmem8", k_spot_rev<16, 8, ACC_TMEM, 3>, 8, 3},
+      {"tmem4", k_spot_rev<16, 4, ACC_TMEM, 3>, 4, 3},      // the only one whose parked state fits for 19..32 surfaces
       {"reg8", S <= 12 ? k_spot_rev<12, 8, ACC_REG, 3> : k_spot_rev<16, 8, ACC_REG, 3>, 8, 3},
   };
   const char *env = getenv("TL_REV");
@@ -605,7 +606,8 @@ int plan_rev(const TlProblem &pb, RevPlan &pl) {
   for (const RevVariant &v : variants) {
     const size_t smem = (size_t)v.nw * (rev_table_floats(S) + (size_t)S * v.ncomp * 2 * 64) * sizeof(float);
     const int tmem_cols = 512 / ((v.nw + 3) / 4);                               // per warp: TMEM column blocks
-    const bool fits = smem <= 227 * 1024 && 6 * S <= tmem_cols - 32;            // (flush reads whole 32-column blocks)
+    const bool is_reg = !strcmp(v.name, "reg8");                                // (register accumulators: 16 surfaces)
+    const bool fits = smem <= 227 * 1024 && (is_reg ? S <= 16 : 6 * S <= tmem_cols - 32);   // (flush reads whole 32-column blocks)
     if (env ? !strcmp(env, v.name) : fits) {
       if (!fits) return fail(TL_ERR_INVALID, "TL_REV variant does not fit this surface count%s");
       pick = &v;

