@@ -23,7 +23,6 @@ import json
 import os
 import statistics
 import sys
-import threading
 import time
 
 import numpy as np
@@ -51,52 +50,73 @@ def workload_name(n_theta):
 # ----------------------------------------------------------------------------
 # clocks
 # ----------------------------------------------------------------------------
+_SAMPLER_CODE = r"""
+import json, select, sys, time
+try:
+    import pynvml as nv
+    nv.nvmlInit()
+    h = nv.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+    max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+except Exception as exc:
+    print(json.dumps({'error': repr(exc)}), flush=True)
+    sys.exit(0)
+print('ready', flush=True)
+samples, mask = [], 0
+while True:
+    try:
+        samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        mask |= nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+    except Exception:
+        pass
+    if select.select([sys.stdin], [], [], 0.0005)[0]:      # the parent closed our stdin: done
+        break
+print(json.dumps({'samples': samples, 'mask': mask, 'max_mhz': max_mhz}), flush=True)
+"""
+
+
 class ClockSampler:
-    """Polls SM clock and throttle reasons through NVML while the timed region runs."""
+    """SM clock and throttle reasons of one GPU, sampled through NVML by a CHILD PROCESS for as long as the `with`
+    block runs.  (A sampling thread of this process gets one or two samples out of a 5 ms timed region: the timing
+    loop holds the GIL.)  `index` is the NVML device index = CUDA_VISIBLE_DEVICES-relative local rank on these boxes."""
     REASONS = {0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap', 0x8: 'hw_slowdown',
                0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown', 0x80: 'hw_power_brake',
                0x100: 'display_clock_setting'}
 
     def __init__(self, index):
-        self.samples, self.mask, self.max_mhz = [], 0, None
-        self._stop = threading.Event()
-        self._thread = None
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
-        except Exception:
-            self.nv = None
-
-    def _run(self):
-        nv = self.nv
-        while not self._stop.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
-                self.mask |= nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-            except Exception:
-                pass
-            time.sleep(0.002)
+        self.index, self.proc, self.result = index, None, None
 
     def __enter__(self):
-        if self.nv is not None:
-            self._thread = threading.Thread(target=self._run, daemon=True)
-            self._thread.start()
+        import subprocess
+        try:
+            self.proc = subprocess.Popen([sys.executable, '-c', _SAMPLER_CODE, str(self.index)], stdin=subprocess.PIPE,
+                                         stdout=subprocess.PIPE, text=True)
+            first = self.proc.stdout.readline().strip()
+            if first != 'ready':
+                self.result = json.loads(first) if first else {'error': 'sampler did not start'}
+                self.proc.stdin.close()
+                self.proc.wait(timeout=10)
+                self.proc = None
+        except Exception as exc:
+            self.result, self.proc = {'error': repr(exc)}, None
         return self
 
     def __exit__(self, *exc):
-        self._stop.set()
-        if self._thread is not None:
-            self._thread.join()
+        if self.proc is not None:
+            try:
+                self.proc.stdin.close()
+                self.result = json.loads(self.proc.stdout.readline())
+                self.proc.wait(timeout=10)
+            except Exception as err:
+                self.result = {'error': repr(err)}
+                self.proc.kill()
 
     def summary(self):
-        if not self.samples:
-            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': ['nvml_unavailable']}
-        reasons = [name for bit, name in self.REASONS.items() if self.mask & bit]
-        return {'sm_mhz': statistics.median(self.samples), 'sm_max_mhz': self.max_mhz,
-                'reasons': reasons, 'samples': len(self.samples)}
+        res = self.result or {'error': 'not run'}
+        if not res.get('samples'):
+            return {'sm_mhz': None, 'sm_max_mhz': res.get('max_mhz'), 'reasons': ['nvml_unavailable: ' + str(res.get('error'))]}
+        reasons = [name for bit, name in self.REASONS.items() if res['mask'] & bit]
+        return {'sm_mhz': statistics.median(res['samples']), 'sm_min_mhz': min(res['samples']), 'sm_max_mhz': res['max_mhz'],
+                'reasons': reasons, 'samples': len(res['samples'])}
 
 
 # ----------------------------------------------------------------------------

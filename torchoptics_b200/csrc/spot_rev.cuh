@@ -21,7 +21,7 @@
 //
 // Per-event op table of the f4 instantiation: profiles/r2_*.txt (SASS mix) and DESIGN.md section 5.
 
-enum { ACC_REG = 0, ACC_TMEM = 1 };
+enum { ACC_REG = 0, ACC_TMEM = 1, ACC_NONE = 2 };   // ACC_NONE: forward sweep only (no parking, no adjoint)
 
 struct RevArgs {
   double *partial;      // [rows, max_owners, n_acc]: row-major by (row, rank of the owning warp within the row)
@@ -128,9 +128,11 @@ __device__ __noinline__ Traced trace_exact_rev(float x, float y, float z, float 
     const Surface s{sf.c, sf.t, sf.mu};
     Parked<float> pk;
     exact_surface_t<false>(r, s, sf.live_prev != 0, allow_backward, ok, backward, nullptr, &pk);
-    mine[rev_ray_offset(ncomp, k, 0, l)] = pk.dist;
-    mine[rev_ray_offset(ncomp, k, 1, l)] = pk.ci;
-    if (ncomp > 2) mine[rev_ray_offset(ncomp, k, 2, l)] = pk.co;
+    if (ncomp > 0) {                       // (ncomp == 0: the forward-only variant parks nothing)
+      mine[rev_ray_offset(ncomp, k, 0, l)] = pk.dist;
+      mine[rev_ray_offset(ncomp, k, 1, l)] = pk.ci;
+      if (ncomp > 2) mine[rev_ray_offset(ncomp, k, 2, l)] = pk.co;
+    }
   }
   Traced out;
   out.pre = r;
@@ -221,6 +223,8 @@ k_spot_rev(TlProblem pb, RevArgs args) {
   using V = f4;
   constexpr int N = 4;
   constexpr int NA = (ACC == ACC_REG) ? NS_MAX : 1;
+  constexpr bool GRAD = ACC != ACC_NONE;      // ACC_NONE: trace + spot moments only (tl_spot_accumulate without gradients)
+  static_assert(GRAD ? NCOMP >= 2 : NCOMP == 0, "parked components: 2 or 3 with the adjoint, none without");
   constexpr uint32_t kTmemCols = 512;
   const int S = pb.S;
   const int lane = threadIdx.x & 31;
@@ -245,7 +249,7 @@ k_spot_rev(TlProblem pb, RevArgs args) {
   }
 
   const size_t tab_floats = rev_table_floats(S);
-  const size_t per_warp = tab_floats + (size_t)S * NCOMP * 2 * 64;
+  const size_t per_warp = tab_floats + (size_t)S * NCOMP * 2 * 64;     // (NCOMP == 0: the table alone)
   float *wbase = smem_rev + warp * per_warp;
   f2 *state = reinterpret_cast<f2 *>(wbase + tab_floats) + lane;     // half h of slot (k, comp): state[((k NCOMP + comp) 2 + h) 32]
   float *mine = wbase + tab_floats + 2 * lane;                       // the same, in floats (rev_ray_offset)
@@ -270,7 +274,7 @@ k_spot_rev(TlProblem pb, RevArgs args) {
       for (int k = 0; k < NA; ++k)
 #pragma unroll
         for (int j = 0; j < 6; ++j) acc[j][k] = 0.f;
-    } else {
+    } else if constexpr (ACC == ACC_TMEM) {
       for (int k = 0; k < S; ++k) {
         tm_st4(tacc + 6 * k, 0.f, 0.f, 0.f, 0.f);
         tm_st2(tacc + 6 * k + 4, 0.f, 0.f);
@@ -302,7 +306,7 @@ k_spot_rev(TlProblem pb, RevArgs args) {
         const int k = i * kPerBatch + lane / 6, j = lane % 6;
         if (lane < 30 && k < S) dst[j * S + k] = (double)sum;
       }
-    } else {
+    } else if constexpr (ACC == ACC_TMEM) {
       tm_wait_st();
       for (int c0 = 0; c0 < 6 * S; c0 += 32) {      // (columns behind 6 S hold stale values: discarded below)
         float v[32];
@@ -319,14 +323,20 @@ k_spot_rev(TlProblem pb, RevArgs args) {
         if (i < 6 * S) dst[(i % 6) * S + i / 6] = (double)sum;
       }
     }
-    const float t0 = warp_sum(wac_z), t1 = warp_sum(acc_z), t2 = warp_sum(m_s1), t3 = warp_sum(m_s2),
-                t4 = warp_sum(m_n);
-    if (lane == 0) {
-      dst[6 * S] = (double)t0;
-      dst[6 * S + 1] = (double)t1;
-      dst[6 * S + 2] = (double)t2;
-      dst[6 * S + 3] = (double)t3;
-      dst[6 * S + 4] = (double)t4;
+    const float t2 = warp_sum(m_s1), t3 = warp_sum(m_s2), t4 = warp_sum(m_n);
+    if constexpr (GRAD) {
+      const float t0 = warp_sum(wac_z), t1 = warp_sum(acc_z);
+      if (lane == 0) {
+        dst[6 * S] = (double)t0;
+        dst[6 * S + 1] = (double)t1;
+        dst[6 * S + 2] = (double)t2;
+        dst[6 * S + 3] = (double)t3;
+        dst[6 * S + 4] = (double)t4;
+      }
+    } else if (lane == 0) {                  // MODE_SPOT_EVAL's three moments
+      dst[0] = (double)t2;
+      dst[1] = (double)t3;
+      dst[2] = (double)t4;
     }
   };
 
@@ -388,10 +398,12 @@ k_spot_rev(TlProblem pb, RevArgs args) {
         V travel;
         Parked<V> pk;
         fast_surface_rev(ray, V(s0.x), V(s0.z), V(s0.w), V(s1.x), V(s0.y), min_cos2, min_cz, travel, pk);
-        slot[0] = pk.dist.a;
-        slot[32] = pk.dist.b;
-        slot[64] = pk.ci.a;
-        slot[96] = pk.ci.b;
+        if constexpr (GRAD) {
+          slot[0] = pk.dist.a;
+          slot[32] = pk.dist.b;
+          slot[64] = pk.ci.a;
+          slot[96] = pk.ci.b;
+        }
         if constexpr (NCOMP > 2) {
           slot[128] = pk.co.a;
           slot[160] = pk.co.b;
@@ -442,6 +454,7 @@ k_spot_rev(TlProblem pb, RevArgs args) {
     m_s1 += lane_sum(wgt);
     m_s2 = lane_dot(wgt, wgt, m_s2);
     m_n += lane_sum(alive);
+    if constexpr (GRAD) {                     // (forward sweep only: the row's three moments are all there is)
     if (!all_ok && any_ok) {
       // (copies: the helper takes addresses, and address-taken variables live in local memory -- of `pre`,
       // `x_img`, `y_img` and `ok` themselves that cost 8 STL.128 + 8 LDL per group on the common path)
@@ -485,7 +498,7 @@ k_spot_rev(TlProblem pb, RevArgs args) {
           acc[5][k] += lane_sum(gr.mu);
         }
       }
-    } else {
+    } else if constexpr (ACC == ACC_TMEM) {
       const float4 *rec = reinterpret_cast<const float4 *>(tab.s) + 2 * (S - 1);
       const f2 *slot = state + (size_t)(S - 1) * NCOMP * 64;
       uint32_t tcol = tacc + 6 * (S - 1);
@@ -516,6 +529,7 @@ k_spot_rev(TlProblem pb, RevArgs args) {
       acc_z += lane_sum(az);
       wac_z = lane_dot(wgt, az, wac_z);
     }
+    }      // GRAD
   }
   if (row >= 0) flush();
 
@@ -581,7 +595,7 @@ struct RevVariant {
   int nw, ncomp;
 };
 
-int plan_rev(const TlProblem &pb, RevPlan &pl) {
+int plan_rev(const TlProblem &pb, RevPlan &pl, int want_grad = 1) {
   DeviceInfo info;
   int rc = device_info(info);
   if (rc) return rc;
@@ -601,9 +615,13 @@ int plan_rev(const TlProblem &pb, RevPlan &pl) {
       {"tmem4", k_spot_rev<16, 4, ACC_TMEM, 3>, 4, 3},      // the only one whose parked state fits for 19..32 surfaces
       {"reg8", S <= 12 ? k_spot_rev<12, 8, ACC_REG, 3> : k_spot_rev<16, 8, ACC_REG, 3>, 8, 3},
   };
-  const char *env = getenv("TL_REV");
-  const RevVariant *pick = nullptr;
+  // forward only (no parked state, 115 registers): 16 warps per SM; 20 / 24 warps measured 1-2 % slower
+  // (tools/profile_forward.py: 0.0940 / 0.0954 / 0.0959 ms against 0.1261 ms for round 1's k_trace_adj<SPOT_EVAL,f4>)
+  const RevVariant eval_variant = {"eval16", k_spot_rev<16, 16, ACC_NONE, 0>, 16, 0};
+  const char *env = want_grad ? getenv("TL_REV") : nullptr;
+  const RevVariant *pick = want_grad ? nullptr : &eval_variant;
   for (const RevVariant &v : variants) {
+    if (pick) break;
     const size_t smem = (size_t)v.nw * (rev_table_floats(S) + (size_t)S * v.ncomp * 2 * 64) * sizeof(float);
     const int tmem_cols = 512 / ((v.nw + 3) / 4);                               // per warp: TMEM column blocks
     const bool is_reg = !strcmp(v.name, "reg8");                                // (register accumulators: 16 surfaces)
@@ -619,7 +637,7 @@ int plan_rev(const TlProblem &pb, RevPlan &pl) {
   pl.name = pick->name;
   const int nw = pick->nw;
   pl.n_warps_cta = nw;
-  pl.n_acc = n_acc_of(MODE_SPOT_GRAD, S);
+  pl.n_acc = n_acc_of(want_grad ? MODE_SPOT_GRAD : MODE_SPOT_EVAL, S);
   pl.smem = (size_t)nw * (rev_table_floats(S) + (size_t)S * pick->ncomp * 2 * 64) * sizeof(float);
   TL_CHECK_CUDA(cudaFuncSetAttribute((const void *)pl.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)pl.smem));
@@ -642,6 +660,8 @@ int plan_rev(const TlProblem &pb, RevPlan &pl) {
 }
 
 bool use_rev_kernel(const TlProblem &pb) { return pb.S <= TL_MAX_SURFACES_SPOT && !getenv("TL_NO_REV"); }
+// the forward-only variant holds nothing per surface but the table: any surface count the forward entry points take
+bool use_rev_eval_kernel(const TlProblem &pb) { return pb.S <= TL_MAX_SURFACES_FWD && !getenv("TL_NO_REV"); }
 
 int launch_spot_rev(const TlProblem &pb, const RevPlan &pl, const float *ref_y, double *partial, double *moments,
                     cudaStream_t stream) {

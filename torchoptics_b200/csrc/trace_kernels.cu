@@ -2312,9 +2312,9 @@ size_t tl_spot_workspace(const TlProblem *pb, int32_t want_grad) {
   } else if (!use_rev_kernel(*pb)) {
     return 0;
   }
-  if (want_grad && use_rev_kernel(*pb)) {
+  if (want_grad ? use_rev_kernel(*pb) : use_rev_eval_kernel(*pb)) {
     RevPlan rp;
-    if (plan_rev(*pb, rp)) return 0;
+    if (plan_rev(*pb, rp, want_grad)) return 0;
     if (rp.partial_bytes > bytes) bytes = rp.partial_bytes;
   }
   return bytes;
@@ -2394,9 +2394,9 @@ static int spot_accumulate(const TlProblem *pb, int32_t want_grad, double *momen
   }
   if (use_rows_kernel(*pb, want_grad))      // many short rows: a warp per row, sums straight into `moments`
     return launch_spot_rows(*pb, want_grad, ref_y, moments, stream);
-  if (want_grad && use_rev_kernel(*pb)) {   // the reversible fused pass (spot_rev.cuh)
+  if (want_grad ? use_rev_kernel(*pb) : use_rev_eval_kernel(*pb)) {   // the reversible fused pass / its forward-only variant (spot_rev.cuh)
     RevPlan rp;
-    rc = plan_rev(*pb, rp);
+    rc = plan_rev(*pb, rp, want_grad);
     if (rc) return rc;
     if (workspace_bytes < rp.partial_bytes)
       return fail(TL_ERR_WORKSPACE, "workspace too small for tl_spot_accumulate%s");
@@ -2416,9 +2416,9 @@ const char *tl_spot_kernel_name(const TlProblem *pb, int32_t want_grad) {
   if (validate(pb, want_grad ? TL_MAX_SURFACES_SPOT : TL_MAX_SURFACES_FWD)) return "invalid";
   if (is_general(*pb)) return want_grad ? "k_trace_gen<SPOT_GRAD,f2>" : "k_trace_gen<SPOT_EVAL,f4>";
   if (use_rows_kernel(*pb, want_grad)) return want_grad ? "k_spot_rows<GRAD,f2>" : "k_spot_rows<EVAL,f2>";
-  if (want_grad && use_rev_kernel(*pb)) {
+  if (want_grad ? use_rev_kernel(*pb) : use_rev_eval_kernel(*pb)) {
     RevPlan rp;
-    if (plan_rev(*pb, rp)) return "invalid";
+    if (plan_rev(*pb, rp, want_grad)) return "invalid";
     snprintf(text, sizeof(text), "k_spot_rev<%s,f4>", rp.name);
     return text;
   }
