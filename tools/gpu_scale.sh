@@ -22,7 +22,7 @@ if [ "$N" -ge 2 ]; then
   timeout 600 python -m pytest tests/test_gpu_peer.py -q -p no:cacheprovider > gpurun_out/peer_tests_n$N.log 2>&1
   echo "peer tests rc=$?"; tail -3 gpurun_out/peer_tests_n$N.log
 fi
-if [ "$N" -eq 8 ]; then
+if [ "$N" -eq 8 ] && [ -z "$SKIP_CONFIG5" ]; then
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 \
       tools/optimize_lens.py --steps 500 --side 2310 > gpurun_out/r2_config5_8gpu_500steps.json 2> gpurun_out/config5_8gpu.err
   echo "config5 rc=$?"; cat gpurun_out/r2_config5_8gpu_500steps.json; tail -3 gpurun_out/config5_8gpu.err
