@@ -12,8 +12,8 @@
 //     sum    : CTA q adds its 1/world chunk of slots[p][0..world-1] in RANK ORDER (every rank gets
 //              the same bits) and writes it to the caller's output vector (out of place: other
 //              CTAs may still be pushing the input)
-//   The last CTA to finish bumps the device-resident epoch, so the kernel takes no per-step
-//   argument and replays unchanged inside a CUDA graph.  Two slot parities suffice: a rank can
+//   The epoch lives in device memory (one copy per CTA, bumped by that CTA at its end), so the kernel takes
+//   no per-step argument and replays unchanged inside a CUDA graph.  Two slot parities suffice: a rank can
 //   only start step e+2 after every peer signalled step e+1, i.e. after they finished reading e.
 //
 // This replaces nothing of the reference (it is single-GPU); it is the
@@ -28,10 +28,11 @@ constexpr unsigned long long kSpinLimitNs = 4000000000ull;   // 4 s: a dead peer
 
 struct Window {                  // header of a rank's window (device memory)
   unsigned int flags[2][kMaxWorld];
-  unsigned int epoch;            // steps completed by this rank
-  unsigned int done;             // CTAs finished in the current step
+  unsigned int epoch;            // steps completed by this rank (CTA 0's copy: what tl_peer_status reports)
+  unsigned int done;             // (unused since the per-CTA epochs)
   unsigned int status;           // 0 = ok, 1 = a wait timed out
-  unsigned int pad[29];          // header = 256 bytes, slots 8-byte aligned
+  unsigned int cta_epoch[kMaxWorld];   // steps completed, one copy per CTA of the exchange kernel
+  unsigned int pad[13];          // header = 256 bytes, slots 8-byte aligned
 };
 static_assert(sizeof(Window) == 256, "window header layout");
 
@@ -63,7 +64,10 @@ k_peer_allreduce(Peers peers, int rank, int world, long long capacity, const dou
                  long long n) {
   Window *mine = peers.win[rank];
   const int q = blockIdx.x;
-  const unsigned int e = *reinterpret_cast<volatile unsigned int *>(&mine->epoch);
+  // every CTA keeps its own copy of the epoch: it is read at the start and bumped at the end by the same CTA of
+  // consecutive launches (ordered by the stream), so the tail needs no cross-CTA counter, atomic or fence -- those
+  // were 2-3 us on the critical path of the step's next kernel
+  const unsigned int e = *reinterpret_cast<volatile unsigned int *>(&mine->cta_epoch[q]);
   const unsigned int p = e & 1u;
   const unsigned int want = e + 1u;
 
@@ -131,15 +135,10 @@ k_peer_allreduce(Peers peers, int rank, int world, long long capacity, const dou
     }
   }
 
-  // the last CTA of the step publishes the next epoch
-  __syncthreads();
+  // this CTA's next epoch (and, from CTA 0, the copy the host reads)
   if (threadIdx.x == 0) {
-    __threadfence();
-    if (atomicAdd(&mine->done, 1u) == (unsigned int)world - 1u) {
-      mine->done = 0;
-      __threadfence();
-      *reinterpret_cast<volatile unsigned int *>(&mine->epoch) = want;
-    }
+    *reinterpret_cast<volatile unsigned int *>(&mine->cta_epoch[q]) = want;
+    if (q == 0) *reinterpret_cast<volatile unsigned int *>(&mine->epoch) = want;
   }
 }
 
