@@ -172,7 +172,7 @@ __device__ __noinline__ void mirror_live_lane_rev(float *mine, int S, int ncomp,
 // 6 % of the kernel (profiles/r2c).  With it a ray costs two indexed loads and the few map steps.
 struct RowRays {
   const float *x, *y;                    // element (b, f, 0, w) of the pupil coordinates
-  float z0, cx0, cy0;                    // z, cx, cy themselves when all three are pupil-invariant
+  float z0, cx0, cy0, cz0;               // z, cx, cy (and fast_cz0 of them) when all three are pupil-invariant
   float vig[3], aim[3], xy_scale;        // apply_vignetting record, ray-aiming record (load_pupil_point)
 };
 // (strides and the presence of the optional tables are kernel parameters: read from the constant bank
@@ -188,6 +188,7 @@ __device__ __forceinline__ RowRays load_row_rays(const TlProblem &pb, int b, int
   r.z0 = pb.z.ptr[offset_of(pb.z, b, f, 0, w)];
   r.cx0 = pb.cx.ptr[offset_of(pb.cx, b, f, 0, w)];
   r.cy0 = pb.cy.ptr[offset_of(pb.cy, b, f, 0, w)];
+  r.cz0 = fast_cz0(r.cx0, r.cy0);
   r.xy_scale = pb.xy_scale ? pb.xy_scale[b] : 1.0f;
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
@@ -340,9 +341,14 @@ k_spot_rev(TlProblem pb, RevArgs args) {
     }
   };
 
+  // (row, group within the row) of the slice's first item by one division; then counted up -- the 64-bit
+  // division per group was ~30 instructions of every 128-ray group
+  int r = (int)(g_begin / args.groups_per_row), j = (int)(g_begin % args.groups_per_row) - 1;
   for (int64_t g = g_begin; g < g_end; ++g) {
-    const int r = (int)(g / args.groups_per_row);
-    const int j = (int)(g % args.groups_per_row);
+    if (++j == args.groups_per_row) {
+      j = 0;
+      ++r;
+    }
     if (r != row) {
       if (row >= 0) flush();
       row = r;
@@ -388,7 +394,7 @@ k_spot_rev(TlProblem pb, RevArgs args) {
 #pragma unroll
     for (int l = 0; l < N; ++l) clear[l] = false;
     if (pb.arith == TL_ARITH_GUARDED) {
-      Ray<V> ray{x, y, z, cx, cy, fast_cz0(cx, cy)};
+      Ray<V> ray{x, y, z, cx, cy, row_uniform_zc(pb) ? V(rr.cz0) : fast_cz0(cx, cy)};
       V min_cos2(1.0f), min_cz(1.0f), min_travel(3.0e38f);
       const float4 *rec = reinterpret_cast<const float4 *>(tab.s);                // running pointers: no index
       f2 *slot = state;                                                           // multiplications in the loop
