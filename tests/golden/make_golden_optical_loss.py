@@ -167,6 +167,10 @@ def main():
         rec['f64_grad_outputs'] = np.asarray(grads64, np.float64)
         mean = loss.optical_loss_unsupervised(torch.tensor(inputs), torch.tensor(outputs), 0.2, device='cpu')
         rec['batch_mean'] = np.asarray([float(v) for v in mean], np.float32)
+        # the supervised loss (ol:136-176) on perturbed copies of the designs as "labels"
+        labels = (outputs * np.random.default_rng(seed + 50).uniform(0.9, 1.1, outputs.shape)).astype(np.float32)
+        rec['supervised_labels'] = labels
+        rec['supervised_loss'] = np.float32(float(loss.optical_loss_supervised(torch.tensor(labels), torch.tensor(outputs), device='cpu')))
         np.savez_compressed(os.path.join(OUT, f'{lens_type}.npz'), **rec)
         rel = np.abs(rec['grad_outputs'] - rec['f64_grad_outputs']).max(axis=1) / np.abs(rec['f64_grad_outputs']).max(axis=1)
         print(lens_type, 'rms', per['rms'], 'penalty', per['penalty'], 'nan grads', int(np.isnan(rec['grad_outputs']).sum()),

@@ -1,9 +1,12 @@
 """Host-side mirror of the reference API (ray-set construction, paraxial optics,
 data model) against the golden records of the reference -- CPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
 
+from tests.conftest import GOLDEN_DIR
 from torchoptics_b200 import lens_modeling as lm
 from torchoptics_b200 import prescriptions
 from torchoptics_b200 import ray_tracing_lite as rt
@@ -158,3 +161,23 @@ def test_lens_tables_follow_the_structure_not_its_id():
     structure.stop_idx[0] = 2
     assert int(tracer._tables(lens).stop_idx[0]) == 2 and tracer._tables(lens) is not first
     assert structure.up_to_stop() is not front and structure.up_to_stop().mask.shape[1] == 2
+
+
+def test_optical_loss_supervised_and_codes_match_the_reference():
+    """optical_loss.py:136-176 (plain tensor arithmetic, runs anywhere) against the records of the reference's own
+    class, and the inferred sequence codes (optical_loss.py:14-18)."""
+    import glob
+    from torchoptics_b200.optical_loss import Optical_Loss, sequence_decoder, sequence_encoder
+    paths = sorted(glob.glob(os.path.join(GOLDEN_DIR, 'optical_loss', '*.npz')))
+    assert len(paths) == 4
+    for path in paths:
+        with np.load(path) as z:
+            lens_type = str(z['lens_type'])
+            loss = Optical_Loss(lens_type)
+            got = loss.optical_loss_supervised(torch.from_numpy(z['supervised_labels']), torch.from_numpy(z['outputs']), device='cpu')
+            assert abs(float(got) - float(z['supervised_loss'])) <= 1e-6 * abs(float(z['supervised_loss']))
+            assert sequence_decoder(sequence_encoder(lens_type)) == lens_type
+            assert z['outputs'].shape[1] == loss.numout and z['inputs'].shape[1] == loss.numin + 4
+    t = torch.arange(4.0)
+    assert torch.equal(Optical_Loss.t_converter(2, 'GAGA', t, torch.tensor([9.0])), torch.tensor([0., 9., 1., 2., 3.]))
+    assert Optical_Loss.t_converter(2, 'GAGA', t, -1) is t and Optical_Loss.t_converter(1, 'GAGA', t, torch.tensor([9.0])) is t
