@@ -571,7 +571,7 @@ def main():
                            'step': 'RayTracer.spot_rms_and_grads: staging -> chief rays -> fused trace+adjoint -> '
                                    'reduce -> (exchange) -> finalize -> chain rule; rms + d rms/d(c,t,nd,v)',
                            'arith': 'guarded'},
-                'clocks': clocks.summary(),
+                'clocks': dict(clocks.summary(), under_sustained_load=sustained['clocks']),
                 'e2e': {'value': e2e_value, 'unit': 'events/s', 'h2d_bytes_per_step': h2d,
                         'd2h_bytes_per_step': d2h, 'ms_per_step': e2e_secs / args.steps * 1e3,
                         'api': 'GraphedSpotStep (CUDA graph of the public RayTracer.spot_rms_and_grads path: one pinned H2D copy, the kernel sequence, one D2H copy)'
