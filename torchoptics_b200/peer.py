@@ -71,7 +71,12 @@ class PeerExchange:
         self._group = group
 
     def all_reduce(self, data):
-        """Sum of ``data`` (float64, contiguous, CUDA) over the ranks; returns a new tensor."""
+        """Sum of ``data`` (float64, contiguous, CUDA) over the ranks; returns a new tensor.
+
+        Every ``all_reduce`` of one ``PeerExchange`` must be issued on ONE stream, in the same order on every
+        rank: the kernel reads its epoch from the window at the start and bumps it at the end, so two calls in
+        flight on different streams would share an epoch (and a slot parity).  A peer that does not show up within
+        4 s makes the result NaN on this rank, now and in every later step (``status()`` then reports 1)."""
         if data.dtype != torch.float64 or not data.is_contiguous():
             raise ValueError('PeerExchange.all_reduce needs a contiguous float64 tensor')
         nat.require_cuda(data, 'data')
