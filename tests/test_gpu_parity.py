@@ -103,6 +103,23 @@ def test_forward_guarded_policy(golden):
 
 
 @pytest.mark.parametrize('arith', ['guarded', 'exact'])
+def test_forward_long_row_kernel_on_every_golden(golden, arith, monkeypatch):
+    """The golden pupils are short (64 .. 1 024 points) and take the flattened forward kernel; with TL_NO_ROWS the
+    same calls take the long-row kernel (k_spot_rev<out16>, the one BASELINE-size traces use): same checks -- masks,
+    parked failed rays, tolerances, and the exact policy bit for bit -- misses, TIR and backward rays included."""
+    monkeypatch.setenv('TL_NO_ROWS', '1')
+    i = _inputs(golden, DEV)
+    allow = bool(golden['allow_backward_rays'])
+    out = rt.trace_skew(*_args(i), allow_backward_rays=allow, arith=arith)
+    ref = None
+    if arith == 'exact':
+        cpu = _inputs(golden, 'cpu')
+        with oracle.ieee_sqrt():
+            ref = oracle.trace(*_args(cpu), False, allow)
+    _check_outputs(out, golden, exact_ref=ref)
+
+
+@pytest.mark.parametrize('arith', ['guarded', 'exact'])
 def test_backward_against_oracle_autograd(golden, arith):
     allow = bool(golden['allow_backward_rays'])
     gen = torch.Generator().manual_seed(1)

@@ -21,12 +21,16 @@
 //
 // Per-event op table of the f4 instantiation: profiles/r2_*.txt (SASS mix) and DESIGN.md section 5.
 
-enum { ACC_REG = 0, ACC_TMEM = 1, ACC_NONE = 2 };   // ACC_NONE: forward sweep only (no parking, no adjoint)
+enum { ACC_REG = 0, ACC_TMEM = 1, ACC_NONE = 2, ACC_OUT = 3 };   // ACC_NONE: forward sweep only (no parking, no adjoint);
+                                                                 // ACC_OUT: forward trace that WRITES its six outputs (tl_trace_fwd)
 
 struct RevArgs {
   double *partial;      // [rows, max_owners, n_acc]: row-major by (row, rank of the owning warp within the row)
   const float *ref_y;   // [B,F]
   int groups_per_row, max_owners, n_acc;
+};
+struct RevOutArgs : RevArgs {      // the ACC_OUT instantiation's argument (the others keep the smaller struct)
+  TlTraceOut out;                  // x, y, cx, cy, ok, backward, contiguous [B,F,P,W]
 };
 
 // Surface table of one (lens, wavelength): one 32-byte record per surface, so that a step of either
@@ -216,15 +220,17 @@ __device__ __forceinline__ void row_pupil_point(const TlProblem &pb, const RowRa
   }
 }
 
-template <int NS_MAX, int NW, int ACC, int NCOMP>
+template <int NS_MAX, int NW, int ACC, int NCOMP, class ARGS = RevArgs>
 __global__ void __launch_bounds__(NW * 32, 1)
-k_spot_rev(TlProblem pb, RevArgs args) {
+k_spot_rev(TlProblem pb, ARGS args) {
   extern __shared__ __align__(16) float smem_rev[];
   __shared__ uint32_t tmem_slot;
   using V = f4;
   constexpr int N = 4;
   constexpr int NA = (ACC == ACC_REG) ? NS_MAX : 1;
-  constexpr bool GRAD = ACC != ACC_NONE;      // ACC_NONE: trace + spot moments only (tl_spot_accumulate without gradients)
+  constexpr bool GRAD = ACC == ACC_REG || ACC == ACC_TMEM;      // ACC_NONE: trace + spot moments only (tl_spot_accumulate
+                                                                // without gradients); ACC_OUT: trace_skew's forward, materialised
+  constexpr bool WRITE = ACC == ACC_OUT;
   static_assert(GRAD ? NCOMP >= 2 : NCOMP == 0, "parked components: 2 or 3 with the adjoint, none without");
   constexpr uint32_t kTmemCols = 512;
   const int S = pb.S;
@@ -287,6 +293,7 @@ k_spot_rev(TlProblem pb, RevArgs args) {
 
   // the warp's sums of this row segment -> one fp64 partial row
   auto flush = [&]() {
+    if constexpr (WRITE) return;      // (the output-writing variant keeps no sums)
     // partial row of (row, this warp's rank among the warps that own a piece of the row): the reducer
     // then sums a row's partials from consecutive memory, without recomputing any slice bounds
     const int64_t first_owner = owner_of((int64_t)row * args.groups_per_row, total, n_warps);
@@ -357,7 +364,7 @@ k_spot_rev(TlProblem pb, RevArgs args) {
       b = r / (pb.W * pb.F);
       tab = load_rev_table(wbase, pb, b, w, lane);
       rr = load_row_rays(pb, b, f, w);
-      y0 = args.ref_y[b * pb.F + f];
+      y0 = WRITE ? 0.f : args.ref_y[b * pb.F + f];
       reset();
     }
     // lane l of this thread = pupil point p_base + 32 l; past the end of the slice: a copy of its
@@ -430,10 +437,12 @@ k_spot_rev(TlProblem pb, RevArgs args) {
       }
     }
     bool any_live = false, all_ok = true, any_ok = false;
+    [[maybe_unused]] bool bw[WRITE ? N : 1];      // ray_backward (ACC_OUT): false on the fast path by construction of its guard band
     V alive;
 #pragma unroll
     for (int l = 0; l < N; ++l) {
       ok[l] = true;
+      if constexpr (WRITE) bw[l] = false;
       if (!clear[l]) {      // not clearly good everywhere: this lane alone, exact policy
         const Traced one = trace_exact_rev(lane_get(x, l), lane_get(y, l), lane_get(z, l), lane_get(cx, l),
                                            lane_get(cy, l), tab, S, allow_backward, mine, NCOMP, l);
@@ -446,12 +455,27 @@ k_spot_rev(TlProblem pb, RevArgs args) {
         lane_set(x_img, l, one.x);
         lane_set(y_img, l, one.y);
         ok[l] = one.ok;
+        if constexpr (WRITE) bw[l] = one.backward;
       }
       const bool live = ok[l] && has[l];
       any_live = any_live || live;
       all_ok = all_ok && ok[l];
       any_ok = any_ok || ok[l];
       lane_set(alive, l, live ? 1.0f : 0.0f);
+    }
+    if constexpr (WRITE) {                    // trace_skew's six outputs (rtl:672-675), contiguous [B,F,P,W]
+#pragma unroll
+      for (int l = 0; l < N; ++l) {
+        if (!has[l]) continue;
+        const int64_t o = (((int64_t)b * pb.F + f) * pb.P + (p_base + l * 32)) * pb.W + w;
+        args.out.x[o] = lane_get(x_img, l);
+        args.out.y[o] = lane_get(y_img, l);
+        args.out.cx[o] = lane_get(pre.cx, l);
+        args.out.cy[o] = lane_get(pre.cy, l);
+        args.out.ok[o] = ok[l];
+        args.out.backward[o] = bw[l];
+      }
+      continue;
     }
     V wgt = (y_img - V(y0)) * alive;
 #pragma unroll
@@ -583,7 +607,7 @@ k_reduce_owner_rows(const double *partial, double *dst, int n_rows, int groups_p
     dst[(int64_t)row * n_acc + slot] = (part[0][slot] + part[1][slot]) + (part[2][slot] + part[3][slot]);
 }
 
-typedef void (*RevKernelPtr)(TlProblem, RevArgs);
+typedef const void *RevKernelPtr;      // (TlProblem, RevArgs), or (TlProblem, RevOutArgs) for the ACC_OUT instantiation
 
 struct RevPlan {
   RevKernelPtr kernel = nullptr;
@@ -612,20 +636,21 @@ int plan_rev(const TlProblem &pb, RevPlan &pl, int want_grad = 1) {
   // that are not a multiple of the four schedulers lose 15 %.  (Round 1's k_trace_adj: 0.2988.)  Residency matters
   // little (8 -> 12 warps per SM: 5 %): the pass is bound by register-operand bandwidth (tools/microbench4.cu).
   const RevVariant variants[] = {
-      {"tmem12", k_spot_rev<16, 12, ACC_TMEM, 3>, 12, 3},
-      {"tmem14c2", k_spot_rev<16, 14, ACC_TMEM, 2>, 14, 2},
-      {"tmem16", k_spot_rev<16, 16, ACC_TMEM, 2>, 16, 2},
-      {"tmem12c2", k_spot_rev<16, 12, ACC_TMEM, 2>, 12, 2},
-      {"tmem10", k_spot_rev<16, 10, ACC_TMEM, 3>, 10, 3},
-      {"tmem8", k_spot_rev<16, 8, ACC_TMEM, 3>, 8, 3},
-      {"tmem4", k_spot_rev<16, 4, ACC_TMEM, 3>, 4, 3},      // the only one whose parked state fits for 19..32 surfaces
-      {"reg8", S <= 12 ? k_spot_rev<12, 8, ACC_REG, 3> : k_spot_rev<16, 8, ACC_REG, 3>, 8, 3},
+      {"tmem12", (const void *)k_spot_rev<16, 12, ACC_TMEM, 3>, 12, 3},
+      {"tmem14c2", (const void *)k_spot_rev<16, 14, ACC_TMEM, 2>, 14, 2},
+      {"tmem16", (const void *)k_spot_rev<16, 16, ACC_TMEM, 2>, 16, 2},
+      {"tmem12c2", (const void *)k_spot_rev<16, 12, ACC_TMEM, 2>, 12, 2},
+      {"tmem10", (const void *)k_spot_rev<16, 10, ACC_TMEM, 3>, 10, 3},
+      {"tmem8", (const void *)k_spot_rev<16, 8, ACC_TMEM, 3>, 8, 3},
+      {"tmem4", (const void *)k_spot_rev<16, 4, ACC_TMEM, 3>, 4, 3},      // the only one whose parked state fits for 19..32 surfaces
+      {"reg8", S <= 12 ? (const void *)k_spot_rev<12, 8, ACC_REG, 3> : (const void *)k_spot_rev<16, 8, ACC_REG, 3>, 8, 3},
   };
   // forward only (no parked state, 115 registers): 16 warps per SM; 20 / 24 warps measured 1-2 % slower
   // (tools/profile_forward.py: 0.0940 / 0.0954 / 0.0959 ms against 0.1261 ms for round 1's k_trace_adj<SPOT_EVAL,f4>)
-  const RevVariant eval_variant = {"eval16", k_spot_rev<16, 16, ACC_NONE, 0>, 16, 0};
-  const char *env = want_grad ? getenv("TL_REV") : nullptr;
-  const RevVariant *pick = want_grad ? nullptr : &eval_variant;
+  const RevVariant eval_variant = {"eval16", (const void *)k_spot_rev<16, 16, ACC_NONE, 0>, 16, 0};
+  const RevVariant out_variant = {"out16", (const void *)k_spot_rev<16, 16, ACC_OUT, 0, RevOutArgs>, 16, 0};      // want_grad == 2: tl_trace_fwd
+  const char *env = want_grad == 1 ? getenv("TL_REV") : nullptr;
+  const RevVariant *pick = want_grad == 1 ? nullptr : (want_grad == 2 ? &out_variant : &eval_variant);
   for (const RevVariant &v : variants) {
     if (pick) break;
     const size_t smem = (size_t)v.nw * (rev_table_floats(S) + (size_t)S * v.ncomp * 2 * 64) * sizeof(float);
@@ -643,7 +668,7 @@ int plan_rev(const TlProblem &pb, RevPlan &pl, int want_grad = 1) {
   pl.name = pick->name;
   const int nw = pick->nw;
   pl.n_warps_cta = nw;
-  pl.n_acc = n_acc_of(want_grad ? MODE_SPOT_GRAD : MODE_SPOT_EVAL, S);
+  pl.n_acc = n_acc_of(want_grad == 1 ? MODE_SPOT_GRAD : MODE_SPOT_EVAL, S);
   pl.smem = (size_t)nw * (rev_table_floats(S) + (size_t)S * pick->ncomp * 2 * 64) * sizeof(float);
   TL_CHECK_CUDA(cudaFuncSetAttribute((const void *)pl.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)pl.smem));
@@ -671,7 +696,7 @@ bool use_rev_eval_kernel(const TlProblem &pb) { return pb.S <= TL_MAX_SURFACES_F
 
 int launch_spot_rev(const TlProblem &pb, const RevPlan &pl, const float *ref_y, double *partial, double *moments,
                     cudaStream_t stream) {
-  RevArgs args;
+  RevArgs args{};
   args.partial = partial;
   args.ref_y = ref_y;
   args.groups_per_row = pl.groups_per_row;
@@ -685,6 +710,27 @@ int launch_spot_rev(const TlProblem &pb, const RevPlan &pl, const float *ref_y, 
   const int rows = pb.B * pb.F * pb.W;
   k_reduce_owner_rows<<<rows, 128, 0, stream>>>(partial, moments, rows, pl.groups_per_row,
                                                 pl.n_blocks * pl.n_warps_cta, pl.max_owners, pl.n_acc);
+  g_launches++;
+  TL_CHECK_CUDA(cudaGetLastError());
+  return TL_OK;
+}
+
+// trace_skew's forward, materialised (tl_trace_fwd): the forward-only kernel writing its six outputs, whole pupil
+int launch_trace_rev(const TlProblem &pb, const TlTraceOut &out, cudaStream_t stream) {
+  TlProblem full = pb;
+  full.p_begin = 0;
+  full.p_end = pb.P;
+  RevPlan pl;
+  int rc = plan_rev(full, pl, 2);
+  if (rc) return rc;
+  RevOutArgs args{};
+  args.groups_per_row = pl.groups_per_row;
+  args.max_owners = pl.max_owners;
+  args.n_acc = pl.n_acc;
+  args.out = out;
+  void *params[] = {(void *)&full, (void *)&args};
+  TL_CHECK_CUDA(cudaLaunchKernel((const void *)pl.kernel, dim3(pl.n_blocks), dim3(pl.n_warps_cta * 32), params,
+                                 pl.smem, stream));
   g_launches++;
   TL_CHECK_CUDA(cudaGetLastError());
   return TL_OK;

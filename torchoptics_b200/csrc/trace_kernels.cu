@@ -2107,9 +2107,11 @@ int tl_trace_fwd(const TlProblem *pb, const TlTraceOut *out, void *stream_) {
   // short pupil axis (the batched-lens workload: 64 rays per (lens, field, wavelength)): the
   // (pupil, wavelength)-flattened map keeps a CTA's threads busy where a CTA per row would idle
   const size_t smem_pw = (size_t)pb->W * ((5 * (size_t)pb->S + 3) & ~(size_t)3) * sizeof(float);
-  const bool short_rows = !is_general(*pb) && smem_pw <= 48 * 1024 &&
-                          ((pb->P < 2 * kFwdThreads && !getenv("TL_NO_ROWS")) || pb->aim || pb->vig);
-  if ((pb->aim || pb->vig) && !short_rows)
+  // long rows of a spherical lens: the warp-owned forward kernel of spot_rev.cuh (any pupil map, any S <= 256)
+  const bool rev_ok = !is_general(*pb) && !stacks && use_rev_eval_kernel(*pb);
+  const bool many_short = pb->P < 2 * kFwdThreads && !getenv("TL_NO_ROWS");
+  const bool short_rows = !is_general(*pb) && smem_pw <= 48 * 1024 && (many_short || ((pb->aim || pb->vig) && !rev_ok));
+  if ((pb->aim || pb->vig) && !short_rows && !rev_ok)
     return fail(TL_ERR_INVALID, "an aimed forward trace needs W * S surface tables within 48 KB of shared memory%s");
   if (stacks || short_rows) {
     const int64_t row_len = (int64_t)pb->P * pb->W;
@@ -2137,6 +2139,7 @@ int tl_trace_fwd(const TlProblem *pb, const TlTraceOut *out, void *stream_) {
     TL_CHECK_CUDA(cudaGetLastError());
     return TL_OK;
   }
+  if (rev_ok) return launch_trace_rev(*pb, *out, (cudaStream_t)stream_);
   const size_t smem = 5 * (size_t)pb->S * sizeof(float);
   k_trace_fwd<<<pl.n_blocks, kFwdThreads, smem, (cudaStream_t)stream_>>>(*pb, *out, pl.nchunks,
                                                                          pl.chunk_len);
@@ -2439,7 +2442,7 @@ int tl_spot_kernel_only(const TlProblem *pb, const float *ref_y, void *workspace
   rc = plan_rev(*pb, pl);
   if (rc) return rc;
   if (workspace_bytes < pl.partial_bytes) return fail(TL_ERR_WORKSPACE, "workspace too small%s");
-  RevArgs args;
+  RevArgs args{};
   args.partial = (double *)workspace;
   args.ref_y = ref_y;
   args.groups_per_row = pl.groups_per_row;
