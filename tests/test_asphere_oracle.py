@@ -123,3 +123,71 @@ def test_semi_diameter_clip_and_parking():
     for j in range(4):
         assert not out[j][dead].any()                  # parked rays output exact zeros
         assert torch.equal(out[j][ok], free[j][ok])    # survivors are untouched by the clip
+
+
+def test_against_an_independent_bracketed_root_finder_fp64():
+    """A second, independent statement of rows A9/A10 in scalar Python: the intersection by a BRACKETED root
+    finder (scipy.optimize.brentq on F(tau) = z + tau cz - sag, no Newton, no base-sphere start), the normal
+    from the analytic slope written with explicit powers, Snell's law in its textbook vector form
+    d' = mu d + (sqrt(1 - mu^2 (1 - (n.d)^2)) - mu n.d) n, the optical path as the sum of n |segment|.
+    1 000 random rays through the four-surface asphere: positions / cosines / OPL of the oracle (fp64,
+    four Newton steps) agree with it to 1e-9 -- the fixed iteration count has converged and the oracle's
+    conventions (shifted vertex coordinates, index bookkeeping) describe the same physical ray."""
+    import math
+    from scipy.optimize import brentq
+
+    p = _asphere_problem(torch.float64, n=500)          # 500 pupil points x 2 fields x 2 wavelengths
+    out = gen.trace(p['x'], p['y'], p['z'], p['cx'], p['cy'], p['c'], p['t'], p['mu'], p['mask'], k=p['k'], a=p['a'])
+    assert bool(out[4].all())
+    c = p['c'].reshape(-1).tolist()
+    k = p['k'].reshape(-1).tolist()
+    t = p['t'].reshape(-1).tolist()
+    a = p['a'].reshape(4, 7).tolist()
+    mu = p['mu'].reshape(2, 4).tolist()
+
+    def sag(s_i, rho):
+        base = c[s_i] * rho / (1.0 + math.sqrt(1.0 - (1.0 + k[s_i]) * c[s_i] ** 2 * rho))
+        return base + sum(a[s_i][j] * rho ** (j + 2) for j in range(7))
+
+    def slope(s_i, rho):                                  # d sag / d rho
+        base = c[s_i] / (2.0 * math.sqrt(1.0 - (1.0 + k[s_i]) * c[s_i] ** 2 * rho))
+        return base + sum((j + 2) * a[s_i][j] * rho ** (j + 1) for j in range(7))
+
+    worst = 0.0
+    checked = 0
+    for f in range(2):
+        for w in range(2):
+            for q in range(0, 500, 2):                    # 250 x 4 = 1 000 rays
+                pos = [float(p['x'][0, 0, q, 0]), float(p['y'][0, 0, q, 0]), float(p['z'][0, 0, 0, 0])]
+                d = [float(p['cx'][0, 0, 0, 0]), float(p['cy'][0, f, 0, 0]), 0.0]
+                d[2] = math.sqrt(1.0 - d[0] ** 2 - d[1] ** 2)
+                index, path = 1.0, 0.0
+                for s_i in range(4):
+                    def gap(tau):
+                        hx, hy = pos[0] + tau * d[0], pos[1] + tau * d[1]
+                        return pos[2] + tau * d[2] - sag(s_i, hx * hx + hy * hy)
+                    lo, hi = -4.0, (4.0 - pos[2]) / d[2]
+                    assert gap(lo) < 0.0 < gap(hi)
+                    tau = brentq(gap, lo, hi, xtol=1e-15, rtol=8.9e-16, maxiter=200)
+                    pos = [pos[j] + tau * d[j] for j in range(3)]
+                    path += index * tau
+                    ds = slope(s_i, pos[0] ** 2 + pos[1] ** 2)
+                    n = [-2.0 * pos[0] * ds, -2.0 * pos[1] * ds, 1.0]
+                    norm = math.sqrt(sum(v * v for v in n))
+                    n = [v / norm for v in n]
+                    m = mu[w][s_i]
+                    cos_in = sum(n[j] * d[j] for j in range(3))
+                    cos_out = math.sqrt(1.0 - m * m * (1.0 - cos_in ** 2))
+                    d = [m * d[j] + (cos_out - m * cos_in) * n[j] for j in range(3)]
+                    norm = math.sqrt(sum(v * v for v in d))
+                    d = [v / norm for v in d]
+                    pos[2] -= t[s_i]
+                    index /= m
+                tau = -pos[2] / d[2]
+                path += index * tau
+                got = [float(out[j][0, f, q, w]) for j in (0, 1, 2, 3, 6)]
+                want = [pos[0] + tau * d[0], pos[1] + tau * d[1], d[0], d[1], path]
+                worst = max(worst, max(abs(g - v) for g, v in zip(got, want)))
+                checked += 1
+    assert checked == 1000
+    assert worst < 1e-9, worst
