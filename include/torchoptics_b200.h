@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define TL_ABI_VERSION 11
+#define TL_ABI_VERSION 12
 
 enum {
   TL_OK = 0,
@@ -103,7 +103,8 @@ typedef struct TlTraceOut {
   float *x, *y, *cx, *cy;
   uint8_t *ok, *backward;      /* 0/1 bytes (torch.bool storage)                   */
   float *opl;                  /* optional: optical path length entrance -> image
-                                  (general-surface lenses only; NULL = not wanted)  */
+                                  (general-surface lenses only; NULL = not wanted);
+                                  differentiable: TlSeeds.gopl                      */
   /* trace_skew(aggregate=True), rtl:641-657: the three penalty stacks, each a contiguous
    * [S,B,F,P,W] array (surface-major; the reference returns them as S-long lists).  All three
    * NULL = aggregate=False; spherical lenses only.
@@ -121,6 +122,9 @@ typedef struct TlSeeds {
    * Where the reference's own gradient is NaN (it takes sqrt of a failed ray's negative cos^2
    * before masking it, rtl:646-654) a failed ray contributes 0 here. */
   const float *gz_relu, *gtheta, *gtheta_prime;
+  /* upstream gradient of TlTraceOut.opl (general-surface lenses only), contiguous [B,F,P,W] or NULL.
+   * A ray that is not ok contributes nothing (its opl is a partial sum up to the failure). */
+  const float *gopl;
 } TlSeeds;
 
 /* Gradients produced by tl_trace_bwd.  Prescription gradients are summed over

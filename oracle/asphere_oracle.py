@@ -142,3 +142,25 @@ def trace(x, y, z, cx, cy, c, t, mu, mask, k=None, a=None, sd=None, allow_backwa
     else:
         ray_ok = ray_ok & ~((travel < 0) & counted)
     return x, y, cx, cy, ray_ok, ray_backward, opl
+
+
+def opd(x, y, cx, cy, opl, ray_ok, n_image, radius, chief=0):
+    """Optical path DIFFERENCE of row A10 from the outputs of `trace`: every ray's path is measured up to the
+    reference sphere -- centre = the image point of the field's chief ray (pupil index `chief`), radius `radius`
+    (> 0: the sphere lies in front of the image plane, normally through the exit pupil's axial point) -- and the
+    chief ray's own path to that sphere is subtracted.
+
+    A ray arrives at the image plane at P = (x, y, 0) with direction d; the sphere is met at P + s d, s < 0 the
+    root of |P - C + s d| = R that lies in front of the plane; path to the sphere = opl + n_image s; for the chief
+    ray itself s = -R.  x, y, cx, cy, opl, ray_ok: [B,F,P,W]; n_image: [B,1,1,W] (index of the image space:
+    the product of 1 / mu over the surfaces); radius: broadcastable to [B,F,1,W].  Rays that are not ok -- and
+    every ray of a field whose chief ray is not ok -- get 0."""
+    cz = sph._sqrt(1 - cx ** 2 - cy ** 2)
+    pick = slice(chief, chief + 1)
+    dx, dy = x - x[:, :, pick], y - y[:, :, pick]
+    along = dx * cx + dy * cy                                  # (P - C) . d
+    disc = along * along - (dx * dx + dy * dy) + radius * radius
+    s = -along - sph._sqrt(disc)
+    out = (opl - opl[:, :, pick]) + n_image * (s + radius)
+    good = ray_ok & ray_ok[:, :, pick]
+    return torch.where(good, out, torch.zeros_like(out))

@@ -100,7 +100,7 @@ def asph_fast(dtype, x, y, z, cx, cy, c, k, a, t, mu, sd, seeds=None):
     outs = [np.zeros(n, dtype) for _ in range(7)]
     grads = [np.zeros(n, dtype) for _ in range(5)]
     gp, gt, gmu = np.zeros(S * 9, np.float64), np.zeros(S, np.float64), np.zeros(S, np.float64)
-    sd_ = [None] * 4 if seeds is None else [f(s) for s in seeds]
+    sd_ = [None] * 5 if seeds is None else [f(s) for s in seeds] + [None] * (5 - len(seeds))      # x, y, cx, cy[, opl]
     fn = lib().hc_asph_fast_f32 if dtype == np.float32 else lib().hc_asph_fast_f64
     fn(ctypes.c_int64(n), _p(x), _p(y), _p(z), _p(cx), _p(cy), ctypes.c_int(S), _p(c), _p(k), _p(a),
        _p(t), _p(mu), _p(sd2), *[_p(s) for s in sd_], *[_p(o) for o in outs], *[_p(g) for g in grads],

@@ -174,7 +174,7 @@ template <class T>
 static void asph_fast_and_adjoint(int64_t n, const T *x, const T *y, const T *z, const T *cx, const T *cy,
                                   int S, const T *c, const T *kk, const T *a, const T *t, const T *mu,
                                   const T *sd2, const T *sx, const T *sy, const T *scx, const T *scy,
-                                  T *ox, T *oy, T *ocx, T *ocy, T *oopl, T *min_cos2, T *min_clip,
+                                  const T *sopl, T *ox, T *oy, T *ocx, T *ocy, T *oopl, T *min_cos2, T *min_clip,
                                   T *gx, T *gy, T *gz, T *gcx, T *gcy, double *gp, double *gt,
                                   double *gmu) {
   std::vector<Ray<T>> st(S + 1);
@@ -200,9 +200,16 @@ static void asph_fast_and_adjoint(int64_t n, const T *x, const T *y, const T *z,
     min_cos2[i] = mq; min_clip[i] = mclip;
     if (!sx) continue;
     Sweep<T> sw = sweep_begin(pre, r.x, r.y, sx[i], sy[i], scx[i], scy[i]);
+    // (the index in front of every surface, as the kernel's table holds it)
+    std::vector<T> n_at(S + 1);
+    n_at[0] = T(1);
+    for (int k = 0; k < S; ++k) n_at[k + 1] = n_at[k] / mu[k];
+    OplSeed<T> os{sopl ? sopl[i] : T(0), T(0)};
+    if (sopl) sweep_begin_opl(sw, pre, os.q, n_at[S]);
     for (int k = S - 1; k >= 0; --k) {
       const AsphSurfaceT<T> sf = make_surface<T>(k, c, kk, a, t, mu, sd2);
-      AsphGrad<T> g = sweep_asphere(sw, st[k + 1].x, st[k + 1].y, st[k].cx, st[k].cy, sf);
+      AsphGrad<T> g = sweep_asphere(sw, st[k + 1].x, st[k + 1].y, st[k].cx, st[k].cy, sf, sopl ? &os : nullptr,
+                                    n_at[k], n_at[k + 1]);
       for (int j = 0; j < kAsphParams; ++j) gp[k * kAsphParams + j] += (double)g.p[j];
       gt[k] += (double)g.t; gmu[k] += (double)g.mu;
     }
@@ -213,9 +220,9 @@ static void asph_fast_and_adjoint(int64_t n, const T *x, const T *y, const T *z,
 #define HCA_ARGS(T)                                                                              \
   int64_t n, const T *x, const T *y, const T *z, const T *cx, const T *cy, int S, const T *c,   \
       const T *kk, const T *a, const T *t, const T *mu, const T *sd2, const T *sx, const T *sy, \
-      const T *scx, const T *scy, T *ox, T *oy, T *ocx, T *ocy, T *oopl, T *min_cos2,           \
+      const T *scx, const T *scy, const T *sopl, T *ox, T *oy, T *ocx, T *ocy, T *oopl, T *min_cos2, \
       T *min_clip, T *gx, T *gy, T *gz, T *gcx, T *gcy, double *gp, double *gt, double *gmu
-#define HCA_PASS n, x, y, z, cx, cy, S, c, kk, a, t, mu, sd2, sx, sy, scx, scy, ox, oy, ocx, ocy, oopl, \
+#define HCA_PASS n, x, y, z, cx, cy, S, c, kk, a, t, mu, sd2, sx, sy, scx, scy, sopl, ox, oy, ocx, ocy, oopl, \
                  min_cos2, min_clip, gx, gy, gz, gcx, gcy, gp, gt, gmu
 extern "C" void hc_asph_fast_f32(HCA_ARGS(float)) { asph_fast_and_adjoint<float>(HCA_PASS); }
 extern "C" void hc_asph_fast_f64(HCA_ARGS(double)) { asph_fast_and_adjoint<double>(HCA_PASS); }

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_argument_checks():
     lib = _native.load()
-    assert lib.tl_abi_version() == _native.ABI_VERSION == 11
+    assert lib.tl_abi_version() == _native.ABI_VERSION == 12
     assert lib.tl_spot_moment_count(11, 1) == 6 * 11 + 5
     assert lib.tl_spot_moment_count(11, 0) == 3
     assert lib.tl_rms_workspace(1, 3, 64, 3) > 0

@@ -50,7 +50,7 @@ def test_fast_policy_and_adjoint_fp64():
     for w in range(2):
         rays, tabs = _flat(p, np.float64, w)
         n = rays['x'].size
-        seeds = [rng.standard_normal(n) for _ in range(4)]
+        seeds = [rng.standard_normal(n) for _ in range(5)]      # on x, y, cx, cy and on the optical path length
         r = hc.asph_fast(np.float64, rays['x'], rays['y'], rays['z'], rays['cx'], rays['cy'], tabs['c'],
                          tabs['k'], tabs['a'], tabs['t'], tabs['mu'], tabs['sd'], seeds)
         # oracle on the same flattened ray set, one wavelength
@@ -63,7 +63,8 @@ def test_fast_policy_and_adjoint_fp64():
         assert bool(out[4].all())
         for key, j in (('x', 0), ('y', 1), ('cx', 2), ('cy', 3), ('opl', 6)):
             assert np.abs(r[key] - out[j].detach().numpy().ravel()).max() < 1e-10, key
-        loss = sum((torch.tensor(s.reshape(1, 1, -1, 1)) * o).sum() for s, o in zip(seeds, out[:4]))
+        loss = sum((torch.tensor(s.reshape(1, 1, -1, 1)) * o).sum()
+                   for s, o in zip(seeds, (out[0], out[1], out[2], out[3], out[6])))
         g = torch.autograd.grad(loss, [q['x'], q['y'], q['z'], q['cx'], q['cy'], tb['c'], tb['k'], ta,
                                        tb['t'], tb['mu']])
         got = (r['gx'], r['gy'], r['gz'], r['gcx'], r['gcy'], r['gp'][:, 0], r['gp'][:, 1], r['gp'][:, 2:],

@@ -191,3 +191,35 @@ def test_against_an_independent_bracketed_root_finder_fp64():
                 checked += 1
     assert checked == 1000
     assert worst < 1e-9, worst
+
+
+def test_opd_of_a_defocused_perfect_wave_has_its_closed_form():
+    """The stigmatic ellipsoid makes a perfect spherical wave converging on its focus; with the image plane moved
+    delta behind the focus, the OPD against a reference sphere of radius R centred on the chief ray's image point
+    is, exactly,  -n (sqrt(R^2 - delta^2 (1 - cz^2)) - delta cz - (R - delta))  for a ray of direction cosine cz
+    (intersect the ray through the focus with the sphere) -- and 0 for every ray when delta = 0, whatever R."""
+    n_glass, radius = 1.5, 20.0
+    dtype = torch.float64
+    focus = radius * n_glass / (n_glass - 1)
+    c = torch.tensor([1 / radius], dtype=dtype).reshape(1, 1, 1, 1, 1)
+    k = torch.tensor([-1 / n_glass ** 2], dtype=dtype).reshape(1, 1, 1, 1, 1)
+    mu = torch.tensor([1 / n_glass], dtype=dtype).reshape(1, 1, 1, 1, 1)
+    mask = torch.ones(1, 1, 1, 1, 1, dtype=torch.bool)
+    r = torch.linspace(0, 8, 33, dtype=dtype)            # the first ray is the chief ray (on the axis)
+    x = (r * np.cos(0.7)).reshape(1, 1, -1, 1)
+    y = (r * np.sin(0.7)).reshape(1, 1, -1, 1)
+    zero = torch.zeros(1, 1, 1, 1, dtype=dtype)
+    n_image = (1 / mu).prod(-1)
+    for delta in (0.0, 0.05, -0.08):
+        t = torch.tensor([focus + delta], dtype=dtype).reshape(1, 1, 1, 1, 1)
+        out = gen.trace(x, y, zero - 5.0, zero, zero, c, t, mu, mask, k=k)
+        assert bool(out[4].all())
+        for big_r in (30.0, 55.0):
+            got = gen.opd(out[0], out[1], out[2], out[3], out[6], out[4], n_image, big_r)
+            cz = torch.sqrt(1 - out[2] ** 2 - out[3] ** 2)
+            want = -n_glass * (torch.sqrt(big_r ** 2 - delta ** 2 * (1 - cz ** 2)) - delta * cz - (big_r - delta))
+            assert float((got - want).abs().max()) < 1e-10, (delta, big_r)
+            if delta == 0.0:
+                assert float(got.abs().max()) < 1e-10
+            else:
+                assert float(got.abs().max()) > 1e-5          # a real defocus term (~ n delta (1 - cz))

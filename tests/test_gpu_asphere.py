@@ -208,3 +208,79 @@ def test_split_backward_general_surfaces(arith):
                 assert _rel(g[..., i], r[..., i]) <= 2e-4, (name, i, _rel(g[..., i], r[..., i]))
         else:
             assert _rel(g, r) <= 2e-4, (name, _rel(g, r))
+
+
+def _oracle_path_run(p, wrt, dtype, seed_opl, seed_opd, radius):
+    """Loss = sum(seed_opl * opl) + sum(seed_opd * opd) on the extension oracle; returns opl, opd and gradients."""
+    o = {k: (v if k == 'mask' else v.to(dtype)) for k, v in p.items()}
+    for k in wrt:
+        o[k] = o[k].clone().requires_grad_(True)
+    out = _call(gen.trace, o, k=o['k'], a=o['a'], sd=o['sd'])
+    n_image = (1 / o['mu']).prod(-1)
+    opd = gen.opd(out[0], out[1], out[2], out[3], out[6], out[4], n_image, radius)
+    loss = (seed_opl.to(dtype) * out[6]).sum() + (seed_opd.to(dtype) * opd).sum()
+    return out, opd, torch.autograd.grad(loss, [o[k] for k in wrt])
+
+
+@pytest.mark.parametrize('arith', ['guarded', 'exact'])
+def test_optical_path_and_opd_values_and_gradients(arith):
+    """Row A10: the optical path length is differentiable (TlSeeds.gopl) and compute_opd subtracts the reference
+    sphere.  Truth = the extension oracle in fp64 (its OPD function has a closed-form test of its own); the fp32
+    oracle next to it shows the fp32 noise of the same formulas.  Every ray of this problem traces."""
+    p = _problem(n=600, clip=False)
+    wrt = ('z', 'c', 't', 'mu', 'k', 'a')
+    radius = 40.0
+    gen_ = torch.Generator().manual_seed(11)
+    shape = (1, 2, 600, 2)
+    seed_opl = torch.randn(shape, generator=gen_)
+    seed_opd = torch.randn(shape, generator=gen_)
+    out64, opd64, ref = _oracle_path_run(p, wrt, torch.float64, seed_opl, seed_opd, radius)
+    out32, opd32, ref32 = _oracle_path_run(p, wrt, torch.float32, seed_opl, seed_opd, radius)
+    assert bool(out64[4].all())
+
+    q = _to(p, DEV, grad=wrt)
+    out = _call(rt.trace_skew, q, arith=arith, k=q['k'], a=q['a'], sd=q['sd'])
+    assert out[6].requires_grad
+    opd = rt.compute_opd(out[0], out[1], out[2], out[3], out[6], out[4], q['mu'], radius)
+    # values: the path to 1e-6 of itself, the OPD to the same ABSOLUTE size (a difference of two paths)
+    path_scale = float(out64[6].detach().abs().max())
+    err_opl = float((out[6].detach().cpu().double() - out64[6]).abs().max())
+    err_opd = float((opd.detach().cpu().double() - opd64).abs().max())
+    noise_opd = float((opd32.double() - opd64).abs().max())
+    print(f'opl err {err_opl:.3e} of {path_scale:.3f}; opd err {err_opd:.3e} (fp32 oracle: {noise_opd:.3e}), '
+          f'opd range {float(opd64.abs().max()):.3e}')
+    assert err_opl <= 2e-6 * path_scale
+    assert err_opd <= max(2.0 * noise_opd, 2e-6 * path_scale)
+    loss = (seed_opl.to(DEV) * out[6]).sum() + (seed_opd.to(DEV) * opd).sum()
+    got = torch.autograd.grad(loss, [q[k] for k in wrt])
+    for name, g, r, r32 in zip(wrt, got, ref, ref32):
+        assert g.shape == r.shape, name
+        g, r, r32 = g.cpu().numpy(), r.numpy(), r32.numpy()
+        if name == 'a':
+            for i in range(7):
+                ours, theirs = _rel(g[..., i], r[..., i]), _rel(r32[..., i], r[..., i])
+                assert ours <= max(2e-4, 2.0 * theirs), (name, i, ours, theirs)
+        else:
+            ours, theirs = _rel(g, r), _rel(r32, r)
+            assert ours <= max(2e-4, 2.0 * theirs), (name, ours, theirs)
+
+
+def test_no_seed_on_the_path_of_a_spherical_lens():
+    """TlSeeds.gopl without extension tables is refused by the C ABI (a spherical trace has no opl output)."""
+    import ctypes
+    from torchoptics_b200 import _native as nat
+    rec = load_golden('cooke_8x8')
+    i = {k[3:]: torch.from_numpy(rec[k]).to(DEV) for k in rec if k.startswith('in_')}
+    lay = ops._Layout(*[i[k] for k in ('x', 'y', 'z', 'cx', 'cy', 'c', 't', 'mu', 'mask')])
+    pb = lay.problem(True, nat.ARITH_GUARDED)
+    seed = torch.ones(lay.shape, device=DEV)
+    sd = nat.TlSeeds(None, None, None, None, None, None, None, seed.data_ptr())
+    gc = torch.empty((lay.B, lay.S), device=DEV)
+    gt, gz = torch.empty_like(gc), torch.empty((lay.B,), device=DEV)
+    gmu = torch.empty((lay.B, lay.W, lay.S), device=DEV)
+    gr = nat.TlGrads(gc.data_ptr(), gt.data_ptr(), gmu.data_ptr(), gz.data_ptr(), *([None] * 7))
+    lib = nat.load()
+    n = lib.tl_trace_bwd_workspace(ctypes.byref(pb))
+    ws = torch.empty((n // 8,), dtype=torch.float64, device=DEV)
+    rc = lib.tl_trace_bwd(ctypes.byref(pb), ctypes.byref(sd), ctypes.byref(gr), ws.data_ptr(), n, nat.stream_ptr(DEV))
+    assert rc != 0 and b"general-surface lenses only" in lib.tl_last_error()

@@ -12,7 +12,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('TL_LIB_OVERRIDE') or os.path.join(_PKG, 'libtorchoptics_b200.so')   # override: kernel experiments only
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 ARITH_GUARDED = 0
 ARITH_EXACT = 1
 AIM_REAL = 0
@@ -55,7 +55,8 @@ class TlTraceOut(ctypes.Structure):
 
 
 class TlSeeds(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_void_p) for n in ('gx', 'gy', 'gcx', 'gcy', 'gz_relu', 'gtheta', 'gtheta_prime')]
+    _fields_ = [(n, ctypes.c_void_p) for n in ('gx', 'gy', 'gcx', 'gcy', 'gz_relu', 'gtheta', 'gtheta_prime',
+                                               'gopl')]
 
 
 class TlGrads(ctypes.Structure):

@@ -230,8 +230,25 @@ struct AsphGrad {
   T t, mu;
 };
 
+// Seed on the optical path length (row A10): opl = sum_k n_k tau_k + n_S tau_image, n_0 = 1, n_{k+1} = n_k / mu_k.
+// With q = d loss / d opl of this ray, tau_k gets the extra adjoint q n_k -- it joins gh.d, the adjoint the hit
+// point induces on tau_k, in front of the implicit-function transfer, and from there reaches the surface
+// parameters, the thickness in front, the ray's point and direction like any other seed -- and mu_k the extra
+// gradient -q (sum_{j>k} n_j tau_j) / mu_k (every index behind surface k is proportional to 1 / mu_k).
+// `tail` is that sum, carried along the backward walk.
+template <class T>
+struct OplSeed {
+  T q, tail;
+};
+// ... at the image plane: tau_image = -z / cz gets q n_S next to (gx cx + gy cy)
+template <class T>
+TL_HD void sweep_begin_opl(Sweep<T> &s, const Ray<T> &pre, T q, T n_image) {
+  s.gr.z = ffma(-(q * n_image), frcp(pre.cz), s.gr.z);
+}
+
 template <class T, class S>
-TL_HD AsphGrad<T> sweep_asphere(Sweep<T> &s, T hx, T hy, T dx, T dy, const AsphSurfaceT<S> &sf) {
+TL_HD AsphGrad<T> sweep_asphere(Sweep<T> &s, T hx, T hy, T dx, T dy, const AsphSurfaceT<S> &sf,
+                                OplSeed<T> *opl = nullptr, T n_in = T(0), T n_out = T(0)) {
   AsphGrad<T> g;
   const T c(sf.c), mu(sf.mu);
   const T rho = ffma(hy, hy, hx * hx);
@@ -256,6 +273,10 @@ TL_HD AsphGrad<T> sweep_asphere(Sweep<T> &s, T hx, T hy, T dx, T dy, const AsphS
   const T u = dot3(gdo, n) * frcp(ap);
   const T ga = -(mu * gsn) * u;
   g.mu = ffma(-u, ffma(a, ap, mu * ffma(-a, a, T(1))), gdd);
+  if (opl) {                                             // (`dist` = tau of the segment behind this surface)
+    opl->tail = ffma(n_out, dist, opl->tail);
+    g.mu = ffma(-(opl->q * opl->tail), frcp(mu), g.mu);
+  }
   const Vec3<T> gn{ffma(ga, d.x, gsn * gdo.x), ffma(ga, d.y, gsn * gdo.y), ffma(ga, d.z, gsn * gdo.z)};
   const Vec3<T> gdi{ffma(ga, n.x, mu * gdo.x), ffma(ga, n.y, mu * gdo.y), ffma(ga, n.z, mu * gdo.z)};
   // n = m / |m|  ->  gm = (gn - (gn.n) n) / |m|   (m_z is the constant 1)
@@ -266,7 +287,8 @@ TL_HD AsphGrad<T> sweep_asphere(Sweep<T> &s, T hx, T hy, T dx, T dy, const AsphS
   const Vec3<T> gh{ffma(-four_q_spp, hx, ffma(-two_sp, gmx, s.gr.x)),
                    ffma(-four_q_spp, hy, ffma(-two_sp, gmy, s.gr.y)), s.gr.z};
   // transfer onto the surface (implicit function theorem)
-  const T sd = dot3(gh, d) * frcp(dot3(m, d));
+  const T gtau = opl ? ffma(opl->q, n_in, dot3(gh, d)) : dot3(gh, d);
+  const T sd = gtau * frcp(dot3(m, d));
   s.gr = Vec3<T>{ffma(-sd, m.x, gh.x), ffma(-sd, m.y, gh.y), gh.z - sd};
   // parameters: g_theta = sd * ds/dtheta - 2 qq * ds'/dtheta
   const T m2q = T(-2) * qq;

@@ -2077,7 +2077,7 @@ const char *tl_abi_describe(int32_t which) {
     case 0: TL_SIZE(TlStrided); TL_OFF(TlStrided, ptr); TL_OFF(TlStrided, stride); break;
     case 1: TL_SIZE(TlProblem); TL_OFF(TlProblem, x); TL_OFF(TlProblem, y); TL_OFF(TlProblem, z); TL_OFF(TlProblem, cx); TL_OFF(TlProblem, cy); TL_OFF(TlProblem, c); TL_OFF(TlProblem, t); TL_OFF(TlProblem, mu); TL_OFF(TlProblem, live); TL_OFF(TlProblem, B); TL_OFF(TlProblem, F); TL_OFF(TlProblem, P); TL_OFF(TlProblem, W); TL_OFF(TlProblem, S); TL_OFF(TlProblem, allow_backward_rays); TL_OFF(TlProblem, arith); TL_OFF(TlProblem, p_begin); TL_OFF(TlProblem, p_end); TL_OFF(TlProblem, xy_scale); TL_OFF(TlProblem, k); TL_OFF(TlProblem, a); TL_OFF(TlProblem, sd); TL_OFF(TlProblem, aim); TL_OFF(TlProblem, vig); break;
     case 2: TL_SIZE(TlTraceOut); TL_OFF(TlTraceOut, x); TL_OFF(TlTraceOut, y); TL_OFF(TlTraceOut, cx); TL_OFF(TlTraceOut, cy); TL_OFF(TlTraceOut, ok); TL_OFF(TlTraceOut, backward); TL_OFF(TlTraceOut, opl); TL_OFF(TlTraceOut, z_relu); TL_OFF(TlTraceOut, theta); TL_OFF(TlTraceOut, theta_prime); break;
-    case 3: TL_SIZE(TlSeeds); TL_OFF(TlSeeds, gx); TL_OFF(TlSeeds, gy); TL_OFF(TlSeeds, gcx); TL_OFF(TlSeeds, gcy); TL_OFF(TlSeeds, gz_relu); TL_OFF(TlSeeds, gtheta); TL_OFF(TlSeeds, gtheta_prime); break;
+    case 3: TL_SIZE(TlSeeds); TL_OFF(TlSeeds, gx); TL_OFF(TlSeeds, gy); TL_OFF(TlSeeds, gcx); TL_OFF(TlSeeds, gcy); TL_OFF(TlSeeds, gz_relu); TL_OFF(TlSeeds, gtheta); TL_OFF(TlSeeds, gtheta_prime); TL_OFF(TlSeeds, gopl); break;
     case 4: TL_SIZE(TlGrads); TL_OFF(TlGrads, gc); TL_OFF(TlGrads, gt); TL_OFF(TlGrads, gmu); TL_OFF(TlGrads, gz_sum); TL_OFF(TlGrads, gx); TL_OFF(TlGrads, gy); TL_OFF(TlGrads, gz); TL_OFF(TlGrads, gcx); TL_OFF(TlGrads, gcy); TL_OFF(TlGrads, gk); TL_OFF(TlGrads, ga); break;
     case 5: TL_SIZE(TlSpotOut); TL_OFF(TlSpotOut, rms); TL_OFF(TlSpotOut, rms_field); TL_OFF(TlSpotOut, gc); TL_OFF(TlSpotOut, gt); TL_OFF(TlSpotOut, gmu); TL_OFF(TlSpotOut, gz); TL_OFF(TlSpotOut, gk); TL_OFF(TlSpotOut, ga); break;
     case 6: TL_SIZE(TlPenaltyOut); TL_OFF(TlPenaltyOut, penalty); TL_OFF(TlPenaltyOut, gc); TL_OFF(TlPenaltyOut, gt); TL_OFF(TlPenaltyOut, gmu); TL_OFF(TlPenaltyOut, gz); break;
@@ -2218,6 +2218,8 @@ int tl_trace_bwd(const TlProblem *pb_, const TlSeeds *seeds, const TlGrads *grad
   TlProblem pb = *pb_;
   pb.p_begin = 0;
   pb.p_end = pb.P;
+  if (seeds->gopl)
+    return fail(TL_ERR_INVALID, "the optical path length is an output of general-surface lenses only (no seed on it without k / a / sd)%s");
   const int pen = (seeds->gz_relu || seeds->gtheta || seeds->gtheta_prime) ? PEN_SEEDED : PEN_NONE;
   AdjPlan pl;
   rc = plan_adj(pb, MODE_BWD, pl, pen);

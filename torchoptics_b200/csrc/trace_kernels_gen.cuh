@@ -422,11 +422,22 @@ k_trace_gen(TlProblem pb, AdjArgs args) {
           wgt = alive;                        // weights: the seeds already carry everything
         }
         Sweep<V> sw = sweep_begin(tr.pre, tr.x, tr.y, sx, sy, scx, scy);
+        // seed on the optical path length (row A10; trace_core_asph.cuh: OplSeed)
+        OplSeed<V> path{V(0.f), V(0.f)};
+        OplSeed<V> *path_seed = nullptr;
+        if (kSeeded && args.seeds.gopl) {
+#pragma unroll
+          for (int l = 0; l < N; ++l)
+            if (live[l]) lane_set(path.q, l, args.seeds.gopl[o[l]]);
+          sweep_begin_opl(sw, tr.pre, path.q, V(tab.index[S]));
+          path_seed = &path;
+        }
 #pragma unroll 1
         for (int k = S - 1; k >= 0; --k) {
           const V *slot = state + (size_t)k * 4 * stride;
           const AsphGrad<V> g = sweep_asphere(sw, slot[0], slot[stride], slot[2 * stride],
-                                              slot[3 * stride], gen_surface(tab, k));
+                                              slot[3 * stride], gen_surface(tab, k), path_seed,
+                                              V(tab.index[k]), V(tab.index[k + 1]));
           float v[32];
 #pragma unroll
           for (int q = 0; q < kAsphParams; ++q) {

@@ -137,8 +137,8 @@ class _TraceSkew(torch.autograd.Function):
 
     @staticmethod
     def _forward_general(ctx, lay, allow_backward_rays, arith):
-        """Forward of a lens with extension surfaces: also returns the optical path length
-        (itself not differentiable; x, y, cx, cy are)."""
+        """Forward of a lens with extension surfaces: also returns the optical path length,
+        differentiable like x, y, cx, cy (TlSeeds.gopl)."""
         lib = nat.load()
         with torch.cuda.device(lay.device):
             outs = [torch.empty(lay.shape, dtype=torch.float32, device=lay.device) for _ in range(4)]
@@ -151,7 +151,7 @@ class _TraceSkew(torch.autograd.Function):
             nat.check(lib.tl_trace_fwd(ctypes.byref(pb), ctypes.byref(out), nat.stream_ptr(lay.device)),
                       'tl_trace_fwd')
         ctx.general = True
-        ctx.mark_non_differentiable(ok, backward, opl)
+        ctx.mark_non_differentiable(ok, backward)
         return (*outs, ok, backward, opl)
 
     @staticmethod
@@ -159,7 +159,9 @@ class _TraceSkew(torch.autograd.Function):
         saved = ctx.saved_tensors
         stack_grads = extra_grads if ctx.aggregate else (None, None, None)
         k = a = sd = None
+        g_opl = None
         if getattr(ctx, 'general', False):
+            g_opl = extra_grads[0] if extra_grads else None
             extra = list(saved[9:])
             has_k, has_a, has_sd = ctx.ext
             k = extra.pop(0) if has_k else None
@@ -176,7 +178,8 @@ class _TraceSkew(torch.autograd.Function):
         need = ctx.needs_input_grad
         with torch.cuda.device(dev):
             seeds = [None if g is None else g.to(torch.float32).expand(lay.shape).contiguous()
-                     for g in (gx, gy, gcx, gcy)]
+                     for g in (gx, gy, gcx, gcy, g_opl)]
+            seed_opl = seeds.pop()
             gc = torch.empty((lay.B, lay.S), dtype=torch.float32, device=dev)
             gt = torch.empty_like(gc)
             gmu = torch.empty((lay.B, lay.W, lay.S), dtype=torch.float32, device=dev)
@@ -189,7 +192,7 @@ class _TraceSkew(torch.autograd.Function):
             pb = lay.problem(allow_backward_rays, arith)
             stack_seeds = [None if g is None else
                            g.to(torch.float32).expand((lay.S,) + lay.shape).contiguous() for g in stack_grads]
-            sd = nat.TlSeeds(*[_ptr(s) for s in seeds], *[_ptr(s) for s in stack_seeds])
+            sd = nat.TlSeeds(*[_ptr(s) for s in seeds], *[_ptr(s) for s in stack_seeds], _ptr(seed_opl))
             gk = ga = None
             if lay.general:
                 gk = torch.empty_like(gc)
@@ -847,7 +850,7 @@ class _LensTrace(torch.autograd.Function):
             grads = torch.zeros((4, B, L), dtype=torch.float32, device=dev)      # gc, gt, gnd, gv
             gmu = torch.empty((B, W, L), dtype=torch.float32, device=dev)
             gz = torch.empty((B,), dtype=torch.float32, device=dev)
-            sd = nat.TlSeeds(*[_ptr(s) for s in seeds], None, None, None)
+            sd = nat.TlSeeds(*[_ptr(s) for s in seeds], None, None, None, None)
             gr = nat.TlGrads(grads[0].data_ptr(), grads[1].data_ptr(), gmu.data_ptr(), gz.data_ptr(),
                              None, None, None, None, None, None, None)
             ws_bytes = lib.tl_trace_bwd_workspace(ctypes.byref(st.pb))

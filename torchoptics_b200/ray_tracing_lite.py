@@ -293,7 +293,8 @@ def trace_skew(x, y, z, cx, cy, c, t, mu, mask, aggregate=False, allow_backward_
     [B,1,1,1,S,7] even-asphere coefficients a4..a16, ``sd`` [B,1,1,1,S] clear
     semi-diameters.  With any of them the surfaces are intersected by Newton
     iteration, rays outside ``sd`` fail, and a 7th output, the optical path length
-    [B,F,P,W] (not differentiable), is returned; gradients also flow to ``k`` and ``a``.
+    [B,F,P,W], is returned -- differentiable like the other four (see :func:`compute_opd`);
+    gradients also flow to ``k`` and ``a``.
 
     ``aggregate=True`` (rtl:641-657, spherical lenses): also returns ``stacks``, the dict of
     per-surface penalty terms ``z_RELU``, ``theta_norm``, ``theta_prime_norm`` (S-long lists of
@@ -318,6 +319,30 @@ def compute_rms2d(x, y, ray_ok):
     compute_rms2d -> backward`` then costs one forward trace plus one fused pass, with no per-ray
     tensor read back or written in backward."""
     return ops.rms_of_trace(y, ray_ok)[0]
+
+
+def compute_opd(x, y, cx, cy, opl, ray_ok, mu, radius, chief=0):
+    """Optical path difference against a reference sphere (extension row A10; the reference has no OPD).
+
+    ``x, y, cx, cy, opl, ray_ok`` are the outputs of :func:`trace_skew` with extension tables ([B,F,P,W]);
+    ``mu`` the index ratios it was given ([B,1,1,W,S]: the image-space index is the product of ``1 / mu``);
+    ``radius`` (> 0, broadcastable to [B,F,1,W]) the radius of the reference sphere, which is centred on the
+    image point of each field's chief ray -- pupil index ``chief`` -- and lies in front of the image plane.
+    A ray meets the image plane at P with direction d and the sphere at P + s d, s < 0;
+    ``opd = (opl + n s) - (opl_chief - n radius)``.  Rays that are not ok, and fields whose chief ray is not
+    ok, get 0.  Differentiable through all five float inputs, i.e. back to c, t, mu, k, a of the trace: a
+    handful of elementwise CUDA ops on top of the trace kernels (the optical path itself, and its adjoint,
+    are computed inside them: ``TlTraceOut.opl`` / ``TlSeeds.gopl``).  fp32: the optical path is a sum of
+    ~10^1 mm carried to ~1e-7 of itself, so an OPD is good to ~1e-5 mm absolute, not to 1e-5 of itself."""
+    nat.require_cuda(opl, 'opl')
+    n_image = (1.0 / mu).prod(-1)
+    pick = slice(chief, chief + 1)
+    dx, dy = x - x[:, :, pick], y - y[:, :, pick]
+    along = dx * cx + dy * cy
+    reach = torch.sqrt(along * along - (dx * dx + dy * dy) + radius * radius)
+    out = (opl - opl[:, :, pick]) + n_image * ((radius - along) - reach)
+    good = ray_ok & ray_ok[:, :, pick]
+    return torch.where(good, out, torch.zeros_like(out))
 
 
 def compute_psf(x, y, n_bins=(21, 21), increment=None, y_target=None):
