@@ -116,3 +116,47 @@ def test_world2_exchange_matches_nccl_and_single_rank(tmp_path):
         scale = np.abs(rec['alone']).max()
         assert np.abs(rec['peer'] - rec['alone']).max() <= 1e-4 * scale
     np.testing.assert_array_equal(recs[0]['peer'], recs[1]['peer'])    # same bits on every rank
+
+
+def _late_peer_worker(rank, world, port, out_dir):
+    """Rank 1 skips one exchange: rank 0's wait runs into the spin limit (~4 s) and must say so LOUDLY."""
+    import torch.distributed as dist
+    from torchoptics_b200.peer import PeerExchange
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = f'cuda:{rank}'
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device(dev))
+    ex = PeerExchange(capacity=1024)
+    data = torch.full((700,), float(rank + 1), dtype=torch.float64, device=dev)
+    first = ex.all_reduce(data).clone()                  # a healthy step: 1 + 2 on both ranks
+    torch.cuda.synchronize()
+    dist.barrier()
+    rec = {'first': first.cpu().numpy()}
+    if rank == 0:
+        lonely = ex.all_reduce(data).clone()             # the peer never comes: spin limit, NaN, status 1
+        torch.cuda.synchronize()
+        rec['lonely'] = lonely.cpu().numpy()
+        rec['status_after'] = ex.status()[0]
+    dist.barrier()                                       # (rank 1 waits here while rank 0 spins)
+    later = ex.all_reduce(data).clone()                  # both ranks call again: rank 0 stays poisoned
+    torch.cuda.synchronize()
+    rec['later'] = later.cpu().numpy()
+    rec['status_end'] = ex.status()[0]
+    np.savez(os.path.join(out_dir, f'late{rank}.npz'), **rec)
+    dist.barrier()
+    ex.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+def test_world2_late_peer_poisons_the_result_and_stays_poisoned(tmp_path):
+    """a wait that times out must not return a sum of stale slots.  The rank that
+    waited in vain gets NaN in every element of that step AND of every later step, and status() == 1."""
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_late_peer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    r0, r1 = (np.load(tmp_path / f'late{r}.npz') for r in range(world))
+    np.testing.assert_array_equal(r0['first'], np.full(700, 3.0))
+    np.testing.assert_array_equal(r1['first'], np.full(700, 3.0))
+    assert np.isnan(r0['lonely']).all() and int(r0['status_after']) == 1
+    assert np.isnan(r0['later']).all() and int(r0['status_end']) == 1      # sticky
