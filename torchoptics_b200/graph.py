@@ -15,6 +15,7 @@ time: CUDA streams and graphs instead of a tracing compiler.  Shapes are static
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from .lens_modeling import Lens, Specs
@@ -67,6 +68,7 @@ class GraphedSpotStep:
                          for i, k in enumerate(self.PARAMS)}
         self.host_rms = self._host_out_buf[n_par * per:n_par * per + n_lens]
         self.host_penalty = self._host_out_buf[n_par * per + n_lens:]
+        self._host_rms_np = self.host_rms.numpy()            # (shares the pinned memory)
         self._out_slices = (per, n_par * per, n_lens)
         self.h2d_bytes = self._host_in_buf.numel() * 4
         self.d2h_bytes = self._host_out_buf.numel() * 4
@@ -110,9 +112,11 @@ class GraphedSpotStep:
         self._host_out_buf.copy_(self._dev_out_buf, non_blocking=True)
 
     def __call__(self, c=None, t=None, nd=None, v=None):
-        for k, val in (('c', c), ('t', t), ('nd', nd), ('v', v)):
-            if val is not None:
-                self.host_in[k].copy_(val)
+        # (the step is synchronous and ~0.24 ms long: the host-side staging is not hidden behind anything, and four
+        # separate copy_ calls are 12 us of dispatch -- one fused call is 7)
+        given = [(self.host_in[k], val) for k, val in (('c', c), ('t', t), ('nd', nd), ('v', v)) if val is not None]
+        if given:
+            torch._foreach_copy_([d for d, _ in given], [s for _, s in given])
         self.graph.replay()
         torch.cuda.current_stream(self.device).synchronize()
         self.check_exchange()
@@ -122,7 +126,8 @@ class GraphedSpotStep:
         """A peer that did not show up within the exchange kernel's spin limit poisons the sums with
         NaN (csrc/peer_exchange.cuh); turn that into an exception instead of a silently wrong step."""
         from .peer import PeerExchange
-        if isinstance(self.group, PeerExchange) and bool(torch.isnan(self.host_rms).any()):
+        # (numpy on the pinned buffer: ~1 us where torch.isnan(...).any() is ~6 us of dispatch, every step)
+        if isinstance(self.group, PeerExchange) and bool(np.isnan(self._host_rms_np).any()):
             status, epoch = self.group.status()
             if status != 0:
                 from ._native import NativeLibraryError
