@@ -203,8 +203,40 @@ def launch_count():
     return int(load().tl_launch_count())
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def stream_ptr(device):
+    """The current stream of ``device`` as a ``cudaStream_t``.  (``torch.cuda.current_stream(device)`` builds a
+    Stream object behind a device-index lookup: ~4 us per call, four calls in an eager step of ~0.5 ms.)"""
+    if _raw_stream is not None:
+        idx = device.index if isinstance(device, torch.device) else torch.device(device).index
+        return ctypes.c_void_p(_raw_stream(torch.cuda.current_device() if idx is None else idx))
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class on_device:
+    """``with torch.cuda.device(dev)`` that costs nothing when ``dev`` is already the current device."""
+    __slots__ = ('idx', 'prev')
+
+    def __init__(self, device):
+        idx = device.index if isinstance(device, torch.device) else torch.device(device).index
+        self.idx = idx
+        self.prev = None
+
+    def __enter__(self):
+        if self.idx is not None:
+            cur = torch.cuda.current_device()
+            if cur != self.idx:
+                self.prev = cur
+                torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+            self.prev = None
+        return False
 
 
 def require_cuda(t, name):

@@ -117,7 +117,7 @@ class _TraceSkew(torch.autograd.Function):
         if lay.S > nat.MAX_SURFACES_FWD:
             raise ValueError(f'at most {nat.MAX_SURFACES_FWD} surfaces are supported')
         lib = nat.load()
-        with torch.cuda.device(lay.device):
+        with nat.on_device(lay.device):
             outs = [torch.empty(lay.shape, dtype=torch.float32, device=lay.device) for _ in range(4)]
             ok = torch.empty(lay.shape, dtype=torch.bool, device=lay.device)
             backward = torch.empty(lay.shape, dtype=torch.bool, device=lay.device)
@@ -140,7 +140,7 @@ class _TraceSkew(torch.autograd.Function):
         """Forward of a lens with extension surfaces: also returns the optical path length,
         differentiable like x, y, cx, cy (TlSeeds.gopl)."""
         lib = nat.load()
-        with torch.cuda.device(lay.device):
+        with nat.on_device(lay.device):
             outs = [torch.empty(lay.shape, dtype=torch.float32, device=lay.device) for _ in range(4)]
             ok = torch.empty(lay.shape, dtype=torch.bool, device=lay.device)
             backward = torch.empty(lay.shape, dtype=torch.bool, device=lay.device)
@@ -176,7 +176,7 @@ class _TraceSkew(torch.autograd.Function):
         lib = nat.load()
         dev = lay.device
         need = ctx.needs_input_grad
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             seeds = [None if g is None else g.to(torch.float32).expand(lay.shape).contiguous()
                      for g in (gx, gy, gcx, gcy, g_opl)]
             seed_opl = seeds.pop()
@@ -271,7 +271,7 @@ class _RmsFromRays(torch.autograd.Function):
         B, F, P, W = y.shape
         lib = nat.load()
         dev = y.device
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             yc = y.detach().contiguous()
             okc = torch.broadcast_to(ray_ok, y.shape).to(torch.uint8).contiguous()
             rms = torch.empty((B,), dtype=torch.float32, device=dev)
@@ -292,7 +292,7 @@ class _RmsFromRays(torch.autograd.Function):
         B, F, P, W = yc.shape
         lib = nat.load()
         dev = yc.device
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             g = grad_rms.to(torch.float32).contiguous()
             gy = torch.empty_like(yc)
             nat.check(lib.tl_rms_bwd(yc.data_ptr(), okc.data_ptr(), stats.data_ptr(), g.data_ptr(),
@@ -388,7 +388,7 @@ def spot_moments(x, y, z, cx, cy, c, t, mu, mask, allow_backward_rays=True, arit
     """Raw additive sums of one pupil slice (no autograd): (moments [B,F,W,n], ref_y [B,F])."""
     lay = _Layout(x, y, z, cx, cy, c, t, mu, mask, k, a, sd)
     p_begin, p_end = pupil_slice(lay.P, *shard)
-    with torch.cuda.device(lay.device):
+    with nat.on_device(lay.device):
         return _accumulate(lay, allow_backward_rays, arith, want_grad, p_begin, p_end)
 
 
@@ -406,7 +406,7 @@ def spot_kernel_runner(x, y, z, cx, cy, c, t, mu, mask, shard=(0, 1)):
     lay = _Layout(x, y, z, cx, cy, c, t, mu, mask)
     p_begin, p_end = pupil_slice(lay.P, *shard)
     lib = nat.load()
-    with torch.cuda.device(lay.device):
+    with nat.on_device(lay.device):
         _, ref_y = _accumulate(lay, True, nat.ARITH_GUARDED, True, p_begin, p_end)
         pb = lay.problem(True, nat.ARITH_GUARDED, p_begin, p_end)
         ws_bytes = lib.tl_spot_workspace(ctypes.byref(pb), 1)
@@ -446,7 +446,7 @@ class _SpotRms(torch.autograd.Function):
         p_begin, p_end = pupil_slice(lay.P, rank, world)
         if p_end <= p_begin:
             raise ValueError(f'pupil axis ({lay.P}) is too short to shard over {world} ranks')
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             moments, ref_y = _accumulate(lay, allow_backward_rays, arith, want_grad, p_begin, p_end)
             stream = nat.stream_ptr(dev)
             if world > 1:
@@ -538,7 +538,7 @@ class _PenaltySum(torch.autograd.Function):
         p_begin, p_end = pupil_slice(lay.P, rank, world)
         if p_end <= p_begin:
             raise ValueError(f'pupil axis ({lay.P}) is too short to shard over {world} ranks')
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             n_acc = lib.tl_penalty_moment_count(lay.S)
             moments = torch.empty((lay.B, lay.F, lay.W, n_acc), dtype=torch.float64, device=dev)
             pb = lay.problem(allow_backward_rays, arith, p_begin, p_end)
@@ -634,7 +634,7 @@ def aim_table(c, t, nd, v, hfov, epd, tables, allow_backward_rays=True, vig=None
         raise ValueError(f'lens tensors must be [B={B}, L={L}], got {tuple(c.shape)}')
     if L > 64:
         raise ValueError('too many surfaces for the staging kernels')
-    with torch.cuda.device(dev), torch.no_grad():
+    with nat.on_device(dev), torch.no_grad():
         cc, tt, ndd, vv = (a.detach().contiguous() for a in (c, t, nd, v))
         hf, ep = hfov.detach().contiguous(), epd.detach().contiguous()
         mu = torch.empty((B, W, L), dtype=torch.float32, device=dev)
@@ -730,7 +730,7 @@ def stage_lens(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays
                aimed=False, vig=None, aim_mode=nat.AIM_REAL):
     """The staged ray set of a lens batch (one ``tl_stage_ref`` launch), for callers that run several
     fused passes over it (``staged=`` of lens_spot_rms / lens_penalty)."""
-    with torch.cuda.device(c.device):
+    with nat.on_device(c.device):
         return _Staged(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, aimed,
                        max_surfaces=nat.MAX_SURFACES_SPOT, want_ref=True, vig=vig, aim_mode=aim_mode)
 
@@ -758,7 +758,7 @@ def _lens_spot_core(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward
 
     nat.require_cuda(c, 'c')
     dev = c.device
-    with torch.cuda.device(dev):
+    with nat.on_device(dev):
         if staged is not None:      # the ray set a staged trace_rays of the same lens already built
             st = staged
             if want_grad and st.L > nat.MAX_SURFACES_SPOT:
@@ -821,7 +821,7 @@ class _LensTrace(torch.autograd.Function):
         lib = nat.load()
         ctx.set_materialize_grads(False)
         dev = c.device
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             st = _Staged(c, t, nd, v, hfov, epd, x_rel, y_rel, tables, allow_backward_rays, arith, aimed,
                          max_surfaces=nat.MAX_SURFACES_FWD, vig=vig, aim_mode=aim_mode)
             outs = torch.empty((4,) + st.shape, dtype=torch.float32, device=dev)
@@ -844,7 +844,7 @@ class _LensTrace(torch.autograd.Function):
         lib = nat.load()
         dev = st.device
         B, L, W = st.B, st.L, st.W
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             seeds = [None if g is None else g.to(torch.float32).expand(st.shape).contiguous()
                      for g in (gx, gy, gcx, gcy)]
             grads = torch.zeros((4, B, L), dtype=torch.float32, device=dev)      # gc, gt, gnd, gv
@@ -889,7 +889,7 @@ class _LensPenalty(torch.autograd.Function):
         dev = c.device
         rank, world = shard
         p_begin, p_end = pupil_slice(x_rel.shape[2], rank, world)
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             if staged is not None:
                 st = staged
                 st.pb.p_begin, st.pb.p_end = int(p_begin), int(p_end)
@@ -1017,7 +1017,7 @@ def psf_bin(x, y, y_target, x_incr, y_incr, x_size, y_size, n_bins):
     n_x, n_y = int(n_bins[0]), int(n_bins[1])
     lib = nat.load()
     dev = x.device
-    with torch.cuda.device(dev):
+    with nat.on_device(dev):
         keep = [v.detach().contiguous() for v in (x, y, y_target, x_incr, y_incr, x_size, y_size)]
         for v in keep[2:]:
             if v.numel() != G:
@@ -1053,7 +1053,7 @@ class _Paraxial(torch.autograd.Function):
             raise ValueError(f'at most {nat.PARAXIAL_MAX_SLOTS} slots per lens')
         lib = nat.load()
         dev = c.device
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             keep = [v.detach().contiguous() for v in (c, t, n)] + [live, glass]
             p = nat.TlParaxial(*[v.data_ptr() for v in keep], B, L, mode)
             out = torch.empty((B, 2), dtype=torch.float32, device=dev)
@@ -1068,7 +1068,7 @@ class _Paraxial(torch.autograd.Function):
         B, L = c.shape
         lib = nat.load()
         dev = c.device
-        with torch.cuda.device(dev):
+        with nat.on_device(dev):
             gout = gout.detach().to(torch.float32).contiguous()
             gc, gt, gn = (torch.empty((B, L), dtype=torch.float32, device=dev) for _ in range(3))
             p = nat.TlParaxial(c.data_ptr(), t.data_ptr(), n.data_ptr(), live.data_ptr(), glass.data_ptr(), B, L, ctx.mode)
