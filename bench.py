@@ -310,6 +310,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def host_lead():
+        """A ~3 ms spin kernel in front of a timed loop (outside every timed interval: the events bracket flush ->
+        step).  The loops below enqueue far faster than the device executes, but they start level with it right after
+        a synchronize: a host hiccup in the first iterations (GC, the clock sampler's child starting) would leave the
+        device idle INSIDE an event pair and be billed to the kernel -- seen once as a 0.239 ms mean over 50 launches
+        of a 0.204 ms kernel.  With the host 3 ms ahead from the first iteration, event pairs measure device time only."""
+        torch.cuda._sleep(int(6.0e6))
+
     note('warm-up')
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -320,6 +328,7 @@ def main():
         barrier()
         # the host barrier leaves the ranks tens of microseconds apart, and the first exchange would bill
         # that skew to the first timed steps: a few UNTIMED steps let the exchange itself align the ranks
+        host_lead()                              # (in front of the aligning steps: the ranks' spins end apart)
         for _ in range(3 if world > 1 else 0):
             flush.zero_()
             run_step()
@@ -373,6 +382,7 @@ def main():
     torch.cuda.synchronize()
     k_starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     k_stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    host_lead()
     for i in range(args.steps):
         flush.zero_()
         k_starts[i].record()
@@ -402,6 +412,7 @@ def main():
             print(f'[bench] forward graph capture failed: {exc}', file=sys.stderr)
         a = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
         b = [torch.cuda.Event(enable_timing=True) for _ in range(reps)]
+        host_lead()
         for i in range(reps):
             flush.zero_()
             a[i].record()
