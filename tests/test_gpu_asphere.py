@@ -284,3 +284,38 @@ def test_no_seed_on_the_path_of_a_spherical_lens():
     ws = torch.empty((n // 8,), dtype=torch.float64, device=DEV)
     rc = lib.tl_trace_bwd(ctypes.byref(pb), ctypes.byref(sd), ctypes.byref(gr), ws.data_ptr(), n, nat.stream_ptr(DEV))
     assert rc != 0 and b"general-surface lenses only" in lib.tl_last_error()
+
+
+def test_newton_early_exit_matches_the_four_fixed_steps(f_number=5.0):
+    """The fast policy leaves the Newton loop once a step is <= 1e-3 |tau| (csrc/trace_core_asph.cuh:
+    newton_settled); the exact policy and the oracle run the four fixed steps.  On the config-3 lens -- eight aspheric surfaces (the last takes a first
+    step of 0.18 |tau|) and four spherical ones -- the yardstick is the fp64 oracle: masks identical, and
+    points, cosines and optical path of the early-exit policy within the north-star 1e-5 of their scale
+    AND no further from fp64 than 1.5 x the four-step fp32 policy's own distance (this lens carries
+    ~7e-6 of fp32 noise in y whichever policy runs, so the two fp32 policies differ from EACH OTHER by
+    about the sum of both).  All three distances are printed.  (The f/4 variant, whose masks both policies
+    reproduce in test_config3_lens_at_3m_rays_against_the_oracle_on_device, is no yardstick for VALUES: its
+    rays within ~1e-3 of a miss are ill-conditioned in fp32 whatever the iteration count)"""
+    from torchoptics_b200 import prescriptions
+    specs, lens = prescriptions.asphere_12(DEV, f_number=f_number)
+    tracer = rt.RayTracer(mode='circular', n_rays=(96, 96), rel_fields=tuple(np.linspace(0, 1, 16).tolist()),
+                          wavelengths=('C', 'd', 'F'), default_device=DEV)
+    args = [a_.detach() for a_ in tracer._ray_set(specs, lens)]
+    ext = {k: v.detach() for k, v in tracer._extension_tables(lens).items() if v is not None}
+    exact = rt.trace_skew(*args, arith='exact', **ext)
+    fast = rt.trace_skew(*args, arith='guarded', **ext)
+    dbl = [a_.double() if a_.is_floating_point() else a_ for a_ in args]
+    ref64 = gen.trace(*dbl, **{k: (v.double() if v.is_floating_point() else v) for k, v in ext.items()})
+    assert torch.equal(fast[4], exact[4]) and torch.equal(fast[5], exact[5])
+    ok = exact[4] & ref64[4]
+    assert float(ok.float().mean()) >= 0.99
+    xy_scale = max(float(ref64[0].abs().max()), float(ref64[1].abs().max()))
+    for j, name in ((0, 'x'), (1, 'y'), (2, 'cx'), (3, 'cy'), (6, 'opl')):
+        scale = 1.0 if name in ('cx', 'cy') else (xy_scale if j < 2 else float(ref64[j].abs().max()))
+        d_fast_exact = float((fast[j] - exact[j])[ok].abs().max())
+        err_fast = float((fast[j].double() - ref64[j])[ok].abs().max())
+        err_exact = float((exact[j].double() - ref64[j])[ok].abs().max())
+        print(f'f/{f_number} {name}: fast-exact {d_fast_exact / scale:.2e}, fast-fp64 {err_fast / scale:.2e}, '
+              f'exact-fp64 {err_exact / scale:.2e} (of scale {scale:.3g})')
+        assert err_fast <= 1e-5 * scale, name
+        assert err_fast <= max(1.5 * err_exact, 1e-6 * scale), name

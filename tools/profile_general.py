@@ -29,7 +29,12 @@ for want_grad in (True, False):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    flops = 566 if want_grad else 316      # n_newton = 4: 61 + 55 n + 35 forward, + 105 + 2 x 55 + 35 adjoint
+    # Two conventions.  `flops`: the oracle's algorithm, 4 fixed Newton steps: 61 + 55 n + 35
+    # forward, + 105 + 2 x 55 + 35 adjoint.  `done`: what the fast policy executes on THIS lens since the early exit
+    # (two steps per event on average, csrc/trace_core_asph.cuh: newton_settled): 348 - 2 x 57 forward, + 271 adjoint.
+    flops = 566 if want_grad else 316
+    done = 505 if want_grad else 234
     print(f'general spot pass want_grad={want_grad}: {ms:.4f} ms -> {events / ms / 1e6:.1f} G events/s '
-          f'({events * flops / ms / 1e9 / 74.45 * 100:.1f}% of 74.45 TFLOP/s at {flops} flop/event), '
+          f'({events * flops / ms / 1e9 / 74.45 * 100:.1f}% of 74.45 TFLOP/s credited at the oracle\'s {flops} flop/event, '
+          f'{events * done / ms / 1e9 / 74.45 * 100:.1f}% at the ~{done} executed), '
           f'ok fraction {float(m[..., -1].sum()) / (16 * 3 * side * side):.4f}')
