@@ -2032,7 +2032,7 @@ int plan_gen(const TlProblem &pb, int want_grad, GenPlan &pl, bool seeded = fals
               : want_grad ? (AdjKernelPtr)k_trace_gen<MODE_SPOT_GRAD, f2>
                           : (AdjKernelPtr)k_trace_gen<MODE_SPOT_EVAL, f4>;
   pl.n_acc = n_acc_gen(pb.S, want_grad);
-  const size_t table = ((14 * (size_t)pb.S + 2 + 3) & ~(size_t)3) * sizeof(float);
+  const size_t table = ((gen_table_floats(pb.S) + 3) & ~(size_t)3) * sizeof(float);
   const size_t rows = want_grad ? (size_t)(kTraceThreads / 32) * pb.S * kGenRow * sizeof(float) : 0;
   const size_t state = want_grad ? (size_t)4 * pb.S * kTraceThreads * pl.lanes * sizeof(float) : 0;
   pl.smem = table + rows + state + 16;
@@ -2132,7 +2132,7 @@ int tl_trace_fwd(const TlProblem *pb, const TlTraceOut *out, void *stream_) {
   }
   const FwdPlan pl = make_fwd_plan(info.sms, pb->B * pb->F * pb->W, pb->P, 2 * kFwdThreads, 4);
   if (is_general(*pb)) {
-    const size_t smem = (14 * (size_t)pb->S + 2) * sizeof(float);
+    const size_t smem = gen_table_floats(pb->S) * sizeof(float);
     k_trace_fwd_gen<<<pl.n_blocks, kFwdThreads, smem, (cudaStream_t)stream_>>>(*pb, *out, pl.nchunks,
                                                                                pl.chunk_len);
     g_launches++;

@@ -15,63 +15,94 @@ constexpr int kGenPar = kAsphParams + 2;        // c, k, a4..a16, t, mu  = 11 pe
 constexpr int kGenSlots = 2 * kGenPar;           // weighted + plain      = 22 per surface
 constexpr int kGenRow = 32;                      // padded row of the per-warp accumulators
 
-// Surface table of one (lens, wavelength) in shared memory, general surfaces.
+// Surface table of one (lens, wavelength) in shared memory, general surfaces: ONE 64-byte record per
+// surface, so that a step of either loop reads it with four 128-bit broadcast loads from one address
+// (the first version kept eight separate arrays: 15 scalar loads and their address arithmetic per
+// surface and pass, a tenth of the fused pass's instructions).
+struct alignas(16) GenSurf {
+  float c, k, t, mu;
+  float sd2, index, index_next;     // sd2 = (clear semi-diameter)^2; refractive index in front of / behind the surface
+  int live_bits;                    // bit 0: structure mask of this surface, bit 1: ... of the surface in front
+  float a[kAsphCoefs];
+  float pad;
+};
+static_assert(sizeof(GenSurf) == 64, "GenSurf is read as four float4");
+
 struct GenTable {
-  float *c, *t, *mu, *k, *sd2, *index, *a;   // index[k] = refractive index in front of surface k
-  int *live;
-  float length;
+  const GenSurf *s;
+  float length;                     // sum |t|
+  float index_image, t_last;        // index behind the last surface; its thickness
+  int live_last;
 };
 
-__device__ __forceinline__ size_t gen_table_floats(int S) { return 14 * (size_t)S + 2; }
+__host__ __device__ __forceinline__ size_t gen_table_floats(int S) { return 16 * (size_t)S; }
 
 __device__ __forceinline__ GenTable load_gen_table(float *base, const TlProblem &pb, int b, int w) {
   GenTable tab;
   const int S = pb.S;
-  tab.c = base;
-  tab.t = base + S;
-  tab.mu = base + 2 * S;
-  tab.k = base + 3 * S;
-  tab.sd2 = base + 4 * S;
-  tab.index = base + 5 * S;                    // S + 1 entries
-  tab.live = reinterpret_cast<int *>(base + 6 * S + 1);
-  tab.a = base + 7 * S + 1;                    // 7 S entries
+  GenSurf *rec = reinterpret_cast<GenSurf *>(base);
+  tab.s = rec;
   for (int k = threadIdx.x; k < S; k += blockDim.x) {
     const int64_t i = (int64_t)b * S + k;
-    tab.c[k] = pb.c[i];
-    tab.t[k] = pb.t[i];
-    tab.mu[k] = pb.mu[((int64_t)b * pb.W + w) * S + k];
-    tab.k[k] = pb.k ? pb.k[i] : 0.f;
+    GenSurf r;
+    r.c = pb.c[i];
+    r.k = pb.k ? pb.k[i] : 0.f;
+    r.t = pb.t[i];
+    r.mu = pb.mu[((int64_t)b * pb.W + w) * S + k];
     const float sd = pb.sd ? pb.sd[i] : INFINITY;
-    tab.sd2[k] = __fmul_rn(sd, sd);
-    tab.live[k] = pb.live[i] != 0;
-    for (int j = 0; j < kAsphCoefs; ++j) tab.a[k * kAsphCoefs + j] = pb.a ? pb.a[i * kAsphCoefs + j] : 0.f;
+    r.sd2 = __fmul_rn(sd, sd);
+    r.index = r.index_next = 1.0f;             // (filled below)
+    r.live_bits = (pb.live[i] != 0 ? 1 : 0) | (k > 0 && pb.live[i - 1] != 0 ? 2 : 0);
+    for (int j = 0; j < kAsphCoefs; ++j) r.a[j] = pb.a ? pb.a[i * kAsphCoefs + j] : 0.f;
+    r.pad = 0.f;
+    rec[k] = r;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     float n = 1.0f;
     for (int k = 0; k < S; ++k) {
-      tab.index[k] = n;
-      n = __fdiv_rn(n, tab.mu[k]);             // like the oracle: index = index / mu
+      rec[k].index = n;
+      n = __fdiv_rn(n, rec[k].mu);             // like the oracle: index = index / mu
+      rec[k].index_next = n;
     }
-    tab.index[S] = n;
   }
   __syncthreads();
   float len = 0.f;
-  for (int k = 0; k < S; ++k) len += fabsf(tab.t[k]);
+  for (int k = 0; k < S; ++k) len += fabsf(rec[k].t);
   tab.length = len;
+  tab.index_image = rec[S - 1].index_next;
+  tab.t_last = rec[S - 1].t;
+  tab.live_last = rec[S - 1].live_bits & 1;
   return tab;
 }
 
-__device__ __forceinline__ AsphSurface gen_surface(const GenTable &tab, int k) {
+// one record, as the kernels use it
+struct GenStep {
   AsphSurface s;
-  s.c = tab.c[k];
-  s.k = tab.k[k];
-  s.t = tab.t[k];
-  s.mu = tab.mu[k];
-  s.sd2 = tab.sd2[k];
-#pragma unroll
-  for (int j = 0; j < kAsphCoefs; ++j) s.a[j] = tab.a[k * kAsphCoefs + j];
-  return s;
+  float index, index_next;
+  bool live_prev;
+};
+
+__device__ __forceinline__ GenStep gen_step(const GenTable &tab, int k) {
+  const float4 *p = reinterpret_cast<const float4 *>(tab.s + k);
+  const float4 q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3];
+  GenStep g;
+  g.s.c = q0.x;
+  g.s.k = q0.y;
+  g.s.t = q0.z;
+  g.s.mu = q0.w;
+  g.s.sd2 = q1.x;
+  g.index = q1.y;
+  g.index_next = q1.z;
+  g.live_prev = (__float_as_int(q1.w) & 2) != 0;
+  g.s.a[0] = q2.x;
+  g.s.a[1] = q2.y;
+  g.s.a[2] = q2.z;
+  g.s.a[3] = q2.w;
+  g.s.a[4] = q3.x;
+  g.s.a[5] = q3.y;
+  g.s.a[6] = q3.z;
+  return g;
 }
 
 struct TracedGen {
@@ -89,13 +120,13 @@ __device__ __noinline__ TracedGen trace_exact_gen(float x, float y, float z, flo
   float index = 1.0f, opl = 0.0f;
   for (int k = 0; k < S; ++k) {
     const float in_cx = r.cx, in_cy = r.cy;
-    exact_asph_surface(r, gen_surface(tab, k), k > 0 && tab.live[k - 1], allow_backward, ok, backward,
-                       index, opl);
+    const GenStep st = gen_step(tab, k);
+    exact_asph_surface(r, st.s, st.live_prev, allow_backward, ok, backward, index, opl);
     park<SAVE, float>(state, stride, k, r.x, r.y, in_cx, in_cy);
   }
   TracedGen out;
   out.pre = r;
-  exact_asph_image(r, tab.live[S - 1] != 0, allow_backward, ok, backward, index, opl);
+  exact_asph_image(r, tab.live_last != 0, allow_backward, ok, backward, index, opl);
   out.x = r.x;
   out.y = r.y;
   out.opl = opl;
@@ -129,16 +160,17 @@ __device__ __forceinline__ TracedGenN<V> trace_guarded_gen(V x, V y, V z, V cx, 
       const V in_cx = r.cx, in_cy = r.cy;
       V travel;
       // clip margin relative to the size of rho: computed against sd2 inside
-      fast_asph_surface(r, gen_surface(tab, k), min_cos2, travel, min_clip, V(tab.index[k]), opl);
+      const GenStep st = gen_step(tab, k);
+      fast_asph_surface(r, st.s, min_cos2, travel, min_clip, V(st.index), opl);
       park<SAVE, V>(state, stride, k, r.x, r.y, in_cx, in_cy);
-      if (k > 0 && tab.live[k - 1]) min_travel = fmin2(min_travel, travel);
+      if (st.live_prev) min_travel = fmin2(min_travel, travel);
     }
     out.pre = r;
     const V rcz = frcp(r.cz);
     const V dist = -r.z * rcz;
-    opl = ffma(V(tab.index[S]), dist, opl);
+    opl = ffma(V(tab.index_image), dist, opl);
     const V travel = fast_image(r);
-    if (tab.live[S - 1]) min_travel = fmin2(min_travel, travel);
+    if (tab.live_last) min_travel = fmin2(min_travel, travel);
     out.x = r.x;
     out.y = r.y;
     out.opl = opl;
@@ -196,7 +228,7 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 // --------------------------------------------------------------------------
 __global__ void __launch_bounds__(kFwdThreads)
 k_trace_fwd_gen(TlProblem pb, TlTraceOut out, int nchunks, int chunk_len) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   int blk = blockIdx.x;
   const int chunk = blk % nchunks; blk /= nchunks;
   const int w = blk % pb.W; blk /= pb.W;
@@ -269,7 +301,7 @@ __global__ void k_chief_rays_gen(TlProblem pb, float *ref_y) {
 template <int MODE, class V>
 __global__ void __launch_bounds__(kTraceThreads)
 k_trace_gen(TlProblem pb, AdjArgs args) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   constexpr int N = LaneCount<V>::value;
   constexpr bool kAdjoint = MODE != MODE_SPOT_EVAL;
   constexpr bool kSeeded = MODE == MODE_BWD;
@@ -401,7 +433,7 @@ k_trace_gen(TlProblem pb, AdjArgs args) {
         if (!any_live) {
           // this thread has no live ray: run the sweep on a harmless axial ray, seeded with 0
           for (int i = 0; i < S * 4; ++i) state[(size_t)i * stride] = V(0.f);
-          tr.pre = Ray<V>{V(0.f), V(0.f), V(-tab.t[S - 1]), V(0.f), V(0.f), V(1.f)};
+          tr.pre = Ray<V>{V(0.f), V(0.f), V(-tab.t_last), V(0.f), V(0.f), V(1.f)};
           tr.x = V(0.f);
           tr.y = V(0.f);
           z = V(0.f);
@@ -429,15 +461,15 @@ k_trace_gen(TlProblem pb, AdjArgs args) {
 #pragma unroll
           for (int l = 0; l < N; ++l)
             if (live[l]) lane_set(path.q, l, args.seeds.gopl[o[l]]);
-          sweep_begin_opl(sw, tr.pre, path.q, V(tab.index[S]));
+          sweep_begin_opl(sw, tr.pre, path.q, V(tab.index_image));
           path_seed = &path;
         }
 #pragma unroll 1
         for (int k = S - 1; k >= 0; --k) {
           const V *slot = state + (size_t)k * 4 * stride;
+          const GenStep st = gen_step(tab, k);
           const AsphGrad<V> g = sweep_asphere(sw, slot[0], slot[stride], slot[2 * stride],
-                                              slot[3 * stride], gen_surface(tab, k), path_seed,
-                                              V(tab.index[k]), V(tab.index[k + 1]));
+                                              slot[3 * stride], st.s, path_seed, V(st.index), V(st.index_next));
           float v[32];
 #pragma unroll
           for (int q = 0; q < kAsphParams; ++q) {
