@@ -223,6 +223,36 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
   return v[0];
 }
 
+// The same for the general-surface pass: every lane brings the kGenSlots = 22 values of its rays (padded to 24), and
+// after five exchange-and-add steps every lane holds the warp total of ONE of them.  Slot counts per lane
+// 24 -> 12 -> 6 -> 3 (padded to 4) -> 2 -> 1: 12 + 6 + 3 + 2 + 1 = 24 shuffles (the first version padded to 32
+// slots: 31 shuffles, 62 selects).  Which slot a lane ends with follows from the halves it kept:
+// slot = 12 b4 + 6 b3 + 3 b2 + (2 b1 + b0) for lane bits b4..b0, lanes with b1 = b0 = 1 hold padding.
+constexpr int kGenPad = 24;
+static_assert(kGenSlots <= kGenPad, "the butterfly carries 24 slots");
+template <int N>
+__device__ __forceinline__ void halve_and_add(float (&v)[kGenPad], bool upper, int off) {
+#pragma unroll
+  for (int i = 0; i < N / 2; ++i) {
+    const float send = upper ? v[i] : v[i + N / 2];
+    const float keep = upper ? v[i + N / 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+  }
+}
+__device__ __forceinline__ float warp_transpose_sum24(float (&v)[kGenPad], int lane) {
+  halve_and_add<24>(v, (lane & 16) != 0, 16);
+  halve_and_add<12>(v, (lane & 8) != 0, 8);
+  halve_and_add<6>(v, (lane & 4) != 0, 4);
+  v[3] = 0.f;
+  halve_and_add<4>(v, (lane & 2) != 0, 2);
+  halve_and_add<2>(v, (lane & 1) != 0, 1);
+  return v[0];
+}
+// the lane that ends up with slot j (j < 22)
+__host__ __device__ __forceinline__ int gen_lane_of_slot(int j) {
+  return 16 * (j / 12) + 8 * ((j % 12) / 6) + 4 * ((j % 6) / 3) + j % 3;
+}
+
 // --------------------------------------------------------------------------
 // forward trace, general surfaces (+ optical path length)
 // --------------------------------------------------------------------------
@@ -337,7 +367,7 @@ k_trace_gen(TlProblem pb, AdjArgs args) {
         const int k = i / kGenSlots, j = i % kGenSlots;
         double s = 0.0;
 #pragma unroll
-        for (int q = 0; q < kWarps; ++q) s += (double)acc_rows[((size_t)q * S + k) * kGenRow + j];
+        for (int q = 0; q < kWarps; ++q) s += (double)acc_rows[((size_t)q * S + k) * kGenRow + gen_lane_of_slot(j)];
         dst[i] = s;
       }
     }
@@ -470,7 +500,7 @@ k_trace_gen(TlProblem pb, AdjArgs args) {
           const GenStep st = gen_step(tab, k);
           const AsphGrad<V> g = sweep_asphere(sw, slot[0], slot[stride], slot[2 * stride],
                                               slot[3 * stride], st.s, path_seed, V(st.index), V(st.index_next));
-          float v[32];
+          float v[kGenPad];
 #pragma unroll
           for (int q = 0; q < kAsphParams; ++q) {
             v[q] = lane_dot(wgt, g.p[q], 0.f);
@@ -481,8 +511,8 @@ k_trace_gen(TlProblem pb, AdjArgs args) {
           v[kGenPar + kAsphParams] = lane_sum(g.t);
           v[kGenPar + kAsphParams + 1] = lane_sum(g.mu);
 #pragma unroll
-          for (int q = kGenSlots; q < 32; ++q) v[q] = 0.f;
-          const float total_of_lane = warp_transpose_sum(v, lane);
+          for (int q = kGenSlots; q < kGenPad; ++q) v[q] = 0.f;
+          const float total_of_lane = warp_transpose_sum24(v, lane);
           my_rows[k * kGenRow + lane] += total_of_lane;
         }
         V vx, vy, vz, vcx, vcy;
