@@ -6,8 +6,8 @@
 // incoming direction, geometric adjoint sweep), with two differences forced by the 11
 // gradients per surface (c, k, a4..a16, t, mu), twice (plain and (y - y0)-weighted):
 //   * the accumulators do not fit the register file, so every adjoint step reduces its 22
-//     values across the warp with a halving butterfly (31 shuffles; lane i ends up with the
-//     warp total of value i) and adds them to a per-warp accumulator row in shared memory;
+//     values across the warp with a halving butterfly (24 shuffles; every lane ends up with the
+//     warp total of one of them) and adds them to a per-warp accumulator row in shared memory;
 //   * the surface loops are therefore rolled (no static accumulator indices needed).
 #pragma once
 
