@@ -52,7 +52,7 @@ for name in ('c', 'k', 'a'):
     getattr(lens, name).requires_grad_(True)
 rms, _ = tracer.spot_rms(specs, lens)
 grads = torch.autograd.grad(rms[0], [lens.c, lens.k, lens.a])
-res['config3'] = {'lens': 'asphere_12 (12 even-asphere surfaces, a4..a16, 4 Newton steps)', 'rays': rays,
+res['config3'] = {'lens': 'asphere_12 (12 even-asphere surfaces, a4..a16; oracle: 4 Newton steps, fast policy: early exit)', 'rays': rays,
                   'events': rays * 12, 'fwd_bwd_ms': ms, 'events_per_s': rays * 12 / (ms * 1e-3),
                   'ok_fraction': float(whole[..., -1].sum()) / rays,
                   'two_slices_vs_whole_rel': rel(parts[0] + parts[1], whole),
