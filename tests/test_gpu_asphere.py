@@ -319,3 +319,40 @@ def test_newton_early_exit_matches_the_four_fixed_steps(f_number=5.0):
               f'exact-fp64 {err_exact / scale:.2e} (of scale {scale:.3g})')
         assert err_fast <= 1e-5 * scale, name
         assert err_fast <= max(1.5 * err_exact, 1e-6 * scale), name
+
+
+def test_four_and_two_rays_per_thread_agree(monkeypatch):
+    """The fused general-surface pass runs four rays per thread when two CTAs of it fit an SM (up to 12
+    surfaces), two otherwise (plan_gen, csrc/trace_kernels.cu); TL_GEN_LANES=2 forces the latter.  Same
+    rays, same arithmetic per ray, different summation order: moments and gradients agree to fp32
+    summation noise, on the config-3 lens and on a small clipped problem whose rows are little longer than
+    one 512-ray group."""
+    from torchoptics_b200 import prescriptions
+
+    def run_config3():
+        specs, lens = prescriptions.asphere_12(DEV)
+        for name in ('c', 't', 'k', 'a'):
+            getattr(lens, name).requires_grad_(True)
+        tracer = rt.RayTracer(mode='circular', n_rays=(64, 64), rel_fields=tuple(np.linspace(0, 1, 16).tolist()),
+                              wavelengths=('C', 'd', 'F'), default_device=DEV)
+        rms, _ = tracer.spot_rms(specs, lens)
+        return rms[0].detach(), torch.autograd.grad(rms[0], [lens.c, lens.t, lens.k, lens.a])
+
+    def run_small():
+        q = _to(_problem(n=600, clip=True), DEV, grad=('z', 'c', 't', 'mu', 'k', 'a'))
+        rms, _ = _call(ops.spot_rms, q, arith=rt._arith_code('guarded'), k=q['k'], a=q['a'], sd=q['sd'])
+        return rms[0].detach(), torch.autograd.grad(rms[0], [q[k] for k in ('z', 'c', 't', 'mu', 'k', 'a')])
+
+    for run in (run_config3, run_small):
+        rms4, g4 = run()
+        monkeypatch.setenv('TL_GEN_LANES', '2')
+        rms2, g2 = run()
+        monkeypatch.delenv('TL_GEN_LANES')
+        assert abs(rms4.item() - rms2.item()) <= 2e-6 * abs(rms2.item()), run.__name__
+        for j, (a_, b_) in enumerate(zip(g4, g2)):
+            a_, b_ = a_.cpu().numpy(), b_.cpu().numpy()
+            if j == len(g4) - 1:          # the asphere coefficients: a4 ... a16 live on very different scales
+                for i in range(7):
+                    assert _rel(a_[..., i], b_[..., i]) <= 2e-5, (run.__name__, 'a', i)
+            else:
+                assert _rel(a_, b_) <= 2e-5, (run.__name__, j)

@@ -2027,13 +2027,23 @@ int plan_gen(const TlProblem &pb, int want_grad, GenPlan &pl, bool seeded = fals
   DeviceInfo info;
   int rc = device_info(info);
   if (rc) return rc;
-  pl.lanes = want_grad ? 2 : 4;
-  pl.kernel = seeded ? (AdjKernelPtr)k_trace_gen<MODE_BWD, f2>
-              : want_grad ? (AdjKernelPtr)k_trace_gen<MODE_SPOT_GRAD, f2>
-                          : (AdjKernelPtr)k_trace_gen<MODE_SPOT_EVAL, f4>;
-  pl.n_acc = n_acc_gen(pb.S, want_grad);
+  // Rays per thread.  The forward-only sweep takes four; so does the fused pass with gradients when two CTAs of
+  // it still fit an SM's shared memory (parked state 8 KB per surface and CTA: up to 12 surfaces) -- four rays
+  // share one 24-slot butterfly and one accumulator update per adjoint step: 0.7313 -> 0.6832 ms on the config-3
+  // lens, at 221 registers and 8 warps per SM against 125 registers and 16 warps for two rays per thread.
+  // TL_GEN_LANES=2 forces the two-ray variant (A/B runs, tests).
   const size_t table = ((gen_table_floats(pb.S) + 3) & ~(size_t)3) * sizeof(float);
   const size_t rows = want_grad ? (size_t)(kTraceThreads / 32) * pb.S * kGenRow * sizeof(float) : 0;
+  const size_t state4 = (size_t)4 * pb.S * kTraceThreads * 4 * sizeof(float);
+  const char *env_lanes = getenv("TL_GEN_LANES");
+  const bool four = want_grad && !seeded && !(env_lanes && atoi(env_lanes) == 2) &&
+                    2 * (table + rows + state4 + 16 + 1024) <= (size_t)227 * 1024;
+  pl.lanes = (!want_grad || four) ? 4 : 2;
+  pl.kernel = seeded ? (AdjKernelPtr)k_trace_gen<MODE_BWD, f2>
+              : !want_grad ? (AdjKernelPtr)k_trace_gen<MODE_SPOT_EVAL, f4>
+              : four ? (AdjKernelPtr)k_trace_gen<MODE_SPOT_GRAD, f4>
+                     : (AdjKernelPtr)k_trace_gen<MODE_SPOT_GRAD, f2>;
+  pl.n_acc = n_acc_gen(pb.S, want_grad);
   const size_t state = want_grad ? (size_t)4 * pb.S * kTraceThreads * pl.lanes * sizeof(float) : 0;
   pl.smem = table + rows + state + 16;
   if (pl.smem > 227 * 1024) return fail(TL_ERR_INVALID, "surface count needs too much shared memory%s");
