@@ -191,10 +191,11 @@ template <class T>
 TL_HD bool newton_settled(T, T) { return false; }                   // (lane types without an early exit)
 TL_HD bool newton_settled(float step, float tau) { return fabsf(step) <= newton_exit<float>() * fabsf(tau); }
 TL_HD bool newton_settled(double step, double tau) { return fabs(step) <= newton_exit<double>() * fabs(tau); }
+// (`&`, not `&&`: one chain of predicated compares and ONE branch per step instead of a branch per ray)
 TL_HD bool newton_settled(f2 step, f2 tau) {
-  return newton_settled(step.v.x, tau.v.x) && newton_settled(step.v.y, tau.v.y);
+  return newton_settled(step.v.x, tau.v.x) & newton_settled(step.v.y, tau.v.y);
 }
-TL_HD bool newton_settled(f4 step, f4 tau) { return newton_settled(step.a, tau.a) && newton_settled(step.b, tau.b); }
+TL_HD bool newton_settled(f4 step, f4 tau) { return newton_settled(step.a, tau.a) & newton_settled(step.b, tau.b); }
 
 // One general surface, fast policy.  Returns through r (state behind the surface, z shifted),
 // hit point in (hit_x, hit_y); tracks predicate margins like fast_surface.
