@@ -168,7 +168,7 @@ TL_HD AsphEval<T> asph_eval(const AsphSurfaceT<S> &s, T rho) {
   }
   e.sag = ffma((c * rho), e.inv1r, (p * rho) * rho);
   e.slope = ffma(T(S(0.5) * s.c), e.rs, dp * rho);
-  if (CURV) e.curv = ffma(T(S(0.25)) * (kc2 * c), (e.rs * e.rs) * e.rs, ddp);
+  if (CURV) e.curv = ffma(T(S(0.25) * ((S(1) + s.k) * s.c * s.c) * s.c), (e.rs * e.rs) * e.rs, ddp);   // (uniform factor: scalar)
   else e.curv = T(0);
   return e;
 }
@@ -321,16 +321,18 @@ TL_HD AsphGrad<T> sweep_asphere(Sweep<T> &s, T hx, T hy, T dx, T dy, const AsphS
   // parameters: g_theta = sd * ds/dtheta - 2 qq * ds'/dtheta
   const T m2q = T(-2) * qq;
   const T rs3 = (e.rs * e.rs) * e.rs;
-  const T c3 = (c * c) * c;
+  const S c3s = (sf.c * sf.c) * sf.c;                    // (uniform over the warp: scalar arithmetic, broadcast operands)
+  const T c3q(S(0.25) * c3s), c3h(S(0.5) * c3s);
   g.p[0] = ffma(m2q * T(S(0.5)), rs3, sd * ((rho * e.rs) * e.inv1r));
-  g.p[1] = ffma(m2q * T(S(0.25)), (c3 * rho) * rs3,
-                sd * (T(S(0.5)) * c3 * (rho * rho) * e.rs * (e.inv1r * e.inv1r)));
-  T pw = rho;                                            // rho^(i-1), i = 2..8
+  g.p[1] = ffma(m2q, (c3q * rho) * rs3, sd * (c3h * (rho * rho) * e.rs * (e.inv1r * e.inv1r)));
+  // a_i (i = 2..8): sd rho^i - 2 qq i rho^(i-1) = rho^(i-1) (sd rho + i m2q)
+  const T sd_rho = sd * rho;
+  T pw = rho;                                            // rho^(i-1)
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
   for (int i = 2; i <= 8; ++i) {
-    g.p[i] = pw * ffma(sd, rho, m2q * T(S(i)));
+    g.p[i] = pw * ffma(m2q, T(S(i)), sd_rho);
     pw = pw * rho;
   }
   s.gd = gdi;
