@@ -557,6 +557,35 @@ def main():
         except Exception as exc:
             print(f'[bench] batched-lens timing failed: {exc}', file=sys.stderr)
 
+    # ---- BASELINE.json configs 3 / 5: the 12-surface even-asphere lens through the general-surface fused pass
+    # (k_trace_gen: Newton sag solve with early exit, 11 gradients per surface), same fields / wavelengths / pupil
+    # as the headline workload; rank 0 at N = 1 only (tools/full_size_configs.py has the 67 M-ray size) ----
+    asphere_row = None
+    if world == 1:
+        note('asphere fused pass')
+        try:
+            from torchoptics_b200 import prescriptions
+            a_specs, a_lens = prescriptions.asphere_12(dev)
+            a_args = [a.detach() for a in tracer._ray_set(a_specs, a_lens)]
+            a_ext = {k: v.detach() for k, v in tracer._extension_tables(a_lens).items() if v is not None}
+            a_events = rays_total * int(a_args[6].shape[-1])
+            a_reps = max(5, min(args.steps, 20))
+            grad_ms = timed_graph(lambda: ops.spot_moments(*a_args, want_grad=True, **a_ext), a_reps)
+            eval_ms = timed_graph(lambda: ops.spot_moments(*a_args, want_grad=False, **a_ext), a_reps)
+            a_mom, _ = ops.spot_moments(*a_args, want_grad=False, **a_ext)
+            asphere_row = {'what': 'asphere_12 (12 even-asphere surfaces, a4..a16), fused spot pass of the general-surface '
+                                   'kernel k_trace_gen, L2 flushed before every launch; oracle: 4 fixed Newton steps, fast '
+                                   'policy: early exit (2 per event on this lens)',
+                           'rays': rays_total, 'events': a_events,
+                           'fwd_bwd': {'value': a_events / (grad_ms * 1e-3), 'unit': 'asphere events/s', 'ms': grad_ms,
+                                       'frac_fp32_peak_at_oracle_566_flop': a_events * 566 / (grad_ms * 1e-3) / 1e12 / peak_tflops,
+                                       'frac_fp32_peak_at_executed_505_flop': a_events * 505 / (grad_ms * 1e-3) / 1e12 / peak_tflops},
+                           'forward_sweep': {'value': a_events / (eval_ms * 1e-3), 'unit': 'asphere events/s', 'ms': eval_ms},
+                           'ok_fraction': float(a_mom[..., -1].sum()) / rays_total}
+            del a_args, a_ext, a_mom
+        except Exception as exc:
+            print(f'[bench] asphere timing failed: {exc}', file=sys.stderr)
+
     if graphed is not None:
         h2d, d2h = graphed.h2d_bytes, graphed.d2h_bytes
     else:
@@ -593,7 +622,8 @@ def main():
                         'drop_in_api': 'the reference\'s own sequence, unchanged: trace_rays (materialises [B,F,P,W]) -> compute_rms2d -> backward; compute_rms2d recognises untouched trace outputs and runs the fused pass on their inputs'},
                 'step_ms': step_stats, 'sustained': sustained,
                 'gpu_launches': launches_per_step * args.steps,
-                'roofline': roofline, 'forward': forward, 'penalty': penalty_row, 'batched_lenses': batched_row}
+                'roofline': roofline, 'forward': forward, 'penalty': penalty_row, 'batched_lenses': batched_row,
+                'asphere': asphere_row}
         if value < 0.97 * e2e_value:      # device-timed slower than host-timed end to end: timed wait (rank skew)
             line['warning'] = ('value < e2e.value: the device-timed steps include waiting for the slowest rank '
                                '(see step_ms min / median / max)')
