@@ -17,7 +17,8 @@ constexpr int kNewton = 4;        // fixed iteration count (oracle: N_NEWTON)
 //   executed     fast_asph_surface 26 (start) + 4 * 57 (iterations) + 94 (hit, normal, Snell, margins) = 348,
 //                19 MUFU; sweep_asphere 238 + 33 (sums) = 271, 8 MUFU
 //                (the fast policy leaves the loop early, newton_settled below: 2 iterations per event on the
-//                config-3 lens, 348 -> ~234 forward; the exact policy always runs the four)
+//                config-3 lens, 348 -> ~234 forward, less where the evaluation behind the loop is skipped too,
+//                newton_is_fresh; the exact policy always runs the four)
 constexpr int kAsphParams = 2 + kAsphCoefs;   // c, k, a4..a16
 
 template <class S>
@@ -196,6 +197,21 @@ TL_HD bool newton_settled(f2 step, f2 tau) {
   return newton_settled(step.v.x, tau.v.x) & newton_settled(step.v.y, tau.v.y);
 }
 TL_HD bool newton_settled(f4 step, f4 tau) { return newton_settled(step.a, tau.a) & newton_settled(step.b, tau.b); }
+// ... and was that last step so small (<= 2e-6 |tau|; fp64: 1e-11) that the sag and slope just evaluated in front
+// of it are those of the new point to working precision?  Then the evaluation at the hit point that follows the
+// loop is skipped too: a surface costs as many evaluations as Newton steps (two on an aspheric surface of the
+// config-3 lens, one on a spherical one) instead of one more.  Steps between the two bounds -- or rounding noise
+// above the small one -- settle the loop and are followed by the evaluation as before: no cliff.
+template <class T> TL_HD T newton_fresh() { return T(2e-6f); }
+template <> TL_HD double newton_fresh<double>() { return 1e-11; }
+template <class T>
+TL_HD bool newton_is_fresh(T, T) { return false; }
+TL_HD bool newton_is_fresh(float step, float tau) { return fabsf(step) <= newton_fresh<float>() * fabsf(tau); }
+TL_HD bool newton_is_fresh(double step, double tau) { return fabs(step) <= newton_fresh<double>() * fabs(tau); }
+TL_HD bool newton_is_fresh(f2 step, f2 tau) {
+  return newton_is_fresh(step.v.x, tau.v.x) & newton_is_fresh(step.v.y, tau.v.y);
+}
+TL_HD bool newton_is_fresh(f4 step, f4 tau) { return newton_is_fresh(step.a, tau.a) & newton_is_fresh(step.b, tau.b); }
 
 // One general surface, fast policy.  Returns through r (state behind the surface, z shifted),
 // hit point in (hit_x, hit_y); tracks predicate margins like fast_surface.
@@ -211,24 +227,30 @@ TL_HD void fast_asph_surface(Ray<T> &r, const AsphSurfaceT<S> &s, T &min_cos2, T
   const T q = ffma(-c, tmp, r.cz * r.cz);
   const T ci = q * frsqrt(q);
   T tau = ffma(tmp, frcp(r.cz + ci), -ne);
+  AsphEval<T> e;
+  bool fresh = false;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
   for (int it = 0; it < kNewton; ++it) {
     const T hx = ffma(tau, r.cx, r.x), hy = ffma(tau, r.cy, r.y);
-    const AsphEval<T> e = asph_eval<false>(s, ffma(hy, hy, hx * hx));
+    e = asph_eval<false>(s, ffma(hy, hy, hx * hx));
     const T f = ffma(tau, r.cz, r.z) - e.sag;
     const T fp = ffma(-(e.slope + e.slope), ffma(hy, r.cy, hx * r.cx), r.cz);
     const T rfp = frcp(fp);
+    const T step = f * rfp;
     tau = ffma(-f, rfp, tau);
-    if (newton_settled(f * rfp, tau)) break;
+    if (newton_settled(step, tau)) {
+      fresh = newton_is_fresh(step, tau);
+      break;
+    }
   }
   travel = tau * r.cz;
   r.x = ffma(tau, r.cx, r.x);
   r.y = ffma(tau, r.cy, r.y);
   r.z = r.z + travel;
   const T rho = ffma(r.y, r.y, r.x * r.x);
-  const AsphEval<T> e = asph_eval<false>(s, rho);
+  if (!fresh) e = asph_eval<false>(s, rho);
   opl = ffma(index, tau, opl);
   min_clip = fmin2(min_clip, T(s.sd2) - rho);
   // unit normal, vector Snell
