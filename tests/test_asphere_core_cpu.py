@@ -73,3 +73,61 @@ def test_fast_policy_and_adjoint_fp64():
             b_ = b_.numpy().reshape(np.shape(a_))
             err = np.abs(a_ - b_).max() / max(np.abs(b_).max(), 1e-3)
             assert err < 1e-8, (name, err)
+
+
+def test_fast_policy_fp32_with_early_exit_on_the_config3_lens(tmp_path):
+    """The fp32 fast policy as the kernels run it -- Newton loop left once a step is <= 1e-3 |tau|, hit-point
+    evaluation skipped after a step <= 2e-6 |tau| (csrc/trace_core_asph.cuh: newton_settled, newton_is_fresh) --
+    on the config-3 lens (eight aspheric surfaces, four flat ones), one wavelength at a time: within the north-star
+    1e-5 of the fp64 oracle (four fixed steps), and within 1e-6 of scale (a few ulp of the image height; a tenth of the budget) of THE SAME header compiled with the exit
+    disabled (-DTL_NEWTON_EXIT=0: four steps and the evaluation, always) -- what the exit itself changes.  The
+    distances are printed next to the fp32 oracle's own."""
+    import ctypes
+    import os
+    import subprocess
+    from torchoptics_b200 import prescriptions, ray_tracing_lite as rt
+    here = os.path.dirname(os.path.abspath(hc.__file__))
+    fixed_so = str(tmp_path / 'hostcore_fixed4.so')
+    subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-fno-fast-math', '-std=c++17', '-shared', '-fPIC',
+                           '-DTL_NEWTON_EXIT=0.0f', '-x', 'c++', os.path.join(here, 'hostcore.cpp'), '-o', fixed_so])
+    specs, lens = prescriptions.asphere_12('cpu')
+    tracer = rt.RayTracer(mode='circular', n_rays=(24, 24), rel_fields=(0.0, 0.35, 0.7, 1.0),
+                          wavelengths=('C', 'd', 'F'), default_device='cpu')
+    args = [a_.detach() for a_ in tracer._ray_set(specs, lens)]
+    ext = {k: v.detach() for k, v in tracer._extension_tables(lens).items() if v is not None}
+    ref32 = gen.trace(*args, **ext)
+    ref64 = gen.trace(*[a_.double() if a_.is_floating_point() else a_ for a_ in args],
+                      **{k: (v.double() if v.is_floating_point() else v) for k, v in ext.items()})
+    assert bool(ref64[4].all()) and bool(ref32[4].all())
+    x, y, z, cx, cy, c, t, mu, mask = args
+    F, W, S, P = cy.shape[1], mu.shape[3], c.shape[-1], x.shape[2]
+    xy_scale = max(float(ref64[0].abs().max()), float(ref64[1].abs().max()))
+
+    def run(w):
+        rays = [torch.broadcast_to(v, (1, F, P, 1)).reshape(-1).numpy().astype(np.float32) for v in (x, y, z, cx, cy)]
+        return hc.asph_fast(np.float32, *rays, c.reshape(S).numpy(), ext['k'].reshape(S).numpy(),
+                            ext['a'].reshape(S, 7).numpy(), t.reshape(S).numpy(), mu[0, 0, 0, w].numpy(),
+                            np.full(S, np.inf))
+
+    hc.lib()
+    shipped = hc._lib
+    worst = {}
+    for w in range(W):
+        r = run(w)
+        try:
+            hc._lib = ctypes.CDLL(fixed_so)
+            r4 = run(w)
+        finally:
+            hc._lib = shipped
+        assert float(r['min_cos2'].min()) > 1e-3          # every ray clear of the guard bands: no exact re-trace
+        for key, j in (('x', 0), ('y', 1), ('cx', 2), ('cy', 3), ('opl', 6)):
+            want64 = ref64[j][0, :, :, w].numpy().ravel()
+            want32 = ref32[j][0, :, :, w].numpy().ravel().astype(np.float64)
+            scale = 1.0 if key in ('cx', 'cy') else (xy_scale if key in ('x', 'y') else float(np.abs(want64).max()))
+            err_fast = float(np.abs(r[key].astype(np.float64) - want64).max()) / scale
+            err_ref = float(np.abs(want32 - want64).max()) / scale
+            d_exit = float(np.abs(r[key].astype(np.float64) - r4[key].astype(np.float64)).max()) / scale
+            worst[key] = tuple(max(p_, q_) for p_, q_ in zip(worst.get(key, (0.0, 0.0, 0.0)), (err_fast, err_ref, d_exit)))
+            assert err_fast <= 1e-5, (key, w, err_fast)
+            assert d_exit <= 1e-6, (key, w, d_exit)
+    print({k: 'fast-fp64 %.1e, fp32 oracle-fp64 %.1e, exit on/off %.1e' % v for k, v in worst.items()})
