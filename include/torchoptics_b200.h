@@ -80,7 +80,10 @@ typedef struct TlProblem {
                                   (relative pupil coordinates * EPD/2, scale_to_epd rtl:497-507) */
   /* EXTENSION surfaces (no reference behaviour; defined by oracle/asphere_oracle.py).  All three
    * NULL = the reference's spherical lens.  Any non-NULL selects the general-surface kernels:
-   *   z = c rho / (1 + sqrt(1 - (1+k) c^2 rho)) + sum_i a_i rho^i,  rho = x^2 + y^2, i = 2..8 */
+   *   z = c rho / (1 + sqrt(1 - (1+k) c^2 rho)) + sum_i a_i rho^i,  rho = x^2 + y^2, i = 2..8
+   * The intersection is the oracle's: base-sphere closed form, then Newton on F(tau) = z + tau cz - s(rho) --
+   * four fixed steps under TL_ARITH_EXACT (bit-identical to the oracle); under TL_ARITH_GUARDED the loop is
+   * left once a step is <= 1e-3 |tau| (the remaining ones would move tau by less than fp32 resolution). */
   const float *k;              /* [B,S]   conic constants (NULL = 0)                */
   const float *a;              /* [B,S,7] a4, a6, ..., a16 (NULL = 0)               */
   const float *sd;             /* [B,S]   clear semi-diameters (NULL = +inf)        */
